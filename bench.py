@@ -1,0 +1,264 @@
+#!/usr/bin/env python3
+"""bench.py — 4K frames/sec of the fisheye + rolling-shutter warp (BASELINE.json `metric`), one JSON line.
+
+Workload (N=1 and per rank for N>1): BASELINE config 2 — 3840x2160 RGBA8, opencv_fisheye, rolling shutter ON
+(2160 per-scanline matrices from a 240 Hz synthetic gyro), bilinear, synthetic high-entropy frames.
+A "step" is one batch of FRAMES_PER_STEP frames, each with its own timestamp (distinct matrices) and drawn from a
+ring of input frames larger than L2, so no launch finds its source in cache.
+
+  value     frames/s with frames + tables already resident in HBM (gf_cuda_undistort_image_dev), CUDA-event timed,
+            max over ranks
+  e2e       frames/s through the reference-facing call gf_cuda_undistort_image with HOST (pinned) buffers:
+            H2D of the frame + tables and D2H of the result inside the timed region
+  roofline  algorithmic bytes per launch (in + out + rows*56 + 368) / mean launch time, vs measured HBM peak
+  cpu_baseline  the CPU oracle (C port of the reference CPU path) on this box's host cores, bounded sample
+
+`--impl reference` times the reference CPU path instead (oracle port; the Rust original cannot be built: no rustc).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+W, H = 3840, 2160
+PIX, LENS = "RGBA8", "opencv_fisheye"
+FRAMES_PER_STEP = 32
+RING = 8                 # 8 x 33.2 MB input frames = 265 MB > 126 MB L2
+N_TIMESTAMPS = 32        # distinct matrix tables
+METRIC = "4K frames/sec (fisheye+RS warp)"
+WORKLOAD = "cfg2: 3840x2160 RGBA8, opencv_fisheye + rolling-shutter ON (2160 matrices), 240 Hz synthetic gyro, bilinear"
+
+
+def algorithmic_bytes(p, rows, mesh_len=0):
+    """sum_planes(in_w*in_h*bpp + out_w*out_h*bpp) + rows*56 + 368 + 4*mesh_len."""
+    return p.width * p.height * p.bytes_per_pixel + p.output_width * p.output_height * p.bytes_per_pixel + rows * 56 + 368 + 4 * mesh_len
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try: self.proc.wait(timeout=2)
+        except Exception: pass
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7: continue
+            try: sm.append(float(f[0])); mx = float(f[1])
+            except ValueError: continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"): reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_tables(n):
+    from gyroflow_b200 import synth
+    p = synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS)
+    org, sm = synth.synthetic_gyro(4.0)
+    mats = np.stack([synth.frame_matrices(p, org, sm, 500.0 + i * (1000.0 / 60.0)) for i in range(n)])   # 60 fps timestamps
+    p.matrix_count = mats.shape[1]
+    return p, mats.astype(np.float32)
+
+
+def cpu_reference_fps(p, mats, frames, threads):
+    """The reference's CPU path (oracle port) on `frames` full 4K frames, all host threads."""
+    from gyroflow_b200 import synth
+    from tests import oracle_lib
+    src = synth.synthetic_frame(W, H, PIX, stride=p.stride)
+    dst = np.zeros((H, p.output_stride), np.uint8)
+    oracle_lib.undistort_image(src, dst, p, PIX, LENS, None, mats[0], None, threads)          # warm-up (page faults, thread start)
+    t0 = time.perf_counter()
+    for i in range(frames):
+        rc = oracle_lib.undistort_image(src, dst, p, PIX, LENS, None, mats[i % len(mats)], None, threads)
+        assert rc == 0
+    return frames / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests import oracle_lib
+    cores = oracle_lib.load().gf_oracle_online_cpus()
+    p, mats = make_tables(4)
+    from gyroflow_b200 import synth
+    src = synth.synthetic_frame(W, H, PIX, stride=p.stride)
+    dst = np.zeros((H, p.output_stride), np.uint8)
+    step = lambda i: oracle_lib.undistort_image(src, dst, p, PIX, LENS, None, mats[i % len(mats)], None, cores)
+    for i in range(args.warmup): step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps): assert step(i) == 0
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d full 4K frames, 1 frame per step, C port of cpu_undistort.rs (Rust original unbuildable: no rustc)" % args.steps},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import gyroflow_b200 as g
+    from gyroflow_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = g.load_library()
+    assert lib.gf_cuda_device_count() > local, "no CUDA device for this rank (there is no CPU fallback)"
+
+    # ---- tables: rank 0 builds them, NCCL broadcasts them (the only collective of the path) -------------------
+    p, mats_np = make_tables(N_TIMESTAMPS) if rank == 0 else (synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS), None)
+    rows = H
+    mats = torch.empty((N_TIMESTAMPS, rows, 14), dtype=torch.float32, device=dev)
+    if rank == 0:
+        mats.copy_(torch.from_numpy(mats_np))
+    if world > 1:
+        dist.broadcast(mats, src=0)
+    p.matrix_count = rows
+
+    # ---- device-resident frames -----------------------------------------------------------------------------
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    frames_in = [torch.randint(0, 256, (H, p.stride), dtype=torch.uint8, device=dev, generator=gen) for _ in range(RING)]
+    frames_out = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(RING)]
+    def dbufs(i):
+        a, b = frames_in[i % RING], frames_out[i % RING]
+        return g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
+                         g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel()))
+    ctx = g.CudaWrapper.new(p, PIX, LENS, None, dbufs(0), device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+    all_bufs = [dbufs(i) for i in range(RING)]
+
+    def step(s):
+        for j in range(FRAMES_PER_STEP):
+            i = s * FRAMES_PER_STEP + j
+            ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows, stream=stream)
+
+    for s in range(args.warmup):
+        step(s)
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for s in range(args.steps):
+        ev[s][0].record()
+        step(s)
+        ev[s][1].record()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clk = clocks.stop()
+    launches = ctx.launch_count - l0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    fps = world * FRAMES_PER_STEP / (ms_per_step / 1e3)
+
+    # ---- e2e: host (pinned) buffers through gf_cuda_undistort_image, copies inside the timed region ------------
+    hin = [torch.randint(0, 256, (H, p.stride), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    hout = [torch.zeros((H, p.output_stride), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    def hbufs(i):
+        a, b = hin[i % 2].numpy(), hout[i % 2].numpy()
+        return g.Buffers(g.BufferDescription((W, H, p.stride), a), g.BufferDescription((W, H, p.output_stride), b))
+    hctx = g.CudaWrapper.new(p, PIX, LENS, None, hbufs(0), device=local)
+    mats_host = mats.cpu().numpy()
+    e2e_frames = max(8, min(64, FRAMES_PER_STEP))
+    itms = [g.FrameTransform(matrices=mats_host[i % N_TIMESTAMPS], kernel_params=p) for i in range(N_TIMESTAMPS)]
+    hb = [hbufs(0), hbufs(1)]
+    for i in range(3): hctx.undistort_image(hb[i % 2], itms[i % N_TIMESTAMPS])
+    if world > 1: dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_frames): hctx.undistort_image(hb[i % 2], itms[i % N_TIMESTAMPS])
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_fps = world * e2e_frames / float(te.item())
+    h2d = int(hin[0].numel() + rows * 56 + 368)
+    d2h = int(W * 4 * H)
+
+    if rank == 0:
+        peaks = {}
+        try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception: pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        abytes = algorithmic_bytes(p, rows)
+        launch_ms = total_ms / max(launches, 1)
+        achieved = abytes / (launch_ms / 1e3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            from tests import oracle_lib
+            cores = oracle_lib.load().gf_oracle_online_cpus()
+            cfps = cpu_reference_fps(p, mats_host, 4, cores)
+            cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "4 full 4K frames of the same workload (C port of cpu_undistort.rs, row-parallel over all host threads)"}
+        out = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
+                       "l2_policy": "inputs larger than L2: %d-frame ring of 33.2 MB inputs (%d MB) + %d distinct matrix tables" % (RING, RING * H * p.stride // 1000000, N_TIMESTAMPS),
+                       "parallelism": "frame-sharded x%d, NCCL broadcast of tables only" % world},
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "per frame: pinned host frame + tables H2D, kernel, D2H, sync; %d frames timed by wall clock" % e2e_frames},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": abytes, "launch_ms": launch_ms, "peak_source": peak_src,
+                         "note": "kernel is FP32-issue bound in bit-exact (-fmad=false) mode; see DESIGN.md"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    hctx.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

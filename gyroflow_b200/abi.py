@@ -1,0 +1,133 @@
+"""ctypes mirror of include/gyroflow_cuda.h and loader of the product library.
+
+The library is the hand-written sm_100a backend (gyroflow_b200/libgyroflow_cuda.so, built in-tree by
+`make -C gyroflow_b200/csrc` / `__graft_entry__.build()`).  Loading fails loudly when it is missing:
+there is no Python, PyTorch or CPU fallback for the warp.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgyroflow_cuda.so")
+
+MATRIX_STRIDE = 14
+MESH_MAX_LEN = 839
+KERNEL_PARAMS_SIZE = 368
+
+
+class KernelParams(C.Structure):
+    """`#[repr(C, packed(4))] struct KernelParams` — src/core/stabilization/mod.rs:101-150 (368 bytes)."""
+    _pack_ = 4
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32),
+        ("output_width", C.c_int32), ("output_height", C.c_int32), ("output_stride", C.c_int32),
+        ("matrix_count", C.c_int32), ("interpolation", C.c_int32), ("background_mode", C.c_int32),
+        ("flags", C.c_int32), ("bytes_per_pixel", C.c_int32), ("pix_element_count", C.c_int32),
+        ("background", C.c_float * 4), ("f", C.c_float * 2), ("c", C.c_float * 2), ("k", C.c_float * 12),
+        ("fov", C.c_float), ("r_limit", C.c_float), ("lens_correction_amount", C.c_float),
+        ("input_vertical_stretch", C.c_float), ("input_horizontal_stretch", C.c_float),
+        ("background_margin", C.c_float), ("background_margin_feather", C.c_float), ("canvas_scale", C.c_float),
+        ("input_rotation", C.c_float), ("output_rotation", C.c_float),
+        ("translation2d", C.c_float * 2), ("translation3d", C.c_float * 4),
+        ("source_rect", C.c_int32 * 4), ("output_rect", C.c_int32 * 4),
+        ("digital_lens_params", C.c_float * 16), ("safe_area_rect", C.c_float * 4),
+        ("max_pixel_value", C.c_float), ("distortion_model", C.c_int32), ("digital_lens", C.c_int32),
+        ("pixel_value_limit", C.c_float), ("light_refraction_coefficient", C.c_float),
+        ("plane_index", C.c_int32), ("reserved1", C.c_float), ("reserved2", C.c_float),
+        ("ewa_coeffs_p", C.c_float * 4), ("ewa_coeffs_q", C.c_float * 4),
+    ]
+
+    def copy(self):
+        o = KernelParams()
+        C.memmove(C.byref(o), C.byref(self), C.sizeof(KernelParams))
+        return o
+
+
+assert C.sizeof(KernelParams) == KERNEL_PARAMS_SIZE
+
+
+class BufferDesc(C.Structure):
+    """gf_buffer_desc <- BufferDescription, src/core/gpu/mod.rs:17-24."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32),
+        ("has_rect", C.c_int32), ("rect", C.c_int32 * 4),
+        ("has_rotation", C.c_int32), ("rotation", C.c_float),
+        ("kind", C.c_int32), ("_pad", C.c_int32),
+        ("ptr", C.c_void_p), ("len", C.c_size_t),
+    ]
+
+
+# KernelParamsFlags — stabilization/mod.rs:85-98
+FLAG_FIX_COLOR_RANGE, FLAG_HAS_DIGITAL_LENS, FLAG_FILL_WITH_BACKGROUND, FLAG_DRAWING_ENABLED = 1, 2, 4, 8
+FLAG_HORIZONTAL_RS, FLAG_HAS_SOURCE_RECT, FLAG_HAS_OUTPUT_RECT, FLAG_FRAMEBUFFER_INVERTED = 16, 32, 64, 128
+FLAG_HAS_IBIS_DATA, FLAG_HAS_MESH_DATA, FLAG_HAS_FPD_DATA, FLAG_ANY_UNDERWATER = 256, 512, 1024, 2048
+
+INTERP = {"Bilinear": 2, "Bicubic": 4, "Lanczos4": 8, "EWA: RobidouxSharp": 10, "EWA: Robidoux": 11,
+          "EWA: Mitchell": 12, "EWA: Catmull-Rom": 13}
+
+LENS = {"none": 0, "opencv_fisheye": 1, "opencv_standard": 2, "poly3": 3, "poly5": 4, "ptlens": 5, "insta360": 6,
+        "sony": 7, "generic_polynomial": 8, "gopro": 9, "gopro_superview": 10, "gopro_hyperview": 11,
+        "gopro_warp": 12, "digital_stretch": 13, "gopro6_superview": 14}
+
+# name -> (id, channel count, numpy scalar dtype string)
+PIXEL_TYPES = {
+    "Luma8": (0, 1, "u1"), "Luma16": (1, 1, "u2"), "RGB8": (2, 3, "u1"), "RGBA8": (3, 4, "u1"), "BGRA8": (4, 4, "u1"),
+    "RGB16": (5, 3, "u2"), "RGBA16": (6, 4, "u2"), "AYUV16": (7, 4, "u2"), "RGBAf": (8, 4, "f4"), "RGBAf16": (9, 4, "f2"),
+    "R32f": (10, 1, "f4"), "UV8": (11, 2, "u1"), "UV16": (12, 2, "u2"),
+}
+
+BUF_NONE, BUF_HOST, BUF_DEVICE = 0, 1, 2
+
+ERRORS = {0: "Ok", -1: "BadParams", -2: "SizeTooSmall", -3: "SizeMismatch", -4: "InvalidStride",
+          -5: "UnsupportedCombo", -6: "CudaError", -7: "BufferTooSmall", -8: "NoStabilizationData"}
+
+# every symbol include/gyroflow_cuda.h declares: (name, restype, argtypes)
+_P = C.POINTER
+EXPORTS = [
+    ("gf_cuda_device_count", C.c_int, []),
+    ("gf_cuda_device_name", C.c_int, [C.c_int, C.c_char_p, C.c_size_t]),
+    ("gf_cuda_supports", C.c_int, [_P(BufferDesc), _P(BufferDesc)]),
+    ("gf_cuda_version", C.c_char_p, []),
+    ("gf_lens_from_name", C.c_int, [C.c_char_p]),
+    ("gf_lens_name", C.c_char_p, [C.c_int]),
+    ("gf_pixel_bytes", C.c_int, [C.c_int]),
+    ("gf_combo_supported", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("gf_cuda_create", C.c_int, [_P(C.c_void_p), C.c_int, _P(KernelParams), C.c_int, C.c_int, C.c_int,
+                                 _P(BufferDesc), _P(BufferDesc), C.c_size_t]),
+    ("gf_cuda_destroy", None, [C.c_void_p]),
+    ("gf_cuda_undistort_image", C.c_int, [C.c_void_p, _P(BufferDesc), _P(BufferDesc), _P(KernelParams),
+                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("gf_cuda_undistort_image_dev", C.c_int, [C.c_void_p, _P(BufferDesc), _P(BufferDesc), _P(KernelParams),
+                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("gf_cuda_synchronize", C.c_int, [C.c_void_p]),
+    ("gf_cuda_last_error", C.c_char_p, [C.c_void_p]),
+    ("gf_cuda_backend_name", C.c_char_p, []),
+    ("gf_cuda_launch_count", C.c_uint64, [C.c_void_p]),
+]
+
+_lib = None
+
+
+class BackendMissing(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the product library and bind every declared entry point.  Raises BackendMissing if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise BackendMissing(
+            "%s is missing: build it with `make -C gyroflow_b200/csrc` (or __graft_entry__.build()). "
+            "There is no CPU fallback for the warp." % p)
+    lib = C.CDLL(p)
+    for name, restype, argtypes in EXPORTS:
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib

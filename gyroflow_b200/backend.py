@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference's backend-wrapper convention, over the C ABI.
+
+Names follow the reference so the parity tests read like its call sites:
+
+  BufferDescription / Buffers      src/core/gpu/mod.rs:17-29
+  FrameTransform                   src/core/stabilization/frame_transform.rs:11-19
+  CudaWrapper.new / undistort_image   <- OclWrapper::new / undistort_image  src/core/gpu/opencl.rs:178,330
+  GyroflowCoreError                src/core/lib.rs:2098-2141
+
+This module only marshals arguments; all pixel work happens in libgyroflow_cuda.so.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import abi
+
+
+class GyroflowCoreError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s: %s" % (abi.ERRORS.get(code, str(code)), message))
+        self.code = code
+        self.kind = abi.ERRORS.get(code, "Unknown")
+
+
+@dataclass
+class BufferDescription:
+    """size = (width, height, stride_bytes); data is a C-contiguous uint8 numpy array (BufferSource::Cpu) or an
+    integer device pointer with `length` bytes (BufferSource::CUDABuffer)."""
+    size: Tuple[int, int, int]
+    data: object = None
+    rect: Optional[Tuple[int, int, int, int]] = None
+    rotation: Optional[float] = None
+    length: Optional[int] = None          # bytes, required for device pointers
+
+    def to_c(self):
+        d = abi.BufferDesc()
+        d.width, d.height, d.stride = self.size
+        if self.rect is not None:
+            d.has_rect = 1
+            d.rect[:] = list(self.rect)
+        if self.rotation is not None:
+            d.has_rotation = 1
+            d.rotation = self.rotation
+        if isinstance(self.data, np.ndarray):
+            assert self.data.dtype == np.uint8 and self.data.flags["C_CONTIGUOUS"]
+            d.kind = abi.BUF_HOST
+            d.ptr = self.data.ctypes.data
+            d.len = self.data.nbytes
+        elif isinstance(self.data, int):
+            d.kind = abi.BUF_DEVICE
+            d.ptr = self.data
+            d.len = int(self.length)
+        else:
+            d.kind = abi.BUF_NONE
+        return d
+
+    def get_rect(self):
+        """Stabilization::get_rect — stabilization/mod.rs:209-224 (stretch to the buffer by default)."""
+        if self.rect is not None:
+            return [int(v) for v in self.rect]
+        return [0, 0, int(self.size[0]), int(self.size[1])]
+
+
+@dataclass
+class Buffers:
+    input: BufferDescription
+    output: BufferDescription
+
+
+@dataclass
+class FrameTransform:
+    matrices: np.ndarray                      # (rows, 14) float32
+    kernel_params: abi.KernelParams
+    fov: float = 1.0
+    minimal_fov: float = 1.0
+    focal_length: Optional[float] = None
+    mesh_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+
+
+@dataclass
+class ProcessedInfo:
+    fov: float
+    minimal_fov: float
+    focal_length: Optional[float]
+    backend: str
+
+
+def list_devices():
+    """`"[CUDA] <name>"` entries, like the `[OpenCL]`/`[wgpu]` lists of stabilization/mod.rs:399-410."""
+    lib = abi.load_library()
+    out = []
+    for i in range(lib.gf_cuda_device_count()):
+        buf = C.create_string_buffer(256)
+        if lib.gf_cuda_device_name(i, buf, 256) == 0:
+            out.append(buf.value.decode())
+    return out
+
+
+class CudaWrapper:
+    """One pre-compiled kernel instantiation + its device staging; not thread-safe (one per host thread/stream)."""
+
+    def __init__(self, handle, lib, pixel_type):
+        self._h = handle
+        self._lib = lib
+        self.pixel_type = pixel_type
+
+    @classmethod
+    def new(cls, params: abi.KernelParams, pixel_type: str, distortion_model: str, digital_lens: Optional[str],
+            buffers: Buffers, drawing_len: int = 0, device: int = 0):
+        lib = abi.load_library()
+        h = C.c_void_p()
+        i, o = buffers.input.to_c(), buffers.output.to_c()
+        rc = lib.gf_cuda_create(C.byref(h), device, C.byref(params), abi.PIXEL_TYPES[pixel_type][0],
+                                abi.LENS[distortion_model], abi.LENS[digital_lens] if digital_lens else 0,
+                                C.byref(i), C.byref(o), drawing_len)
+        if rc != 0:
+            raise GyroflowCoreError(rc, (lib.gf_cuda_last_error(None) or b"").decode())
+        return cls(h, lib, pixel_type)
+
+    def _err(self, rc):
+        return GyroflowCoreError(rc, (self._lib.gf_cuda_last_error(self._h) or b"").decode())
+
+    def undistort_image(self, buffers: Buffers, itm: FrameTransform, drawing_buffer: bytes = b"", stream: int = 0):
+        i, o = buffers.input.to_c(), buffers.output.to_c()
+        m = np.ascontiguousarray(itm.matrices, dtype=np.float32)
+        mesh = np.ascontiguousarray(itm.mesh_data, dtype=np.float32)
+        rc = self._lib.gf_cuda_undistort_image(
+            self._h, C.byref(i), C.byref(o), C.byref(itm.kernel_params),
+            m.ctypes.data, m.shape[0], mesh.ctypes.data if mesh.size else None, mesh.size,
+            None, 0, stream or None)
+        if rc != 0:
+            raise self._err(rc)
+
+    def undistort_image_dev(self, buffers: Buffers, params: abi.KernelParams, matrices_dev: int, matrix_rows: int,
+                            mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0):
+        i, o = buffers.input.to_c(), buffers.output.to_c()
+        rc = self._lib.gf_cuda_undistort_image_dev(self._h, C.byref(i), C.byref(o), C.byref(params),
+                                                   matrices_dev, matrix_rows, mesh_dev or None, mesh_len, stream or None)
+        if rc != 0:
+            raise self._err(rc)
+
+    def synchronize(self):
+        rc = self._lib.gf_cuda_synchronize(self._h)
+        if rc != 0:
+            raise self._err(rc)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.gf_cuda_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.gf_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

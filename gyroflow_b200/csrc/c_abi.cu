@@ -1,0 +1,346 @@
+// c_abi.cu — extern "C" boundary of the CUDA backend (include/gyroflow_cuda.h).
+//
+// Mirrors the reference's backend-wrapper life cycle:
+//   gf_cuda_create          <- OclWrapper::new        src/core/gpu/opencl.rs:178  (WgpuWrapper::new wgpu.rs:147)
+//   gf_cuda_undistort_image <- OclWrapper::undistort_image opencl.rs:330-448 (wgpu.rs:454-559)
+//   gf_cuda_destroy         <- Drop / clear_gpu_cache_current_thread  stabilization/mod.rs:72-81
+// plus the validation `Stabilization::process_pixels` performs before dispatch (stabilization/mod.rs:612-640).
+// There is no CPU fallback: without a usable CUDA device every compute call fails with GF_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+
+#include "kernel_registry.h"
+
+using namespace gf;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Slot {                 // one in-flight set of per-frame tables
+    float* h_mat = nullptr;   // pinned
+    float* d_mat = nullptr;
+    float* h_mesh = nullptr;  // pinned
+    float* d_mesh = nullptr;
+    cudaEvent_t done = nullptr;
+};
+constexpr int kSlots = 4;
+
+} // namespace
+
+struct gf_cuda_ctx {
+    int device = 0;
+    int pixel_type = 0, distortion_model = 0, digital_lens = 0, interpolation = 0;
+    int layout = 0, bpp = 0;
+    int width = 0, height = 0, output_width = 0, output_height = 0;    // Stabilization.size / output_size
+    KernelFn fn = nullptr;
+    cudaStream_t stream = nullptr;
+    size_t max_rows = 0;
+    Slot slots[kSlots];
+    int next_slot = 0;
+    uint8_t* d_src = nullptr; size_t d_src_len = 0;     // staging when buffers are HOST
+    uint8_t* d_dst = nullptr; size_t d_dst_len = 0;
+    size_t drawing_len = 0;
+    unsigned long long launches = 0;
+    std::string last_error;
+};
+
+namespace {
+
+int fail(gf_cuda_ctx* ctx, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+int cuda_fail(gf_cuda_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, GF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+bool pix_layout(int pixel_type, int* layout, int* bpp) {
+    switch (pixel_type) {
+    case GF_PIX_LUMA8:   *layout = LAY_1U8;  *bpp = 1;  return true;
+    case GF_PIX_UV8:     *layout = LAY_2U8;  *bpp = 2;  return true;
+    case GF_PIX_RGB8:    *layout = LAY_3U8;  *bpp = 3;  return true;
+    case GF_PIX_RGBA8:
+    case GF_PIX_BGRA8:   *layout = LAY_4U8;  *bpp = 4;  return true;
+    case GF_PIX_LUMA16:  *layout = LAY_1U16; *bpp = 2;  return true;
+    case GF_PIX_UV16:    *layout = LAY_2U16; *bpp = 4;  return true;
+    case GF_PIX_RGB16:   *layout = LAY_3U16; *bpp = 6;  return true;
+    case GF_PIX_RGBA16:
+    case GF_PIX_AYUV16:  *layout = LAY_4U16; *bpp = 8;  return true;
+    case GF_PIX_R32F:    *layout = LAY_1F32; *bpp = 4;  return true;
+    case GF_PIX_RGBAF:   *layout = LAY_4F32; *bpp = 16; return true;
+    case GF_PIX_RGBAF16: *layout = LAY_4F16; *bpp = 8;  return true;
+    default: return false;
+    }
+}
+
+KernelFn find_kernel(int lens, int digital, int layout, int interp) {
+    switch (lens) {
+    case GF_LENS_OPENCV_FISHEYE:     return gf_kernel_opencv_fisheye(digital, layout, interp);
+    case GF_LENS_OPENCV_STANDARD:    return gf_kernel_opencv_standard(digital, layout, interp);
+    case GF_LENS_POLY3:              return gf_kernel_poly3(digital, layout, interp);
+    case GF_LENS_POLY5:              return gf_kernel_poly5(digital, layout, interp);
+    case GF_LENS_PTLENS:             return gf_kernel_ptlens(digital, layout, interp);
+    case GF_LENS_INSTA360:           return gf_kernel_insta360(digital, layout, interp);
+    case GF_LENS_SONY:               return gf_kernel_sony(digital, layout, interp);
+    case GF_LENS_GENERIC_POLYNOMIAL: return gf_kernel_generic_polynomial(digital, layout, interp);
+    case GF_LENS_GOPRO:              return gf_kernel_gopro(digital, layout, interp);
+    default: return nullptr;
+    }
+}
+
+const char* const kLensNames[GF_LENS_COUNT] = {
+    "none", "opencv_fisheye", "opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony", "generic_polynomial",
+    "gopro", "gopro_superview", "gopro_hyperview", "gopro_warp", "digital_stretch", "gopro6_superview" };
+
+// process_pixels / OclWrapper::new validation (stabilization/mod.rs:613,636-640; opencl.rs:179; wgpu.rs:150)
+int validate(gf_cuda_ctx* ctx, const gf_kernel_params* p, const gf_buffer_desc* in, const gf_buffer_desc* out, int bpp) {
+    if (!p || !in || !out) return fail(ctx, GF_ERR_BAD_PARAMS, "null argument");
+    if (in->height < 4 || out->height < 4 || p->height < 4 || p->output_height < 4)
+        return fail(ctx, GF_ERR_SIZE_TOO_SMALL, "SizeTooSmall: height < 4");
+    if (p->stride < 1 || p->output_stride < 1) return fail(ctx, GF_ERR_BAD_STRIDE, "InvalidStride: stride < 1");
+    if (p->width > 16384 || p->output_width > 16384 || p->width < 1 || p->output_width < 1)
+        return fail(ctx, GF_ERR_BAD_PARAMS, "width out of range (1..16384)");
+    if (in->width > p->stride)         return fail(ctx, GF_ERR_BAD_STRIDE, "InvalidStride: input width > stride");
+    if (out->width > p->output_stride) return fail(ctx, GF_ERR_BAD_STRIDE, "InvalidStride: output width > output_stride");
+    if (p->stride != in->stride || p->output_stride != out->stride)
+        return fail(ctx, GF_ERR_BAD_STRIDE, "InvalidStride: KernelParams stride differs from the buffer description");
+    if (p->bytes_per_pixel != bpp) return fail(ctx, GF_ERR_BAD_PARAMS, "bytes_per_pixel does not match the pixel type");
+    if (p->matrix_count < 1) return fail(ctx, GF_ERR_BAD_PARAMS, "matrix_count < 1");
+    if ((in->kind != GF_BUF_HOST && in->kind != GF_BUF_DEVICE) || (out->kind != GF_BUF_HOST && out->kind != GF_BUF_DEVICE) || !in->ptr || !out->ptr)
+        return fail(ctx, GF_ERR_BAD_PARAMS, "unsupported buffer source");
+    // every tap the kernel may read must be inside the input buffer (Rust would panic on the slice index)
+    const long long x0 = p->source_rect[0], y0 = p->source_rect[1], x1 = x0 + p->source_rect[2], y1 = y0 + p->source_rect[3];
+    if (p->source_rect[2] > 0 && p->source_rect[3] > 0) {
+        if (x0 < 0 || y0 < 0) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "source_rect has a negative origin");
+        const unsigned long long last = (unsigned long long)(y1 - 1) * (unsigned long long)p->stride + (unsigned long long)x1 * (unsigned long long)bpp;
+        if (last > in->len) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch input: source_rect exceeds the input buffer");
+    }
+    if (out->len == 0) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "empty output buffer");
+    return GF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+GF_API int gf_cuda_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { g_last_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+GF_API int gf_cuda_device_name(int device, char* buf, size_t buf_len) {
+    if (!buf || buf_len == 0) return GF_ERR_BAD_PARAMS;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(nullptr, GF_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)); }
+    snprintf(buf, buf_len, "[CUDA] %s", prop.name);      // listed like "[OpenCL] ..." / "[wgpu] ..." (stabilization/mod.rs:399-410)
+    return GF_OK;
+}
+
+GF_API int gf_cuda_supports(const gf_buffer_desc* in, const gf_buffer_desc* out) {
+    if (!in || !out) return 0;
+    const bool i = in->kind == GF_BUF_HOST || in->kind == GF_BUF_DEVICE;
+    const bool o = out->kind == GF_BUF_HOST || out->kind == GF_BUF_DEVICE;
+    return (i && o) ? 1 : 0;
+}
+
+GF_API const char* gf_cuda_version(void) { return "gyroflow-b200 0.1 (sm_100a)"; }
+GF_API const char* gf_cuda_backend_name(void) { return "CUDA"; }
+
+GF_API int gf_lens_from_name(const char* id) {
+    if (id) for (int i = 1; i < GF_LENS_COUNT; ++i) if (!strcmp(id, kLensNames[i])) return i;
+    return GF_LENS_OPENCV_FISHEYE;     // DistortionModel::from_name falls back to the default model
+}
+GF_API const char* gf_lens_name(int lens_id) { return (lens_id >= 0 && lens_id < GF_LENS_COUNT) ? kLensNames[lens_id] : nullptr; }
+GF_API int gf_pixel_bytes(int pixel_type) { int l, b; return pix_layout(pixel_type, &l, &b) ? b : 0; }
+GF_API int gf_combo_supported(int pixel_type, int distortion_model, int digital_lens, int interpolation) {
+    int l, b;
+    if (!pix_layout(pixel_type, &l, &b)) return 0;
+    return find_kernel(distortion_model, digital_lens, l, interpolation) != nullptr ? 1 : 0;
+}
+
+GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_params* params, int pixel_type,
+                          int distortion_model, int digital_lens,
+                          const gf_buffer_desc* in, const gf_buffer_desc* out, size_t drawing_len) {
+    if (!out_ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "out_ctx is null");
+    *out_ctx = nullptr;
+    int layout = 0, bpp = 0;
+    if (!pix_layout(pixel_type, &layout, &bpp)) return fail(nullptr, GF_ERR_BAD_PARAMS, "unknown pixel type");
+    { int rc = validate(nullptr, params, in, out, bpp); if (rc != GF_OK) return rc; }
+    KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation);
+    if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
+
+    gf_cuda_ctx* ctx = new gf_cuda_ctx();
+    ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn;
+    ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
+    ctx->drawing_len = drawing_len;
+    auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaSetDevice"); return bail(GF_ERR_CUDA); }
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaStreamCreate"); return bail(GF_ERR_CUDA); }
+    // matrices: 14 * max(W, H) f32 (rows = height, or width for horizontal rolling shutter) — opencl.rs:268, wgpu.rs:260
+    size_t rows = (size_t)std::max(std::max(params->width, params->height), std::max(params->output_width, params->output_height));
+    rows = std::max(rows, (size_t)params->matrix_count);
+    ctx->max_rows = rows;
+    for (int s = 0; s < kSlots; ++s) {
+        Slot& sl = ctx->slots[s];
+        if ((e = cudaMallocHost(&sl.h_mat, rows * GF_MATRIX_STRIDE * sizeof(float))) != cudaSuccess ||
+            (e = cudaMalloc(&sl.d_mat, rows * GF_MATRIX_STRIDE * sizeof(float))) != cudaSuccess ||
+            (e = cudaMallocHost(&sl.h_mesh, GF_MESH_MAX_LEN * sizeof(float))) != cudaSuccess ||
+            (e = cudaMalloc(&sl.d_mesh, GF_MESH_MAX_LEN * sizeof(float))) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) {
+            cuda_fail(ctx, e, "table staging allocation"); return bail(GF_ERR_CUDA);
+        }
+    }
+    if (in->kind == GF_BUF_HOST)  { if ((e = cudaMalloc(&ctx->d_src, in->len)) != cudaSuccess)  { cuda_fail(ctx, e, "cudaMalloc(src staging)"); return bail(GF_ERR_CUDA); } ctx->d_src_len = in->len; }
+    if (out->kind == GF_BUF_HOST) { if ((e = cudaMalloc(&ctx->d_dst, out->len)) != cudaSuccess) { cuda_fail(ctx, e, "cudaMalloc(dst staging)"); return bail(GF_ERR_CUDA); } ctx->d_dst_len = out->len; }
+    *out_ctx = ctx;
+    return GF_OK;
+}
+
+GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < kSlots; ++s) {
+        Slot& sl = ctx->slots[s];
+        if (sl.h_mat) cudaFreeHost(sl.h_mat);
+        if (sl.d_mat) cudaFree(sl.d_mat);
+        if (sl.h_mesh) cudaFreeHost(sl.h_mesh);
+        if (sl.d_mesh) cudaFree(sl.d_mesh);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (ctx->d_src) cudaFree(ctx->d_src);
+    if (ctx->d_dst) cudaFree(ctx->d_dst);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
+                    const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len,
+                    bool tables_on_device, void* cu_stream) {
+    if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
+    { int rc = validate(ctx, p, in, out, ctx->bpp); if (rc != GF_OK) return rc; }
+    if (!matrices) return fail(ctx, GF_ERR_NO_DATA, "NoStabilizationData: matrices is null");
+    if (p->width != ctx->width || p->height != ctx->height || p->output_width != ctx->output_width || p->output_height != ctx->output_height)
+        return fail(ctx, GF_ERR_SIZE_MISMATCH, "SizeMismatch: KernelParams size differs from the size this context was created for");
+    if (p->interpolation != ctx->interpolation)
+        return fail(ctx, GF_ERR_UNSUPPORTED_COMBO, "interpolation differs from the one this context was created for");
+    if ((size_t)p->matrix_count > matrix_rows) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch matrices: matrix_count > rows supplied");
+    if (!tables_on_device && matrix_rows > ctx->max_rows) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch matrices");
+    if (mesh_len > GF_MESH_MAX_LEN) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch buf_mesh_data");
+    if (mesh_len > 0 && !mesh) return fail(ctx, GF_ERR_BAD_PARAMS, "mesh is null");
+    if (in->kind == GF_BUF_HOST && in->len > ctx->d_src_len)   return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch input");
+    if (out->kind == GF_BUF_HOST && out->len > ctx->d_dst_len) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch output");
+    if (tables_on_device && (reinterpret_cast<uintptr_t>(matrices) & 7u)) return fail(ctx, GF_ERR_BAD_PARAMS, "device matrices must be 8-byte aligned");
+
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : ctx->stream;
+
+    WarpArgs A;
+    memset(&A, 0, sizeof(A));
+    A.p = *p;
+    if (tables_on_device) {
+        A.matrices = matrices;
+        A.mesh = mesh_len ? mesh : nullptr;
+    } else {
+        Slot& sl = ctx->slots[ctx->next_slot];
+        ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+        CK(cudaEventSynchronize(sl.done));                     // the slot's previous frame has consumed its tables
+        memcpy(sl.h_mat, matrices, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float));
+        CK(cudaMemcpyAsync(sl.d_mat, sl.h_mat, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float), cudaMemcpyHostToDevice, st));
+        A.matrices = sl.d_mat;
+        if (mesh_len) {
+            memcpy(sl.h_mesh, mesh, mesh_len * sizeof(float));
+            CK(cudaMemcpyAsync(sl.d_mesh, sl.h_mesh, mesh_len * sizeof(float), cudaMemcpyHostToDevice, st));
+            A.mesh = sl.d_mesh;
+        }
+        // recorded after the launch below
+    }
+    A.mesh_len = (int)mesh_len;
+
+    const uint8_t* src = (const uint8_t*)in->ptr;
+    uint8_t* dst = (uint8_t*)out->ptr;
+    if (in->kind == GF_BUF_HOST) {                             // opencl.rs:359 `self.src.write(buffer)`
+        CK(cudaMemcpyAsync(ctx->d_src, in->ptr, in->len, cudaMemcpyHostToDevice, st));
+        src = ctx->d_src;
+    }
+    // Does the kernel write every pixel of [0,w) x [0,h)?  (output_rect == whole buffer == output size: the bounds test of
+    // cpu_undistort.rs:551 then passes everywhere.)  If so only those bytes travel back; otherwise the untouched pixels
+    // must keep their previous content, like on the CPU path, so the buffer is uploaded first.
+    const bool full_cover = p->output_rect[0] == 0 && p->output_rect[1] == 0 && p->output_rect[2] == out->width && p->output_rect[3] == out->height &&
+                            out->width == p->output_width && out->height == p->output_height && (p->flags & 4) == 0 &&
+                            (size_t)out->height * (size_t)p->output_stride <= out->len + (size_t)(p->output_stride - out->width * ctx->bpp);
+    if (out->kind == GF_BUF_HOST) {
+        if (!full_cover) CK(cudaMemcpyAsync(ctx->d_dst, out->ptr, out->len, cudaMemcpyHostToDevice, st));
+        dst = ctx->d_dst;
+    }
+    A.src = src; A.dst = dst; A.src_len = in->len; A.dst_len = out->len;
+    const int bpp = ctx->bpp;
+    A.out_rows = (int)((out->len + (size_t)p->output_stride - 1) / (size_t)p->output_stride);
+    A.out_cols = p->output_stride / bpp;
+    A.src_vec_ok = ((reinterpret_cast<uintptr_t>(src) % (uintptr_t)bpp) == 0 && (p->stride % bpp) == 0) ? 1 : 0;
+    A.dst_vec_ok = ((reinterpret_cast<uintptr_t>(dst) % (uintptr_t)bpp) == 0 && (p->output_stride % bpp) == 0) ? 1 : 0;
+    // cpu_undistort.rs:521-528, same float operations
+    A.r_limit_sq = p->r_limit * p->r_limit;
+    for (int i = 0; i < 4; ++i) A.bg[i] = p->background[i] * p->max_pixel_value;
+    const float factor = fmaxf(1.0f - p->lens_correction_amount, 0.001f);
+    A.out_c[0] = (float)p->output_width / 2.0f; A.out_c[1] = (float)p->output_height / 2.0f;
+    A.out_f[0] = p->f[0] / p->fov / factor;      A.out_f[1] = p->f[1] / p->fov / factor;
+
+    const dim3 block(GF_BLOCK_X, GF_BLOCK_Y);
+    const dim3 grid((A.out_cols + GF_BLOCK_X - 1) / GF_BLOCK_X, (A.out_rows + GF_BLOCK_Y - 1) / GF_BLOCK_Y);
+    if (grid.x == 0 || grid.y == 0 || grid.y > 65535) return fail(ctx, GF_ERR_BAD_PARAMS, "output buffer geometry out of range");
+    ctx->fn<<<grid, block, 0, st>>>(A);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (!tables_on_device) {
+        Slot& used = ctx->slots[(ctx->next_slot + kSlots - 1) % kSlots];
+        CK(cudaEventRecord(used.done, st));
+    }
+    if (out->kind == GF_BUF_HOST) {                                                                                  // opencl.rs:413
+        if (full_cover) CK(cudaMemcpy2DAsync(out->ptr, (size_t)p->output_stride, ctx->d_dst, (size_t)p->output_stride,
+                                             (size_t)out->width * (size_t)bpp, (size_t)out->height, cudaMemcpyDeviceToHost, st));
+        else            CK(cudaMemcpyAsync(out->ptr, ctx->d_dst, out->len, cudaMemcpyDeviceToHost, st));
+    }
+    if (in->kind == GF_BUF_HOST || out->kind == GF_BUF_HOST) CK(cudaStreamSynchronize(st));
+    return GF_OK;
+}
+
+GF_API int gf_cuda_undistort_image(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                   const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
+                                   const float* mesh, size_t mesh_len, const uint8_t* drawing, size_t drawing_len, void* cu_stream) {
+    (void)drawing; (void)drawing_len;    // the CPU path (the parity target) draws no overlay: cpu_undistort.rs:234-251,607,617
+    return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream);
+}
+
+GF_API int gf_cuda_undistort_image_dev(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                       const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                       const float* mesh_dev, size_t mesh_len, void* cu_stream) {
+    return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream);
+}
+
+GF_API int gf_cuda_synchronize(gf_cuda_ctx* ctx) {
+    if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GF_OK;
+}
+
+GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+GF_API uint64_t gf_cuda_launch_count(gf_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

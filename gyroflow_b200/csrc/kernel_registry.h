@@ -1,0 +1,62 @@
+// kernel_registry.h — ahead-of-time kernel family: one instantiation per
+// (lens model, digital lens, pixel layout, interpolation).  The reference selects its kernel by
+// splicing lens-model source text into the OpenCL/WGSL program at run time (gpu/opencl.rs:184-211);
+// here every valid combination is compiled for sm_100a up front and looked up by id.
+#pragma once
+#include "warp_kernel.cuh"
+
+namespace gf {
+
+typedef void (*KernelFn)(const WarpArgs);
+
+// pixel layouts: (COUNT, SCALAR) pairs that exist in pixel_formats.rs
+enum {
+    LAY_1U8 = 0, LAY_2U8, LAY_3U8, LAY_4U8,
+    LAY_1U16, LAY_2U16, LAY_3U16, LAY_4U16,
+    LAY_1F32, LAY_4F32, LAY_4F16,
+    LAY_COUNT
+};
+
+struct KernelInfo { KernelFn fn; int bytes_per_pixel; };
+
+// implemented once per lens model in inst_<model>.cu; returns nullptr for combinations that are not compiled
+KernelFn gf_kernel_opencv_fisheye(int digital, int layout, int interp);
+KernelFn gf_kernel_opencv_standard(int digital, int layout, int interp);
+KernelFn gf_kernel_poly3(int digital, int layout, int interp);
+KernelFn gf_kernel_poly5(int digital, int layout, int interp);
+KernelFn gf_kernel_ptlens(int digital, int layout, int interp);
+KernelFn gf_kernel_insta360(int digital, int layout, int interp);
+KernelFn gf_kernel_sony(int digital, int layout, int interp);
+KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp);
+KernelFn gf_kernel_gopro(int digital, int layout, int interp);
+
+template <int LENS, int DIGITAL, class PIX>
+static KernelFn pick_interp(int interp) {
+    switch (interp) {
+    case GF_INTERP_BILINEAR: return warp_kernel<LENS, DIGITAL, PIX, 2>;
+#ifdef GF_ENABLE_HIGH_ORDER
+    case GF_INTERP_BICUBIC:  return warp_kernel<LENS, DIGITAL, PIX, 4>;
+    case GF_INTERP_LANCZOS4: return warp_kernel<LENS, DIGITAL, PIX, 8>;
+#endif
+    default: return nullptr;
+    }
+}
+template <int LENS, int DIGITAL>
+static KernelFn pick_layout(int layout, int interp) {
+    switch (layout) {
+    case LAY_1U8:  return pick_interp<LENS, DIGITAL, Pix<1, SC_U8>>(interp);
+    case LAY_2U8:  return pick_interp<LENS, DIGITAL, Pix<2, SC_U8>>(interp);
+    case LAY_3U8:  return pick_interp<LENS, DIGITAL, Pix<3, SC_U8>>(interp);
+    case LAY_4U8:  return pick_interp<LENS, DIGITAL, Pix<4, SC_U8>>(interp);
+    case LAY_1U16: return pick_interp<LENS, DIGITAL, Pix<1, SC_U16>>(interp);
+    case LAY_2U16: return pick_interp<LENS, DIGITAL, Pix<2, SC_U16>>(interp);
+    case LAY_3U16: return pick_interp<LENS, DIGITAL, Pix<3, SC_U16>>(interp);
+    case LAY_4U16: return pick_interp<LENS, DIGITAL, Pix<4, SC_U16>>(interp);
+    case LAY_1F32: return pick_interp<LENS, DIGITAL, Pix<1, SC_F32>>(interp);
+    case LAY_4F32: return pick_interp<LENS, DIGITAL, Pix<4, SC_F32>>(interp);
+    case LAY_4F16: return pick_interp<LENS, DIGITAL, Pix<4, SC_F16>>(interp);
+    default: return nullptr;
+    }
+}
+
+} // namespace gf

@@ -1,0 +1,254 @@
+/* gyroflow_cuda.h — C ABI of the B200 (sm_100a) backend for Gyroflow's per-pixel warp.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one method of the
+ * reference's backend-wrapper convention (there is no C ABI in the reference; the
+ * convention is `<Backend>Wrapper::{new, undistort_image, list_devices, ...}` driven by
+ * `Stabilization::{init_backends, process_pixels}`).  Citations are relative to the
+ * reference tree (gyroflow/gyroflow @ b5e8828):
+ *
+ *   gf_kernel_params            <- KernelParams            src/core/stabilization/mod.rs:101-150
+ *   GF_FLAG_*                   <- KernelParamsFlags       src/core/stabilization/mod.rs:83-99
+ *   GF_INTERP_*                 <- Interpolation           src/core/stabilization/mod.rs:24-34
+ *   GF_LENS_*                   <- DistortionModel ids     src/core/stabilization/distortion_models/mod.rs:92-110
+ *                                  (numeric ids follow gpu/stabilize_spirv/src/distortion_models/mod.rs:62-80)
+ *   GF_PIX_*                    <- PixelType impls         src/core/stabilization/pixel_formats.rs:50-302
+ *   gf_buffer_desc              <- BufferDescription       src/core/gpu/mod.rs:17-24 (+ BufferSource::{Cpu,CUDABuffer} 34,67-70)
+ *   matrices: rows x 14 f32     <- FrameTransform.matrices src/core/stabilization/frame_transform.rs:13,301-307
+ *   mesh: <= 839 f32            <- FrameTransform.mesh_data src/core/gyro_source/splines.rs:88-89, sony.rs:483-548
+ *
+ * No torch / C++ types cross this boundary: plain pointers, sizes and PODs only.
+ * There is NO CPU fallback behind these calls; when no CUDA device is usable every
+ * compute entry point returns GF_ERR_CUDA.
+ */
+#ifndef GYROFLOW_CUDA_H
+#define GYROFLOW_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#  define GF_API __declspec(dllexport)
+#else
+#  define GF_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * KernelParams — byte-for-byte mirror of `#[repr(C, packed(4))] struct KernelParams`
+ * (src/core/stabilization/mod.rs:103-148).  368 bytes, every member 4-byte aligned.
+ * ---------------------------------------------------------------------------------------- */
+#pragma pack(push, 4)
+typedef struct gf_kernel_params {
+    int32_t width;                       /*   0 */
+    int32_t height;                      /*   4 */
+    int32_t stride;                      /*   8  input stride in bytes */
+    int32_t output_width;                /*  12 */
+    int32_t output_height;               /*  16 */
+    int32_t output_stride;               /*  20  output stride in bytes */
+    int32_t matrix_count;                /*  24  1 = no rolling-shutter correction */
+    int32_t interpolation;               /*  28  GF_INTERP_* */
+    int32_t background_mode;             /*  32  0 colour, 1 edge repeat, 2 edge mirror, 3 margin+feather */
+    int32_t flags;                       /*  36  GF_FLAG_* */
+    int32_t bytes_per_pixel;             /*  40 */
+    int32_t pix_element_count;           /*  44 */
+    float   background[4];               /*  48 */
+    float   f[2];                        /*  64  focal length in pixels */
+    float   c[2];                        /*  72  principal point */
+    float   k[12];                       /*  80  distortion coefficients */
+    float   fov;                         /* 128 */
+    float   r_limit;                     /* 132 */
+    float   lens_correction_amount;      /* 136 */
+    float   input_vertical_stretch;      /* 140 */
+    float   input_horizontal_stretch;    /* 144 */
+    float   background_margin;           /* 148 */
+    float   background_margin_feather;   /* 152 */
+    float   canvas_scale;                /* 156 */
+    float   input_rotation;              /* 160 */
+    float   output_rotation;             /* 164 */
+    float   translation2d[2];            /* 168 */
+    float   translation3d[4];            /* 176 */
+    int32_t source_rect[4];              /* 192  x, y, w, h */
+    int32_t output_rect[4];              /* 208  x, y, w, h */
+    float   digital_lens_params[16];     /* 224 */
+    float   safe_area_rect[4];           /* 288 */
+    float   max_pixel_value;             /* 304 */
+    int32_t distortion_model;            /* 308  (unused by the CPU path; informational) */
+    int32_t digital_lens;                /* 312  (unused by the CPU path; informational) */
+    float   pixel_value_limit;           /* 316 */
+    float   light_refraction_coefficient;/* 320 */
+    int32_t plane_index;                 /* 324 */
+    float   reserved1;                   /* 328 */
+    float   reserved2;                   /* 332 */
+    float   ewa_coeffs_p[4];             /* 336 */
+    float   ewa_coeffs_q[4];             /* 352 */
+} gf_kernel_params;                      /* 368 */
+#pragma pack(pop)
+
+#define GF_KERNEL_PARAMS_SIZE 368
+#define GF_MATRIX_STRIDE      14     /* f32 per row: 3x3 inverse, sx, sy, ra, ox, oy */
+#define GF_MESH_MAX_LEN       839    /* 9 + 9*9*2 + 9*9*4*2 + 20, splines.rs:88-89 */
+
+#if defined(__cplusplus)
+static_assert(sizeof(gf_kernel_params) == GF_KERNEL_PARAMS_SIZE, "KernelParams ABI drift");
+#else
+_Static_assert(sizeof(gf_kernel_params) == GF_KERNEL_PARAMS_SIZE, "KernelParams ABI drift");
+#endif
+
+/* KernelParamsFlags — src/core/stabilization/mod.rs:85-98 */
+enum {
+    GF_FLAG_FIX_COLOR_RANGE      = 1 << 0,
+    GF_FLAG_HAS_DIGITAL_LENS     = 1 << 1,
+    GF_FLAG_FILL_WITH_BACKGROUND = 1 << 2,
+    GF_FLAG_DRAWING_ENABLED      = 1 << 3,
+    GF_FLAG_HORIZONTAL_RS        = 1 << 4,
+    GF_FLAG_HAS_SOURCE_RECT      = 1 << 5,
+    GF_FLAG_HAS_OUTPUT_RECT      = 1 << 6,
+    GF_FLAG_FRAMEBUFFER_INVERTED = 1 << 7,
+    GF_FLAG_HAS_IBIS_DATA        = 1 << 8,
+    GF_FLAG_HAS_MESH_DATA        = 1 << 9,
+    GF_FLAG_HAS_FPD_DATA         = 1 << 10,
+    GF_FLAG_ANY_UNDERWATER       = 1 << 11
+};
+
+/* Interpolation — src/core/stabilization/mod.rs:25-34 */
+enum {
+    GF_INTERP_BILINEAR       = 2,
+    GF_INTERP_BICUBIC        = 4,
+    GF_INTERP_LANCZOS4       = 8,
+    GF_INTERP_ROBIDOUX_SHARP = 10,
+    GF_INTERP_ROBIDOUX       = 11,
+    GF_INTERP_MITCHELL       = 12,
+    GF_INTERP_CATMULL_ROM    = 13
+};
+
+/* Lens-model plugin ids.  String ids are the reference's `DistortionModel::id()`
+ * (distortion_models/mod.rs:92-110); integers 0..13 follow the `#[repr(i32)]` order in
+ * gpu/stabilize_spirv/src/distortion_models/mod.rs:62-80, gopro6_superview (absent there) is 14. */
+enum {
+    GF_LENS_NONE               = 0,   /* also: "no digital lens" */
+    GF_LENS_OPENCV_FISHEYE     = 1,
+    GF_LENS_OPENCV_STANDARD    = 2,
+    GF_LENS_POLY3              = 3,
+    GF_LENS_POLY5              = 4,
+    GF_LENS_PTLENS             = 5,
+    GF_LENS_INSTA360           = 6,
+    GF_LENS_SONY               = 7,
+    GF_LENS_GENERIC_POLYNOMIAL = 8,
+    GF_LENS_GOPRO              = 9,
+    GF_LENS_GOPRO_SUPERVIEW    = 10,
+    GF_LENS_GOPRO_HYPERVIEW    = 11,
+    GF_LENS_GOPRO_WARP         = 12,
+    GF_LENS_DIGITAL_STRETCH    = 13,
+    GF_LENS_GOPRO6_SUPERVIEW   = 14,
+    GF_LENS_COUNT              = 15
+};
+
+/* Pixel formats — the PixelType impls of pixel_formats.rs.  Formats that share a memory
+ * layout and conversion (BGRA8 == RGBA8, AYUV16 == RGBA16) keep distinct ids for callers. */
+enum {
+    GF_PIX_LUMA8   = 0,   /* pixel_formats.rs:64-81   */
+    GF_PIX_LUMA16  = 1,   /* :82-99   */
+    GF_PIX_RGB8    = 2,   /* :100-117 */
+    GF_PIX_RGBA8   = 3,   /* :118-135 */
+    GF_PIX_BGRA8   = 4,   /* :136-153 */
+    GF_PIX_RGB16   = 5,   /* :154-171 */
+    GF_PIX_RGBA16  = 6,   /* :172-189 */
+    GF_PIX_AYUV16  = 7,   /* :190-207 */
+    GF_PIX_RGBAF   = 8,   /* :208-225 */
+    GF_PIX_RGBAF16 = 9,   /* :231-248 */
+    GF_PIX_R32F    = 10,  /* :249-266 */
+    GF_PIX_UV8     = 11,  /* :267-284 */
+    GF_PIX_UV16    = 12,  /* :285-302 */
+    GF_PIX_COUNT   = 13
+};
+
+/* Error codes.  0 = ok.  The Rust side maps them onto GyroflowCoreError (src/core/lib.rs:2098-2141):
+ * SIZE_TOO_SMALL -> SizeTooSmall, SIZE_MISMATCH -> SizeMismatch, BAD_STRIDE -> InvalidStride,
+ * NO_DATA -> NoStabilizationData, everything else -> Unknown. */
+enum {
+    GF_OK                    =  0,
+    GF_ERR_BAD_PARAMS        = -1,
+    GF_ERR_SIZE_TOO_SMALL    = -2,   /* height < 4, stabilization/mod.rs:613, opencl.rs:179 */
+    GF_ERR_SIZE_MISMATCH     = -3,   /* stabilization/mod.rs:636-637 */
+    GF_ERR_BAD_STRIDE        = -4,   /* stabilization/mod.rs:639-640 */
+    GF_ERR_UNSUPPORTED_COMBO = -5,
+    GF_ERR_CUDA              = -6,   /* no device / driver error; see gf_cuda_last_error */
+    GF_ERR_BUFFER_TOO_SMALL  = -7,   /* opencl.rs:336,352,355 "Buffer size mismatch" */
+    GF_ERR_NO_DATA           = -8
+};
+
+/* BufferDescription + BufferSource::{Cpu, CUDABuffer} — src/core/gpu/mod.rs:17-24,34,67-70 */
+enum { GF_BUF_NONE = 0, GF_BUF_HOST = 1, GF_BUF_DEVICE = 2 };
+
+typedef struct gf_buffer_desc {
+    int32_t  width, height, stride;  /* size: (w, h, stride in bytes) */
+    int32_t  has_rect;               /* rect: Option<(x, y, w, h)> */
+    int32_t  rect[4];
+    int32_t  has_rotation;           /* rotation: Option<f32>, degrees */
+    float    rotation;
+    int32_t  kind;                   /* GF_BUF_HOST (BufferSource::Cpu) or GF_BUF_DEVICE (BufferSource::CUDABuffer) */
+    int32_t  _pad;
+    void*    ptr;                    /* host pointer or CUdeviceptr; borrowed for the call only */
+    size_t   len;                    /* bytes reachable from ptr */
+} gf_buffer_desc;
+
+typedef struct gf_cuda_ctx gf_cuda_ctx;   /* opaque; one per host thread / stream, like the thread-local LRU (mod.rs:62-66) */
+
+/* ---- capability probe: OclWrapper::list_devices opencl.rs:60, wgpu.rs:77,99,113 ---------- */
+GF_API int         gf_cuda_device_count(void);
+GF_API int         gf_cuda_device_name(int device, char* buf, size_t buf_len);   /* "[CUDA] NVIDIA B200" style name */
+GF_API int         gf_cuda_supports(const gf_buffer_desc* in, const gf_buffer_desc* out); /* is_buffer_supported opencl.rs:451 */
+GF_API const char* gf_cuda_version(void);
+
+/* ---- lens plugin surface: DistortionModel::from_name / id  distortion_models/mod.rs:79-90 -- */
+GF_API int         gf_lens_from_name(const char* id);     /* unknown -> GF_LENS_OPENCV_FISHEYE, like from_name's default */
+GF_API const char* gf_lens_name(int lens_id);             /* NULL if out of range */
+GF_API int         gf_pixel_bytes(int pixel_type);        /* COUNT * SCALAR_BYTES, 0 if unknown */
+GF_API int         gf_combo_supported(int pixel_type, int distortion_model, int digital_lens, int interpolation);
+
+/* ---- construct: OclWrapper::new opencl.rs:178 / WgpuWrapper::new wgpu.rs:147 ----------------
+ * Validates (height >= 4, stride >= 1, width <= 16384 — opencl.rs:179, wgpu.rs:150), selects the
+ * pre-compiled kernel instantiation for (pixel_type, distortion_model, digital_lens, interpolation)
+ * and allocates device staging for params / matrices (14*max(W,H) f32) / mesh (839 f32) / drawing,
+ * plus src/dst staging when the buffers are HOST.  `digital_lens` = GF_LENS_NONE for Option::None. */
+GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device,
+                          const gf_kernel_params* params, int pixel_type,
+                          int distortion_model, int digital_lens,
+                          const gf_buffer_desc* in, const gf_buffer_desc* out,
+                          size_t drawing_len);
+GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx);
+
+/* ---- run: OclWrapper::undistort_image opencl.rs:330 / WgpuWrapper::undistort_image wgpu.rs:454
+ * `params`, `matrices`, `mesh`, `drawing` are HOST pointers (they come out of FrameTransform).
+ * HOST image buffers: H2D -> kernel -> D2H -> stream sync before return (opencl.rs:359,413).
+ * DEVICE image buffers: everything is enqueued on `cu_stream` (NULL = the ctx's own stream) and the
+ * call returns without synchronising. */
+GF_API int gf_cuda_undistort_image(gf_cuda_ctx* ctx,
+                                   const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                   const gf_kernel_params* params,
+                                   const float* matrices, size_t matrix_rows,
+                                   const float* mesh, size_t mesh_len,
+                                   const uint8_t* drawing, size_t drawing_len,
+                                   void* cu_stream);
+
+/* Same, but `matrices_dev` / `mesh_dev` already live in device memory (frame-sharded render queue:
+ * tables are broadcast once, see DESIGN.md "multi-GPU").  No reference counterpart. */
+GF_API int gf_cuda_undistort_image_dev(gf_cuda_ctx* ctx,
+                                       const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                       const gf_kernel_params* params,
+                                       const float* matrices_dev, size_t matrix_rows,
+                                       const float* mesh_dev, size_t mesh_len,
+                                       void* cu_stream);
+
+GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
+GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
+GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */
+GF_API uint64_t    gf_cuda_launch_count(gf_cuda_ctx* ctx);   /* kernels launched by this ctx so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYROFLOW_CUDA_H */

@@ -1,0 +1,1080 @@
+/* gf_oracle.c — CPU oracle (TEST INFRASTRUCTURE ONLY; see gf_oracle.h for the rules).
+ *
+ * Restates, function by function, the reference CPU path.  Citations are relative to
+ * /root/reference/src/core (gyroflow @ b5e8828).  PARITY UNPINNED — see gf_oracle.h.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
+ */
+#define _GNU_SOURCE
+#include "gf_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Rust scalar semantics
+ * ---------------------------------------------------------------------------------------- */
+/* `x as i32` for f32: truncate toward zero, saturate, NaN -> 0 */
+static inline int32_t rs_f32_as_i32(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT32_MAX;
+    if (x <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)x;
+}
+/* `x as usize` for f64 */
+static inline size_t rs_f64_as_usize(double x) {
+    if (x != x) return 0;
+    if (x <= 0.0) return 0;
+    if (x >= 18446744073709551616.0) return SIZE_MAX;
+    return (size_t)x;
+}
+static inline uint8_t rs_f32_as_u8(float x) {
+    if (x != x) return 0;
+    if (x <= 0.0f) return 0;
+    if (x >= 255.0f) return 255;
+    return (uint8_t)x;
+}
+static inline uint16_t rs_f32_as_u16(float x) {
+    if (x != x) return 0;
+    if (x <= 0.0f) return 0;
+    if (x >= 65535.0f) return 65535;
+    return (uint16_t)x;
+}
+/* f32::round — half away from zero (glibc roundf is exact) */
+static inline float rs_round(float x) { return roundf(x); }
+/* f32::max / f32::min — NaN-ignoring, like fmaxf/fminf */
+static inline float rs_max(float a, float b) { return fmaxf(a, b); }
+static inline float rs_min(float a, float b) { return fminf(a, b); }
+static inline double rs_maxd(double a, double b) { return fmax(a, b); }
+static inline double rs_mind(double a, double b) { return fmin(a, b); }
+/* f32::clamp */
+static inline float rs_clamp(float x, float lo, float hi) {
+    if (x < lo) return lo;
+    if (x > hi) return hi;
+    return x;
+}
+/* half::f16 <-> f32 (half 2.7.1: round-to-nearest-even) */
+static inline float f16_to_f32(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu, u;
+    if (exp == 0) {
+        if (man == 0) u = sign;
+        else { int e = -1; do { e++; man <<= 1; } while (!(man & 0x400u)); u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13); }
+    } else if (exp == 31) u = sign | 0x7f800000u | (man << 13);
+    else u = sign | ((exp + 112) << 23) | (man << 13);
+    float f; memcpy(&f, &u, 4); return f;
+}
+static inline uint16_t f32_to_f16(float f) {
+    uint32_t x; memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u, man = x & 0x7fffffu; int32_t exp = (int32_t)((x >> 23) & 0xff);
+    if (exp == 255) return (uint16_t)(sign | 0x7c00u | (man ? (0x200u | (man >> 13)) : 0));
+    int32_t e = exp - 127 + 15;
+    if (e >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        uint32_t shift = (uint32_t)(14 - e);
+        uint32_t half = man >> shift, rem = man & ((1u << shift) - 1), mid = 1u << (shift - 1);
+        if (rem > mid || (rem == mid && (half & 1))) half++;
+        return (uint16_t)(sign | half);
+    }
+    uint32_t half = ((uint32_t)e << 10) | (man >> 13), rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) half++;
+    return (uint16_t)(sign | half);
+}
+
+/* util::map_coord — util.rs:144-147 (operation order preserved) */
+static inline float map_coord(float x, float in_min, float in_max, float out_min, float out_max) {
+    return (x - in_min) * (out_max - out_min) / (in_max - in_min) + out_min;
+}
+
+typedef struct { float x, y; } v2;
+
+/* ------------------------------------------------------------------------------------------
+ * Lens models — distortion_models/ (one .rs per model)
+ * ---------------------------------------------------------------------------------------- */
+#define RS_PI_F 3.14159274101257324f  /* std::f32::consts::PI */
+
+/* opencv_fisheye.rs:12-70 */
+static int fisheye_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    if (k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f) { *o = p; return 1; }
+    const float EPS = 1e-6f;
+    float theta_d = sqrtf(p.x * p.x + p.y * p.y);
+    theta_d = rs_min(rs_max(theta_d, -RS_PI_F), RS_PI_F);
+    int converged = 0;
+    float theta = theta_d, scale = 0.0f;
+    if (fabsf(theta_d) > EPS) {
+        theta = 0.0f;
+        for (int i = 0; i < 10; ++i) {
+            float theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta6 * theta2;
+            float k0_theta2 = k[0] * theta2, k1_theta4 = k[1] * theta4, k2_theta6 = k[2] * theta6, k3_theta8 = k[3] * theta8;
+            float theta_fix = (theta * (1.0f + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d)
+                            / (1.0f + 3.0f * k0_theta2 + 5.0f * k1_theta4 + 7.0f * k2_theta6 + 9.0f * k3_theta8);
+            theta_fix = rs_min(rs_max(theta_fix, -0.9f), 0.9f);
+            theta = theta - theta_fix;
+            if (fabsf(theta_fix) < EPS) { converged = 1; break; }
+        }
+        scale = tanf(theta) / theta_d;
+    } else {
+        converged = 1;
+    }
+    int theta_flipped = (theta_d < 0.0f && theta > 0.0f) || (theta_d > 0.0f && theta < 0.0f);
+    if (converged && !theta_flipped) { o->x = p.x * scale; o->y = p.y * scale; return 1; }
+    return 0;
+}
+/* opencv_fisheye.rs:72-93 */
+static v2 fisheye_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    x = x / z; y = y / z;
+    if (k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f) return (v2){x, y};
+    float r = sqrtf(x * x + y * y);
+    float theta = atanf(r);
+    float theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta4 * theta4;
+    float theta_d = theta * (1.0f + k[0] * theta2 + k[1] * theta4 + k[2] * theta6 + k[3] * theta8);
+    float scale = r == 0.0f ? 1.0f : theta_d / r;
+    return (v2){x * scale, y * scale};
+}
+
+/* opencv_standard.rs:12-30 */
+static int standard_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    float x = p.x, y = p.y, x0 = p.x, y0 = p.y;
+    for (int i = 0; i < 20; ++i) {
+        float r2 = x * x + y * y;
+        float icdist = (1.0f + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1.0f + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0.0f) return 0;
+        float delta_x = 2.0f * k[2] * x * y + k[3] * (r2 + 2.0f * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        float delta_y = k[2] * (r2 + 2.0f * y * y) + 2.0f * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - delta_x) * icdist;
+        y = (y0 - delta_y) * icdist;
+    }
+    o->x = x; o->y = y; return 1;
+}
+/* opencv_standard.rs:32-48 */
+static v2 standard_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    x = x / z; y = y / z;
+    float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    float a1 = 2.0f * x * y, a2 = r2 + 2.0f * x * x, a3 = r2 + 2.0f * y * y;
+    float cdist = 1.0f + k[0] * r2 + k[1] * r4 + k[4] * r6;
+    float icdist2 = 1.0f / (1.0f + k[5] * r2 + k[6] * r4 + k[7] * r6);
+    float xd0 = x * cdist * icdist2 + k[2] * a1 + k[3] * a2 + k[8] * r2 + k[9] * r4;
+    float yd0 = y * cdist * icdist2 + k[2] * a3 + k[3] * a1 + k[10] * r2 + k[11] * r4;
+    return (v2){xd0, yd0};
+}
+
+#define NEWTON_EPS 0.00001f
+/* poly3.rs:14-52 */
+static int poly3_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    float inv_k1 = 1.0f / P->k[0];
+    float rd = sqrtf(p.x * p.x + p.y * p.y);
+    if (rd == 0.0f) return 0;
+    float rd_div_k1 = rd * inv_k1;
+    float ru = rd;
+    for (int i = 0; i < 10; ++i) {
+        float fru = ru * ru * ru + ru * inv_k1 - rd_div_k1;
+        if (fru >= -NEWTON_EPS && fru < NEWTON_EPS) break;
+        if (i > 5) return 0;
+        ru = ru - (fru / (3.0f * ru * ru + inv_k1));
+    }
+    if (ru < 0.0f) return 0;
+    ru = ru / rd;
+    o->x = p.x * ru; o->y = p.y * ru; return 1;
+}
+/* poly3.rs:54-63 */
+static v2 poly3_distort(float x, float y, float z, const gf_kernel_params* P) {
+    x = x / z; y = y / z;
+    float poly2 = P->k[0] * (x * x + y * y) + 1.0f;
+    return (v2){x * poly2, y * poly2};
+}
+/* poly5.rs:14-41 */
+static int poly5_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    float rd = sqrtf(p.x * p.x + p.y * p.y);
+    if (rd == 0.0f) return 0;
+    float ru = rd;
+    for (int i = 0; i < 10; ++i) {
+        float ru2 = ru * ru;
+        float fru = ru * (1.0f + k[0] * ru2 + k[1] * ru2 * ru2) - rd;
+        if (fru >= -NEWTON_EPS && fru < NEWTON_EPS) break;
+        if (i > 5) return 0;
+        ru = ru - (fru / (1.0f + 3.0f * k[0] * ru2 + 5.0f * k[1] * ru2 * ru2));
+    }
+    if (ru < 0.0f) return 0;
+    ru = ru / rd;
+    o->x = p.x * ru; o->y = p.y * ru; return 1;
+}
+/* poly5.rs:43-53 */
+static v2 poly5_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    x = x / z; y = y / z;
+    float ru2 = x * x + y * y;
+    float poly4 = 1.0f + k[0] * ru2 + k[1] * ru2 * ru2;
+    return (v2){x * poly4, y * poly4};
+}
+/* ptlens.rs:14-40 */
+static int ptlens_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    float rd = sqrtf(p.x * p.x + p.y * p.y);
+    if (rd == 0.0f) return 0;
+    float ru = rd;
+    for (int i = 0; i < 10; ++i) {
+        float fru = ru * (k[0] * ru * ru * ru + k[1] * ru * ru + k[2] * ru + 1.0f) - rd;
+        if (fru >= -NEWTON_EPS && fru < NEWTON_EPS) break;
+        if (i > 5) return 0;
+        ru = ru - (fru / (4.0f * k[0] * ru * ru * ru + 3.0f * k[1] * ru * ru + 2.0f * k[2] * ru + 1.0f));
+    }
+    if (ru < 0.0f) return 0;
+    ru = ru / rd;
+    o->x = p.x * ru; o->y = p.y * ru; return 1;
+}
+/* ptlens.rs:42-53 */
+static v2 ptlens_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    x = x / z; y = y / z;
+    float ru2 = x * x + y * y;
+    float r = sqrtf(ru2);
+    float poly3 = k[0] * ru2 * r + k[1] * ru2 + k[2] * r + 1.0f;
+    return (v2){x * poly3, y * poly3};
+}
+/* insta360.rs:27-48 */
+static v2 insta360_distort(float x, float y, float z, const gf_kernel_params* P) {
+    float k1 = P->k[0], k2 = P->k[1], k3 = P->k[2], p1 = P->k[3], p2 = P->k[4], xi = P->k[5];
+    float len = sqrtf(x * x + y * y + z * z);
+    x = (x / len) / ((z / len) + xi);
+    y = (y / len) / ((z / len) + xi);
+    float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    return (v2){
+        x * (1.0f + k1 * r2 + k2 * r4 + k3 * r6) + 2.0f * p1 * x * y + p2 * (r2 + 2.0f * x * x),
+        y * (1.0f + k1 * r2 + k2 * r4 + k3 * r6) + 2.0f * p2 * x * y + p1 * (r2 + 2.0f * y * y)
+    };
+}
+/* insta360.rs:10-25 */
+static int insta360_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    float px = p.x, py = p.y;
+    for (int i = 0; i < 200; ++i) {
+        v2 dp = insta360_distort(px, py, 1.0f, P);
+        float dx = dp.x - p.x, dy = dp.y - p.y;
+        if (fabsf(dx) < 1e-6f && fabsf(dy) < 1e-6f) break;
+        px -= dx; py -= dy;
+    }
+    o->x = px; o->y = py; return 1;
+}
+/* sony.rs:10-63 */
+static int sony_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    if (k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f) { *o = p; return 1; }
+    const float EPS = 1e-6f;
+    float theta_d = sqrtf(p.x * p.x + p.y * p.y);
+    int converged = 0;
+    float theta = theta_d, scale = 0.0f;
+    if (fabsf(theta_d) > EPS) {
+        theta = 0.0f;
+        for (int i = 0; i < 10; ++i) {
+            float theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta2 * theta3;
+            float k0 = k[0], k1_theta1 = k[1] * theta, k2_theta2 = k[2] * theta2, k3_theta3 = k[3] * theta3,
+                  k4_theta4 = k[4] * theta4, k5_theta5 = k[5] * theta5;
+            float theta_fix = (theta * (k0 + k1_theta1 + k2_theta2 + k3_theta3 + k4_theta4 + k5_theta5) - theta_d)
+                            / (k0 + 2.0f * k1_theta1 + 3.0f * k2_theta2 + 4.0f * k3_theta3 + 5.0f * k4_theta4 + 6.0f * k5_theta5);
+            theta = theta - theta_fix;
+            if (fabsf(theta_fix) < EPS) { converged = 1; break; }
+        }
+        scale = tanf(theta) / theta_d;
+    } else {
+        converged = 1;
+    }
+    int theta_flipped = (theta_d < 0.0f && theta > 0.0f) || (theta_d > 0.0f && theta < 0.0f);
+    if (converged && !theta_flipped) { o->x = p.x * scale; o->y = p.y * scale; return 1; }
+    return 0;
+}
+/* sony.rs:65-89 */
+static v2 sony_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    x = x / z; y = y / z;
+    if (k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f) return (v2){x, y};
+    float r = sqrtf(x * x + y * y);
+    float theta = atanf(r);
+    float theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta2 * theta3, theta6 = theta3 * theta3;
+    float theta_d = theta * k[0] + theta2 * k[1] + theta3 * k[2] + theta4 * k[3] + theta5 * k[4] + theta6 * k[5];
+    float scale = r == 0.0f ? 1.0f : theta_d / r;
+    return (v2){x * scale, y * scale};
+}
+static int genpoly_all_zero(const float* k) {
+    for (int i = 0; i < 12; ++i) if (!(k[i] == 0.0f)) return 0;
+    return 1;
+}
+/* generic_polynomial.rs:18-81 */
+static int genpoly_undistort(v2 p, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    if (genpoly_all_zero(k)) { *o = p; return 1; }
+    const float EPS = 1e-6f;
+    float theta_d = sqrtf(p.x * p.x + p.y * p.y);
+    int converged = 0;
+    float theta = theta_d, scale = 0.0f;
+    if (fabsf(theta_d) > EPS) {
+        theta = 0.0f;
+        for (int i = 0; i < 10; ++i) {
+            float theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta2 * theta3,
+                  theta6 = theta3 * theta3, theta7 = theta3 * theta4, theta8 = theta4 * theta4, theta9 = theta4 * theta5,
+                  theta10 = theta5 * theta5, theta11 = theta5 * theta6;
+            float k0 = k[0], k1t = k[1] * theta, k2t = k[2] * theta2, k3t = k[3] * theta3, k4t = k[4] * theta4, k5t = k[5] * theta5,
+                  k6t = k[6] * theta6, k7t = k[7] * theta7, k8t = k[8] * theta8, k9t = k[9] * theta9, k10t = k[10] * theta10, k11t = k[11] * theta11;
+            float theta_fix = (theta * (k0 + k1t + k2t + k3t + k4t + k5t + k6t + k7t + k8t + k9t + k10t + k11t) - theta_d)
+                            / (k0 + 2.0f * k1t + 3.0f * k2t + 4.0f * k3t + 5.0f * k4t + 6.0f * k5t + 7.0f * k6t + 8.0f * k7t + 9.0f * k8t + 10.0f * k9t + 11.0f * k10t + 12.0f * k11t);
+            theta = theta - theta_fix;
+            if (fabsf(theta_fix) < EPS) { converged = 1; break; }
+        }
+        scale = tanf(theta) / theta_d;
+    } else {
+        converged = 1;
+    }
+    int theta_flipped = (theta_d < 0.0f && theta > 0.0f) || (theta_d > 0.0f && theta < 0.0f);
+    if (converged && !theta_flipped) { o->x = p.x * scale; o->y = p.y * scale; return 1; }
+    return 0;
+}
+/* generic_polynomial.rs:83-122 */
+static v2 genpoly_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    x = x / z; y = y / z;
+    if (genpoly_all_zero(k)) return (v2){x, y};
+    float r = sqrtf(x * x + y * y);
+    float theta = atanf(r);
+    float theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta2 * theta3,
+          theta6 = theta3 * theta3, theta7 = theta3 * theta4, theta8 = theta4 * theta4, theta9 = theta4 * theta5,
+          theta10 = theta5 * theta5, theta11 = theta5 * theta6, theta12 = theta6 * theta6;
+    float theta_d = theta * k[0] + theta2 * k[1] + theta3 * k[2] + theta4 * k[3] + theta5 * k[4] + theta6 * k[5]
+                  + theta7 * k[6] + theta8 * k[7] + theta9 * k[8] + theta10 * k[9] + theta11 * k[10] + theta12 * k[11];
+    float scale = r == 0.0f ? 1.0f : theta_d / r;
+    return (v2){x * scale, y * scale};
+}
+/* gopro.rs:19-38 */
+static inline float gopro_poly_eval(float p, const float* k) {
+    return k[0] + p * (k[1] + p * (k[2] + p * (k[3] + p * (k[4] + p * (k[5] + p * k[6])))));
+}
+static inline float gopro_poly_deriv(float p, const float* k) {
+    return k[1] + p * (2.0f * k[2] + p * (3.0f * k[3] + p * (4.0f * k[4] + p * (5.0f * k[5] + p * (6.0f * k[6])))));
+}
+static float gopro_poly_invert(float theta, const float* k) {
+    float p = (theta - k[0]) / k[1];
+    for (int i = 0; i < 10; ++i) {
+        float d = gopro_poly_deriv(p, k);
+        if (fabsf(d) < 1e-12f) break;
+        float fix = (gopro_poly_eval(p, k) - theta) / d;
+        p -= fix;
+        if (fabsf(fix) < 1e-7f) break;
+    }
+    return p;
+}
+#define GOPRO_TMAX 1.5533f
+/* gopro.rs:42-57 */
+static int gopro_undistort(v2 pt, const gf_kernel_params* P, v2* o) {
+    const float* k = P->k;
+    if (k[1] == 0.0f) { *o = pt; return 1; }
+    float r_norm = sqrtf(pt.x * pt.x + pt.y * pt.y);
+    if (r_norm < 1e-9f) { *o = pt; return 1; }
+    float p = r_norm / k[1];
+    float theta = gopro_poly_eval(p, k);
+    float tt = tanf(GOPRO_TMAX);
+    float rr = theta < GOPRO_TMAX ? tanf(theta) : tt + (theta - GOPRO_TMAX) * (1.0f + tt * tt);
+    float scale = rr / r_norm;
+    o->x = pt.x * scale; o->y = pt.y * scale; return 1;
+}
+/* gopro.rs:61-74 */
+static v2 gopro_distort(float x, float y, float z, const gf_kernel_params* P) {
+    const float* k = P->k;
+    v2 pos = {x / z, y / z};
+    if (k[1] == 0.0f) return pos;
+    float r = sqrtf(pos.x * pos.x + pos.y * pos.y);
+    float tt = tanf(GOPRO_TMAX);
+    float theta = r < tt ? atanf(r) : GOPRO_TMAX + (r - tt) / (1.0f + tt * tt);
+    float p = gopro_poly_invert(theta, k);
+    float r_norm = k[1] * p;
+    float scale = r < 1e-9f ? 1.0f : r_norm / r;
+    return (v2){pos.x * scale, pos.y * scale};
+}
+
+/* ---- digital lenses -------------------------------------------------------------------- */
+/* gopro_superview.rs:12-19 */
+static v2 superview_fn(v2 uv) {
+    float x2 = uv.x * uv.x, y2 = uv.y * uv.y;
+    return (v2){
+        uv.x * (1.2100393f + x2 * (-1.2758402f + x2 * 1.7751845f)),
+        uv.y * (0.9364505f + (0.4465308f - 0.7683315f * y2) * y2 + (-0.3574087f + 1.1584653f * y2 + 0.3529348f * x2) * x2)
+    };
+}
+/* gopro6_superview.rs:12-17 */
+static v2 superview6_fn(v2 uv) {
+    uv.x *= 1.0f - 0.48f * fabsf(uv.x);
+    uv.x *= 0.943396f * (1.0f + 0.157895f * fabsf(uv.x));
+    uv.y *= 0.943396f * (1.0f + 0.060000f * fabsf(uv.y * 2.0f));
+    return uv;
+}
+/* gopro_hyperview.rs:10-17 */
+static v2 hyperview_fn(v2 uv) {
+    float x2 = uv.x * uv.x, y2 = uv.y * uv.y;
+    return (v2){
+        uv.x * (1.5805143f + x2 * (-8.1668825f + x2 * (74.5198746f + x2 * (-451.5002441f + x2 * (1551.2922363f + x2 * (-2735.5422363f + x2 * 1923.1572266f))))) + y2 * -0.1086027f),
+        uv.y * (1.0238225f + y2 * -0.1025671f + x2 * (-0.2639930f + x2 * 0.2979266f))
+    };
+}
+/* gopro_warp.rs:22-39 */
+static v2 gopro_map(v2 uv, const float* p) {
+    float x = rs_clamp(uv.x, -0.5f, 0.5f), y = rs_clamp(uv.y, -0.5f, 0.5f);
+    float x2 = x * x, y2 = y * y;
+    float poly_x = p[0] + x2 * (p[1] + x2 * (p[2] + x2 * (p[3] + x2 * (p[4] + x2 * (p[5] + x2 * p[6])))));
+    return (v2){
+        x * (poly_x + p[7] * y2) + (uv.x - x),
+        y * (p[8] + p[9] * y2 + p[10] * y2 * y2 + x2 * (p[11] + p[12] * y2 + p[13] * x2)) + (uv.y - y)
+    };
+}
+
+/* "uv range (0,0)..(width,height)": {superview,superview6,hyperview}.rs undistort_point */
+static int digital_undistort(int model, v2 uv, const gf_kernel_params* P, v2* o) {
+    v2 out_c2 = {(float)P->output_width, (float)P->output_height};
+    switch (model) {
+    case GF_LENS_GOPRO_SUPERVIEW:   /* gopro_superview.rs:23-34 */
+        uv.x = (uv.x / out_c2.x) - 0.5f; uv.y = (uv.y / out_c2.y) - 0.5f;
+        uv = superview_fn(uv);
+        uv.x = uv.x / 1.333333333f;
+        o->x = (uv.x + 0.5f) * out_c2.x; o->y = (uv.y + 0.5f) * out_c2.y; return 1;
+    case GF_LENS_GOPRO6_SUPERVIEW:  /* gopro6_superview.rs:21-30 */
+        uv.x = (uv.x / out_c2.x) - 0.5f; uv.y = (uv.y / out_c2.y) - 0.5f;
+        uv = superview6_fn(uv);
+        o->x = (uv.x + 0.5f) * out_c2.x; o->y = (uv.y + 0.5f) * out_c2.y; return 1;
+    case GF_LENS_GOPRO_HYPERVIEW:   /* gopro_hyperview.rs:21-32 */
+        uv.x = (uv.x / out_c2.x) - 0.5f; uv.y = (uv.y / out_c2.y) - 0.5f;
+        uv = hyperview_fn(uv);
+        uv.x = uv.x / 1.555555555f;
+        o->x = (uv.x + 0.5f) * out_c2.x; o->y = (uv.y + 0.5f) * out_c2.y; return 1;
+    case GF_LENS_GOPRO_WARP: {      /* gopro_warp.rs:43-56 */
+        const float* p = P->digital_lens_params;
+        float factor = p[14] != 0.0f ? p[14] : 1.0f;
+        uv.x = (uv.x / out_c2.x) - 0.5f; uv.y = (uv.y / out_c2.y) - 0.5f;
+        uv = gopro_map(uv, p);
+        uv.x = uv.x / factor;
+        o->x = (uv.x + 0.5f) * out_c2.x; o->y = (uv.y + 0.5f) * out_c2.y; return 1;
+    }
+    case GF_LENS_DIGITAL_STRETCH:   /* digital_stretch.rs:12-15 */
+        o->x = uv.x / P->digital_lens_params[0]; o->y = uv.y / P->digital_lens_params[1]; return 1;
+    default: return -1;
+    }
+}
+typedef v2 (*warp_fn)(v2);
+static v2 fixed_point_invert(warp_fn f, float x, float y) {   /* the 12-iteration loops of *_view.rs distort_point */
+    v2 pp = {x, y};
+    for (int i = 0; i < 12; ++i) {
+        v2 dp = f(pp);
+        float dx = dp.x - x, dy = dp.y - y;
+        if (fabsf(dx) < 1e-6f && fabsf(dy) < 1e-6f) break;
+        pp.x -= dx; pp.y -= dy;
+    }
+    return pp;
+}
+static int digital_distort(int model, float x, float y, const gf_kernel_params* P, v2* o) {
+    v2 size = {(float)P->width, (float)P->height};
+    switch (model) {
+    case GF_LENS_GOPRO_SUPERVIEW: {  /* gopro_superview.rs:38-57 */
+        x = (x / size.x) - 0.5f; y = (y / size.y) - 0.5f;
+        x = x * 1.333333333f;
+        v2 pp = fixed_point_invert(superview_fn, x, y);
+        o->x = (pp.x + 0.5f) * size.x; o->y = (pp.y + 0.5f) * size.y; return 1;
+    }
+    case GF_LENS_GOPRO6_SUPERVIEW: { /* gopro6_superview.rs:34-51 */
+        x = (x / size.x) - 0.5f; y = (y / size.y) - 0.5f;
+        v2 pp = fixed_point_invert(superview6_fn, x, y);
+        o->x = (pp.x + 0.5f) * size.x; o->y = (pp.y + 0.5f) * size.y; return 1;
+    }
+    case GF_LENS_GOPRO_HYPERVIEW: {  /* gopro_hyperview.rs:36-55 */
+        x = (x / size.x) - 0.5f; y = (y / size.y) - 0.5f;
+        x = x * 1.555555555f;
+        v2 pp = fixed_point_invert(hyperview_fn, x, y);
+        o->x = (pp.x + 0.5f) * size.x; o->y = (pp.y + 0.5f) * size.y; return 1;
+    }
+    case GF_LENS_GOPRO_WARP: {       /* gopro_warp.rs:60-94 */
+        const float* p = P->digital_lens_params;
+        float factor = p[14] != 0.0f ? p[14] : 1.0f;
+        x = (x / size.x) - 0.5f; y = (y / size.y) - 0.5f;
+        v2 target = {x * factor, y};
+        v2 pp = {x, y};
+        for (int i = 0; i < 12; ++i) {
+            v2 dp = gopro_map(pp, p);
+            float dx = dp.x - target.x, dy = dp.y - target.y;
+            if (fabsf(dx) < 1e-6f && fabsf(dy) < 1e-6f) break;
+            pp.x -= dx; pp.y -= dy;
+        }
+        v2 res = gopro_map(pp, p);
+        if (fabsf(res.x - target.x) > 0.02f || fabsf(res.y - target.y) > 0.02f) { o->x = -99999.0f; o->y = -99999.0f; return 1; }
+        o->x = (pp.x + 0.5f) * size.x; o->y = (pp.y + 0.5f) * size.y; return 1;
+    }
+    case GF_LENS_DIGITAL_STRETCH:    /* digital_stretch.rs:19-22 */
+        o->x = x * P->digital_lens_params[0]; o->y = y * P->digital_lens_params[1]; return 1;
+    default: return -1;
+    }
+}
+
+/* DistortionModel::undistort_point / distort_point — distortion_models/mod.rs:36-45.
+ * Digital models are also reachable here (the enum does not distinguish). */
+static int lens_undistort(int model, v2 p, const gf_kernel_params* P, v2* o) {
+    switch (model) {
+    case GF_LENS_OPENCV_FISHEYE:     return fisheye_undistort(p, P, o);
+    case GF_LENS_OPENCV_STANDARD:    return standard_undistort(p, P, o);
+    case GF_LENS_POLY3:              return poly3_undistort(p, P, o);
+    case GF_LENS_POLY5:              return poly5_undistort(p, P, o);
+    case GF_LENS_PTLENS:             return ptlens_undistort(p, P, o);
+    case GF_LENS_INSTA360:           return insta360_undistort(p, P, o);
+    case GF_LENS_SONY:               return sony_undistort(p, P, o);
+    case GF_LENS_GENERIC_POLYNOMIAL: return genpoly_undistort(p, P, o);
+    case GF_LENS_GOPRO:              return gopro_undistort(p, P, o);
+    default: { int r = digital_undistort(model, p, P, o); if (r < 0) { *o = p; return 1; } return r; }
+    }
+}
+static v2 lens_distort(int model, float x, float y, float z, const gf_kernel_params* P) {
+    switch (model) {
+    case GF_LENS_OPENCV_FISHEYE:     return fisheye_distort(x, y, z, P);
+    case GF_LENS_OPENCV_STANDARD:    return standard_distort(x, y, z, P);
+    case GF_LENS_POLY3:              return poly3_distort(x, y, z, P);
+    case GF_LENS_POLY5:              return poly5_distort(x, y, z, P);
+    case GF_LENS_PTLENS:             return ptlens_distort(x, y, z, P);
+    case GF_LENS_INSTA360:           return insta360_distort(x, y, z, P);
+    case GF_LENS_SONY:               return sony_distort(x, y, z, P);
+    case GF_LENS_GENERIC_POLYNOMIAL: return genpoly_distort(x, y, z, P);
+    case GF_LENS_GOPRO:              return gopro_distort(x, y, z, P);
+    default: { v2 o = {x, y}; digital_distort(model, x, y, P, &o); return o; }
+    }
+}
+
+int gf_oracle_lens_undistort_point(int model, float x, float y, const gf_kernel_params* P, float* ox, float* oy) {
+    v2 o = {0, 0}; int r = lens_undistort(model, (v2){x, y}, P, &o); *ox = o.x; *oy = o.y; return r;
+}
+void gf_oracle_lens_distort_point(int model, float x, float y, float z, const gf_kernel_params* P, float* ox, float* oy) {
+    v2 o = lens_distort(model, x, y, z, P); *ox = o.x; *oy = o.y;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Mesh correction — gyro_source/splines.rs:88-176, sony.rs:557-563 (all f64)
+ * ---------------------------------------------------------------------------------------- */
+#define MAX_GRID_SIZE 9
+
+/* splines.rs:100-124 */
+static void cubic_spline_coefficients(const double* mesh, size_t step, size_t offset, double size, size_t n,
+                                      double* a, double* b, double* c, double* d, double* alpha, double* mu, double* z) {
+    double h = size / (double)(n - 1);
+    double inv_h = 1.0 / h;
+    double three_inv_h = 3.0 * inv_h;
+    double h_over_3 = h / 3.0;
+    double inv_3h = 1.0 / (3.0 * h);
+    for (size_t i = 0; i < n; ++i) a[i] = mesh[(i + offset) * step];
+    for (size_t i = 1; i + 1 < n; ++i) alpha[i] = three_inv_h * (a[i + 1] - 2.0 * a[i] + a[i - 1]);
+    mu[0] = 0.0; z[0] = 0.0;
+    for (size_t i = 1; i + 1 < n; ++i) {
+        mu[i] = 1.0 / (4.0 - mu[i - 1]);
+        z[i] = (alpha[i] * inv_h - z[i - 1]) * mu[i];
+    }
+    c[n - 1] = 0.0;
+    for (size_t jj = n - 1; jj-- > 0;) {
+        c[jj] = z[jj] - mu[jj] * c[jj + 1];
+        b[jj] = (a[jj + 1] - a[jj]) * inv_h - h_over_3 * (c[jj + 1] + 2.0 * c[jj]);
+        d[jj] = (c[jj + 1] - c[jj]) * inv_3h;
+    }
+}
+void gf_oracle_cubic_spline_coefficients(const double* mesh, size_t step, size_t offset, double size, size_t n,
+                                         double* a, double* b, double* c, double* d) {
+    double alpha[MAX_GRID_SIZE] = {0}, mu[MAX_GRID_SIZE] = {0}, z[MAX_GRID_SIZE] = {0};
+    for (int i = 0; i < MAX_GRID_SIZE; ++i) { a[i] = b[i] = c[i] = d[i] = 0.0; }
+    cubic_spline_coefficients(mesh, step, offset, size, n, a, b, c, d, alpha, mu, z);
+}
+/* splines.rs:126-139 */
+static double cubic_spline_interpolate(const double* a, const double* b, const double* c, const double* d, size_t n, double x, double size) {
+    if (x <= 0.0) return a[0] + b[0] * x;
+    if (x >= size) {
+        double h = size / (double)(n - 1);
+        double slope = b[n - 2] + 2.0 * c[n - 2] * h + 3.0 * d[n - 2] * h * h;
+        return a[n - 1] + slope * (x - size);
+    }
+    size_t i = rs_f64_as_usize(((double)n - 1.0) * x / size);
+    if (i > n - 2) i = n - 2;
+    double dx = x - size * (double)i / (double)(n - 1);
+    return a[i] + b[i] * dx + c[i] * dx * dx + d[i] * dx * dx * dx;
+}
+/* splines.rs:141-176 */
+static double bivariate_interpolate(size_t n_x, size_t n_y, double size_x, double size_y, const double* mesh, size_t mesh_offset, double x, double y) {
+    double iv[MAX_GRID_SIZE] = {0}, a[MAX_GRID_SIZE] = {0}, b[MAX_GRID_SIZE] = {0}, c[MAX_GRID_SIZE] = {0}, d[MAX_GRID_SIZE] = {0};
+    double alpha[MAX_GRID_SIZE] = {0}, mu[MAX_GRID_SIZE] = {0}, z[MAX_GRID_SIZE] = {0};
+    size_t i = rs_f64_as_usize(((double)n_x - 1.0) * x / size_x);
+    if (i > n_x - 2) i = n_x - 2;
+    double dx = x - size_x * (double)i / (double)(n_x - 1);
+    double dx2 = dx * dx;
+    size_t grid = MAX_GRID_SIZE, raw_mesh_len = n_x * n_y * 2, block = grid * 4;
+    size_t coeff_base = 9 + raw_mesh_len + (mesh_offset * n_y * block);
+    size_t offs = coeff_base + i;
+    for (size_t j = 0; j < n_y; ++j) {
+        size_t rb = offs + j * block;
+        iv[j] = mesh[rb + grid * 0] + mesh[rb + grid * 1] * dx + mesh[rb + grid * 2] * dx2 + mesh[rb + grid * 3] * dx2 * dx;
+    }
+    cubic_spline_coefficients(iv, 1, 0, size_y, n_y, a, b, c, d, alpha, mu, z);
+    return cubic_spline_interpolate(a, b, c, d, n_y, y, size_y);
+}
+/* sony.rs:557-563 — size = (mesh[3], mesh[4]) at the call site cpu_undistort.rs:170,179 */
+void gf_oracle_interpolate_mesh(double x, double y, const double* mesh, double* ox, double* oy) {
+    size_t n_x = rs_f64_as_usize(mesh[1]), n_y = rs_f64_as_usize(mesh[2]);
+    *ox = bivariate_interpolate(n_x, n_y, mesh[3], mesh[4], mesh, 0, x, y);
+    *oy = bivariate_interpolate(n_x, n_y, mesh[3], mesh[4], mesh, 1, x, y);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * rotate_and_distort — cpu_undistort.rs:133-228
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const gf_kernel_params* P;
+    const float* matrices;       /* rows x 14 */
+    size_t matrix_rows;
+    int model, digital;          /* digital: GF_LENS_NONE for Option::None */
+    float r_limit_sq;
+    const double* mesh;          /* widened copy, cpu_undistort.rs:539 */
+    size_t mesh_len;
+} warp_ctx;
+
+static int rotate_and_distort(v2 pos, size_t idx, const warp_ctx* W, v2* out) {
+    const gf_kernel_params* P = W->P;
+    const float* m = W->matrices + idx * GF_MATRIX_STRIDE;
+    const double* mesh = W->mesh; const size_t mesh_len = W->mesh_len;
+    float _x = (pos.x * m[0]) + (pos.y * m[1]) + m[2] + P->translation3d[0];
+    float _y = (pos.x * m[3]) + (pos.y * m[4]) + m[5] + P->translation3d[1];
+    float _w = (pos.x * m[6]) + (pos.y * m[7]) + m[8] + P->translation3d[2];
+    if (_w > 0.0f) {
+        if (W->r_limit_sq > 0.0f && (_x * _x + _y * _y) > W->r_limit_sq * _w) return 0;   /* :139 (sic: * _w) */
+
+        if (P->light_refraction_coefficient != 1.0f && P->light_refraction_coefficient > 0.0f) {   /* :143-152 */
+            if (_w != 0.0f) {
+                float r = sqrtf(_x * _x + _y * _y) / _w;
+                float sin_theta_d = (r / sqrtf(1.0f + r * r)) * P->light_refraction_coefficient;
+                float r_d = sin_theta_d / sqrtf(1.0f - sin_theta_d * sin_theta_d);
+                if (r_d != 0.0f) _w *= r / r_d;
+            }
+        }
+
+        v2 uv = lens_distort(W->model, _x, _y, _w, P);           /* :154 */
+        uv.x = uv.x * P->f[0]; uv.y = uv.y * P->f[1];             /* :155 */
+
+        if (m[9] != 0.0f || m[10] != 0.0f || m[11] != 0.0f || m[12] != 0.0f || m[13] != 0.0f) {   /* :157-165 */
+            float ang_rad = m[11];
+            float cos_a = cosf(-ang_rad), sin_a = sinf(-ang_rad);
+            v2 t = { cos_a * uv.x - sin_a * uv.y - m[9]  + m[12],
+                     sin_a * uv.x + cos_a * uv.y - m[10] + m[13] };
+            uv = t;
+        }
+
+        uv.x = uv.x + P->c[0]; uv.y = uv.y + P->c[1];             /* :167 */
+
+        if (mesh_len > 0 && mesh[0] > 10.0) {                      /* :169-185 */
+            float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
+            float crop_w = (float)mesh[7], crop_h = (float)mesh[8];
+            if ((P->flags & 128) == 128) uv.y = (float)P->height - uv.y;
+            uv.x = map_coord(uv.x, 0.0f, (float)P->width,  origin_x, origin_x + crop_w);
+            uv.y = map_coord(uv.y, 0.0f, (float)P->height, origin_y, origin_y + crop_h);
+            double nx, ny;
+            gf_oracle_interpolate_mesh((double)uv.x, (double)uv.y, mesh, &nx, &ny);
+            uv.x = map_coord((float)nx, origin_x, origin_x + crop_w, 0.0f, (float)P->width);
+            uv.y = map_coord((float)ny, origin_y, origin_y + crop_h, 0.0f, (float)P->height);
+            if ((P->flags & 128) == 128) uv.y = (float)P->height - uv.y;
+        }
+
+        /* FocalPlaneDistortion :188-214.  The reference indexes mesh_data[mesh_data[0]] unchecked (would panic
+         * when no FPD block follows); here a missing block simply means "no FPD". */
+        if (mesh_len > 0 && mesh[0] > 0.0 && rs_f64_as_usize(mesh[0]) < mesh_len && mesh[rs_f64_as_usize(mesh[0])] > 0.0) {
+            size_t o = rs_f64_as_usize(mesh[0]);
+            double mesh_size_y = mesh[4];
+            float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
+            float crop_w = (float)mesh[7], crop_h = (float)mesh[8];
+            double stblz_grid = mesh_size_y / 8.0;
+            if ((P->flags & 128) == 128) uv.y = (float)P->height - uv.y;
+            uv.x = map_coord(uv.x, 0.0f, (float)P->width,  origin_x, origin_x + crop_w);
+            uv.y = map_coord(uv.y, 0.0f, (float)P->height, origin_y, origin_y + crop_h);
+            size_t idx2 = rs_f64_as_usize(rs_mind(rs_maxd(floor((double)uv.y / stblz_grid), 0.0), 7.0));
+            double delta = (double)uv.y - stblz_grid * (double)idx2;
+            uv.x -= (float)(mesh[o + 4 + idx2 * 2 + 0] * delta);
+            uv.y -= (float)(mesh[o + 4 + idx2 * 2 + 1] * delta);
+            for (size_t j = 0; j < idx2; ++j) {
+                uv.x -= (float)(mesh[o + 4 + j * 2 + 0] * stblz_grid);
+                uv.y -= (float)(mesh[o + 4 + j * 2 + 1] * stblz_grid);
+            }
+            uv.x = map_coord(uv.x, origin_x, origin_x + crop_w, 0.0f, (float)P->width);
+            uv.y = map_coord(uv.y, origin_y, origin_y + crop_h, 0.0f, (float)P->height);
+            if ((P->flags & 128) == 128) uv.y = (float)P->height - uv.y;
+        }
+
+        if ((P->flags & 2) == 2 && W->digital != GF_LENS_NONE) {   /* :216-220 */
+            uv = lens_distort(W->digital, uv.x, uv.y, 1.0f, P);
+        }
+
+        if (P->input_horizontal_stretch > 0.001f) uv.x /= P->input_horizontal_stretch;   /* :222-223 */
+        if (P->input_vertical_stretch   > 0.001f) uv.y /= P->input_vertical_stretch;
+
+        *out = uv;
+        return 1;
+    }
+    return 0;
+}
+
+/* cpu_undistort.rs:262-265 */
+static v2 rotate_point(v2 pos, float angle, v2 origin, v2 origin2) {
+    return (v2){ cosf(angle) * (pos.x - origin.x) - sinf(angle) * (pos.y - origin.y) + origin2.x,
+                 sinf(angle) * (pos.x - origin.x) + cosf(angle) * (pos.y - origin.y) + origin2.y };
+}
+
+/* undistort_coord — cpu_undistort.rs:421-517 */
+static int undistort_coord(v2 out_pos, const warp_ctx* W, v2 out_c, v2 out_f, v2* result) {
+    const gf_kernel_params* P = W->P;
+    out_pos.x = map_coord(out_pos.x, (float)P->output_rect[0], (float)(P->output_rect[0] + P->output_rect[2]), 0.0f, (float)P->output_width);
+    out_pos.y = map_coord(out_pos.y, (float)P->output_rect[1], (float)(P->output_rect[1] + P->output_rect[3]), 0.0f, (float)P->output_height);
+    out_pos.x += P->translation2d[0];
+    out_pos.y += P->translation2d[1];
+
+    if (P->lens_correction_amount < 1.0f) {                               /* :429-460 */
+        v2 np = out_pos;
+        if ((P->flags & 2) == 2 && W->digital != GF_LENS_NONE) {
+            v2 uz = { (np.x - out_c.x) * P->fov + out_c.x, (np.y - out_c.y) * P->fov + out_c.y };
+            v2 pt;
+            if (lens_undistort(W->digital, uz, P, &pt)) {
+                np.x = (pt.x - out_c.x) / P->fov + out_c.x;
+                np.y = (pt.y - out_c.y) / P->fov + out_c.y;
+            }
+        }
+        np.x = (np.x - out_c.x) / out_f.x; np.y = (np.y - out_c.y) / out_f.y;
+        v2 pt;
+        if (lens_undistort(W->model, np, P, &pt)) np = pt;
+        if (P->light_refraction_coefficient != 1.0f && P->light_refraction_coefficient > 0.0f) {
+            float r = sqrtf(np.x * np.x + np.y * np.y);
+            if (r != 0.0f) {
+                float sin_theta_d = (r / sqrtf(1.0f + r * r)) / P->light_refraction_coefficient;
+                float r_d = sin_theta_d / sqrtf(1.0f - sin_theta_d * sin_theta_d);
+                float factor = r_d / r;
+                np.x *= factor; np.y *= factor;
+            }
+        }
+        np.x = (np.x * out_f.x) + out_c.x; np.y = (np.y * out_f.y) + out_c.y;
+        float ia = 1.0f - P->lens_correction_amount;
+        out_pos.x = np.x * ia + (out_pos.x * P->lens_correction_amount);
+        out_pos.y = np.y * ia + (out_pos.y * P->lens_correction_amount);
+    }
+
+    /* :465-479 rolling-shutter row */
+    const int hrs = (P->flags & 16) == 16;
+    int32_t sy_i = hrs ? rs_f32_as_i32(rs_round(out_pos.x)) : rs_f32_as_i32(rs_round(out_pos.y));
+    { int32_t lim = hrs ? P->width : P->height; if (sy_i > lim) sy_i = lim; if (sy_i < 0) sy_i = 0; }
+    size_t sy = (size_t)sy_i;
+    if (P->matrix_count > 1) {
+        size_t idx = (size_t)P->matrix_count / 2;
+        v2 pt;
+        if (rotate_and_distort(out_pos, idx, W, &pt)) {
+            int32_t v = hrs ? rs_f32_as_i32(rs_round(pt.x)) : rs_f32_as_i32(rs_round(pt.y));
+            int32_t lim = hrs ? P->width : P->height;
+            if (v > lim) v = lim; if (v < 0) v = 0;
+            sy = (size_t)v;
+        }
+    }
+
+    size_t idx = sy; { size_t last = (size_t)P->matrix_count - 1; if (idx > last) idx = last; }   /* :482 */
+    v2 uv;
+    if (!rotate_and_distort(out_pos, idx, W, &uv)) return 0;                                        /* :483 */
+    v2 frame_size = {(float)P->width, (float)P->height};
+    if (P->input_rotation != 0.0f) {                                                                 /* :485-491 */
+        float rotation = P->input_rotation * (RS_PI_F / 180.0f);
+        v2 size = frame_size;
+        frame_size = rotate_point(size, rotation, (v2){0.0f, 0.0f}, (v2){0.0f, 0.0f});
+        frame_size.x = rs_round(fabsf(frame_size.x)); frame_size.y = rs_round(fabsf(frame_size.y));
+        uv = rotate_point(uv, rotation, (v2){size.x / 2.0f, size.y / 2.0f}, (v2){frame_size.x / 2.0f, frame_size.y / 2.0f});
+    }
+
+    float width_f = (float)P->width, height_f = (float)P->height;
+    if (P->background_mode == 1) {                /* edge repeat :495-499 */
+        uv.x = rs_min(rs_max(uv.x, 3.0f), width_f - 3.0f);
+        uv.y = rs_min(rs_max(uv.y, 3.0f), height_f - 3.0f);
+    } else if (P->background_mode == 2) {         /* edge mirror :500-509 */
+        float rx = rs_round(uv.x), ry = rs_round(uv.y);
+        float width3 = width_f - 3.0f, height3 = height_f - 3.0f;
+        if (rx > width3)  uv.x = width3  - (rx - width3);
+        if (rx < 3.0f)    uv.x = 3.0f + width_f - (width3 + rx);
+        if (ry > height3) uv.y = height3 - (ry - height3);
+        if (ry < 3.0f)    uv.y = 3.0f + height_f - (height3 + ry);
+    }
+    if (P->background_mode != 3) {                /* :510-515 */
+        uv.x = map_coord(uv.x, 0.0f, frame_size.x, (float)P->source_rect[0], (float)(P->source_rect[0] + P->source_rect[2]));
+        uv.y = map_coord(uv.y, 0.0f, frame_size.y, (float)P->source_rect[1], (float)(P->source_rect[1] + P->source_rect[3]));
+    }
+    *result = uv;
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Pixel formats — pixel_formats.rs.  (count, scalar kind) is all the kernel needs.
+ * ---------------------------------------------------------------------------------------- */
+enum { SC_U8 = 0, SC_U16 = 1, SC_F32 = 2, SC_F16 = 3 };
+static int pix_layout(int pixel_type, int* count, int* scalar) {
+    switch (pixel_type) {
+    case GF_PIX_LUMA8:   *count = 1; *scalar = SC_U8;  return 1;
+    case GF_PIX_LUMA16:  *count = 1; *scalar = SC_U16; return 1;
+    case GF_PIX_RGB8:    *count = 3; *scalar = SC_U8;  return 1;
+    case GF_PIX_RGBA8:   *count = 4; *scalar = SC_U8;  return 1;
+    case GF_PIX_BGRA8:   *count = 4; *scalar = SC_U8;  return 1;
+    case GF_PIX_RGB16:   *count = 3; *scalar = SC_U16; return 1;
+    case GF_PIX_RGBA16:  *count = 4; *scalar = SC_U16; return 1;
+    case GF_PIX_AYUV16:  *count = 4; *scalar = SC_U16; return 1;
+    case GF_PIX_RGBAF:   *count = 4; *scalar = SC_F32; return 1;
+    case GF_PIX_RGBAF16: *count = 4; *scalar = SC_F16; return 1;
+    case GF_PIX_R32F:    *count = 1; *scalar = SC_F32; return 1;
+    case GF_PIX_UV8:     *count = 2; *scalar = SC_U8;  return 1;
+    case GF_PIX_UV16:    *count = 2; *scalar = SC_U16; return 1;
+    default: return 0;
+    }
+}
+typedef struct { float v[4]; } v4;
+
+static inline v4 pix_to_float(const uint8_t* p, int count, int scalar) {   /* PixelType::to_float */
+    v4 r = {{0.0f, 0.0f, 0.0f, 0.0f}};
+    for (int i = 0; i < count; ++i) {
+        switch (scalar) {
+        case SC_U8:  r.v[i] = (float)p[i]; break;
+        case SC_U16: { uint16_t t; memcpy(&t, p + 2 * i, 2); r.v[i] = (float)t; } break;
+        case SC_F32: { float t; memcpy(&t, p + 4 * i, 4); r.v[i] = t; } break;
+        default:     { uint16_t t; memcpy(&t, p + 2 * i, 2); r.v[i] = f16_to_f32(t); } break;
+        }
+    }
+    return r;
+}
+static inline void pix_from_float(uint8_t* p, v4 val, int count, int scalar) {   /* PixelType::from_float (`as` casts) */
+    for (int i = 0; i < count; ++i) {
+        switch (scalar) {
+        case SC_U8:  p[i] = rs_f32_as_u8(val.v[i]); break;
+        case SC_U16: { uint16_t t = rs_f32_as_u16(val.v[i]); memcpy(p + 2 * i, &t, 2); } break;
+        case SC_F32: { float t = val.v[i]; memcpy(p + 4 * i, &t, 4); } break;
+        default:     { uint16_t t = f32_to_f16(val.v[i]); memcpy(p + 2 * i, &t, 2); } break;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * sample_input_at — cpu_undistort.rs:329-419, separable branch (I <= 8) :370-412.
+ * Bilinear weights: COEFFS[0..64] (cpu_undistort.rs:14-19) are exactly (1 - i/32, i/32).
+ * ---------------------------------------------------------------------------------------- */
+#include "gf_coeffs.inc"   /* generated by oracle/gen_coeffs.py: bicubic + lanczos4 5-bit tables */
+
+static inline const float* coeff_row(int I, uint32_t frac, float* tmp) {
+    if (I == 2) { tmp[0] = 1.0f - (float)frac / 32.0f; tmp[1] = (float)frac / 32.0f; return tmp; }
+    if (I == 4) return &GF_COEFFS_BICUBIC[frac << 2];
+    return &GF_COEFFS_LANCZOS4[frac << 3];
+}
+
+static v4 sample_input_at(int I, v2 uv, const uint8_t* input, size_t in_len, const gf_kernel_params* P, v4 bg, int count, int scalar, int* oob) {
+    v4 sum = {{0.0f, 0.0f, 0.0f, 0.0f}};
+    const float offset = (I == 2) ? 0.0f : (I == 4 ? 1.0f : 3.0f);
+    float u = uv.x - offset, v = uv.y - offset;
+    int32_t sx0 = rs_f32_as_i32(rs_round(u * 32.0f));
+    int32_t sy0 = rs_f32_as_i32(rs_round(v * 32.0f));
+    int32_t sx = sx0 >> 5, sy = sy0 >> 5;
+    float tx[2], ty[2];
+    const float* coeffs_x = coeff_row(I, (uint32_t)sx0 & 31u, tx);
+    const float* coeffs_y = coeff_row(I, (uint32_t)sy0 & 31u, ty);
+    int64_t src_index = (int64_t)sy * (int64_t)P->stride + (int64_t)sx * (int64_t)P->bytes_per_pixel;
+    for (int yp = 0; yp < I; ++yp) {
+        if (sy + yp >= P->source_rect[1] && sy + yp < P->source_rect[1] + P->source_rect[3]) {
+            v4 xsum = {{0.0f, 0.0f, 0.0f, 0.0f}};
+            for (int xp = 0; xp < I; ++xp) {
+                v4 pixel;
+                if (sx + xp >= P->source_rect[0] && sx + xp < P->source_rect[0] + P->source_rect[2]) {
+                    int64_t off = src_index + (int64_t)P->bytes_per_pixel * xp;
+                    if (off < 0 || (uint64_t)off + (uint64_t)P->bytes_per_pixel > in_len) { *oob = 1; pixel = bg; }   /* Rust: slice index panic */
+                    else pixel = pix_to_float(input + off, count, scalar);
+                } else {
+                    pixel = bg;
+                }
+                for (int ch = 0; ch < 4; ++ch) xsum.v[ch] += pixel.v[ch] * coeffs_x[xp];
+            }
+            for (int ch = 0; ch < 4; ++ch) sum.v[ch] += xsum.v[ch] * coeffs_y[yp];
+        } else {
+            for (int ch = 0; ch < 4; ++ch) sum.v[ch] += bg.v[ch] * coeffs_y[yp];
+        }
+        src_index += P->stride;
+    }
+    for (int ch = 0; ch < 4; ++ch) sum.v[ch] = rs_min(sum.v[ch], P->pixel_value_limit);
+    return sum;
+}
+
+/* cpu_undistort.rs:255-260 */
+static void remap_colorrange(v4* px, int is_y) {
+    float s = is_y ? 0.85882352f : 0.87843137f;
+    for (int ch = 0; ch < 4; ++ch) px->v[ch] *= s;
+    px->v[0] += 16.0f;
+    px->v[1] += 16.0f;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * undistort_image_cpu — cpu_undistort.rs:233-633 (main loop 519-633)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t* in; size_t in_len;
+    uint8_t* out; size_t out_len;
+    warp_ctx W;
+    int count, scalar, I;
+    size_t rows;
+    int tid, nthreads;
+    int oob;
+} job_t;
+
+#define ROW_CHUNK 8
+
+static void process_row(job_t* J, size_t y) {
+    const gf_kernel_params* P = J->W.P;
+    const size_t ostride = (size_t)P->output_stride;
+    const size_t bpp = (size_t)P->bytes_per_pixel;
+    size_t row_off = y * ostride;
+    size_t row_len = J->out_len - row_off; if (row_len > ostride) row_len = ostride;
+    size_t npix = row_len / bpp;   /* a trailing partial chunk cannot hold a pixel */
+    uint8_t* row = J->out + row_off;
+
+    v4 bg; for (int ch = 0; ch < 4; ++ch) bg.v[ch] = P->background[ch] * P->max_pixel_value;   /* :523 */
+    const float factor = rs_max(1.0f - P->lens_correction_amount, 0.001f);                       /* :526 */
+    const v2 out_c = {(float)P->output_width / 2.0f, (float)P->output_height / 2.0f};            /* :527 */
+    const v2 out_f = {P->f[0] / P->fov / factor, P->f[1] / P->fov / factor};                     /* :528 */
+    const int fill_bg = (P->flags & 4) == 4, fix_range = (P->flags & 1) == 1, is_y = P->plane_index == 0;
+
+    for (size_t x = 0; x < npix; ++x) {
+        float opx = map_coord((float)x, (float)P->output_rect[0], (float)(P->output_rect[0] + P->output_rect[2]), 0.0f, (float)P->output_width);
+        float opy = map_coord((float)y, (float)P->output_rect[1], (float)(P->output_rect[1] + P->output_rect[3]), 0.0f, (float)P->output_height);
+        if (opx >= 0.0f && opy >= 0.0f && rs_f32_as_i32(opx) < P->output_width && rs_f32_as_i32(opy) < P->output_height) {   /* :551 */
+            v4 pixel = bg;
+            uint8_t* pix_out = row + x * bpp;
+            if (fill_bg) { pix_from_float(pix_out, bg, J->count, J->scalar); continue; }          /* :558-561 */
+            v2 position = {(float)x, (float)y};
+            v2 uv;
+            if (undistort_coord(position, &J->W, out_c, out_f, &uv)) {                            /* :565 */
+                float width_f = (float)P->width, height_f = (float)P->height;
+                if (P->background_mode == 3) {                                                     /* :576-613 */
+                    float widthf = width_f - 1.0f, heightf = height_f - 1.0f;
+                    float feather = rs_max(P->background_margin_feather * heightf, 0.0001f);
+                    v2 pt2 = uv;
+                    float alpha = 1.0f;
+                    if ((uv.x > widthf - feather) || (uv.x < feather) || (uv.y > heightf - feather) || (uv.y < feather)) {
+                        alpha = rs_max(rs_min(rs_min(rs_min(rs_min(widthf - uv.x, heightf - uv.y), uv.x), uv.y) / feather, 1.0f), 0.0f);
+                        pt2.x = pt2.x / width_f; pt2.y = pt2.y / height_f;
+                        pt2.x = ((pt2.x - 0.5f) * (1.0f - P->background_margin)) + 0.5f;
+                        pt2.y = ((pt2.y - 0.5f) * (1.0f - P->background_margin)) + 0.5f;
+                        pt2.x = pt2.x * width_f; pt2.y = pt2.y * height_f;
+                    }
+                    v2 frame_size = {(float)P->width, (float)P->height};
+                    if (P->input_rotation != 0.0f) {
+                        float rotation = P->input_rotation * (RS_PI_F / 180.0f);
+                        v2 size = frame_size;
+                        frame_size = rotate_point(size, rotation, (v2){0.0f, 0.0f}, (v2){0.0f, 0.0f});
+                        frame_size.x = rs_round(fabsf(frame_size.x)); frame_size.y = rs_round(fabsf(frame_size.y));
+                    }
+                    float sx0 = (float)P->source_rect[0], sx1 = (float)(P->source_rect[0] + P->source_rect[2]);
+                    float sy0 = (float)P->source_rect[1], sy1 = (float)(P->source_rect[1] + P->source_rect[3]);
+                    uv.x  = map_coord(uv.x,  0.0f, frame_size.x, sx0, sx1); uv.y  = map_coord(uv.y,  0.0f, frame_size.y, sy0, sy1);
+                    pt2.x = map_coord(pt2.x, 0.0f, frame_size.x, sx0, sx1); pt2.y = map_coord(pt2.y, 0.0f, frame_size.y, sy0, sy1);
+                    v4 c1 = sample_input_at(J->I, uv,  J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);
+                    v4 c2 = sample_input_at(J->I, pt2, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);
+                    for (int ch = 0; ch < 4; ++ch) pixel.v[ch] = c1.v[ch] * alpha + c2.v[ch] * (1.0f - alpha);
+                    if (fix_range) remap_colorrange(&pixel, is_y);
+                    pix_from_float(pix_out, pixel, J->count, J->scalar);
+                    continue;
+                }
+                pixel = sample_input_at(J->I, uv, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);   /* :615 */
+            }
+            if (fix_range) remap_colorrange(&pixel, is_y);                                         /* :619-621 */
+            pix_from_float(pix_out, pixel, J->count, J->scalar);                                   /* :622 */
+        }
+    }
+}
+
+static void* worker(void* arg) {
+    job_t* J = (job_t*)arg;
+    /* rows dealt round-robin in chunks of ROW_CHUNK (rayon par_chunks_mut is row-granular, :543) */
+    for (size_t base = (size_t)J->tid * ROW_CHUNK; base < J->rows; base += (size_t)J->nthreads * ROW_CHUNK) {
+        size_t end = base + ROW_CHUNK; if (end > J->rows) end = J->rows;
+        for (size_t y = base; y < end; ++y) process_row(J, y);
+    }
+    return NULL;
+}
+
+int gf_oracle_online_cpus(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+const char* gf_oracle_describe(void) {
+    return "gyroflow CPU oracle (C restatement of cpu_undistort.rs @ b5e8828; libm transcendentals; parity unpinned)";
+}
+
+int gf_oracle_undistort_image(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
+                              const gf_kernel_params* P, int pixel_type, int distortion_model, int digital_lens,
+                              const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len, int threads) {
+    int count, scalar;
+    if (!in || !out || !P || !matrices) return GF_ERR_BAD_PARAMS;
+    if (!pix_layout(pixel_type, &count, &scalar)) return GF_ERR_BAD_PARAMS;
+    static const int scalar_bytes[4] = {1, 2, 4, 2};
+    if (P->bytes_per_pixel != count * scalar_bytes[scalar]) return GF_ERR_BAD_PARAMS;          /* assert_eq! :541 */
+    if (P->output_stride <= 0 || P->stride <= 0) return GF_ERR_BAD_STRIDE;                      /* :534-537 */
+    if (P->matrix_count < 1 || (size_t)P->matrix_count > matrix_rows) return GF_ERR_BAD_PARAMS; /* matrices[idx] would panic */
+    const int I = P->interpolation;
+    if (!(I == 2 || I == 4 || I == 8)) return GF_ERR_UNSUPPORTED_COMBO;                         /* EWA (I > 8): not restated yet */
+    if (distortion_model <= GF_LENS_NONE || distortion_model >= GF_LENS_COUNT) return GF_ERR_BAD_PARAMS;
+    if (digital_lens < 0 || digital_lens >= GF_LENS_COUNT) return GF_ERR_BAD_PARAMS;
+
+    double* mesh64 = NULL;
+    if (mesh && mesh_len) {
+        mesh64 = (double*)malloc(mesh_len * sizeof(double));
+        if (!mesh64) return GF_ERR_BAD_PARAMS;
+        for (size_t i = 0; i < mesh_len; ++i) mesh64[i] = (double)mesh[i];                       /* :539 */
+    }
+
+    int nthreads = threads > 0 ? threads : gf_oracle_online_cpus();
+    size_t rows = (out_len + (size_t)P->output_stride - 1) / (size_t)P->output_stride;
+    if ((size_t)nthreads > (rows + ROW_CHUNK - 1) / ROW_CHUNK) nthreads = (int)((rows + ROW_CHUNK - 1) / ROW_CHUNK);
+    if (nthreads < 1) nthreads = 1;
+
+    job_t* jobs = (job_t*)calloc((size_t)nthreads, sizeof(job_t));
+    pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    for (int t = 0; t < nthreads; ++t) {
+        job_t* J = &jobs[t];
+        J->in = in; J->in_len = in_len; J->out = out; J->out_len = out_len;
+        J->W.P = P; J->W.matrices = matrices; J->W.matrix_rows = matrix_rows;
+        J->W.model = distortion_model; J->W.digital = digital_lens;
+        J->W.r_limit_sq = P->r_limit * P->r_limit;                                                /* :521 */
+        J->W.mesh = mesh64; J->W.mesh_len = mesh64 ? mesh_len : 0;
+        J->count = count; J->scalar = scalar; J->I = I; J->rows = rows; J->tid = t; J->nthreads = nthreads;
+    }
+    if (nthreads == 1) worker(&jobs[0]);
+    else {
+        for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, &jobs[t]);
+        for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    }
+    int oob = 0; for (int t = 0; t < nthreads; ++t) oob |= jobs[t].oob;
+    free(jobs); free(th); free(mesh64);
+    return oob ? GF_ERR_BUFFER_TOO_SMALL : GF_OK;
+}
+
+int gf_oracle_rotate_and_distort(float x, float y, size_t idx, const gf_kernel_params* P, const float* matrices,
+                                 int distortion_model, int digital_lens, const float* mesh, size_t mesh_len, float* ou, float* ov) {
+    double mesh64[GF_MESH_MAX_LEN];
+    if (mesh_len > GF_MESH_MAX_LEN) mesh_len = GF_MESH_MAX_LEN;
+    for (size_t i = 0; i < mesh_len; ++i) mesh64[i] = (double)mesh[i];
+    warp_ctx W = { P, matrices, (size_t)P->matrix_count, distortion_model, digital_lens, P->r_limit * P->r_limit, mesh64, mesh ? mesh_len : 0 };
+    v2 o = {0, 0};
+    int r = rotate_and_distort((v2){x, y}, idx, &W, &o);
+    *ou = o.x; *ov = o.y; return r;
+}
+
+int gf_oracle_undistort_coord(float x, float y, const gf_kernel_params* P, const float* matrices,
+                              int distortion_model, int digital_lens, const float* mesh, size_t mesh_len, float* ou, float* ov) {
+    double mesh64[GF_MESH_MAX_LEN];
+    if (mesh_len > GF_MESH_MAX_LEN) mesh_len = GF_MESH_MAX_LEN;
+    for (size_t i = 0; i < mesh_len; ++i) mesh64[i] = (double)mesh[i];
+    warp_ctx W = { P, matrices, (size_t)P->matrix_count, distortion_model, digital_lens, P->r_limit * P->r_limit, mesh64, mesh ? mesh_len : 0 };
+    const float factor = rs_max(1.0f - P->lens_correction_amount, 0.001f);
+    const v2 out_c = {(float)P->output_width / 2.0f, (float)P->output_height / 2.0f};
+    const v2 out_f = {P->f[0] / P->fov / factor, P->f[1] / P->fov / factor};
+    v2 o = {0, 0};
+    int r = undistort_coord((v2){x, y}, &W, out_c, out_f, &o);
+    *ou = o.x; *ov = o.y; return r;
+}

@@ -1,0 +1,70 @@
+/* gf_oracle.h — CPU oracle for Gyroflow's per-pixel warp.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, line-by-line restatement of the reference's CPU path
+ * (src/core/stabilization/cpu_undistort.rs and the files it calls).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+ * load this library; the product (libgyroflow_cuda.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no test, golden vector or fixture for this path
+ * (its only test module is src/ui/ui_tools.rs:294+) and its Rust sources cannot be built
+ * in this image (no rustc/cargo).  The oracle is therefore pinned only by (a) review
+ * against the cited lines, (b) analytical known-answer cases (identity warp, pure
+ * translation, forward/inverse lens round trips) in tests/, and (c) an independent numpy
+ * restatement of the fisheye + rolling-shutter + bilinear path (tests/np_restatement.py).
+ *
+ * Float semantics mirrored from Rust: f32 ops are IEEE with no FMA contraction (build
+ * with -ffp-contract=off), `as` casts truncate + saturate + NaN->0, f32::round is
+ * half-away-from-zero, f32::max/min ignore NaN, and transcendental functions are the
+ * platform libm's atanf/tanf/sinf/cosf — exactly what Rust's std calls on Linux.
+ */
+#ifndef GF_ORACLE_H
+#define GF_ORACLE_H
+
+#include "../include/gyroflow_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* undistort_image_cpu<I, T>  — cpu_undistort.rs:233-633.
+ * in/out are the Cpu buffers; out is only written where the reference writes.
+ * `threads` <= 0 means all online cores (rayon's default pool), rows are dealt in chunks.
+ * Returns 0 on success, <0 on invalid arguments (the reference would panic or return false). */
+int gf_oracle_undistort_image(const uint8_t* in, size_t in_len,
+                              uint8_t* out, size_t out_len,
+                              const gf_kernel_params* params, int pixel_type,
+                              int distortion_model, int digital_lens,
+                              const float* matrices, size_t matrix_rows,
+                              const float* mesh, size_t mesh_len,
+                              int threads);
+
+/* DistortionModel::{undistort_point, distort_point} — distortion_models/mod.rs:36-45.
+ * undistort returns 1 for Some, 0 for None. */
+int  gf_oracle_lens_undistort_point(int model, float x, float y, const gf_kernel_params* params, float* ox, float* oy);
+void gf_oracle_lens_distort_point(int model, float x, float y, float z, const gf_kernel_params* params, float* ox, float* oy);
+
+/* Stabilization::rotate_and_distort — cpu_undistort.rs:133-228 (mesh given as f32, widened like :539).
+ * Returns 1 for Some. */
+int gf_oracle_rotate_and_distort(float x, float y, size_t idx, const gf_kernel_params* params,
+                                 const float* matrices, int distortion_model, int digital_lens,
+                                 const float* mesh, size_t mesh_len, float* ou, float* ov);
+
+/* undistort_coord — cpu_undistort.rs:421-517.  Returns 1 for Some. */
+int gf_oracle_undistort_coord(float x, float y, const gf_kernel_params* params,
+                              const float* matrices, int distortion_model, int digital_lens,
+                              const float* mesh, size_t mesh_len, float* ou, float* ov);
+
+/* interpolate_mesh — gyro_source/sony.rs:557-563 + splines.rs:100-176 (f64). */
+void gf_oracle_interpolate_mesh(double x, double y, const double* mesh, double* ox, double* oy);
+/* cubic_spline_coefficients over one grid row — splines.rs:100-124; used by tests to build meshes
+ * the way sony.rs:500-511 does.  a,b,c,d have 9 entries. */
+void gf_oracle_cubic_spline_coefficients(const double* mesh, size_t step, size_t offset, double size, size_t n,
+                                         double* a, double* b, double* c, double* d);
+
+int gf_oracle_online_cpus(void);
+const char* gf_oracle_describe(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,71 @@
+"""ctypes access to the CPU oracle (oracle/libgf_oracle.so).  TESTS / smoke / cpu_baseline ONLY — never the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gyroflow_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "libgf_oracle.so")
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    src_m = max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("gf_oracle.c", "gf_oracle.h", "gf_coeffs.inc"))
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < src_m:
+        build()
+    lib = C.CDLL(LIB)
+    P = C.POINTER
+    lib.gf_oracle_undistort_image.restype = C.c_int
+    lib.gf_oracle_undistort_image.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, P(abi.KernelParams), C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    lib.gf_oracle_lens_undistort_point.restype = C.c_int
+    lib.gf_oracle_lens_undistort_point.argtypes = [C.c_int, C.c_float, C.c_float, P(abi.KernelParams), P(C.c_float), P(C.c_float)]
+    lib.gf_oracle_lens_distort_point.restype = None
+    lib.gf_oracle_lens_distort_point.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, P(abi.KernelParams), P(C.c_float), P(C.c_float)]
+    lib.gf_oracle_rotate_and_distort.restype = C.c_int
+    lib.gf_oracle_rotate_and_distort.argtypes = [C.c_float, C.c_float, C.c_size_t, P(abi.KernelParams), C.c_void_p, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_size_t, P(C.c_float), P(C.c_float)]
+    lib.gf_oracle_undistort_coord.restype = C.c_int
+    lib.gf_oracle_undistort_coord.argtypes = [C.c_float, C.c_float, P(abi.KernelParams), C.c_void_p, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_size_t, P(C.c_float), P(C.c_float)]
+    lib.gf_oracle_interpolate_mesh.restype = None
+    lib.gf_oracle_interpolate_mesh.argtypes = [C.c_double, C.c_double, C.c_void_p, P(C.c_double), P(C.c_double)]
+    lib.gf_oracle_online_cpus.restype = C.c_int
+    lib.gf_oracle_describe.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def undistort_image(src, dst, params, pixel_type, lens, digital_lens, matrices, mesh=None, threads=0):
+    """Run the oracle in place on `dst` (numpy uint8, C-contiguous).  Returns the oracle's status code."""
+    lib = load()
+    m = np.ascontiguousarray(matrices, dtype=np.float32)
+    mesh = np.zeros(0, np.float32) if mesh is None else np.ascontiguousarray(mesh, dtype=np.float32)
+    assert src.dtype == np.uint8 and dst.dtype == np.uint8 and src.flags["C_CONTIGUOUS"] and dst.flags["C_CONTIGUOUS"]
+    return lib.gf_oracle_undistort_image(src.ctypes.data, src.nbytes, dst.ctypes.data, dst.nbytes, C.byref(params),
+                                         abi.PIXEL_TYPES[pixel_type][0], abi.LENS[lens], abi.LENS[digital_lens] if digital_lens else 0,
+                                         m.ctypes.data, m.shape[0], mesh.ctypes.data if mesh.size else None, mesh.size, threads)
+
+
+def distort_point(lens, x, y, z, params):
+    lib = load(); ox, oy = C.c_float(), C.c_float()
+    lib.gf_oracle_lens_distort_point(abi.LENS[lens], x, y, z, C.byref(params), C.byref(ox), C.byref(oy))
+    return ox.value, oy.value
+
+
+def undistort_point(lens, x, y, params):
+    lib = load(); ox, oy = C.c_float(), C.c_float()
+    ok = lib.gf_oracle_lens_undistort_point(abi.LENS[lens], x, y, C.byref(params), C.byref(ox), C.byref(oy))
+    return (ox.value, oy.value) if ok else None

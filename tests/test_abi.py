@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: the ABI struct, the exported symbols, host-side validation."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gyroflow_b200 as g
+from gyroflow_b200 import abi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_kernel_params_layout():
+    assert C.sizeof(abi.KernelParams) == 368
+    off = {n: getattr(abi.KernelParams, n).offset for n, _ in abi.KernelParams._fields_}
+    assert off["background"] == 48 and off["f"] == 64 and off["k"] == 80 and off["fov"] == 128
+    assert off["translation3d"] == 176 and off["source_rect"] == 192 and off["digital_lens_params"] == 224
+    assert off["max_pixel_value"] == 304 and off["pixel_value_limit"] == 316 and off["ewa_coeffs_q"] == 352
+
+
+def test_library_exports_every_declared_symbol():
+    lib = g.load_library()            # raises if the .so is missing or a symbol is absent
+    header = open(os.path.join(ROOT, "include", "gyroflow_cuda.h")).read()
+    declared = set(re.findall(r"GF_API\s+[\w\s\*]+?\b(gf_\w+)\s*\(", header))
+    bound = {n for n, _, _ in abi.EXPORTS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_lens_plugin_surface():
+    lib = g.load_library()
+    for name, idx in abi.LENS.items():
+        if idx:
+            assert lib.gf_lens_from_name(name.encode()) == idx
+            assert lib.gf_lens_name(idx).decode() == name
+    assert lib.gf_lens_from_name(b"no_such_model") == abi.LENS["opencv_fisheye"]    # DistortionModel::from_name default
+    for name, (idx, count, sdt) in abi.PIXEL_TYPES.items():
+        assert lib.gf_pixel_bytes(idx) == count * np.dtype(sdt).itemsize
+    # the 21 (lens, digital) pairs the reference pre-compiles (qt_gpu/compiled/compile_shaders.sh:6-27)
+    pairs = [("opencv_fisheye", d) for d in (None, "gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch")]
+    pairs += [("gopro", None), ("gopro", "gopro_warp")]
+    pairs += [(l, d) for l in ("opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony", "generic_polynomial") for d in (None, "digital_stretch")]
+    assert len(pairs) == 21
+    for lens, dig in pairs:
+        for pix, (pid, _, _) in abi.PIXEL_TYPES.items():
+            assert lib.gf_combo_supported(pid, abi.LENS[lens], abi.LENS[dig] if dig else 0, 2) == 1, (lens, dig, pix)
+    assert lib.gf_combo_supported(3, abi.LENS["poly3"], abi.LENS["gopro_superview"], 2) == 0
+
+
+def test_validation_happens_before_any_cuda_call():
+    """SizeTooSmall / InvalidStride / unsupported combos are reported even without a GPU (stabilization/mod.rs:613-640)."""
+    p = synth.base_kernel_params(64, 36)
+    src = np.zeros((36, p.stride), np.uint8); dst = np.zeros((36, p.output_stride), np.uint8)
+    bufs = g.Buffers(g.BufferDescription((64, 36, p.stride), src), g.BufferDescription((64, 36, p.output_stride), dst))
+    with pytest.raises(g.GyroflowCoreError) as e:
+        g.CudaWrapper.new(p, "RGBA8", "poly3", "gopro_superview", bufs)
+    assert e.value.kind == "UnsupportedCombo"
+    p2 = p.copy(); p2.stride = 0
+    with pytest.raises(g.GyroflowCoreError) as e:
+        g.CudaWrapper.new(p2, "RGBA8", "opencv_fisheye", None, bufs)
+    assert e.value.kind == "InvalidStride"
+    tiny = g.Buffers(g.BufferDescription((64, 3, p.stride), src), g.BufferDescription((64, 36, p.output_stride), dst))
+    with pytest.raises(g.GyroflowCoreError) as e:
+        g.CudaWrapper.new(p, "RGBA8", "opencv_fisheye", None, tiny)
+    assert e.value.kind == "SizeTooSmall"
+
+
+def test_no_cpu_fallback_without_a_gpu(gpu_available):
+    if gpu_available:
+        pytest.skip("a GPU is present; the fallback question does not arise")
+    p = synth.base_kernel_params(64, 36)
+    src = np.zeros((36, p.stride), np.uint8); dst = np.zeros((36, p.output_stride), np.uint8)
+    bufs = g.Buffers(g.BufferDescription((64, 36, p.stride), src), g.BufferDescription((64, 36, p.output_stride), dst))
+    with pytest.raises(g.GyroflowCoreError) as e:
+        g.CudaWrapper.new(p, "RGBA8", "opencv_fisheye", None, bufs)
+    assert e.value.kind == "CudaError"          # fails loudly; nothing is computed on the CPU
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(g.BackendMissing):
+        abi.load_library(str(tmp_path / "libgyroflow_cuda.so"))

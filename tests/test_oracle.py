@@ -1,0 +1,109 @@
+"""CPU-only checks of the oracle itself (parity is unpinned by the reference: it has no tests for this path,
+so the oracle is pinned by analytical known answers + committed self-generated golden CRCs)."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from gyroflow_b200 import abi, synth
+from tests import cases, oracle_lib
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_crc.json")
+
+
+def run_oracle(case, threads=0):
+    p, src, m, mesh, dst, pix, lens, digital = cases.build(case)
+    rc = oracle_lib.undistort_image(src, dst, p, pix, lens, digital, m, mesh, threads)
+    return rc, p, src, dst
+
+
+def test_identity_warp_is_a_copy():
+    # no distortion (k = 0), fov = 1, identity rotation  =>  every in-bounds pixel maps onto itself
+    for pix in ("RGBA8", "Luma16", "R32f", "UV8", "RGB8", "RGBAf16"):
+        case = dict(w=97, h=53, pix=pix, identity=True, rs=False, stride_pad=5 if pix in ("RGBA8", "RGB8") else 0,
+                    params=dict(k=[0.0] * 12))
+        rc, p, src, dst = run_oracle(case)
+        assert rc == 0
+        bpp = p.bytes_per_pixel
+        assert np.array_equal(dst[:, : 97 * bpp], src[:, : 97 * bpp]), pix
+        assert (dst[:, 97 * bpp:] == 0xA5).all()          # stride padding untouched
+
+
+def test_pure_translation():
+    # translation2d shifts the sampling position by whole pixels: out(x, y) = in(x + 3, y + 2), background outside
+    case = dict(w=64, h=48, pix="Luma8", identity=True, rs=False, params=dict(k=[0.0] * 12, translation2d=[3.0, 2.0]))
+    rc, p, src, dst = run_oracle(case)
+    assert rc == 0
+    assert np.array_equal(dst[:46, :61], src[2:48, 3:64])
+    assert (dst[46:, :64] == 0).all() and (dst[:, 61:64] == 0).all()
+
+
+def test_fill_with_background():
+    case = dict(w=32, h=16, pix="RGBA8", identity=True, rs=False, flags=abi.FLAG_FILL_WITH_BACKGROUND,
+                params=dict(background=[0.25, 0.5, 1.0, 2.0]))
+    rc, p, src, dst = run_oracle(case)
+    assert rc == 0
+    assert (dst[:, : 32 * 4].reshape(16, 32, 4) == np.array([63, 127, 255, 255], np.uint8)).all()   # trunc + saturate
+
+
+@pytest.mark.parametrize("lens", ["opencv_fisheye", "opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony",
+                                  "generic_polynomial", "gopro"])
+def test_lens_roundtrip(lens):
+    # distort(undistort(p)) ~= p inside the valid field of view
+    p = synth.base_kernel_params(1920, 1080, lens=lens)
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for _ in range(200):
+        x, y = rng.uniform(-0.6, 0.6, 2)
+        u = oracle_lib.undistort_point(lens, float(x), float(y), p)
+        assert u is not None
+        d = oracle_lib.distort_point(lens, u[0], u[1], 1.0, p)
+        worst = max(worst, abs(d[0] - x), abs(d[1] - y))
+    assert worst < (2e-3 if lens in ("poly3", "poly5", "ptlens") else 2e-4), worst
+
+
+@pytest.mark.parametrize("digital", ["gopro_superview", "gopro6_superview", "gopro_hyperview", "gopro_warp", "digital_stretch"])
+def test_digital_lens_roundtrip(digital):
+    p = synth.base_kernel_params(1920, 1080, lens="gopro" if digital == "gopro_warp" else "opencv_fisheye", digital_lens=digital)
+    rng = np.random.default_rng(2)
+    for _ in range(100):
+        x, y = rng.uniform(0.2, 0.8) * 1920, rng.uniform(0.2, 0.8) * 1080
+        d = oracle_lib.distort_point(digital, float(x), float(y), 1.0, p)
+        u = oracle_lib.undistort_point(digital, d[0], d[1], p)
+        assert abs(u[0] - x) < 0.05 and abs(u[1] - y) < 0.05
+
+
+def test_thread_count_does_not_change_output():
+    case = dict(w=320, h=180)
+    _, _, _, d1 = run_oracle(case, threads=1)
+    _, _, _, d8 = run_oracle(case, threads=8)
+    assert np.array_equal(d1, d8)
+
+
+def golden_cases():
+    base = dict(w=160, h=90)
+    out = {
+        "cfg1_fisheye_rsoff_identity": dict(base, identity=True, rs=False),
+        "cfg2_fisheye_rs": dict(base),
+        "cfg3_luma16_superview": dict(base, pix="Luma16", digital="gopro_superview", fov=1.1),
+        "cfg4_r32f_sony_ibis_mesh": dict(base, pix="R32f", lens="sony", ibis=True, mesh=True),
+        "bicubic": dict(base, interp="Bicubic"),
+        "lanczos4": dict(base, interp="Lanczos4"),
+        "chroma_rects": dict(w=160, h=90, pix="UV8", in_size=(80, 45), out_size=(80, 45)),
+        "lens_correction_half": dict(base, params=dict(lens_correction_amount=0.5)),
+        "edge_mirror_rot": dict(base, params=dict(background_mode=2, input_rotation=7.0)),
+    }
+    for lens in ("opencv_standard", "poly3", "poly5", "ptlens", "insta360", "generic_polynomial", "gopro"):
+        out["lens_" + lens] = dict(base, lens=lens)
+    return out
+
+
+def test_golden_crcs():
+    """Self-generated KATs (tests/golden/make_golden.py): guards the oracle against accidental edits."""
+    want = json.load(open(GOLDEN))
+    for name, case in golden_cases().items():
+        rc, p, src, dst = run_oracle(case)
+        assert rc == 0, name
+        assert zlib.crc32(dst.tobytes()) == want[name], name

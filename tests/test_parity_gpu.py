@@ -1,0 +1,222 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Every test here needs a real B200 (`-m gpu`).  A missing GPU or a missing libgyroflow_cuda.so is a FAILURE,
+never a skip: there is no fallback path to test instead.
+"""
+import numpy as np
+import pytest
+
+import gyroflow_b200 as g
+from gyroflow_b200 import abi, synth
+from tests import cases, oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(case, device_buffers=False):
+    p, src, m, mesh, dst0, pix, lens, digital = cases.build(case)
+    want = dst0.copy()
+    rc = oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh)
+    assert rc == 0, "oracle rc %d" % rc
+    got = dst0.copy()
+    bw, bh = case.get("in_size", (case["w"], case["h"]))
+    obw, obh = case.get("out_size", (case.get("ow", case["w"]), case.get("oh", case["h"])))
+    itm = g.FrameTransform(matrices=m, kernel_params=p, mesh_data=mesh if mesh is not None else np.zeros(0, np.float32))
+    if not device_buffers:
+        bufs = g.Buffers(g.BufferDescription((bw, bh, p.stride), src), g.BufferDescription((obw, obh, p.output_stride), got))
+        w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+        w.undistort_image(bufs, itm)
+        assert w.launch_count == 1
+        w.close()
+    else:
+        import torch
+        tsrc = torch.from_numpy(src).cuda()
+        tdst = torch.from_numpy(got).cuda()
+        bufs = g.Buffers(g.BufferDescription((bw, bh, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
+                         g.BufferDescription((obw, obh, p.output_stride), tdst.data_ptr(), length=tdst.numel()))
+        w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+        w.undistort_image(bufs, itm, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = tdst.cpu().numpy()
+        w.close()
+    return want, got, pix
+
+
+def assert_bit_exact(case, **kw):
+    want, got, pix = run_both(case, **kw)
+    n, mx = cases.compare(want, got, pix)
+    assert n == 0, "%d mismatching bytes (max abs diff %s) for %r" % (n, mx, case)
+    assert (want != 0xA5).any()     # the oracle really wrote something
+
+
+def test_device_present():
+    assert g.load_library().gf_cuda_device_count() > 0
+    assert g.list_devices()[0].startswith("[CUDA] ")
+
+
+# ---- BASELINE configs at reduced size (full size: test_full_size_*) --------------------------------------
+def test_cfg1_fisheye_rs_off_identity():
+    assert_bit_exact(dict(w=640, h=360, identity=True, rs=False))
+
+
+def test_cfg2_fisheye_rolling_shutter():
+    assert_bit_exact(dict(w=640, h=360))
+    assert_bit_exact(dict(w=640, h=360, ts=2345.6))
+
+
+def test_cfg3_luma16_superview_planes():
+    assert_bit_exact(dict(w=960, h=540, pix="Luma16", digital="gopro_superview", fov=1.07))
+    # 4:2:2 chroma plane: half-width buffer with source/output rect scaling (stabilization/mod.rs:230-231)
+    assert_bit_exact(dict(w=960, h=540, pix="Luma16", digital="gopro_superview", fov=1.07, in_size=(480, 540), out_size=(480, 540)))
+
+
+def test_cfg4_f32_sony_ibis_mesh():
+    for pix in ("R32f", "RGBAf"):
+        assert_bit_exact(dict(w=480, h=270, pix=pix, lens="sony", ibis=True, mesh=True))
+    assert_bit_exact(dict(w=480, h=270, pix="R32f", lens="sony", ibis=True, mesh=True, fpd=True))
+
+
+# ---- lens-model plugins ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("lens", ["opencv_fisheye", "opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony",
+                                  "generic_polynomial", "gopro"])
+def test_every_lens_model(lens):
+    assert_bit_exact(dict(w=320, h=180, lens=lens))
+    assert_bit_exact(dict(w=320, h=180, lens=lens, digital="gopro_warp" if lens == "gopro" else "digital_stretch"))
+    # lens_correction_amount < 1 exercises undistort_point (Newton solvers, tanf)
+    assert_bit_exact(dict(w=320, h=180, lens=lens, params=dict(lens_correction_amount=0.35)))
+
+
+@pytest.mark.parametrize("digital", ["gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch"])
+def test_fisheye_digital_lenses(digital):
+    assert_bit_exact(dict(w=320, h=180, digital=digital))
+    assert_bit_exact(dict(w=320, h=180, digital=digital, params=dict(lens_correction_amount=0.5)))
+
+
+# ---- pixel formats ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pix", sorted(abi.PIXEL_TYPES))
+def test_every_pixel_format(pix):
+    assert_bit_exact(dict(w=200, h=120, pix=pix))
+    assert_bit_exact(dict(w=203, h=117, pix=pix, stride_pad=3))       # odd size, unaligned stride -> byte path
+
+
+# ---- ragged / edge geometry ------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(4, 4), (5, 7), (33, 9), (31, 65), (257, 131), (1000, 4)])
+def test_small_and_odd_sizes(w, h):
+    assert_bit_exact(dict(w=w, h=h))
+    assert_bit_exact(dict(w=w, h=h, identity=True, rs=False, stride_pad=1))
+
+
+def test_output_size_differs_from_input():
+    assert_bit_exact(dict(w=640, h=360, ow=480, oh=270))
+    assert_bit_exact(dict(w=320, h=240, ow=640, oh=360, pix="Luma8"))
+
+
+def test_rects():
+    assert_bit_exact(dict(w=320, h=180, in_size=(400, 200), in_rect=(40, 10, 320, 180)))
+    assert_bit_exact(dict(w=320, h=180, out_size=(400, 220), out_rect=(30, 20, 320, 180)))      # untouched border must survive
+    assert_bit_exact(dict(w=320, h=180, pix="UV8", in_size=(160, 90), out_size=(160, 90)))      # NV12 chroma plane
+
+
+# ---- per-frame features ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_background_modes(mode):
+    prm = dict(background_mode=mode, background=[0.1, 0.4, 0.7, 1.0])
+    if mode == 3:
+        prm.update(background_margin=0.2, background_margin_feather=0.1)
+    assert_bit_exact(dict(w=320, h=180, fov=1.6, params=prm))
+
+
+def test_background_colour_and_zoomed_out():
+    assert_bit_exact(dict(w=320, h=180, fov=2.2, params=dict(background=[0.2, 0.4, 0.6, 1.0])))
+
+
+def test_input_rotation_and_video_rotation():
+    assert_bit_exact(dict(w=320, h=180, params=dict(input_rotation=90.0)))
+    assert_bit_exact(dict(w=320, h=180, params=dict(input_rotation=-13.5, background_mode=2)))
+    assert_bit_exact(dict(w=320, h=180, video_rotation=25.0))
+
+
+def test_horizontal_rolling_shutter():
+    assert_bit_exact(dict(w=320, h=180, horizontal_rs=True))
+
+
+def test_light_refraction_and_r_limit():
+    assert_bit_exact(dict(w=320, h=180, params=dict(light_refraction_coefficient=1.33)))
+    assert_bit_exact(dict(w=320, h=180, params=dict(light_refraction_coefficient=1.33, lens_correction_amount=0.6)))
+    assert_bit_exact(dict(w=320, h=180, fov=2.5, params=dict(r_limit=0.9)))
+
+
+def test_fix_color_range_and_fill_background():
+    assert_bit_exact(dict(w=320, h=180, pix="Luma8", flags=abi.FLAG_FIX_COLOR_RANGE))
+    assert_bit_exact(dict(w=320, h=180, pix="UV8", flags=abi.FLAG_FIX_COLOR_RANGE, params=dict(plane_index=1)))
+    assert_bit_exact(dict(w=320, h=180, flags=abi.FLAG_FILL_WITH_BACKGROUND, params=dict(background=[0.3, 0.6, 0.9, 1.0])))
+
+
+def test_input_stretch_and_translation():
+    assert_bit_exact(dict(w=320, h=180, params=dict(input_horizontal_stretch=1.3333, input_vertical_stretch=0.9, translation2d=[4.5, -3.25])))
+
+
+def test_ibis_and_mesh_on_u8():
+    assert_bit_exact(dict(w=320, h=180, ibis=True))
+    assert_bit_exact(dict(w=320, h=180, mesh=True, fpd=True, flags=abi.FLAG_FRAMEBUFFER_INVERTED))
+
+
+# ---- buffer sources --------------------------------------------------------------------------------------
+def test_device_buffers_cuda_buffer_source():
+    assert_bit_exact(dict(w=640, h=360), device_buffers=True)
+    assert_bit_exact(dict(w=203, h=117, pix="RGB8", stride_pad=3), device_buffers=True)
+
+
+# ---- full BASELINE sizes ---------------------------------------------------------------------------------
+def test_full_size_cfg2_4k_rgba8():
+    assert_bit_exact(dict(w=3840, h=2160))
+
+
+def test_full_size_cfg3_8k_luma16():
+    assert_bit_exact(dict(w=7680, h=4320, pix="Luma16", digital="gopro_superview", fov=1.05))
+
+
+# ---- size-independent properties at full size ------------------------------------------------------------
+def test_property_frame_sharding_is_order_independent():
+    """Frames are independent units: warping frames in any order / on a reused context gives identical bytes."""
+    case = dict(w=1920, h=1080)
+    p, src, m, mesh, dst0, pix, lens, digital = cases.build(case)
+    bufs = lambda d: g.Buffers(g.BufferDescription((1920, 1080, p.stride), src), g.BufferDescription((1920, 1080, p.output_stride), d))
+    w = g.CudaWrapper.new(p, pix, lens, digital, bufs(dst0))
+    org, sm = cases.gyro()
+    outs = {}
+    for ts in (500.0, 1500.0, 500.0, 2500.0, 1500.0):
+        mm = synth.frame_matrices(p, org, sm, ts)
+        d = dst0.copy()
+        w.undistort_image(bufs(d), g.FrameTransform(matrices=mm, kernel_params=p))
+        if ts in outs:
+            assert np.array_equal(outs[ts], d)
+        outs[ts] = d
+    assert not np.array_equal(outs[500.0], outs[1500.0])
+    w.close()
+
+
+# ---- error behaviour (mirrors GyroflowCoreError) ---------------------------------------------------------
+def test_errors():
+    p, src, m, mesh, dst, pix, lens, digital = cases.build(dict(w=64, h=36))
+    bufs = g.Buffers(g.BufferDescription((64, 36, p.stride), src), g.BufferDescription((64, 36, p.output_stride), dst))
+    with pytest.raises(g.GyroflowCoreError) as e:
+        g.CudaWrapper.new(p, pix, "poly3", "gopro_superview", bufs)          # pair the reference never builds
+    assert e.value.kind == "UnsupportedCombo"
+    small = g.Buffers(g.BufferDescription((64, 3, p.stride), src), g.BufferDescription((64, 36, p.output_stride), dst))
+    with pytest.raises(g.GyroflowCoreError) as e:
+        g.CudaWrapper.new(p, pix, lens, digital, small)
+    assert e.value.kind == "SizeTooSmall"
+    w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+    p2 = p.copy(); p2.width = 65
+    with pytest.raises(g.GyroflowCoreError) as e:
+        w.undistort_image(bufs, g.FrameTransform(matrices=m, kernel_params=p2))
+    assert e.value.kind == "SizeMismatch"
+    p3 = p.copy(); p3.source_rect[:] = [0, 0, 64, 400]
+    with pytest.raises(g.GyroflowCoreError) as e:
+        w.undistort_image(bufs, g.FrameTransform(matrices=m, kernel_params=p3))
+    assert e.value.kind == "BufferTooSmall"
+    with pytest.raises(g.GyroflowCoreError) as e:
+        w.undistort_image(bufs, g.FrameTransform(matrices=m[:10], kernel_params=p))
+    assert e.value.kind == "BufferTooSmall"
+    w.close()
