@@ -32,7 +32,7 @@ import numpy as np
 
 W, H = 3840, 2160
 PIX, LENS = "RGBA8", "opencv_fisheye"
-FRAMES_PER_STEP = 32
+FRAMES_PER_STEP = 128
 RING = 8                 # 8 x 33.2 MB input frames = 265 MB > 126 MB L2
 N_TIMESTAMPS = 32        # distinct matrix tables
 METRIC = "4K frames/sec (fisheye+RS warp)"
@@ -53,7 +53,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -172,7 +172,10 @@ def main():
         return g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
                          g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel()))
     ctx = g.CudaWrapper.new(p, PIX, LENS, None, dbufs(0), device=local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: kernels, CUDA events and the timed region all live on it
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+    assert stream != 0
     all_bufs = [dbufs(i) for i in range(RING)]
 
     def step(s):
@@ -180,6 +183,7 @@ def main():
             i = s * FRAMES_PER_STEP + j
             ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows, stream=stream)
 
+    torch.cuda.synchronize()
     for s in range(args.warmup):
         step(s)
     torch.cuda.synchronize()
@@ -189,9 +193,9 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     for s in range(args.steps):
-        ev[s][0].record()
+        ev[s][0].record(tstream)
         step(s)
-        ev[s][1].record()
+        ev[s][1].record(tstream)
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)

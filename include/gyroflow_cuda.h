@@ -224,8 +224,9 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx);
 /* ---- run: OclWrapper::undistort_image opencl.rs:330 / WgpuWrapper::undistort_image wgpu.rs:454
  * `params`, `matrices`, `mesh`, `drawing` are HOST pointers (they come out of FrameTransform).
  * HOST image buffers: H2D -> kernel -> D2H -> stream sync before return (opencl.rs:359,413).
- * DEVICE image buffers: everything is enqueued on `cu_stream` (NULL = the ctx's own stream) and the
- * call returns without synchronising. */
+ * DEVICE image buffers: everything is enqueued on `cu_stream` and the call returns without synchronising.
+ * `cu_stream` is a CUstream/cudaStream_t handle; NULL selects the context's own non-blocking stream (NOT the
+ * legacy default stream — pass cudaStreamLegacy (0x1) or cudaStreamPerThread (0x2) to name those explicitly). */
 GF_API int gf_cuda_undistort_image(gf_cuda_ctx* ctx,
                                    const gf_buffer_desc* in, const gf_buffer_desc* out,
                                    const gf_kernel_params* params,

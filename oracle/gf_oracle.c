@@ -923,9 +923,10 @@ typedef struct {
     size_t rows;
     int tid, nthreads;
     int oob;
+    size_t* next_row;   /* shared cursor: chunks of ROW_CHUNK rows are claimed dynamically (rayon splits work adaptively too) */
 } job_t;
 
-#define ROW_CHUNK 8
+#define ROW_CHUNK 4
 
 static void process_row(job_t* J, size_t y) {
     const gf_kernel_params* P = J->W.P;
@@ -993,8 +994,10 @@ static void process_row(job_t* J, size_t y) {
 
 static void* worker(void* arg) {
     job_t* J = (job_t*)arg;
-    /* rows dealt round-robin in chunks of ROW_CHUNK (rayon par_chunks_mut is row-granular, :543) */
-    for (size_t base = (size_t)J->tid * ROW_CHUNK; base < J->rows; base += (size_t)J->nthreads * ROW_CHUNK) {
+    /* rows are claimed in chunks of ROW_CHUNK from a shared cursor (rayon par_chunks_mut is row-granular, :543) */
+    for (;;) {
+        size_t base = __atomic_fetch_add(J->next_row, (size_t)ROW_CHUNK, __ATOMIC_RELAXED);
+        if (base >= J->rows) break;
         size_t end = base + ROW_CHUNK; if (end > J->rows) end = J->rows;
         for (size_t y = base; y < end; ++y) process_row(J, y);
     }
@@ -1033,6 +1036,7 @@ int gf_oracle_undistort_image(const uint8_t* in, size_t in_len, uint8_t* out, si
     if ((size_t)nthreads > (rows + ROW_CHUNK - 1) / ROW_CHUNK) nthreads = (int)((rows + ROW_CHUNK - 1) / ROW_CHUNK);
     if (nthreads < 1) nthreads = 1;
 
+    size_t next_row = 0;
     job_t* jobs = (job_t*)calloc((size_t)nthreads, sizeof(job_t));
     pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
     for (int t = 0; t < nthreads; ++t) {
@@ -1042,7 +1046,7 @@ int gf_oracle_undistort_image(const uint8_t* in, size_t in_len, uint8_t* out, si
         J->W.model = distortion_model; J->W.digital = digital_lens;
         J->W.r_limit_sq = P->r_limit * P->r_limit;                                                /* :521 */
         J->W.mesh = mesh64; J->W.mesh_len = mesh64 ? mesh_len : 0;
-        J->count = count; J->scalar = scalar; J->I = I; J->rows = rows; J->tid = t; J->nthreads = nthreads;
+        J->count = count; J->scalar = scalar; J->I = I; J->rows = rows; J->tid = t; J->nthreads = nthreads; J->next_row = &next_row;
     }
     if (nthreads == 1) worker(&jobs[0]);
     else {

@@ -35,8 +35,10 @@ def run_both(case, device_buffers=False):
         bufs = g.Buffers(g.BufferDescription((bw, bh, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
                          g.BufferDescription((obw, obh, p.output_stride), tdst.data_ptr(), length=tdst.numel()))
         w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
-        w.undistort_image(bufs, itm, stream=torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        torch.cuda.synchronize()                     # uploads done before the side stream starts
+        w.undistort_image(bufs, itm, stream=side.cuda_stream)
+        side.synchronize()
         got = tdst.cpu().numpy()
         w.close()
     return want, got, pix
