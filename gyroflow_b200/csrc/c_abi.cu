@@ -11,6 +11,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <cmath>
+#include <algorithm>
 #include <string>
 
 #include "kernel_registry.h"
@@ -124,6 +126,91 @@ int validate(gf_cuda_ctx* ctx, const gf_kernel_params* p, const gf_buffer_desc* 
     }
     if (out->len == 0) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "empty output buffer");
     return GF_OK;
+}
+
+// map_coord's per-frame-uniform pieces (util.rs:144-147), same float operations as the reference evaluates per pixel
+MapC make_map(float in_min, float in_max, float out_min, float out_max, float max_abs_int_coord) {
+    MapC m;
+    m.in_min = in_min;
+    m.mul = out_max - out_min;
+    m.div = in_max - in_min;
+    m.rcp = 1.0f / m.div;
+    m.add = out_min;
+    const float ad = fabsf(m.div);
+    m.fast_div = (std::isfinite(m.div) && ad >= 0x1p-40f && ad <= 0x1p40f) ? 1 : 0;
+    // integer-valued x: (x - in_min) and (x - in_min) * mul are exact below 2^24, and exact / div == (x - in_min) when mul == div
+    m.identity = (max_abs_int_coord >= 0.0f && m.mul == m.div && m.mul > 0.0f && in_min == truncf(in_min) &&
+                  (max_abs_int_coord + fabsf(in_min)) * m.mul < 16777216.0f) ? 1 : 0;
+    return m;
+}
+
+bool lens_noop(int lens, const gf_kernel_params* p) {
+    const float* k = p->k;
+    switch (lens) {
+    case GF_LENS_OPENCV_FISHEYE:
+    case GF_LENS_SONY:               return k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f;
+    case GF_LENS_GENERIC_POLYNOMIAL: { for (int i = 0; i < 12; ++i) if (!(k[i] == 0.0f)) return false; return true; }
+    case GF_LENS_GOPRO:              return k[1] == 0.0f;
+    default: return false;
+    }
+}
+
+// Everything the reference recomputes per pixel from per-frame constants (cpu_undistort.rs:421-528), computed once, on the
+// host, with the same IEEE float operations (this TU is built with -ffp-contract=off; sin/cos come from gf_math.cuh, the
+// same code the device runs).
+void fill_uniforms(WarpArgs& A, const gf_cuda_ctx* ctx, const uint8_t* src, const uint8_t* dst) {
+    const gf_kernel_params* p = &A.p;
+    const int bpp = ctx->bpp;
+    const int align = (bpp == 1 || bpp == 2 || bpp == 4 || bpp == 8 || bpp == 16) ? bpp : (bpp == 3 ? 1 : 2);
+    uint32_t f = 0;
+    if (p->matrix_count > 1) f |= F_RS;
+    if ((p->flags & 16) == 16) f |= F_HRS;
+    A.r_limit_sq = p->r_limit * p->r_limit;                                      // :521
+    if (A.r_limit_sq > 0.0f) f |= F_RLIMIT;
+    if (p->light_refraction_coefficient != 1.0f && p->light_refraction_coefficient > 0.0f) f |= F_REFRACT;
+    if (A.mesh_len > 0) f |= F_MESH;
+    if ((p->flags & 2) == 2 && ctx->digital_lens != GF_LENS_NONE) f |= F_DIGITAL;
+    if (p->input_horizontal_stretch > 0.001f && p->input_horizontal_stretch != 1.0f) f |= F_HSTRETCH;
+    if (p->input_vertical_stretch   > 0.001f && p->input_vertical_stretch   != 1.0f) f |= F_VSTRETCH;
+    if (p->lens_correction_amount < 1.0f) f |= F_LCA;
+    if (p->input_rotation != 0.0f) f |= F_INROT;
+    if (p->background_mode == 1) f |= F_BG1;
+    if (p->background_mode == 2) f |= F_BG2;
+    if (p->background_mode == 3) f |= F_BG3;
+    if ((p->flags & 1) == 1) f |= F_FIXRANGE;
+    if ((p->flags & 4) == 4) f |= F_FILLBG;
+    if (lens_noop(ctx->distortion_model, p)) f |= F_LENS_NOOP;
+    if ((reinterpret_cast<uintptr_t>(src) % (uintptr_t)align) == 0 && (p->stride % align) == 0) f |= F_SRC_VEC;
+    if ((reinterpret_cast<uintptr_t>(dst) % (uintptr_t)align) == 0 && (p->output_stride % align) == 0) f |= F_DST_VEC;
+    if ((p->flags & 128) == 128) f |= F_FB_INV;
+    if (p->plane_index == 0) f |= F_IS_Y;
+    if (p->translation3d[0] != 0.0f || p->translation3d[1] != 0.0f || p->translation3d[2] != 0.0f) f |= F_T3D;
+    A.feat = f;
+
+    for (int i = 0; i < 4; ++i) A.bg[i] = p->background[i] * p->max_pixel_value;  // :523
+    const float factor = fmaxf(1.0f - p->lens_correction_amount, 0.001f);         // :526
+    A.out_c[0] = (float)p->output_width / 2.0f; A.out_c[1] = (float)p->output_height / 2.0f;   // :527
+    A.out_f[0] = p->f[0] / p->fov / factor;      A.out_f[1] = p->f[1] / p->fov / factor;        // :528
+
+    A.width_f = (float)p->width; A.height_f = (float)p->height;
+    A.frame_w = A.width_f; A.frame_h = A.height_f;
+    A.rot_cos = 1.0f; A.rot_sin = 0.0f;
+    if (p->input_rotation != 0.0f) {                                              // :485-489 (rotate_point :262-265)
+        const float rotation = p->input_rotation * (3.14159274101257324f / 180.0f);
+        A.rot_cos = gf_cosf(rotation); A.rot_sin = gf_sinf(rotation);
+        const float fx = A.rot_cos * (A.width_f - 0.0f) - A.rot_sin * (A.height_f - 0.0f) + 0.0f;
+        const float fy = A.rot_sin * (A.width_f - 0.0f) + A.rot_cos * (A.height_f - 0.0f) + 0.0f;
+        A.frame_w = rs_round(fabsf(fx)); A.frame_h = rs_round(fabsf(fy));
+    }
+    A.omap_x = make_map((float)p->output_rect[0], (float)(p->output_rect[0] + p->output_rect[2]), 0.0f, (float)p->output_width,  (float)A.out_cols);
+    A.omap_y = make_map((float)p->output_rect[1], (float)(p->output_rect[1] + p->output_rect[3]), 0.0f, (float)p->output_height, (float)A.out_rows);
+    A.smap_x = make_map(0.0f, A.frame_w, (float)p->source_rect[0], (float)(p->source_rect[0] + p->source_rect[2]), -1.0f);
+    A.smap_y = make_map(0.0f, A.frame_h, (float)p->source_rect[1], (float)(p->source_rect[1] + p->source_rect[3]), -1.0f);
+    A.rs_lim = (p->flags & 16) == 16 ? p->width : p->height;
+    const float lim = p->pixel_value_limit;
+    A.u8_limit = (lim != lim) ? 255 : (lim < 0.0f ? 0 : (lim >= 255.0f ? 255 : (int)lim));
+    A.src_rect[0] = p->source_rect[0]; A.src_rect[1] = p->source_rect[1];
+    A.src_rect[2] = p->source_rect[0] + p->source_rect[2]; A.src_rect[3] = p->source_rect[1] + p->source_rect[3];
 }
 
 } // namespace
@@ -292,14 +379,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const int bpp = ctx->bpp;
     A.out_rows = (int)((out->len + (size_t)p->output_stride - 1) / (size_t)p->output_stride);
     A.out_cols = p->output_stride / bpp;
-    A.src_vec_ok = ((reinterpret_cast<uintptr_t>(src) % (uintptr_t)bpp) == 0 && (p->stride % bpp) == 0) ? 1 : 0;
-    A.dst_vec_ok = ((reinterpret_cast<uintptr_t>(dst) % (uintptr_t)bpp) == 0 && (p->output_stride % bpp) == 0) ? 1 : 0;
-    // cpu_undistort.rs:521-528, same float operations
-    A.r_limit_sq = p->r_limit * p->r_limit;
-    for (int i = 0; i < 4; ++i) A.bg[i] = p->background[i] * p->max_pixel_value;
-    const float factor = fmaxf(1.0f - p->lens_correction_amount, 0.001f);
-    A.out_c[0] = (float)p->output_width / 2.0f; A.out_c[1] = (float)p->output_height / 2.0f;
-    A.out_f[0] = p->f[0] / p->fov / factor;      A.out_f[1] = p->f[1] / p->fov / factor;
+    fill_uniforms(A, ctx, src, dst);
 
     const dim3 block(GF_BLOCK_X, GF_BLOCK_Y);
     const dim3 grid((A.out_cols + GF_BLOCK_X - 1) / GF_BLOCK_X, (A.out_rows + GF_BLOCK_Y - 1) / GF_BLOCK_Y);

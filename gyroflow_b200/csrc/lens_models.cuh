@@ -2,8 +2,10 @@
 //
 // Behavioural source: src/core/stabilization/distortion_models/<model>.rs (gyroflow @ b5e8828).
 // Each model M provides
-//     bool lens_undistort<M>(px, py, P, &ox, &oy)   <- DistortionModel::undistort_point (Option -> bool)
-//     void lens_distort<M>(x, y, z, P, &ox, &oy)    <- DistortionModel::distort_point
+//     bool Lens<M>::undistort(px, py, P, noop, &ox, &oy)   <- DistortionModel::undistort_point (Option -> bool)
+//     void Lens<M>::distort(x, y, z, P, noop, &ox, &oy)    <- DistortionModel::distort_point
+// `noop` is the model's own "all coefficients are zero -> identity" test (fisheye/sony: k0..k3 == 0, generic
+// polynomial: k0..k11 == 0, gopro: k1 == 0), evaluated once per launch on the host instead of once per pixel.
 // Operation order inside every expression follows the Rust source so that, with -fmad=false,
 // results are bit-identical to the CPU path.  `P` is the 368-byte KernelParams living in the
 // kernel's constant parameter bank, so k[]/f[]/c[] reads are uniform-register loads.
@@ -19,9 +21,9 @@ template <int M> struct Lens;   // primary template intentionally undefined
 
 // ---- opencv_fisheye.rs ---------------------------------------------------------------------
 template <> struct Lens<GF_LENS_OPENCV_FISHEYE> {
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :12-70
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :12-70
         const float k0 = P.k[0], k1 = P.k[1], k2 = P.k[2], k3 = P.k[3];
-        if (k0 == 0.0f && k1 == 0.0f && k2 == 0.0f && k3 == 0.0f) { ox = px; oy = py; return true; }
+        if (noop) { ox = px; oy = py; return true; }
         const float EPS = 1e-6f;
         const float PI_F = 3.14159274101257324f;
         float theta_d = sqrtf(px * px + py * py);
@@ -47,10 +49,10 @@ template <> struct Lens<GF_LENS_OPENCV_FISHEYE> {
         if (converged && !theta_flipped) { ox = px * scale; oy = py * scale; return true; }
         return false;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :72-93
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :72-93
         const float k0 = P.k[0], k1 = P.k[1], k2 = P.k[2], k3 = P.k[3];
         x = x / z; y = y / z;
-        if (k0 == 0.0f && k1 == 0.0f && k2 == 0.0f && k3 == 0.0f) { ox = x; oy = y; return; }
+        if (noop) { ox = x; oy = y; return; }
         const float r = sqrtf(x * x + y * y);
         const float theta = gf_atanf(r);
         const float theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta4 * theta4;
@@ -62,7 +64,7 @@ template <> struct Lens<GF_LENS_OPENCV_FISHEYE> {
 
 // ---- opencv_standard.rs --------------------------------------------------------------------
 template <> struct Lens<GF_LENS_OPENCV_STANDARD> {
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :12-30
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :12-30
         const float* k = P.k;
         float x = px, y = py;
         const float x0 = px, y0 = py;
@@ -77,7 +79,7 @@ template <> struct Lens<GF_LENS_OPENCV_STANDARD> {
         }
         ox = x; oy = y; return true;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :32-48
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :32-48
         const float* k = P.k;
         x = x / z; y = y / z;
         const float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
@@ -92,7 +94,7 @@ template <> struct Lens<GF_LENS_OPENCV_STANDARD> {
 #define GF_NEWTON_EPS 0.00001f
 // ---- poly3.rs ------------------------------------------------------------------------------
 template <> struct Lens<GF_LENS_POLY3> {
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :14-52
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :14-52
         const float inv_k1 = 1.0f / P.k[0];
         const float rd = sqrtf(px * px + py * py);
         if (rd == 0.0f) return false;
@@ -108,7 +110,7 @@ template <> struct Lens<GF_LENS_POLY3> {
         ru = ru / rd;
         ox = px * ru; oy = py * ru; return true;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :54-63
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :54-63
         x = x / z; y = y / z;
         const float poly2 = P.k[0] * (x * x + y * y) + 1.0f;
         ox = x * poly2; oy = y * poly2;
@@ -116,7 +118,7 @@ template <> struct Lens<GF_LENS_POLY3> {
 };
 // ---- poly5.rs ------------------------------------------------------------------------------
 template <> struct Lens<GF_LENS_POLY5> {
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :14-41
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :14-41
         const float k0 = P.k[0], k1 = P.k[1];
         const float rd = sqrtf(px * px + py * py);
         if (rd == 0.0f) return false;
@@ -132,7 +134,7 @@ template <> struct Lens<GF_LENS_POLY5> {
         ru = ru / rd;
         ox = px * ru; oy = py * ru; return true;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :43-53
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :43-53
         x = x / z; y = y / z;
         const float ru2 = x * x + y * y;
         const float poly4 = 1.0f + P.k[0] * ru2 + P.k[1] * ru2 * ru2;
@@ -141,7 +143,7 @@ template <> struct Lens<GF_LENS_POLY5> {
 };
 // ---- ptlens.rs -----------------------------------------------------------------------------
 template <> struct Lens<GF_LENS_PTLENS> {
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :14-40
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :14-40
         const float k0 = P.k[0], k1 = P.k[1], k2 = P.k[2];
         const float rd = sqrtf(px * px + py * py);
         if (rd == 0.0f) return false;
@@ -156,7 +158,7 @@ template <> struct Lens<GF_LENS_PTLENS> {
         ru = ru / rd;
         ox = px * ru; oy = py * ru; return true;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :42-53
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :42-53
         x = x / z; y = y / z;
         const float ru2 = x * x + y * y;
         const float r = sqrtf(ru2);
@@ -166,7 +168,7 @@ template <> struct Lens<GF_LENS_PTLENS> {
 };
 // ---- insta360.rs ---------------------------------------------------------------------------
 template <> struct Lens<GF_LENS_INSTA360> {
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :27-48
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :27-48
         const float k1 = P.k[0], k2 = P.k[1], k3 = P.k[2], p1 = P.k[3], p2 = P.k[4], xi = P.k[5];
         const float len = sqrtf(x * x + y * y + z * z);
         x = (x / len) / ((z / len) + xi);
@@ -175,11 +177,11 @@ template <> struct Lens<GF_LENS_INSTA360> {
         ox = x * (1.0f + k1 * r2 + k2 * r4 + k3 * r6) + 2.0f * p1 * x * y + p2 * (r2 + 2.0f * x * x);
         oy = y * (1.0f + k1 * r2 + k2 * r4 + k3 * r6) + 2.0f * p2 * x * y + p1 * (r2 + 2.0f * y * y);
     }
-    static GF_DEV bool undistort(float ptx, float pty, const gf_kernel_params& P, float& ox, float& oy) {       // :10-25
+    static GF_DEV bool undistort(float ptx, float pty, const gf_kernel_params& P, bool noop, float& ox, float& oy) {       // :10-25
         float px = ptx, py = pty;
         for (int i = 0; i < 200; ++i) {
             float dx, dy;
-            distort(px, py, 1.0f, P, dx, dy);
+            distort(px, py, 1.0f, P, noop, dx, dy);
             dx = dx - ptx; dy = dy - pty;
             if (fabsf(dx) < 1e-6f && fabsf(dy) < 1e-6f) break;
             px -= dx; py -= dy;
@@ -189,9 +191,9 @@ template <> struct Lens<GF_LENS_INSTA360> {
 };
 // ---- sony.rs -------------------------------------------------------------------------------
 template <> struct Lens<GF_LENS_SONY> {
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :10-63
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :10-63
         const float* k = P.k;
-        if (k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f) { ox = px; oy = py; return true; }
+        if (noop) { ox = px; oy = py; return true; }
         const float EPS = 1e-6f;
         const float theta_d = sqrtf(px * px + py * py);
         bool converged = false;
@@ -214,10 +216,10 @@ template <> struct Lens<GF_LENS_SONY> {
         if (converged && !theta_flipped) { ox = px * scale; oy = py * scale; return true; }
         return false;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :65-89
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :65-89
         const float* k = P.k;
         x = x / z; y = y / z;
-        if (k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f) { ox = x; oy = y; return; }
+        if (noop) { ox = x; oy = y; return; }
         const float r = sqrtf(x * x + y * y);
         const float theta = gf_atanf(r);
         const float theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta2 * theta3, theta6 = theta3 * theta3;
@@ -234,9 +236,9 @@ template <> struct Lens<GF_LENS_GENERIC_POLYNOMIAL> {
         for (int i = 0; i < 12; ++i) z = z && (k[i] == 0.0f);
         return z;
     }
-    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, float& ox, float& oy) {   // :18-81
+    static GF_DEV bool undistort(float px, float py, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :18-81
         const float* k = P.k;
-        if (all_zero(k)) { ox = px; oy = py; return true; }
+        if (noop) { ox = px; oy = py; return true; }
         const float EPS = 1e-6f;
         const float theta_d = sqrtf(px * px + py * py);
         bool converged = false;
@@ -262,10 +264,10 @@ template <> struct Lens<GF_LENS_GENERIC_POLYNOMIAL> {
         if (converged && !theta_flipped) { ox = px * scale; oy = py * scale; return true; }
         return false;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :83-122
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :83-122
         const float* k = P.k;
         x = x / z; y = y / z;
-        if (all_zero(k)) { ox = x; oy = y; return; }
+        if (noop) { ox = x; oy = y; return; }
         const float r = sqrtf(x * x + y * y);
         const float theta = gf_atanf(r);
         const float theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta2 * theta3,
@@ -296,9 +298,9 @@ template <> struct Lens<GF_LENS_GOPRO> {
         }
         return p;
     }
-    static GF_DEV bool undistort(float ptx, float pty, const gf_kernel_params& P, float& ox, float& oy) {   // :42-57
+    static GF_DEV bool undistort(float ptx, float pty, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :42-57
         const float* k = P.k;
-        if (k[1] == 0.0f) { ox = ptx; oy = pty; return true; }
+        if (noop) { ox = ptx; oy = pty; return true; }
         const float r_norm = sqrtf(ptx * ptx + pty * pty);
         if (r_norm < 1e-9f) { ox = ptx; oy = pty; return true; }
         const float p = r_norm / k[1];
@@ -309,10 +311,10 @@ template <> struct Lens<GF_LENS_GOPRO> {
         const float scale = rr / r_norm;
         ox = ptx * scale; oy = pty * scale; return true;
     }
-    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, float& ox, float& oy) {   // :61-74
+    static GF_DEV void distort(float x, float y, float z, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // :61-74
         const float* k = P.k;
         const float posx = x / z, posy = y / z;
-        if (k[1] == 0.0f) { ox = posx; oy = posy; return; }
+        if (noop) { ox = posx; oy = posy; return; }
         const float r = sqrtf(posx * posx + posy * posy);
         const float TMAX = 1.5533f;
         const float tt = gf_tanf(TMAX);
@@ -363,7 +365,7 @@ struct GoproMapFn {      // gopro_warp.rs:22-39
 template <typename Fn, int XSCALE_KIND /*0 none, 1 superview 1.333333333, 2 hyperview 1.555555555*/>
 struct ViewLens {
     static GF_DEV float xs() { return XSCALE_KIND == 1 ? 1.333333333f : 1.555555555f; }
-    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params& P, float& ox, float& oy) {
+    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params& P, bool noop, float& ox, float& oy) {
         const float cw = (float)P.output_width, chh = (float)P.output_height;
         ux = (ux / cw) - 0.5f; uy = (uy / chh) - 0.5f;
         Fn::map(ux, uy, nullptr);
@@ -371,7 +373,7 @@ struct ViewLens {
         ox = (ux + 0.5f) * cw; oy = (uy + 0.5f) * chh;
         return true;
     }
-    static GF_DEV void distort(float x, float y, float, const gf_kernel_params& P, float& ox, float& oy) {
+    static GF_DEV void distort(float x, float y, float, const gf_kernel_params& P, bool noop, float& ox, float& oy) {
         const float sw = (float)P.width, sh = (float)P.height;
         x = (x / sw) - 0.5f; y = (y / sh) - 0.5f;
         if (XSCALE_KIND != 0) x = x * xs();
@@ -391,7 +393,7 @@ template <> struct Lens<GF_LENS_GOPRO6_SUPERVIEW> : ViewLens<Superview6Fn, 0> {}
 template <> struct Lens<GF_LENS_GOPRO_HYPERVIEW>  : ViewLens<HyperviewFn, 2>  {};   // gopro_hyperview.rs:21-55
 
 template <> struct Lens<GF_LENS_GOPRO_WARP> {
-    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params& P, float& ox, float& oy) {   // gopro_warp.rs:43-56
+    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // gopro_warp.rs:43-56
         const float* p = P.digital_lens_params;
         const float factor = p[14] != 0.0f ? p[14] : 1.0f;
         const float cw = (float)P.output_width, chh = (float)P.output_height;
@@ -401,7 +403,7 @@ template <> struct Lens<GF_LENS_GOPRO_WARP> {
         ox = (ux + 0.5f) * cw; oy = (uy + 0.5f) * chh;
         return true;
     }
-    static GF_DEV void distort(float x, float y, float, const gf_kernel_params& P, float& ox, float& oy) {   // gopro_warp.rs:60-94
+    static GF_DEV void distort(float x, float y, float, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // gopro_warp.rs:60-94
         const float* p = P.digital_lens_params;
         const float factor = p[14] != 0.0f ? p[14] : 1.0f;
         const float sw = (float)P.width, sh = (float)P.height;
@@ -422,17 +424,17 @@ template <> struct Lens<GF_LENS_GOPRO_WARP> {
     }
 };
 template <> struct Lens<GF_LENS_DIGITAL_STRETCH> {
-    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params& P, float& ox, float& oy) {   // digital_stretch.rs:12-15
+    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // digital_stretch.rs:12-15
         ox = ux / P.digital_lens_params[0]; oy = uy / P.digital_lens_params[1]; return true;
     }
-    static GF_DEV void distort(float x, float y, float, const gf_kernel_params& P, float& ox, float& oy) {   // digital_stretch.rs:19-22
+    static GF_DEV void distort(float x, float y, float, const gf_kernel_params& P, bool noop, float& ox, float& oy) {   // digital_stretch.rs:19-22
         ox = x * P.digital_lens_params[0]; oy = y * P.digital_lens_params[1];
     }
 };
 // "no digital lens" (Option::None): identity, never called when DIGITAL == GF_LENS_NONE
 template <> struct Lens<GF_LENS_NONE> {
-    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params&, float& ox, float& oy) { ox = ux; oy = uy; return true; }
-    static GF_DEV void distort(float x, float y, float, const gf_kernel_params&, float& ox, float& oy) { ox = x; oy = y; }
+    static GF_DEV bool undistort(float ux, float uy, const gf_kernel_params&, bool, float& ox, float& oy) { ox = ux; oy = uy; return true; }
+    static GF_DEV void distort(float x, float y, float, const gf_kernel_params&, bool, float& ox, float& oy) { ox = x; oy = y; }
 };
 
 } // namespace gf

@@ -16,6 +16,39 @@
 
 namespace gf {
 
+// map_coord (util.rs:144-147) with every per-frame-uniform piece evaluated once on the host, in the same float
+// operations: map(x) = ((x - in_min) * mul) / div + add, mul = out_max - out_min, div = in_max - in_min.
+struct MapC {
+    float in_min, mul, div, rcp, add;   // rcp = 1.0f / div (correctly rounded), used by the exact fast division
+    int   fast_div;                     // div is finite, normal and of moderate magnitude
+    int   identity;                     // integer-valued x only: ((x - in_min) * mul) / div == x - in_min exactly (products < 2^24, mul == div)
+};
+
+// feature bits, decided once per launch on the host (all per-frame uniform)
+enum : uint32_t {
+    F_RS         = 1u << 0,   // matrix_count > 1
+    F_HRS        = 1u << 1,   // flags & 16: horizontal rolling shutter
+    F_RLIMIT     = 1u << 2,   // r_limit_sq > 0
+    F_REFRACT    = 1u << 3,   // light_refraction_coefficient != 1 && > 0
+    F_MESH       = 1u << 4,   // mesh_len > 0
+    F_DIGITAL    = 1u << 5,   // flags & 2 (and a digital lens is compiled in)
+    F_HSTRETCH   = 1u << 6,   // input_horizontal_stretch > 0.001 and != 1 (x / 1.0f == x exactly, so 1.0 is skipped)
+    F_VSTRETCH   = 1u << 7,
+    F_LCA        = 1u << 8,   // lens_correction_amount < 1
+    F_INROT      = 1u << 9,   // input_rotation != 0
+    F_BG1        = 1u << 10,  // background_mode == 1 / 2 / 3
+    F_BG2        = 1u << 11,
+    F_BG3        = 1u << 12,
+    F_FIXRANGE   = 1u << 13,  // flags & 1
+    F_FILLBG     = 1u << 14,  // flags & 4
+    F_LENS_NOOP  = 1u << 15,  // the lens model's "all coefficients zero" early-out applies (fisheye/sony: k0..k3, generic: k0..k11, gopro: k1)
+    F_SRC_VEC    = 1u << 16,  // whole-pixel vector loads / stores are legal (pointer and stride alignment)
+    F_DST_VEC    = 1u << 17,
+    F_FB_INV     = 1u << 18,  // flags & 128
+    F_IS_Y       = 1u << 19,  // plane_index == 0
+    F_T3D        = 1u << 20,  // translation3d != 0 (x + 0.0f only differs from x in the sign of zero, which no consumer sees)
+};
+
 struct WarpArgs {
     gf_kernel_params p;             // verbatim KernelParams
     const uint8_t* src;
@@ -26,11 +59,19 @@ struct WarpArgs {
     int   mesh_len;
     int   out_rows;                 // ceil(dst_len / output_stride): rows the reference iterates (par_chunks_mut)
     int   out_cols;                 // floor(output_stride / bpp): pixels per full row (chunks_mut)
-    int   src_vec_ok, dst_vec_ok;   // base pointer and stride allow whole-pixel vector access
-    // derived on the host with the same IEEE float ops as cpu_undistort.rs:521-528
+    uint32_t feat;                  // F_* bits
+    // derived on the host with the same IEEE float ops as cpu_undistort.rs:521-528 / :421-517
     float r_limit_sq;
     float out_c[2], out_f[2];
     float bg[4];
+    MapC  omap_x, omap_y;           // output_rect -> output size   (:422-423, :546-549)
+    MapC  smap_x, smap_y;           // frame size  -> source_rect   (:510-515, :599-602)
+    float width_f, height_f;        // (float)width / height
+    float frame_w, frame_h;         // frame size after input_rotation (:485-489)
+    float rot_cos, rot_sin;         // cos/sin(input_rotation * PI/180) via gf_cosf/gf_sinf
+    int   rs_lim;                   // HRS ? width : height
+    int   u8_limit;                 // trunc(min(pixel_value_limit, 255)) for the integer u8 sampler
+    int   src_rect[4];              // rx0, ry0, rx1, ry1
 };
 
 // ------------------------------------------------------------------------------------------
@@ -43,72 +84,85 @@ template <int COUNT_, int SCALAR_> struct Pix {
     static constexpr int SCALAR = SCALAR_;
     static constexpr int SBYTES = SCALAR_ == SC_U8 ? 1 : (SCALAR_ == SC_F32 ? 4 : 2);
     static constexpr int BYTES = COUNT_ * SBYTES;
-    static constexpr bool VEC = (BYTES == 1 || BYTES == 2 || BYTES == 4 || BYTES == 8 || BYTES == 16);
+    static constexpr bool POW2 = (BYTES == 1 || BYTES == 2 || BYTES == 4 || BYTES == 8 || BYTES == 16);
+    static constexpr int ALIGN = POW2 ? BYTES : SBYTES;      // alignment F_SRC_VEC / F_DST_VEC vouch for
 
-    static GF_DEV float scalar_to_float(uint32_t raw) {
+    static GF_DEV float scalar_to_float(uint32_t raw) {      // PixelType::to_float
         if (SCALAR == SC_F32) return __uint_as_float(raw);
         if (SCALAR == SC_F16) return __half2float(__ushort_as_half((unsigned short)raw));
-        return (float)raw;                                  // u8 / u16 widen exactly
+        return (float)raw;                                   // u8 / u16 widen exactly
     }
-    static GF_DEV uint32_t float_to_scalar(float v) {       // PixelType::from_float: Rust `as` casts
+    static GF_DEV uint32_t float_to_scalar(float v) {        // PixelType::from_float: Rust `as` casts
         if (SCALAR == SC_F32) return __float_as_uint(v);
         if (SCALAR == SC_F16) return (uint32_t)__half_as_ushort(__float2half_rn(v));
-        int i = __float2int_rz(v);                          // trunc, saturating, NaN -> 0
+        int i = __float2int_rz(v);                           // trunc, saturating, NaN -> 0
         const int hi = SCALAR == SC_U8 ? 255 : 65535;
         i = i < 0 ? 0 : (i > hi ? hi : i);
         return (uint32_t)i;
     }
-    // to_float
-    static GF_DEV void load(const uint8_t* __restrict__ p, bool vec_ok, float (&v)[COUNT]) {
-        if (VEC && vec_ok) {
-            if (BYTES == 1) { v[0] = scalar_to_float(__ldg(p)); }
-            else if (BYTES == 2) {
-                const uint32_t w = __ldg(reinterpret_cast<const unsigned short*>(p));
-                if (COUNT == 1) v[0] = scalar_to_float(w);
-                else { v[0] = scalar_to_float(w & 0xffu); v[COUNT > 1 ? 1 : 0] = scalar_to_float(w >> 8); }
-            } else if (BYTES == 4) {
-                const uint32_t w = __ldg(reinterpret_cast<const unsigned int*>(p));
-                if (COUNT == 1) v[0] = scalar_to_float(w);
-                else if (COUNT == 2) { v[0] = scalar_to_float(w & 0xffffu); v[COUNT > 1 ? 1 : 0] = scalar_to_float(w >> 16); }
-                else {
-                    #pragma unroll
-                    for (int i = 0; i < COUNT; ++i) v[i] = scalar_to_float((w >> (8 * i)) & 0xffu);
-                }
-            } else if (BYTES == 8) {
-                const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
-                #pragma unroll
-                for (int i = 0; i < COUNT; ++i) { const uint32_t q = (i < 2) ? w.x : w.y; v[i] = scalar_to_float((q >> (16 * (i & 1))) & 0xffffu); }
-            } else {
-                const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
-                const uint32_t q[4] = {w.x, w.y, w.z, w.w};
-                #pragma unroll
-                for (int i = 0; i < COUNT; ++i) v[i] = scalar_to_float(q[i & 3]);
-            }
-        } else {
+    static GF_DEV uint32_t load_scalar(const uint8_t* __restrict__ p) {      // one aligned scalar
+        if (SBYTES == 1) return __ldg(p);
+        if (SBYTES == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
+        return __ldg(reinterpret_cast<const unsigned int*>(p));
+    }
+    // aligned pixel -> COUNT raw scalars
+    static GF_DEV void load_raw(const uint8_t* __restrict__ p, uint32_t (&r)[COUNT]) {
+        if (!POW2) {
             #pragma unroll
-            for (int i = 0; i < COUNT; ++i) {
-                uint32_t raw = 0;
-                #pragma unroll
-                for (int b = 0; b < SBYTES; ++b) raw |= (uint32_t)__ldg(p + i * SBYTES + b) << (8 * b);
-                v[i] = scalar_to_float(raw);
-            }
+            for (int i = 0; i < COUNT; ++i) r[i] = load_scalar(p + i * SBYTES);
+        } else if (BYTES <= 4) {
+            const uint32_t w = BYTES == 1 ? (uint32_t)__ldg(p) : (BYTES == 2 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) : __ldg(reinterpret_cast<const unsigned int*>(p)));
+            #pragma unroll
+            for (int i = 0; i < COUNT; ++i) r[i] = COUNT == 1 ? w : ((w >> (8 * SBYTES * i)) & (SBYTES == 1 ? 0xffu : 0xffffu));
+        } else if (BYTES == 8) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+            #pragma unroll
+            for (int i = 0; i < COUNT; ++i) { const uint32_t q = (i < 2) ? w.x : w.y; r[i] = (q >> (16 * (i & 1))) & 0xffffu; }
+        } else {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+            const uint32_t q[4] = {w.x, w.y, w.z, w.w};
+            #pragma unroll
+            for (int i = 0; i < COUNT; ++i) r[i] = q[i & 3];
         }
     }
-    static GF_DEV void store(uint8_t* __restrict__ p, bool vec_ok, const float (&v)[COUNT]) {
-        uint32_t s[COUNT];
+    static GF_DEV void load_vec(const uint8_t* __restrict__ p, float (&v)[COUNT]) {
+        uint32_t r[COUNT];
+        load_raw(p, r);
         #pragma unroll
-        for (int i = 0; i < COUNT; ++i) s[i] = float_to_scalar(v[i]);
-        if (VEC && vec_ok) {
-            if (BYTES == 1) { *p = (uint8_t)s[0]; }
-            else if (BYTES == 2) {
-                const uint32_t w = COUNT == 1 ? s[0] : (s[0] | (s[COUNT > 1 ? 1 : 0] << 8));
-                *reinterpret_cast<unsigned short*>(p) = (unsigned short)w;
-            } else if (BYTES == 4) {
-                uint32_t w;
-                if (COUNT == 1) w = s[0];
-                else if (COUNT == 2) w = s[0] | (s[COUNT > 1 ? 1 : 0] << 16);
-                else { w = 0; _Pragma("unroll") for (int i = 0; i < COUNT; ++i) w |= s[i] << (8 * i); }
-                *reinterpret_cast<unsigned int*>(p) = w;
+        for (int i = 0; i < COUNT; ++i) v[i] = scalar_to_float(r[i]);
+    }
+    static GF_DEV void load_bytes(const uint8_t* __restrict__ p, float (&v)[COUNT]) {     // no alignment assumed
+        #pragma unroll
+        for (int i = 0; i < COUNT; ++i) {
+            uint32_t raw = 0;
+            #pragma unroll
+            for (int b = 0; b < SBYTES; ++b) raw |= (uint32_t)__ldg(p + i * SBYTES + b) << (8 * b);
+            v[i] = scalar_to_float(raw);
+        }
+    }
+    // 8-bit formats: channel c in byte c of one word (aligned)
+    static GF_DEV uint32_t load_packed(const uint8_t* __restrict__ p) {
+        if (COUNT == 1) return __ldg(p);
+        if (COUNT == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
+        if (COUNT == 4) return __ldg(reinterpret_cast<const unsigned int*>(p));
+        return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    }
+    static GF_DEV void store_scalars(uint8_t* __restrict__ p, bool vec_ok, const uint32_t (&s)[COUNT]) {
+        if (vec_ok) {
+            if (!POW2) {
+                #pragma unroll
+                for (int i = 0; i < COUNT; ++i) {
+                    if (SBYTES == 1) p[i] = (uint8_t)s[i];
+                    else if (SBYTES == 2) reinterpret_cast<unsigned short*>(p)[i] = (unsigned short)s[i];
+                    else reinterpret_cast<unsigned int*>(p)[i] = s[i];
+                }
+            } else if (BYTES <= 4) {
+                uint32_t w = 0;
+                #pragma unroll
+                for (int i = 0; i < COUNT; ++i) w |= s[i] << (8 * SBYTES * i);
+                if (BYTES == 1) *p = (uint8_t)w;
+                else if (BYTES == 2) *reinterpret_cast<unsigned short*>(p) = (unsigned short)w;
+                else *reinterpret_cast<unsigned int*>(p) = w;
             } else if (BYTES == 8) {
                 uint2 w = make_uint2(0u, 0u);
                 #pragma unroll
@@ -124,6 +178,12 @@ template <int COUNT_, int SCALAR_> struct Pix {
                 for (int b = 0; b < SBYTES; ++b) p[i * SBYTES + b] = (uint8_t)(s[i] >> (8 * b));
             }
         }
+    }
+    static GF_DEV void store(uint8_t* __restrict__ p, bool vec_ok, const float (&v)[COUNT]) {
+        uint32_t s[COUNT];
+        #pragma unroll
+        for (int i = 0; i < COUNT; ++i) s[i] = float_to_scalar(v[i]);
+        store_scalars(p, vec_ok, s);
     }
 };
 
@@ -182,21 +242,48 @@ static __device__ __noinline__ double mesh_bivariate(const MeshView mesh, uint32
 }
 
 // ------------------------------------------------------------------------------------------
+// Exact division by a per-frame-uniform divisor: q = RN(a / d) from the precomputed rcp = RN(1/d).
+// One Markstein correction step (the same shape as the compiler's own div.rn.f32 fast path, whose refined
+// reciprocal is *less* accurate than RN(1/d)); checked against IEEE division over every float `a` for the
+// divisors that occur here (tools/udiv_check.c).  Outside a conservative magnitude window — or when the host
+// did not vouch for the divisor — the ordinary division is used.
+// ------------------------------------------------------------------------------------------
+GF_DEV float div_uniform(float a, const MapC& m) {
+    const float aa = fabsf(a);
+    if (m.fast_div && aa < 0x1p60f && aa > 0x1p-80f) {
+        const float q0 = a * m.rcp;
+        const float r0 = __fmaf_rn(-m.div, q0, a);
+        return __fmaf_rn(r0, m.rcp, q0);
+    }
+    return a / m.div;
+}
+// map_coord for an integer-valued coordinate (pixel index)
+GF_DEV float map_apply_int(float x, const MapC& m) {
+    if (m.identity) return (x - m.in_min) + m.add;
+    return div_uniform((x - m.in_min) * m.mul, m) + m.add;
+}
+GF_DEV float map_apply(float x, const MapC& m) {
+    return div_uniform((x - m.in_min) * m.mul, m) + m.add;
+}
+
+// ------------------------------------------------------------------------------------------
 // rotate_and_distort — cpu_undistort.rs:133-228
 // ------------------------------------------------------------------------------------------
 template <int LENS, int DIGITAL>
 GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs& A, float& ou, float& ov) {
     const gf_kernel_params& P = A.p;
+    const uint32_t feat = A.feat;
     const float2* __restrict__ mp = reinterpret_cast<const float2*>(A.matrices + (size_t)idx * GF_MATRIX_STRIDE);
     const float2 m01 = __ldg(mp + 0), m23 = __ldg(mp + 1), m45 = __ldg(mp + 2), m67 = __ldg(mp + 3), m8_9 = __ldg(mp + 4);
-    const float _x = (px * m01.x) + (py * m01.y) + m23.x + P.translation3d[0];
-    const float _y = (px * m23.y) + (py * m45.x) + m45.y + P.translation3d[1];
-    float       _w = (px * m67.x) + (py * m67.y) + m8_9.x + P.translation3d[2];
+    const float2 m10_11 = __ldg(mp + 5), m12_13 = __ldg(mp + 6);
+    float _x = (px * m01.x) + (py * m01.y) + m23.x;
+    float _y = (px * m23.y) + (py * m45.x) + m45.y;
+    float _w = (px * m67.x) + (py * m67.y) + m8_9.x;
+    if (feat & F_T3D) { _x += P.translation3d[0]; _y += P.translation3d[1]; _w += P.translation3d[2]; }   // :135-137
     if (!(_w > 0.0f)) return false;
-    if (A.r_limit_sq > 0.0f && (_x * _x + _y * _y) > A.r_limit_sq * _w) return false;                // :139 (sic: * _w)
-
-    if (P.light_refraction_coefficient != 1.0f && P.light_refraction_coefficient > 0.0f) {            // :143-152
-        if (_w != 0.0f) {
+    if (feat & (F_RLIMIT | F_REFRACT)) {
+        if ((feat & F_RLIMIT) && (_x * _x + _y * _y) > A.r_limit_sq * _w) return false;                 // :139 (sic: * _w)
+        if (feat & F_REFRACT) {                                                                          // :143-152 (_w != 0 holds: _w > 0)
             const float r = sqrtf(_x * _x + _y * _y) / _w;
             const float sin_theta_d = (r / sqrtf(1.0f + r * r)) * P.light_refraction_coefficient;
             const float r_d = sin_theta_d / sqrtf(1.0f - sin_theta_d * sin_theta_d);
@@ -205,11 +292,12 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
     }
 
     float ux, uy;
-    Lens<LENS>::distort(_x, _y, _w, P, ux, uy);                                                        // :154
+    Lens<LENS>::distort(_x, _y, _w, P, (feat & F_LENS_NOOP) != 0, ux, uy);                             // :154
     ux = ux * P.f[0]; uy = uy * P.f[1];                                                                // :155
 
-    const float2 m10_11 = __ldg(mp + 5), m12_13 = __ldg(mp + 6);
-    if (m8_9.y != 0.0f || m10_11.x != 0.0f || m10_11.y != 0.0f || m12_13.x != 0.0f || m12_13.y != 0.0f) {   // :157-165
+    // :157 — any of m[9..13] != 0.0 (NaN counts as non-zero; -0.0 does not): all bits but the sign
+    if (((__float_as_uint(m8_9.y) | __float_as_uint(m10_11.x) | __float_as_uint(m10_11.y) |
+          __float_as_uint(m12_13.x) | __float_as_uint(m12_13.y)) << 1) != 0u) {                        // :157-165
         const float ang_rad = m10_11.y;
         const float cos_a = gf_cosf(-ang_rad), sin_a = gf_sinf(-ang_rad);
         const float tx = cos_a * ux - sin_a * uy - m8_9.y   + m12_13.x;
@@ -219,22 +307,23 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
 
     ux = ux + P.c[0]; uy = uy + P.c[1];                                                                // :167
 
-    if (A.mesh_len > 0) {
+    if (feat & F_MESH) {
         const MeshView mesh{A.mesh};
+        const bool inv = (feat & F_FB_INV) != 0;
         const double mesh0 = mesh[0];
         if (mesh0 > 10.0) {                                                                            // :169-185
             const float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
             const float crop_w = (float)mesh[7], crop_h = (float)mesh[8];
-            if ((P.flags & 128) == 128) uy = (float)P.height - uy;
-            ux = map_coord(ux, 0.0f, (float)P.width,  origin_x, origin_x + crop_w);
-            uy = map_coord(uy, 0.0f, (float)P.height, origin_y, origin_y + crop_h);
+            if (inv) uy = A.height_f - uy;
+            ux = map_coord(ux, 0.0f, A.width_f,  origin_x, origin_x + crop_w);
+            uy = map_coord(uy, 0.0f, A.height_f, origin_y, origin_y + crop_h);
             const uint32_t n_x = as_usize_small(mesh[1]), n_y = as_usize_small(mesh[2]);
             const double sx = mesh[3], sy = mesh[4];
             const double nx = mesh_bivariate(mesh, n_x, n_y, sx, sy, 0, (double)ux, (double)uy);
             const double ny = mesh_bivariate(mesh, n_x, n_y, sx, sy, 1, (double)ux, (double)uy);
-            ux = map_coord((float)nx, origin_x, origin_x + crop_w, 0.0f, (float)P.width);
-            uy = map_coord((float)ny, origin_y, origin_y + crop_h, 0.0f, (float)P.height);
-            if ((P.flags & 128) == 128) uy = (float)P.height - uy;
+            ux = map_coord((float)nx, origin_x, origin_x + crop_w, 0.0f, A.width_f);
+            uy = map_coord((float)ny, origin_y, origin_y + crop_h, 0.0f, A.height_f);
+            if (inv) uy = A.height_f - uy;
         }
         // FocalPlaneDistortion :188-214 (a missing FPD block means "none"; the reference would index out of bounds)
         const uint32_t o = as_usize_small(mesh0);
@@ -243,9 +332,9 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
             const float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
             const float crop_w = (float)mesh[7], crop_h = (float)mesh[8];
             const double stblz_grid = mesh_size_y / 8.0;
-            if ((P.flags & 128) == 128) uy = (float)P.height - uy;
-            ux = map_coord(ux, 0.0f, (float)P.width,  origin_x, origin_x + crop_w);
-            uy = map_coord(uy, 0.0f, (float)P.height, origin_y, origin_y + crop_h);
+            if (inv) uy = A.height_f - uy;
+            ux = map_coord(ux, 0.0f, A.width_f,  origin_x, origin_x + crop_w);
+            uy = map_coord(uy, 0.0f, A.height_f, origin_y, origin_y + crop_h);
             const uint32_t idx2 = as_usize_small(fmin(fmax(floor((double)uy / stblz_grid), 0.0), 7.0));
             const double delta = (double)uy - stblz_grid * (double)idx2;
             ux -= (float)(mesh[o + 4 + idx2 * 2 + 0] * delta);
@@ -254,54 +343,55 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
                 ux -= (float)(mesh[o + 4 + j * 2 + 0] * stblz_grid);
                 uy -= (float)(mesh[o + 4 + j * 2 + 1] * stblz_grid);
             }
-            ux = map_coord(ux, origin_x, origin_x + crop_w, 0.0f, (float)P.width);
-            uy = map_coord(uy, origin_y, origin_y + crop_h, 0.0f, (float)P.height);
-            if ((P.flags & 128) == 128) uy = (float)P.height - uy;
+            ux = map_coord(ux, origin_x, origin_x + crop_w, 0.0f, A.width_f);
+            uy = map_coord(uy, origin_y, origin_y + crop_h, 0.0f, A.height_f);
+            if (inv) uy = A.height_f - uy;
         }
     }
 
-    if (DIGITAL != GF_LENS_NONE && (P.flags & 2) == 2) {                                               // :216-220
+    if (DIGITAL != GF_LENS_NONE && (feat & F_DIGITAL)) {                                               // :216-220
         float dx, dy;
-        Lens<DIGITAL>::distort(ux, uy, 1.0f, P, dx, dy);
+        Lens<DIGITAL>::distort(ux, uy, 1.0f, P, false, dx, dy);
         ux = dx; uy = dy;
     }
 
-    if (P.input_horizontal_stretch > 0.001f) ux /= P.input_horizontal_stretch;                         // :222-223
-    if (P.input_vertical_stretch   > 0.001f) uy /= P.input_vertical_stretch;
+    if (feat & (F_HSTRETCH | F_VSTRETCH)) {                                                            // :222-223
+        if (feat & F_HSTRETCH) ux /= P.input_horizontal_stretch;
+        if (feat & F_VSTRETCH) uy /= P.input_vertical_stretch;
+    }
 
     ou = ux; ov = uy;
     return true;
 }
 
-GF_DEV void rotate_point(float px, float py, float angle, float ox, float oy, float o2x, float o2y, float& rx, float& ry) {   // :262-265
-    const float ca = gf_cosf(angle), sa = gf_sinf(angle);
+// rotate_point (cpu_undistort.rs:262-265) with the frame-uniform cos/sin supplied
+GF_DEV void rotate_point(float px, float py, float ca, float sa, float ox, float oy, float o2x, float o2y, float& rx, float& ry) {
     rx = ca * (px - ox) - sa * (py - oy) + o2x;
     ry = sa * (px - ox) + ca * (py - oy) + o2y;
 }
 
-// undistort_coord — cpu_undistort.rs:421-517
+// undistort_coord — cpu_undistort.rs:421-517.  (opx, opy) = out_pos after the output-rect mapping of :422-423.
 template <int LENS, int DIGITAL>
-GF_DEV bool undistort_coord(float ox_, float oy_, const WarpArgs& A, float& ru, float& rv) {
+GF_DEV bool undistort_coord(float opx, float opy, const WarpArgs& A, float& ru, float& rv) {
     const gf_kernel_params& P = A.p;
-    float opx = map_coord(ox_, (float)P.output_rect[0], (float)(P.output_rect[0] + P.output_rect[2]), 0.0f, (float)P.output_width);
-    float opy = map_coord(oy_, (float)P.output_rect[1], (float)(P.output_rect[1] + P.output_rect[3]), 0.0f, (float)P.output_height);
+    const uint32_t feat = A.feat;
     opx += P.translation2d[0];
     opy += P.translation2d[1];
 
-    if (P.lens_correction_amount < 1.0f) {                                                             // :429-460
+    if (feat & F_LCA) {                                                                                // :429-460
         float nx = opx, ny = opy;
         const float ocx = A.out_c[0], ocy = A.out_c[1], ofx = A.out_f[0], ofy = A.out_f[1];
-        if (DIGITAL != GF_LENS_NONE && (P.flags & 2) == 2) {
+        if (DIGITAL != GF_LENS_NONE && (feat & F_DIGITAL)) {
             const float uzx = (nx - ocx) * P.fov + ocx, uzy = (ny - ocy) * P.fov + ocy;
             float tx, ty;
-            if (Lens<DIGITAL>::undistort(uzx, uzy, P, tx, ty)) {
+            if (Lens<DIGITAL>::undistort(uzx, uzy, P, false, tx, ty)) {
                 nx = (tx - ocx) / P.fov + ocx;
                 ny = (ty - ocy) / P.fov + ocy;
             }
         }
         nx = (nx - ocx) / ofx; ny = (ny - ocy) / ofy;
-        { float tx, ty; if (Lens<LENS>::undistort(nx, ny, P, tx, ty)) { nx = tx; ny = ty; } }
-        if (P.light_refraction_coefficient != 1.0f && P.light_refraction_coefficient > 0.0f) {
+        { float tx, ty; if (Lens<LENS>::undistort(nx, ny, P, (feat & F_LENS_NOOP) != 0, tx, ty)) { nx = tx; ny = ty; } }
+        if (feat & F_REFRACT) {
             const float r = sqrtf(nx * nx + ny * ny);
             if (r != 0.0f) {
                 const float sin_theta_d = (r / sqrtf(1.0f + r * r)) / P.light_refraction_coefficient;
@@ -317,14 +407,14 @@ GF_DEV bool undistort_coord(float ox_, float oy_, const WarpArgs& A, float& ru, 
     }
 
     // rolling-shutter row :465-482
-    const bool hrs = (P.flags & 16) == 16;
-    const int lim = hrs ? P.width : P.height;
+    const bool hrs = (feat & F_HRS) != 0;
+    const int lim = A.rs_lim;
     int sy = as_i32(rs_round(hrs ? opx : opy));
     sy = max(min(sy, lim), 0);
-    if (P.matrix_count > 1) {
+    if (feat & F_RS) {
         float tu, tv;
         if (rotate_and_distort<LENS, DIGITAL>(opx, opy, (uint32_t)P.matrix_count / 2u, A, tu, tv)) {
-            int v = as_i32(rs_round(hrs ? tu : tv));
+            const int v = as_i32(rs_round(hrs ? tu : tv));
             sy = max(min(v, lim), 0);
         }
     }
@@ -333,32 +423,28 @@ GF_DEV bool undistort_coord(float ox_, float oy_, const WarpArgs& A, float& ru, 
     float u, v;
     if (!rotate_and_distort<LENS, DIGITAL>(opx, opy, idx, A, u, v)) return false;                      // :483
 
-    float fsx = (float)P.width, fsy = (float)P.height;
-    if (P.input_rotation != 0.0f) {                                                                    // :485-491
-        const float rotation = P.input_rotation * (3.14159274101257324f / 180.0f);
-        const float sx = fsx, sy2 = fsy;
-        rotate_point(sx, sy2, rotation, 0.0f, 0.0f, 0.0f, 0.0f, fsx, fsy);
-        fsx = rs_round(fabsf(fsx)); fsy = rs_round(fabsf(fsy));
-        float nu, nv;
-        rotate_point(u, v, rotation, sx / 2.0f, sy2 / 2.0f, fsx / 2.0f, fsy / 2.0f, nu, nv);
-        u = nu; v = nv;
+    if (feat & (F_INROT | F_BG1 | F_BG2)) {
+        if (feat & F_INROT) {                                                                          // :485-491
+            float nu, nv;
+            rotate_point(u, v, A.rot_cos, A.rot_sin, A.width_f / 2.0f, A.height_f / 2.0f, A.frame_w / 2.0f, A.frame_h / 2.0f, nu, nv);
+            u = nu; v = nv;
+        }
+        const float width_f = A.width_f, height_f = A.height_f;
+        if (feat & F_BG1) {                                                                            // edge repeat :495-499
+            u = rs_min(rs_max(u, 3.0f), width_f - 3.0f);
+            v = rs_min(rs_max(v, 3.0f), height_f - 3.0f);
+        } else if (feat & F_BG2) {                                                                     // edge mirror :500-509
+            const float rx = rs_round(u), ry = rs_round(v);
+            const float width3 = width_f - 3.0f, height3 = height_f - 3.0f;
+            if (rx > width3)  u = width3  - (rx - width3);
+            if (rx < 3.0f)    u = 3.0f + width_f - (width3 + rx);
+            if (ry > height3) v = height3 - (ry - height3);
+            if (ry < 3.0f)    v = 3.0f + height_f - (height3 + ry);
+        }
     }
-
-    const float width_f = (float)P.width, height_f = (float)P.height;
-    if (P.background_mode == 1) {                                                                      // edge repeat :495-499
-        u = rs_min(rs_max(u, 3.0f), width_f - 3.0f);
-        v = rs_min(rs_max(v, 3.0f), height_f - 3.0f);
-    } else if (P.background_mode == 2) {                                                               // edge mirror :500-509
-        const float rx = rs_round(u), ry = rs_round(v);
-        const float width3 = width_f - 3.0f, height3 = height_f - 3.0f;
-        if (rx > width3)  u = width3  - (rx - width3);
-        if (rx < 3.0f)    u = 3.0f + width_f - (width3 + rx);
-        if (ry > height3) v = height3 - (ry - height3);
-        if (ry < 3.0f)    v = 3.0f + height_f - (height3 + ry);
-    }
-    if (P.background_mode != 3) {                                                                      // :510-515
-        u = map_coord(u, 0.0f, fsx, (float)P.source_rect[0], (float)(P.source_rect[0] + P.source_rect[2]));
-        v = map_coord(v, 0.0f, fsy, (float)P.source_rect[1], (float)(P.source_rect[1] + P.source_rect[3]));
+    if (!(feat & F_BG3)) {                                                                             // :510-515
+        u = map_apply(u, A.smap_x);
+        v = map_apply(v, A.smap_y);
     }
     ru = u; rv = v;
     return true;
@@ -368,28 +454,26 @@ GF_DEV bool undistort_coord(float ox_, float oy_, const WarpArgs& A, float& ru, 
 // sample_input_at, separable branch (I = 2, 4, 8) — cpu_undistort.rs:370-418
 // ------------------------------------------------------------------------------------------
 template <int I> GF_DEV void coeff_row(uint32_t frac, float (&c)[I]) {
-    if (I == 2) { c[0] = 1.0f - (float)frac / 32.0f; c[1] = (float)frac / 32.0f; }     // == COEFFS[frac*2 ..], exact dyadics
-    else if (I == 4) { _Pragma("unroll") for (int i = 0; i < I; ++i) c[i] = GF_COEFFS_BICUBIC_DEV[(frac << 2) + i]; }
-    else { _Pragma("unroll") for (int i = 0; i < I; ++i) c[i] = GF_COEFFS_LANCZOS4_DEV[(frac << 3) + i]; }
+    if (I == 2) { c[1] = (float)frac * 0.03125f; c[0] = 1.0f - c[1]; }                  // == COEFFS[frac*2 ..]: exact dyadics (k/32)
+    else if (I == 4) { _Pragma("unroll") for (int i = 0; i < I; ++i) c[i] = __ldg(&GF_COEFFS_BICUBIC_DEV[(frac << 2) + i]); }
+    else { _Pragma("unroll") for (int i = 0; i < I; ++i) c[i] = __ldg(&GF_COEFFS_LANCZOS4_DEV[(frac << 3) + i]); }
 }
 
+// The generic (float) sampler: any pixel format, any tap outside source_rect replaced by the background colour.
 template <int I, class PIX>
-GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+static __device__ __noinline__ void sample_generic(int sx0, int sy0, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;
-    const float offset = I == 2 ? 0.0f : (I == 4 ? 1.0f : 3.0f);
-    const float u = uvx - offset, v = uvy - offset;
-    const int sx0 = as_i32(rs_round(u * 32.0f));
-    const int sy0 = as_i32(rs_round(v * 32.0f));
     const int sx = sx0 >> 5, sy = sy0 >> 5;
     float cx[I], cy[I];
     coeff_row<I>((uint32_t)sx0 & 31u, cx);
     coeff_row<I>((uint32_t)sy0 & 31u, cy);
-    const int rx0 = P.source_rect[0], ry0 = P.source_rect[1], rx1 = rx0 + P.source_rect[2], ry1 = ry0 + P.source_rect[3];
+    const int rx0 = A.src_rect[0], ry0 = A.src_rect[1], rx1 = A.src_rect[2], ry1 = A.src_rect[3];
+    const bool vec = (A.feat & F_SRC_VEC) != 0;
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
     const long long row_base = (long long)sy * (long long)P.stride + (long long)sx * (long long)PIX::BYTES;
-    #pragma unroll
+    #pragma unroll 1
     for (int yp = 0; yp < I; ++yp) {
         if (sy + yp >= ry0 && sy + yp < ry1) {
             float xsum[C];
@@ -399,7 +483,8 @@ GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum
             for (int xp = 0; xp < I; ++xp) {
                 float px[C];
                 if (sx + xp >= rx0 && sx + xp < rx1) {
-                    PIX::load(A.src + (row_base + (long long)yp * P.stride + (long long)xp * PIX::BYTES), A.src_vec_ok != 0, px);
+                    const uint8_t* tap = A.src + (row_base + (long long)yp * P.stride + (long long)xp * PIX::BYTES);
+                    if (vec) PIX::load_vec(tap, px); else PIX::load_bytes(tap, px);
                 } else {
                     #pragma unroll
                     for (int ch = 0; ch < C; ++ch) px[ch] = A.bg[ch];
@@ -418,12 +503,84 @@ GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum
     for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(sum[ch], P.pixel_value_limit);
 }
 
+// Interior fast path: all IxI taps inside source_rect, whole-pixel vector loads.  Same arithmetic, no per-tap tests.
+template <int I, class PIX>
+GF_DEV void sample_interior(int sx0, int sy0, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+    const gf_kernel_params& P = A.p;
+    constexpr int C = PIX::COUNT;
+    const int sx = sx0 >> 5, sy = sy0 >> 5;
+    float cx[I], cy[I];
+    coeff_row<I>((uint32_t)sx0 & 31u, cx);
+    coeff_row<I>((uint32_t)sy0 & 31u, cy);
+    const uint8_t* row = A.src + ((long long)sy * (long long)P.stride + (long long)sx * (long long)PIX::BYTES);
+    #pragma unroll
+    for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
+    #pragma unroll
+    for (int yp = 0; yp < I; ++yp) {
+        float xsum[C];
+        #pragma unroll
+        for (int ch = 0; ch < C; ++ch) xsum[ch] = 0.0f;
+        #pragma unroll
+        for (int xp = 0; xp < I; ++xp) {
+            float px[C];
+            PIX::load_vec(row + xp * PIX::BYTES, px);
+            #pragma unroll
+            for (int ch = 0; ch < C; ++ch) xsum[ch] += px[ch] * cx[xp];
+        }
+        #pragma unroll
+        for (int ch = 0; ch < C; ++ch) sum[ch] += xsum[ch] * cy[yp];
+        row += P.stride;
+    }
+    #pragma unroll
+    for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(sum[ch], P.pixel_value_limit);
+}
+
+// Integer bilinear for 8-bit formats (interior only).  For u8 taps and 5-bit weights every float operation of the
+// reference is exact (8+5+5 = 18 bits < 24), so sum[ch] == N[ch] / 1024 with N = sum p * wx * wy (integers).
+// Channels are processed two at a time in 16-bit lanes (max lane value 255*32 = 8160), the vertical pass is one dp2a.
+template <class PIX>
+GF_DEV void sample_u8_bilinear(int sx0, int sy0, const WarpArgs& A, uint32_t (&N)[PIX::COUNT]) {
+    constexpr int C = PIX::COUNT;
+    const int sx = sx0 >> 5, sy = sy0 >> 5;
+    const uint32_t fx = (uint32_t)sx0 & 31u, fy = (uint32_t)sy0 & 31u;
+    const uint32_t wx0 = 32u - fx, wx1 = fx;
+    const uint32_t wy = (32u - fy) | (fy << 8);                 // dp2a byte operands: wy0, wy1
+    const uint8_t* row0 = A.src + ((long long)sy * (long long)A.p.stride + (long long)sx * (long long)C);
+    const uint8_t* row1 = row0 + A.p.stride;
+    const uint32_t p00 = PIX::load_packed(row0), p01 = PIX::load_packed(row0 + C);
+    const uint32_t p10 = PIX::load_packed(row1), p11 = PIX::load_packed(row1 + C);
+    // even channels (bytes 0, 2) and odd channels (bytes 1, 3) in 16-bit lanes
+    const uint32_t he0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;      // row 0: ch0 | ch2 << 16
+    const uint32_t he1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;      // row 1
+    N[0] = __dp2a_lo(__byte_perm(he0, he1, 0x5410), wy, 0u);                          // (he0.lo, he1.lo) . (wy0, wy1)
+    if (C > 2) N[C > 2 ? 2 : 0] = __dp2a_lo(__byte_perm(he0, he1, 0x7632), wy, 0u);   // (he0.hi, he1.hi)
+    if (C > 1) {
+        const uint32_t ho0 = __byte_perm(p00, 0u, 0x4341) * wx0 + __byte_perm(p01, 0u, 0x4341) * wx1;   // ch1 | ch3 << 16
+        const uint32_t ho1 = __byte_perm(p10, 0u, 0x4341) * wx0 + __byte_perm(p11, 0u, 0x4341) * wx1;
+        N[1] = __dp2a_lo(__byte_perm(ho0, ho1, 0x5410), wy, 0u);
+        if (C > 3) N[C > 3 ? 3 : 0] = __dp2a_lo(__byte_perm(ho0, ho1, 0x7632), wy, 0u);
+    }
+}
+
 template <int C> GF_DEV void remap_colorrange(float (&px)[C], bool is_y) {      // cpu_undistort.rs:255-260
     const float s = is_y ? 0.85882352f : 0.87843137f;
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) px[ch] *= s;
     px[0] += 16.0f;
     if (C > 1) px[C > 1 ? 1 : 0] += 16.0f;
+}
+
+// sample_input_at at (u, v): picks the integer / interior / generic sampler.  Returns the clamped float sums
+// (what the reference's `sum` holds after :413-418).
+template <int I, class PIX>
+GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+    const float offset = I == 2 ? 0.0f : (I == 4 ? 1.0f : 3.0f);
+    const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
+    const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
+    const int sx = sx0 >> 5, sy = sy0 >> 5;
+    const bool interior = (A.feat & F_SRC_VEC) && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
+    if (interior) sample_interior<I, PIX>(sx0, sy0, A, sum);
+    else          sample_generic<I, PIX>(sx0, sy0, A, sum);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -437,27 +594,28 @@ __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
 warp_kernel(const __grid_constant__ WarpArgs A) {
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;
+    const uint32_t feat = A.feat;
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
     const int y = blockIdx.y * GF_BLOCK_Y + threadIdx.y;
     if (x >= A.out_cols || y >= A.out_rows) return;
     const unsigned long long off = (unsigned long long)y * (unsigned long long)P.output_stride + (unsigned long long)x * PIX::BYTES;
     if (off + PIX::BYTES > A.dst_len) return;                     // trailing partial row (chunks_mut of a short last row)
 
-    const float opx = map_coord((float)x, (float)P.output_rect[0], (float)(P.output_rect[0] + P.output_rect[2]), 0.0f, (float)P.output_width);
-    const float opy = map_coord((float)y, (float)P.output_rect[1], (float)(P.output_rect[1] + P.output_rect[3]), 0.0f, (float)P.output_height);
+    const float opx = map_apply_int((float)x, A.omap_x);          // :546-549 (and :422-423: same expression, same value)
+    const float opy = map_apply_int((float)y, A.omap_y);
     if (!(opx >= 0.0f && opy >= 0.0f && as_i32(opx) < P.output_width && as_i32(opy) < P.output_height)) return;   // :551
 
     uint8_t* const out = A.dst + off;
+    const bool dvec = (feat & F_DST_VEC) != 0;
     float pixel[C];
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
-    if ((P.flags & 4) == 4) { PIX::store(out, A.dst_vec_ok != 0, pixel); return; }                              // fill_bg :558-561
+    if (feat & F_FILLBG) { PIX::store(out, dvec, pixel); return; }                                              // :558-561
 
-    const bool fix_range = (P.flags & 1) == 1, is_y = P.plane_index == 0;
     float u, v;
-    if (undistort_coord<LENS, DIGITAL>((float)x, (float)y, A, u, v)) {                                          // :565
-        if (P.background_mode == 3) {                                                                            // :576-613
-            const float width_f = (float)P.width, height_f = (float)P.height;
+    if (undistort_coord<LENS, DIGITAL>(opx, opy, A, u, v)) {                                                    // :565
+        if (feat & F_BG3) {                                                                                      // :576-613
+            const float width_f = A.width_f, height_f = A.height_f;
             const float widthf = width_f - 1.0f, heightf = height_f - 1.0f;
             const float feather = rs_max(P.background_margin_feather * heightf, 0.0001f);
             float p2x = u, p2y = v, alpha = 1.0f;
@@ -468,29 +626,35 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
                 p2y = ((p2y - 0.5f) * (1.0f - P.background_margin)) + 0.5f;
                 p2x = p2x * width_f; p2y = p2y * height_f;
             }
-            float fsx = width_f, fsy = height_f;
-            if (P.input_rotation != 0.0f) {
-                const float rotation = P.input_rotation * (3.14159274101257324f / 180.0f);
-                rotate_point(width_f, height_f, rotation, 0.0f, 0.0f, 0.0f, 0.0f, fsx, fsy);
-                fsx = rs_round(fabsf(fsx)); fsy = rs_round(fabsf(fsy));
-            }
-            const float sx0 = (float)P.source_rect[0], sx1 = (float)(P.source_rect[0] + P.source_rect[2]);
-            const float sy0 = (float)P.source_rect[1], sy1 = (float)(P.source_rect[1] + P.source_rect[3]);
-            u   = map_coord(u,   0.0f, fsx, sx0, sx1); v   = map_coord(v,   0.0f, fsy, sy0, sy1);
-            p2x = map_coord(p2x, 0.0f, fsx, sx0, sx1); p2y = map_coord(p2y, 0.0f, fsy, sy0, sy1);
+            u   = map_apply(u,   A.smap_x); v   = map_apply(v,   A.smap_y);
+            p2x = map_apply(p2x, A.smap_x); p2y = map_apply(p2y, A.smap_y);
             float c1[C], c2[C];
             sample_input_at<I, PIX>(u, v, A, c1);
             sample_input_at<I, PIX>(p2x, p2y, A, c2);
             #pragma unroll
             for (int ch = 0; ch < C; ++ch) pixel[ch] = c1[ch] * alpha + c2[ch] * (1.0f - alpha);
-            if (fix_range) remap_colorrange<C>(pixel, is_y);
-            PIX::store(out, A.dst_vec_ok != 0, pixel);
-            return;
+        } else {
+            if (I == 2 && PIX::SCALAR == SC_U8 && !(feat & F_FIXRANGE)) {
+                // 8-bit bilinear interior: integer arithmetic, exact (see sample_u8_bilinear)
+                const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
+                const int sx = sx0 >> 5, sy = sy0 >> 5;
+                if ((feat & F_SRC_VEC) && sx >= A.src_rect[0] && sx + 2 <= A.src_rect[2] && sy >= A.src_rect[1] && sy + 2 <= A.src_rect[3]) {
+                    uint32_t N[C];
+                    sample_u8_bilinear<PIX>(sx0, sy0, A, N);
+                    uint32_t s[C];
+                    #pragma unroll
+                    for (int ch = 0; ch < C; ++ch) s[ch] = (uint32_t)min((int)(N[ch] >> 10), A.u8_limit);   // trunc(min(N/1024, limit))
+                    PIX::store_scalars(out, dvec, s);
+                    return;
+                }
+                sample_generic<I, PIX>(sx0, sy0, A, pixel);
+            } else {
+                sample_input_at<I, PIX>(u, v, A, pixel);                                                         // :615
+            }
         }
-        sample_input_at<I, PIX>(u, v, A, pixel);                                                                 // :615
     }
-    if (fix_range) remap_colorrange<C>(pixel, is_y);                                                             // :619-621
-    PIX::store(out, A.dst_vec_ok != 0, pixel);                                                                   // :622
+    if (feat & F_FIXRANGE) remap_colorrange<C>(pixel, (feat & F_IS_Y) != 0);                                     // :608-610 / :619-621
+    PIX::store(out, dvec, pixel);                                                                                // :611 / :622
 }
 
 } // namespace gf
