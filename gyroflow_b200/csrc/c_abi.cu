@@ -39,7 +39,9 @@ struct gf_cuda_ctx {
     int pixel_type = 0, distortion_model = 0, digital_lens = 0, interpolation = 0;
     int layout = 0, bpp = 0;
     int width = 0, height = 0, output_width = 0, output_height = 0;    // Stabilization.size / output_size
-    KernelFn fn = nullptr;
+    KernelFn fn = nullptr;        // general instantiation (run-time feature tests)
+    KernelFn fn_lean = nullptr;   // rare features compiled out
+    unsigned long long lean_launches = 0;
     cudaStream_t stream = nullptr;
     size_t max_rows = 0;
     Slot slots[kSlots];
@@ -82,17 +84,17 @@ bool pix_layout(int pixel_type, int* layout, int* bpp) {
     }
 }
 
-KernelFn find_kernel(int lens, int digital, int layout, int interp) {
+KernelFn find_kernel(int lens, int digital, int layout, int interp, int lean) {
     switch (lens) {
-    case GF_LENS_OPENCV_FISHEYE:     return gf_kernel_opencv_fisheye(digital, layout, interp);
-    case GF_LENS_OPENCV_STANDARD:    return gf_kernel_opencv_standard(digital, layout, interp);
-    case GF_LENS_POLY3:              return gf_kernel_poly3(digital, layout, interp);
-    case GF_LENS_POLY5:              return gf_kernel_poly5(digital, layout, interp);
-    case GF_LENS_PTLENS:             return gf_kernel_ptlens(digital, layout, interp);
-    case GF_LENS_INSTA360:           return gf_kernel_insta360(digital, layout, interp);
-    case GF_LENS_SONY:               return gf_kernel_sony(digital, layout, interp);
-    case GF_LENS_GENERIC_POLYNOMIAL: return gf_kernel_generic_polynomial(digital, layout, interp);
-    case GF_LENS_GOPRO:              return gf_kernel_gopro(digital, layout, interp);
+    case GF_LENS_OPENCV_FISHEYE:     return gf_kernel_opencv_fisheye(digital, layout, interp, lean);
+    case GF_LENS_OPENCV_STANDARD:    return gf_kernel_opencv_standard(digital, layout, interp, lean);
+    case GF_LENS_POLY3:              return gf_kernel_poly3(digital, layout, interp, lean);
+    case GF_LENS_POLY5:              return gf_kernel_poly5(digital, layout, interp, lean);
+    case GF_LENS_PTLENS:             return gf_kernel_ptlens(digital, layout, interp, lean);
+    case GF_LENS_INSTA360:           return gf_kernel_insta360(digital, layout, interp, lean);
+    case GF_LENS_SONY:               return gf_kernel_sony(digital, layout, interp, lean);
+    case GF_LENS_GENERIC_POLYNOMIAL: return gf_kernel_generic_polynomial(digital, layout, interp, lean);
+    case GF_LENS_GOPRO:              return gf_kernel_gopro(digital, layout, interp, lean);
     default: return nullptr;
     }
 }
@@ -252,7 +254,7 @@ GF_API int gf_pixel_bytes(int pixel_type) { int l, b; return pix_layout(pixel_ty
 GF_API int gf_combo_supported(int pixel_type, int distortion_model, int digital_lens, int interpolation) {
     int l, b;
     if (!pix_layout(pixel_type, &l, &b)) return 0;
-    return find_kernel(distortion_model, digital_lens, l, interpolation) != nullptr ? 1 : 0;
+    return find_kernel(distortion_model, digital_lens, l, interpolation, 0) != nullptr ? 1 : 0;
 }
 
 GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_params* params, int pixel_type,
@@ -263,12 +265,13 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     int layout = 0, bpp = 0;
     if (!pix_layout(pixel_type, &layout, &bpp)) return fail(nullptr, GF_ERR_BAD_PARAMS, "unknown pixel type");
     { int rc = validate(nullptr, params, in, out, bpp); if (rc != GF_OK) return rc; }
-    KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation);
+    KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0);
+    KernelFn fn_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1);
     if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
 
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
-    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn;
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean;
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -384,7 +387,11 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const dim3 block(GF_BLOCK_X, GF_BLOCK_Y);
     const dim3 grid((A.out_cols + GF_BLOCK_X - 1) / GF_BLOCK_X, (A.out_rows + GF_BLOCK_Y - 1) / GF_BLOCK_Y);
     if (grid.x == 0 || grid.y == 0 || grid.y > 65535) return fail(ctx, GF_ERR_BAD_PARAMS, "output buffer geometry out of range");
-    ctx->fn<<<grid, block, 0, st>>>(A);
+    // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
+    const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
+                         (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
+    if (lean_ok) { ctx->fn_lean<<<grid, block, 0, st>>>(A); ctx->lean_launches++; }
+    else         { ctx->fn<<<grid, block, 0, st>>>(A); }
     CK(cudaGetLastError());
     ctx->launches++;
     if (!tables_on_device) {

@@ -1,10 +1,10 @@
 // insta360 x {none, digital_stretch} (src/qt_gpu/compiled/compile_shaders.sh:6-27)
 #include "kernel_registry.h"
 namespace gf {
-KernelFn gf_kernel_insta360(int digital, int layout, int interp) {
+KernelFn gf_kernel_insta360(int digital, int layout, int interp, int lean) {
     switch (digital) {
-    case GF_LENS_NONE:            return pick_layout<GF_LENS_INSTA360, GF_LENS_NONE>(layout, interp);
-    case GF_LENS_DIGITAL_STRETCH: return pick_layout<GF_LENS_INSTA360, GF_LENS_DIGITAL_STRETCH>(layout, interp);
+    case GF_LENS_NONE:            return pick_layout<GF_LENS_INSTA360, GF_LENS_NONE>(layout, interp, lean);
+    case GF_LENS_DIGITAL_STRETCH: return pick_layout<GF_LENS_INSTA360, GF_LENS_DIGITAL_STRETCH>(layout, interp, lean);
     default: return nullptr;
     }
 }

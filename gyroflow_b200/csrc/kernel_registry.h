@@ -20,41 +20,42 @@ enum {
 struct KernelInfo { KernelFn fn; int bytes_per_pixel; };
 
 // implemented once per lens model in inst_<model>.cu; returns nullptr for combinations that are not compiled
-KernelFn gf_kernel_opencv_fisheye(int digital, int layout, int interp);
-KernelFn gf_kernel_opencv_standard(int digital, int layout, int interp);
-KernelFn gf_kernel_poly3(int digital, int layout, int interp);
-KernelFn gf_kernel_poly5(int digital, int layout, int interp);
-KernelFn gf_kernel_ptlens(int digital, int layout, int interp);
-KernelFn gf_kernel_insta360(int digital, int layout, int interp);
-KernelFn gf_kernel_sony(int digital, int layout, int interp);
-KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp);
-KernelFn gf_kernel_gopro(int digital, int layout, int interp);
+// `lean` selects the instantiation with the rare per-frame features compiled out (see F_GENERAL_ONLY)
+KernelFn gf_kernel_opencv_fisheye(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_opencv_standard(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_poly3(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_poly5(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_ptlens(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_insta360(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_sony(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp, int lean);
+KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
 
 template <int LENS, int DIGITAL, class PIX>
-static KernelFn pick_interp(int interp) {
+static KernelFn pick_interp(int interp, int lean) {
     switch (interp) {
-    case GF_INTERP_BILINEAR: return warp_kernel<LENS, DIGITAL, PIX, 2>;
+    case GF_INTERP_BILINEAR: return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
 #ifdef GF_ENABLE_HIGH_ORDER
-    case GF_INTERP_BICUBIC:  return warp_kernel<LENS, DIGITAL, PIX, 4>;
-    case GF_INTERP_LANCZOS4: return warp_kernel<LENS, DIGITAL, PIX, 8>;
+    case GF_INTERP_BICUBIC:  return lean ? warp_kernel<LENS, DIGITAL, PIX, 4, false> : warp_kernel<LENS, DIGITAL, PIX, 4, true>;
+    case GF_INTERP_LANCZOS4: return lean ? warp_kernel<LENS, DIGITAL, PIX, 8, false> : warp_kernel<LENS, DIGITAL, PIX, 8, true>;
 #endif
     default: return nullptr;
     }
 }
 template <int LENS, int DIGITAL>
-static KernelFn pick_layout(int layout, int interp) {
+static KernelFn pick_layout(int layout, int interp, int lean) {
     switch (layout) {
-    case LAY_1U8:  return pick_interp<LENS, DIGITAL, Pix<1, SC_U8>>(interp);
-    case LAY_2U8:  return pick_interp<LENS, DIGITAL, Pix<2, SC_U8>>(interp);
-    case LAY_3U8:  return pick_interp<LENS, DIGITAL, Pix<3, SC_U8>>(interp);
-    case LAY_4U8:  return pick_interp<LENS, DIGITAL, Pix<4, SC_U8>>(interp);
-    case LAY_1U16: return pick_interp<LENS, DIGITAL, Pix<1, SC_U16>>(interp);
-    case LAY_2U16: return pick_interp<LENS, DIGITAL, Pix<2, SC_U16>>(interp);
-    case LAY_3U16: return pick_interp<LENS, DIGITAL, Pix<3, SC_U16>>(interp);
-    case LAY_4U16: return pick_interp<LENS, DIGITAL, Pix<4, SC_U16>>(interp);
-    case LAY_1F32: return pick_interp<LENS, DIGITAL, Pix<1, SC_F32>>(interp);
-    case LAY_4F32: return pick_interp<LENS, DIGITAL, Pix<4, SC_F32>>(interp);
-    case LAY_4F16: return pick_interp<LENS, DIGITAL, Pix<4, SC_F16>>(interp);
+    case LAY_1U8:  return pick_interp<LENS, DIGITAL, Pix<1, SC_U8>>(interp, lean);
+    case LAY_2U8:  return pick_interp<LENS, DIGITAL, Pix<2, SC_U8>>(interp, lean);
+    case LAY_3U8:  return pick_interp<LENS, DIGITAL, Pix<3, SC_U8>>(interp, lean);
+    case LAY_4U8:  return pick_interp<LENS, DIGITAL, Pix<4, SC_U8>>(interp, lean);
+    case LAY_1U16: return pick_interp<LENS, DIGITAL, Pix<1, SC_U16>>(interp, lean);
+    case LAY_2U16: return pick_interp<LENS, DIGITAL, Pix<2, SC_U16>>(interp, lean);
+    case LAY_3U16: return pick_interp<LENS, DIGITAL, Pix<3, SC_U16>>(interp, lean);
+    case LAY_4U16: return pick_interp<LENS, DIGITAL, Pix<4, SC_U16>>(interp, lean);
+    case LAY_1F32: return pick_interp<LENS, DIGITAL, Pix<1, SC_F32>>(interp, lean);
+    case LAY_4F32: return pick_interp<LENS, DIGITAL, Pix<4, SC_F32>>(interp, lean);
+    case LAY_4F16: return pick_interp<LENS, DIGITAL, Pix<4, SC_F16>>(interp, lean);
     default: return nullptr;
     }
 }

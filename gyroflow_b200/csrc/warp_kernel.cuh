@@ -49,6 +49,21 @@ enum : uint32_t {
     F_T3D        = 1u << 20,  // translation3d != 0 (x + 0.0f only differs from x in the sign of zero, which no consumer sees)
 };
 
+// Features the specialised ("lean") instantiation compiles out entirely.  The reference's OpenCL backend does the same
+// thing at run time: it constant-folds every `(params->flags & N)` test into the program text before building it
+// (src/core/gpu/opencl.rs:207-211).  A launch whose feature word has any of these bits uses the general instantiation.
+constexpr uint32_t F_GENERAL_ONLY = F_HRS | F_RLIMIT | F_REFRACT | F_MESH | F_HSTRETCH | F_VSTRETCH | F_LCA | F_INROT |
+                                    F_BG1 | F_BG2 | F_BG3 | F_FIXRANGE | F_FILLBG | F_LENS_NOOP | F_FB_INV | F_T3D;
+constexpr uint32_t F_LEAN_REQUIRED = F_SRC_VEC | F_DST_VEC;   // and F_DIGITAL iff a digital lens is compiled in
+
+// has<GEN>(feat, bit): run-time test in the general kernel, compile-time constant in the lean one
+template <bool GEN> __device__ __forceinline__ bool has(uint32_t feat, uint32_t bit) {
+    if (GEN) return (feat & bit) != 0;
+    if (bit & F_GENERAL_ONLY) return false;
+    if (bit & (F_LEAN_REQUIRED | F_DIGITAL)) return true;
+    return (feat & bit) != 0;        // F_RS, F_IS_Y stay dynamic
+}
+
 struct WarpArgs {
     gf_kernel_params p;             // verbatim KernelParams
     const uint8_t* src;
@@ -269,7 +284,7 @@ GF_DEV float map_apply(float x, const MapC& m) {
 // ------------------------------------------------------------------------------------------
 // rotate_and_distort — cpu_undistort.rs:133-228
 // ------------------------------------------------------------------------------------------
-template <int LENS, int DIGITAL>
+template <int LENS, int DIGITAL, bool GEN>
 GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs& A, float& ou, float& ov) {
     const gf_kernel_params& P = A.p;
     const uint32_t feat = A.feat;
@@ -279,11 +294,11 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
     float _x = (px * m01.x) + (py * m01.y) + m23.x;
     float _y = (px * m23.y) + (py * m45.x) + m45.y;
     float _w = (px * m67.x) + (py * m67.y) + m8_9.x;
-    if (feat & F_T3D) { _x += P.translation3d[0]; _y += P.translation3d[1]; _w += P.translation3d[2]; }   // :135-137
+    if (has<GEN>(feat, F_T3D)) { _x += P.translation3d[0]; _y += P.translation3d[1]; _w += P.translation3d[2]; }   // :135-137
     if (!(_w > 0.0f)) return false;
-    if (feat & (F_RLIMIT | F_REFRACT)) {
-        if ((feat & F_RLIMIT) && (_x * _x + _y * _y) > A.r_limit_sq * _w) return false;                 // :139 (sic: * _w)
-        if (feat & F_REFRACT) {                                                                          // :143-152 (_w != 0 holds: _w > 0)
+    if (has<GEN>(feat, F_RLIMIT | F_REFRACT)) {
+        if (has<GEN>(feat, F_RLIMIT) && (_x * _x + _y * _y) > A.r_limit_sq * _w) return false;          // :139 (sic: * _w)
+        if (has<GEN>(feat, F_REFRACT)) {                                                                          // :143-152 (_w != 0 holds: _w > 0)
             const float r = sqrtf(_x * _x + _y * _y) / _w;
             const float sin_theta_d = (r / sqrtf(1.0f + r * r)) * P.light_refraction_coefficient;
             const float r_d = sin_theta_d / sqrtf(1.0f - sin_theta_d * sin_theta_d);
@@ -292,7 +307,7 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
     }
 
     float ux, uy;
-    Lens<LENS>::distort(_x, _y, _w, P, (feat & F_LENS_NOOP) != 0, ux, uy);                             // :154
+    Lens<LENS>::distort(_x, _y, _w, P, has<GEN>(feat, F_LENS_NOOP), ux, uy);                             // :154
     ux = ux * P.f[0]; uy = uy * P.f[1];                                                                // :155
 
     // :157 — any of m[9..13] != 0.0 (NaN counts as non-zero; -0.0 does not): all bits but the sign
@@ -307,9 +322,9 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
 
     ux = ux + P.c[0]; uy = uy + P.c[1];                                                                // :167
 
-    if (feat & F_MESH) {
+    if (has<GEN>(feat, F_MESH)) {
         const MeshView mesh{A.mesh};
-        const bool inv = (feat & F_FB_INV) != 0;
+        const bool inv = has<GEN>(feat, F_FB_INV);
         const double mesh0 = mesh[0];
         if (mesh0 > 10.0) {                                                                            // :169-185
             const float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
@@ -349,15 +364,15 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
         }
     }
 
-    if (DIGITAL != GF_LENS_NONE && (feat & F_DIGITAL)) {                                               // :216-220
+    if (DIGITAL != GF_LENS_NONE && has<GEN>(feat, F_DIGITAL)) {                                        // :216-220
         float dx, dy;
         Lens<DIGITAL>::distort(ux, uy, 1.0f, P, false, dx, dy);
         ux = dx; uy = dy;
     }
 
-    if (feat & (F_HSTRETCH | F_VSTRETCH)) {                                                            // :222-223
-        if (feat & F_HSTRETCH) ux /= P.input_horizontal_stretch;
-        if (feat & F_VSTRETCH) uy /= P.input_vertical_stretch;
+    if (has<GEN>(feat, F_HSTRETCH | F_VSTRETCH)) {                                                     // :222-223
+        if (has<GEN>(feat, F_HSTRETCH)) ux /= P.input_horizontal_stretch;
+        if (has<GEN>(feat, F_VSTRETCH)) uy /= P.input_vertical_stretch;
     }
 
     ou = ux; ov = uy;
@@ -371,17 +386,17 @@ GF_DEV void rotate_point(float px, float py, float ca, float sa, float ox, float
 }
 
 // undistort_coord — cpu_undistort.rs:421-517.  (opx, opy) = out_pos after the output-rect mapping of :422-423.
-template <int LENS, int DIGITAL>
+template <int LENS, int DIGITAL, bool GEN>
 GF_DEV bool undistort_coord(float opx, float opy, const WarpArgs& A, float& ru, float& rv) {
     const gf_kernel_params& P = A.p;
     const uint32_t feat = A.feat;
     opx += P.translation2d[0];
     opy += P.translation2d[1];
 
-    if (feat & F_LCA) {                                                                                // :429-460
+    if (has<GEN>(feat, F_LCA)) {                                                                       // :429-460
         float nx = opx, ny = opy;
         const float ocx = A.out_c[0], ocy = A.out_c[1], ofx = A.out_f[0], ofy = A.out_f[1];
-        if (DIGITAL != GF_LENS_NONE && (feat & F_DIGITAL)) {
+        if (DIGITAL != GF_LENS_NONE && has<GEN>(feat, F_DIGITAL)) {
             const float uzx = (nx - ocx) * P.fov + ocx, uzy = (ny - ocy) * P.fov + ocy;
             float tx, ty;
             if (Lens<DIGITAL>::undistort(uzx, uzy, P, false, tx, ty)) {
@@ -390,8 +405,8 @@ GF_DEV bool undistort_coord(float opx, float opy, const WarpArgs& A, float& ru, 
             }
         }
         nx = (nx - ocx) / ofx; ny = (ny - ocy) / ofy;
-        { float tx, ty; if (Lens<LENS>::undistort(nx, ny, P, (feat & F_LENS_NOOP) != 0, tx, ty)) { nx = tx; ny = ty; } }
-        if (feat & F_REFRACT) {
+        { float tx, ty; if (Lens<LENS>::undistort(nx, ny, P, has<GEN>(feat, F_LENS_NOOP), tx, ty)) { nx = tx; ny = ty; } }
+        if (has<GEN>(feat, F_REFRACT)) {
             const float r = sqrtf(nx * nx + ny * ny);
             if (r != 0.0f) {
                 const float sin_theta_d = (r / sqrtf(1.0f + r * r)) / P.light_refraction_coefficient;
@@ -407,13 +422,13 @@ GF_DEV bool undistort_coord(float opx, float opy, const WarpArgs& A, float& ru, 
     }
 
     // rolling-shutter row :465-482
-    const bool hrs = (feat & F_HRS) != 0;
+    const bool hrs = has<GEN>(feat, F_HRS);
     const int lim = A.rs_lim;
     int sy = as_i32(rs_round(hrs ? opx : opy));
     sy = max(min(sy, lim), 0);
-    if (feat & F_RS) {
+    if (has<GEN>(feat, F_RS)) {
         float tu, tv;
-        if (rotate_and_distort<LENS, DIGITAL>(opx, opy, (uint32_t)P.matrix_count / 2u, A, tu, tv)) {
+        if (rotate_and_distort<LENS, DIGITAL, GEN>(opx, opy, (uint32_t)P.matrix_count / 2u, A, tu, tv)) {
             const int v = as_i32(rs_round(hrs ? tu : tv));
             sy = max(min(v, lim), 0);
         }
@@ -421,19 +436,19 @@ GF_DEV bool undistort_coord(float opx, float opy, const WarpArgs& A, float& ru, 
     const uint32_t idx = min((uint32_t)sy, (uint32_t)(P.matrix_count - 1));
 
     float u, v;
-    if (!rotate_and_distort<LENS, DIGITAL>(opx, opy, idx, A, u, v)) return false;                      // :483
+    if (!rotate_and_distort<LENS, DIGITAL, GEN>(opx, opy, idx, A, u, v)) return false;                      // :483
 
-    if (feat & (F_INROT | F_BG1 | F_BG2)) {
-        if (feat & F_INROT) {                                                                          // :485-491
+    if (has<GEN>(feat, F_INROT | F_BG1 | F_BG2)) {
+        if (has<GEN>(feat, F_INROT)) {                                                                          // :485-491
             float nu, nv;
             rotate_point(u, v, A.rot_cos, A.rot_sin, A.width_f / 2.0f, A.height_f / 2.0f, A.frame_w / 2.0f, A.frame_h / 2.0f, nu, nv);
             u = nu; v = nv;
         }
         const float width_f = A.width_f, height_f = A.height_f;
-        if (feat & F_BG1) {                                                                            // edge repeat :495-499
+        if (has<GEN>(feat, F_BG1)) {                                                                   // edge repeat :495-499
             u = rs_min(rs_max(u, 3.0f), width_f - 3.0f);
             v = rs_min(rs_max(v, 3.0f), height_f - 3.0f);
-        } else if (feat & F_BG2) {                                                                     // edge mirror :500-509
+        } else if (has<GEN>(feat, F_BG2)) {                                                            // edge mirror :500-509
             const float rx = rs_round(u), ry = rs_round(v);
             const float width3 = width_f - 3.0f, height3 = height_f - 3.0f;
             if (rx > width3)  u = width3  - (rx - width3);
@@ -442,7 +457,7 @@ GF_DEV bool undistort_coord(float opx, float opy, const WarpArgs& A, float& ru, 
             if (ry < 3.0f)    v = 3.0f + height_f - (height3 + ry);
         }
     }
-    if (!(feat & F_BG3)) {                                                                             // :510-515
+    if (!has<GEN>(feat, F_BG3)) {                                                                      // :510-515
         u = map_apply(u, A.smap_x);
         v = map_apply(v, A.smap_y);
     }
@@ -572,13 +587,13 @@ template <int C> GF_DEV void remap_colorrange(float (&px)[C], bool is_y) {      
 
 // sample_input_at at (u, v): picks the integer / interior / generic sampler.  Returns the clamped float sums
 // (what the reference's `sum` holds after :413-418).
-template <int I, class PIX>
+template <int I, class PIX, bool GEN>
 GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
     const float offset = I == 2 ? 0.0f : (I == 4 ? 1.0f : 3.0f);
     const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
     const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
     const int sx = sx0 >> 5, sy = sy0 >> 5;
-    const bool interior = (A.feat & F_SRC_VEC) && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
+    const bool interior = has<GEN>(A.feat, F_SRC_VEC) && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
     if (interior) sample_interior<I, PIX>(sx0, sy0, A, sum);
     else          sample_generic<I, PIX>(sx0, sy0, A, sum);
 }
@@ -589,7 +604,7 @@ GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum
 #define GF_BLOCK_X 32
 #define GF_BLOCK_Y 8
 
-template <int LENS, int DIGITAL, class PIX, int I>
+template <int LENS, int DIGITAL, class PIX, int I, bool GEN>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
 warp_kernel(const __grid_constant__ WarpArgs A) {
     const gf_kernel_params& P = A.p;
@@ -606,15 +621,15 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
     if (!(opx >= 0.0f && opy >= 0.0f && as_i32(opx) < P.output_width && as_i32(opy) < P.output_height)) return;   // :551
 
     uint8_t* const out = A.dst + off;
-    const bool dvec = (feat & F_DST_VEC) != 0;
+    const bool dvec = has<GEN>(feat, F_DST_VEC);
     float pixel[C];
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
-    if (feat & F_FILLBG) { PIX::store(out, dvec, pixel); return; }                                              // :558-561
+    if (has<GEN>(feat, F_FILLBG)) { PIX::store(out, dvec, pixel); return; }                                              // :558-561
 
     float u, v;
-    if (undistort_coord<LENS, DIGITAL>(opx, opy, A, u, v)) {                                                    // :565
-        if (feat & F_BG3) {                                                                                      // :576-613
+    if (undistort_coord<LENS, DIGITAL, GEN>(opx, opy, A, u, v)) {                                                    // :565
+        if (has<GEN>(feat, F_BG3)) {                                                                             // :576-613
             const float width_f = A.width_f, height_f = A.height_f;
             const float widthf = width_f - 1.0f, heightf = height_f - 1.0f;
             const float feather = rs_max(P.background_margin_feather * heightf, 0.0001f);
@@ -629,16 +644,16 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
             u   = map_apply(u,   A.smap_x); v   = map_apply(v,   A.smap_y);
             p2x = map_apply(p2x, A.smap_x); p2y = map_apply(p2y, A.smap_y);
             float c1[C], c2[C];
-            sample_input_at<I, PIX>(u, v, A, c1);
-            sample_input_at<I, PIX>(p2x, p2y, A, c2);
+            sample_input_at<I, PIX, GEN>(u, v, A, c1);
+            sample_input_at<I, PIX, GEN>(p2x, p2y, A, c2);
             #pragma unroll
             for (int ch = 0; ch < C; ++ch) pixel[ch] = c1[ch] * alpha + c2[ch] * (1.0f - alpha);
         } else {
-            if (I == 2 && PIX::SCALAR == SC_U8 && !(feat & F_FIXRANGE)) {
+            if (I == 2 && PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE)) {
                 // 8-bit bilinear interior: integer arithmetic, exact (see sample_u8_bilinear)
                 const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
                 const int sx = sx0 >> 5, sy = sy0 >> 5;
-                if ((feat & F_SRC_VEC) && sx >= A.src_rect[0] && sx + 2 <= A.src_rect[2] && sy >= A.src_rect[1] && sy + 2 <= A.src_rect[3]) {
+                if (has<GEN>(feat, F_SRC_VEC) && sx >= A.src_rect[0] && sx + 2 <= A.src_rect[2] && sy >= A.src_rect[1] && sy + 2 <= A.src_rect[3]) {
                     uint32_t N[C];
                     sample_u8_bilinear<PIX>(sx0, sy0, A, N);
                     uint32_t s[C];
@@ -649,11 +664,11 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
                 }
                 sample_generic<I, PIX>(sx0, sy0, A, pixel);
             } else {
-                sample_input_at<I, PIX>(u, v, A, pixel);                                                         // :615
+                sample_input_at<I, PIX, GEN>(u, v, A, pixel);                                                    // :615
             }
         }
     }
-    if (feat & F_FIXRANGE) remap_colorrange<C>(pixel, (feat & F_IS_Y) != 0);                                     // :608-610 / :619-621
+    if (has<GEN>(feat, F_FIXRANGE)) remap_colorrange<C>(pixel, (feat & F_IS_Y) != 0);                                     // :608-610 / :619-621
     PIX::store(out, dvec, pixel);                                                                                // :611 / :622
 }
 
