@@ -104,6 +104,7 @@ EXPORTS = [
     ("gf_cuda_last_error", C.c_char_p, [C.c_void_p]),
     ("gf_cuda_backend_name", C.c_char_p, []),
     ("gf_cuda_launch_count", C.c_uint64, [C.c_void_p]),
+    ("gf_cuda_selftest", C.c_int, [C.c_int, C.c_ulonglong, C.c_ulonglong, _P(C.c_ulonglong)]),
 ]
 
 _lib = None

@@ -41,6 +41,8 @@ struct gf_cuda_ctx {
     int width = 0, height = 0, output_width = 0, output_height = 0;    // Stabilization.size / output_size
     KernelFn fn = nullptr;        // general instantiation (run-time feature tests)
     KernelFn fn_lean = nullptr;   // rare features compiled out
+    KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe
+    unsigned long long x2_launches = 0;
     unsigned long long lean_launches = 0;
     cudaStream_t stream = nullptr;
     size_t max_rows = 0;
@@ -267,11 +269,12 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     { int rc = validate(nullptr, params, in, out, bpp); if (rc != GF_OK) return rc; }
     KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0);
     KernelFn fn_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1);
+    KernelFn fn_x2 = getenv("GF_DISABLE_X2") ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 2);
     if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
 
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
-    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean;
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2;
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -390,7 +393,11 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
-    if (lean_ok) { ctx->fn_lean<<<grid, block, 0, st>>>(A); ctx->lean_launches++; }
+    if (lean_ok && ctx->fn_x2) {
+        const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
+        ctx->fn_x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
+    }
+    else if (lean_ok) { ctx->fn_lean<<<grid, block, 0, st>>>(A); ctx->lean_launches++; }
     else         { ctx->fn<<<grid, block, 0, st>>>(A); }
     CK(cudaGetLastError());
     ctx->launches++;

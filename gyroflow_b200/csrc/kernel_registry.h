@@ -3,7 +3,7 @@
 // splicing lens-model source text into the OpenCL/WGSL program at run time (gpu/opencl.rs:184-211);
 // here every valid combination is compiled for sm_100a up front and looked up by id.
 #pragma once
-#include "warp_kernel.cuh"
+#include "warp_kernel_x2.cuh"
 
 namespace gf {
 
@@ -31,8 +31,17 @@ KernelFn gf_kernel_sony(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
 
+// lean == 2: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form
+template <int LENS, int DIGITAL, class PIX>
+static KernelFn pick_x2(int interp) {
+    if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) {
+        if (interp == GF_INTERP_BILINEAR) return warp_kernel_x2<LENS, PIX>;
+    }
+    return nullptr;
+}
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
+    if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp);
     switch (interp) {
     case GF_INTERP_BILINEAR: return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
 #ifdef GF_ENABLE_HIGH_ORDER

@@ -1,0 +1,70 @@
+// selftest.cu — device-side check of the packed f32x2 primitives against the scalar operations they replace.
+// gf_cuda_selftest(device, n, out[4]): n pseudo-random operand pairs per primitive; out = mismatch counts for
+// {div_exact_checked vs '/', sqrt_exact vs sqrtf, atanf2 vs gf_atanf, div_uniform vs '/'}.
+#include <cuda_runtime.h>
+#include "../../include/gyroflow_cuda.h"
+#include "warp_kernel_x2.cuh"
+
+using namespace gf;
+
+namespace {
+__device__ __forceinline__ uint32_t mix(uint64_t v) {
+    v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+    return (uint32_t)v;
+}
+// operand generator: a mix of fully random bit patterns, "coordinate-like" magnitudes and values near 1
+__device__ __forceinline__ float gen(uint64_t i, uint32_t salt) {
+    const uint32_t h = mix(i * 0x9E3779B97F4A7C15ULL + salt);
+    const uint32_t sel = mix(i + 77u * salt) & 7u;
+    if (sel < 3) return __uint_as_float(h);                                             // anything, incl. NaN/inf/denormals
+    if (sel < 6) return __uint_as_float((h & 0x807fffffu) | ((100u + (mix(i ^ salt) % 56u)) << 23));   // 2^-27 .. 2^28
+    return __uint_as_float((h & 0x007fffffu) | 0x3f800000u) - ((h >> 31) ? 0.0f : 1.0f);        // [1,2) or [0,1)
+}
+__device__ __forceinline__ bool same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
+
+__global__ void selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long* out) {
+    __shared__ p2::AtanRow tab[p2::ATAN_ROWS];
+    p2::atan_table_init(tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    unsigned long long bad[4] = {0, 0, 0, 0};
+    MapC m; m.in_min = 0.0f; m.mul = 1.0f; m.add = 0.0f; m.identity = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = i + seed;
+        const float a0 = gen(k, 1), a1 = gen(k, 2), b0 = gen(k, 3), b1 = gen(k, 4);
+        const p2::f2 q = p2::div_exact_checked(p2::mk(a0, a1), p2::mk(b0, b1));
+        if (!same(q.x, a0 / b0)) bad[0]++;
+        if (!same(q.y, a1 / b1)) bad[0]++;
+        const float s0 = fabsf(a0), s1 = fabsf(b1);
+        const p2::f2 r = p2::sqrt_exact(p2::mk(s0, s1));
+        if (!same(r.x, sqrtf(s0))) bad[1]++;
+        if (!same(r.y, sqrtf(s1))) bad[1]++;
+        const p2::f2 t = p2::atanf2(p2::mk(a1, b0), tab);
+        if (!same(t.x, gf_atanf(a1))) bad[2]++;
+        if (!same(t.y, gf_atanf(b0))) bad[2]++;
+        // uniform divisor: typical frame sizes and random ones
+        const float dv = (k & 1) ? (float)(16 + (mix(k) % 16368)) : fabsf(gen(k, 5));
+        m.div = dv; m.rcp = 1.0f / dv;
+        const float ad = fabsf(dv);
+        m.fast_div = (ad >= 0x1p-40f && ad <= 0x1p40f) ? 1 : 0;
+        if (!same(div_uniform(a0, m), a0 / dv)) bad[3]++;
+        const p2::f2 mq = map_apply_x2(p2::mk(a0, b1), m);
+        if (!same(mq.x, ((a0 - 0.0f) * 1.0f) / dv + 0.0f)) bad[3]++;
+        if (!same(mq.y, ((b1 - 0.0f) * 1.0f) / dv + 0.0f)) bad[3]++;
+    }
+    for (int j = 0; j < 4; ++j) if (bad[j]) atomicAdd(&out[j], bad[j]);
+}
+} // namespace
+
+extern "C" GF_API int gf_cuda_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long* out4) {
+    if (!out4) return GF_ERR_BAD_PARAMS;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 4 * sizeof(unsigned long long)) != cudaSuccess) return GF_ERR_CUDA;
+    cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+    selftest_kernel<<<148 * 8, 256>>>(n, seed, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    return GF_OK;
+}

@@ -249,6 +249,11 @@ GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL:
 GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */
 GF_API uint64_t    gf_cuda_launch_count(gf_cuda_ctx* ctx);   /* kernels launched by this ctx so far */
 
+/* Device self-test of the exact packed-f32x2 primitives (division, square root, atanf, uniform-divisor division)
+ * against the scalar IEEE operations they replace: n pseudo-random operand sets, mismatch counts in out4[0..3].
+ * No reference counterpart (test hook). */
+GF_API int         gf_cuda_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long* out4);
+
 #ifdef __cplusplus
 }
 #endif
