@@ -134,6 +134,17 @@ class CudaWrapper:
         if rc != 0:
             raise self._err(rc)
 
+    def undistort_image_async(self, buffers: Buffers, itm: FrameTransform, stream: int = 0):
+        """Enqueue only (HOST buffers must be pinned and outlive the call); pair with synchronize()."""
+        i, o = buffers.input.to_c(), buffers.output.to_c()
+        m = np.ascontiguousarray(itm.matrices, dtype=np.float32)
+        mesh = np.ascontiguousarray(itm.mesh_data, dtype=np.float32)
+        rc = self._lib.gf_cuda_undistort_image_async(
+            self._h, C.byref(i), C.byref(o), C.byref(itm.kernel_params),
+            m.ctypes.data, m.shape[0], mesh.ctypes.data if mesh.size else None, mesh.size, stream or None)
+        if rc != 0:
+            raise self._err(rc)
+
     def undistort_image_dev(self, buffers: Buffers, params: abi.KernelParams, matrices_dev: int, matrix_rows: int,
                             mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0):
         i, o = buffers.input.to_c(), buffers.output.to_c()

@@ -324,7 +324,7 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
 
 static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
                     const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len,
-                    bool tables_on_device, void* cu_stream) {
+                    bool tables_on_device, void* cu_stream, bool sync_host = true) {
     if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
     { int rc = validate(ctx, p, in, out, ctx->bpp); if (rc != GF_OK) return rc; }
     if (!matrices) return fail(ctx, GF_ERR_NO_DATA, "NoStabilizationData: matrices is null");
@@ -410,7 +410,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
                                              (size_t)out->width * (size_t)bpp, (size_t)out->height, cudaMemcpyDeviceToHost, st));
         else            CK(cudaMemcpyAsync(out->ptr, ctx->d_dst, out->len, cudaMemcpyDeviceToHost, st));
     }
-    if (in->kind == GF_BUF_HOST || out->kind == GF_BUF_HOST) CK(cudaStreamSynchronize(st));
+    if (sync_host && (in->kind == GF_BUF_HOST || out->kind == GF_BUF_HOST)) CK(cudaStreamSynchronize(st));
     return GF_OK;
 }
 
@@ -425,6 +425,12 @@ GF_API int gf_cuda_undistort_image_dev(gf_cuda_ctx* ctx, const gf_buffer_desc* i
                                        const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
                                        const float* mesh_dev, size_t mesh_len, void* cu_stream) {
     return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream);
+}
+
+GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                         const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
+                                         const float* mesh, size_t mesh_len, void* cu_stream) {
+    return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream, false);
 }
 
 GF_API int gf_cuda_synchronize(gf_cuda_ctx* ctx) {

@@ -3,6 +3,7 @@
 // splicing lens-model source text into the OpenCL/WGSL program at run time (gpu/opencl.rs:184-211);
 // here every valid combination is compiled for sm_100a up front and looked up by id.
 #pragma once
+#include <cstdlib>
 #include "warp_kernel_x2.cuh"
 
 namespace gf {
@@ -35,7 +36,13 @@ KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_x2(int interp) {
     if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) {
-        if (interp == GF_INTERP_BILINEAR) return warp_kernel_x2<LENS, PIX>;
+        if (interp == GF_INTERP_BILINEAR) {
+            const char* e = getenv("GF_X2_MINB");            // tuning knob: resident blocks per SM the register budget targets
+            const int minb = e ? atoi(e) : 6;                // measured on B200 (4K RGBA8 fisheye+RS): 4 -> 7150, 5 -> 7740, 6 -> 7750 frames/s
+            if (minb == 4) return warp_kernel_x2<LENS, PIX, 4>;
+            if (minb == 5) return warp_kernel_x2<LENS, PIX, 5>;
+            return warp_kernel_x2<LENS, PIX, 6>;
+        }
     }
     return nullptr;
 }

@@ -2,6 +2,9 @@
 // gf_cuda_selftest(device, n, out[4]): n pseudo-random operand pairs per primitive; out = mismatch counts for
 // {div_exact_checked vs '/', sqrt_exact vs sqrtf, atanf2 vs gf_atanf, div_uniform vs '/'}.
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include "../../include/gyroflow_cuda.h"
 #include "warp_kernel_x2.cuh"
 
@@ -22,7 +25,7 @@ __device__ __forceinline__ float gen(uint64_t i, uint32_t salt) {
 }
 __device__ __forceinline__ bool same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
 
-__global__ void selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long* out) {
+__global__ void selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long* out, uint32_t* dbg) {
     __shared__ p2::AtanRow tab[p2::ATAN_ROWS];
     p2::atan_table_init(tab, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -39,7 +42,7 @@ __global__ void selftest_kernel(unsigned long long n, unsigned long long seed, u
         if (!same(r.x, sqrtf(s0))) bad[1]++;
         if (!same(r.y, sqrtf(s1))) bad[1]++;
         const p2::f2 t = p2::atanf2(p2::mk(a1, b0), tab);
-        if (!same(t.x, gf_atanf(a1))) bad[2]++;
+        if (!same(t.x, gf_atanf(a1))) { bad[2]++; if (dbg) { const unsigned slot = atomicAdd(&dbg[0], 1u); if (slot < 16) { dbg[1 + slot * 4] = __float_as_uint(a1); dbg[2 + slot * 4] = __float_as_uint(t.x); dbg[3 + slot * 4] = __float_as_uint(gf_atanf(a1)); dbg[4 + slot * 4] = __float_as_uint(b0); } } }
         if (!same(t.y, gf_atanf(b0))) bad[2]++;
         // uniform divisor: typical frame sizes and random ones
         const float dv = (k & 1) ? (float)(16 + (mix(k) % 16368)) : fabsf(gen(k, 5));
@@ -61,9 +64,19 @@ extern "C" GF_API int gf_cuda_selftest(int device, unsigned long long n, unsigne
     unsigned long long* d = nullptr;
     if (cudaMalloc(&d, 4 * sizeof(unsigned long long)) != cudaSuccess) return GF_ERR_CUDA;
     cudaMemset(d, 0, 4 * sizeof(unsigned long long));
-    selftest_kernel<<<148 * 8, 256>>>(n, seed, d);
+    uint32_t* dbg = nullptr;
+    if (getenv("GF_SELFTEST_DEBUG")) { cudaMalloc(&dbg, 65 * 4); cudaMemset(dbg, 0, 65 * 4); }
+    selftest_kernel<<<148 * 8, 256>>>(n, seed, d, dbg);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (dbg) {
+        uint32_t h[65]; cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        for (unsigned i = 0; i < (h[0] < 16 ? h[0] : 16); ++i) {
+            float x, g, w, o; memcpy(&x, &h[1 + i * 4], 4); memcpy(&g, &h[2 + i * 4], 4); memcpy(&w, &h[3 + i * 4], 4); memcpy(&o, &h[4 + i * 4], 4);
+            printf("atanf2 mismatch: x=%a (%08x) got=%a want=%a other-lane=%a (%08x)\n", x, h[1 + i * 4], g, w, o, h[4 + i * 4]);
+        }
+        cudaFree(dbg);
+    }
     cudaFree(d);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
     return GF_OK;

@@ -130,8 +130,8 @@ GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __
 
 #define GF_X2_ROWS_PER_BLOCK (2 * GF_BLOCK_Y)
 
-template <int LENS, class PIX>
-__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
+template <int LENS, class PIX, int MINB>
+__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     using namespace p2;
     __shared__ AtanRow atan_tab[ATAN_ROWS];

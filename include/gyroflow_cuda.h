@@ -244,6 +244,16 @@ GF_API int gf_cuda_undistort_image_dev(gf_cuda_ctx* ctx,
                                        const float* mesh_dev, size_t mesh_len,
                                        void* cu_stream);
 
+/* gf_cuda_undistort_image without the final stream synchronisation: with HOST buffers the H2D copy, the kernel and the
+ * D2H copy are only enqueued.  The host buffers must be page-locked and stay valid until gf_cuda_synchronize(ctx).
+ * Round-robin over a few contexts pipelines frame i+1's upload under frame i's kernel and frame i-1's download (the
+ * reference's render loop is strictly sequential per device, rendering/mod.rs:451,657-661).  No reference counterpart. */
+GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx,
+                                         const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                         const gf_kernel_params* params,
+                                         const float* matrices, size_t matrix_rows,
+                                         const float* mesh, size_t mesh_len, void* cu_stream);
+
 GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
 GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
 GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */

@@ -10,6 +10,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -1004,7 +1005,23 @@ static void* worker(void* arg) {
     return NULL;
 }
 
-int gf_oracle_online_cpus(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+/* usable hardware threads: online CPUs, capped by the cgroup v2 CPU quota (cpu.max) when the container has one —
+ * 128 runnable threads on a 16-CPU quota only get throttled. */
+int gf_oracle_online_cpus(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    if (n < 1) n = 1;
+    FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char q[64]; long period = 0;
+        if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            long quota = atol(q);
+            long cpus = (quota + period - 1) / period;
+            if (cpus >= 1 && cpus < n) n = cpus;
+        }
+        fclose(f);
+    }
+    return (int)n;
+}
 const char* gf_oracle_describe(void) {
     return "gyroflow CPU oracle (C restatement of cpu_undistort.rs @ b5e8828; libm transcendentals; parity unpinned)";
 }
