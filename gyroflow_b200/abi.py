@@ -57,6 +57,30 @@ class BufferDesc(C.Structure):
     ]
 
 
+class QuatTrack(C.Structure):
+    """gf_quat_track: sorted (timestamp us, unit quaternion w,i,j,k) arrays — TimeQuat, gyro_source/mod.rs:34."""
+    _fields_ = [("ts_us", C.POINTER(C.c_int64)), ("quats", C.POINTER(C.c_double)), ("n", C.c_size_t)]
+
+
+class ComputeParams(C.Structure):
+    """gf_compute_params: the slice of ComputeParams (compute_params.rs:13-69) FrameTransform::at_timestamp reads."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("output_width", C.c_int32), ("output_height", C.c_int32),
+        ("camera_matrix", C.c_double * 9), ("distortion_coeffs", C.c_double * 12), ("radial_distortion_limit", C.c_double),
+        ("input_horizontal_stretch", C.c_double), ("input_vertical_stretch", C.c_double), ("fov_scale", C.c_double),
+        ("fovs", C.POINTER(C.c_double)), ("n_fovs", C.c_size_t), ("minimal_fovs", C.POINTER(C.c_double)), ("n_minimal_fovs", C.c_size_t),
+        ("lens_optimal_fov", C.c_double), ("has_optimal_fov", C.c_int32),
+        ("frame_readout_time", C.c_double), ("readout_horizontal", C.c_int32), ("readout_inverted", C.c_int32),
+        ("framebuffer_inverted", C.c_int32), ("suppress_rotation", C.c_int32), ("fov_overview", C.c_int32),
+        ("video_rotation", C.c_double), ("lens_correction_amount", C.c_double), ("light_refraction_coefficient", C.c_double),
+        ("background_margin", C.c_double), ("background_margin_feather", C.c_double), ("background_mode", C.c_int32),
+        ("adaptive_zoom_center_offset", C.c_double * 2),
+        ("digital_lens_params", C.c_double * 16), ("n_digital_lens_params", C.c_int32),
+        ("gyro_offset_ms", C.c_double), ("duration_ms", C.c_double),
+        ("org", QuatTrack), ("smoothed", QuatTrack),
+    ]
+
+
 # KernelParamsFlags — stabilization/mod.rs:85-98
 FLAG_FIX_COLOR_RANGE, FLAG_HAS_DIGITAL_LENS, FLAG_FILL_WITH_BACKGROUND, FLAG_DRAWING_ENABLED = 1, 2, 4, 8
 FLAG_HORIZONTAL_RS, FLAG_HAS_SOURCE_RECT, FLAG_HAS_OUTPUT_RECT, FLAG_FRAMEBUFFER_INVERTED = 16, 32, 64, 128
@@ -107,6 +131,12 @@ EXPORTS = [
     ("gf_cuda_backend_name", C.c_char_p, []),
     ("gf_cuda_launch_count", C.c_uint64, [C.c_void_p]),
     ("gf_cuda_selftest", C.c_int, [C.c_int, C.c_ulonglong, C.c_ulonglong, _P(C.c_ulonglong)]),
+    ("gf_frame_transform_at_timestamp", C.c_int, [_P(ComputeParams), C.c_double, C.c_size_t, _P(KernelParams), C.c_void_p, C.c_size_t,
+                                                  _P(C.c_size_t), _P(C.c_double), _P(C.c_double)]),
+    ("gf_cuda_gyro_upload", C.c_int, [_P(C.c_void_p), C.c_int, _P(ComputeParams)]),
+    ("gf_cuda_gyro_free", None, [C.c_void_p]),
+    ("gf_cuda_frame_transform_dev", C.c_int, [C.c_void_p, _P(ComputeParams), C.c_double, C.c_size_t, _P(KernelParams), C.c_void_p, C.c_size_t,
+                                              _P(C.c_size_t), _P(C.c_double), _P(C.c_double), C.c_void_p]),
 ]
 
 _lib = None

@@ -172,3 +172,81 @@ class CudaWrapper:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------ per-frame transform producer
+
+
+class ComputeParams:
+    """Owns a gf_compute_params plus the numpy arrays it points to (quaternion tracks, fovs)."""
+
+    def __init__(self, kernel_params: abi.KernelParams, org, smoothed, frame_readout_time_ms=16.0, fovs=None, video_rotation=0.0,
+                 horizontal=False, inverted=False, framebuffer_inverted=False, fov_scale=1.0):
+        p = kernel_params
+        c = abi.ComputeParams()
+        c.width, c.height, c.output_width, c.output_height = p.width, p.height, p.output_width, p.output_height
+        c.camera_matrix[:] = [float(p.f[0]), 0.0, float(p.c[0]), 0.0, float(p.f[1]), float(p.c[1]), 0.0, 0.0, 1.0]
+        c.distortion_coeffs[:] = [float(v) for v in p.k]
+        c.radial_distortion_limit = float(p.r_limit)
+        c.input_horizontal_stretch = float(p.input_horizontal_stretch)
+        c.input_vertical_stretch = float(p.input_vertical_stretch)
+        c.fov_scale = fov_scale
+        self._fovs = np.ascontiguousarray(fovs if fovs is not None else [], dtype=np.float64)
+        if self._fovs.size:
+            c.fovs = self._fovs.ctypes.data_as(C.POINTER(C.c_double)); c.n_fovs = self._fovs.size
+        c.frame_readout_time = frame_readout_time_ms
+        c.readout_horizontal, c.readout_inverted = int(horizontal), int(inverted)
+        c.framebuffer_inverted = int(framebuffer_inverted)
+        c.video_rotation = video_rotation
+        c.lens_correction_amount = float(p.lens_correction_amount)
+        c.light_refraction_coefficient = float(p.light_refraction_coefficient)
+        c.background_mode = p.background_mode
+        c.digital_lens_params[:] = [float(v) for v in p.digital_lens_params]
+        c.n_digital_lens_params = 16
+        self._ots = np.ascontiguousarray(org.ts, dtype=np.int64); self._oq = np.ascontiguousarray(org.q, dtype=np.float64)
+        self._sts = np.ascontiguousarray(smoothed.ts, dtype=np.int64); self._sq = np.ascontiguousarray(smoothed.q, dtype=np.float64)
+        c.org = abi.QuatTrack(self._ots.ctypes.data_as(C.POINTER(C.c_int64)), self._oq.ctypes.data_as(C.POINTER(C.c_double)), len(self._ots))
+        c.smoothed = abi.QuatTrack(self._sts.ctypes.data_as(C.POINTER(C.c_int64)), self._sq.ctypes.data_as(C.POINTER(C.c_double)), len(self._sts))
+        c.duration_ms = float(self._ots[-1] - self._ots[0]) / 1000.0
+        self.c = c
+
+    def at_timestamp(self, timestamp_ms, frame=0):
+        """FrameTransform::at_timestamp on the host (f64): returns (KernelParams fields it sets, matrices[rows,14], fov, minimal_fov)."""
+        lib = abi.load_library()
+        rows_max = max(self.c.width, self.c.height)
+        m = np.zeros((rows_max, 14), np.float32)
+        kp = abi.KernelParams(); rows = C.c_size_t(); fov = C.c_double(); mfov = C.c_double()
+        rc = lib.gf_frame_transform_at_timestamp(C.byref(self.c), timestamp_ms, frame, C.byref(kp), m.ctypes.data, rows_max,
+                                                 C.byref(rows), C.byref(fov), C.byref(mfov))
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_frame_transform_at_timestamp")
+        return kp, m[: rows.value].copy(), fov.value, mfov.value
+
+
+class DeviceGyro:
+    """Quaternion tracks resident in HBM + the per-frame matrix kernel (gf_cuda_frame_transform_dev)."""
+
+    def __init__(self, cp: ComputeParams, device=0):
+        self._lib = abi.load_library()
+        self.cp = cp
+        h = C.c_void_p()
+        rc = self._lib.gf_cuda_gyro_upload(C.byref(h), device, C.byref(cp.c))
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_gyro_upload")
+        self._h = h
+
+    def frame_transform(self, timestamp_ms, matrices_dev: int, max_rows: int, frame=0, stream=0):
+        kp = abi.KernelParams(); rows = C.c_size_t(); fov = C.c_double(); mfov = C.c_double()
+        rc = self._lib.gf_cuda_frame_transform_dev(self._h, C.byref(self.cp.c), timestamp_ms, frame, C.byref(kp), matrices_dev, max_rows,
+                                                   C.byref(rows), C.byref(fov), C.byref(mfov), stream or None)
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_frame_transform_dev")
+        return kp, rows.value
+
+    def close(self):
+        if self._h:
+            self._lib.gf_cuda_gyro_free(self._h); self._h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass

@@ -106,7 +106,8 @@ class GyroTrack:
     def quat_at_timestamp(self, timestamp_ms):
         """gyro_source/mod.rs:857-879 with zero sync offset; vectorised over timestamp_ms."""
         t = np.atleast_1d(np.asarray(timestamp_ms, dtype=np.float64))
-        lookup = np.clip(np.round(t * 1000.0).astype(np.int64), self.ts[0], self.ts[-1])   # f64::round: half away; values are >= 0 here
+        us = t * 1000.0
+        lookup = np.clip((np.sign(us) * np.floor(np.abs(us) + 0.5)).astype(np.int64), self.ts[0], self.ts[-1])   # f64::round: half away from zero
         i1 = np.searchsorted(self.ts, lookup, side="right") - 1          # last key <= lookup
         i2 = np.minimum(np.searchsorted(self.ts, lookup, side="left"), len(self.ts) - 1)   # first key >= lookup
         t1, t2 = self.ts[i1], self.ts[i2]

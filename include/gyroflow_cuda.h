@@ -264,6 +264,60 @@ GF_API uint64_t    gf_cuda_launch_count(gf_cuda_ctx* ctx);   /* kernels launched
  * No reference counterpart (test hook). */
 GF_API int         gf_cuda_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long* out4);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Per-frame transform producer — FrameTransform::at_timestamp, src/core/stabilization/frame_transform.rs:165-350,
+ * with GyroSource::quat_at_timestamp, src/core/gyro_source/mod.rs:857-879.  f64 like the reference.
+ * Scope: the no-metadata case (fixed camera matrix, no keyframes, no lens interpolation, no IBIS/OIS splines, no mesh):
+ * what the render path computes for an ordinary clip.  The 3x3 pinv(K_new * R) is an analytic f64 inverse (nalgebra
+ * uses an SVD; both round to the same f32 except for last-ulp cases — `matrices` are *inputs* of the bit-exact contract).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gf_quat_track {          /* TimeQuat = BTreeMap<i64 us, UnitQuaternion<f64>> (gyro_source/mod.rs:34) as sorted arrays */
+    const int64_t* ts_us;
+    const double*  quats;               /* n x 4: w, i, j, k */
+    size_t         n;
+} gf_quat_track;
+
+typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_params.rs:13-69) + lens data at_timestamp reads */
+    int32_t width, height, output_width, output_height;
+    double  camera_matrix[9];           /* row-major, already scaled to the frame (get_lens_data_at_timestamp :95-160) */
+    double  distortion_coeffs[12];
+    double  radial_distortion_limit;
+    double  input_horizontal_stretch, input_vertical_stretch;   /* <= 0.01 means 1.0 (:146-147) */
+    double  fov_scale;
+    const double* fovs;          size_t n_fovs;                  /* adaptive-zoom result, may be empty */
+    const double* minimal_fovs;  size_t n_minimal_fovs;
+    double  lens_optimal_fov;    int32_t has_optimal_fov;
+    double  frame_readout_time;                                  /* ms; 0 = no rolling-shutter correction */
+    int32_t readout_horizontal, readout_inverted;                /* ReadoutDirection::is_horizontal / is_inverted */
+    int32_t framebuffer_inverted, suppress_rotation, fov_overview;
+    double  video_rotation;                                      /* degrees */
+    double  lens_correction_amount, light_refraction_coefficient;
+    double  background_margin, background_margin_feather;
+    int32_t background_mode;
+    double  adaptive_zoom_center_offset[2];
+    double  digital_lens_params[16]; int32_t n_digital_lens_params;
+    double  gyro_offset_ms;                                      /* offset_at_video_timestamp for a single sync point */
+    double  duration_ms;                                         /* <= 0: quat_at_timestamp returns identity (:858) */
+    gf_quat_track org, smoothed;                                 /* quaternions / smoothed_quaternions (stored form smooth^-1 * org) */
+} gf_compute_params;
+
+/* Host producer.  Fills the fields at_timestamp sets in `out_params` (everything else zeroed: `..Default::default()`),
+ * writes rows x 14 f32 to `out_matrices` (rows = 1, height, or width for horizontal readout).  Returns GF_OK or
+ * GF_ERR_BUFFER_TOO_SMALL when max_rows is too small. */
+GF_API int gf_frame_transform_at_timestamp(const gf_compute_params* cp, double timestamp_ms, size_t frame,
+                                           gf_kernel_params* out_params, float* out_matrices, size_t max_rows,
+                                           size_t* out_rows, double* out_fov, double* out_minimal_fov);
+
+/* Device producer: the quaternion tracks live in HBM (uploaded / broadcast once per job), one small kernel per frame
+ * writes the rows x 14 table straight into device memory — no per-frame host SVD loop, no per-frame table upload. */
+typedef struct gf_cuda_gyro gf_cuda_gyro;
+GF_API int  gf_cuda_gyro_upload(gf_cuda_gyro** out, int device, const gf_compute_params* cp);
+GF_API void gf_cuda_gyro_free(gf_cuda_gyro* g);
+GF_API int  gf_cuda_frame_transform_dev(gf_cuda_gyro* g, const gf_compute_params* cp, double timestamp_ms, size_t frame,
+                                        gf_kernel_params* out_params, float* matrices_dev, size_t max_rows,
+                                        size_t* out_rows, double* out_fov, double* out_minimal_fov, void* cu_stream);
+
 #ifdef __cplusplus
 }
 #endif
