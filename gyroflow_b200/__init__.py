@@ -6,7 +6,7 @@ This package is the thin host-side mirror used by tests and bench.py.
 from . import abi
 from .abi import KernelParams, BackendMissing, load_library
 from .backend import (BufferDescription, Buffers, FrameTransform, ProcessedInfo, CudaWrapper,
-                      GyroflowCoreError, list_devices, ComputeParams, DeviceGyro)
+                      GyroflowCoreError, list_devices, ComputeParams, DeviceGyro, zoom_dynamic)
 
 __all__ = ["abi", "KernelParams", "BackendMissing", "load_library", "BufferDescription", "Buffers", "FrameTransform",
-           "ProcessedInfo", "CudaWrapper", "GyroflowCoreError", "list_devices", "ComputeParams", "DeviceGyro"]
+           "ProcessedInfo", "CudaWrapper", "GyroflowCoreError", "list_devices", "ComputeParams", "DeviceGyro", "zoom_dynamic"]

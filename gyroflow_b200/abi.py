@@ -137,6 +137,8 @@ EXPORTS = [
     ("gf_cuda_gyro_free", None, [C.c_void_p]),
     ("gf_cuda_frame_transform_dev", C.c_int, [C.c_void_p, _P(ComputeParams), C.c_double, C.c_size_t, _P(KernelParams), C.c_void_p, C.c_size_t,
                                               _P(C.c_size_t), _P(C.c_double), _P(C.c_double), C.c_void_p]),
+    ("gf_cuda_find_fovs", C.c_int, [C.c_void_p, _P(ComputeParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p]),
+    ("gf_zoom_dynamic_compute", C.c_int, [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_void_p]),
 ]
 
 _lib = None

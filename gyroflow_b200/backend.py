@@ -243,6 +243,16 @@ class DeviceGyro:
             raise GyroflowCoreError(rc, "gf_cuda_frame_transform_dev")
         return kp, rows.value
 
+    def find_fovs(self, distortion_model: str, digital_lens, timestamps_ms, margin=2.0, stream=0):
+        """FovIterative::compute on the device: per-frame minimal FOV (zooming/fov_iterative.rs:31-134)."""
+        ts = np.ascontiguousarray(timestamps_ms, dtype=np.float64)
+        out = np.zeros(ts.size, np.float64)
+        rc = self._lib.gf_cuda_find_fovs(self._h, C.byref(self.cp.c), abi.LENS[distortion_model], abi.LENS[digital_lens] if digital_lens else 0,
+                                         ts.ctypes.data, ts.size, margin, out.ctypes.data, stream or None)
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_find_fovs")
+        return out
+
     def close(self):
         if self._h:
             self._lib.gf_cuda_gyro_free(self._h); self._h = None
@@ -250,3 +260,14 @@ class DeviceGyro:
     def __del__(self):
         try: self.close()
         except Exception: pass
+
+
+def zoom_dynamic(fov_minimal, window_s, fps, method=1):
+    """zoom_dynamic::compute, static-window branch (zoom_dynamic.rs:56-76) — host."""
+    lib = abi.load_library()
+    a = np.ascontiguousarray(fov_minimal, dtype=np.float64)
+    out = np.zeros_like(a)
+    rc = lib.gf_zoom_dynamic_compute(a.ctypes.data, a.size, window_s, fps, method, out.ctypes.data)
+    if rc != 0:
+        raise GyroflowCoreError(rc, "gf_zoom_dynamic_compute")
+    return out

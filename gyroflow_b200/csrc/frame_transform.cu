@@ -191,10 +191,10 @@ size_t prepare(const gf_compute_params* cp, double timestamp_ms, size_t frame, c
 
 } // namespace
 
-struct gf_cuda_gyro {
-    int device = 0;
-    int64_t* d_org_ts = nullptr; double* d_org_q = nullptr; size_t n_org = 0;
-    cudaStream_t stream = nullptr;
+struct gf_cuda_gyro {            // (same layout in zoom_kernel.cu)
+    int device;
+    int64_t* d_org_ts; double* d_org_q; size_t n_org;
+    cudaStream_t stream;
 };
 
 extern "C" {
@@ -217,6 +217,7 @@ GF_API int gf_cuda_gyro_upload(gf_cuda_gyro** out, int device, const gf_compute_
     *out = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
     gf_cuda_gyro* g = new gf_cuda_gyro();
+    memset(g, 0, sizeof(*g));
     g->device = device; g->n_org = cp->org.n;
     bool ok = cudaMalloc(&g->d_org_ts, cp->org.n * sizeof(int64_t)) == cudaSuccess &&
               cudaMalloc(&g->d_org_q, cp->org.n * 4 * sizeof(double)) == cudaSuccess &&

@@ -318,6 +318,19 @@ GF_API int  gf_cuda_frame_transform_dev(gf_cuda_gyro* g, const gf_compute_params
                                         gf_kernel_params* out_params, float* matrices_dev, size_t max_rows,
                                         size_t* out_rows, double* out_fov, double* out_minimal_fov, void* cu_stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Adaptive-zoom companion — zooming::FovIterative (src/core/zooming/fov_iterative.rs:31-189) over
+ * undistort_points_with_rolling_shutter (src/core/stabilization/cpu_undistort.rs:636-858).
+ * gf_cuda_find_fovs: one CTA per frame warps the 120 frame-edge points (+ <= 4 refinement rounds of 63) and reduces them to
+ * the minimal FOV; the calculate_fovs adjustments (zooming/mod.rs:41-49) are applied inside.
+ * gf_zoom_dynamic_compute: the temporal filter over the per-frame vector (zoom_dynamic.rs:56-76; method 0 gaussian,
+ * 1 envelope follower), sequential, on the host like the reference.
+ * ---------------------------------------------------------------------------------------- */
+GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                             const double* timestamps_ms, size_t n, float fov_algorithm_margin,
+                             double* out_fov_minimal, void* cu_stream);
+GF_API int gf_zoom_dynamic_compute(const double* fov_minimal, size_t n, double window_s, double fps, int method, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1099,3 +1099,305 @@ int gf_oracle_undistort_coord(float x, float y, const gf_kernel_params* P, const
     int r = undistort_coord((v2){x, y}, &W, out_c, out_f, &o);
     *ou = o.x; *ov = o.y; return r;
 }
+
+/* ==========================================================================================
+ * Adaptive-zoom companion — zooming/fov_iterative.rs, cpu_undistort.rs:636-858, frame_transform.rs:352-438
+ * (f64 quaternion algebra as nalgebra 0.34.2; quat_at_timestamp gyro_source/mod.rs:857-879)
+ * ======================================================================================== */
+typedef struct { double w, i, j, k; } quat;
+static quat q_mul(quat a, quat b) {
+    quat r = { a.w*b.w - a.i*b.i - a.j*b.j - a.k*b.k, a.w*b.i + a.i*b.w + a.j*b.k - a.k*b.j,
+               a.w*b.j - a.i*b.k + a.j*b.w + a.k*b.i, a.w*b.k + a.i*b.j - a.j*b.i + a.k*b.w };
+    return r;
+}
+static quat q_slerp(quat a, quat b, double t) {
+    double d = a.w*b.w + a.i*b.i + a.j*b.j + a.k*b.k;
+    if (d < 0.0) { b.w = -b.w; b.i = -b.i; b.j = -b.j; b.k = -b.k; d = -d; }
+    if (d >= 1.0) return a;
+    double hang = acos(d), s = sqrt(1.0 - d*d);
+    if (fabs(s) < 1e-14) return a;
+    double ta = sin((1.0 - t) * hang) / s, tb = sin(t * hang) / s;
+    quat r = { a.w*ta + b.w*tb, a.i*ta + b.i*tb, a.j*ta + b.j*tb, a.k*ta + b.k*tb };
+    return r;
+}
+static quat track_get(const gf_quat_track* t, size_t i) { quat q = { t->quats[4*i], t->quats[4*i+1], t->quats[4*i+2], t->quats[4*i+3] }; return q; }
+static quat quat_at_timestamp(const gf_quat_track* t, double duration_ms, double timestamp_ms) {     /* gyro_source/mod.rs:857-879 */
+    quat id = {1.0, 0.0, 0.0, 0.0};
+    if (t->n < 2 || duration_ms <= 0.0) return id;
+    int64_t first_ts = t->ts_us[0], last_ts = t->ts_us[t->n - 1];
+    int64_t lookup = (int64_t)llround(timestamp_ms * 1000.0);
+    if (lookup > last_ts) lookup = last_ts;
+    if (lookup < first_ts) lookup = first_ts;
+    size_t lo = 0, hi = t->n;
+    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (t->ts_us[mid] <= lookup) lo = mid; else hi = mid; }
+    if (t->ts_us[lo] == lookup || lo + 1 >= t->n) return track_get(t, lo);
+    double fract = (double)(lookup - t->ts_us[lo]) / (double)(t->ts_us[lo + 1] - t->ts_us[lo]);
+    return q_slerp(track_get(t, lo), track_get(t, lo + 1), fract);
+}
+static void mat3_mul_d(const double* a, const double* b, double* o) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[r*3+c] = a[r*3]*b[c] + a[r*3+1]*b[3+c] + a[r*3+2]*b[6+c];
+}
+
+/* frame_transform.rs:52-58 */
+static double pts_get_fov(const gf_compute_params* cp, size_t frame, int use_fovs) {
+    double fov_scale = cp->fov_scale + ((cp->fov_overview && use_fovs) ? 1.0 : 0.0);
+    double fov = 1.0;
+    if (use_fovs) {
+        double f = 1.0;
+        if (frame < cp->n_fovs) f = cp->fovs[frame]; else if (cp->n_fovs > 1) f = cp->fovs[cp->n_fovs - 1];
+        fov = f * fov_scale;
+    }
+    fov = fmax(fov, 0.001);
+    return fov * (double)cp->width / (double)(cp->output_width > 1 ? cp->output_width : 1);
+}
+
+/* at_timestamp_for_points — frame_transform.rs:352-438: per-point K_new * R (f64), use_fovs = false */
+static void rotations_for_points(const gf_compute_params* cp, const float* pts, size_t n, double timestamp_ms, size_t frame,
+                                 double* rot /* n x 9 */, double* fov_out) {
+    double fov = pts_get_fov(cp, frame, 0);
+    const double* K = cp->camera_matrix;
+    double hr = cp->input_horizontal_stretch > 0.01 ? cp->input_horizontal_stretch : 1.0;
+    double new_k[9]; memcpy(new_k, K, sizeof(new_k));
+    new_k[0] = new_k[0] * (1.0 / hr) / fov; new_k[4] = new_k[4] * (1.0 / hr) / fov;
+    new_k[2] = (double)cp->output_width / 2.0; new_k[5] = (double)cp->output_height / 2.0;
+    double frt = fabs(cp->frame_readout_time);                       /* get_frame_readout_time(can_invert = false) :376 */
+    if (cp->readout_inverted) frt *= -1.0;
+    double row_readout_time = frt / (double)(cp->readout_horizontal ? cp->width : cp->height);
+    double start_ts = timestamp_ms - frt / 2.0;
+    double a = cp->video_rotation * (M_PI / 180.0);
+    double rz[9] = { cos(a), -sin(a), 0.0, sin(a), cos(a), 0.0, 0.0, 0.0, 1.0 };
+    quat q1 = quat_at_timestamp(&cp->org, cp->duration_ms, timestamp_ms - cp->gyro_offset_ms);
+    q1.i = -q1.i; q1.j = -q1.j; q1.k = -q1.k;
+    quat sq1 = quat_at_timestamp(&cp->smoothed, cp->duration_ms, timestamp_ms - cp->gyro_offset_ms);
+    quat q0 = q_mul(sq1, q1);
+    size_t cnt = fabs(frt) > 0.0 ? n : 1;                            /* :389 */
+    for (size_t p = 0; p < cnt; ++p) {
+        double px = fabs(frt) > 0.0 ? (double)pts[2*p] : 0.0, py = fabs(frt) > 0.0 ? (double)pts[2*p+1] : 0.0;
+        double quat_time = fabs(frt) > 0.0 ? start_ts + row_readout_time * (cp->readout_horizontal ? px : py) : start_ts;
+        quat q = q_mul(q0, quat_at_timestamp(&cp->org, cp->duration_ms, quat_time - cp->gyro_offset_ms));
+        double ww = q.w*q.w, ii = q.i*q.i, jj = q.j*q.j, kk = q.k*q.k;
+        double ij = q.i*q.j*2.0, wk = q.w*q.k*2.0, wj = q.w*q.j*2.0, ik = q.i*q.k*2.0, jk = q.j*q.k*2.0, wi = q.w*q.i*2.0;
+        double rq[9] = { ww+ii-jj-kk, ij-wk, wj+ik, wk+ij, ww-ii+jj-kk, jk-wi, ik-wj, wi+jk, ww-ii-jj+kk };
+        double r[9]; mat3_mul_d(rz, rq, r);
+        r[1] *= -1.0; r[2] *= -1.0; r[3] *= -1.0; r[6] *= -1.0;      /* :402-403 */
+        if (cp->suppress_rotation) { for (int t = 0; t < 9; ++t) r[t] = (t % 4 == 0) ? 1.0 : 0.0; }
+        mat3_mul_d(new_k, r, rot + 9 * p);
+    }
+    for (size_t p = cnt; p < n; ++p) memcpy(rot + 9 * p, rot, 9 * sizeof(double));   /* rot_per_point.get(index).unwrap_or(&rr) with rr = rotations[0] */
+    *fov_out = fov;
+}
+
+/* R(o) of cpu_undistort.rs:794-815 */
+typedef struct { const gf_kernel_params* kp; int model, digital; float out_cx, out_cy, out_fx, out_fy, fov; } lc_ctx;
+static v2 lc_r_of(const lc_ctx* L, v2 o) {
+    v2 q = o;
+    if (L->digital != GF_LENS_NONE) {
+        v2 uz = { (q.x - L->out_cx) * L->fov + L->out_cx, (q.y - L->out_cy) * L->fov + L->out_cy }, d;
+        if (lens_undistort(L->digital, uz, L->kp, &d)) { q.x = (d.x - L->out_cx) / L->fov + L->out_cx; q.y = (d.y - L->out_cy) / L->fov + L->out_cy; }
+    }
+    v2 nn = { (q.x - L->out_cx) / L->out_fx, (q.y - L->out_cy) / L->out_fy }, d;
+    if (lens_undistort(L->model, nn, L->kp, &d)) nn = d;
+    float lrc = L->kp->light_refraction_coefficient;
+    if (lrc != 1.0f && lrc > 0.0f) {
+        float r = sqrtf(nn.x * nn.x + nn.y * nn.y);
+        if (r != 0.0f) {
+            float sin_theta_d = (r / sqrtf(1.0f + r * r)) / lrc;
+            float r_d = sin_theta_d / sqrtf(1.0f - sin_theta_d * sin_theta_d);
+            float s = r_d / r;
+            nn.x = nn.x * s; nn.y = nn.y * s;
+        }
+    }
+    v2 res = { (nn.x * L->out_fx) + L->out_cx, (nn.y * L->out_fy) + L->out_cy };
+    return res;
+}
+
+/* undistort_points — cpu_undistort.rs:652-858 (mesh = None, shift_per_point = None) */
+static void undistort_points(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
+                             const double* rot_per_point, double lens_correction_amount, double fov, float* out) {
+    const double* K = cp->camera_matrix;
+    const float fx = (float)K[0], fy = (float)K[4], cx = (float)K[2], cy = (float)K[5];
+    gf_kernel_params kp; memset(&kp, 0, sizeof(kp));                /* :671-683 */
+    kp.width = cp->width; kp.height = cp->height; kp.output_width = cp->output_width; kp.output_height = cp->output_height;
+    kp.f[0] = fx; kp.f[1] = fy; kp.c[0] = cx; kp.c[1] = cy;
+    for (int i = 0; i < 12; ++i) kp.k[i] = (float)cp->distortion_coeffs[i];
+    for (int i = 0; i < 16 && i < cp->n_digital_lens_params; ++i) kp.digital_lens_params[i] = (float)cp->digital_lens_params[i];
+    kp.light_refraction_coefficient = (float)cp->light_refraction_coefficient;
+    const int lc = lens_correction_amount < 1.0;
+    lc_ctx L; memset(&L, 0, sizeof(L));
+    float amount = 0.0f, factor = 0.0f;
+    if (lc) {                                                        /* :686-694 */
+        L.kp = &kp; L.model = model; L.digital = digital;
+        L.out_cx = (float)cp->output_width / 2.0f; L.out_cy = (float)cp->output_height / 2.0f;
+        amount = (float)lens_correction_amount;
+        factor = rs_max(1.0f - amount, 0.001f);
+        L.out_fx = fx / (float)fov / factor; L.out_fy = fy / (float)fov / factor;
+        L.fov = (float)fov;
+    }
+    for (size_t idx = 0; idx < n; ++idx) {
+        float x = distorted[2*idx], y = distorted[2*idx+1];
+        if (cp->input_horizontal_stretch > 0.001) x *= (float)cp->input_horizontal_stretch;     /* :702-703 */
+        if (cp->input_vertical_stretch   > 0.001) y *= (float)cp->input_vertical_stretch;
+        if (digital != GF_LENS_NONE) { v2 t; if (lens_undistort(digital, (v2){x, y}, &kp, &t)) { x = t.x; y = t.y; } }   /* :705-710 */
+        v2 pw = { (x - cx) / fx, (y - cy) / fy };                    /* :762 */
+        float rot[9]; for (int t = 0; t < 9; ++t) rot[t] = (float)rot_per_point[9*idx + t];      /* :764 */
+        v2 pt;
+        if (lens_undistort(model, pw, &kp, &pt)) {
+            if (kp.light_refraction_coefficient != 1.0f && kp.light_refraction_coefficient > 0.0f) {   /* :767-776 */
+                float r = sqrtf(pt.x * pt.x + pt.y * pt.y);
+                if (r != 0.0f) {
+                    float sin_theta_d = (r / sqrtf(1.0f + r * r)) / kp.light_refraction_coefficient;
+                    float r_d = sin_theta_d / sqrtf(1.0f - sin_theta_d * sin_theta_d);
+                    float f2 = r_d / r;
+                    pt.x *= f2; pt.y *= f2;
+                }
+            }
+            /* pr = rot * (pt.0, pt.1, 1): nalgebra gemv accumulates column by column */
+            float pr0 = rot[0] * pt.x + rot[1] * pt.y + rot[2] * 1.0f;
+            float pr1 = rot[3] * pt.x + rot[4] * pt.y + rot[5] * 1.0f;
+            float pr2 = rot[6] * pt.x + rot[7] * pt.y + rot[8] * 1.0f;
+            pt.x = pr0 / pr2; pt.y = pr1 / pr2;                      /* :780 */
+            if (lc) {                                                /* :782-852 */
+                v2 nn = { (pt.x - L.out_cx) / L.out_fx, (pt.y - L.out_cy) / L.out_fy };
+                v2 d = lens_distort(model, nn.x, nn.y, 1.0f, &kp);
+                v2 p2 = { (d.x * L.out_fx) + L.out_cx, (d.y * L.out_fy) + L.out_cy };
+                if (digital != GF_LENS_NONE) {
+                    v2 uz = { (p2.x - L.out_cx) * L.fov + L.out_cx, (p2.y - L.out_cy) * L.fov + L.out_cy };
+                    v2 dd = lens_distort(digital, uz.x, uz.y, 1.0f, &kp);
+                    p2.x = (dd.x - L.out_cx) / L.fov + L.out_cx; p2.y = (dd.y - L.out_cy) / L.fov + L.out_cy;
+                }
+                v2 o = pt;
+                if (isfinite(p2.x) && isfinite(p2.y)) { o.x = p2.x * factor + pt.x * amount; o.y = p2.y * factor + pt.y * amount; }
+                for (int it = 0; it < 10; ++it) {
+                    v2 r = lc_r_of(&L, o);
+                    float g0 = amount * o.x + factor * r.x - pt.x, g1 = amount * o.y + factor * r.y - pt.y;
+                    if (fabsf(g0) < 0.02f && fabsf(g1) < 0.02f) break;
+                    const float eps = 1.0f;
+                    v2 rx = lc_r_of(&L, (v2){o.x + eps, o.y}), ry = lc_r_of(&L, (v2){o.x, o.y + eps});
+                    float j11 = amount + factor * (rx.x - r.x) / eps, j21 = factor * (rx.y - r.y) / eps;
+                    float j12 = factor * (ry.x - r.x) / eps,          j22 = amount + factor * (ry.y - r.y) / eps;
+                    float det = j11 * j22 - j12 * j21;
+                    if (!isfinite(det) || fabsf(det) < 1e-9f) break;
+                    float dx = ( j22 * g0 - j12 * g1) / det, dy = (-j21 * g0 + j11 * g1) / det;
+                    if (!isfinite(dx) || !isfinite(dy)) break;
+                    o.x = o.x - dx; o.y = o.y - dy;
+                }
+                pt = o;
+            }
+            out[2*idx] = pt.x; out[2*idx+1] = pt.y;
+        } else {
+            out[2*idx] = -1000000.0f; out[2*idx+1] = -1000000.0f;    /* :855 */
+        }
+    }
+}
+
+void gf_oracle_undistort_points_rs(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
+                                   double timestamp_ms, size_t frame, double lens_correction_amount, float* out) {
+    if (n == 0) return;
+    double* rot = (double*)malloc(n * 9 * sizeof(double));
+    double fov;
+    rotations_for_points(cp, distorted, n, timestamp_ms, frame, rot, &fov);
+    undistort_points(cp, model, digital, distorted, n, rot, lens_correction_amount, fov, out);
+    free(rot);
+}
+
+/* fov_iterative.rs:136-151 */
+static int nearest_edge(const float* poly, size_t n, float cx, float cy, float inv_aspect, float* w, float* h) {
+    int idx = -1;
+    for (size_t i = 0; i < n; ++i) {
+        float ap0 = fabsf(poly[2*i] - cx), ap1 = fabsf(poly[2*i+1] - cy);
+        if (ap0 < *w && ap1 < *h) {
+            if (ap1 > ap0 * inv_aspect) { *w = ap1 / inv_aspect; *h = ap1; }
+            else                        { *w = ap0; *h = ap0 * inv_aspect; }
+            idx = (int)i;
+        }
+    }
+    return idx;
+}
+/* fov_iterative.rs:154-175 */
+static size_t points_around_rect(float w, float h, size_t w_div, size_t h_div, float margin, float* out) {
+    w -= margin * 2.0f; h -= margin * 2.0f;
+    size_t wcnt = (w_div > 2 ? w_div : 2) - 1, hcnt = (h_div > 2 ? h_div : 2) - 1;
+    float wstep = w / (float)wcnt, hstep = h / (float)hcnt;
+    size_t k = 0;
+    for (size_t i = 0; i < wcnt; ++i) { out[2*k] = (float)i * wstep;          out[2*k+1] = 0.0f; ++k; }
+    for (size_t i = 0; i < hcnt; ++i) { out[2*k] = w;                         out[2*k+1] = (float)i * hstep; ++k; }
+    for (size_t i = 0; i < wcnt; ++i) { out[2*k] = (float)(wcnt - i) * wstep; out[2*k+1] = h; ++k; }
+    for (size_t i = 0; i < hcnt; ++i) { out[2*k] = 0.0f;                      out[2*k+1] = (float)(hcnt - i) * hstep; ++k; }
+    for (size_t i = 0; i < k; ++i) { out[2*i] += margin; out[2*i+1] += margin; }
+    return k;
+}
+
+double gf_oracle_find_fov(const gf_compute_params* cp, int model, int digital, int org_ow, int org_oh, float margin,
+                          double timestamp_ms, size_t frame) {
+    /* FovIterative::new :78-89 */
+    float ratio = (float)cp->width / (float)(org_ow > 1 ? org_ow : 1);
+    float in_w = (float)cp->width, in_h = (float)cp->height;
+    float out_w = (float)org_ow * ratio, out_h = (float)org_oh * ratio;
+    float inv_aspect = out_h / out_w;
+    float rect[2 * 124], poly[2 * 124], relevant[6], distorted[2 * 64];
+    size_t len = points_around_rect(in_w, in_h, 31, 31, margin, rect);         /* :38 */
+    float cx = in_w / 2.0f, cy = in_h / 2.0f;                                   /* :40 */
+    const double lca = cp->lens_correction_amount;
+    gf_oracle_undistort_points_rs(cp, model, digital, rect, len, timestamp_ms, frame, lca, poly);   /* :98 */
+    for (size_t i = 0; i < len; ++i) { poly[2*i] -= (float)cp->adaptive_zoom_center_offset[0] * in_w; poly[2*i+1] -= (float)cp->adaptive_zoom_center_offset[1] * in_h; }
+    float w = 1000000.0f, h = 1000000.0f * inv_aspect;                          /* :107 */
+    size_t plen = len;
+    for (int it = 1; it < 5; ++it) {                                            /* :110-131 */
+        int idx = nearest_edge(poly, plen, cx, cy, inv_aspect, &w, &h);
+        if (idx < 0) break;
+        if (len == 0) continue;
+        /* NB (reference behaviour kept): idx indexes the *current* polygon but is applied to `rect` */
+        /*     and `idx.overflowing_sub(1).0 % len` wraps through usize::MAX: idx = 0 -> (2^64 - 1) % len (= 15 for len = 120), not len - 1 */
+        size_t i0 = ((size_t)idx - (size_t)1) % len, i1 = (size_t)idx, i2 = ((size_t)idx + 1) % len;
+        relevant[0] = rect[2*i0]; relevant[1] = rect[2*i0+1]; relevant[2] = rect[2*i1]; relevant[3] = rect[2*i1+1]; relevant[4] = rect[2*i2]; relevant[5] = rect[2*i2+1];
+        /* interpolate_points(&relevant, 30) :180-189 */
+        const size_t steps = 30, d = steps + 1, new_len = d * 3 - steps;
+        for (size_t i = 0; i < new_len; ++i) {
+            size_t idx1 = i / d, idx2 = idx1 + 1 < 2 ? idx1 + 1 : 2;
+            float f = (float)(i % d) / (float)d;
+            distorted[2*i]   = relevant[2*idx1]   + f * (relevant[2*idx2]   - relevant[2*idx1]);
+            distorted[2*i+1] = relevant[2*idx1+1] + f * (relevant[2*idx2+1] - relevant[2*idx1+1]);
+        }
+        gf_oracle_undistort_points_rs(cp, model, digital, distorted, new_len, timestamp_ms, frame, lca, poly);
+        plen = new_len;
+        for (size_t i = 0; i < plen; ++i) { poly[2*i] -= (float)cp->adaptive_zoom_center_offset[0] * in_w; poly[2*i+1] -= (float)cp->adaptive_zoom_center_offset[1] * in_h; }
+        nearest_edge(poly, plen, cx, cy, inv_aspect, &w, &h);                   /* :127 (index discarded: re-evaluated at loop top) */
+    }
+    return (double)(w * 2.0f / out_w);                                          /* :133 */
+}
+
+/* zoom_dynamic.rs:177-200 */
+static void envelope_follower(const double* a, size_t n, double alpha, double* out) {
+    if (n == 0) return;
+    double* rev = (double*)malloc(n * sizeof(double));
+    double q = a[n - 1];
+    for (size_t r = 0; r < n; ++r) { double x = a[n - 1 - r]; q = fmin(x, x * alpha + q * (1.0 - alpha)); rev[r] = q; }
+    q = rev[n - 1];
+    for (size_t r = 0; r < n; ++r) { double x = rev[n - 1 - r]; q = fmin(x, x * alpha + q * (1.0 - alpha)); out[r] = q; }
+    free(rev);
+}
+void gf_oracle_zoom_dynamic(const double* fov_minimal, size_t n, double window_s, double fps, int method, double* out) {
+    if (n == 0) return;
+    if (method == 1) {                                               /* :69-75 */
+        double a1 = 1.0 - exp(-(1.0 / fps) / window_s), a2 = 1.0 - exp(-(1.0 / fps) / 0.2);
+        double* tmp = (double*)malloc(n * sizeof(double));
+        envelope_follower(fov_minimal, n, a1, tmp);
+        envelope_follower(tmp, n, a2, out);
+        free(tmp);
+        return;
+    }
+    /* gaussian: :58-67, helpers :80-126 */
+    size_t frames = (size_t)floor(window_s * fps); if (frames % 2 == 0) frames += 1;
+    size_t half = frames / 2, padn = n + 2 * half;
+    double* pad = (double*)malloc(padn * sizeof(double));
+    for (size_t i = 0; i < padn; ++i) pad[i] = i < half ? fov_minimal[0] : (i >= half + n ? fov_minimal[n - 1] : fov_minimal[i - half]);
+    double* mn = (double*)malloc(n * sizeof(double));
+    for (size_t i = 0; i + frames <= padn; ++i) { double m = pad[i]; for (size_t j = 1; j < frames; ++j) m = fmin(m, pad[i + j]); mn[i] = m; }
+    for (size_t i = 0; i < padn; ++i) pad[i] = i < half ? mn[0] : (i >= half + n ? mn[n - 1] : mn[i - half]);
+    double* g = (double*)malloc(frames * sizeof(double));
+    double std = (double)frames / 6.0, sig2 = 2.0 * std * std, sum = 0.0;
+    for (size_t i = 0; i < frames; ++i) { long x = (long)i - (long)half; g[i] = exp(-(double)(x * x) / sig2); sum += g[i]; }
+    for (size_t i = 0; i < frames; ++i) g[i] /= sum;
+    for (size_t i = 0; i + frames <= padn; ++i) { double s = 0.0; for (size_t j = 0; j < frames; ++j) s += pad[i + j] * g[j]; out[i] = s; }
+    free(pad); free(mn); free(g);
+}

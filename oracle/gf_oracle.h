@@ -61,6 +61,21 @@ void gf_oracle_interpolate_mesh(double x, double y, const double* mesh, double* 
 void gf_oracle_cubic_spline_coefficients(const double* mesh, size_t step, size_t offset, double size, size_t n,
                                          double* a, double* b, double* c, double* d);
 
+/* ---- adaptive-zoom companion ------------------------------------------------------------------
+ * undistort_points_with_rolling_shutter (cpu_undistort.rs:636-641) = FrameTransform::at_timestamp_for_points
+ * (frame_transform.rs:352-438, no-metadata case) + undistort_points (cpu_undistort.rs:652-858, no mesh / IBIS shifts).
+ * `distorted`/`out` are n (x, y) f32 pairs.  `digital_lens` = GF_LENS_NONE for Option::None. */
+void gf_oracle_undistort_points_rs(const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                   const float* distorted, size_t n, double timestamp_ms, size_t frame,
+                                   double lens_correction_amount, float* out);
+/* FovIterative::find_fov — zooming/fov_iterative.rs:91-134 for one frame; `cp` already has output = input size and
+ * fov_scale = 1 (calculate_fovs, zooming/mod.rs:41-49), org_output_* is the real output size, margin = fov_algorithm_margin. */
+double gf_oracle_find_fov(const gf_compute_params* cp, int distortion_model, int digital_lens,
+                          int org_output_width, int org_output_height, float margin, double timestamp_ms, size_t frame);
+/* zoom_dynamic::compute, static-window branch — zooming/zoom_dynamic.rs:56-76 (method 0 gaussian, 1 envelope follower).
+ * in/out: n per-frame fovs. */
+void gf_oracle_zoom_dynamic(const double* fov_minimal, size_t n, double window_s, double fps, int method, double* out);
+
 int gf_oracle_online_cpus(void);
 const char* gf_oracle_describe(void);
 

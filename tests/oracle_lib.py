@@ -42,6 +42,12 @@ def load():
                                               C.c_void_p, C.c_size_t, P(C.c_float), P(C.c_float)]
     lib.gf_oracle_interpolate_mesh.restype = None
     lib.gf_oracle_interpolate_mesh.argtypes = [C.c_double, C.c_double, C.c_void_p, P(C.c_double), P(C.c_double)]
+    lib.gf_oracle_find_fov.restype = C.c_double
+    lib.gf_oracle_find_fov.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_size_t]
+    lib.gf_oracle_undistort_points_rs.restype = None
+    lib.gf_oracle_undistort_points_rs.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_size_t, C.c_double, C.c_void_p]
+    lib.gf_oracle_zoom_dynamic.restype = None
+    lib.gf_oracle_zoom_dynamic.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_void_p]
     lib.gf_oracle_online_cpus.restype = C.c_int
     lib.gf_oracle_describe.restype = C.c_char_p
     _lib = lib
@@ -69,3 +75,21 @@ def undistort_point(lens, x, y, params):
     lib = load(); ox, oy = C.c_float(), C.c_float()
     ok = lib.gf_oracle_lens_undistort_point(abi.LENS[lens], x, y, C.byref(params), C.byref(ox), C.byref(oy))
     return (ox.value, oy.value) if ok else None
+
+
+def find_fovs(cp, lens, digital_lens, timestamps_ms, margin=2.0):
+    """FovIterative::compute with the calculate_fovs adjustments (zooming/mod.rs:41-49): oracle, one frame at a time."""
+    lib = load()
+    c = abi.ComputeParams()
+    C.memmove(C.byref(c), C.byref(cp.c), C.sizeof(abi.ComputeParams))
+    ow, oh = c.output_width, c.output_height
+    c.fov_scale = 1.0; c.n_fovs = 0; c.n_minimal_fovs = 0; c.output_width = c.width; c.output_height = c.height
+    return np.array([lib.gf_oracle_find_fov(C.byref(c), abi.LENS[lens], abi.LENS[digital_lens] if digital_lens else 0, ow, oh, margin, float(t), i)
+                     for i, t in enumerate(timestamps_ms)])
+
+
+def zoom_dynamic(fov_minimal, window_s, fps, method=1):
+    lib = load()
+    a = np.ascontiguousarray(fov_minimal, dtype=np.float64); out = np.zeros_like(a)
+    lib.gf_oracle_zoom_dynamic(a.ctypes.data, a.size, window_s, fps, method, out.ctypes.data)
+    return out

@@ -1,0 +1,64 @@
+"""Adaptive-zoom companion: FovIterative::find_fov + zoom_dynamic."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import gyroflow_b200 as g
+from gyroflow_b200 import abi, synth
+from tests import cases, oracle_lib
+
+
+def make_cp(w=1920, h=1080, ow=None, oh=None, lens="opencv_fisheye", digital=None, **kw):
+    p = synth.base_kernel_params(w, h, ow, oh, lens=lens, digital_lens=digital)
+    for k, v in kw.pop("params", {}).items():
+        setattr(p, k, v)
+    org, sm = cases.gyro()
+    return g.ComputeParams(p, org, sm, **kw)
+
+
+def test_oracle_fov_properties():
+    ts = np.arange(30) * (1000.0 / 60.0)
+    # identity lens, no rotation: the whole frame (minus the 2 px margin) is visible -> fov just below 1
+    cp = make_cp(params=dict())
+    cp.c.distortion_coeffs[:] = [0.0] * 12
+    cp.c.suppress_rotation = 1
+    f = oracle_lib.find_fovs(cp, "opencv_fisheye", None, ts)
+    assert np.allclose(f, (1920 - 4) / 1920.0, atol=2e-3)
+    # with the synthetic shake the fov varies frame to frame and stays in a sane range
+    f2 = oracle_lib.find_fovs(make_cp(), "opencv_fisheye", None, ts)
+    assert f2.std() > 1e-3 and 0.5 < f2.min() and f2.max() < 1.5
+
+
+def test_zoom_dynamic_host_matches_oracle_bit_for_bit():
+    rng = np.random.default_rng(3)
+    fm = 0.9 + 0.1 * rng.random(400)
+    for method in (0, 1):
+        a = g.zoom_dynamic(fm, 4.0, 60.0, method)
+        b = oracle_lib.zoom_dynamic(fm, 4.0, 60.0, method)
+        assert np.array_equal(a, b)
+        assert (a <= fm + 1e-12).all() if method == 1 else a.shape == fm.shape      # the envelope never exceeds the per-frame minimum
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lens,digital,kw", [
+    ("opencv_fisheye", None, {}),
+    ("opencv_fisheye", "gopro_superview", {}),
+    ("sony", None, {}),
+    ("gopro", "gopro_warp", {}),
+    ("opencv_standard", "digital_stretch", {}),
+    ("opencv_fisheye", None, dict(ow=1280, oh=720)),
+    ("opencv_fisheye", None, dict(frame_readout_time_ms=0.0)),
+    ("opencv_fisheye", None, dict(video_rotation=12.0, horizontal=True)),
+    ("opencv_fisheye", "gopro_superview", dict(params=dict(lens_correction_amount=0.4))),
+    ("poly5", None, dict(params=dict(lens_correction_amount=0.7))),
+])
+def test_device_find_fovs_matches_oracle(lens, digital, kw):
+    cp = make_cp(lens=lens, digital=digital, **dict(kw))
+    ts = np.arange(120) * (1000.0 / 60.0)
+    want = oracle_lib.find_fovs(cp, lens, digital, ts)
+    dg = g.DeviceGyro(cp)
+    got = dg.find_fovs(lens, digital, ts)
+    dg.close()
+    assert np.allclose(got, want, rtol=1e-6, atol=0), float(np.abs(got / want - 1).max())
+    assert (got == want).mean() > 0.9            # almost always identical; the rest is f64 device-vs-host libm in the rotation
