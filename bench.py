@@ -30,13 +30,34 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-W, H = 3840, 2160
-PIX, LENS = "RGBA8", "opencv_fisheye"
+# BASELINE.json configs.  cfg2 is the one `metric` is quoted on (default); cfg1/3/4 are selectable with --config for the
+# per-lens-model ncu captures (profiles/) — they are parity-test cases, not additional headline numbers.
+CONFIGS = {
+    1: dict(w=3840, h=2160, pix="RGBA8", lens="opencv_fisheye", digital=None, rs=False, identity=True,
+            name="cfg1: 3840x2160 RGBA8, opencv_fisheye, rolling-shutter OFF, identity quaternion, bilinear"),
+    2: dict(w=3840, h=2160, pix="RGBA8", lens="opencv_fisheye", digital=None, rs=True,
+            name="cfg2: 3840x2160 RGBA8, opencv_fisheye + rolling-shutter ON (2160 matrices), 240 Hz synthetic gyro, bilinear"),
+    3: dict(w=7680, h=4320, pix="Luma16", lens="opencv_fisheye", digital="gopro_superview", rs=True,
+            name="cfg3: 7680x4320 16-bit luma plane of YUV 4:2:2, opencv_fisheye + gopro_superview digital lens, rolling-shutter ON (4320 matrices), bilinear"),
+    4: dict(w=3840, h=2160, pix="R32f", lens="sony", digital=None, rs=True, ibis=True, mesh=True,
+            name="cfg4: 3840x2160 f32 plane (GBRAPF32), sony lens + IBIS rows + 9x9 mesh correction, rolling-shutter ON, bilinear"),
+}
+CFG = CONFIGS[2]
+W, H = CFG["w"], CFG["h"]
+PIX, LENS = CFG["pix"], CFG["lens"]
 FRAMES_PER_STEP = 128
 RING = 8                 # 8 x 33.2 MB input frames = 265 MB > 126 MB L2
 N_TIMESTAMPS = 32        # distinct matrix tables
 METRIC = "4K frames/sec (fisheye+RS warp)"
-WORKLOAD = "cfg2: 3840x2160 RGBA8, opencv_fisheye + rolling-shutter ON (2160 matrices), 240 Hz synthetic gyro, bilinear"
+WORKLOAD = CFG["name"]
+
+
+def select_config(n):
+    global CFG, W, H, PIX, LENS, WORKLOAD, FRAMES_PER_STEP, RING, N_TIMESTAMPS
+    CFG = CONFIGS[n]
+    W, H, PIX, LENS, WORKLOAD = CFG["w"], CFG["h"], CFG["pix"], CFG["lens"], CFG["name"]
+    if n == 3: FRAMES_PER_STEP, RING, N_TIMESTAMPS = 32, 4, 8        # 66 MB planes: 4-frame ring = 265 MB
+    if n == 4: FRAMES_PER_STEP, RING, N_TIMESTAMPS = 32, 8, 8
 
 
 def algorithmic_bytes(p, rows, mesh_len=0):
@@ -77,13 +98,33 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_tables(n):
+def base_params():
     from gyroflow_b200 import synth
-    p = synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS)
-    org, sm = synth.synthetic_gyro(4.0)
-    mats = np.stack([synth.frame_matrices(p, org, sm, 500.0 + i * (1000.0 / 60.0)) for i in range(n)])   # 60 fps timestamps
+    return synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS, digital_lens=CFG.get("digital"), fov=1.05 if CFG.get("digital") else 1.0)
+
+
+def make_tables(n):
+    import math
+    from gyroflow_b200 import synth
+    p = base_params()
+    if CFG.get("identity"):
+        mats = np.stack([synth.identity_matrices(p, rows=1) for _ in range(n)])
+    else:
+        org, sm = synth.synthetic_gyro(4.0)
+        ibis = None
+        if CFG.get("ibis"):
+            def ibis(y, hh=H):
+                t = y / max(hh - 1, 1)
+                return (3.0 * math.sin(6.28 * t), -3.0 * math.cos(6.28 * t), math.radians(0.2) * math.sin(3.0 * t), math.sin(9.0 * t), -math.cos(5.0 * t))
+        mats = np.stack([synth.frame_matrices(p, org, sm, 500.0 + i * (1000.0 / 60.0), frame_readout_time_ms=16.0 if CFG.get("rs") else 0.0, ibis=ibis)
+                         for i in range(n)])   # 60 fps timestamps
     p.matrix_count = mats.shape[1]
     return p, mats.astype(np.float32)
+
+
+def make_mesh():
+    from gyroflow_b200 import synth
+    return synth.synthetic_mesh(W, H) if CFG.get("mesh") else None
 
 
 def cpu_reference_fps(p, mats, frames, threads):
@@ -92,10 +133,11 @@ def cpu_reference_fps(p, mats, frames, threads):
     from tests import oracle_lib
     src = synth.synthetic_frame(W, H, PIX, stride=p.stride)
     dst = np.zeros((H, p.output_stride), np.uint8)
-    oracle_lib.undistort_image(src, dst, p, PIX, LENS, None, mats[0], None, threads)          # warm-up (page faults, thread start)
+    mesh = make_mesh()
+    oracle_lib.undistort_image(src, dst, p, PIX, LENS, CFG.get("digital"), mats[0], mesh, threads)          # warm-up (page faults, thread start)
     t0 = time.perf_counter()
     for i in range(frames):
-        rc = oracle_lib.undistort_image(src, dst, p, PIX, LENS, None, mats[i % len(mats)], None, threads)
+        rc = oracle_lib.undistort_image(src, dst, p, PIX, LENS, CFG.get("digital"), mats[i % len(mats)], mesh, threads)
         assert rc == 0
     return frames / (time.perf_counter() - t0)
 
@@ -110,7 +152,8 @@ def run_reference(args):
     from gyroflow_b200 import synth
     src = synth.synthetic_frame(W, H, PIX, stride=p.stride)
     dst = np.zeros((H, p.output_stride), np.uint8)
-    step = lambda i: oracle_lib.undistort_image(src, dst, p, PIX, LENS, None, mats[i % len(mats)], None, cores)
+    mesh = make_mesh()
+    step = lambda i: oracle_lib.undistort_image(src, dst, p, PIX, LENS, CFG.get("digital"), mats[i % len(mats)], mesh, cores)
     for i in range(args.warmup): step(i)
     t0 = time.perf_counter()
     for i in range(args.steps): assert step(i) == 0
@@ -133,7 +176,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -155,8 +201,10 @@ def main():
 
     # ---- tables: rank 0 builds them, NCCL broadcasts them (the only collective of the path) -------------------
     from gyroflow_b200 import render_queue
-    p, mats_np = make_tables(N_TIMESTAMPS) if rank == 0 else (synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS), np.zeros((0, 0, 0), np.float32))
-    rows = H
+    p, mats_np = make_tables(N_TIMESTAMPS) if rank == 0 else (base_params(), np.zeros((0, 0, 0), np.float32))
+    rows = H if CFG.get("rs") else 1
+    mesh_np = make_mesh()
+    mesh_dev = torch.from_numpy(mesh_np).to(dev) if mesh_np is not None else None
     if world > 1:
         p, mats = render_queue.broadcast_tables(p, mats_np, dist, torch, dev)      # NCCL: KernelParams + all matrix tables, once
     else:
@@ -165,13 +213,19 @@ def main():
 
     # ---- device-resident frames -----------------------------------------------------------------------------
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    frames_in = [torch.randint(0, 256, (H, p.stride), dtype=torch.uint8, device=dev, generator=gen) for _ in range(RING)]
+    def rand_frame(pin=False):
+        if PIX in ("R32f", "RGBAf"):     # finite floats in [0, 1)
+            t = torch.rand((H, p.stride // 4), dtype=torch.float32, device=dev, generator=gen).view(torch.uint8).reshape(H, p.stride)
+        else:
+            t = torch.randint(0, 256, (H, p.stride), dtype=torch.uint8, device=dev, generator=gen)
+        return t
+    frames_in = [rand_frame() for _ in range(RING)]
     frames_out = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(RING)]
     def dbufs(i):
         a, b = frames_in[i % RING], frames_out[i % RING]
         return g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
                          g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel()))
-    ctx = g.CudaWrapper.new(p, PIX, LENS, None, dbufs(0), device=local)
+    ctx = g.CudaWrapper.new(p, PIX, LENS, CFG.get("digital"), dbufs(0), device=local)
     # a real (non-default) stream: kernels, CUDA events and the timed region all live on it
     tstream = torch.cuda.Stream(device=dev)
     stream = tstream.cuda_stream
@@ -181,7 +235,8 @@ def main():
     def step(s):
         for j in range(FRAMES_PER_STEP):
             i = s * FRAMES_PER_STEP + j
-            ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows, stream=stream)
+            ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows,
+                                    mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
 
     torch.cuda.synchronize()
     for s in range(args.warmup):
@@ -212,16 +267,17 @@ def main():
     # (b) the same work pipelined: DEPTH contexts round-robin through gf_cuda_undistort_image_async + gf_cuda_synchronize,
     #     so frame i+1's upload overlaps frame i's kernel and frame i-1's download.  (b) is the reported e2e value.
     DEPTH = 3
-    hin = [torch.randint(0, 256, (H, p.stride), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+    hin = [rand_frame().cpu().pin_memory() for _ in range(DEPTH)]
     hout = [torch.zeros((H, p.output_stride), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
     def hbufs(i):
         a, b = hin[i % DEPTH].numpy(), hout[i % DEPTH].numpy()
         return g.Buffers(g.BufferDescription((W, H, p.stride), a), g.BufferDescription((W, H, p.output_stride), b))
     hb = [hbufs(i) for i in range(DEPTH)]
-    hctx = [g.CudaWrapper.new(p, PIX, LENS, None, hb[i], device=local) for i in range(DEPTH)]
+    hctx = [g.CudaWrapper.new(p, PIX, LENS, CFG.get("digital"), hb[i], device=local) for i in range(DEPTH)]
     mats_host = mats.cpu().numpy()
-    itms = [g.FrameTransform(matrices=mats_host[i % N_TIMESTAMPS], kernel_params=p) for i in range(N_TIMESTAMPS)]
-    e2e_frames = 96
+    itms = [g.FrameTransform(matrices=mats_host[i % N_TIMESTAMPS], kernel_params=p, mesh_data=mesh_np if mesh_np is not None else np.zeros(0, np.float32))
+            for i in range(N_TIMESTAMPS)]
+    e2e_frames = 24 if args.no_e2e else 96
     for i in range(3): hctx[0].undistort_image(hb[0], itms[i % N_TIMESTAMPS])
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
@@ -241,28 +297,28 @@ def main():
     if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_fps = world * e2e_frames / float(te.item())
     h2d = int(hin[0].numel() + rows * 56 + 368)
-    d2h = int(W * 4 * H)
+    d2h = int(W * p.bytes_per_pixel * H)
 
     if rank == 0:
         peaks = {}
         try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception: pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        abytes = algorithmic_bytes(p, rows)
+        abytes = algorithmic_bytes(p, rows, mesh_np.size if mesh_np is not None else 0)
         launch_ms = total_ms / max(launches, 1)
         achieved = abytes / (launch_ms / 1e3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:
             from tests import oracle_lib
             cores = oracle_lib.load().gf_oracle_online_cpus()
-            cfps = cpu_reference_fps(p, mats_host, 4, cores)
+            cfps = cpu_reference_fps(p, mats_host, 4 if args.config != 3 else 2, cores)
             cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "4 full 4K frames of the same workload (C port of cpu_undistort.rs, row-parallel over all host threads)"}
         out = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
-                       "l2_policy": "inputs larger than L2: %d-frame ring of 33.2 MB inputs (%d MB) + %d distinct matrix tables" % (RING, RING * H * p.stride // 1000000, N_TIMESTAMPS),
+            "config": {"workload": WORKLOAD, "frame_bytes_in": int(H * p.stride), "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
+                       "l2_policy": "inputs larger than L2: %d-frame ring of %.1f MB inputs (%d MB) + %d distinct matrix tables" % (RING, H * p.stride / 1e6, RING * H * p.stride // 1000000, N_TIMESTAMPS),
                        "parallelism": "frame-sharded x%d, NCCL broadcast of tables only" % world},
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
