@@ -42,6 +42,8 @@ struct gf_cuda_ctx {
     KernelFn fn = nullptr;        // general instantiation (run-time feature tests)
     KernelFn fn_lean = nullptr;   // rare features compiled out
     KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe
+    KernelFn fn_tile = nullptr;   // x2 + rolling-shutter row search amortised over a warp tile
+    unsigned long long tile_launches = 0;
     unsigned long long x2_launches = 0;
     unsigned long long lean_launches = 0;
     cudaStream_t stream = nullptr;
@@ -270,11 +272,12 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0);
     KernelFn fn_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1);
     KernelFn fn_x2 = getenv("GF_DISABLE_X2") ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 2);
+    KernelFn fn_tile = (getenv("GF_DISABLE_X2") || getenv("GF_DISABLE_TILE")) ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 3);
     if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
 
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
-    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2;
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_tile = fn_tile;
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -393,7 +396,11 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
-    if (lean_ok && ctx->fn_x2) {
+    if (lean_ok && ctx->fn_tile) {
+        const dim3 grid3((A.out_cols + 2 * GF_TILE_REGION_W - 1) / (2 * GF_TILE_REGION_W), (A.out_rows + 4 * GF_TILE_REGION_H - 1) / (4 * GF_TILE_REGION_H));
+        ctx->fn_tile<<<grid3, block, 0, st>>>(A); ctx->tile_launches++;
+    }
+    else if (lean_ok && ctx->fn_x2) {
         const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
         ctx->fn_x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
     }

@@ -4,7 +4,7 @@
 // here every valid combination is compiled for sm_100a up front and looked up by id.
 #pragma once
 #include <cstdlib>
-#include "warp_kernel_x2.cuh"
+#include "warp_kernel_tile.cuh"
 
 namespace gf {
 
@@ -46,9 +46,24 @@ static KernelFn pick_x2(int interp) {
     }
     return nullptr;
 }
+// lean == 3: packed kernel + rolling-shutter row search amortised over a warp tile (warp_kernel_tile.cuh)
+template <int LENS, int DIGITAL, class PIX>
+static KernelFn pick_tile(int interp) {
+    if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) {
+        if (interp == GF_INTERP_BILINEAR) {
+            const char* e = getenv("GF_TILE_MINB");
+            const int minb = e ? atoi(e) : 5;
+            if (minb == 4) return warp_kernel_tile<LENS, PIX, 4>;
+            if (minb == 6) return warp_kernel_tile<LENS, PIX, 6>;
+            return warp_kernel_tile<LENS, PIX, 5>;
+        }
+    }
+    return nullptr;
+}
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
     if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp);
+    if (lean == 3) return pick_tile<LENS, DIGITAL, PIX>(interp);
     switch (interp) {
     case GF_INTERP_BILINEAR: return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
 #ifdef GF_ENABLE_HIGH_ORDER

@@ -234,11 +234,30 @@ def test_packed_primitives_selftest():
     assert list(out) == [0, 0, 0, 0], list(out)
 
 
+def test_row_search_stress():
+    """The tile kernel's interpolated rolling-shutter row search must reproduce the exact search: many frames, strong shake,
+    in-plane rotation (large d(pt.y)/dx), zoomed-out views with invalid (w <= 0) regions, odd sizes."""
+    org, sm = cases.gyro()
+    for i in range(12):
+        assert_bit_exact(dict(w=1280, h=720, ts=137.0 + 311.7 * i))
+    for rot in (3.0, 17.0, 45.0, 90.0, 179.0):
+        assert_bit_exact(dict(w=1280, h=720, video_rotation=rot, ts=777.0))
+    for fov in (0.4, 1.0, 3.0, 8.0):
+        assert_bit_exact(dict(w=1031, h=577, fov=fov, ts=1999.0, readout=33.0))
+    assert_bit_exact(dict(w=1280, h=720, readout=-20.0))
+    assert_bit_exact(dict(w=70, h=41))
+    assert_bit_exact(dict(w=1280, h=720, pix="Luma8"))
+    assert_bit_exact(dict(w=1280, h=720, pix="RGBAf"))
+
+
 def test_kernel_variants_agree(monkeypatch):
     """The packed two-pixel kernel, the lean scalar kernel and the general kernel produce identical bytes."""
     case = dict(w=1280, h=720)
     want, got_x2, pix = run_both(case)
     assert cases.compare(want, got_x2, pix)[0] == 0
+    monkeypatch.setenv("GF_DISABLE_TILE", "1")
+    _, got_x2only, _ = run_both(case)
+    assert np.array_equal(got_x2, got_x2only)
     monkeypatch.setenv("GF_DISABLE_X2", "1")
     _, got_lean, _ = run_both(case)
     assert np.array_equal(got_x2, got_lean)
