@@ -51,11 +51,7 @@ template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_tile(int interp) {
     if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) {
         if (interp == GF_INTERP_BILINEAR) {
-            const char* e = getenv("GF_TILE_MINB");
-            const int minb = e ? atoi(e) : 5;
-            if (minb == 4) return warp_kernel_tile<LENS, PIX, 4>;
-            if (minb == 6) return warp_kernel_tile<LENS, PIX, 6>;
-            return warp_kernel_tile<LENS, PIX, 5>;
+            return warp_kernel_tile<LENS, PIX, 4>;
         }
     }
     return nullptr;

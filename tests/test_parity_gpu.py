@@ -234,9 +234,10 @@ def test_packed_primitives_selftest():
     assert list(out) == [0, 0, 0, 0], list(out)
 
 
-def test_row_search_stress():
-    """The tile kernel's interpolated rolling-shutter row search must reproduce the exact search: many frames, strong shake,
-    in-plane rotation (large d(pt.y)/dx), zoomed-out views with invalid (w <= 0) regions, odd sizes."""
+def test_row_search_stress(monkeypatch):
+    """The (opt-in) tile kernel's interpolated rolling-shutter row search must reproduce the exact search: many frames, strong
+    shake, in-plane rotation (large d(pt.y)/dx), zoomed-out views with invalid (w <= 0) regions, odd sizes."""
+    monkeypatch.setenv("GF_ENABLE_TILE", "1")
     org, sm = cases.gyro()
     for i in range(12):
         assert_bit_exact(dict(w=1280, h=720, ts=137.0 + 311.7 * i))
@@ -255,9 +256,10 @@ def test_kernel_variants_agree(monkeypatch):
     case = dict(w=1280, h=720)
     want, got_x2, pix = run_both(case)
     assert cases.compare(want, got_x2, pix)[0] == 0
-    monkeypatch.setenv("GF_DISABLE_TILE", "1")
-    _, got_x2only, _ = run_both(case)
-    assert np.array_equal(got_x2, got_x2only)
+    monkeypatch.setenv("GF_ENABLE_TILE", "1")
+    _, got_tile, _ = run_both(case)
+    assert np.array_equal(got_x2, got_tile)
+    monkeypatch.delenv("GF_ENABLE_TILE")
     monkeypatch.setenv("GF_DISABLE_X2", "1")
     _, got_lean, _ = run_both(case)
     assert np.array_equal(got_x2, got_lean)
