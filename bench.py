@@ -231,6 +231,7 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
     all_bufs = [dbufs(i) for i in range(RING)]
+    table_verdicts = [ctx.validate_tables_dev(mats[i].data_ptr(), rows) for i in range(N_TIMESTAMPS)]   # once per table, outside the timed region
 
     def step(s):
         for j in range(FRAMES_PER_STEP):

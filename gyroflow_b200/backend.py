@@ -153,6 +153,13 @@ class CudaWrapper:
         if rc != 0:
             raise self._err(rc)
 
+    def validate_tables_dev(self, matrices_dev: int, matrix_rows: int):
+        """Scan a device-resident table once so later undistort_image_dev calls on it may take the trusted fast path."""
+        rc = self._lib.gf_cuda_validate_tables_dev(self._h, matrices_dev, matrix_rows)
+        if rc < 0:
+            raise self._err(rc)
+        return rc
+
     def synchronize(self):
         rc = self._lib.gf_cuda_synchronize(self._h)
         if rc != 0:

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <algorithm>
 #include <string>
+#include <unordered_map>
 
 #include "kernel_registry.h"
 
@@ -41,9 +42,10 @@ struct gf_cuda_ctx {
     int width = 0, height = 0, output_width = 0, output_height = 0;    // Stabilization.size / output_size
     KernelFn fn = nullptr;        // general instantiation (run-time feature tests)
     KernelFn fn_lean = nullptr;   // rare features compiled out
-    KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe
-    KernelFn fn_tile = nullptr;   // x2 + rolling-shutter row search amortised over a warp tile
-    unsigned long long tile_launches = 0;
+    KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe (unvalidated tables)
+    KernelFn fn_x2t = nullptr;    // same, tables validated: no per-pixel numerator / IBIS tests
+    std::unordered_map<const void*, uint32_t> validated;   // device tables vouched for by gf_cuda_validate_tables_dev
+    unsigned* d_vflags = nullptr;
     unsigned long long x2_launches = 0;
     unsigned long long lean_launches = 0;
     cudaStream_t stream = nullptr;
@@ -150,6 +152,28 @@ MapC make_map(float in_min, float in_max, float out_min, float out_max, float ma
     return m;
 }
 
+// "tame": zero, or finite with 2^-40 <= |v| <= 2^40 — the magnitudes for which the packed kernel's unguarded numerators are safe
+inline bool tame(float v) { const float a = fabsf(v); return v == 0.0f || (a >= 0x1p-40f && a <= 0x1p40f); }
+enum : uint32_t { TBL_WILD = 1u, TBL_IBIS = 2u };
+uint32_t scan_tables_host(const float* m, size_t rows) {
+    uint32_t f = 0;
+    for (size_t r = 0; r < rows; ++r) {
+        const float* p = m + r * GF_MATRIX_STRIDE;
+        for (int i = 0; i < 9; ++i) if (!tame(p[i])) f |= TBL_WILD;
+        for (int i = 9; i < 14; ++i) if (!(p[i] == 0.0f)) f |= TBL_IBIS;
+    }
+    return f;
+}
+__global__ void scan_tables_kernel(const float* __restrict__ m, size_t rows, unsigned* flags) {
+    unsigned f = 0;
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+        const float* p = m + r * GF_MATRIX_STRIDE;
+        for (int i = 0; i < 9; ++i) { const float v = p[i], a = fabsf(v); if (!(v == 0.0f || (a >= 0x1p-40f && a <= 0x1p40f))) f |= TBL_WILD; }
+        for (int i = 9; i < 14; ++i) if (!(p[i] == 0.0f)) f |= TBL_IBIS;
+    }
+    if (f) atomicOr(flags, f);
+}
+
 bool lens_noop(int lens, const gf_kernel_params* p) {
     const float* k = p->k;
     switch (lens) {
@@ -191,6 +215,15 @@ void fill_uniforms(WarpArgs& A, const gf_cuda_ctx* ctx, const uint8_t* src, cons
     if ((p->flags & 128) == 128) f |= F_FB_INV;
     if (p->plane_index == 0) f |= F_IS_Y;
     if (p->translation3d[0] != 0.0f || p->translation3d[1] != 0.0f || p->translation3d[2] != 0.0f) f |= F_T3D;
+    const float maxv = ctx->bpp > 0 && (ctx->layout <= LAY_4U8) ? 255.0f : ((ctx->layout <= LAY_4U16) ? 65535.0f : 3.402823466e38f);
+    if (!(p->pixel_value_limit >= maxv)) f |= F_PIXLIMIT;
+    {   // magnitudes the packed kernel's fast paths rely on (otherwise the scalar lean kernel, which has no such assumptions, runs)
+        bool wild = false;
+        for (int i = 0; i < 12; ++i) if (!(std::isfinite(p->k[i]) && fabsf(p->k[i]) <= 0x1p40f)) wild = true;
+        if (!(fabsf(p->translation2d[0]) < 0x1p19f && fabsf(p->translation2d[1]) < 0x1p19f)) wild = true;
+        if (!(tame(p->f[0]) && tame(p->f[1]) && std::isfinite(p->c[0]) && std::isfinite(p->c[1]))) wild = true;
+        if (wild) f |= F_WILD;
+    }
     A.feat = f;
 
     for (int i = 0; i < 4; ++i) A.bg[i] = p->background[i] * p->max_pixel_value;  // :523
@@ -217,6 +250,9 @@ void fill_uniforms(WarpArgs& A, const gf_cuda_ctx* ctx, const uint8_t* src, cons
     A.u8_limit = (lim != lim) ? 255 : (lim < 0.0f ? 0 : (lim >= 255.0f ? 255 : (int)lim));
     A.src_rect[0] = p->source_rect[0]; A.src_rect[1] = p->source_rect[1];
     A.src_rect[2] = p->source_rect[0] + p->source_rect[2]; A.src_rect[3] = p->source_rect[1] + p->source_rect[3];
+    A.interior_span[0] = A.src_rect[2] - 2 - A.src_rect[0]; A.interior_span[1] = A.src_rect[3] - 2 - A.src_rect[1];
+    if (A.interior_span[0] < 0 || A.interior_span[1] < 0) { A.interior_span[0] = 0; A.interior_span[1] = 0; A.feat |= F_WILD; }   // no interior at all
+    if (!(A.smap_x.fast_div && A.smap_y.fast_div && A.smap_x.mul != 0.0f && A.smap_y.mul != 0.0f)) A.feat |= F_WILD;
 }
 
 } // namespace
@@ -272,14 +308,12 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0);
     KernelFn fn_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1);
     KernelFn fn_x2 = getenv("GF_DISABLE_X2") ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 2);
-    // measured slower than the plain packed kernel on B200 (6.7k vs 7.75k frames/s at 4K): with ~1 degree of roll an 8x8 tile is
-    // "decisive" only 23 % of the time, so the exact fallback runs for 77 % of the tiles on top of the coarse pass.  Opt-in only.
-    KernelFn fn_tile = (getenv("GF_ENABLE_TILE") && !getenv("GF_DISABLE_X2")) ? find_kernel(distortion_model, digital_lens, layout, params->interpolation, 3) : nullptr;
+    KernelFn fn_x2t = getenv("GF_DISABLE_X2") ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 3);
     if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
 
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
-    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_tile = fn_tile;
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_x2t = fn_x2t;
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -322,6 +356,7 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
     }
     if (ctx->d_src) cudaFree(ctx->d_src);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
+    if (ctx->d_vflags) cudaFree(ctx->d_vflags);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
     delete ctx;
@@ -351,7 +386,10 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     WarpArgs A;
     memset(&A, 0, sizeof(A));
     A.p = *p;
+    uint32_t table_flags = TBL_WILD;       // unknown device tables are not trusted until validated
     if (tables_on_device) {
+        auto it = ctx->validated.find((const void*)matrices);
+        if (it != ctx->validated.end()) table_flags = it->second;
         A.matrices = matrices;
         A.mesh = mesh_len ? mesh : nullptr;
     } else {
@@ -359,6 +397,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         ctx->next_slot = (ctx->next_slot + 1) % kSlots;
         CK(cudaEventSynchronize(sl.done));                     // the slot's previous frame has consumed its tables
         memcpy(sl.h_mat, matrices, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float));
+        table_flags = scan_tables_host(sl.h_mat, (size_t)p->matrix_count);
         CK(cudaMemcpyAsync(sl.d_mat, sl.h_mat, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float), cudaMemcpyHostToDevice, st));
         A.matrices = sl.d_mat;
         if (mesh_len) {
@@ -398,13 +437,11 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
-    if (lean_ok && ctx->fn_tile) {
-        const dim3 grid3((A.out_cols + 2 * GF_TILE_REGION_W - 1) / (2 * GF_TILE_REGION_W), (A.out_rows + 4 * GF_TILE_REGION_H - 1) / (4 * GF_TILE_REGION_H));
-        ctx->fn_tile<<<grid3, block, 0, st>>>(A); ctx->tile_launches++;
-    }
-    else if (lean_ok && ctx->fn_x2) {
+    // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
+    KernelFn x2 = ((A.feat & F_WILD) != 0) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
+    if (lean_ok && x2) {
         const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
-        ctx->fn_x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
+        x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
     }
     else if (lean_ok) { ctx->fn_lean<<<grid, block, 0, st>>>(A); ctx->lean_launches++; }
     else         { ctx->fn<<<grid, block, 0, st>>>(A); }
@@ -440,6 +477,20 @@ GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx, const gf_buffer_desc*
                                          const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
                                          const float* mesh, size_t mesh_len, void* cu_stream) {
     return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream, false);
+}
+
+GF_API int gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows) {
+    if (!ctx || !matrices_dev) return fail(ctx, GF_ERR_BAD_PARAMS, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_vflags) CK(cudaMalloc(&ctx->d_vflags, sizeof(unsigned)));
+    CK(cudaMemsetAsync(ctx->d_vflags, 0, sizeof(unsigned), ctx->stream));
+    scan_tables_kernel<<<32, 256, 0, ctx->stream>>>(matrices_dev, matrix_rows, ctx->d_vflags);
+    CK(cudaGetLastError());
+    unsigned f = 0;
+    CK(cudaMemcpyAsync(&f, ctx->d_vflags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->validated[(const void*)matrices_dev] = f;
+    return (int)f;      // 0 = tame and IBIS-free; bit 0 = wild entry, bit 1 = IBIS rows present (both still render correctly, on the guarded path)
 }
 
 GF_API int gf_cuda_synchronize(gf_cuda_ctx* ctx) {

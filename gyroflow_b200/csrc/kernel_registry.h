@@ -4,7 +4,7 @@
 // here every valid combination is compiled for sm_100a up front and looked up by id.
 #pragma once
 #include <cstdlib>
-#include "warp_kernel_tile.cuh"
+#include "warp_kernel_x2.cuh"
 
 namespace gf {
 
@@ -32,34 +32,28 @@ KernelFn gf_kernel_sony(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
 
-// lean == 2: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form
+// lean == 2 / 3: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form;
+// 3 = tables validated (no wild entries, no IBIS rows), 2 = unvalidated device tables (per-pixel numerator / IBIS tests kept)
 template <int LENS, int DIGITAL, class PIX>
-static KernelFn pick_x2(int interp) {
+static KernelFn pick_x2(int interp, bool trusted) {
     if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) {
         if (interp == GF_INTERP_BILINEAR) {
             const char* e = getenv("GF_X2_MINB");            // tuning knob: resident blocks per SM the register budget targets
-            const int minb = e ? atoi(e) : 6;                // measured on B200 (4K RGBA8 fisheye+RS): 4 -> 7150, 5 -> 7740, 6 -> 7750 frames/s
-            if (minb == 4) return warp_kernel_x2<LENS, PIX, 4>;
-            if (minb == 5) return warp_kernel_x2<LENS, PIX, 5>;
-            return warp_kernel_x2<LENS, PIX, 6>;
-        }
-    }
-    return nullptr;
-}
-// lean == 3: packed kernel + rolling-shutter row search amortised over a warp tile (warp_kernel_tile.cuh)
-template <int LENS, int DIGITAL, class PIX>
-static KernelFn pick_tile(int interp) {
-    if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) {
-        if (interp == GF_INTERP_BILINEAR) {
-            return warp_kernel_tile<LENS, PIX, 4>;
+            const int minb = e ? atoi(e) : 6;
+            if (trusted) {
+                if (minb == 4) return warp_kernel_x2<LENS, PIX, 4, true>;
+                if (minb == 5) return warp_kernel_x2<LENS, PIX, 5, true>;
+                return warp_kernel_x2<LENS, PIX, 6, true>;
+            }
+            return warp_kernel_x2<LENS, PIX, 6, false>;
         }
     }
     return nullptr;
 }
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
-    if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp);
-    if (lean == 3) return pick_tile<LENS, DIGITAL, PIX>(interp);
+    if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp, false);
+    if (lean == 3) return pick_x2<LENS, DIGITAL, PIX>(interp, true);
     switch (interp) {
     case GF_INTERP_BILINEAR: return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
 #ifdef GF_ENABLE_HIGH_ORDER

@@ -50,9 +50,28 @@ __global__ void selftest_kernel(unsigned long long n, unsigned long long seed, u
         const float ad = fabsf(dv);
         m.fast_div = (ad >= 0x1p-40f && ad <= 0x1p40f) ? 1 : 0;
         if (!same(div_uniform(a0, m), a0 / dv)) bad[3]++;
-        const p2::f2 mq = map_apply_x2(p2::mk(a0, b1), m);
-        if (!same(mq.x, ((a0 - 0.0f) * 1.0f) / dv + 0.0f)) bad[3]++;
-        if (!same(mq.y, ((b1 - 0.0f) * 1.0f) / dv + 0.0f)) bad[3]++;
+        if (m.fast_div) {
+            bool flagged = false;                        // the kernel sends flagged pairs to the scalar code; unflagged ones must be exact
+            const p2::f2 mq = map_apply_x2(p2::mk(a0, b1), m, true, true, flagged);
+            if (!flagged && !same(mq.x, ((a0 - 0.0f) * 1.0f) / dv + 0.0f)) bad[3]++;
+            if (!flagged && !same(mq.y, ((b1 - 0.0f) * 1.0f) / dv + 0.0f)) bad[3]++;
+        }
+        if (round_away_i32(a0) != as_i32(rs_round(a0))) bad[3]++;
+        if (round_away_i32(b1 * 32.0f) != as_i32(rs_round(b1 * 32.0f))) bad[3]++;
+        // straight-line atanf on the range the kernel admits (r = sqrt(a), a in [2^-56, 2^48))
+        const float c0 = fabsf(a1), c1 = fabsf(b0);
+        if (in_window_r2(c0) && in_window_r2(c1)) {
+            const p2::f2 rr = p2::sqrt_seq(p2::mk(c0, c1));
+            if (!same(rr.x, sqrtf(c0)) || !same(rr.y, sqrtf(c1))) bad[1]++;
+            const p2::f2 tc = p2::atanf2_core(rr, tab);
+            if (!same(tc.x, gf_atanf(rr.x))) bad[2]++;
+            if (!same(tc.y, gf_atanf(rr.y))) bad[2]++;
+        }
+        // unguarded division inside the windows the kernel checks
+        if (p2::in_window(b0) && p2::in_window(b1) && zero_or_in_window(a0) && zero_or_in_window(a1)) {
+            const p2::f2 qs = p2::div_seq(p2::mk(a0, a1), p2::mk(b0, b1));
+            if (!same(qs.x, a0 / b0) || !same(qs.y, a1 / b1)) bad[0]++;
+        }
     }
     for (int j = 0; j < 4; ++j) if (bad[j]) atomicAdd(&out[j], bad[j]);
 }

@@ -47,13 +47,15 @@ enum : uint32_t {
     F_FB_INV     = 1u << 18,  // flags & 128
     F_IS_Y       = 1u << 19,  // plane_index == 0
     F_T3D        = 1u << 20,  // translation3d != 0 (x + 0.0f only differs from x in the sign of zero, which no consumer sees)
+    F_PIXLIMIT   = 1u << 21,  // pixel_value_limit below the format's maximum (the min() after sampling can bite)
+    F_WILD       = 1u << 22,  // lens coefficients / translation2d / source mapping outside the magnitudes the packed fast paths assume
 };
 
 // Features the specialised ("lean") instantiation compiles out entirely.  The reference's OpenCL backend does the same
 // thing at run time: it constant-folds every `(params->flags & N)` test into the program text before building it
 // (src/core/gpu/opencl.rs:207-211).  A launch whose feature word has any of these bits uses the general instantiation.
 constexpr uint32_t F_GENERAL_ONLY = F_HRS | F_RLIMIT | F_REFRACT | F_MESH | F_HSTRETCH | F_VSTRETCH | F_LCA | F_INROT |
-                                    F_BG1 | F_BG2 | F_BG3 | F_FIXRANGE | F_FILLBG | F_LENS_NOOP | F_FB_INV | F_T3D;
+                                    F_BG1 | F_BG2 | F_BG3 | F_FIXRANGE | F_FILLBG | F_LENS_NOOP | F_FB_INV | F_T3D | F_PIXLIMIT;
 constexpr uint32_t F_LEAN_REQUIRED = F_SRC_VEC | F_DST_VEC;   // and F_DIGITAL iff a digital lens is compiled in
 
 // has<GEN>(feat, bit): run-time test in the general kernel, compile-time constant in the lean one
@@ -87,6 +89,7 @@ struct WarpArgs {
     int   rs_lim;                   // HRS ? width : height
     int   u8_limit;                 // trunc(min(pixel_value_limit, 255)) for the integer u8 sampler
     int   src_rect[4];              // rx0, ry0, rx1, ry1
+    int   interior_span[2];         // rx1 - 2 - rx0, ry1 - 2 - ry0: a bilinear footprint at (sx, sy) is interior iff (unsigned)(sx - rx0) <= span (both axes)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -1,12 +1,18 @@
 // warp_kernel_x2.cuh — the warp with two output pixels per thread on Blackwell's packed f32x2 pipe.
 //
 // Same arithmetic, same rounding, same results as warp_kernel.cuh (the scalar kernel remains the general
-// implementation and the fallback for every feature this file does not cover).  What changes is the schedule:
-// a thread owns the vertically adjacent pixels (x, y) and (x, y + 1); every FP32 multiply/add of the
-// undistort -> rotate -> redistort chain is issued once for both (FFMA2/FMUL2/FADD2, see f32x2.cuh), the range
-// selection of atanf becomes a shared-memory table lookup so both lanes run straight-line code, and division /
-// square root use the compiler's own MUFU + FFMA refinement sequences on pairs.  Only the "lean" feature set
-// (see F_GENERAL_ONLY in warp_kernel.cuh) is compiled here.
+// implementation and the exact fallback).  What changes is the schedule:
+//   * a thread owns the vertically adjacent pixels (x, y) and (x, y + 1); every FP32 multiply/add of the
+//     undistort -> rotate -> redistort chain is issued once for both (FFMA2, see f32x2.cuh);
+//   * the hot path is BRANCH-FREE: divisions, square roots and atanf run their exact fast sequences unconditionally
+//     while a handful of integer tests accumulate one `bad` predicate (an operand outside the magnitude window in which
+//     those sequences are the correctly rounded result, a scanline with IBIS data, ...).  Only if `bad` is set — in
+//     practice never — the pair is re-evaluated with the scalar kernel's code (cold, out of line).  No convergence
+//     barriers, no slow-path stubs inside the arithmetic, so the scheduler can overlap the two lens evaluations' loads,
+//     MUFU ops and FFMA2 chains;
+//   * `TRUSTED` tables: the host (or gf_cuda_validate_tables_dev) has checked that every matrix entry is zero or of
+//     moderate magnitude and that no row carries IBIS data, which removes the per-pixel numerator / IBIS tests.
+// Only the "lean" feature set (F_GENERAL_ONLY in warp_kernel.cuh) is compiled here.
 //
 // Behavioural source: src/core/stabilization/cpu_undistort.rs:133-228, :421-517, :543-625 (as warp_kernel.cuh).
 #pragma once
@@ -17,28 +23,41 @@ namespace gf {
 
 using p2::f2;
 
+// `a` in [2^-56, 2^48): then r = sqrt(a) lies in [2^-28, 2^24), strictly inside atanf's ordinary range [2^-29, 2^25)
+GF_DEV bool in_window_r2(float a) {
+    const uint32_t t = (__float_as_uint(a) << 1) - (71u << 24);
+    return t < (104u << 24);
+}
+// zero, or 2^-60 <= |v| <= 2^60
+GF_DEV bool zero_or_in_window(float v) {
+    const uint32_t u = __float_as_uint(v) << 1;
+    return u == 0u || (u - (67u << 24)) < (121u << 24);
+}
+
 // ------------------------------------------------------------------------------------------
 // packed lens models: Lens2<M>::distort(x, y, z) for two pixels.  kHas = a packed implementation exists.
+// `bad` is OR-ed with "some lane left the window in which the fast sequences are exact".
 // ------------------------------------------------------------------------------------------
 template <int M> struct Lens2 { static constexpr bool kHas = false; };
 
-// opencv_fisheye.rs:72-93 (k != 0: the lean kernel is only chosen when F_LENS_NOOP is clear)
+// opencv_fisheye.rs:72-93 (k != 0: the lean kernel is only chosen when F_LENS_NOOP is clear; |k| bounded by the host)
 template <> struct Lens2<GF_LENS_OPENCV_FISHEYE> {
     static constexpr bool kHas = true;
-    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, const p2::AtanRow* tab, f2& ox, f2& oy) {
+    static GF_DEV void distort(f2 x, f2 y, f2 z, bool va, bool vb, const gf_kernel_params& P, const p2::AtanRow* tab, f2& ox, f2& oy, bool& bad) {
         using namespace p2;
-        const bool ok = in_window(x) && in_window(y) && in_window(z);
-        x = div_exact(x, z, ok); y = div_exact(y, z, ok);
-        const f2 r = sqrt_exact(add(mul(x, x), mul(y, y)));
-        const f2 theta = atanf2(r, tab);
+        bad |= (va && !in_window(z.x)) || (vb && !in_window(z.y));
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 a = add(mul(x, x), mul(y, y));
+        bad |= (va && !in_window_r2(a.x)) || (vb && !in_window_r2(a.y));     // also excludes r == 0 and atanf's special ranges
+        const f2 r = sqrt_seq(a);
+        const f2 theta = atanf2_core(r, tab);
         const f2 theta2 = mul(theta, theta), theta4 = mul(theta2, theta2), theta6 = mul(theta4, theta2), theta8 = mul(theta4, theta4);
         f2 s = add(bc(1.0f), mul(bc(P.k[0]), theta2));
         s = add(s, mul(bc(P.k[1]), theta4));
         s = add(s, mul(bc(P.k[2]), theta6));
         s = add(s, mul(bc(P.k[3]), theta8));
         const f2 theta_d = mul(theta, s);
-        const f2 q = div_exact(theta_d, r, in_window(theta_d) && in_window(r));
-        const f2 scale = mk(r.x == 0.0f ? 1.0f : q.x, r.y == 0.0f ? 1.0f : q.y);
+        const f2 scale = div_seq(theta_d, r);           // r != 0 whenever !bad; theta_d is 0 or of moderate size (|k| <= 2^40, host-checked)
         ox = mul(x, scale); oy = mul(y, scale);
     }
 };
@@ -55,65 +74,80 @@ GF_DEV MatRow load_row(const float* __restrict__ matrices, uint32_t idx) {
     r.m89 = __ldg(mp + 4); r.m1011 = __ldg(mp + 5); r.m1213 = __ldg(mp + 6);
     return r;
 }
-GF_DEV bool row_has_ibis(const MatRow& r) {      // :157 — any of m[9..13] != 0.0
-    return ((__float_as_uint(r.m89.y) | __float_as_uint(r.m1011.x) | __float_as_uint(r.m1011.y) |
-             __float_as_uint(r.m1213.x) | __float_as_uint(r.m1213.y)) << 1) != 0u;
+struct MatRow9 { float2 m01, m23, m45, m67; float m8; };      // rows without the IBIS tail (TRUSTED tables have none)
+GF_DEV MatRow9 load_row9(const float* __restrict__ matrices, uint32_t idx) {
+    const float2* __restrict__ mp = reinterpret_cast<const float2*>(matrices + (size_t)idx * GF_MATRIX_STRIDE);
+    MatRow9 r;
+    r.m01 = __ldg(mp + 0); r.m23 = __ldg(mp + 1); r.m45 = __ldg(mp + 2); r.m67 = __ldg(mp + 3);
+    r.m8 = __ldg(reinterpret_cast<const float*>(mp + 4));
+    return r;
 }
-GF_DEV void apply_ibis(const MatRow& r, float& ux, float& uy) {     // :158-164
-    const float ang_rad = r.m1011.y;
-    const float cos_a = gf_cosf(-ang_rad), sin_a = gf_sinf(-ang_rad);
-    const float tx = cos_a * ux - sin_a * uy - r.m89.y   + r.m1213.x;
-    const float ty = sin_a * ux + cos_a * uy - r.m1011.x + r.m1213.y;
-    ux = tx; uy = ty;
+GF_DEV bool row_has_ibis(const float* __restrict__ matrices, uint32_t idx) {      // :157 — any of m[9..13] != 0.0
+    const float* __restrict__ m = matrices + (size_t)idx * GF_MATRIX_STRIDE;
+    return ((__float_as_uint(__ldg(m + 9)) | __float_as_uint(__ldg(m + 10)) | __float_as_uint(__ldg(m + 11)) |
+             __float_as_uint(__ldg(m + 12)) | __float_as_uint(__ldg(m + 13))) << 1) != 0u;
 }
 
-template <int LENS>
-GF_DEV void rotate_and_distort_x2(f2 px, f2 py, const MatRow& ra, const MatRow& rb, const WarpArgs& A, const p2::AtanRow* tab,
-                                  f2& ou, f2& ov, bool& oka, bool& okb) {
+// hot path: no branches.  Returns u, v for both lanes, validity (w > 0) per lane, and ORs `bad`.
+template <int LENS, bool TRUSTED>
+GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, const p2::AtanRow* tab,
+                                  f2& ou, f2& ov, bool& oka, bool& okb, bool& bad) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
+    const MatRow9 ra = load_row9(A.matrices, idx_a), rb = load_row9(A.matrices, idx_b);
     const f2 _x = add(add(mul(px, mk(ra.m01.x, rb.m01.x)), mul(py, mk(ra.m01.y, rb.m01.y))), mk(ra.m23.x, rb.m23.x));
     const f2 _y = add(add(mul(px, mk(ra.m23.y, rb.m23.y)), mul(py, mk(ra.m45.x, rb.m45.x))), mk(ra.m45.y, rb.m45.y));
-    const f2 _w = add(add(mul(px, mk(ra.m67.x, rb.m67.x)), mul(py, mk(ra.m67.y, rb.m67.y))), mk(ra.m89.x, rb.m89.x));
+    const f2 _w = add(add(mul(px, mk(ra.m67.x, rb.m67.x)), mul(py, mk(ra.m67.y, rb.m67.y))), mk(ra.m8, rb.m8));
     oka = _w.x > 0.0f; okb = _w.y > 0.0f;                                                              // :138
+    if (!TRUSTED) {
+        bad |= (oka && (!zero_or_in_window(_x.x) || !zero_or_in_window(_y.x) || row_has_ibis(A.matrices, idx_a))) ||
+               (okb && (!zero_or_in_window(_x.y) || !zero_or_in_window(_y.y) || row_has_ibis(A.matrices, idx_b)));
+    }
     f2 ux, uy;
-    Lens2<LENS>::distort(_x, _y, _w, P, tab, ux, uy);                                                  // :154
+    Lens2<LENS>::distort(_x, _y, _w, oka, okb, P, tab, ux, uy, bad);                                   // :154
     ux = mul(ux, bc(P.f[0])); uy = mul(uy, bc(P.f[1]));                                                // :155
-    if (row_has_ibis(ra)) apply_ibis(ra, ux.x, uy.x);                                                  // :157-165
-    if (row_has_ibis(rb)) apply_ibis(rb, ux.y, uy.y);
-    ou = add(ux, bc(P.c[0])); ov = add(uy, bc(P.c[1]));                                                // :167
+    ou = add(ux, bc(P.c[0])); ov = add(uy, bc(P.c[1]));                                                // :167 (no IBIS rows on this path)
 }
 
-// map_coord with a uniform divisor on a pair (see div_uniform in warp_kernel.cuh)
-GF_DEV f2 map_apply_x2(f2 x, const MapC& m) {
+// cold path: the scalar kernel's exact code for one pixel
+template <int LENS>
+static __device__ __noinline__ bool rotate_and_distort_cold(float px, float py, uint32_t idx, const WarpArgs& A, float& u, float& v) {
+    return rotate_and_distort<LENS, GF_LENS_NONE, false>(px, py, idx, A, u, v);
+}
+
+// map_coord with a uniform divisor on a pair (see div_uniform in warp_kernel.cuh); `bad` if a numerator leaves the window
+GF_DEV f2 map_apply_x2(f2 x, const MapC& m, bool va, bool vb, bool& bad) {
     using namespace p2;
     const f2 a = mul(sub(x, bc(m.in_min)), bc(m.mul));
     const float a0 = fabsf(a.x), a1 = fabsf(a.y);
-    f2 q;
-    if (m.fast_div && a0 < 0x1p60f && a0 > 0x1p-80f && a1 < 0x1p60f && a1 > 0x1p-80f) {
-        const f2 q0 = mul(a, bc(m.rcp));
-        const f2 r0 = fma(bc(-m.div), q0, a);
-        q = fma(r0, bc(m.rcp), q0);
-    } else {
-        q = mk(a.x / m.div, a.y / m.div);
-    }
-    return add(q, bc(m.add));
+    bad |= (va && !(a0 < 0x1p60f && a0 > 0x1p-80f)) || (vb && !(a1 < 0x1p60f && a1 > 0x1p-80f));
+    const f2 q0 = mul(a, bc(m.rcp));
+    const f2 r0 = fma(bc(-m.div), q0, a);
+    return add(fma(r0, bc(m.rcp), q0), bc(m.add));
 }
 
-// sampling + conversion + store of one pixel, lean feature set (no fix_range, background mode 0)
+// (v * 32).round() as i32 — f32::round is half away from zero.  (double)t + (+-0.5) is exact for every float t below 2^28 and
+// truncation toward zero of that sum is round-half-away; above, t is an integer already.  cvt.rzi.s32.f64 saturates and maps NaN to 0
+// like Rust's `as i32`.
+GF_DEV int round_away_i32(float t) {
+    const double h = __hiloint2double((int)((__float_as_uint(t) & 0x80000000u) | 0x3fe00000u), 0);     // copysign(0.5, t)
+    return __double2int_rz((double)t + h);
+}
+
+// sampling + conversion + store of one pixel, lean feature set (no fix_range, background mode 0, pixel_value_limit >= max)
 template <class PIX>
 GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __restrict__ out) {
     constexpr int C = PIX::COUNT;
     float pixel[C];
     if (ok) {
         if (PIX::SCALAR == SC_U8) {
-            const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
+            const int sx0 = round_away_i32(u * 32.0f), sy0 = round_away_i32(v * 32.0f);
             const int sx = sx0 >> 5, sy = sy0 >> 5;
-            if (sx >= A.src_rect[0] && sx + 2 <= A.src_rect[2] && sy >= A.src_rect[1] && sy + 2 <= A.src_rect[3]) {
+            if ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0] && (unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]) {
                 uint32_t N[C], s[C];
                 sample_u8_bilinear<PIX>(sx0, sy0, A, N);
                 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) s[ch] = (uint32_t)min((int)(N[ch] >> 10), A.u8_limit);
+                for (int ch = 0; ch < C; ++ch) s[ch] = N[ch] >> 10;      // trunc(N / 1024); N / 1024 <= 255 <= pixel_value_limit
                 PIX::store_scalars(out, true, s);
                 return;
             }
@@ -130,7 +164,7 @@ GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __
 
 #define GF_X2_ROWS_PER_BLOCK (2 * GF_BLOCK_Y)
 
-template <int LENS, class PIX, int MINB>
+template <int LENS, class PIX, int MINB, bool TRUSTED>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     using namespace p2;
@@ -155,25 +189,37 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     if (!wr_a && !wr_b) return;
 
     // undistort_coord, :421-517
-    const f2 px = bc(opx + P.translation2d[0]);
+    const float pxs = opx + P.translation2d[0];
+    const f2 px = bc(pxs);
     const f2 py = mk(opy_a + P.translation2d[1], opy_b + P.translation2d[1]);
     const int lim = A.rs_lim;
-    int sy_a = max(min(as_i32(rs_round(py.x)), lim), 0);
-    int sy_b = max(min(as_i32(rs_round(py.y)), lim), 0);
+    int sy_a = max(min(round_away_i32(py.x), lim), 0);                                                  // :465-469
+    int sy_b = max(min(round_away_i32(py.y), lim), 0);
     if (A.feat & F_RS) {                                                                                // :470-479
-        const MatRow mid = load_row(A.matrices, (uint32_t)P.matrix_count / 2u);
-        f2 tu, tv; bool oa, ob;
-        rotate_and_distort_x2<LENS>(px, py, mid, mid, A, atan_tab, tu, tv, oa, ob);
-        if (oa) sy_a = max(min(as_i32(rs_round(tv.x)), lim), 0);
-        if (ob) sy_b = max(min(as_i32(rs_round(tv.y)), lim), 0);
+        const uint32_t mid = (uint32_t)P.matrix_count / 2u;
+        f2 tu, tv; bool oa, ob, bad = false;
+        rotate_and_distort_x2<LENS, TRUSTED>(px, py, mid, mid, A, atan_tab, tu, tv, oa, ob, bad);
+        if (bad) {                                       // cold: exact scalar code for both pixels
+            float cu, cv;
+            oa = rotate_and_distort_cold<LENS>(pxs, py.x, mid, A, cu, cv); tv.x = cv;
+            ob = rotate_and_distort_cold<LENS>(pxs, py.y, mid, A, cu, cv); tv.y = cv;
+        }
+        if (oa) sy_a = max(min(round_away_i32(tv.x), lim), 0);
+        if (ob) sy_b = max(min(round_away_i32(tv.y), lim), 0);
     }
     const uint32_t last = (uint32_t)(P.matrix_count - 1);
-    const MatRow ra = load_row(A.matrices, min((uint32_t)sy_a, last));                                  // :482
-    const MatRow rb = load_row(A.matrices, min((uint32_t)sy_b, last));
-    f2 u, v; bool ok_a, ok_b;
-    rotate_and_distort_x2<LENS>(px, py, ra, rb, A, atan_tab, u, v, ok_a, ok_b);                         // :483
-    u = map_apply_x2(u, A.smap_x);                                                                      // :510-515
-    v = map_apply_x2(v, A.smap_y);
+    const uint32_t idx_a = min((uint32_t)sy_a, last), idx_b = min((uint32_t)sy_b, last);               // :482
+    f2 u, v; bool ok_a, ok_b, bad = false;
+    rotate_and_distort_x2<LENS, TRUSTED>(px, py, idx_a, idx_b, A, atan_tab, u, v, ok_a, ok_b, bad);     // :483
+    u = map_apply_x2(u, A.smap_x, ok_a, ok_b, bad);                                                     // :510-515
+    v = map_apply_x2(v, A.smap_y, ok_a, ok_b, bad);
+    if (bad) {
+        float cu, cv;
+        ok_a = rotate_and_distort_cold<LENS>(pxs, py.x, idx_a, A, cu, cv);
+        if (ok_a) { u.x = map_apply(cu, A.smap_x); v.x = map_apply(cv, A.smap_y); }
+        ok_b = rotate_and_distort_cold<LENS>(pxs, py.y, idx_b, A, cu, cv);
+        if (ok_b) { u.y = map_apply(cu, A.smap_x); v.y = map_apply(cv, A.smap_y); }
+    }
 
     if (wr_a) shade_lean<PIX>(ok_a, u.x, v.x, A, A.dst + off_a);                                        // :615-622
     if (wr_b) shade_lean<PIX>(ok_b, u.y, v.y, A, A.dst + off_b);

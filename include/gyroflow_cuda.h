@@ -254,6 +254,12 @@ GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx,
                                          const float* matrices, size_t matrix_rows,
                                          const float* mesh, size_t mesh_len, void* cu_stream);
 
+/* Device-resident tables (gf_cuda_undistort_image_dev) are untrusted by default: the kernel keeps per-pixel tests for wild matrix
+ * entries and IBIS rows.  This call scans `matrix_rows x 14` floats on the device once and remembers the verdict for that pointer
+ * (until gf_cuda_destroy; call it again after rewriting the table).  Returns 0 (tame, IBIS-free: fastest path), a positive bit mask
+ * (1 = wild entry, 2 = IBIS rows; still rendered correctly), or a negative GF_ERR_*.  Host tables are scanned while they are staged. */
+GF_API int         gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows);
+
 GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
 GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
 GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */

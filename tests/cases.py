@@ -66,6 +66,8 @@ def build(case):
                 return (3.0 * math.sin(6.28 * t), -3.0 * math.cos(6.28 * t), math.radians(0.2) * math.sin(3.0 * t), math.sin(9.0 * t), -math.cos(5.0 * t))
         m = synth.frame_matrices(p, org, sm, case.get("ts", 1000.0), frame_readout_time_ms=(case.get("readout", 16.0) if rs else 0.0),
                                  video_rotation_deg=case.get("video_rotation", 0.0), horizontal=bool(case.get("horizontal_rs")), ibis=ibis)
+    if case.get("matrix_hook"):
+        m = np.ascontiguousarray(case["matrix_hook"](m.copy()), dtype=np.float32)
     p.matrix_count = m.shape[0]
     mesh = None
     if case.get("mesh"):

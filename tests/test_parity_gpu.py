@@ -234,10 +234,8 @@ def test_packed_primitives_selftest():
     assert list(out) == [0, 0, 0, 0], list(out)
 
 
-def test_row_search_stress(monkeypatch):
-    """The (opt-in) tile kernel's interpolated rolling-shutter row search must reproduce the exact search: many frames, strong
-    shake, in-plane rotation (large d(pt.y)/dx), zoomed-out views with invalid (w <= 0) regions, odd sizes."""
-    monkeypatch.setenv("GF_ENABLE_TILE", "1")
+def test_many_frames_and_rotations():
+    """Many frames, strong shake, in-plane rotation, zoomed-out views with invalid (w <= 0) regions, odd sizes."""
     org, sm = cases.gyro()
     for i in range(12):
         assert_bit_exact(dict(w=1280, h=720, ts=137.0 + 311.7 * i))
@@ -251,15 +249,75 @@ def test_row_search_stress(monkeypatch):
     assert_bit_exact(dict(w=1280, h=720, pix="RGBAf"))
 
 
+def _wild(kind):
+    def hook(m):
+        n = m.shape[0]
+        if kind == "nan_row":    m[n // 3, :9] = np.nan
+        if kind == "inf":        m[n // 2, 2] = np.inf; m[n // 2 + 1, 8] = -np.inf
+        if kind == "huge":       m[n // 4:n // 4 + 5, :9] *= np.float32(1e30)
+        if kind == "tiny":       m[n // 4:n // 4 + 5, :9] *= np.float32(1e-30)
+        if kind == "denormal":   m[n // 5, :9] *= np.float32(1e-38); m[n // 5 + 1, 6:9] = np.float32(1e-44)
+        if kind == "zero_rows":  m[::7, :9] = 0.0
+        if kind == "zero_w":     m[n // 2:n // 2 + 9, 6:9] = 0.0
+        if kind == "negzero":    m[::5, 0:2] = -0.0
+        if kind == "on_axis":    m[:, 0:2] = 0.0; m[:, 3:5] = 0.0; m[:, 2] = 0.0; m[:, 5] = 0.0       # x = y = 0 everywhere: r == 0 branch
+        if kind == "ibis_some":  m[n // 2:, 9] = 2.5; m[n // 2:, 11] = 0.01
+        if kind == "ibis_negzero": m[:, 9:14] = -0.0                                                 # -0.0 != 0.0 is false: not IBIS
+        return m
+    return hook
+
+
+@pytest.mark.parametrize("kind", ["nan_row", "inf", "huge", "tiny", "denormal", "zero_rows", "zero_w", "negzero", "on_axis", "ibis_some", "ibis_negzero"])
+def test_packed_kernel_cold_path_on_unusual_tables(kind):
+    """Tables the packed kernel's fast sequences do not cover (non-finite / extreme entries, r == 0, IBIS rows under a fisheye
+    lens) must take the exact scalar code and still match the CPU path byte for byte."""
+    for rs in (True, False):
+        assert_bit_exact(dict(w=640, h=360, rs=rs, matrix_hook=_wild(kind)))
+
+
+def test_packed_kernel_unusual_params():
+    assert_bit_exact(dict(w=640, h=360, params=dict(pixel_value_limit=200.0)))
+    assert_bit_exact(dict(w=640, h=360, params=dict(k=[1e30, -1e30, 0.0, 0.0] + [0.0] * 8)))
+    assert_bit_exact(dict(w=640, h=360, params=dict(k=[float("nan"), 0.1, 0.0, 0.0] + [0.0] * 8)))
+    assert_bit_exact(dict(w=640, h=360, params=dict(k=[-0.3, 0.0, 0.0, 0.0] + [0.0] * 8)))         # theta_d crosses zero
+    assert_bit_exact(dict(w=640, h=360, params=dict(translation2d=[1e6, -3.25])))
+    assert_bit_exact(dict(w=640, h=360, params=dict(f=[1e-30, 1e30])))
+    assert_bit_exact(dict(w=640, h=360, params=dict(c=[0.0, 0.0])))
+    assert_bit_exact(dict(w=640, h=360, in_size=(640, 362), in_rect=(0, 1, 640, 1)))                  # 1-row source rect: no interior
+
+
+def test_device_tables_validated_and_not():
+    """gf_cuda_undistort_image_dev on unvalidated tables (guarded kernel) and validated ones (trusted kernel) == oracle;
+    validation reports wild entries / IBIS rows and those tables still render exactly."""
+    import torch
+    for hook, verdict in ((None, 0), (_wild("huge"), 1), (_wild("ibis_some"), 2), (_wild("nan_row"), 1)):
+        case = dict(w=1280, h=720)
+        if hook: case["matrix_hook"] = hook
+        p, src, m, mesh, dst0, pix, lens, digital = cases.build(case)
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        tsrc = torch.from_numpy(src).cuda(); tm = torch.from_numpy(m).cuda()
+        outs = []
+        for validate in (False, True):
+            tdst = torch.from_numpy(dst0.copy()).cuda()
+            bufs = g.Buffers(g.BufferDescription((1280, 720, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
+                             g.BufferDescription((1280, 720, p.output_stride), tdst.data_ptr(), length=tdst.numel()))
+            w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+            torch.cuda.synchronize()
+            if validate:
+                assert w.validate_tables_dev(tm.data_ptr(), m.shape[0]) == verdict
+            side = torch.cuda.Stream()
+            w.undistort_image_dev(bufs, p, tm.data_ptr(), m.shape[0], stream=side.cuda_stream)
+            side.synchronize()
+            outs.append(tdst.cpu().numpy()); w.close()
+        assert np.array_equal(outs[0], want) and np.array_equal(outs[1], want)
+
+
 def test_kernel_variants_agree(monkeypatch):
     """The packed two-pixel kernel, the lean scalar kernel and the general kernel produce identical bytes."""
     case = dict(w=1280, h=720)
     want, got_x2, pix = run_both(case)
     assert cases.compare(want, got_x2, pix)[0] == 0
-    monkeypatch.setenv("GF_ENABLE_TILE", "1")
-    _, got_tile, _ = run_both(case)
-    assert np.array_equal(got_x2, got_tile)
-    monkeypatch.delenv("GF_ENABLE_TILE")
     monkeypatch.setenv("GF_DISABLE_X2", "1")
     _, got_lean, _ = run_both(case)
     assert np.array_equal(got_x2, got_lean)
