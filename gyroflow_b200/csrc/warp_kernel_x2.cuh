@@ -37,20 +37,21 @@ GF_DEV bool zero_or_in_window(float v) {
 // ------------------------------------------------------------------------------------------
 // packed lens models: Lens2<M>::distort(x, y, z) for two pixels.  kHas = a packed implementation exists.
 // `bad` is OR-ed with "some lane left the window in which the fast sequences are exact".
+// All predicates are combined with & and | (never && / ||) so that no branch is generated for them.
 // ------------------------------------------------------------------------------------------
 template <int M> struct Lens2 { static constexpr bool kHas = false; };
 
 // opencv_fisheye.rs:72-93 (k != 0: the lean kernel is only chosen when F_LENS_NOOP is clear; |k| bounded by the host)
 template <> struct Lens2<GF_LENS_OPENCV_FISHEYE> {
     static constexpr bool kHas = true;
-    static GF_DEV void distort(f2 x, f2 y, f2 z, bool va, bool vb, const gf_kernel_params& P, const p2::AtanRow* tab, f2& ox, f2& oy, bool& bad) {
+    static GF_DEV void distort(f2 x, f2 y, f2 z, bool va, bool vb, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
         using namespace p2;
-        bad |= (va && !in_window(z.x)) || (vb && !in_window(z.y));
+        bad |= (va & !in_window(z.x)) | (vb & !in_window(z.y));
         x = div_seq(x, z); y = div_seq(y, z);
         const f2 a = add(mul(x, x), mul(y, y));
-        bad |= (va && !in_window_r2(a.x)) || (vb && !in_window_r2(a.y));     // also excludes r == 0 and atanf's special ranges
+        bad |= (va & !in_window_r2(a.x)) | (vb & !in_window_r2(a.y));       // also excludes r == 0 and atanf's special ranges
         const f2 r = sqrt_seq(a);
-        const f2 theta = atanf2_core(r, tab);
+        const f2 theta = atanf2_core(r, GF_ATAN_TAB);
         const f2 theta2 = mul(theta, theta), theta4 = mul(theta2, theta2), theta6 = mul(theta4, theta2), theta8 = mul(theta4, theta4);
         f2 s = add(bc(1.0f), mul(bc(P.k[0]), theta2));
         s = add(s, mul(bc(P.k[1]), theta4));
@@ -66,14 +67,6 @@ template <> struct Lens2<GF_LENS_OPENCV_FISHEYE> {
 // rotate_and_distort for two pixels — cpu_undistort.rs:133-228, lean feature set
 // (no translation3d, r_limit, refraction, mesh, digital lens, input stretch).
 // ------------------------------------------------------------------------------------------
-struct MatRow { float2 m01, m23, m45, m67, m89, m1011, m1213; };
-GF_DEV MatRow load_row(const float* __restrict__ matrices, uint32_t idx) {
-    const float2* __restrict__ mp = reinterpret_cast<const float2*>(matrices + (size_t)idx * GF_MATRIX_STRIDE);
-    MatRow r;
-    r.m01 = __ldg(mp + 0); r.m23 = __ldg(mp + 1); r.m45 = __ldg(mp + 2); r.m67 = __ldg(mp + 3);
-    r.m89 = __ldg(mp + 4); r.m1011 = __ldg(mp + 5); r.m1213 = __ldg(mp + 6);
-    return r;
-}
 struct MatRow9 { float2 m01, m23, m45, m67; float m8; };      // rows without the IBIS tail (TRUSTED tables have none)
 GF_DEV MatRow9 load_row9(const float* __restrict__ matrices, uint32_t idx) {
     const float2* __restrict__ mp = reinterpret_cast<const float2*>(matrices + (size_t)idx * GF_MATRIX_STRIDE);
@@ -90,7 +83,7 @@ GF_DEV bool row_has_ibis(const float* __restrict__ matrices, uint32_t idx) {    
 
 // hot path: no branches.  Returns u, v for both lanes, validity (w > 0) per lane, and ORs `bad`.
 template <int LENS, bool TRUSTED>
-GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, const p2::AtanRow* tab,
+GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A,
                                   f2& ou, f2& ov, bool& oka, bool& okb, bool& bad) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
@@ -100,19 +93,31 @@ GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, 
     const f2 _w = add(add(mul(px, mk(ra.m67.x, rb.m67.x)), mul(py, mk(ra.m67.y, rb.m67.y))), mk(ra.m8, rb.m8));
     oka = _w.x > 0.0f; okb = _w.y > 0.0f;                                                              // :138
     if (!TRUSTED) {
-        bad |= (oka && (!zero_or_in_window(_x.x) || !zero_or_in_window(_y.x) || row_has_ibis(A.matrices, idx_a))) ||
-               (okb && (!zero_or_in_window(_x.y) || !zero_or_in_window(_y.y) || row_has_ibis(A.matrices, idx_b)));
+        bad |= (oka & (!zero_or_in_window(_x.x) | !zero_or_in_window(_y.x) | row_has_ibis(A.matrices, idx_a))) |
+               (okb & (!zero_or_in_window(_x.y) | !zero_or_in_window(_y.y) | row_has_ibis(A.matrices, idx_b)));
     }
     f2 ux, uy;
-    Lens2<LENS>::distort(_x, _y, _w, oka, okb, P, tab, ux, uy, bad);                                   // :154
+    Lens2<LENS>::distort(_x, _y, _w, oka, okb, P, ux, uy, bad);                                        // :154
     ux = mul(ux, bc(P.f[0])); uy = mul(uy, bc(P.f[1]));                                                // :155
     ou = add(ux, bc(P.c[0])); ov = add(uy, bc(P.c[1]));                                                // :167 (no IBIS rows on this path)
 }
 
-// cold path: the scalar kernel's exact code for one pixel
+// cold path: the scalar kernel's exact code for both pixels of the pair, one call site per pass.
+// A NaN coordinate is returned as 0: every consumer rounds it with `as i32`, which maps NaN to 0 (and round(0 * 32) == 0).
+struct PairUV { float ua, va, ub, vb; int ok; };
 template <int LENS>
-static __device__ __noinline__ bool rotate_and_distort_cold(float px, float py, uint32_t idx, const WarpArgs& A, float& u, float& v) {
-    return rotate_and_distort<LENS, GF_LENS_NONE, false>(px, py, idx, A, u, v);
+static __device__ __noinline__ PairUV rotate_and_distort_cold(float px, float pya, float pyb, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, int apply_smap) {
+    PairUV o; o.ua = o.va = o.ub = o.vb = 0.0f; o.ok = 0;
+    float cu, cv;
+    if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pya, idx_a, A, cu, cv)) {
+        if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
+        o.ua = cu == cu ? cu : 0.0f; o.va = cv == cv ? cv : 0.0f; o.ok |= 1;
+    }
+    if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pyb, idx_b, A, cu, cv)) {
+        if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
+        o.ub = cu == cu ? cu : 0.0f; o.vb = cv == cv ? cv : 0.0f; o.ok |= 2;
+    }
+    return o;
 }
 
 // map_coord with a uniform divisor on a pair (see div_uniform in warp_kernel.cuh); `bad` if a numerator leaves the window
@@ -120,46 +125,74 @@ GF_DEV f2 map_apply_x2(f2 x, const MapC& m, bool va, bool vb, bool& bad) {
     using namespace p2;
     const f2 a = mul(sub(x, bc(m.in_min)), bc(m.mul));
     const float a0 = fabsf(a.x), a1 = fabsf(a.y);
-    bad |= (va && !(a0 < 0x1p60f && a0 > 0x1p-80f)) || (vb && !(a1 < 0x1p60f && a1 > 0x1p-80f));
+    bad |= (va & !((a0 < 0x1p60f) & (a0 > 0x1p-80f))) | (vb & !((a1 < 0x1p60f) & (a1 > 0x1p-80f)));
     const f2 q0 = mul(a, bc(m.rcp));
     const f2 r0 = fma(bc(-m.div), q0, a);
     return add(fma(r0, bc(m.rcp), q0), bc(m.add));
 }
+// map_coord of a pixel index; the host only selects this kernel when the map is the identity or has
+// mul, div > 0 of moderate size (then (x - in_min) * mul is +0 or inside the window of the exact two-step division)
+GF_DEV float map_apply_int_lean(float x, const MapC& m) {
+    if (m.identity) return (x - m.in_min) + m.add;
+    const float a = (x - m.in_min) * m.mul;
+    const float q0 = a * m.rcp;
+    const float r0 = __fmaf_rn(-m.div, q0, a);
+    return __fmaf_rn(r0, m.rcp, q0) + m.add;
+}
 
 // (v * 32).round() as i32 — f32::round is half away from zero.  (double)t + (+-0.5) is exact for every float t below 2^28 and
-// truncation toward zero of that sum is round-half-away; above, t is an integer already.  cvt.rzi.s32.f64 saturates and maps NaN to 0
-// like Rust's `as i32`.
-GF_DEV int round_away_i32(float t) {
+// truncation toward zero of that sum is round-half-away; above, t is an integer already.  cvt.rzi.s32.f64 saturates like Rust's
+// `as i32`, but the hardware turns NaN into INT_MIN where Rust gives 0.
+GF_DEV int round_away_i32_nan_min(float t) {
     const double h = __hiloint2double((int)((__float_as_uint(t) & 0x80000000u) | 0x3fe00000u), 0);     // copysign(0.5, t)
     return __double2int_rz((double)t + h);
 }
+GF_DEV int round_away_i32(float t) { const int r = round_away_i32_nan_min(t); return t == t ? r : 0; }
+// max(min(round(t) as i32, lim), 0) with lim >= 0: NaN -> INT_MIN -> 0, the same as NaN -> 0 -> 0
+GF_DEV int round_away_clamped(float t, int lim) { return max(min(round_away_i32_nan_min(t), lim), 0); }
 
-// sampling + conversion + store of one pixel, lean feature set (no fix_range, background mode 0, pixel_value_limit >= max)
+// everything that is not "valid pixel with an interior 8-bit bilinear footprint": background fill or the generic sampler
 template <class PIX>
-GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __restrict__ out) {
+static __device__ __noinline__ void shade_cold(bool ok, int sx0, int sy0, const WarpArgs& A, uint8_t* __restrict__ out) {
     constexpr int C = PIX::COUNT;
     float pixel[C];
     if (ok) {
-        if (PIX::SCALAR == SC_U8) {
-            const int sx0 = round_away_i32(u * 32.0f), sy0 = round_away_i32(v * 32.0f);
-            const int sx = sx0 >> 5, sy = sy0 >> 5;
-            if ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0] && (unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]) {
-                uint32_t N[C], s[C];
-                sample_u8_bilinear<PIX>(sx0, sy0, A, N);
-                #pragma unroll
-                for (int ch = 0; ch < C; ++ch) s[ch] = N[ch] >> 10;      // trunc(N / 1024); N / 1024 <= 255 <= pixel_value_limit
-                PIX::store_scalars(out, true, s);
-                return;
-            }
-            sample_generic<2, PIX>(sx0, sy0, A, pixel);
-        } else {
-            sample_input_at<2, PIX, false>(u, v, A, pixel);
-        }
+        sample_generic<2, PIX>(sx0, sy0, A, pixel);
     } else {
         #pragma unroll
         for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
     }
     PIX::store(out, true, pixel);
+}
+
+// sampling + conversion + store of one pixel, lean feature set (no fix_range, background mode 0, pixel_value_limit >= max).
+// u, v are never NaN here (finite on the hot path, sanitised by the cold one).
+template <class PIX>
+GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __restrict__ out) {
+    constexpr int C = PIX::COUNT;
+    if (PIX::SCALAR == SC_U8) {
+        const int sx0 = round_away_i32_nan_min(u * 32.0f), sy0 = round_away_i32_nan_min(v * 32.0f);
+        const int sx = sx0 >> 5, sy = sy0 >> 5;
+        const bool interior = ok & ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0]) & ((unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]);
+        if (interior) {
+            uint32_t N[C], s[C];
+            sample_u8_bilinear<PIX>(sx0, sy0, A, N);
+            #pragma unroll
+            for (int ch = 0; ch < C; ++ch) s[ch] = N[ch] >> 10;      // trunc(N / 1024); N / 1024 <= 255 <= pixel_value_limit
+            PIX::store_scalars(out, true, s);
+        } else {
+            shade_cold<PIX>(ok, sx0, sy0, A, out);
+        }
+    } else {
+        float pixel[C];
+        if (ok) {
+            sample_input_at<2, PIX, false>(u, v, A, pixel);
+        } else {
+            #pragma unroll
+            for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
+        }
+        PIX::store(out, true, pixel);
+    }
 }
 
 #define GF_X2_ROWS_PER_BLOCK (2 * GF_BLOCK_Y)
@@ -168,10 +201,6 @@ template <int LENS, class PIX, int MINB, bool TRUSTED>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     using namespace p2;
-    __shared__ AtanRow atan_tab[ATAN_ROWS];
-    atan_table_init(atan_tab, threadIdx.y * GF_BLOCK_X + threadIdx.x, GF_BLOCK_X * GF_BLOCK_Y);
-    __syncthreads();
-
     const gf_kernel_params& P = A.p;
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
     const int y0 = (blockIdx.y * GF_BLOCK_Y + threadIdx.y) * 2;
@@ -180,45 +209,41 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     const unsigned long long off_a = (unsigned long long)y0 * ostride + (unsigned long long)x * PIX::BYTES;
     const unsigned long long off_b = off_a + ostride;
     // lane validity: row exists, pixel fits in the buffer (short last row), bounds test of :551
-    const float opx = map_apply_int((float)x, A.omap_x);
-    const float opy_a = map_apply_int((float)y0, A.omap_y);
-    const float opy_b = map_apply_int((float)(y0 + 1), A.omap_y);
-    const bool in_x = opx >= 0.0f && as_i32(opx) < P.output_width;
-    const bool wr_a = in_x && off_a + PIX::BYTES <= A.dst_len && opy_a >= 0.0f && as_i32(opy_a) < P.output_height;
-    const bool wr_b = in_x && (y0 + 1) < A.out_rows && off_b + PIX::BYTES <= A.dst_len && opy_b >= 0.0f && as_i32(opy_b) < P.output_height;
-    if (!wr_a && !wr_b) return;
+    const float opx = map_apply_int_lean((float)x, A.omap_x);
+    const float opy_a = map_apply_int_lean((float)y0, A.omap_y);
+    const float opy_b = map_apply_int_lean((float)(y0 + 1), A.omap_y);
+    const bool in_x = (opx >= 0.0f) & (as_i32(opx) < P.output_width);
+    const bool wr_a = in_x & (off_a + PIX::BYTES <= A.dst_len) & (opy_a >= 0.0f) & (as_i32(opy_a) < P.output_height);
+    const bool wr_b = in_x & ((y0 + 1) < A.out_rows) & (off_b + PIX::BYTES <= A.dst_len) & (opy_b >= 0.0f) & (as_i32(opy_b) < P.output_height);
+    if (!(wr_a | wr_b)) return;
 
     // undistort_coord, :421-517
     const float pxs = opx + P.translation2d[0];
     const f2 px = bc(pxs);
     const f2 py = mk(opy_a + P.translation2d[1], opy_b + P.translation2d[1]);
     const int lim = A.rs_lim;
-    int sy_a = max(min(round_away_i32(py.x), lim), 0);                                                  // :465-469
-    int sy_b = max(min(round_away_i32(py.y), lim), 0);
+    int sy_a = round_away_clamped(py.x, lim);                                                           // :465-469
+    int sy_b = round_away_clamped(py.y, lim);
     if (A.feat & F_RS) {                                                                                // :470-479
         const uint32_t mid = (uint32_t)P.matrix_count / 2u;
         f2 tu, tv; bool oa, ob, bad = false;
-        rotate_and_distort_x2<LENS, TRUSTED>(px, py, mid, mid, A, atan_tab, tu, tv, oa, ob, bad);
+        rotate_and_distort_x2<LENS, TRUSTED>(px, py, mid, mid, A, tu, tv, oa, ob, bad);
         if (bad) {                                       // cold: exact scalar code for both pixels
-            float cu, cv;
-            oa = rotate_and_distort_cold<LENS>(pxs, py.x, mid, A, cu, cv); tv.x = cv;
-            ob = rotate_and_distort_cold<LENS>(pxs, py.y, mid, A, cu, cv); tv.y = cv;
+            const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, mid, mid, A, 0);
+            oa = (c.ok & 1) != 0; ob = (c.ok & 2) != 0; tv = mk(c.va, c.vb);
         }
-        if (oa) sy_a = max(min(round_away_i32(tv.x), lim), 0);
-        if (ob) sy_b = max(min(round_away_i32(tv.y), lim), 0);
+        const int ra = round_away_clamped(tv.x, lim), rb = round_away_clamped(tv.y, lim);
+        sy_a = oa ? ra : sy_a; sy_b = ob ? rb : sy_b;
     }
     const uint32_t last = (uint32_t)(P.matrix_count - 1);
     const uint32_t idx_a = min((uint32_t)sy_a, last), idx_b = min((uint32_t)sy_b, last);               // :482
     f2 u, v; bool ok_a, ok_b, bad = false;
-    rotate_and_distort_x2<LENS, TRUSTED>(px, py, idx_a, idx_b, A, atan_tab, u, v, ok_a, ok_b, bad);     // :483
+    rotate_and_distort_x2<LENS, TRUSTED>(px, py, idx_a, idx_b, A, u, v, ok_a, ok_b, bad);               // :483
     u = map_apply_x2(u, A.smap_x, ok_a, ok_b, bad);                                                     // :510-515
     v = map_apply_x2(v, A.smap_y, ok_a, ok_b, bad);
     if (bad) {
-        float cu, cv;
-        ok_a = rotate_and_distort_cold<LENS>(pxs, py.x, idx_a, A, cu, cv);
-        if (ok_a) { u.x = map_apply(cu, A.smap_x); v.x = map_apply(cv, A.smap_y); }
-        ok_b = rotate_and_distort_cold<LENS>(pxs, py.y, idx_b, A, cu, cv);
-        if (ok_b) { u.y = map_apply(cu, A.smap_x); v.y = map_apply(cv, A.smap_y); }
+        const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, idx_a, idx_b, A, 1);
+        ok_a = (c.ok & 1) != 0; ok_b = (c.ok & 2) != 0; u = mk(c.ua, c.ub); v = mk(c.va, c.vb);
     }
 
     if (wr_a) shade_lean<PIX>(ok_a, u.x, v.x, A, A.dst + off_a);                                        // :615-622
