@@ -251,7 +251,7 @@ void fill_uniforms(WarpArgs& A, const gf_cuda_ctx* ctx, const uint8_t* src, cons
     A.src_rect[0] = p->source_rect[0]; A.src_rect[1] = p->source_rect[1];
     A.src_rect[2] = p->source_rect[0] + p->source_rect[2]; A.src_rect[3] = p->source_rect[1] + p->source_rect[3];
     A.interior_span[0] = A.src_rect[2] - 2 - A.src_rect[0]; A.interior_span[1] = A.src_rect[3] - 2 - A.src_rect[1];
-    if (A.interior_span[0] < 0 || A.interior_span[1] < 0) { A.interior_span[0] = 0; A.interior_span[1] = 0; A.feat |= F_WILD; }   // no interior at all
+    if (A.interior_span[0] < 0 || A.interior_span[1] < 0 || A.interior_span[0] >= (1 << 17) || A.interior_span[1] >= (1 << 17) || A.rs_lim >= (1 << 22)) { A.interior_span[0] = 0; A.interior_span[1] = 0; A.feat |= F_WILD; }   // no interior at all
     if (!(A.smap_x.fast_div && A.smap_y.fast_div && A.smap_x.mul != 0.0f && A.smap_y.mul != 0.0f)) A.feat |= F_WILD;
     // pixel-index maps of the packed kernel: identity, or a positive moderate scale (map_apply_int_lean in warp_kernel_x2.cuh)
     auto int_map_ok = [](const MapC& m) {

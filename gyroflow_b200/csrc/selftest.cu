@@ -62,8 +62,22 @@ __global__ void selftest_kernel(unsigned long long n, unsigned long long seed, u
         }
         if (round_away_i32(a0) != as_i32(rs_round(a0))) bad[3]++;
         if (round_away_i32(b1 * 32.0f) != as_i32(rs_round(b1 * 32.0f))) bad[3]++;
-        const int lim = (int)(mix(k ^ 0x55u) & 0xffffu);
-        if (round_away_clamped(b0, lim) != max(min(as_i32(rs_round(b0)), lim), 0)) bad[3]++;
+        {   // conversion-free rounding: exact inside its window, a safe sentinel outside (contract at round_half_away_w)
+            int wa, wb;
+            round_half_away_w(p2::mul(p2::mk(a0, b0), p2::bc(64.0f)), wa, wb);
+            const float t[2] = {a0 * 32.0f, b0 * 32.0f}; const int r[2] = {wa >> 1, wb >> 1};
+            for (int j = 0; j < 2; ++j) {
+                const int e = as_i32(rs_round(t[j]));
+                const bool fine = (t[j] > -0.25f && t[j] < 4194304.0f) ? (r[j] == e)
+                                : (t[j] >= 4194304.0f) ? (r[j] >= 4194304) : (r[j] <= 0 && (e >= 0 || r[j] < 0));   // t <= -1/4 or NaN
+                if (!fine) bad[3]++;
+            }
+            const int lim = (int)(mix(k ^ 0x55u) & 0x3fffffu);
+            int ra, rb;
+            round_away_clamped_x2(p2::mk(a1, b1), lim, ra, rb);
+            if (ra != max(min(as_i32(rs_round(a1)), lim), 0)) bad[3]++;
+            if (rb != max(min(as_i32(rs_round(b1)), lim), 0)) bad[3]++;
+        }
         // straight-line atanf on the range the kernel admits (r = sqrt(a), a in [2^-56, 2^48))
         const float c0 = fabsf(a1), c1 = fabsf(b0);
         if (in_window_r2(c0) && in_window_r2(c1)) {

@@ -103,7 +103,6 @@ GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, 
 }
 
 // cold path: the scalar kernel's exact code for both pixels of the pair, one call site per pass.
-// A NaN coordinate is returned as 0: every consumer rounds it with `as i32`, which maps NaN to 0 (and round(0 * 32) == 0).
 struct PairUV { float ua, va, ub, vb; int ok; };
 template <int LENS>
 static __device__ __noinline__ PairUV rotate_and_distort_cold(float px, float pya, float pyb, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, int apply_smap) {
@@ -111,11 +110,11 @@ static __device__ __noinline__ PairUV rotate_and_distort_cold(float px, float py
     float cu, cv;
     if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pya, idx_a, A, cu, cv)) {
         if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
-        o.ua = cu == cu ? cu : 0.0f; o.va = cv == cv ? cv : 0.0f; o.ok |= 1;
+        o.ua = cu; o.va = cv; o.ok |= 1;
     }
     if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pyb, idx_b, A, cu, cv)) {
         if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
-        o.ub = cu == cu ? cu : 0.0f; o.vb = cv == cv ? cv : 0.0f; o.ok |= 2;
+        o.ub = cu; o.vb = cv; o.ok |= 2;
     }
     return o;
 }
@@ -140,24 +139,43 @@ GF_DEV float map_apply_int_lean(float x, const MapC& m) {
     return __fmaf_rn(r0, m.rcp, q0) + m.add;
 }
 
-// (v * 32).round() as i32 — f32::round is half away from zero.  (double)t + (+-0.5) is exact for every float t below 2^28 and
-// truncation toward zero of that sum is round-half-away; above, t is an integer already.  cvt.rzi.s32.f64 saturates like Rust's
-// `as i32`, but the hardware turns NaN into INT_MIN where Rust gives 0.
-GF_DEV int round_away_i32_nan_min(float t) {
+// (v * 32).round() as i32 — f32::round is half away from zero.  Exact version: (double)t + (+-0.5) is exact for every float t
+// below 2^28 and truncation toward zero of that sum is round-half-away; above, t is an integer already.  cvt.rzi.s32.f64 saturates
+// like Rust's `as i32`, but the hardware turns NaN into INT_MIN where Rust gives 0, hence the select.
+GF_DEV int round_away_i32(float t) {
     const double h = __hiloint2double((int)((__float_as_uint(t) & 0x80000000u) | 0x3fe00000u), 0);     // copysign(0.5, t)
-    return __double2int_rz((double)t + h);
+    const int r = __double2int_rz((double)t + h);
+    return t == t ? r : 0;
 }
-GF_DEV int round_away_i32(float t) { const int r = round_away_i32_nan_min(t); return t == t ? r : 0; }
-// max(min(round(t) as i32, lim), 0) with lim >= 0: NaN -> INT_MIN -> 0, the same as NaN -> 0 -> 0
-GF_DEV int round_away_clamped(float t, int lim) { return max(min(round_away_i32_nan_min(t), lim), 0); }
 
-// everything that is not "valid pixel with an interior 8-bit bilinear footprint": background fill or the generic sampler
+// Hot-path rounding without conversions (no XU / FP64 pipe work).  Input a2 = 2 * t (exact: t is scaled by a power of two).
+// max(a2, -4) tames large negative values and NaN (fmaxf(NaN, -4) == -4); s = RZ(a2 + 2^23) puts floor(a2) in the mantissa
+// for 0 <= a2 < 2^23, so w = bits(s) - 0x4affffff == floor(2t) + 1 and w >> 1 == floor(t + 1/2) == round-half-away(t).
+// Contract of w >> 1 (checked by the self-test):  -1/4 < t < 2^22: the exact result;  t <= -1/4 or NaN: some value <= 0, and < 0
+// whenever the exact result is < 0 (it may also be -1 where the exact result is 0);  t >= 2^22 (or +inf): some value >= 2^22.
+// Callers either clamp to [0, lim] with lim < 2^22 (then the result is exact for every input except NaN -> 0, which is also
+// what the reference gives) or treat every negative / huge result as "not interior" and recompute exactly out of line.
+GF_DEV void round_half_away_w(f2 a2, int& wa, int& wb) {
+    float sa, sb;
+    asm("{ .reg .b64 t, m, r; mov.b64 t, {%2, %3}; mov.b64 m, {%4, %4}; add.rz.f32x2 r, t, m; mov.b64 {%0, %1}, r; }"
+        : "=f"(sa), "=f"(sb) : "f"(fmaxf(a2.x, -4.0f)), "f"(fmaxf(a2.y, -4.0f)), "f"(8388608.0f));
+    wa = __float_as_int(sa) - 0x4affffff; wb = __float_as_int(sb) - 0x4affffff;
+}
+// max(min(round(t) as i32, lim), 0) for both lanes, 0 <= lim < 2^22
+GF_DEV void round_away_clamped_x2(f2 t, int lim, int& ra, int& rb) {
+    int wa, wb;
+    round_half_away_w(p2::mul(t, p2::bc(2.0f)), wa, wb);
+    ra = max(min(wa >> 1, lim), 0); rb = max(min(wb >> 1, lim), 0);
+}
+
+// everything that is not "valid pixel with an interior 8-bit bilinear footprint": background fill or the generic sampler,
+// from the exact coordinates
 template <class PIX>
-static __device__ __noinline__ void shade_cold(bool ok, int sx0, int sy0, const WarpArgs& A, uint8_t* __restrict__ out) {
+static __device__ __noinline__ void shade_cold(bool ok, float u, float v, const WarpArgs& A, uint8_t* __restrict__ out) {
     constexpr int C = PIX::COUNT;
     float pixel[C];
     if (ok) {
-        sample_generic<2, PIX>(sx0, sy0, A, pixel);
+        sample_generic<2, PIX>(round_away_i32(u * 32.0f), round_away_i32(v * 32.0f), A, pixel);
     } else {
         #pragma unroll
         for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
@@ -166,13 +184,14 @@ static __device__ __noinline__ void shade_cold(bool ok, int sx0, int sy0, const 
 }
 
 // sampling + conversion + store of one pixel, lean feature set (no fix_range, background mode 0, pixel_value_limit >= max).
-// u, v are never NaN here (finite on the hot path, sanitised by the cold one).
+// wu, wv: round_half_away_w of 64 * u, 64 * v (8-bit formats only).
 template <class PIX>
-GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __restrict__ out) {
+GF_DEV void shade_lean(bool ok, float u, float v, int wu, int wv, const WarpArgs& A, uint8_t* __restrict__ out) {
     constexpr int C = PIX::COUNT;
     if (PIX::SCALAR == SC_U8) {
-        const int sx0 = round_away_i32_nan_min(u * 32.0f), sy0 = round_away_i32_nan_min(v * 32.0f);
+        const int sx0 = wu >> 1, sy0 = wv >> 1;
         const int sx = sx0 >> 5, sy = sy0 >> 5;
+        // interior_span < 2^17 (host): negative and >= 2^22 results of the rounding shortcut can never pass
         const bool interior = ok & ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0]) & ((unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]);
         if (interior) {
             uint32_t N[C], s[C];
@@ -181,7 +200,7 @@ GF_DEV void shade_lean(bool ok, float u, float v, const WarpArgs& A, uint8_t* __
             for (int ch = 0; ch < C; ++ch) s[ch] = N[ch] >> 10;      // trunc(N / 1024); N / 1024 <= 255 <= pixel_value_limit
             PIX::store_scalars(out, true, s);
         } else {
-            shade_cold<PIX>(ok, sx0, sy0, A, out);
+            shade_cold<PIX>(ok, u, v, A, out);
         }
     } else {
         float pixel[C];
@@ -222,8 +241,8 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     const f2 px = bc(pxs);
     const f2 py = mk(opy_a + P.translation2d[1], opy_b + P.translation2d[1]);
     const int lim = A.rs_lim;
-    int sy_a = round_away_clamped(py.x, lim);                                                           // :465-469
-    int sy_b = round_away_clamped(py.y, lim);
+    int sy_a, sy_b;
+    round_away_clamped_x2(py, lim, sy_a, sy_b);                                                         // :465-469
     if (A.feat & F_RS) {                                                                                // :470-479
         const uint32_t mid = (uint32_t)P.matrix_count / 2u;
         f2 tu, tv; bool oa, ob, bad = false;
@@ -232,7 +251,8 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
             const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, mid, mid, A, 0);
             oa = (c.ok & 1) != 0; ob = (c.ok & 2) != 0; tv = mk(c.va, c.vb);
         }
-        const int ra = round_away_clamped(tv.x, lim), rb = round_away_clamped(tv.y, lim);
+        int ra, rb;
+        round_away_clamped_x2(tv, lim, ra, rb);
         sy_a = oa ? ra : sy_a; sy_b = ob ? rb : sy_b;
     }
     const uint32_t last = (uint32_t)(P.matrix_count - 1);
@@ -246,8 +266,13 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
         ok_a = (c.ok & 1) != 0; ok_b = (c.ok & 2) != 0; u = mk(c.ua, c.ub); v = mk(c.va, c.vb);
     }
 
-    if (wr_a) shade_lean<PIX>(ok_a, u.x, v.x, A, A.dst + off_a);                                        // :615-622
-    if (wr_b) shade_lean<PIX>(ok_b, u.y, v.y, A, A.dst + off_b);
+    int wu_a = 0, wu_b = 0, wv_a = 0, wv_b = 0;
+    if (PIX::SCALAR == SC_U8) {                          // (u * 32).round() for both pixels: 64 * u == 2 * (32 * u) exactly
+        round_half_away_w(mul(u, bc(64.0f)), wu_a, wu_b);
+        round_half_away_w(mul(v, bc(64.0f)), wv_a, wv_b);
+    }
+    if (wr_a) shade_lean<PIX>(ok_a, u.x, v.x, wu_a, wv_a, A, A.dst + off_a);                            // :615-622
+    if (wr_b) shade_lean<PIX>(ok_b, u.y, v.y, wu_b, wv_b, A, A.dst + off_b);
 }
 
 } // namespace gf

@@ -253,10 +253,10 @@ def _wild(kind):
     def hook(m):
         n = m.shape[0]
         if kind == "nan_row":    m[n // 3, :9] = np.nan
-        if kind == "inf":        m[n // 2, 2] = np.inf; m[n // 2 + 1, 8] = -np.inf
+        if kind == "inf":        m[n // 2, 2] = np.inf; m[(n // 2 + 1) % n, 8] = -np.inf
         if kind == "huge":       m[n // 4:n // 4 + 5, :9] *= np.float32(1e30)
         if kind == "tiny":       m[n // 4:n // 4 + 5, :9] *= np.float32(1e-30)
-        if kind == "denormal":   m[n // 5, :9] *= np.float32(1e-38); m[n // 5 + 1, 6:9] = np.float32(1e-44)
+        if kind == "denormal":   m[n // 5, :9] *= np.float32(1e-38); m[(n // 5 + 1) % n, 6:9] = np.float32(1e-44)
         if kind == "zero_rows":  m[::7, :9] = 0.0
         if kind == "zero_w":     m[n // 2:n // 2 + 9, 6:9] = 0.0
         if kind == "negzero":    m[::5, 0:2] = -0.0
