@@ -590,8 +590,105 @@ template <int C> GF_DEV void remap_colorrange(float (&px)[C], bool is_y) {      
 
 // sample_input_at at (u, v): picks the integer / interior / generic sampler.  Returns the clamped float sums
 // (what the reference's `sum` holds after :413-418).
+// Bicubic (I = 4) and Lanczos4 (I = 8) — cpu_undistort.rs:370-418 with offset 1 / 3 (:372-376).  One out-of-line body per pixel
+// format, shared by every lens model of a translation unit and reached from the general kernel through a uniform run-time branch
+// (the kernel family stays one instantiation per (lens, digital lens, pixel format) instead of three).
+template <int I, class PIX>
+GF_DEV void sample_input_at_hi(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+    const float offset = I == 4 ? 1.0f : 3.0f;
+    const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
+    const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
+    const int sx = sx0 >> 5, sy = sy0 >> 5;
+    const bool interior = (A.feat & F_SRC_VEC) != 0 && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
+    if (interior) sample_interior<I, PIX>(sx0, sy0, A, sum);
+    else          sample_generic<I, PIX>(sx0, sy0, A, sum);
+}
+// EWA (Elliptical Weighted Average) CubicBC resampling, I = 10..13 — cpu_undistort.rs:271-327 (helpers), :331-369 (loop).
+// jac = (du/dx, du/dy, dv/dx, dv/dy) by forward differences (:567-572).
+GF_DEV float bc2(float x, const gf_kernel_params& P) {                                          // :316-326
+    x = fabsf(x);
+    const float x2 = x * x;
+    if (x < 1.0f) return P.ewa_coeffs_p[0] + P.ewa_coeffs_p[1] * x + P.ewa_coeffs_p[2] * x2 + P.ewa_coeffs_p[3] * x2 * x;
+    if (x < 2.0f) return P.ewa_coeffs_q[0] + P.ewa_coeffs_q[1] * x + P.ewa_coeffs_q[2] * x2 + P.ewa_coeffs_q[3] * x2 * x;
+    return 0.0f;
+}
+template <class PIX>
+GF_DEV void sample_ewa(float uvx, float uvy, float4 jac, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+    const gf_kernel_params& P = A.p;
+    constexpr int C = PIX::COUNT;
+    // affine_bbox :272-277
+    const float tsx = 2.0f * rs_max(rs_max(fabsf(jac.x + jac.y), fabsf(jac.x - jac.y)), 1.0f);
+    const float tsy = 2.0f * rs_max(rs_max(fabsf(jac.z + jac.w), fabsf(jac.z - jac.w)), 1.0f);
+    const int b0 = as_i32(floorf(uvx - tsx)), b1 = as_i32(ceilf(uvx + tsx));
+    const int b2 = as_i32(floorf(uvy - tsy)), b3 = as_i32(ceilf(uvy + tsy));
+    // clamped_ellipse :279-315
+    const float f0 = fabsf(jac.x * jac.w - jac.y * jac.z);
+    const float f = rs_max(f0 * f0, 0.1f);
+    const float a = (jac.z * jac.z + jac.w * jac.w) / f;
+    const float b = -2.0f * (jac.x * jac.z + jac.y * jac.w) / f;
+    const float c = (jac.x * jac.x + jac.y * jac.y) / f;
+    const float vx = c - a, vy = -b;
+    const float lv = sqrtf(vx * vx + vy * vy);
+    const float v0 = lv > 0.01f ? vx / lv : 1.0f;
+    const float cc = sqrtf(rs_max(1.0f + v0, 0.0f) / 2.0f);
+    float s = sqrtf(rs_max(1.0f - v0, 0.0f) / 2.0f);
+    float a0 = a * cc * cc - b * cc * s + c * s * s;
+    float c0 = a * s * s + b * cc * s + c * cc * cc;
+    const float bt1 = b * (cc * cc - s * s);
+    const float bt2 = 2.0f * (a - c) * cc * s;
+    float b0v = bt1 + bt2;
+    const float b0v2 = bt1 - bt2;
+    if (fabsf(b0v) > fabsf(b0v2)) { s = -s; b0v = b0v2; }
+    a0 = rs_min(a0, 1.0f);
+    c0 = rs_min(c0, 1.0f);
+    const float sn = -s;
+    const float ea = a0 * cc * cc - b0v * cc * sn + c0 * sn * sn;
+    const float eb = 2.0f * a0 * cc * sn + b0v * cc * cc - b0v * sn * sn - 2.0f * c0 * cc * sn;
+    const float ec = a0 * sn * sn + b0v * cc * sn + c0 * cc * cc;
+
+    const int rx0 = A.src_rect[0], ry0 = A.src_rect[1], rx1 = A.src_rect[2], ry1 = A.src_rect[3];
+    const bool vec = (A.feat & F_SRC_VEC) != 0;
+    #pragma unroll
+    for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
+    float sum_div = 0.0f;
+    for (long long in_y = b2; in_y <= (long long)b3; ++in_y) {
+        const float in_fy = (float)(int)in_y - uvy;
+        const float in_fy2 = in_fy * eb;
+        const float in_fy3 = in_fy * in_fy * ec;
+        const bool row_in = in_y >= ry0 && in_y < ry1;
+        const uint8_t* row = A.src + in_y * (long long)P.stride;
+        for (long long in_x = b0; in_x <= (long long)b1; ++in_x) {
+            const float in_fx = (float)(int)in_x - uvx;
+            const float dr = in_fx * in_fx * ea + in_fx * in_fy2 + in_fy3;
+            const float k = bc2(sqrtf(dr), P);                         // cylindrical filtering
+            if (k == 0.0f) continue;
+            float px[C];
+            if (row_in && in_x >= rx0 && in_x < rx1) {
+                const uint8_t* tap = row + in_x * (long long)PIX::BYTES;
+                if (vec) PIX::load_vec(tap, px); else PIX::load_bytes(tap, px);
+            } else {
+                #pragma unroll
+                for (int ch = 0; ch < C; ++ch) px[ch] = A.bg[ch];
+            }
+            #pragma unroll
+            for (int ch = 0; ch < C; ++ch) sum[ch] += k * px[ch];
+            sum_div += k;
+        }
+    }
+    #pragma unroll
+    for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(sum[ch] / sum_div, P.pixel_value_limit);
+}
+
+template <class PIX>
+static __device__ __noinline__ void sample_high_order(float uvx, float uvy, float4 jac, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+    if (A.p.interpolation == GF_INTERP_BICUBIC)       sample_input_at_hi<4, PIX>(uvx, uvy, A, sum);
+    else if (A.p.interpolation == GF_INTERP_LANCZOS4) sample_input_at_hi<8, PIX>(uvx, uvy, A, sum);
+    else                                              sample_ewa<PIX>(uvx, uvy, jac, A, sum);
+}
+
 template <int I, class PIX, bool GEN>
-GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT], float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f)) {
+    if (GEN && I == 2 && A.p.interpolation != GF_INTERP_BILINEAR) { sample_high_order<PIX>(uvx, uvy, jac, A, sum); return; }
     const float offset = I == 2 ? 0.0f : (I == 4 ? 1.0f : 3.0f);
     const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
     const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
@@ -630,8 +727,25 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
     for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
     if (has<GEN>(feat, F_FILLBG)) { PIX::store(out, dvec, pixel); return; }                                              // :558-561
 
-    float u, v;
-    if (undistort_coord<LENS, DIGITAL, GEN>(opx, opy, A, u, v)) {                                                    // :565
+    // :565; for EWA (interpolation > 8, general kernel only) the forward-difference Jacobian of :567-572 comes from two more
+    // evaluations at (x + eps, y) and (x, y + eps), run through the same (single) inlined copy of undistort_coord
+    float u = 0.0f, v = 0.0f;
+    bool have_uv = false;
+    float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
+    const int npos = (GEN && P.interpolation > 8) ? 3 : 1;
+    #pragma unroll 1
+    for (int j = 0; j < npos; ++j) {
+        const float eps = 0.01f;
+        const float qx = j == 1 ? map_apply((float)x + eps, A.omap_x) : opx;
+        const float qy = j == 2 ? map_apply((float)y + eps, A.omap_y) : opy;
+        float tu, tv;
+        const bool ok = undistort_coord<LENS, DIGITAL, GEN>(qx, qy, A, tu, tv);
+        if (j == 0) { if (!ok) break; u = tu; v = tv; have_uv = true; continue; }
+        if (!ok) { tu = 0.0f; tv = 0.0f; }                                                                           // unwrap_or_default()
+        if (j == 1) { jac.x = (tu - u) / eps; jac.z = (tv - v) / eps; }
+        else        { jac.y = (tu - u) / eps; jac.w = (tv - v) / eps; }
+    }
+    if (have_uv) {
         if (has<GEN>(feat, F_BG3)) {                                                                             // :576-613
             const float width_f = A.width_f, height_f = A.height_f;
             const float widthf = width_f - 1.0f, heightf = height_f - 1.0f;
@@ -647,12 +761,12 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
             u   = map_apply(u,   A.smap_x); v   = map_apply(v,   A.smap_y);
             p2x = map_apply(p2x, A.smap_x); p2y = map_apply(p2y, A.smap_y);
             float c1[C], c2[C];
-            sample_input_at<I, PIX, GEN>(u, v, A, c1);
-            sample_input_at<I, PIX, GEN>(p2x, p2y, A, c2);
+            sample_input_at<I, PIX, GEN>(u, v, A, c1, jac);
+            sample_input_at<I, PIX, GEN>(p2x, p2y, A, c2, jac);          // (the reference notes jac should be adjusted for pt2; it is not)
             #pragma unroll
             for (int ch = 0; ch < C; ++ch) pixel[ch] = c1[ch] * alpha + c2[ch] * (1.0f - alpha);
         } else {
-            if (I == 2 && PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE)) {
+            if (I == 2 && PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && !(GEN && P.interpolation != GF_INTERP_BILINEAR)) {
                 // 8-bit bilinear interior: integer arithmetic, exact (see sample_u8_bilinear)
                 const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
                 const int sx = sx0 >> 5, sy = sy0 >> 5;
@@ -667,7 +781,7 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
                 }
                 sample_generic<I, PIX>(sx0, sy0, A, pixel);
             } else {
-                sample_input_at<I, PIX, GEN>(u, v, A, pixel);                                                    // :615
+                sample_input_at<I, PIX, GEN>(u, v, A, pixel, jac);                                               // :615
             }
         }
     }

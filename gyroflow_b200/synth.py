@@ -182,6 +182,14 @@ def base_kernel_params(width, height, out_width=None, out_height=None, pixel_typ
     p.output_width, p.output_height, p.output_stride = out_width, out_height, out_stride
     p.matrix_count = 1
     p.interpolation = abi.INTERP[interpolation]
+    if p.interpolation > 8:                          # EWA CubicBC coefficients, stabilization/mod.rs:279-295 (f32 arithmetic)
+        f = np.float32
+        b, c = {10: (0.2620145, 0.3689927), 11: (0.3782157, 0.3108921), 12: (0.3333333, 0.3333333), 13: (0.0, 0.5)}[p.interpolation]
+        b, c = f(b), f(c)
+        p.ewa_coeffs_p[:] = [float((f(6.0) - f(2.0) * b) / f(6.0)), 0.0, float((f(-18.0) + f(12.0) * b + f(6.0) * c) / f(6.0)),
+                             float((f(12.0) - f(9.0) * b - f(6.0) * c) / f(6.0))]
+        p.ewa_coeffs_q[:] = [float((f(8.0) * b + f(24.0) * c) / f(6.0)), float((f(-12.0) * b - f(48.0) * c) / f(6.0)),
+                             float((f(6.0) * b + f(30.0) * c) / f(6.0)), float((f(-1.0) * b - f(6.0) * c) / f(6.0))]
     p.background_mode = 0
     p.flags = abi.FLAG_HAS_DIGITAL_LENS if digital_lens else 0
     p.bytes_per_pixel = bpp

@@ -870,8 +870,83 @@ static inline const float* coeff_row(int I, uint32_t frac, float* tmp) {
     return &GF_COEFFS_LANCZOS4[frac << 3];
 }
 
-static v4 sample_input_at(int I, v2 uv, const uint8_t* input, size_t in_len, const gf_kernel_params* P, v4 bg, int count, int scalar, int* oob) {
+/* EWA (Elliptical Weighted Average) CubicBC helpers — cpu_undistort.rs:271-327.  jac = (dx/du, dx/dv, dy/du, dy/dv) as v4. */
+static v2 affine_bbox(v4 jac) {                                                                  /* :272-277 */
+    v2 r;
+    r.x = 2.0f * rs_max(rs_max(fabsf(jac.v[0] + jac.v[1]), fabsf(jac.v[0] - jac.v[1])), 1.0f);
+    r.y = 2.0f * rs_max(rs_max(fabsf(jac.v[2] + jac.v[3]), fabsf(jac.v[2] - jac.v[3])), 1.0f);
+    return r;
+}
+static void clamped_ellipse(v4 jac, float* oa, float* ob, float* oc) {                           /* :279-315 */
+    const float jx = jac.v[0], jy = jac.v[1], jz = jac.v[2], jw = jac.v[3];
+    float f0 = fabsf(jx * jw - jy * jz);
+    float f = rs_max(f0 * f0, 0.1f);
+    float a = (jz * jz + jw * jw) / f;
+    float b = -2.0f * (jx * jz + jy * jw) / f;
+    float c = (jx * jx + jy * jy) / f;
+    float vx = c - a, vy = -b;
+    float lv = sqrtf(vx * vx + vy * vy);                                                         /* nalgebra norm(): sqrt of the dot product */
+    float v0 = lv > 0.01f ? vx / lv : 1.0f;
+    float cc = sqrtf(rs_max(1.0f + v0, 0.0f) / 2.0f);
+    float s  = sqrtf(rs_max(1.0f - v0, 0.0f) / 2.0f);
+    float a0 = a * cc * cc - b * cc * s + c * s * s;
+    float c0 = a * s * s + b * cc * s + c * cc * cc;
+    float bt1 = b * (cc * cc - s * s);
+    float bt2 = 2.0f * (a - c) * cc * s;
+    float b0 = bt1 + bt2;
+    float b0v2 = bt1 - bt2;
+    if (fabsf(b0) > fabsf(b0v2)) { s = -s; b0 = b0v2; }
+    a0 = rs_min(a0, 1.0f);
+    c0 = rs_min(c0, 1.0f);
+    float sn = -s;
+    *oa = a0 * cc * cc - b0 * cc * sn + c0 * sn * sn;
+    *ob = 2.0f * a0 * cc * sn + b0 * cc * cc - b0 * sn * sn - 2.0f * c0 * cc * sn;
+    *oc = a0 * sn * sn + b0 * cc * sn + c0 * cc * cc;
+}
+static float bc2(float x, const gf_kernel_params* P) {                                           /* :316-326 */
+    x = fabsf(x);
+    float x2 = x * x;
+    if (x < 1.0f) return P->ewa_coeffs_p[0] + P->ewa_coeffs_p[1] * x + P->ewa_coeffs_p[2] * x2 + P->ewa_coeffs_p[3] * x2 * x;
+    if (x < 2.0f) return P->ewa_coeffs_q[0] + P->ewa_coeffs_q[1] * x + P->ewa_coeffs_q[2] * x2 + P->ewa_coeffs_q[3] * x2 * x;
+    return 0.0f;
+}
+
+static v4 sample_input_at(int I, v2 uv, v4 jac, const uint8_t* input, size_t in_len, const gf_kernel_params* P, v4 bg, int count, int scalar, int* oob) {
     v4 sum = {{0.0f, 0.0f, 0.0f, 0.0f}};
+    if (I > 8) {                                                                                  /* :331-369 */
+        v2 trans_size = affine_bbox(jac);
+        int32_t b0 = rs_f32_as_i32(floorf(uv.x - trans_size.x)), b1 = rs_f32_as_i32(ceilf(uv.x + trans_size.x));
+        int32_t b2 = rs_f32_as_i32(floorf(uv.y - trans_size.y)), b3 = rs_f32_as_i32(ceilf(uv.y + trans_size.y));
+        float sum_div = 0.0f;
+        int64_t src_index = (int64_t)(int32_t)((uint32_t)b2 * (uint32_t)P->stride);               /* i32 multiply, wrapping in release builds */
+        float ea, eb, ec;
+        clamped_ellipse(jac, &ea, &eb, &ec);
+        for (int64_t in_y = b2; in_y <= (int64_t)b3; ++in_y) {
+            float in_fy = (float)(int32_t)in_y - uv.y;
+            float in_fy2 = in_fy * eb;
+            float in_fy3 = in_fy * in_fy * ec;
+            for (int64_t in_x = b0; in_x <= (int64_t)b1; ++in_x) {
+                float in_fx = (float)(int32_t)in_x - uv.x;
+                float dr = in_fx * in_fx * ea + in_fx * in_fy2 + in_fy3;
+                float k = bc2(sqrtf(dr), P);
+                if (k == 0.0f) continue;
+                v4 pixel;
+                if (in_y >= P->source_rect[1] && in_y < P->source_rect[1] + P->source_rect[3] && in_x >= P->source_rect[0] && in_x < P->source_rect[0] + P->source_rect[2]) {
+                    int64_t off = src_index + (int64_t)P->bytes_per_pixel * in_x;
+                    if (off < 0 || (uint64_t)off + (uint64_t)P->bytes_per_pixel > in_len) { *oob = 1; pixel = bg; }
+                    else pixel = pix_to_float(input + off, count, scalar);
+                } else {
+                    pixel = bg;
+                }
+                for (int ch = 0; ch < 4; ++ch) sum.v[ch] += k * pixel.v[ch];
+                sum_div += k;
+            }
+            src_index += P->stride;
+        }
+        for (int ch = 0; ch < 4; ++ch) sum.v[ch] /= sum_div;
+        for (int ch = 0; ch < 4; ++ch) sum.v[ch] = rs_min(sum.v[ch], P->pixel_value_limit);
+        return sum;
+    }
     const float offset = (I == 2) ? 0.0f : (I == 4 ? 1.0f : 3.0f);
     float u = uv.x - offset, v = uv.y - offset;
     int32_t sx0 = rs_f32_as_i32(rs_round(u * 32.0f));
@@ -954,6 +1029,15 @@ static void process_row(job_t* J, size_t y) {
             v2 position = {(float)x, (float)y};
             v2 uv;
             if (undistort_coord(position, &J->W, out_c, out_f, &uv)) {                            /* :565 */
+                v4 jac = {{1.0f, 0.0f, 0.0f, 1.0f}};
+                if (J->I > 8) {                                                                    /* :567-572 */
+                    const float eps = 0.01f;
+                    v2 px = {position.x + eps, position.y}, py = {position.x, position.y + eps}, rx = {0.0f, 0.0f}, ry = {0.0f, 0.0f};
+                    if (!undistort_coord(px, &J->W, out_c, out_f, &rx)) { rx.x = 0.0f; rx.y = 0.0f; }    /* unwrap_or_default() */
+                    if (!undistort_coord(py, &J->W, out_c, out_f, &ry)) { ry.x = 0.0f; ry.y = 0.0f; }
+                    v2 xyx = {rx.x - uv.x, rx.y - uv.y}, xyy = {ry.x - uv.x, ry.y - uv.y};
+                    jac.v[0] = xyx.x / eps; jac.v[1] = xyy.x / eps; jac.v[2] = xyx.y / eps; jac.v[3] = xyy.y / eps;
+                }
                 float width_f = (float)P->width, height_f = (float)P->height;
                 if (P->background_mode == 3) {                                                     /* :576-613 */
                     float widthf = width_f - 1.0f, heightf = height_f - 1.0f;
@@ -978,14 +1062,14 @@ static void process_row(job_t* J, size_t y) {
                     float sy0 = (float)P->source_rect[1], sy1 = (float)(P->source_rect[1] + P->source_rect[3]);
                     uv.x  = map_coord(uv.x,  0.0f, frame_size.x, sx0, sx1); uv.y  = map_coord(uv.y,  0.0f, frame_size.y, sy0, sy1);
                     pt2.x = map_coord(pt2.x, 0.0f, frame_size.x, sx0, sx1); pt2.y = map_coord(pt2.y, 0.0f, frame_size.y, sy0, sy1);
-                    v4 c1 = sample_input_at(J->I, uv,  J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);
-                    v4 c2 = sample_input_at(J->I, pt2, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);
+                    v4 c1 = sample_input_at(J->I, uv,  jac, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);
+                    v4 c2 = sample_input_at(J->I, pt2, jac, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);
                     for (int ch = 0; ch < 4; ++ch) pixel.v[ch] = c1.v[ch] * alpha + c2.v[ch] * (1.0f - alpha);
                     if (fix_range) remap_colorrange(&pixel, is_y);
                     pix_from_float(pix_out, pixel, J->count, J->scalar);
                     continue;
                 }
-                pixel = sample_input_at(J->I, uv, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);   /* :615 */
+                pixel = sample_input_at(J->I, uv, jac, J->in, J->in_len, P, bg, J->count, J->scalar, &J->oob);   /* :615 */
             }
             if (fix_range) remap_colorrange(&pixel, is_y);                                         /* :619-621 */
             pix_from_float(pix_out, pixel, J->count, J->scalar);                                   /* :622 */
@@ -1037,7 +1121,7 @@ int gf_oracle_undistort_image(const uint8_t* in, size_t in_len, uint8_t* out, si
     if (P->output_stride <= 0 || P->stride <= 0) return GF_ERR_BAD_STRIDE;                      /* :534-537 */
     if (P->matrix_count < 1 || (size_t)P->matrix_count > matrix_rows) return GF_ERR_BAD_PARAMS; /* matrices[idx] would panic */
     const int I = P->interpolation;
-    if (!(I == 2 || I == 4 || I == 8)) return GF_ERR_UNSUPPORTED_COMBO;                         /* EWA (I > 8): not restated yet */
+    if (!(I == 2 || I == 4 || I == 8 || (I >= 10 && I <= 13))) return GF_ERR_UNSUPPORTED_COMBO;  /* Interpolation enum, stabilization/mod.rs:24-34 */
     if (distortion_model <= GF_LENS_NONE || distortion_model >= GF_LENS_COUNT) return GF_ERR_BAD_PARAMS;
     if (digital_lens < 0 || digital_lens >= GF_LENS_COUNT) return GF_ERR_BAD_PARAMS;
 

@@ -163,6 +163,30 @@ def test_ibis_and_mesh_on_u8():
     assert_bit_exact(dict(w=320, h=180, mesh=True, fpd=True, flags=abi.FLAG_FRAMEBUFFER_INVERTED))
 
 
+# ---- higher-order resamplers: bicubic, Lanczos4 (the default render setting), EWA CubicBC ------------------
+@pytest.mark.parametrize("interp", ["Bicubic", "Lanczos4"])
+def test_bicubic_and_lanczos4(interp):
+    assert_bit_exact(dict(w=640, h=360, interp=interp))
+    assert_bit_exact(dict(w=320, h=180, interp=interp, pix="Luma16", lens="sony"))
+    assert_bit_exact(dict(w=320, h=180, interp=interp, pix="RGBAf", lens="gopro", digital="gopro_warp"))
+    assert_bit_exact(dict(w=203, h=117, interp=interp, pix="RGB8", stride_pad=3, fov=2.5))              # zoomed out: taps cross the source edge
+    assert_bit_exact(dict(w=320, h=180, interp=interp, params=dict(background_mode=3, background_margin=0.1, background_margin_feather=0.1), fov=1.6))
+    assert_bit_exact(dict(w=320, h=180, interp=interp, in_size=(400, 260), in_rect=(40, 30, 320, 180), out_size=(352, 200), out_rect=(16, 10, 320, 180)))
+    assert_bit_exact(dict(w=320, h=180, interp=interp, pix="UV16", flags=abi.FLAG_FIX_COLOR_RANGE, params=dict(pixel_value_limit=60000.0)))
+
+
+@pytest.mark.parametrize("interp", ["EWA: RobidouxSharp", "EWA: Robidoux", "EWA: Mitchell", "EWA: Catmull-Rom"])
+def test_ewa_cubic_bc(interp):
+    assert_bit_exact(dict(w=320, h=180, interp=interp))
+    assert_bit_exact(dict(w=200, h=120, interp=interp, pix="Luma16", lens="opencv_standard", rs=False))
+    assert_bit_exact(dict(w=200, h=120, interp=interp, pix="RGBAf", fov=1.4, params=dict(background=[0.2, 0.4, 0.6, 1.0])))
+    assert_bit_exact(dict(w=200, h=120, interp=interp, ow=100, oh=60))                                   # 2x minification: wide ellipses
+
+
+def test_lanczos4_full_size_4k():
+    assert_bit_exact(dict(w=3840, h=2160, interp="Lanczos4"))
+
+
 # ---- buffer sources --------------------------------------------------------------------------------------
 def test_device_buffers_cuda_buffer_source():
     assert_bit_exact(dict(w=640, h=360), device_buffers=True)
