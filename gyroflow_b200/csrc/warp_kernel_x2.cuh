@@ -87,14 +87,11 @@ GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, 
                                   f2& ou, f2& ov, bool& oka, bool& okb, bool& bad) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
-    // scalar loads straight into the register pairs the packed ops read (wide loads would need a transposing MOV per entry)
-    const float* __restrict__ ma = A.matrices + (size_t)idx_a * GF_MATRIX_STRIDE;
-    const float* __restrict__ mb = A.matrices + (size_t)idx_b * GF_MATRIX_STRIDE;
-    #define GF_M2(i) mk(__ldg(ma + (i)), __ldg(mb + (i)))
-    const f2 _x = add(add(mul(px, GF_M2(0)), mul(py, GF_M2(1))), GF_M2(2));
-    const f2 _y = add(add(mul(px, GF_M2(3)), mul(py, GF_M2(4))), GF_M2(5));
-    const f2 _w = add(add(mul(px, GF_M2(6)), mul(py, GF_M2(7))), GF_M2(8));
-    #undef GF_M2
+    // wide loads + pair-building moves measured faster than 18 scalar loads straight into register pairs (9.55k vs 9.39k frames/s)
+    const MatRow9 ra = load_row9(A.matrices, idx_a), rb = load_row9(A.matrices, idx_b);
+    const f2 _x = add(add(mul(px, mk(ra.m01.x, rb.m01.x)), mul(py, mk(ra.m01.y, rb.m01.y))), mk(ra.m23.x, rb.m23.x));
+    const f2 _y = add(add(mul(px, mk(ra.m23.y, rb.m23.y)), mul(py, mk(ra.m45.x, rb.m45.x))), mk(ra.m45.y, rb.m45.y));
+    const f2 _w = add(add(mul(px, mk(ra.m67.x, rb.m67.x)), mul(py, mk(ra.m67.y, rb.m67.y))), mk(ra.m8, rb.m8));
     oka = _w.x > 0.0f; okb = _w.y > 0.0f;                                                              // :138
     if (!TRUSTED) {
         bad |= (oka & (!zero_or_in_window(_x.x) | !zero_or_in_window(_y.x) | row_has_ibis(A.matrices, idx_a))) |
