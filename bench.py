@@ -43,6 +43,7 @@ CONFIGS = {
             name="cfg4: 3840x2160 f32 plane (GBRAPF32), sony lens + IBIS rows + 9x9 mesh correction, rolling-shutter ON, bilinear"),
 }
 CFG = CONFIGS[2]
+INTERP = "Bilinear"          # BASELINE configs are bilinear; --interp measures the other resamplers (side measurement, not the headline)
 W, H = CFG["w"], CFG["h"]
 PIX, LENS = CFG["pix"], CFG["lens"]
 FRAMES_PER_STEP = 128
@@ -100,7 +101,8 @@ class ClockSampler:
 
 def base_params():
     from gyroflow_b200 import synth
-    return synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS, digital_lens=CFG.get("digital"), fov=1.05 if CFG.get("digital") else 1.0)
+    return synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS, digital_lens=CFG.get("digital"), fov=1.05 if CFG.get("digital") else 1.0,
+                                    interpolation=INTERP)
 
 
 def make_tables(n):
@@ -178,8 +180,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--interp", default="Bilinear", help="Bilinear (BASELINE), Bicubic, Lanczos4, 'EWA: Robidoux', ... (side measurement)")
     args = ap.parse_args()
     select_config(args.config)
+    global INTERP
+    INTERP = args.interp
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -318,7 +323,7 @@ def main():
         out = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frame_bytes_in": int(H * p.stride), "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
+            "config": {"workload": WORKLOAD if INTERP == "Bilinear" else WORKLOAD.replace("bilinear", INTERP), "frame_bytes_in": int(H * p.stride), "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
                        "l2_policy": "inputs larger than L2: %d-frame ring of %.1f MB inputs (%d MB) + %d distinct matrix tables" % (RING, H * p.stride / 1e6, RING * H * p.stride // 1000000, N_TIMESTAMPS),
                        "parallelism": "frame-sharded x%d, NCCL broadcast of tables only" % world},
             "clocks": clk, "gpu_launches": launches,

@@ -29,6 +29,7 @@ struct Slot {                 // one in-flight set of per-frame tables
     float* d_mat = nullptr;
     float* h_mesh = nullptr;  // pinned
     float* d_mesh = nullptr;
+    double* d_mesh64 = nullptr;   // the mesh widened to f64 once per frame, like cpu_undistort.rs:539
     cudaEvent_t done = nullptr;
 };
 constexpr int kSlots = 4;
@@ -46,6 +47,7 @@ struct gf_cuda_ctx {
     KernelFn fn_x2t = nullptr;    // same, tables validated: no per-pixel numerator / IBIS tests
     std::unordered_map<const void*, uint32_t> validated;   // device tables vouched for by gf_cuda_validate_tables_dev
     unsigned* d_vflags = nullptr;
+    unsigned long long aux_launches = 0;   // helper kernels (mesh widening, table scans): not counted by gf_cuda_launch_count
     unsigned long long x2_launches = 0;
     unsigned long long lean_launches = 0;
     cudaStream_t stream = nullptr;
@@ -163,6 +165,10 @@ uint32_t scan_tables_host(const float* m, size_t rows) {
         for (int i = 9; i < 14; ++i) if (!(p[i] == 0.0f)) f |= TBL_IBIS;
     }
     return f;
+}
+__global__ void widen_mesh_kernel(const float* __restrict__ m, double* __restrict__ o, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = (double)m[i];
 }
 __global__ void scan_tables_kernel(const float* __restrict__ m, size_t rows, unsigned* flags) {
     unsigned f = 0;
@@ -337,6 +343,7 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
             (e = cudaMalloc(&sl.d_mat, rows * GF_MATRIX_STRIDE * sizeof(float))) != cudaSuccess ||
             (e = cudaMallocHost(&sl.h_mesh, GF_MESH_MAX_LEN * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&sl.d_mesh, GF_MESH_MAX_LEN * sizeof(float))) != cudaSuccess ||
+            (e = cudaMalloc(&sl.d_mesh64, GF_MESH_MAX_LEN * sizeof(double))) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) {
             cuda_fail(ctx, e, "table staging allocation"); return bail(GF_ERR_CUDA);
         }
@@ -357,6 +364,7 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
         if (sl.d_mat) cudaFree(sl.d_mat);
         if (sl.h_mesh) cudaFreeHost(sl.h_mesh);
         if (sl.d_mesh) cudaFree(sl.d_mesh);
+        if (sl.d_mesh64) cudaFree(sl.d_mesh64);
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (ctx->d_src) cudaFree(ctx->d_src);
@@ -392,15 +400,18 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     memset(&A, 0, sizeof(A));
     A.p = *p;
     uint32_t table_flags = TBL_WILD;       // unknown device tables are not trusted until validated
+    const bool use_slot = !tables_on_device || mesh_len > 0;   // device tables still need a slot for the widened mesh
+    Slot& sl = ctx->slots[ctx->next_slot];
+    if (use_slot) {
+        ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+        CK(cudaEventSynchronize(sl.done));                     // the slot's previous frame has consumed its tables
+    }
     if (tables_on_device) {
         auto it = ctx->validated.find((const void*)matrices);
         if (it != ctx->validated.end()) table_flags = it->second;
         A.matrices = matrices;
         A.mesh = mesh_len ? mesh : nullptr;
     } else {
-        Slot& sl = ctx->slots[ctx->next_slot];
-        ctx->next_slot = (ctx->next_slot + 1) % kSlots;
-        CK(cudaEventSynchronize(sl.done));                     // the slot's previous frame has consumed its tables
         memcpy(sl.h_mat, matrices, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float));
         table_flags = scan_tables_host(sl.h_mat, (size_t)p->matrix_count);
         CK(cudaMemcpyAsync(sl.d_mat, sl.h_mat, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -413,6 +424,11 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         // recorded after the launch below
     }
     A.mesh_len = (int)mesh_len;
+    if (mesh_len) {                                            // cpu_undistort.rs:539 — `mesh_data.iter().map(|x| *x as f64)`, once per frame
+        widen_mesh_kernel<<<(unsigned)((mesh_len + 255) / 256), 256, 0, st>>>(A.mesh, sl.d_mesh64, (int)mesh_len);
+        CK(cudaGetLastError());
+        A.mesh64 = sl.d_mesh64; ctx->aux_launches++;
+    }
 
     const uint8_t* src = (const uint8_t*)in->ptr;
     uint8_t* dst = (uint8_t*)out->ptr;
@@ -452,10 +468,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     else         { ctx->fn<<<grid, block, 0, st>>>(A); }
     CK(cudaGetLastError());
     ctx->launches++;
-    if (!tables_on_device) {
-        Slot& used = ctx->slots[(ctx->next_slot + kSlots - 1) % kSlots];
-        CK(cudaEventRecord(used.done, st));
-    }
+    if (use_slot) CK(cudaEventRecord(sl.done, st));
     if (out->kind == GF_BUF_HOST) {                                                                                  // opencl.rs:413
         if (full_cover) CK(cudaMemcpy2DAsync(out->ptr, (size_t)p->output_stride, ctx->d_dst, (size_t)p->output_stride,
                                              (size_t)out->width * (size_t)bpp, (size_t)out->height, cudaMemcpyDeviceToHost, st));

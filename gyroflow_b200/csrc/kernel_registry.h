@@ -56,11 +56,11 @@ static KernelFn pick_interp(int interp, int lean) {
     if (lean == 3) return pick_x2<LENS, DIGITAL, PIX>(interp, true);
     switch (interp) {
     case GF_INTERP_BILINEAR: return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
-    // bicubic / Lanczos4: the general kernel with its run-time high-order sampler (sample_high_order in warp_kernel.cuh)
+    // bicubic / Lanczos4: the same scalar kernels with their run-time high-order sampler (sample_high_order in warp_kernel.cuh)
     // EWA CubicBC (Robidoux sharp / Robidoux / Mitchell / Catmull-Rom): same, coefficients in KernelParams::ewa_coeffs_{p,q}
     case GF_INTERP_BICUBIC: case GF_INTERP_LANCZOS4:
     case GF_INTERP_ROBIDOUX_SHARP: case GF_INTERP_ROBIDOUX: case GF_INTERP_MITCHELL: case GF_INTERP_CATMULL_ROM:
-        return lean ? nullptr : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
+        return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
     default: return nullptr;
     }
 }

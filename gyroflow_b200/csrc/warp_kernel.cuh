@@ -72,6 +72,7 @@ struct WarpArgs {
     uint8_t*       dst;
     const float*   matrices;        // device, rows x 14, 8-byte aligned
     const float*   mesh;            // device f32 (nullptr when mesh_len == 0)
+    const double*  mesh64;          // the same values widened to f64 by a helper kernel before the launch (cpu_undistort.rs:539)
     unsigned long long src_len, dst_len;
     int   mesh_len;
     int   out_rows;                 // ceil(dst_len / output_stride): rows the reference iterates (par_chunks_mut)
@@ -211,9 +212,70 @@ template <int COUNT_, int SCALAR_> struct Pix {
 // ------------------------------------------------------------------------------------------
 #define GF_MAX_GRID 9
 struct MeshView {
-    const float* __restrict__ m;
-    GF_DEV double operator[](uint32_t i) const { return (double)__ldg(m + i); }
+    const double* __restrict__ m;
+    GF_DEV double operator[](uint32_t i) const { return __ldg(m + i); }
 };
+
+// mu[] of the natural-spline solve (splines.rs:112-115) does not depend on the data: mu[0] = 0, mu[i] = 1 / (4 - mu[i-1]).
+// The same IEEE double operations, evaluated at compile time.
+namespace spline_mu {
+constexpr double M0 = 0.0, M1 = 1.0 / (4.0 - M0), M2 = 1.0 / (4.0 - M1), M3 = 1.0 / (4.0 - M2), M4 = 1.0 / (4.0 - M3),
+                 M5 = 1.0 / (4.0 - M4), M6 = 1.0 / (4.0 - M5), M7 = 1.0 / (4.0 - M6);
+}
+
+// BivariateSpline::interpolate for both maps (mesh_offset 0 and 1) of a grid with n_y == 9 rows — splines.rs:141-176.
+// Same operations in the same order as the general routine below, restricted to what the result depends on:
+// the tridiagonal forward sweep z[], the back-substitution c[] only down to the interval k that contains y, and b, d only at k
+// (the extrapolation branches use k = 0 and k = n - 2).  Fully unrolled, everything in registers, no divisions inside.
+static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, uint32_t n_x, double size_x, double size_y, double x, double y,
+                                                       double& out_x, double& out_y) {
+    using namespace spline_mu;
+    constexpr uint32_t n = 9, grid = GF_MAX_GRID, block = GF_MAX_GRID * 4;
+    uint32_t i = as_usize_small(((double)n_x - 1.0) * x / size_x);
+    if (i > n_x - 2) i = n_x - 2;
+    const double dx = x - size_x * (double)i / (double)(n_x - 1);
+    const double dx2 = dx * dx;
+    const double h = size_y / (double)(n - 1);
+    const double inv_h = 1.0 / h;
+    const double three_inv_h = 3.0 * inv_h;
+    const double h_over_3 = h / 3.0;
+    const double inv_3h = 1.0 / (3.0 * h);
+    const int mode = y <= 0.0 ? 0 : (y >= size_y ? 2 : 1);
+    uint32_t k = 0;
+    if (mode == 1) { k = as_usize_small(((double)n - 1.0) * y / size_y); if (k > n - 2) k = n - 2; }
+    else if (mode == 2) k = n - 2;
+    const double dy = y - size_y * (double)k / (double)(n - 1);
+    const double MU[8] = {M0, M1, M2, M3, M4, M5, M6, M7};
+    #pragma unroll 1
+    for (uint32_t mo = 0; mo < 2; ++mo) {
+        const uint32_t offs = 9 + n_x * n * 2 + mo * n * block + i;
+        double a[9];
+        #pragma unroll
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t rb = offs + j * block;
+            a[j] = mesh[rb] + mesh[rb + grid] * dx + mesh[rb + grid * 2] * dx2 + mesh[rb + grid * 3] * dx2 * dx;
+        }
+        double z[8];
+        z[0] = 0.0;
+        #pragma unroll
+        for (uint32_t q = 1; q + 1 < n; ++q) {
+            const double alpha = three_inv_h * (a[q + 1] - 2.0 * a[q] + a[q - 1]);
+            z[q] = (alpha * inv_h - z[q - 1]) * MU[q];
+        }
+        double cur = 0.0, nxt = 0.0, ak = a[n - 2], ak1 = a[n - 1];       // cur = c[q], nxt = c[q + 1]
+        #pragma unroll
+        for (int q = (int)n - 2; q >= 0; --q) {
+            if ((uint32_t)q >= k) { nxt = cur; cur = z[q] - MU[q] * cur; ak = a[q]; ak1 = a[q + 1]; }
+        }
+        const double bk = (ak1 - ak) * inv_h - h_over_3 * (nxt + 2.0 * cur);
+        const double dk = (nxt - cur) * inv_3h;
+        double r;
+        if (mode == 0)      r = ak + bk * y;                                                   // a[0] + b[0] * x
+        else if (mode == 2) r = ak1 + (bk + 2.0 * cur * h + 3.0 * dk * h * h) * (y - size_y);   // a[n-1] + slope * (x - size)
+        else                r = ak + bk * dy + cur * dy * dy + dk * dy * dy * dy;
+        if (mo == 0) out_x = r; else out_y = r;
+    }
+}
 
 static __device__ __noinline__ double mesh_bivariate(const MeshView mesh, uint32_t n_x, uint32_t n_y, double size_x, double size_y,
                                               uint32_t mesh_offset, double x, double y) {
@@ -326,7 +388,7 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
     ux = ux + P.c[0]; uy = uy + P.c[1];                                                                // :167
 
     if (has<GEN>(feat, F_MESH)) {
-        const MeshView mesh{A.mesh};
+        const MeshView mesh{A.mesh64};
         const bool inv = has<GEN>(feat, F_FB_INV);
         const double mesh0 = mesh[0];
         if (mesh0 > 10.0) {                                                                            // :169-185
@@ -337,8 +399,13 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
             uy = map_coord(uy, 0.0f, A.height_f, origin_y, origin_y + crop_h);
             const uint32_t n_x = as_usize_small(mesh[1]), n_y = as_usize_small(mesh[2]);
             const double sx = mesh[3], sy = mesh[4];
-            const double nx = mesh_bivariate(mesh, n_x, n_y, sx, sy, 0, (double)ux, (double)uy);
-            const double ny = mesh_bivariate(mesh, n_x, n_y, sx, sy, 1, (double)ux, (double)uy);
+            double nx, ny;
+            if (n_y == 9 && n_x >= 2 && n_x <= 9) {
+                mesh_interpolate9(mesh, n_x, sx, sy, (double)ux, (double)uy, nx, ny);
+            } else {
+                nx = mesh_bivariate(mesh, n_x, n_y, sx, sy, 0, (double)ux, (double)uy);
+                ny = mesh_bivariate(mesh, n_x, n_y, sx, sy, 1, (double)ux, (double)uy);
+            }
             ux = map_coord((float)nx, origin_x, origin_x + crop_w, 0.0f, A.width_f);
             uy = map_coord((float)ny, origin_y, origin_y + crop_h, 0.0f, A.height_f);
             if (inv) uy = A.height_f - uy;
@@ -591,7 +658,7 @@ template <int C> GF_DEV void remap_colorrange(float (&px)[C], bool is_y) {      
 // sample_input_at at (u, v): picks the integer / interior / generic sampler.  Returns the clamped float sums
 // (what the reference's `sum` holds after :413-418).
 // Bicubic (I = 4) and Lanczos4 (I = 8) — cpu_undistort.rs:370-418 with offset 1 / 3 (:372-376).  One out-of-line body per pixel
-// format, shared by every lens model of a translation unit and reached from the general kernel through a uniform run-time branch
+// format, shared by every lens model of a translation unit and reached from the scalar kernels through a uniform run-time branch
 // (the kernel family stays one instantiation per (lens, digital lens, pixel format) instead of three).
 template <int I, class PIX>
 GF_DEV void sample_input_at_hi(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
@@ -688,7 +755,7 @@ static __device__ __noinline__ void sample_high_order(float uvx, float uvy, floa
 
 template <int I, class PIX, bool GEN>
 GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT], float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f)) {
-    if (GEN && I == 2 && A.p.interpolation != GF_INTERP_BILINEAR) { sample_high_order<PIX>(uvx, uvy, jac, A, sum); return; }
+    if (I == 2 && A.p.interpolation != GF_INTERP_BILINEAR) { sample_high_order<PIX>(uvx, uvy, jac, A, sum); return; }
     const float offset = I == 2 ? 0.0f : (I == 4 ? 1.0f : 3.0f);
     const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
     const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
@@ -727,12 +794,12 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
     for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
     if (has<GEN>(feat, F_FILLBG)) { PIX::store(out, dvec, pixel); return; }                                              // :558-561
 
-    // :565; for EWA (interpolation > 8, general kernel only) the forward-difference Jacobian of :567-572 comes from two more
+    // :565; for EWA (interpolation > 8) the forward-difference Jacobian of :567-572 comes from two more
     // evaluations at (x + eps, y) and (x, y + eps), run through the same (single) inlined copy of undistort_coord
     float u = 0.0f, v = 0.0f;
     bool have_uv = false;
     float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
-    const int npos = (GEN && P.interpolation > 8) ? 3 : 1;
+    const int npos = P.interpolation > 8 ? 3 : 1;
     #pragma unroll 1
     for (int j = 0; j < npos; ++j) {
         const float eps = 0.01f;
@@ -766,7 +833,7 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
             #pragma unroll
             for (int ch = 0; ch < C; ++ch) pixel[ch] = c1[ch] * alpha + c2[ch] * (1.0f - alpha);
         } else {
-            if (I == 2 && PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && !(GEN && P.interpolation != GF_INTERP_BILINEAR)) {
+            if (I == 2 && PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && P.interpolation == GF_INTERP_BILINEAR) {
                 // 8-bit bilinear interior: integer arithmetic, exact (see sample_u8_bilinear)
                 const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
                 const int sx = sx0 >> 5, sy = sy0 >> 5;

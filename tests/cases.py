@@ -71,7 +71,7 @@ def build(case):
     p.matrix_count = m.shape[0]
     mesh = None
     if case.get("mesh"):
-        mesh = synth.synthetic_mesh(w, h, with_fpd=bool(case.get("fpd")))
+        mesh = synth.synthetic_mesh(w, h, n=case.get("mesh_n", 9), with_fpd=bool(case.get("fpd")))
     dst_init = np.full((obh, ostride), 0xA5, dtype=np.uint8)       # sentinel: untouched bytes must stay untouched
     return p, src, m, mesh, dst_init, pix, lens, digital
 

@@ -163,6 +163,15 @@ def test_ibis_and_mesh_on_u8():
     assert_bit_exact(dict(w=320, h=180, mesh=True, fpd=True, flags=abi.FLAG_FRAMEBUFFER_INVERTED))
 
 
+def test_mesh_spline_variants():
+    """Unrolled 9-row spline (both extrapolation branches via a zoomed-out view), smaller grids through the general routine."""
+    assert_bit_exact(dict(w=320, h=180, mesh=True, pix="RGBAf", lens="sony"))
+    assert_bit_exact(dict(w=320, h=180, mesh=True, fov=1.8, lens="sony"))
+    assert_bit_exact(dict(w=320, h=180, mesh=True, fpd=True, fov=0.7, pix="Luma16"))
+    assert_bit_exact(dict(w=320, h=180, mesh=True, mesh_n=7, lens="sony"))
+    assert_bit_exact(dict(w=320, h=180, mesh=True, mesh_n=5, fpd=True, ibis=True, lens="sony", pix="R32f"))
+
+
 # ---- higher-order resamplers (SURVEY f1): bicubic, Lanczos4 (the default render setting), EWA CubicBC ------------------
 @pytest.mark.parametrize("interp", ["Bicubic", "Lanczos4"])
 def test_bicubic_and_lanczos4(interp):
