@@ -43,6 +43,10 @@ CONFIGS = {
             name="cfg4: 3840x2160 f32 plane (GBRAPF32), sony lens + IBIS rows + 9x9 mesh correction, rolling-shutter ON, bilinear"),
 }
 CFG = CONFIGS[2]
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed `ncu --set full` captures
+# (ncu flushes the caches before the launch and the output stays in L2 after it, hence traffic < algorithmic bytes)
+NCU_TRAFFIC = {(2, "Bilinear"): 23118336 + 768512}
+NCU_TRAFFIC_SOURCE = "profiles/r01h_x2_rz_rounding_fisheye_rgba8_summary.txt"
 INTERP = "Bilinear"          # BASELINE configs are bilinear; --interp measures the other resamplers (side measurement, not the headline)
 W, H = CFG["w"], CFG["h"]
 PIX, LENS = CFG["pix"], CFG["lens"]
@@ -283,7 +287,9 @@ def main():
     mats_host = mats.cpu().numpy()
     itms = [g.FrameTransform(matrices=mats_host[i % N_TIMESTAMPS], kernel_params=p, mesh_data=mesh_np if mesh_np is not None else np.zeros(0, np.float32))
             for i in range(N_TIMESTAMPS)]
-    e2e_frames = 24 if args.no_e2e else 96
+    # an e2e step = the same FRAMES_PER_STEP frames as a device-resident step (--no-e2e: a token 24 frames)
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
+    e2e_frames = 24 if args.no_e2e else e2e_steps * FRAMES_PER_STEP
     for i in range(3): hctx[0].undistort_image(hb[0], itms[i % N_TIMESTAMPS])
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
@@ -302,8 +308,9 @@ def main():
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_fps = world * e2e_frames / float(te.item())
-    h2d = int(hin[0].numel() + rows * 56 + 368)
-    d2h = int(W * p.bytes_per_pixel * H)
+    h2d_frame = int(hin[0].numel() + rows * 56 + 368 + (mesh_np.size * 4 if mesh_np is not None else 0))    # frame + matrices + KernelParams (+ mesh)
+    d2h_frame = int(W * p.bytes_per_pixel * H)
+    h2d, d2h = h2d_frame * FRAMES_PER_STEP * world, d2h_frame * FRAMES_PER_STEP * world
 
     if rank == 0:
         peaks = {}
@@ -328,9 +335,11 @@ def main():
                        "parallelism": "frame-sharded x%d, NCCL broadcast of tables only" % world},
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_bytes_per_frame": h2d_frame, "d2h_bytes_per_frame": d2h_frame, "frames_per_step": FRAMES_PER_STEP * world, "steps": e2e_steps,
                     "sync_call_value": sync_fps * world,
                     "note": "pinned host frame + tables H2D, kernel, D2H per frame; value = %d-deep pipeline over gf_cuda_undistort_image_async, sync_call_value = strictly sequential gf_cuda_undistort_image; %d frames, wall clock" % (DEPTH, e2e_frames)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.config, INTERP)),
+                         "traffic_source": NCU_TRAFFIC_SOURCE if (args.config, INTERP) in NCU_TRAFFIC else None,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": launch_ms, "peak_source": peak_src,
                          "note": "kernel is FP32-issue bound in bit-exact (-fmad=false) mode; see DESIGN.md"},
             "cpu_baseline": cpu,

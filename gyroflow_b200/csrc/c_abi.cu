@@ -166,9 +166,31 @@ uint32_t scan_tables_host(const float* m, size_t rows) {
     }
     return f;
 }
-__global__ void widen_mesh_kernel(const float* __restrict__ m, double* __restrict__ o, int n) {
+// f32 mesh -> f64 once per frame (cpu_undistort.rs:539) + the per-frame constants of MeshAux, all on the device so that
+// device-resident meshes never touch the host.  o has room for GF_MESH_MAX_LEN doubles followed by one MeshAux.
+__device__ MapC make_map_dev(float in_min, float in_max, float out_min, float out_max) {
+    MapC m;
+    m.in_min = in_min; m.mul = out_max - out_min; m.div = in_max - in_min; m.rcp = 1.0f / m.div; m.add = out_min;
+    const float ad = fabsf(m.div);
+    m.fast_div = (isfinite(m.div) && ad >= 0x1p-40f && ad <= 0x1p40f) ? 1 : 0;
+    m.identity = 0;
+    return m;
+}
+__global__ void widen_mesh_kernel(const float* __restrict__ m, double* __restrict__ o, int n, float width_f, float height_f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = (double)m[i];
+    if (i == 0 && n >= 9) {
+        MeshAux* aux = reinterpret_cast<MeshAux*>(o + GF_MESH_MAX_LEN);
+        const double size_y = (double)m[4];
+        const double h = size_y / 8.0;
+        aux->h = h; aux->inv_h = 1.0 / h; aux->three_inv_h = 3.0 * aux->inv_h; aux->h_over_3 = h / 3.0; aux->inv_3h = 1.0 / (3.0 * h);
+        // `mesh[5] as f32` etc.: the f64 value is the widened f32, so the narrowing is the identity
+        const float origin_x = m[5], origin_y = m[6], crop_w = m[7], crop_h = m[8];
+        aux->to_crop_x  = make_map_dev(0.0f, width_f,  origin_x, origin_x + crop_w);
+        aux->to_crop_y  = make_map_dev(0.0f, height_f, origin_y, origin_y + crop_h);
+        aux->to_frame_x = make_map_dev(origin_x, origin_x + crop_w, 0.0f, width_f);
+        aux->to_frame_y = make_map_dev(origin_y, origin_y + crop_h, 0.0f, height_f);
+    }
 }
 __global__ void scan_tables_kernel(const float* __restrict__ m, size_t rows, unsigned* flags) {
     unsigned f = 0;
@@ -343,7 +365,7 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
             (e = cudaMalloc(&sl.d_mat, rows * GF_MATRIX_STRIDE * sizeof(float))) != cudaSuccess ||
             (e = cudaMallocHost(&sl.h_mesh, GF_MESH_MAX_LEN * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&sl.d_mesh, GF_MESH_MAX_LEN * sizeof(float))) != cudaSuccess ||
-            (e = cudaMalloc(&sl.d_mesh64, GF_MESH_MAX_LEN * sizeof(double))) != cudaSuccess ||
+            (e = cudaMalloc(&sl.d_mesh64, GF_MESH_MAX_LEN * sizeof(double) + sizeof(MeshAux))) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) {
             cuda_fail(ctx, e, "table staging allocation"); return bail(GF_ERR_CUDA);
         }
@@ -389,6 +411,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     if (!tables_on_device && matrix_rows > ctx->max_rows) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch matrices");
     if (mesh_len > GF_MESH_MAX_LEN) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch buf_mesh_data");
     if (mesh_len > 0 && !mesh) return fail(ctx, GF_ERR_BAD_PARAMS, "mesh is null");
+    if (mesh_len > 0 && mesh_len < 9) return fail(ctx, GF_ERR_BAD_PARAMS, "mesh shorter than its 9-value header (the reference would index out of bounds)");
     if (in->kind == GF_BUF_HOST && in->len > ctx->d_src_len)   return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch input");
     if (out->kind == GF_BUF_HOST && out->len > ctx->d_dst_len) return fail(ctx, GF_ERR_BUFFER_TOO_SMALL, "Buffer size mismatch output");
     if (tables_on_device && (reinterpret_cast<uintptr_t>(matrices) & 7u)) return fail(ctx, GF_ERR_BAD_PARAMS, "device matrices must be 8-byte aligned");
@@ -425,9 +448,9 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     }
     A.mesh_len = (int)mesh_len;
     if (mesh_len) {                                            // cpu_undistort.rs:539 — `mesh_data.iter().map(|x| *x as f64)`, once per frame
-        widen_mesh_kernel<<<(unsigned)((mesh_len + 255) / 256), 256, 0, st>>>(A.mesh, sl.d_mesh64, (int)mesh_len);
+        widen_mesh_kernel<<<(unsigned)((mesh_len + 255) / 256), 256, 0, st>>>(A.mesh, sl.d_mesh64, (int)mesh_len, (float)p->width, (float)p->height);
         CK(cudaGetLastError());
-        A.mesh64 = sl.d_mesh64; ctx->aux_launches++;
+        A.mesh64 = sl.d_mesh64; A.mesh_aux = reinterpret_cast<const MeshAux*>(sl.d_mesh64 + GF_MESH_MAX_LEN); ctx->aux_launches++;
     }
 
     const uint8_t* src = (const uint8_t*)in->ptr;

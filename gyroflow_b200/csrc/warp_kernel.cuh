@@ -73,6 +73,7 @@ struct WarpArgs {
     const float*   matrices;        // device, rows x 14, 8-byte aligned
     const float*   mesh;            // device f32 (nullptr when mesh_len == 0)
     const double*  mesh64;          // the same values widened to f64 by a helper kernel before the launch (cpu_undistort.rs:539)
+    const struct MeshAux* mesh_aux; // per-frame constants derived from the mesh header by the same helper kernel
     unsigned long long src_len, dst_len;
     int   mesh_len;
     int   out_rows;                 // ceil(dst_len / output_stride): rows the reference iterates (par_chunks_mut)
@@ -109,7 +110,9 @@ template <int COUNT_, int SCALAR_> struct Pix {
     static GF_DEV float scalar_to_float(uint32_t raw) {      // PixelType::to_float
         if (SCALAR == SC_F32) return __uint_as_float(raw);
         if (SCALAR == SC_F16) return __half2float(__ushort_as_half((unsigned short)raw));
-        return (float)raw;                                   // u8 / u16 widen exactly
+        // u8 / u16 widen exactly: 2^23 + raw has raw in its mantissa, the subtraction is exact.  (float)raw compiles to I2F on
+        // the quarter-rate XU pipe, which capped the 64-tap Lanczos4 sampler; this is one LOP3/PRMT + one FADD.
+        return __uint_as_float(0x4b000000u | raw) - 8388608.0f;
     }
     static GF_DEV uint32_t float_to_scalar(float v) {        // PixelType::from_float: Rust `as` casts
         if (SCALAR == SC_F32) return __float_as_uint(v);
@@ -223,11 +226,19 @@ constexpr double M0 = 0.0, M1 = 1.0 / (4.0 - M0), M2 = 1.0 / (4.0 - M1), M3 = 1.
                  M5 = 1.0 / (4.0 - M4), M6 = 1.0 / (4.0 - M5), M7 = 1.0 / (4.0 - M6);
 }
 
+// Per-frame constants of the mesh block, computed once (helper kernel in c_abi.cu) with the operations the reference repeats
+// per pixel: the spline step terms of splines.rs:101-105 for n = 9 and the four map_coord()s of cpu_undistort.rs:173-183 /
+// :194-211 (frame <-> mesh-crop coordinates) in the uniform-divisor form of div_uniform.
+struct MeshAux {
+    double h, inv_h, three_inv_h, h_over_3, inv_3h;      // size_y / 8, 1 / h, 3 * inv_h, h / 3, 1 / (3 h)
+    MapC to_crop_x, to_crop_y, to_frame_x, to_frame_y;
+};
+
 // BivariateSpline::interpolate for both maps (mesh_offset 0 and 1) of a grid with n_y == 9 rows — splines.rs:141-176.
 // Same operations in the same order as the general routine below, restricted to what the result depends on:
 // the tridiagonal forward sweep z[], the back-substitution c[] only down to the interval k that contains y, and b, d only at k
-// (the extrapolation branches use k = 0 and k = n - 2).  Fully unrolled, everything in registers, no divisions inside.
-static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, uint32_t n_x, double size_x, double size_y, double x, double y,
+// (the extrapolation branches use k = 0 and k = n - 2).  Fully unrolled, everything in registers.
+static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, const MeshAux& aux, uint32_t n_x, double size_x, double size_y, double x, double y,
                                                        double& out_x, double& out_y) {
     using namespace spline_mu;
     constexpr uint32_t n = 9, grid = GF_MAX_GRID, block = GF_MAX_GRID * 4;
@@ -235,11 +246,7 @@ static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, uint3
     if (i > n_x - 2) i = n_x - 2;
     const double dx = x - size_x * (double)i / (double)(n_x - 1);
     const double dx2 = dx * dx;
-    const double h = size_y / (double)(n - 1);
-    const double inv_h = 1.0 / h;
-    const double three_inv_h = 3.0 * inv_h;
-    const double h_over_3 = h / 3.0;
-    const double inv_3h = 1.0 / (3.0 * h);
+    const double h = aux.h, inv_h = aux.inv_h, three_inv_h = aux.three_inv_h, h_over_3 = aux.h_over_3, inv_3h = aux.inv_3h;
     const int mode = y <= 0.0 ? 0 : (y >= size_y ? 2 : 1);
     uint32_t k = 0;
     if (mode == 1) { k = as_usize_small(((double)n - 1.0) * y / size_y); if (k > n - 2) k = n - 2; }
@@ -262,10 +269,11 @@ static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, uint3
             const double alpha = three_inv_h * (a[q + 1] - 2.0 * a[q] + a[q - 1]);
             z[q] = (alpha * inv_h - z[q - 1]) * MU[q];
         }
-        double cur = 0.0, nxt = 0.0, ak = a[n - 2], ak1 = a[n - 1];       // cur = c[q], nxt = c[q + 1]
+        double cur = 0.0, nxt = 0.0, ak = a[0], ak1 = a[1];               // cur = c[q], nxt = c[q + 1]
         #pragma unroll
-        for (int q = (int)n - 2; q >= 0; --q) {
-            if ((uint32_t)q >= k) { nxt = cur; cur = z[q] - MU[q] * cur; ak = a[q]; ak1 = a[q + 1]; }
+        for (int q = (int)n - 2; q >= 0; --q) {                            // c[q] = z[q] - mu[q] * c[q+1], stop at q == k
+            nxt = cur; cur = z[q] - MU[q] * cur;
+            if ((uint32_t)q == k) { ak = a[q]; ak1 = a[q + 1]; break; }
         }
         const double bk = (ak1 - ak) * inv_h - h_over_3 * (nxt + 2.0 * cur);
         const double dk = (nxt - cur) * inv_3h;
@@ -389,37 +397,33 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
 
     if (has<GEN>(feat, F_MESH)) {
         const MeshView mesh{A.mesh64};
+        const MeshAux& aux = *A.mesh_aux;
         const bool inv = has<GEN>(feat, F_FB_INV);
         const double mesh0 = mesh[0];
         if (mesh0 > 10.0) {                                                                            // :169-185
-            const float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
-            const float crop_w = (float)mesh[7], crop_h = (float)mesh[8];
             if (inv) uy = A.height_f - uy;
-            ux = map_coord(ux, 0.0f, A.width_f,  origin_x, origin_x + crop_w);
-            uy = map_coord(uy, 0.0f, A.height_f, origin_y, origin_y + crop_h);
+            ux = map_apply(ux, aux.to_crop_x);                 // map_coord(ux, 0, width_f,  origin_x, origin_x + crop_w)
+            uy = map_apply(uy, aux.to_crop_y);                 // map_coord(uy, 0, height_f, origin_y, origin_y + crop_h)
             const uint32_t n_x = as_usize_small(mesh[1]), n_y = as_usize_small(mesh[2]);
             const double sx = mesh[3], sy = mesh[4];
             double nx, ny;
             if (n_y == 9 && n_x >= 2 && n_x <= 9) {
-                mesh_interpolate9(mesh, n_x, sx, sy, (double)ux, (double)uy, nx, ny);
+                mesh_interpolate9(mesh, aux, n_x, sx, sy, (double)ux, (double)uy, nx, ny);
             } else {
                 nx = mesh_bivariate(mesh, n_x, n_y, sx, sy, 0, (double)ux, (double)uy);
                 ny = mesh_bivariate(mesh, n_x, n_y, sx, sy, 1, (double)ux, (double)uy);
             }
-            ux = map_coord((float)nx, origin_x, origin_x + crop_w, 0.0f, A.width_f);
-            uy = map_coord((float)ny, origin_y, origin_y + crop_h, 0.0f, A.height_f);
+            ux = map_apply((float)nx, aux.to_frame_x);         // map_coord(nx, origin_x, origin_x + crop_w, 0, width_f)
+            uy = map_apply((float)ny, aux.to_frame_y);
             if (inv) uy = A.height_f - uy;
         }
         // FocalPlaneDistortion :188-214 (a missing FPD block means "none"; the reference would index out of bounds)
         const uint32_t o = as_usize_small(mesh0);
         if (mesh0 > 0.0 && o < (uint32_t)A.mesh_len && mesh[o] > 0.0) {
-            const double mesh_size_y = mesh[4];
-            const float origin_x = (float)mesh[5], origin_y = (float)mesh[6];
-            const float crop_w = (float)mesh[7], crop_h = (float)mesh[8];
-            const double stblz_grid = mesh_size_y / 8.0;
+            const double stblz_grid = aux.h;                                                           // mesh_size_y / 8.0
             if (inv) uy = A.height_f - uy;
-            ux = map_coord(ux, 0.0f, A.width_f,  origin_x, origin_x + crop_w);
-            uy = map_coord(uy, 0.0f, A.height_f, origin_y, origin_y + crop_h);
+            ux = map_apply(ux, aux.to_crop_x);
+            uy = map_apply(uy, aux.to_crop_y);
             const uint32_t idx2 = as_usize_small(fmin(fmax(floor((double)uy / stblz_grid), 0.0), 7.0));
             const double delta = (double)uy - stblz_grid * (double)idx2;
             ux -= (float)(mesh[o + 4 + idx2 * 2 + 0] * delta);
@@ -428,8 +432,8 @@ GF_DEV bool rotate_and_distort(float px, float py, uint32_t idx, const WarpArgs&
                 ux -= (float)(mesh[o + 4 + j * 2 + 0] * stblz_grid);
                 uy -= (float)(mesh[o + 4 + j * 2 + 1] * stblz_grid);
             }
-            ux = map_coord(ux, origin_x, origin_x + crop_w, 0.0f, A.width_f);
-            uy = map_coord(uy, origin_y, origin_y + crop_h, 0.0f, A.height_f);
+            ux = map_apply(ux, aux.to_frame_x);
+            uy = map_apply(uy, aux.to_frame_y);
             if (inv) uy = A.height_f - uy;
         }
     }
