@@ -41,8 +41,9 @@ static KernelFn pick_x2(int interp, bool trusted) {
             const char* e = getenv("GF_X2_MINB");            // tuning knob: resident blocks per SM the register budget targets
             const int minb = e ? atoi(e) : 6;
             if (trusted) {
-                if (minb == 4) return warp_kernel_x2<LENS, PIX, 4, true>;
                 if (minb == 5) return warp_kernel_x2<LENS, PIX, 5, true>;
+                if (minb == 7) return warp_kernel_x2<LENS, PIX, 7, true>;
+                if (minb == 8) return warp_kernel_x2<LENS, PIX, 8, true>;
                 return warp_kernel_x2<LENS, PIX, 6, true>;
             }
             return warp_kernel_x2<LENS, PIX, 6, false>;
