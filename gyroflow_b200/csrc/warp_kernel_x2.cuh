@@ -44,12 +44,20 @@ template <int M> struct Lens2 { static constexpr bool kHas = false; };
 // opencv_fisheye.rs:72-93 (k != 0: the lean kernel is only chosen when F_LENS_NOOP is clear; |k| bounded by the host)
 template <> struct Lens2<GF_LENS_OPENCV_FISHEYE> {
     static constexpr bool kHas = true;
-    static GF_DEV void distort(f2 x, f2 y, f2 z, bool va, bool vb, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
         using namespace p2;
-        bad |= (va & !in_window(z.x)) | (vb & !in_window(z.y));
         x = div_seq(x, z); y = div_seq(y, z);
         const f2 a = add(mul(x, x), mul(y, y));
-        bad |= (va & !in_window_r2(a.x)) | (vb & !in_window_r2(a.y));       // also excludes r == 0 and atanf's special ranges
+        // one window for the four quantities the fast sequences depend on: z (divisor; z <= 0 is the reference's `w > 0` test,
+        // :138, and goes to the exact code as well) and a = r^2 (square root, r != 0, atanf's ordinary range), both in [2^-56, 2^48).
+        if (TRUSTED) {      // no NaN can reach here (finite tame matrices and coordinates): fminf/fmaxf see every lane
+            const float lo = fminf(fminf(z.x, z.y), fminf(a.x, a.y)), hi = fmaxf(fmaxf(z.x, z.y), fmaxf(a.x, a.y));
+            bad |= !(lo >= 0x1p-56f) | !(hi < 0x1p48f);
+        } else {
+            bad |= !(z.x >= 0x1p-56f) | !(z.x < 0x1p48f) | !(z.y >= 0x1p-56f) | !(z.y < 0x1p48f) |
+                   !in_window_r2(a.x) | !in_window_r2(a.y);
+        }
         const f2 r = sqrt_seq(a);
         const f2 theta = atanf2_core(r, GF_ATAN_TAB);
         const f2 theta2 = mul(theta, theta), theta4 = mul(theta2, theta2), theta6 = mul(theta4, theta2), theta8 = mul(theta4, theta4);
@@ -81,10 +89,10 @@ GF_DEV bool row_has_ibis(const float* __restrict__ matrices, uint32_t idx) {    
              __float_as_uint(__ldg(m + 12)) | __float_as_uint(__ldg(m + 13))) << 1) != 0u;
 }
 
-// hot path: no branches.  Returns u, v for both lanes, validity (w > 0) per lane, and ORs `bad`.
+// hot path: no branches.  Returns u, v for both lanes and ORs `bad`; a lane with w <= 0 (the reference's None, :138) counts as
+// bad too — it is rare (rays more than 90 degrees off axis) and the exact code handles it.
 template <int LENS, bool TRUSTED>
-GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A,
-                                  f2& ou, f2& ov, bool& oka, bool& okb, bool& bad) {
+GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, f2& ou, f2& ov, bool& bad) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
     // wide loads + pair-building moves measured faster than 18 scalar loads straight into register pairs (9.55k vs 9.39k frames/s)
@@ -92,43 +100,47 @@ GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, 
     const f2 _x = add(add(mul(px, mk(ra.m01.x, rb.m01.x)), mul(py, mk(ra.m01.y, rb.m01.y))), mk(ra.m23.x, rb.m23.x));
     const f2 _y = add(add(mul(px, mk(ra.m23.y, rb.m23.y)), mul(py, mk(ra.m45.x, rb.m45.x))), mk(ra.m45.y, rb.m45.y));
     const f2 _w = add(add(mul(px, mk(ra.m67.x, rb.m67.x)), mul(py, mk(ra.m67.y, rb.m67.y))), mk(ra.m8, rb.m8));
-    oka = _w.x > 0.0f; okb = _w.y > 0.0f;                                                              // :138
     if (!TRUSTED) {
-        bad |= (oka & (!zero_or_in_window(_x.x) | !zero_or_in_window(_y.x) | row_has_ibis(A.matrices, idx_a))) |
-               (okb & (!zero_or_in_window(_x.y) | !zero_or_in_window(_y.y) | row_has_ibis(A.matrices, idx_b)));
+        bad |= !zero_or_in_window(_x.x) | !zero_or_in_window(_y.x) | row_has_ibis(A.matrices, idx_a) |
+               !zero_or_in_window(_x.y) | !zero_or_in_window(_y.y) | row_has_ibis(A.matrices, idx_b);
     }
     f2 ux, uy;
-    Lens2<LENS>::distort(_x, _y, _w, oka, okb, P, ux, uy, bad);                                        // :154
+    Lens2<LENS>::template distort<TRUSTED>(_x, _y, _w, P, ux, uy, bad);                                // :154
     ux = mul(ux, bc(P.f[0])); uy = mul(uy, bc(P.f[1]));                                                // :155
     ou = add(ux, bc(P.c[0])); ov = add(uy, bc(P.c[1]));                                                // :167 (no IBIS rows on this path)
 }
 
 // cold path: the scalar kernel's exact code for both pixels of the pair, one call site per pass.
-struct PairUV { float ua, va, ub, vb; int ok; };
+struct PairUV { float ua, va, ub, vb; int ok; };      // ok: bit 0/1 = lane a/b is Some(..); bit 2/3 = its coordinates are outside the
+                                                       // domain of the hot path's rounding shortcut (|u| or |v| >= 2^16, or NaN)
+GF_DEV bool outside_shortcut(float u, float v) { return !(fabsf(u) < 0x1p16f) | !(fabsf(v) < 0x1p16f); }
 template <int LENS>
 static __device__ __noinline__ PairUV rotate_and_distort_cold(float px, float pya, float pyb, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, int apply_smap) {
     PairUV o; o.ua = o.va = o.ub = o.vb = 0.0f; o.ok = 0;
     float cu, cv;
     if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pya, idx_a, A, cu, cv)) {
         if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
-        o.ua = cu; o.va = cv; o.ok |= 1;
+        o.ua = cu; o.va = cv; o.ok |= 1 | (outside_shortcut(cu, cv) ? 4 : 0);
     }
     if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pyb, idx_b, A, cu, cv)) {
         if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
-        o.ub = cu; o.vb = cv; o.ok |= 2;
+        o.ub = cu; o.vb = cv; o.ok |= 2 | (outside_shortcut(cu, cv) ? 8 : 0);
     }
     return o;
 }
 
-// map_coord with a uniform divisor on a pair (see div_uniform in warp_kernel.cuh); `bad` if a numerator leaves the window
-GF_DEV f2 map_apply_x2(f2 x, const MapC& m, bool va, bool vb, bool& bad) {
+// map_coord with a uniform divisor on a pair (see div_uniform in warp_kernel.cuh).  The two-step division is exact for a numerator
+// that is +-0 or has 2^-80 < |a| < 2^60.  The host guarantees in_min == 0, 2^-40 <= |mul| and |c| >= 2^-10 (so a non-zero x is at
+// least 2^-34 in magnitude and |a| >= 2^-74), and div <= 2^20 (so |a| >= 2^60 would give |result| >= 2^39): testing the RESULT
+// against 2^16 therefore covers the numerator window, catches NaN/Inf, and bounds what the rounding shortcut has to handle.
+GF_DEV f2 map_apply_x2(f2 x, const MapC& m, bool& bad) {
     using namespace p2;
     const f2 a = mul(sub(x, bc(m.in_min)), bc(m.mul));
-    const float a0 = fabsf(a.x), a1 = fabsf(a.y);
-    bad |= (va & !((a0 < 0x1p60f) & (a0 > 0x1p-80f))) | (vb & !((a1 < 0x1p60f) & (a1 > 0x1p-80f)));
     const f2 q0 = mul(a, bc(m.rcp));
     const f2 r0 = fma(bc(-m.div), q0, a);
-    return add(fma(r0, bc(m.rcp), q0), bc(m.add));
+    const f2 r = add(fma(r0, bc(m.rcp), q0), bc(m.add));
+    bad |= !(fabsf(r.x) < 0x1p16f) | !(fabsf(r.y) < 0x1p16f);
+    return r;
 }
 // map_coord of a pixel index; the host only selects this kernel when the map is the identity or has
 // mul, div > 0 of moderate size (then (x - in_min) * mul is +0 or inside the window of the exact two-step division)
@@ -156,10 +168,11 @@ GF_DEV int round_away_i32(float t) {
 // whenever the exact result is < 0 (it may also be -1 where the exact result is 0);  t >= 2^22 (or +inf): some value >= 2^22.
 // Callers either clamp to [0, lim] with lim < 2^22 (then the result is exact for every input except NaN -> 0, which is also
 // what the reference gives) or treat every negative / huge result as "not interior" and recompute exactly out of line.
+template <bool BOUNDED = false>     // BOUNDED: the caller guarantees |a2| < 2^23 (no NaN), the max() is not needed
 GF_DEV void round_half_away_w(f2 a2, int& wa, int& wb) {
     float sa, sb;
     asm("{ .reg .b64 t, m, r; mov.b64 t, {%2, %3}; mov.b64 m, {%4, %4}; add.rz.f32x2 r, t, m; mov.b64 {%0, %1}, r; }"
-        : "=f"(sa), "=f"(sb) : "f"(fmaxf(a2.x, -4.0f)), "f"(fmaxf(a2.y, -4.0f)), "f"(8388608.0f));
+        : "=f"(sa), "=f"(sb) : "f"(BOUNDED ? a2.x : fmaxf(a2.x, -4.0f)), "f"(BOUNDED ? a2.y : fmaxf(a2.y, -4.0f)), "f"(8388608.0f));
     wa = __float_as_int(sa) - 0x4affffff; wb = __float_as_int(sb) - 0x4affffff;
 }
 // max(min(round(t) as i32, lim), 0) for both lanes, 0 <= lim < 2^22
@@ -187,13 +200,13 @@ static __device__ __noinline__ void shade_cold(bool ok, float u, float v, const 
 // sampling + conversion + store of one pixel, lean feature set (no fix_range, background mode 0, pixel_value_limit >= max).
 // wu, wv: round_half_away_w of 64 * u, 64 * v (8-bit formats only).
 template <class PIX>
-GF_DEV void shade_lean(bool ok, float u, float v, int wu, int wv, const WarpArgs& A, uint8_t* __restrict__ out) {
+GF_DEV void shade_lean(bool ok, bool far, float u, float v, int wu, int wv, const WarpArgs& A, uint8_t* __restrict__ out) {
     constexpr int C = PIX::COUNT;
     if (PIX::SCALAR == SC_U8) {
         const int sx0 = wu >> 1, sy0 = wv >> 1;
         const int sx = sx0 >> 5, sy = sy0 >> 5;
         // interior_span < 2^17 (host): negative and >= 2^22 results of the rounding shortcut can never pass
-        const bool interior = ok & ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0]) & ((unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]);
+        const bool interior = ok & !far & ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0]) & ((unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]);
         if (interior) {
             uint32_t N[C], s[C];
             sample_u8_bilinear<PIX>(sx0, sy0, A, N);
@@ -246,8 +259,8 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     round_away_clamped_x2(py, lim, sy_a, sy_b);                                                         // :465-469
     if (A.feat & F_RS) {                                                                                // :470-479
         const uint32_t mid = (uint32_t)P.matrix_count / 2u;
-        f2 tu, tv; bool oa, ob, bad = false;
-        rotate_and_distort_x2<LENS, TRUSTED>(px, py, mid, mid, A, tu, tv, oa, ob, bad);
+        f2 tu, tv; bool oa = true, ob = true, bad = false;
+        rotate_and_distort_x2<LENS, TRUSTED>(px, py, mid, mid, A, tu, tv, bad);
         if (bad) {                                       // cold: exact scalar code for both pixels
             const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, mid, mid, A, 0);
             oa = (c.ok & 1) != 0; ob = (c.ok & 2) != 0; tv = mk(c.va, c.vb);
@@ -258,22 +271,25 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     }
     const uint32_t last = (uint32_t)(P.matrix_count - 1);
     const uint32_t idx_a = min((uint32_t)sy_a, last), idx_b = min((uint32_t)sy_b, last);               // :482
-    f2 u, v; bool ok_a, ok_b, bad = false;
-    rotate_and_distort_x2<LENS, TRUSTED>(px, py, idx_a, idx_b, A, u, v, ok_a, ok_b, bad);               // :483
-    u = map_apply_x2(u, A.smap_x, ok_a, ok_b, bad);                                                     // :510-515
-    v = map_apply_x2(v, A.smap_y, ok_a, ok_b, bad);
+    f2 u, v; bool ok_a = true, ok_b = true, far_a = false, far_b = false, bad = false;
+    rotate_and_distort_x2<LENS, TRUSTED>(px, py, idx_a, idx_b, A, u, v, bad);                           // :483
+    u = map_apply_x2(u, A.smap_x, bad);                                                                 // :510-515
+    v = map_apply_x2(v, A.smap_y, bad);
     if (bad) {
         const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, idx_a, idx_b, A, 1);
-        ok_a = (c.ok & 1) != 0; ok_b = (c.ok & 2) != 0; u = mk(c.ua, c.ub); v = mk(c.va, c.vb);
+        ok_a = (c.ok & 1) != 0; ok_b = (c.ok & 2) != 0; far_a = (c.ok & 4) != 0; far_b = (c.ok & 8) != 0;
+        u = mk(c.ua, c.ub); v = mk(c.va, c.vb);
     }
 
     int wu_a = 0, wu_b = 0, wv_a = 0, wv_b = 0;
-    if (PIX::SCALAR == SC_U8) {                          // (u * 32).round() for both pixels: 64 * u == 2 * (32 * u) exactly
-        round_half_away_w(mul(u, bc(64.0f)), wu_a, wu_b);
-        round_half_away_w(mul(v, bc(64.0f)), wv_a, wv_b);
+    if (PIX::SCALAR == SC_U8) {                          // (u * 32).round() for both pixels: 64 * u == 2 * (32 * u) exactly.
+        // |u|, |v| < 2^16 here unless far_* is set (then the result is not used), so the unguarded form of the shortcut applies;
+        // a garbage value for a far lane is harmless because `interior` below is false for it
+        round_half_away_w<true>(mul(u, bc(64.0f)), wu_a, wu_b);
+        round_half_away_w<true>(mul(v, bc(64.0f)), wv_a, wv_b);
     }
-    if (wr_a) shade_lean<PIX>(ok_a, u.x, v.x, wu_a, wv_a, A, A.dst + off_a);                            // :615-622
-    if (wr_b) shade_lean<PIX>(ok_b, u.y, v.y, wu_b, wv_b, A, A.dst + off_b);
+    if (wr_a) shade_lean<PIX>(ok_a, far_a, u.x, v.x, wu_a, wv_a, A, A.dst + off_a);                     // :615-622
+    if (wr_b) shade_lean<PIX>(ok_b, far_b, u.y, v.y, wu_b, wv_b, A, A.dst + off_b);
 }
 
 } // namespace gf
