@@ -12,6 +12,7 @@
 #pragma once
 #include "lens_models.cuh"
 #include "gf_coeffs_tables.h"
+#include "f32x2.cuh"
 #include <cuda_fp16.h>
 
 namespace gf {
@@ -145,6 +146,25 @@ template <int COUNT_, int SCALAR_> struct Pix {
             const uint32_t q[4] = {w.x, w.y, w.z, w.w};
             #pragma unroll
             for (int i = 0; i < COUNT; ++i) r[i] = q[i & 3];
+        }
+    }
+    // aligned pixel -> COUNT "magic" floats 2^23 + raw (integer formats only): the raw value sits in the mantissa, so the
+    // caller's exact `- 2^23` yields PixelType::to_float.  One PRMT per channel straight from the loaded word.
+    static GF_DEV void load_magic(const uint8_t* __restrict__ p, float (&m)[COUNT]) {
+        if (SCALAR == SC_U8 && POW2) {
+            const uint32_t w = BYTES == 1 ? (uint32_t)__ldg(p) : (BYTES == 2 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) : __ldg(reinterpret_cast<const unsigned int*>(p)));
+            #pragma unroll
+            for (int i = 0; i < COUNT; ++i) m[i] = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7540u + i));          // bytes: w[i], 00, 00, 4b
+        } else if (SCALAR == SC_U16 && POW2) {
+            uint32_t w[2] = {0u, 0u};
+            if (BYTES == 2) w[0] = __ldg(reinterpret_cast<const unsigned short*>(p));
+            else if (BYTES == 4) w[0] = __ldg(reinterpret_cast<const unsigned int*>(p));
+            else { const uint2 q = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = q.x; w[1] = q.y; }
+            #pragma unroll
+            for (int i = 0; i < COUNT; ++i) m[i] = __uint_as_float(__byte_perm(w[i >> 1], 0x4b000000u, (i & 1) ? 0x7432u : 0x7410u));   // w.h[i], 00, 4b
+        } else {
+            #pragma unroll
+            for (int i = 0; i < COUNT; ++i) m[i] = __uint_as_float(0x4b000000u | load_scalar(p + i * SBYTES));
         }
     }
     static GF_DEV void load_vec(const uint8_t* __restrict__ p, float (&v)[COUNT]) {
@@ -598,27 +618,88 @@ GF_DEV void sample_interior(int sx0, int sy0, const WarpArgs& A, float (&sum)[PI
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;
     const int sx = sx0 >> 5, sy = sy0 >> 5;
-    float cx[I], cy[I];
-    coeff_row<I>((uint32_t)sx0 & 31u, cx);
-    coeff_row<I>((uint32_t)sy0 & 31u, cy);
     const uint8_t* row = A.src + ((long long)sy * (long long)P.stride + (long long)sx * (long long)PIX::BYTES);
-    #pragma unroll
-    for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
-    #pragma unroll
-    for (int yp = 0; yp < I; ++yp) {
-        float xsum[C];
+    if (I == 2) {
+        float cx[I], cy[I];
+        coeff_row<I>((uint32_t)sx0 & 31u, cx);
+        coeff_row<I>((uint32_t)sy0 & 31u, cy);
         #pragma unroll
-        for (int ch = 0; ch < C; ++ch) xsum[ch] = 0.0f;
+        for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
         #pragma unroll
-        for (int xp = 0; xp < I; ++xp) {
-            float px[C];
-            PIX::load_vec(row + xp * PIX::BYTES, px);
+        for (int yp = 0; yp < I; ++yp) {
+            float xsum[C];
             #pragma unroll
-            for (int ch = 0; ch < C; ++ch) xsum[ch] += px[ch] * cx[xp];
+            for (int ch = 0; ch < C; ++ch) xsum[ch] = 0.0f;
+            #pragma unroll
+            for (int xp = 0; xp < I; ++xp) {
+                float px[C];
+                PIX::load_vec(row + xp * PIX::BYTES, px);
+                #pragma unroll
+                for (int ch = 0; ch < C; ++ch) xsum[ch] += px[ch] * cx[xp];
+            }
+            #pragma unroll
+            for (int ch = 0; ch < C; ++ch) sum[ch] += xsum[ch] * cy[yp];
+            row += P.stride;
         }
+    } else {
+        // 16 / 64 taps.  Same operations in the same order (xsum += px * cx[xp] along a row, sum += xsum * cy[yp] down the rows);
+        // the schedule differs: rows are a rolled loop (the fully unrolled 64-tap body stalled on instruction fetch) with cy[yp]
+        // read from the table, integer taps are widened by PRMT + exact subtraction, and with an even channel count the
+        // multiply/add stream runs on register pairs (FADD2 / FFMA2), halving its issue slots.
+        constexpr bool INT_FMT = PIX::SCALAR == SC_U8 || PIX::SCALAR == SC_U16;
+        constexpr bool PAIRS = (C % 2) == 0;
+        constexpr int NP = PAIRS ? C / 2 : 1;
+        float cx[I];
+        coeff_row<I>((uint32_t)sx0 & 31u, cx);
+        const float* __restrict__ cyp = (I == 4 ? GF_COEFFS_BICUBIC_DEV : GF_COEFFS_LANCZOS4_DEV) + (((uint32_t)sy0 & 31u) * I);
+        float2 s2[NP];
         #pragma unroll
-        for (int ch = 0; ch < C; ++ch) sum[ch] += xsum[ch] * cy[yp];
-        row += P.stride;
+        for (int k = 0; k < NP; ++k) s2[k] = make_float2(0.0f, 0.0f);
+        #pragma unroll
+        for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
+        #pragma unroll 1
+        for (int yp = 0; yp < I; ++yp) {
+            const float cy = __ldg(cyp + yp);
+            if (PAIRS) {
+                float2 x2[NP];
+                #pragma unroll
+                for (int k = 0; k < NP; ++k) x2[k] = make_float2(0.0f, 0.0f);
+                #pragma unroll
+                for (int xp = 0; xp < I; ++xp) {
+                    float v[C];
+                    if (INT_FMT) PIX::load_magic(row + xp * PIX::BYTES, v); else PIX::load_vec(row + xp * PIX::BYTES, v);
+                    #pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        float2 px = make_float2(v[2 * k], v[2 * k + 1]);
+                        if (INT_FMT) px = __fadd2_rn(px, make_float2(-8388608.0f, -8388608.0f));
+                        x2[k] = p2::add(x2[k], p2::mul(px, p2::bc(cx[xp])));
+                    }
+                }
+                #pragma unroll
+                for (int k = 0; k < NP; ++k) s2[k] = p2::add(s2[k], p2::mul(x2[k], p2::bc(cy)));
+            } else {
+                float xsum[C];
+                #pragma unroll
+                for (int ch = 0; ch < C; ++ch) xsum[ch] = 0.0f;
+                #pragma unroll
+                for (int xp = 0; xp < I; ++xp) {
+                    float v[C];
+                    if (INT_FMT) PIX::load_magic(row + xp * PIX::BYTES, v); else PIX::load_vec(row + xp * PIX::BYTES, v);
+                    #pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        const float px = INT_FMT ? v[ch] - 8388608.0f : v[ch];
+                        xsum[ch] += px * cx[xp];
+                    }
+                }
+                #pragma unroll
+                for (int ch = 0; ch < C; ++ch) sum[ch] += xsum[ch] * cy;
+            }
+            row += P.stride;
+        }
+        if (PAIRS) {
+            #pragma unroll
+            for (int k = 0; k < NP; ++k) { sum[2 * k] = s2[k].x; sum[2 * k + 1] = s2[k].y; }
+        }
     }
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(sum[ch], P.pixel_value_limit);

@@ -17,7 +17,6 @@
 // Behavioural source: src/core/stabilization/cpu_undistort.rs:133-228, :421-517, :543-625 (as warp_kernel.cuh).
 #pragma once
 #include "warp_kernel.cuh"
-#include "f32x2.cuh"
 
 namespace gf {
 
