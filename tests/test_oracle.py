@@ -107,3 +107,22 @@ def test_golden_crcs():
         rc, p, src, dst = run_oracle(case)
         assert rc == 0, name
         assert zlib.crc32(dst.tobytes()) == want[name], name
+
+
+def test_independent_numpy_restatement_agrees():
+    """A second restatement of the north-star path (fisheye + rolling shutter + bilinear on 8-bit pixels), written separately in
+    numpy.float32 scalars (tests/np_restatement.py), produces the same bytes as the C oracle — incl. a zoomed-out view with
+    invalid / out-of-frame pixels, a single-matrix frame and a chroma-like plane with source/output rects."""
+    import warnings
+    from tests import cases, np_restatement
+    for c in (dict(w=160, h=90), dict(w=64, h=36, fov=2.2, ts=1700.0), dict(w=48, h=30, pix="Luma8", rs=False),
+              dict(w=60, h=34, pix="UV8", in_size=(80, 50), in_rect=(10, 8, 60, 34), out_size=(72, 40), out_rect=(6, 3, 60, 34)),
+              dict(w=72, h=40, pix="RGB8", stride_pad=5, params=dict(translation2d=[1.25, -0.5], background=[0.25, 0.5, 0.75, 1.0]), fov=1.7)):
+        p, src, m, mesh, dst0, pix, lens, digital = cases.build(c)
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        got = dst0.copy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # float32 overflow warnings on far-off-axis pixels are expected
+            np_restatement.undistort_image(src, got, p, m)
+        assert np.array_equal(got, want), c
