@@ -39,6 +39,8 @@ CONFIGS = {
             name="cfg2: 3840x2160 RGBA8, opencv_fisheye + rolling-shutter ON (2160 matrices), 240 Hz synthetic gyro, bilinear"),
     3: dict(w=7680, h=4320, pix="Luma16", lens="opencv_fisheye", digital="gopro_superview", rs=True,
             name="cfg3: 7680x4320 16-bit luma plane of YUV 4:2:2, opencv_fisheye + gopro_superview digital lens, rolling-shutter ON (4320 matrices), bilinear"),
+    31: dict(w=7680, h=4320, plane=(3840, 4320), pix="Luma16", lens="opencv_fisheye", digital="gopro_superview", rs=True,
+             name="cfg3 chroma: 3840x4320 16-bit U/V plane of 7680x4320 YUV 4:2:2 (source/output rects), opencv_fisheye + gopro_superview, rolling-shutter ON, bilinear"),
     4: dict(w=3840, h=2160, pix="R32f", lens="sony", digital=None, rs=True, ibis=True, mesh=True,
             name="cfg4: 3840x2160 f32 plane (GBRAPF32), sony lens + IBIS rows + 9x9 mesh correction, rolling-shutter ON, bilinear"),
 }
@@ -61,13 +63,14 @@ def select_config(n):
     global CFG, W, H, PIX, LENS, WORKLOAD, FRAMES_PER_STEP, RING, N_TIMESTAMPS
     CFG = CONFIGS[n]
     W, H, PIX, LENS, WORKLOAD = CFG["w"], CFG["h"], CFG["pix"], CFG["lens"], CFG["name"]
-    if n == 3: FRAMES_PER_STEP, RING, N_TIMESTAMPS = 32, 4, 8        # 66 MB planes: 4-frame ring = 265 MB
+    if n in (3, 31): FRAMES_PER_STEP, RING, N_TIMESTAMPS = 32, 4, 8  # 66 MB planes: 4-frame ring = 265 MB
     if n == 4: FRAMES_PER_STEP, RING, N_TIMESTAMPS = 32, 8, 8
 
 
-def algorithmic_bytes(p, rows, mesh_len=0):
+def algorithmic_bytes(p, rows, mesh_len=0, planes=1):
     """sum_planes(in_w*in_h*bpp + out_w*out_h*bpp) + rows*56 + 368 + 4*mesh_len."""
-    return p.width * p.height * p.bytes_per_pixel + p.output_width * p.output_height * p.bytes_per_pixel + rows * 56 + 368 + 4 * mesh_len
+    pw, ph = CFG.get("plane", (p.width, p.height))
+    return planes * 2 * pw * ph * p.bytes_per_pixel + rows * 56 + 368 + 4 * mesh_len
 
 
 class ClockSampler:
@@ -105,8 +108,16 @@ class ClockSampler:
 
 def base_params():
     from gyroflow_b200 import synth
-    return synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS, digital_lens=CFG.get("digital"), fov=1.05 if CFG.get("digital") else 1.0,
-                                    interpolation=INTERP)
+    p = synth.base_kernel_params(W, H, pixel_type=PIX, lens=LENS, digital_lens=CFG.get("digital"), fov=1.05 if CFG.get("digital") else 1.0,
+                                 interpolation=INTERP)
+    if CFG.get("plane"):         # a plane smaller than the frame: described by rects, like stabilization/mod.rs:209-231
+        from gyroflow_b200 import abi
+        pw, ph = CFG["plane"]
+        bpp = p.bytes_per_pixel
+        p.stride = p.output_stride = (pw * bpp + 255) // 256 * 256
+        p.source_rect[:] = [0, 0, pw, ph]; p.output_rect[:] = [0, 0, pw, ph]
+        p.flags |= abi.FLAG_HAS_SOURCE_RECT | abi.FLAG_HAS_OUTPUT_RECT
+    return p
 
 
 def make_tables(n):
@@ -137,8 +148,9 @@ def cpu_reference_fps(p, mats, frames, threads):
     """The reference's CPU path (oracle port) on `frames` full 4K frames, all host threads."""
     from gyroflow_b200 import synth
     from tests import oracle_lib
-    src = synth.synthetic_frame(W, H, PIX, stride=p.stride)
-    dst = np.zeros((H, p.output_stride), np.uint8)
+    bw, bh = CFG.get("plane", (W, H))
+    src = synth.synthetic_frame(bw, bh, PIX, stride=p.stride)
+    dst = np.zeros((bh, p.output_stride), np.uint8)
     mesh = make_mesh()
     oracle_lib.undistort_image(src, dst, p, PIX, LENS, CFG.get("digital"), mats[0], mesh, threads)          # warm-up (page faults, thread start)
     t0 = time.perf_counter()
@@ -184,6 +196,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--planes", type=int, default=1, help="planes of this geometry per frame, rendered by one gf_cuda_undistort_planes_dev call (side measurement)")
     ap.add_argument("--interp", default="Bilinear", help="Bilinear (BASELINE), Bicubic, Lanczos4, 'EWA: Robidoux', ... (side measurement)")
     args = ap.parse_args()
     select_config(args.config)
@@ -228,25 +241,35 @@ def main():
         else:
             t = torch.randint(0, 256, (H, p.stride), dtype=torch.uint8, device=dev, generator=gen)
         return t
-    frames_in = [rand_frame() for _ in range(RING)]
-    frames_out = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(RING)]
+    NPL = max(1, args.planes)
+    BW, BH = CFG.get("plane", (W, H))                 # buffer size of one plane
+    frames_in = [rand_frame() for _ in range(RING * NPL)]
+    frames_out = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(RING * NPL)]
     def dbufs(i):
-        a, b = frames_in[i % RING], frames_out[i % RING]
-        return g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
-                         g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel()))
+        a, b = frames_in[i % (RING * NPL)], frames_out[i % (RING * NPL)]
+        return g.Buffers(g.BufferDescription((BW, BH, p.stride), a.data_ptr(), length=a.numel()),
+                         g.BufferDescription((BW, BH, p.output_stride), b.data_ptr(), length=b.numel()))
     ctx = g.CudaWrapper.new(p, PIX, LENS, CFG.get("digital"), dbufs(0), device=local)
     # a real (non-default) stream: kernels, CUDA events and the timed region all live on it
     tstream = torch.cuda.Stream(device=dev)
     stream = tstream.cuda_stream
     assert stream != 0
-    all_bufs = [dbufs(i) for i in range(RING)]
+    all_bufs = [dbufs(i) for i in range(RING * NPL)]
+    plane_params = []
+    for k in range(NPL):
+        q = p.copy(); q.plane_index = k; plane_params.append(q)
     table_verdicts = [ctx.validate_tables_dev(mats[i].data_ptr(), rows) for i in range(N_TIMESTAMPS)]   # once per table, outside the timed region
 
     def step(s):
         for j in range(FRAMES_PER_STEP):
             i = s * FRAMES_PER_STEP + j
-            ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows,
-                                    mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
+            if NPL == 1:
+                ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows,
+                                        mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
+            else:       # one multi-plane frame: coordinates once, NPL sampling passes
+                b0 = (i % RING) * NPL
+                ctx.undistort_planes_dev(all_bufs[b0:b0 + NPL], plane_params, mats[i % N_TIMESTAMPS].data_ptr(), rows,
+                                         mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
 
     torch.cuda.synchronize()
     for s in range(args.warmup):
@@ -281,7 +304,7 @@ def main():
     hout = [torch.zeros((H, p.output_stride), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
     def hbufs(i):
         a, b = hin[i % DEPTH].numpy(), hout[i % DEPTH].numpy()
-        return g.Buffers(g.BufferDescription((W, H, p.stride), a), g.BufferDescription((W, H, p.output_stride), b))
+        return g.Buffers(g.BufferDescription((BW, BH, p.stride), a), g.BufferDescription((BW, BH, p.output_stride), b))
     hb = [hbufs(i) for i in range(DEPTH)]
     hctx = [g.CudaWrapper.new(p, PIX, LENS, CFG.get("digital"), hb[i], device=local) for i in range(DEPTH)]
     mats_host = mats.cpu().numpy()
@@ -309,7 +332,7 @@ def main():
     if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_fps = world * e2e_frames / float(te.item())
     h2d_frame = int(hin[0].numel() + rows * 56 + 368 + (mesh_np.size * 4 if mesh_np is not None else 0))    # frame + matrices + KernelParams (+ mesh)
-    d2h_frame = int(W * p.bytes_per_pixel * H)
+    d2h_frame = int(BW * p.bytes_per_pixel * BH)
     h2d, d2h = h2d_frame * FRAMES_PER_STEP * world, d2h_frame * FRAMES_PER_STEP * world
 
     if rank == 0:
@@ -317,8 +340,8 @@ def main():
         try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception: pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        abytes = algorithmic_bytes(p, rows, mesh_np.size if mesh_np is not None else 0)
-        launch_ms = total_ms / max(launches, 1)
+        abytes = algorithmic_bytes(p, rows, mesh_np.size if mesh_np is not None else 0, NPL)
+        launch_ms = total_ms / max(launches, 1) * (1 + NPL if NPL > 1 else 1)      # multi-plane frames: the frame's 1 + NPL launches together
         achieved = abytes / (launch_ms / 1e3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:
@@ -332,6 +355,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if INTERP == "Bilinear" else WORKLOAD.replace("bilinear", INTERP), "frame_bytes_in": int(H * p.stride), "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
                        "l2_policy": "inputs larger than L2: %d-frame ring of %.1f MB inputs (%d MB) + %d distinct matrix tables" % (RING, H * p.stride / 1e6, RING * H * p.stride // 1000000, N_TIMESTAMPS),
+                       "planes_per_frame": NPL,
                        "parallelism": "frame-sharded x%d, NCCL broadcast of tables only" % world},
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

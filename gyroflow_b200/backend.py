@@ -153,6 +153,16 @@ class CudaWrapper:
         if rc != 0:
             raise self._err(rc)
 
+    def undistort_planes_dev(self, buffers, params, matrices_dev: int, matrix_rows: int, mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0):
+        """buffers: list of Buffers (DEVICE), params: list of KernelParams — the planes of one frame (gf_cuda_undistort_planes_dev)."""
+        n = len(buffers)
+        ins = (abi.BufferDesc * n)(*[b.input.to_c() for b in buffers])
+        outs = (abi.BufferDesc * n)(*[b.output.to_c() for b in buffers])
+        ps = (abi.KernelParams * n)(*params)
+        rc = self._lib.gf_cuda_undistort_planes_dev(self._h, n, ins, outs, ps, matrices_dev, matrix_rows, mesh_dev or None, mesh_len, stream or None)
+        if rc != 0:
+            raise self._err(rc)
+
     def validate_tables_dev(self, matrices_dev: int, matrix_rows: int):
         """Scan a device-resident table once so later undistort_image_dev calls on it may take the trusted fast path."""
         rc = self._lib.gf_cuda_validate_tables_dev(self._h, matrices_dev, matrix_rows)

@@ -47,6 +47,8 @@ struct gf_cuda_ctx {
     KernelFn fn_x2t = nullptr;    // same, tables validated: no per-pixel numerator / IBIS tests
     std::unordered_map<const void*, uint32_t> validated;   // device tables vouched for by gf_cuda_validate_tables_dev
     unsigned* d_vflags = nullptr;
+    uint2* d_coords = nullptr; size_t d_coords_len = 0;   // multi-plane mode: the frame's coordinate map
+    KernelFn fn_shade = nullptr;
     unsigned long long aux_launches = 0;   // helper kernels (mesh widening, table scans): not counted by gf_cuda_launch_count
     unsigned long long x2_launches = 0;
     unsigned long long lean_launches = 0;
@@ -350,7 +352,7 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
 
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
-    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_x2t = fn_x2t;
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_x2t = fn_x2t; ctx->fn_shade = gf_shade_kernel(layout);
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -396,14 +398,17 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
     if (ctx->d_src) cudaFree(ctx->d_src);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     if (ctx->d_vflags) cudaFree(ctx->d_vflags);
+    if (ctx->d_coords) cudaFree(ctx->d_coords);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
     delete ctx;
 }
 
+// `more_planes` > 0: multi-plane mode — in/out/p are arrays of 1 + more_planes planes that share one geometry (checked by the caller);
+// the coordinates are computed once (pass 1, into ctx->d_coords) and every plane is then sampled from them (pass 2).
 static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
                     const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len,
-                    bool tables_on_device, void* cu_stream, bool sync_host = true) {
+                    bool tables_on_device, void* cu_stream, bool sync_host = true, size_t more_planes = 0) {
     if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
     { int rc = validate(ctx, p, in, out, ctx->bpp); if (rc != GF_OK) return rc; }
     if (!matrices) return fail(ctx, GF_ERR_NO_DATA, "NoStabilizationData: matrices is null");
@@ -482,11 +487,20 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const dim3 block(GF_BLOCK_X, GF_BLOCK_Y);
     const dim3 grid((A.out_cols + GF_BLOCK_X - 1) / GF_BLOCK_X, (A.out_rows + GF_BLOCK_Y - 1) / GF_BLOCK_Y);
     if (grid.x == 0 || grid.y == 0 || grid.y > 65535) return fail(ctx, GF_ERR_BAD_PARAMS, "output buffer geometry out of range");
+    if (more_planes > 0) {
+        const size_t need = (size_t)A.out_cols * (size_t)A.out_rows;
+        if (need > ctx->d_coords_len) {
+            if (ctx->d_coords) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_coords); ctx->d_coords = nullptr; ctx->d_coords_len = 0; }
+            CK(cudaMalloc(&ctx->d_coords, need * sizeof(uint2)));
+            ctx->d_coords_len = need;
+        }
+        A.coord_out = ctx->d_coords;
+    }
     // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
     // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
-    KernelFn x2 = ((A.feat & F_WILD) != 0) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
+    KernelFn x2 = ((A.feat & F_WILD) != 0 || more_planes > 0) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
     if (lean_ok && x2) {
         const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
         x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
@@ -495,6 +509,18 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     else         { ctx->fn<<<grid, block, 0, st>>>(A); }
     CK(cudaGetLastError());
     ctx->launches++;
+    if (more_planes > 0) {                                     // pass 2: one sampling-only launch per plane
+        for (size_t i = 0; i <= more_planes; ++i) {
+            WarpArgs B = A;
+            B.p = p[i];
+            B.coord_out = nullptr; B.coord_in = ctx->d_coords;
+            B.src = (const uint8_t*)in[i].ptr; B.dst = (uint8_t*)out[i].ptr; B.src_len = in[i].len; B.dst_len = out[i].len;
+            fill_uniforms(B, ctx, B.src, B.dst);
+            ctx->fn_shade<<<grid, block, 0, st>>>(B);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+    }
     if (use_slot) CK(cudaEventRecord(sl.done, st));
     if (out->kind == GF_BUF_HOST) {                                                                                  // opencl.rs:413
         if (full_cover) CK(cudaMemcpy2DAsync(out->ptr, (size_t)p->output_stride, ctx->d_dst, (size_t)p->output_stride,
@@ -522,6 +548,42 @@ GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx, const gf_buffer_desc*
                                          const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
                                          const float* mesh, size_t mesh_len, void* cu_stream) {
     return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream, false);
+}
+
+// Planes of one frame that share their geometry (GBRAPF32's four R32f planes, the U and V planes of planar YUV, ...):
+// every KernelParams field except plane_index and background must agree, as must buffer sizes, strides and rects.
+static bool planes_share_geometry(const gf_kernel_params* p, const gf_buffer_desc* in, const gf_buffer_desc* out, size_t n) {
+    for (size_t i = 1; i < n; ++i) {
+        gf_kernel_params a = p[0], b = p[i];
+        a.plane_index = b.plane_index = 0;
+        memset(a.background, 0, sizeof(a.background)); memset(b.background, 0, sizeof(b.background));
+        if (memcmp(&a, &b, sizeof(a)) != 0) return false;
+        const gf_buffer_desc* d[2][2] = {{&in[0], &in[i]}, {&out[0], &out[i]}};
+        for (auto& q : d) {
+            if (q[0]->width != q[1]->width || q[0]->height != q[1]->height || q[0]->stride != q[1]->stride || q[0]->len != q[1]->len ||
+                q[0]->has_rect != q[1]->has_rect || memcmp(q[0]->rect, q[1]->rect, sizeof(q[0]->rect)) != 0 ||
+                q[0]->has_rotation != q[1]->has_rotation || q[0]->rotation != q[1]->rotation || q[0]->kind != q[1]->kind) return false;
+        }
+    }
+    return true;
+}
+
+GF_API int gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                        const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                        const float* mesh_dev, size_t mesh_len, void* cu_stream) {
+    if (!ctx || !in || !out || !params || n_planes == 0) return fail(ctx, GF_ERR_BAD_PARAMS, "null argument");
+    for (size_t i = 0; i < n_planes; ++i) {
+        if (in[i].kind != GF_BUF_DEVICE || out[i].kind != GF_BUF_DEVICE) return fail(ctx, GF_ERR_BAD_PARAMS, "gf_cuda_undistort_planes_dev takes DEVICE buffers");
+        int rc = validate(ctx, &params[i], &in[i], &out[i], ctx->bpp); if (rc != GF_OK) return rc;
+    }
+    // one coordinate pass for all planes when they share a geometry; EWA needs a per-pixel Jacobian the map does not carry
+    const bool fuse = n_planes > 1 && ctx->fn_shade && params[0].interpolation <= 8 && planes_share_geometry(params, in, out, n_planes);
+    if (fuse) return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, n_planes - 1);
+    for (size_t i = 0; i < n_planes; ++i) {
+        int rc = run_warp(ctx, &in[i], &out[i], &params[i], matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream);
+        if (rc != GF_OK) return rc;
+    }
+    return GF_OK;
 }
 
 GF_API int gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows) {

@@ -31,6 +31,7 @@ KernelFn gf_kernel_insta360(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_sony(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp, int lean);
 KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
+KernelFn gf_shade_kernel(int layout);      // pass 2 of the multi-plane mode (shade_kernel.cu)
 
 // lean == 2 / 3: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form;
 // 3 = tables validated (no wild entries, no IBIS rows), 2 = unvalidated device tables (per-pixel numerator / IBIS tests kept)

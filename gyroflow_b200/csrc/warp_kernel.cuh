@@ -75,6 +75,8 @@ struct WarpArgs {
     const float*   mesh;            // device f32 (nullptr when mesh_len == 0)
     const double*  mesh64;          // the same values widened to f64 by a helper kernel before the launch (cpu_undistort.rs:539)
     const struct MeshAux* mesh_aux; // per-frame constants derived from the mesh header by the same helper kernel
+    uint2*         coord_out;       // multi-plane mode, pass 1: write the source coordinates of every output pixel here instead of sampling
+    const uint2*   coord_in;        // multi-plane mode, pass 2 (shade_from_coords_kernel): read them back
     unsigned long long src_len, dst_len;
     int   mesh_len;
     int   out_rows;                 // ceil(dst_len / output_stride): rows the reference iterates (par_chunks_mut)
@@ -856,47 +858,22 @@ GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum
 #define GF_BLOCK_X 32
 #define GF_BLOCK_Y 8
 
-template <int LENS, int DIGITAL, class PIX, int I, bool GEN>
-__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
-warp_kernel(const __grid_constant__ WarpArgs A) {
+// Coordinate-map entries of the multi-plane mode: (u, v) as raw bits, or one of three markers.  The marker's first word is a
+// NaN with a payload no arithmetic instruction produces (results are canonical NaNs), so it cannot collide with a computed u.
+#define GF_COORD_MARK 0x7fb0c0deu
+enum { GF_COORD_NONE = 1, GF_COORD_SKIP = 2, GF_COORD_FILL = 3 };     // undistort_coord returned None / pixel not written / fill-with-background
+
+// cpu_undistort.rs:576-622 — everything after undistort_coord for one output pixel: feather mode, sampling, range fix, store.
+template <class PIX, bool GEN>
+GF_DEV void finish_pixel(bool have_uv, float u, float v, float4 jac, const WarpArgs& A, uint8_t* __restrict__ out) {
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;
+    constexpr int I = 2;
     const uint32_t feat = A.feat;
-    const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
-    const int y = blockIdx.y * GF_BLOCK_Y + threadIdx.y;
-    if (x >= A.out_cols || y >= A.out_rows) return;
-    const unsigned long long off = (unsigned long long)y * (unsigned long long)P.output_stride + (unsigned long long)x * PIX::BYTES;
-    if (off + PIX::BYTES > A.dst_len) return;                     // trailing partial row (chunks_mut of a short last row)
-
-    const float opx = map_apply_int((float)x, A.omap_x);          // :546-549 (and :422-423: same expression, same value)
-    const float opy = map_apply_int((float)y, A.omap_y);
-    if (!(opx >= 0.0f && opy >= 0.0f && as_i32(opx) < P.output_width && as_i32(opy) < P.output_height)) return;   // :551
-
-    uint8_t* const out = A.dst + off;
     const bool dvec = has<GEN>(feat, F_DST_VEC);
     float pixel[C];
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
-    if (has<GEN>(feat, F_FILLBG)) { PIX::store(out, dvec, pixel); return; }                                              // :558-561
-
-    // :565; for EWA (interpolation > 8) the forward-difference Jacobian of :567-572 comes from two more
-    // evaluations at (x + eps, y) and (x, y + eps), run through the same (single) inlined copy of undistort_coord
-    float u = 0.0f, v = 0.0f;
-    bool have_uv = false;
-    float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
-    const int npos = P.interpolation > 8 ? 3 : 1;
-    #pragma unroll 1
-    for (int j = 0; j < npos; ++j) {
-        const float eps = 0.01f;
-        const float qx = j == 1 ? map_apply((float)x + eps, A.omap_x) : opx;
-        const float qy = j == 2 ? map_apply((float)y + eps, A.omap_y) : opy;
-        float tu, tv;
-        const bool ok = undistort_coord<LENS, DIGITAL, GEN>(qx, qy, A, tu, tv);
-        if (j == 0) { if (!ok) break; u = tu; v = tv; have_uv = true; continue; }
-        if (!ok) { tu = 0.0f; tv = 0.0f; }                                                                           // unwrap_or_default()
-        if (j == 1) { jac.x = (tu - u) / eps; jac.z = (tv - v) / eps; }
-        else        { jac.y = (tu - u) / eps; jac.w = (tv - v) / eps; }
-    }
     if (have_uv) {
         if (has<GEN>(feat, F_BG3)) {                                                                             // :576-613
             const float width_f = A.width_f, height_f = A.height_f;
@@ -918,7 +895,7 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
             #pragma unroll
             for (int ch = 0; ch < C; ++ch) pixel[ch] = c1[ch] * alpha + c2[ch] * (1.0f - alpha);
         } else {
-            if (I == 2 && PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && P.interpolation == GF_INTERP_BILINEAR) {
+            if (PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && P.interpolation == GF_INTERP_BILINEAR) {
                 // 8-bit bilinear interior: integer arithmetic, exact (see sample_u8_bilinear)
                 const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
                 const int sx = sx0 >> 5, sy = sy0 >> 5;
@@ -939,6 +916,84 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
     }
     if (has<GEN>(feat, F_FIXRANGE)) remap_colorrange<C>(pixel, (feat & F_IS_Y) != 0);                                     // :608-610 / :619-621
     PIX::store(out, dvec, pixel);                                                                                // :611 / :622
+}
+
+template <int LENS, int DIGITAL, class PIX, int I, bool GEN>
+__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
+warp_kernel(const __grid_constant__ WarpArgs A) {
+    const gf_kernel_params& P = A.p;
+    constexpr int C = PIX::COUNT;
+    const uint32_t feat = A.feat;
+    const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
+    const int y = blockIdx.y * GF_BLOCK_Y + threadIdx.y;
+    if (x >= A.out_cols || y >= A.out_rows) return;
+    uint2* const cmap = A.coord_out ? A.coord_out + ((size_t)y * (size_t)A.out_cols + (size_t)x) : nullptr;   // multi-plane mode, pass 1
+    const unsigned long long off = (unsigned long long)y * (unsigned long long)P.output_stride + (unsigned long long)x * PIX::BYTES;
+    if (off + PIX::BYTES > A.dst_len) { if (cmap) *cmap = make_uint2(GF_COORD_MARK, GF_COORD_SKIP); return; }   // trailing partial row (chunks_mut of a short last row)
+
+    const float opx = map_apply_int((float)x, A.omap_x);          // :546-549 (and :422-423: same expression, same value)
+    const float opy = map_apply_int((float)y, A.omap_y);
+    if (!(opx >= 0.0f && opy >= 0.0f && as_i32(opx) < P.output_width && as_i32(opy) < P.output_height)) {            // :551
+        if (cmap) *cmap = make_uint2(GF_COORD_MARK, GF_COORD_SKIP);
+        return;
+    }
+
+    uint8_t* const out = A.dst + off;
+    if (has<GEN>(feat, F_FILLBG)) {                                                                                  // :558-561
+        if (cmap) { *cmap = make_uint2(GF_COORD_MARK, GF_COORD_FILL); return; }
+        float pixel[C];
+        #pragma unroll
+        for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
+        PIX::store(out, has<GEN>(feat, F_DST_VEC), pixel);
+        return;
+    }
+
+    // :565; for EWA (interpolation > 8) the forward-difference Jacobian of :567-572 comes from two more
+    // evaluations at (x + eps, y) and (x, y + eps), run through the same (single) inlined copy of undistort_coord
+    float u = 0.0f, v = 0.0f;
+    bool have_uv = false;
+    float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
+    const int npos = P.interpolation > 8 ? 3 : 1;
+    #pragma unroll 1
+    for (int j = 0; j < npos; ++j) {
+        const float eps = 0.01f;
+        const float qx = j == 1 ? map_apply((float)x + eps, A.omap_x) : opx;
+        const float qy = j == 2 ? map_apply((float)y + eps, A.omap_y) : opy;
+        float tu, tv;
+        const bool ok = undistort_coord<LENS, DIGITAL, GEN>(qx, qy, A, tu, tv);
+        if (j == 0) { if (!ok) break; u = tu; v = tv; have_uv = true; continue; }
+        if (!ok) { tu = 0.0f; tv = 0.0f; }                                                                           // unwrap_or_default()
+        if (j == 1) { jac.x = (tu - u) / eps; jac.z = (tv - v) / eps; }
+        else        { jac.y = (tu - u) / eps; jac.w = (tv - v) / eps; }
+    }
+    if (cmap) {      // pass 1 of the multi-plane mode: the planes of one frame share these coordinates (the host checks that they do)
+        *cmap = have_uv ? make_uint2(__float_as_uint(u), __float_as_uint(v)) : make_uint2(GF_COORD_MARK, GF_COORD_NONE);
+        return;
+    }
+    finish_pixel<PIX, GEN>(have_uv, u, v, jac, A, out);
+}
+
+// Pass 2 of the multi-plane mode: one launch per plane, coordinates from the map — sampling, conversion and store only.
+template <class PIX>
+__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
+shade_from_coords_kernel(const __grid_constant__ WarpArgs A) {
+    const gf_kernel_params& P = A.p;
+    constexpr int C = PIX::COUNT;
+    const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
+    const int y = blockIdx.y * GF_BLOCK_Y + threadIdx.y;
+    if (x >= A.out_cols || y >= A.out_rows) return;
+    const uint2 e = __ldg(A.coord_in + ((size_t)y * (size_t)A.out_cols + (size_t)x));
+    const bool marked = e.x == GF_COORD_MARK;
+    if (marked && e.y == GF_COORD_SKIP) return;
+    uint8_t* const out = A.dst + ((unsigned long long)y * (unsigned long long)P.output_stride + (unsigned long long)x * PIX::BYTES);
+    if (marked && e.y == GF_COORD_FILL) {
+        float pixel[C];
+        #pragma unroll
+        for (int ch = 0; ch < C; ++ch) pixel[ch] = A.bg[ch];
+        PIX::store(out, (A.feat & F_DST_VEC) != 0, pixel);
+        return;
+    }
+    finish_pixel<PIX, true>(!marked, __uint_as_float(e.x), __uint_as_float(e.y), make_float4(1.0f, 0.0f, 0.0f, 1.0f), A, out);
 }
 
 } // namespace gf

@@ -254,6 +254,16 @@ GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx,
                                          const float* matrices, size_t matrix_rows,
                                          const float* mesh, size_t mesh_len, void* cu_stream);
 
+/* Multi-plane frames.  The reference renders planar formats one plane at a time, each with its own Stabilization
+ * object (rendering/mod.rs:484-548, 596-629), recomputing every pixel's source coordinate per plane.  When the planes share one
+ * geometry — the four R32f planes of GBRAPF32, the U and V planes of planar YUV: all KernelParams fields equal except plane_index
+ * and background, same buffer sizes/strides/rects — this call computes the coordinates once into a device map and then samples
+ * each plane from it (1 + n launches, bit-identical to n separate calls).  Otherwise (or for EWA) it degrades to n ordinary
+ * launches.  DEVICE buffers and device tables; `in`, `out`, `params` are arrays of n_planes. */
+GF_API int         gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                                const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                                const float* mesh_dev, size_t mesh_len, void* cu_stream);
+
 /* Device-resident tables (gf_cuda_undistort_image_dev) are untrusted by default: the kernel keeps per-pixel tests for wild matrix
  * entries and IBIS rows.  This call scans `matrix_rows x 14` floats on the device once and remembers the verdict for that pointer
  * (until gf_cuda_destroy; call it again after rewriting the table).  Returns 0 (tame, IBIS-free: fastest path), a positive bit mask

@@ -172,6 +172,73 @@ def test_mesh_spline_variants():
     assert_bit_exact(dict(w=320, h=180, mesh=True, mesh_n=5, fpd=True, ibis=True, lens="sony", pix="R32f"))
 
 
+# ---- multi-plane frames: coordinates once, every plane sampled from the map -----------------------------------------
+def _run_planes(case, n_planes, vary=None):
+    """n planes with the case's geometry and different content / plane_index (/ background); returns [(want, got)] per plane."""
+    import torch
+    built = [cases.build(dict(case, frame=i)) for i in range(n_planes)]
+    p0, _, m, mesh, dst0, pix, lens, digital = built[0]
+    tm = torch.from_numpy(m).cuda()
+    tmesh = torch.from_numpy(mesh).cuda() if mesh is not None else None
+    params, bufs, keep, wants = [], [], [], []
+    for i, (p, src, _, _, d0, _, _, _) in enumerate(built):
+        p = p.copy(); p.plane_index = i
+        if vary: vary(p, i)
+        want = d0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        tsrc, tdst = torch.from_numpy(src).cuda(), torch.from_numpy(d0.copy()).cuda()
+        bw, bh = case.get("in_size", (case["w"], case["h"]))
+        obw, obh = case.get("out_size", (case.get("ow", case["w"]), case.get("oh", case["h"])))
+        bufs.append(g.Buffers(g.BufferDescription((bw, bh, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
+                              g.BufferDescription((obw, obh, p.output_stride), tdst.data_ptr(), length=tdst.numel())))
+        params.append(p); keep.append((tsrc, tdst)); wants.append(want)
+    w = g.CudaWrapper.new(params[0], pix, lens, digital, bufs[0])
+    side = torch.cuda.Stream(); torch.cuda.synchronize()
+    l0 = w.launch_count
+    w.undistort_planes_dev(bufs, params, tm.data_ptr(), m.shape[0], tmesh.data_ptr() if tmesh is not None else 0, mesh.size if mesh is not None else 0,
+                           stream=side.cuda_stream)
+    side.synchronize()
+    launches = w.launch_count - l0
+    outs = [(wants[i], keep[i][1].cpu().numpy()) for i in range(n_planes)]
+    w.close()
+    return outs, launches, pix
+
+
+def _assert_planes(case, n_planes, fused, vary=None):
+    outs, launches, pix = _run_planes(case, n_planes, vary)
+    assert launches == (1 + n_planes if fused else n_planes), launches
+    for i, (want, got) in enumerate(outs):
+        n, mx = cases.compare(want, got, pix)
+        assert n == 0, "plane %d: %d mismatching bytes (max abs diff %s) for %r" % (i, n, mx, case)
+
+
+def test_fused_planes_gbrapf32_like():
+    """Four R32f planes (GBRAPF32, cfg 4): sony lens + IBIS + mesh, one coordinate pass, four sampling passes."""
+    _assert_planes(dict(w=320, h=180, pix="R32f", lens="sony", ibis=True, mesh=True), 4, fused=True)
+
+
+def test_fused_planes_yuv_chroma_pair():
+    """U and V of planar 16-bit YUV 4:2:2: half-width planes described by source / output rects (stabilization/mod.rs:209-231)."""
+    case = dict(w=320, h=180, pix="Luma16", digital="gopro_superview", in_size=(160, 180), in_rect=(0, 0, 160, 180),
+                out_size=(160, 180), out_rect=(0, 0, 160, 180))
+    _assert_planes(case, 2, fused=True)
+
+
+def test_fused_planes_options():
+    fix = lambda p, i: setattr(p, "flags", p.flags | abi.FLAG_FIX_COLOR_RANGE)                    # is_y differs per plane (plane_index)
+    _assert_planes(dict(w=320, h=180, pix="Luma8"), 3, fused=True, vary=fix)
+    bgv = lambda p, i: p.background.__setitem__(slice(0, 4), [0.1 * (i + 1), 0.5, 0.25, 1.0])     # per-plane background colour
+    _assert_planes(dict(w=320, h=180, pix="Luma16", fov=2.2), 3, fused=True, vary=bgv)
+    _assert_planes(dict(w=320, h=180, pix="RGBA8", interp="Lanczos4"), 2, fused=True)
+    _assert_planes(dict(w=320, h=180, pix="Luma8", params=dict(background_mode=3, background_margin=0.1, background_margin_feather=0.1), fov=1.6), 2, fused=True)
+    _assert_planes(dict(w=320, h=180, pix="Luma8", flags=abi.FLAG_FILL_WITH_BACKGROUND, params=dict(background=[0.3, 0.3, 0.3, 1.0])), 2, fused=True)
+    _assert_planes(dict(w=203, h=117, pix="UV8", stride_pad=2), 2, fused=True)
+    # not fusable: EWA, and planes whose parameters differ -> n ordinary launches, same results
+    _assert_planes(dict(w=200, h=120, pix="Luma8", interp="EWA: Mitchell"), 2, fused=False)
+    diff = lambda p, i: setattr(p, "lens_correction_amount", 1.0 if i == 0 else 0.5)
+    _assert_planes(dict(w=320, h=180, pix="Luma8"), 2, fused=False, vary=diff)
+
+
 # ---- higher-order resamplers (SURVEY f1): bicubic, Lanczos4 (the default render setting), EWA CubicBC ------------------
 @pytest.mark.parametrize("interp", ["Bicubic", "Lanczos4"])
 def test_bicubic_and_lanczos4(interp):
