@@ -270,6 +270,34 @@ class DeviceGyro:
             raise GyroflowCoreError(rc, "gf_cuda_find_fovs")
         return out
 
+    def undistort_points(self, distortion_model: str, digital_lens, points_xy, timestamp_ms, frame=0, use_fovs=False, lens_correction_amount=1.0):
+        """undistort_points_with_rolling_shutter (cpu_undistort.rs:636-641) on the device; points_xy: (n, 2) float32."""
+        pts = np.ascontiguousarray(points_xy, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros_like(pts)
+        rc = self._lib.gf_cuda_undistort_points(self._h, C.byref(self.cp.c), abi.LENS[distortion_model], abi.LENS[digital_lens] if digital_lens else 0,
+                                                timestamp_ms, frame, int(use_fovs), lens_correction_amount, pts.ctypes.data, pts.shape[0], out.ctypes.data, None)
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_undistort_points")
+        return out
+
+    def generate_stmap(self, distortion_model: str, digital_lens, timestamp_ms, frame=0, per_frame=True):
+        """generate_stmaps for one frame (stmap.rs:6-146): returns (dist[h, w, 3], undist[new_h, new_w, 3]) float32 RGB maps."""
+        import torch
+        m, d = abi.LENS[distortion_model], abi.LENS[digital_lens] if digital_lens else 0
+        nw, nh = C.c_int32(), C.c_int32()
+        rc = self._lib.gf_cuda_generate_stmap(self._h, C.byref(self.cp.c), m, d, int(per_frame), frame, timestamp_ms, C.byref(nw), C.byref(nh), None, 0, None, 0, None)
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_generate_stmap (size query)")
+        w, h = self.cp.c.width, self.cp.c.height
+        dist = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
+        und = torch.empty((nh.value, nw.value, 3), dtype=torch.float32, device="cuda")
+        rc = self._lib.gf_cuda_generate_stmap(self._h, C.byref(self.cp.c), m, d, int(per_frame), frame, timestamp_ms, C.byref(nw), C.byref(nh),
+                                              dist.data_ptr(), dist.numel(), und.data_ptr(), und.numel(), None)
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_generate_stmap")
+        torch.cuda.synchronize()
+        return dist.cpu().numpy(), und.cpu().numpy()
+
     def close(self):
         if self._h:
             self._lib.gf_cuda_gyro_free(self._h); self._h = None

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <algorithm>
 #include <string>
+#include <vector>
 #include <unordered_map>
 
 #include "kernel_registry.h"
@@ -408,7 +409,7 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
 // the coordinates are computed once (pass 1, into ctx->d_coords) and every plane is then sampled from them (pass 2).
 static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
                     const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len,
-                    bool tables_on_device, void* cu_stream, bool sync_host = true, size_t more_planes = 0) {
+                    bool tables_on_device, void* cu_stream, bool sync_host = true, size_t more_planes = 0, bool coord_only = false) {
     if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
     { int rc = validate(ctx, p, in, out, ctx->bpp); if (rc != GF_OK) return rc; }
     if (!matrices) return fail(ctx, GF_ERR_NO_DATA, "NoStabilizationData: matrices is null");
@@ -487,7 +488,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const dim3 block(GF_BLOCK_X, GF_BLOCK_Y);
     const dim3 grid((A.out_cols + GF_BLOCK_X - 1) / GF_BLOCK_X, (A.out_rows + GF_BLOCK_Y - 1) / GF_BLOCK_Y);
     if (grid.x == 0 || grid.y == 0 || grid.y > 65535) return fail(ctx, GF_ERR_BAD_PARAMS, "output buffer geometry out of range");
-    if (more_planes > 0) {
+    if (more_planes > 0 || coord_only) {
         const size_t need = (size_t)A.out_cols * (size_t)A.out_rows;
         if (need > ctx->d_coords_len) {
             if (ctx->d_coords) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_coords); ctx->d_coords = nullptr; ctx->d_coords_len = 0; }
@@ -500,7 +501,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
     // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
-    KernelFn x2 = ((A.feat & F_WILD) != 0 || more_planes > 0) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
+    KernelFn x2 = ((A.feat & F_WILD) != 0 || more_planes > 0 || coord_only) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
     if (lean_ok && x2) {
         const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
         x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
@@ -548,6 +549,112 @@ GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx, const gf_buffer_desc*
                                          const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
                                          const float* mesh, size_t mesh_len, void* cu_stream) {
     return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream, false);
+}
+
+// ------------------------------------------------------------------------------------------
+// ST maps — src/core/stmap.rs:6-146 without the EXR container: the two maps are returned as raw RGB f32 images
+// (SpecificChannels::rgb of :131-135: x / width, 1 - y / height, 0).
+// ------------------------------------------------------------------------------------------
+__global__ void stmap_rgb_kernel(const uint2* __restrict__ coords, int w, int h, int pitch, float* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint2 e = coords[(size_t)y * pitch + x];
+    float cx = 0.0f, cy = 0.0f;                              // `coords` starts zeroed and stays so where the closure returns None (:121-127)
+    if (e.x != GF_COORD_MARK) { cx = __uint_as_float(e.x); cy = __uint_as_float(e.y); }
+    float* o = out + ((size_t)y * w + x) * 3;
+    o[0] = cx / (float)w; o[1] = 1.0f - (cy / (float)h); o[2] = 0.0f;
+}
+
+extern "C" int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                        double timestamp_ms, size_t frame, int use_fovs, double lens_correction_amount,
+                                        const float* points_xy, size_t n, float* out_xy, void* cu_stream);
+extern "C" int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                         double timestamp_ms, size_t frame, float* out_rgb_dev, void* cu_stream);
+
+GF_API int gf_cuda_generate_stmap(gf_cuda_gyro* g, const gf_compute_params* cp_user, int distortion_model, int digital_lens,
+                                  int per_frame, size_t frame, double timestamp_ms, int32_t* out_new_width, int32_t* out_new_height,
+                                  float* dist_rgb_dev, size_t dist_capacity_floats, float* undist_rgb_dev, size_t undist_capacity_floats,
+                                  void* cu_stream) {
+    if (!g || !cp_user || !out_new_width || !out_new_height) return fail(nullptr, GF_ERR_BAD_PARAMS, "null argument");
+    gf_compute_params cp = *cp_user;                                                         // stmap.rs:24-35
+    const int width = cp.width, height = cp.height;
+    if (width < 4 || height < 4) return fail(nullptr, GF_ERR_SIZE_TOO_SMALL, "SizeTooSmall");
+    if (!per_frame) cp.frame_readout_time = 0.0;
+    cp.suppress_rotation = 1; cp.fovs = nullptr; cp.n_fovs = 0; cp.minimal_fovs = nullptr; cp.n_minimal_fovs = 0;
+    cp.fov_scale = 1.0; cp.output_width = width; cp.output_height = height;                  // :44-46
+
+    // bbox of the undistorted frame edge: points_around_rect(width, height, 31, 31) with fov_algorithm_margin = 0 (:58-60, fov_iterative.rs:154-175)
+    std::vector<float> rect, und;
+    {
+        const float w = (float)width, h = (float)height;
+        const int wcnt = 30, hcnt = 30;
+        const float wstep = w / (float)wcnt, hstep = h / (float)hcnt;
+        for (int i = 0; i < wcnt; ++i) { rect.push_back((float)i * wstep); rect.push_back(0.0f); }
+        for (int i = 0; i < hcnt; ++i) { rect.push_back(w); rect.push_back((float)i * hstep); }
+        for (int i = 0; i < wcnt; ++i) { rect.push_back((float)(wcnt - i) * wstep); rect.push_back(h); }
+        for (int i = 0; i < hcnt; ++i) { rect.push_back(0.0f); rect.push_back((float)(hcnt - i) * hstep); }
+        for (float& v : rect) v += 0.0f;
+    }
+    und.resize(rect.size());
+    int rc = gf_cuda_undistort_points(g, &cp, distortion_model, digital_lens, timestamp_ms, frame, 0, 1.0, rect.data(), rect.size() / 2, und.data(), cu_stream);
+    if (rc != GF_OK) return fail(nullptr, rc, "gf_cuda_undistort_points failed");
+    float min_x = 0.0f, min_y = 0.0f, max_x = 0.0f, max_y = 0.0f;                             // :62-71 (f32::min / max ignore NaN)
+    for (size_t i = 0; i < und.size(); i += 2) {
+        min_x = fminf(und[i], min_x); min_y = fminf(und[i + 1], min_y);
+        max_x = fmaxf(und[i], max_x); max_y = fmaxf(und[i + 1], max_y);
+    }
+    const float fw = ceilf(max_x - min_x), fh = ceilf(max_y - min_y);
+    // `as usize`: truncating, saturating, NaN -> 0
+    const long long new_w = fw != fw ? 0 : (fw <= 0.0f ? 0 : (fw >= 2147483647.0f ? 2147483647LL : (long long)fw));
+    const long long new_h = fh != fh ? 0 : (fh <= 0.0f ? 0 : (fh >= 2147483647.0f ? 2147483647LL : (long long)fh));
+    *out_new_width = (int32_t)new_w; *out_new_height = (int32_t)new_h;
+    if (new_w < 4 || new_h < 4 || new_w > 32768 || new_h > 32768) return fail(nullptr, GF_ERR_SIZE_MISMATCH, "ST map: undistorted frame size out of range");
+    if (!dist_rgb_dev || !undist_rgb_dev) return GF_OK;                                      // size query
+    if (dist_capacity_floats < (size_t)width * height * 3 || undist_capacity_floats < (size_t)new_w * new_h * 3)
+        return fail(nullptr, GF_ERR_BUFFER_TOO_SMALL, "ST map output buffers too small");
+
+    cp.fov_scale = (double)fmaxf((float)new_w / (float)width, (float)new_h / (float)height);  // :75
+    cp.width = (int)new_w; cp.height = (int)new_h; cp.output_width = (int)new_w; cp.output_height = (int)new_h;
+    gf_kernel_params kp;
+    const size_t max_rows = (size_t)std::max(new_w, new_h);
+    std::vector<float> mats(max_rows * GF_MATRIX_STRIDE);
+    size_t rows = 0;
+    rc = gf_frame_transform_at_timestamp(&cp, timestamp_ms, frame, &kp, mats.data(), max_rows, &rows, nullptr, nullptr);   // :79
+    if (rc != GF_OK) return fail(nullptr, rc, "gf_frame_transform_at_timestamp failed");
+    kp.width = (int)new_w; kp.height = (int)new_h; kp.output_width = (int)new_w; kp.output_height = (int)new_h;   // :80-84
+    kp.flags = (digital_lens != GF_LENS_NONE ? GF_FLAG_HAS_DIGITAL_LENS : 0) | (cp.readout_horizontal ? GF_FLAG_HORIZONTAL_RS : 0);
+    // The closure of :88-109 is undistort_coord's row selection + rotate_and_distort and nothing else: run the warp kernel in
+    // coordinate mode with the optional stages switched off (no lens-correction blend, no source-rect map: background mode 3
+    // defers that map to the sampling stage, which never runs here).
+    gf_kernel_params kq = kp;
+    kq.lens_correction_amount = 1.0f; kq.background_mode = 3; kq.input_rotation = 0.0f;
+    kq.translation2d[0] = kq.translation2d[1] = 0.0f;
+    kq.interpolation = GF_INTERP_BILINEAR; kq.bytes_per_pixel = 1; kq.pix_element_count = 1;
+    kq.stride = (int)new_w; kq.output_stride = (int)new_w;
+    kq.source_rect[0] = kq.source_rect[1] = 0; kq.source_rect[2] = (int)new_w; kq.source_rect[3] = (int)new_h;
+    kq.output_rect[0] = kq.output_rect[1] = 0; kq.output_rect[2] = (int)new_w; kq.output_rect[3] = (int)new_h;
+    kq.max_pixel_value = 255.0f; kq.pixel_value_limit = 255.0f;
+    gf_buffer_desc d; memset(&d, 0, sizeof(d));
+    d.width = (int)new_w; d.height = (int)new_h; d.stride = (int)new_w; d.kind = GF_BUF_DEVICE;
+    d.ptr = undist_rgb_dev; d.len = (size_t)new_w * (size_t)new_h;                          // never dereferenced in coordinate mode
+    gf_cuda_ctx* ctx = nullptr;
+    int device = 0; cudaGetDevice(&device);
+    rc = gf_cuda_create(&ctx, device, &kq, GF_PIX_LUMA8, distortion_model, digital_lens, &d, &d, 0);
+    if (rc != GF_OK) return rc;
+    cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : ctx->stream;
+    rc = run_warp(ctx, &d, &d, &kq, mats.data(), rows, nullptr, 0, false, (void*)st, true, 0, true);
+    if (rc == GF_OK) {
+        const dim3 block(32, 8), grid(((unsigned)new_w + 31) / 32, ((unsigned)new_h + 7) / 8);
+        stmap_rgb_kernel<<<grid, block, 0, st>>>(ctx->d_coords, (int)new_w, (int)new_h, (int)new_w, undist_rgb_dev);
+        if (cudaGetLastError() != cudaSuccess) rc = GF_ERR_CUDA;
+    }
+    if (rc == GF_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = GF_ERR_CUDA;
+    gf_cuda_destroy(ctx);
+    if (rc != GF_OK) return rc;
+
+    cp.width = width; cp.height = height; cp.output_width = width; cp.output_height = height;   // :111-112 (fov_scale stays)
+    rc = gf_cuda_stmap_distort_dev(g, &cp, distortion_model, digital_lens, timestamp_ms, frame, dist_rgb_dev, cu_stream);
+    return rc;
 }
 
 // Planes of one frame that share their geometry (GBRAPF32's four R32f planes, the U and V planes of planar YUV, ...):

@@ -271,6 +271,47 @@ ZoomFn pick_zoom(int lens, int digital) {
     }
 }
 
+// undistort_points over an explicit point list (pts != nullptr: out = n x (x, y)) or over every pixel centre of a w x h grid
+// (pts == nullptr: out = w*h x RGB, the ST-map encoding of stmap.rs:131-135: x / w, 1 - y / h, 0).
+template <int LENS, int DIGITAL>
+__global__ void __launch_bounds__(128) points_kernel(const ZoomArgs A, const ZoomFrame F, const float2* __restrict__ pts, size_t n, int grid_w, int grid_h, float* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float px, py;
+    if (pts) { const float2 p = pts[i]; px = p.x; py = p.y; }
+    else     { px = (float)(int)(i % (size_t)grid_w); py = (float)(int)(i / (size_t)grid_w); }
+    float ox, oy;
+    undistort_point_rs<LENS, DIGITAL>(A, F, px, py, ox, oy);
+    if (pts) { out[2 * i] = ox; out[2 * i + 1] = oy; }
+    else     { out[3 * i] = ox / (float)grid_w; out[3 * i + 1] = 1.0f - (oy / (float)grid_h); out[3 * i + 2] = 0.0f; }
+}
+typedef void (*PointsFn)(const ZoomArgs, const ZoomFrame, const float2*, size_t, int, int, float*);
+template <int LENS> PointsFn pick_points_digital(int digital) {
+    switch (digital) {
+    case GF_LENS_NONE:             return points_kernel<LENS, GF_LENS_NONE>;
+    case GF_LENS_DIGITAL_STRETCH:  return points_kernel<LENS, GF_LENS_DIGITAL_STRETCH>;
+    case GF_LENS_GOPRO_SUPERVIEW:  return LENS == GF_LENS_OPENCV_FISHEYE ? points_kernel<LENS, GF_LENS_GOPRO_SUPERVIEW> : nullptr;
+    case GF_LENS_GOPRO6_SUPERVIEW: return LENS == GF_LENS_OPENCV_FISHEYE ? points_kernel<LENS, GF_LENS_GOPRO6_SUPERVIEW> : nullptr;
+    case GF_LENS_GOPRO_HYPERVIEW:  return LENS == GF_LENS_OPENCV_FISHEYE ? points_kernel<LENS, GF_LENS_GOPRO_HYPERVIEW> : nullptr;
+    case GF_LENS_GOPRO_WARP:       return LENS == GF_LENS_GOPRO ? points_kernel<LENS, GF_LENS_GOPRO_WARP> : nullptr;
+    default: return nullptr;
+    }
+}
+PointsFn pick_points(int lens, int digital) {
+    switch (lens) {
+    case GF_LENS_OPENCV_FISHEYE:     return pick_points_digital<GF_LENS_OPENCV_FISHEYE>(digital);
+    case GF_LENS_OPENCV_STANDARD:    return pick_points_digital<GF_LENS_OPENCV_STANDARD>(digital);
+    case GF_LENS_POLY3:              return pick_points_digital<GF_LENS_POLY3>(digital);
+    case GF_LENS_POLY5:              return pick_points_digital<GF_LENS_POLY5>(digital);
+    case GF_LENS_PTLENS:             return pick_points_digital<GF_LENS_PTLENS>(digital);
+    case GF_LENS_INSTA360:           return pick_points_digital<GF_LENS_INSTA360>(digital);
+    case GF_LENS_SONY:               return pick_points_digital<GF_LENS_SONY>(digital);
+    case GF_LENS_GENERIC_POLYNOMIAL: return pick_points_digital<GF_LENS_GENERIC_POLYNOMIAL>(digital);
+    case GF_LENS_GOPRO:              return pick_points_digital<GF_LENS_GOPRO>(digital);
+    default: return nullptr;
+    }
+}
+
 bool zoom_lens_noop(int lens, const float* k) {
     switch (lens) {
     case GF_LENS_OPENCV_FISHEYE: case GF_LENS_SONY: return k[0] == 0.0f && k[1] == 0.0f && k[2] == 0.0f && k[3] == 0.0f;
@@ -289,26 +330,25 @@ struct gf_cuda_gyro {
     cudaStream_t stream;
 };
 
-extern "C" {
+// FrameTransform::get_fov without keyframes — frame_transform.rs:52-58
+static double gf_points_fov(const gf_compute_params* cp, size_t frame, int use_fovs) {
+    double fov_scale = cp->fov_scale;
+    if (cp->fov_overview && use_fovs) fov_scale += 1.0;
+    double fov = 1.0;
+    if (use_fovs) {
+        double f = 1.0;
+        if (cp->fovs && frame < cp->n_fovs) f = cp->fovs[frame]; else if (cp->fovs && cp->n_fovs > 1) f = cp->fovs[cp->n_fovs - 1];
+        fov = f * fov_scale;
+    }
+    fov = fmax(fov, 0.001);
+    return fov * (double)cp->width / (double)(cp->output_width > 1 ? cp->output_width : 1);
+}
 
-// FovIterative::compute for `n` frames (zooming/fov_iterative.rs:31-74 without trim ranges / keyframes): out[i] = find_fov(frame i).
-// `cp` is the user's ComputeParams; the calculate_fovs adjustments (fov_scale = 1, fovs cleared, output size = input size,
-// zooming/mod.rs:41-49) are applied here.
-GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, int distortion_model, int digital_lens,
-                             const double* timestamps_ms, size_t n, float fov_algorithm_margin, double* out_fov_minimal, void* cu_stream) {
-    if (!g || !cp_user || !timestamps_ms || !out_fov_minimal) return GF_ERR_BAD_PARAMS;
-    if (n == 0) return GF_OK;
-    ZoomFn fn = pick_zoom(distortion_model, digital_lens);
-    if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
-    if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
-    gf_compute_params cp = *cp_user;
-    const int org_ow = cp.output_width, org_oh = cp.output_height;
-    cp.fov_scale = 1.0; cp.n_fovs = 0; cp.n_minimal_fovs = 0; cp.output_width = cp.width; cp.output_height = cp.height;
-
-    ZoomArgs A; memset(&A, 0, sizeof(A));
+// Everything undistort_points (cpu_undistort.rs:652-698) and at_timestamp_for_points (frame_transform.rs:352-410) derive from
+// ComputeParams for one call: kernel params, K_new, readout timing.  Returns the signed frame readout time.
+static double setup_points_args(const gf_cuda_gyro* g, const gf_compute_params& cp, int distortion_model, double fov, double lens_correction_amount, ZoomArgs& A) {
+    memset(&A, 0, sizeof(A));
     const double* K = cp.camera_matrix;
-    // at_timestamp_for_points with use_fovs = false: fov = max(1, 0.001) * width / output_width (= 1 after the adjustments)
-    const double fov = fmax(1.0, 0.001) * (double)cp.width / (double)(cp.output_width > 1 ? cp.output_width : 1);
     const double hr = cp.input_horizontal_stretch > 0.01 ? cp.input_horizontal_stretch : 1.0;
     memcpy(A.new_k, K, sizeof(A.new_k));
     A.new_k[0] = A.new_k[0] * (1.0 / hr) / fov; A.new_k[4] = A.new_k[4] * (1.0 / hr) / fov;
@@ -330,26 +370,53 @@ GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, 
     A.lens_noop = zoom_lens_noop(distortion_model, kp.k) ? 1 : 0;
     A.hstretch = cp.input_horizontal_stretch > 0.001 ? (float)cp.input_horizontal_stretch : 0.0f;
     A.vstretch = cp.input_vertical_stretch   > 0.001 ? (float)cp.input_vertical_stretch   : 0.0f;
+    A.lc = lens_correction_amount < 1.0 ? 1 : 0;
+    if (A.lc) {
+        A.out_cx = (float)cp.output_width / 2.0f; A.out_cy = (float)cp.output_height / 2.0f;
+        A.amount = (float)lens_correction_amount; A.factor = fmaxf(1.0f - A.amount, 0.001f);
+        A.out_fx = A.fx / (float)fov / A.factor; A.out_fy = A.fy / (float)fov / A.factor; A.fov = (float)fov;
+    }
+    return frt;
+}
+// smoothed(ts) * org(ts)^-1 and the readout start time of one frame — frame_transform.rs:376-388
+static ZoomFrame frame_uniforms(const gf_compute_params& cp, double ts, double frt) {
+    const ZTrack horg{ cp.org.ts_us, cp.org.quats, cp.org.n }, hsm{ cp.smoothed.ts_us, cp.smoothed.quats, cp.smoothed.n };
+    ZoomFrame f;
+    ZQuat q1 = zq_at(horg, cp.duration_ms, ts - cp.gyro_offset_ms); q1 = { q1.w, -q1.i, -q1.j, -q1.k };
+    f.q0 = zq_mul(zq_at(hsm, cp.duration_ms, ts - cp.gyro_offset_ms), q1);
+    f.start_ts = ts - frt / 2.0;
+    return f;
+}
+
+
+extern "C" {
+
+// FovIterative::compute for `n` frames (zooming/fov_iterative.rs:31-74 without trim ranges / keyframes): out[i] = find_fov(frame i).
+// `cp` is the user's ComputeParams; the calculate_fovs adjustments (fov_scale = 1, fovs cleared, output size = input size,
+// zooming/mod.rs:41-49) are applied here.
+GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, int distortion_model, int digital_lens,
+                             const double* timestamps_ms, size_t n, float fov_algorithm_margin, double* out_fov_minimal, void* cu_stream) {
+    if (!g || !cp_user || !timestamps_ms || !out_fov_minimal) return GF_ERR_BAD_PARAMS;
+    if (n == 0) return GF_OK;
+    ZoomFn fn = pick_zoom(distortion_model, digital_lens);
+    if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
+    if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    gf_compute_params cp = *cp_user;
+    const int org_ow = cp.output_width, org_oh = cp.output_height;
+    cp.fov_scale = 1.0; cp.n_fovs = 0; cp.n_minimal_fovs = 0; cp.output_width = cp.width; cp.output_height = cp.height;
+
+    ZoomArgs A;
+    // at_timestamp_for_points with use_fovs = false: fov = max(1, 0.001) * width / output_width (= 1 after the adjustments)
+    const double fov = fmax(1.0, 0.001) * (double)cp.width / (double)(cp.output_width > 1 ? cp.output_width : 1);
+    const double frt = setup_points_args(g, cp, distortion_model, fov, cp.lens_correction_amount, A);
     const float ratio = (float)cp.width / (float)(org_ow > 1 ? org_ow : 1);                // FovIterative::new :78-89
     A.in_w = (float)cp.width; A.in_h = (float)cp.height;
     A.out_w = (float)org_ow * ratio; const float out_h = (float)org_oh * ratio;
     A.inv_aspect = out_h / A.out_w; A.margin = fov_algorithm_margin;
     A.zc_x = (float)cp.adaptive_zoom_center_offset[0] * A.in_w; A.zc_y = (float)cp.adaptive_zoom_center_offset[1] * A.in_h;
-    A.lc = cp.lens_correction_amount < 1.0 ? 1 : 0;
-    if (A.lc) {
-        A.out_cx = (float)cp.output_width / 2.0f; A.out_cy = (float)cp.output_height / 2.0f;
-        A.amount = (float)cp.lens_correction_amount; A.factor = fmaxf(1.0f - A.amount, 0.001f);
-        A.out_fx = A.fx / (float)fov / A.factor; A.out_fy = A.fy / (float)fov / A.factor; A.fov = (float)fov;
-    }
     // per-frame uniforms on the host: two O(log n) lookups per frame
-    const ZTrack horg{ cp.org.ts_us, cp.org.quats, cp.org.n }, hsm{ cp.smoothed.ts_us, cp.smoothed.quats, cp.smoothed.n };
     std::vector<ZoomFrame> hf(n);
-    for (size_t i = 0; i < n; ++i) {
-        const double ts = timestamps_ms[i];
-        ZQuat q1 = zq_at(horg, cp.duration_ms, ts - cp.gyro_offset_ms); q1 = { q1.w, -q1.i, -q1.j, -q1.k };
-        hf[i].q0 = zq_mul(zq_at(hsm, cp.duration_ms, ts - cp.gyro_offset_ms), q1);
-        hf[i].start_ts = ts - frt / 2.0;
-    }
+    for (size_t i = 0; i < n; ++i) hf[i] = frame_uniforms(cp, timestamps_ms[i], frt);
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     ZoomFrame* d_frames = nullptr; double* d_out = nullptr;
     cudaError_t e;
@@ -362,6 +429,54 @@ GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d_frames); cudaFree(d_out);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    return GF_OK;
+}
+
+// undistort_points_with_rolling_shutter for an arbitrary point list (cpu_undistort.rs:636-641): host in / host out, synchronous.
+GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                    double timestamp_ms, size_t frame, int use_fovs, double lens_correction_amount,
+                                    const float* points_xy, size_t n, float* out_xy, void* cu_stream) {
+    if (!g || !cp || !points_xy || !out_xy) return GF_ERR_BAD_PARAMS;
+    if (n == 0) return GF_OK;
+    PointsFn fn = pick_points(distortion_model, digital_lens);
+    if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
+    if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    ZoomArgs A;
+    const double fov = gf_points_fov(cp, frame, use_fovs);
+    const double frt = setup_points_args(g, *cp, distortion_model, fov, lens_correction_amount, A);
+    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt);
+    cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
+    float2* d_in = nullptr; float* d_out = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_in, n * sizeof(float2))) != cudaSuccess || (e = cudaMalloc(&d_out, n * 2 * sizeof(float))) != cudaSuccess) {
+        if (d_in) cudaFree(d_in); (void)cudaGetLastError(); return GF_ERR_CUDA;
+    }
+    e = cudaMemcpyAsync(d_in, points_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) { fn<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, F, d_in, n, 0, 0, d_out); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_xy, d_out, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    return GF_OK;
+}
+
+// The "redistort" ST map (stmap.rs:112-116): undistort_points of every pixel centre of the width x height frame, written to
+// device memory as RGB f32 (x / width, 1 - y / height, 0).  Asynchronous on the stream.
+GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                     double timestamp_ms, size_t frame, float* out_rgb_dev, void* cu_stream) {
+    if (!g || !cp || !out_rgb_dev) return GF_ERR_BAD_PARAMS;
+    PointsFn fn = pick_points(distortion_model, digital_lens);
+    if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
+    if (cp->width < 1 || cp->height < 1) return GF_ERR_BAD_PARAMS;
+    if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    ZoomArgs A;
+    const double fov = gf_points_fov(cp, frame, 1);
+    const double frt = setup_points_args(g, *cp, distortion_model, fov, 1.0, A);
+    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt);
+    cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
+    const size_t n = (size_t)cp->width * (size_t)cp->height;
+    fn<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, F, nullptr, n, cp->width, cp->height, out_rgb_dev);
+    if (cudaGetLastError() != cudaSuccess) return GF_ERR_CUDA;
     return GF_OK;
 }
 

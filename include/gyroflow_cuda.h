@@ -345,6 +345,25 @@ GF_API int  gf_cuda_frame_transform_dev(gf_cuda_gyro* g, const gf_compute_params
 GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
                              const double* timestamps_ms, size_t n, float fov_algorithm_margin,
                              double* out_fov_minimal, void* cu_stream);
+/* undistort_points_with_rolling_shutter for an arbitrary list of (x, y) points — cpu_undistort.rs:636-641 (host in/out, synchronous). */
+GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                    double timestamp_ms, size_t frame, int use_fovs, double lens_correction_amount,
+                                    const float* points_xy, size_t n, float* out_xy, void* cu_stream);
+
+/* ST maps — generate_stmaps, src/core/stmap.rs:6-146, for one frame, without the EXR container: both maps are raw
+ * RGB f32 images in device memory (x / width, 1 - y / height, 0 — stmap.rs:131-135).
+ *   dist   : width x height, undistort_points of every pixel (the "redistort" map, :112-116)
+ *   undist : new_width x new_height (the bounding box of the undistorted frame edge, :58-77), rotate_and_distort of every pixel (:86-109)
+ * Call once with NULL buffers to get new_width / new_height, then with buffers of width*height*3 and new_width*new_height*3 floats.
+ * `cp` is the user's ComputeParams; the adjustments of :24-35 (suppress_rotation, fovs cleared, per_frame == 0 -> no readout time)
+ * are applied inside.  Synchronous. */
+GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                     double timestamp_ms, size_t frame, float* out_rgb_dev, void* cu_stream);
+GF_API int gf_cuda_generate_stmap(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                  int per_frame, size_t frame, double timestamp_ms, int32_t* out_new_width, int32_t* out_new_height,
+                                  float* dist_rgb_dev, size_t dist_capacity_floats, float* undist_rgb_dev, size_t undist_capacity_floats,
+                                  void* cu_stream);
+
 GF_API int gf_zoom_dynamic_compute(const double* fov_minimal, size_t n, double window_s, double fps, int method, double* out);
 
 #ifdef __cplusplus

@@ -1236,9 +1236,9 @@ static double pts_get_fov(const gf_compute_params* cp, size_t frame, int use_fov
 }
 
 /* at_timestamp_for_points — frame_transform.rs:352-438: per-point K_new * R (f64), use_fovs = false */
-static void rotations_for_points(const gf_compute_params* cp, const float* pts, size_t n, double timestamp_ms, size_t frame,
+static void rotations_for_points(const gf_compute_params* cp, const float* pts, size_t n, double timestamp_ms, size_t frame, int use_fovs,
                                  double* rot /* n x 9 */, double* fov_out) {
-    double fov = pts_get_fov(cp, frame, 0);
+    double fov = pts_get_fov(cp, frame, use_fovs);
     const double* K = cp->camera_matrix;
     double hr = cp->input_horizontal_stretch > 0.01 ? cp->input_horizontal_stretch : 1.0;
     double new_k[9]; memcpy(new_k, K, sizeof(new_k));
@@ -1374,14 +1374,58 @@ static void undistort_points(const gf_compute_params* cp, int model, int digital
     }
 }
 
-void gf_oracle_undistort_points_rs(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
-                                   double timestamp_ms, size_t frame, double lens_correction_amount, float* out) {
+void gf_oracle_undistort_points_rs_ex(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
+                                      double timestamp_ms, size_t frame, double lens_correction_amount, int use_fovs, float* out) {
     if (n == 0) return;
     double* rot = (double*)malloc(n * 9 * sizeof(double));
     double fov;
-    rotations_for_points(cp, distorted, n, timestamp_ms, frame, rot, &fov);
+    rotations_for_points(cp, distorted, n, timestamp_ms, frame, use_fovs, rot, &fov);
     undistort_points(cp, model, digital, distorted, n, rot, lens_correction_amount, fov, out);
     free(rot);
+}
+void gf_oracle_undistort_points_rs(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
+                                   double timestamp_ms, size_t frame, double lens_correction_amount, float* out) {
+    gf_oracle_undistort_points_rs_ex(cp, model, digital, distorted, n, timestamp_ms, frame, lens_correction_amount, 0, out);
+}
+
+/* ---- ST maps — stmap.rs:86-136 -------------------------------------------------------------------
+ * The two closures of generate_stmaps and the RGB encoding of parallel_exr (:131-135); the size computation of :58-77 is
+ * restated by the test around gf_oracle_undistort_points_rs_ex. */
+void gf_oracle_stmap_undistort(const gf_kernel_params* P, const float* matrices, int model, int digital, float* out_rgb) {
+    const int w = P->width, h = P->height;
+    warp_ctx W = { P, matrices, (size_t)P->matrix_count, model, digital, P->r_limit * P->r_limit, NULL, 0 };
+    const int horizontal = (P->flags & 16) == 16;
+    for (int yi = 0; yi < h; ++yi) for (int xi = 0; xi < w; ++xi) {
+        float x = (float)xi, y = (float)yi;
+        v2 coords = {0.0f, 0.0f};
+        int32_t s0 = horizontal ? rs_f32_as_i32(rs_round(x)) : rs_f32_as_i32(rs_round(y));                  /* :91-95 */
+        int32_t lim = horizontal ? P->width : P->height;
+        if (s0 > lim) s0 = lim; if (s0 < 0) s0 = 0;
+        size_t sy = (size_t)s0;
+        if (P->matrix_count > 1) {                                                                            /* :96-105 */
+            v2 pt;
+            if (rotate_and_distort((v2){x, y}, (size_t)P->matrix_count / 2, &W, &pt)) {
+                int32_t s1 = rs_f32_as_i32(rs_round(horizontal ? pt.x : pt.y));
+                if (s1 > lim) s1 = lim; if (s1 < 0) s1 = 0;
+                sy = (size_t)s1;
+            }
+        }
+        size_t idx = sy < (size_t)P->matrix_count - 1 ? sy : (size_t)P->matrix_count - 1;                    /* :108 */
+        v2 r;
+        if (rotate_and_distort((v2){x, y}, idx, &W, &r)) coords = r;                                          /* :109, :123-126 */
+        float* o = out_rgb + ((size_t)yi * (size_t)w + (size_t)xi) * 3;
+        o[0] = coords.x / (float)w; o[1] = 1.0f - (coords.y / (float)h); o[2] = 0.0f;                        /* :131-135 */
+    }
+}
+void gf_oracle_stmap_distort(const gf_compute_params* cp, int model, int digital, double timestamp_ms, size_t frame, float* out_rgb) {
+    const int w = cp->width, h = cp->height;
+    const size_t n = (size_t)w * (size_t)h;
+    float* pts = (float*)malloc(n * 2 * sizeof(float)); float* und = (float*)malloc(n * 2 * sizeof(float));
+    for (int yi = 0; yi < h; ++yi) for (int xi = 0; xi < w; ++xi) { pts[2 * ((size_t)yi * w + xi)] = (float)xi; pts[2 * ((size_t)yi * w + xi) + 1] = (float)yi; }
+    /* :113-115: one point at a time in the reference; per-point rotations make the batch identical */
+    gf_oracle_undistort_points_rs_ex(cp, model, digital, pts, n, timestamp_ms, frame, 1.0, 1, und);
+    for (size_t i = 0; i < n; ++i) { out_rgb[3 * i] = und[2 * i] / (float)w; out_rgb[3 * i + 1] = 1.0f - (und[2 * i + 1] / (float)h); out_rgb[3 * i + 2] = 0.0f; }
+    free(pts); free(und);
 }
 
 /* fov_iterative.rs:136-151 */

@@ -10,7 +10,8 @@
  * in this image (no rustc/cargo).  The oracle is therefore pinned only by (a) review
  * against the cited lines, (b) analytical known-answer cases (identity warp, pure
  * translation, forward/inverse lens round trips) in tests/, and (c) an independent numpy
- * restatement of the fisheye + rolling-shutter + bilinear path (tests/np_restatement.py).
+ * restatement of the fisheye + rolling-shutter + bilinear path (tests/np_restatement.py,
+ * tests/test_oracle.py::test_independent_numpy_restatement_agrees).
  *
  * Float semantics mirrored from Rust: f32 ops are IEEE with no FMA contraction (build
  * with -ffp-contract=off), `as` casts truncate + saturate + NaN->0, f32::round is
@@ -68,6 +69,14 @@ void gf_oracle_cubic_spline_coefficients(const double* mesh, size_t step, size_t
 void gf_oracle_undistort_points_rs(const gf_compute_params* cp, int distortion_model, int digital_lens,
                                    const float* distorted, size_t n, double timestamp_ms, size_t frame,
                                    double lens_correction_amount, float* out);
+/* the same with at_timestamp_for_points' `use_fovs` flag (frame_transform.rs:352, :361) */
+void gf_oracle_undistort_points_rs_ex(const gf_compute_params* cp, int distortion_model, int digital_lens,
+                                      const float* distorted, size_t n, double timestamp_ms, size_t frame,
+                                      double lens_correction_amount, int use_fovs, float* out);
+/* ST maps — stmap.rs:86-136: the "undistort" closure over P->width x P->height (:86-109) and the "redistort" closure over
+ * cp->width x cp->height (:112-116), both encoded as RGB f32 like parallel_exr (:131-135). */
+void gf_oracle_stmap_undistort(const gf_kernel_params* P, const float* matrices, int distortion_model, int digital_lens, float* out_rgb);
+void gf_oracle_stmap_distort(const gf_compute_params* cp, int distortion_model, int digital_lens, double timestamp_ms, size_t frame, float* out_rgb);
 /* FovIterative::find_fov — zooming/fov_iterative.rs:91-134 for one frame; `cp` already has output = input size and
  * fov_scale = 1 (calculate_fovs, zooming/mod.rs:41-49), org_output_* is the real output size, margin = fov_algorithm_margin. */
 double gf_oracle_find_fov(const gf_compute_params* cp, int distortion_model, int digital_lens,

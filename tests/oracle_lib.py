@@ -44,6 +44,12 @@ def load():
     lib.gf_oracle_interpolate_mesh.argtypes = [C.c_double, C.c_double, C.c_void_p, P(C.c_double), P(C.c_double)]
     lib.gf_oracle_find_fov.restype = C.c_double
     lib.gf_oracle_find_fov.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_size_t]
+    lib.gf_oracle_undistort_points_rs_ex.restype = None
+    lib.gf_oracle_undistort_points_rs_ex.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_size_t, C.c_double, C.c_int, C.c_void_p]
+    lib.gf_oracle_stmap_undistort.restype = None
+    lib.gf_oracle_stmap_undistort.argtypes = [P(abi.KernelParams), C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.gf_oracle_stmap_distort.restype = None
+    lib.gf_oracle_stmap_distort.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_double, C.c_size_t, C.c_void_p]
     lib.gf_oracle_undistort_points_rs.restype = None
     lib.gf_oracle_undistort_points_rs.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_size_t, C.c_double, C.c_void_p]
     lib.gf_oracle_zoom_dynamic.restype = None
