@@ -426,3 +426,46 @@ def test_kernel_variants_agree(monkeypatch):
     # on a frame whose samples are all interior is not guaranteed either -> compare against the oracle instead
     want2, got_gen, _ = run_both(dict(w=1280, h=720, params=dict(background_mode=1)))
     assert np.array_equal(want2, got_gen)
+
+
+# ---- randomized sweep ------------------------------------------------------------------------------------------------------
+_PAIRS = [("opencv_fisheye", d) for d in (None, "gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch")] + \
+         [("gopro", None), ("gopro", "gopro_warp")] + \
+         [(l, d) for l in ("opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony", "generic_polynomial") for d in (None, "digital_stretch")]
+
+
+def _random_case(rng):
+    lens, digital = _PAIRS[rng.integers(len(_PAIRS))]
+    pix = sorted(abi.PIXEL_TYPES)[rng.integers(len(abi.PIXEL_TYPES))]
+    w, h = int(rng.integers(8, 200)), int(rng.integers(8, 120))
+    c = dict(w=w, h=h, lens=lens, digital=digital, pix=pix, ts=float(rng.uniform(100, 3500)), fov=float(rng.choice([0.6, 1.0, 1.0, 1.5, 2.5])),
+             rs=bool(rng.integers(4) != 0), readout=float(rng.choice([16.0, 33.0, -12.0])), stride_pad=int(rng.choice([0, 0, 1, 3, 64])),
+             interp=str(rng.choice(["Bilinear", "Bilinear", "Bicubic", "Lanczos4"])))
+    params = {}
+    r = rng.integers(10)
+    if r == 0: params["background_mode"] = int(rng.integers(1, 4)); params["background_margin"] = 0.1; params["background_margin_feather"] = 0.05
+    if r == 1: params["input_rotation"] = float(rng.choice([90.0, 180.0, 270.0, 33.0]))
+    if r == 2: params["light_refraction_coefficient"] = 1.33
+    if r == 3: params["lens_correction_amount"] = float(rng.uniform(0.0, 0.9))
+    if r == 4: params["translation2d"] = [float(rng.uniform(-20, 20)), float(rng.uniform(-20, 20))]
+    if r == 5: params["r_limit"] = float(rng.uniform(0.5, 2.0))
+    if r == 6: params["input_horizontal_stretch"] = 1.1; params["input_vertical_stretch"] = 0.95
+    if r == 7: params["background"] = [float(x) for x in rng.uniform(0, 1, 4)]
+    if rng.integers(6) == 0: c["horizontal_rs"] = True
+    if rng.integers(8) == 0: c["ibis"] = True
+    if rng.integers(8) == 0: c["mesh"] = True; c["fpd"] = bool(rng.integers(2))
+    if rng.integers(8) == 0: c["flags"] = int(rng.choice([abi.FLAG_FIX_COLOR_RANGE, abi.FLAG_FILL_WITH_BACKGROUND, abi.FLAG_FRAMEBUFFER_INVERTED]))
+    if rng.integers(6) == 0:
+        mx, my = int(rng.integers(0, 9)), int(rng.integers(0, 9))
+        c["in_size"] = (w + 2 * mx, h + 2 * my); c["in_rect"] = (mx, my, w, h)
+        c["out_size"] = (w + mx, h + my); c["out_rect"] = (mx // 2, my // 2, w, h)
+    if params: c["params"] = params
+    return c
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomized_sweep(seed):
+    """40 random combinations per seed of lens / digital lens / pixel format / resampler / size / stride / rects / per-frame options."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(40):
+        assert_bit_exact(_random_case(rng))
