@@ -50,6 +50,7 @@ enum : uint32_t {
     F_T3D        = 1u << 20,  // translation3d != 0 (x + 0.0f only differs from x in the sign of zero, which no consumer sees)
     F_PIXLIMIT   = 1u << 21,  // pixel_value_limit below the format's maximum (the min() after sampling can bite)
     F_WILD       = 1u << 22,  // lens coefficients / translation2d / source mapping outside the magnitudes the packed fast paths assume
+    F_INTPRO     = 1u << 23,  // packed kernel: both output maps are the identity -> integer prologue (X2Hot below)
 };
 
 // Features the specialised ("lean") instantiation compiles out entirely.  The reference's OpenCL backend does the same
@@ -95,6 +96,14 @@ struct WarpArgs {
     int   u8_limit;                 // trunc(min(pixel_value_limit, 255)) for the integer u8 sampler
     int   src_rect[4];              // rx0, ry0, rx1, ry1
     int   interior_span[2];         // rx1 - 2 - rx0, ry1 - 2 - ry0: a bilinear footprint at (sx, sy) is interior iff (unsigned)(sx - rx0) <= span (both axes)
+    // packed kernel: per-frame integers that replace the float rect map + bounds test of :546-551 when both output maps are the
+    // identity (F_INTPRO), and the sampler's rect constants side by side (one 128-bit constant load)
+    struct X2Hot {
+        int x_off, y_off;           // opx == (float)(x + x_off), opy likewise (exact: integers below 2^24)
+        int x0, x1, y0, y1;         // pixel (x, y) is written iff x0 <= x < x1 and y0 <= y < y1 ...
+        int full_rows, last_cols;   // ... and it fits the buffer: y < full_rows, or y == full_rows and x < last_cols (short last row)
+        int rect[4];                // rx0, ry0, span_x, span_y
+    } hot;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -205,7 +205,7 @@ GF_DEV void shade_lean(bool ok, bool far, float u, float v, int wu, int wv, cons
         const int sx0 = wu >> 1, sy0 = wv >> 1;
         const int sx = sx0 >> 5, sy = sy0 >> 5;
         // interior_span < 2^17 (host): negative and >= 2^22 results of the rounding shortcut can never pass
-        const bool interior = ok & !far & ((unsigned)(sx - A.src_rect[0]) <= (unsigned)A.interior_span[0]) & ((unsigned)(sy - A.src_rect[1]) <= (unsigned)A.interior_span[1]);
+        const bool interior = ok & !far & ((unsigned)(sx - A.hot.rect[0]) <= (unsigned)A.hot.rect[2]) & ((unsigned)(sy - A.hot.rect[1]) <= (unsigned)A.hot.rect[3]);
         if (interior) {
             uint32_t N[C], s[C];
             sample_u8_bilinear<PIX>(sx0, sy0, A, N);
@@ -241,12 +241,22 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     const unsigned long long off_a = (unsigned long long)y0 * ostride + (unsigned long long)x * PIX::BYTES;
     const unsigned long long off_b = off_a + ostride;
     // lane validity: row exists, pixel fits in the buffer (short last row), bounds test of :551
-    const float opx = map_apply_int_lean((float)x, A.omap_x);
-    const float opy_a = map_apply_int_lean((float)y0, A.omap_y);
-    const float opy_b = map_apply_int_lean((float)(y0 + 1), A.omap_y);
-    const bool in_x = (opx >= 0.0f) & (as_i32(opx) < P.output_width);
-    const bool wr_a = in_x & (off_a + PIX::BYTES <= A.dst_len) & (opy_a >= 0.0f) & (as_i32(opy_a) < P.output_height);
-    const bool wr_b = in_x & ((y0 + 1) < A.out_rows) & (off_b + PIX::BYTES <= A.dst_len) & (opy_b >= 0.0f) & (as_i32(opy_b) < P.output_height);
+    float opx, opy_a, opy_b;
+    bool wr_a, wr_b;
+    if (A.feat & F_INTPRO) {                                 // identity rect maps: the same tests on integers (host: fill_uniforms)
+        const bool in_x = (x >= A.hot.x0) & (x < A.hot.x1);
+        const int y1 = y0 + 1;
+        wr_a = in_x & (y0 >= A.hot.y0) & (y0 < A.hot.y1) & ((y0 < A.hot.full_rows) | ((y0 == A.hot.full_rows) & (x < A.hot.last_cols)));
+        wr_b = in_x & (y1 >= A.hot.y0) & (y1 < A.hot.y1) & ((y1 < A.hot.full_rows) | ((y1 == A.hot.full_rows) & (x < A.hot.last_cols)));
+        opx = (float)(x + A.hot.x_off); opy_a = (float)(y0 + A.hot.y_off); opy_b = (float)(y1 + A.hot.y_off);
+    } else {
+        opx = map_apply_int_lean((float)x, A.omap_x);
+        opy_a = map_apply_int_lean((float)y0, A.omap_y);
+        opy_b = map_apply_int_lean((float)(y0 + 1), A.omap_y);
+        const bool in_x = (opx >= 0.0f) & (as_i32(opx) < P.output_width);
+        wr_a = in_x & (off_a + PIX::BYTES <= A.dst_len) & (opy_a >= 0.0f) & (as_i32(opy_a) < P.output_height);
+        wr_b = in_x & ((y0 + 1) < A.out_rows) & (off_b + PIX::BYTES <= A.dst_len) & (opy_b >= 0.0f) & (as_i32(opy_b) < P.output_height);
+    }
     if (!(wr_a | wr_b)) return;
 
     // undistort_coord, :421-517

@@ -32,6 +32,24 @@ __global__ void ks(float* out, const float* cptr, float a, float b) {
     float s = 0; for (int i = 0; i < 2 * CH; ++i) s += v[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// issue-slot model: does an FFMA2 (or an ALU instruction) block the issue port for its second cycle?  An FP stream interleaved 1:1
+// with an independent integer LOP3 stream: if the pair costs max(fp, int) the pipes overlap, if it costs the sum they do not.
+template <int MODE>   // 0: FFMA2 + LOP3, 1: FMUL/FADD + LOP3, 2: LOP3 only
+__global__ void kmix(float* out, float2 nz, float2 one, float2 a2, float2 b2, unsigned m) {
+    float2 v[CH]; unsigned w[CH];
+    for (int i = 0; i < CH; ++i) { v[i] = make_float2(threadIdx.x * 0.001f + 2 * i, threadIdx.x * 0.001f + 2 * i + 1); w[i] = threadIdx.x * 977u + i; }
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (MODE == 0) { v[i] = __ffma2_rn(v[i], a2, nz); w[i] = (w[i] ^ m) | (w[i] >> 31); v[i] = __ffma2_rn(v[i], one, b2); w[i] = (w[i] & ~m) ^ (w[i] << 1); }
+            if (MODE == 1) { v[i].x = v[i].x * a2.x; w[i] = (w[i] ^ m) | (w[i] >> 31); v[i].x = v[i].x + b2.x; w[i] = (w[i] & ~m) ^ (w[i] << 1); }
+            if (MODE == 2) { w[i] = (w[i] ^ m) | (w[i] >> 31); w[i] = (w[i] & ~m) ^ (w[i] << 1); }
+        }
+    }
+    float s = 0; for (int i = 0; i < CH; ++i) s += v[i].x + v[i].y + (float)w[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     float* d; cudaMalloc(&d, 148 * 8 * 256 * sizeof(float));
     float2 h[8] = {{-0.f, -0.f}, {-0.f, -0.f}, {1, 1}, {1, 1}, {1.0000001f, 1.0000001f}, {1.0000001f, 1.0000001f}, {1e-7f, 1e-7f}, {1e-7f, 1e-7f}};
@@ -50,6 +68,18 @@ int main() {
         const double cyc = ms * 1e-3 * 1.965e9 * 148 * 4;                                       // SMSP-cycles at 1.965 GHz
         const char* nm[4] = {"FFMA2 R,R,R       ", "FFMA2 const operand", "FMUL/FADD R,R     ", "FMUL/FADD const   "};
         printf("%s: %.3f ms  %.2f cycles per warp-instruction per SMSP\n", nm[mode], ms, cyc / warp_instr);
+    }
+    for (int mode = 0; mode < 3; ++mode) {
+        cudaEventRecord(e0);
+        if (mode == 0) kmix<0><<<148 * 8, 256>>>(d, h[0], h[2], h[4], h[6], 0x5a5a5a5au);
+        if (mode == 1) kmix<1><<<148 * 8, 256>>>(d, h[0], h[2], h[4], h[6], 0x5a5a5a5au);
+        if (mode == 2) kmix<2><<<148 * 8, 256>>>(d, h[0], h[2], h[4], h[6], 0x5a5a5a5au);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double groups = 148.0 * 8 * 8 * ITERS * 2.0 * CH;      // (fp op + int op) groups per launch
+        const double cyc = ms * 1e-3 * 1.965e9 * 148 * 4;
+        const char* nm[3] = {"FFMA2 + int ops interleaved", "FMUL/FADD + int ops        ", "int ops alone              "};
+        printf("%s: %.3f ms  %.2f cycles per (fp, int) group per SMSP\n", nm[mode], ms, cyc / groups);
     }
     return 0;
 }
