@@ -428,6 +428,40 @@ def test_kernel_variants_agree(monkeypatch):
     assert np.array_equal(want2, got_gen)
 
 
+def test_concurrent_contexts_from_host_threads():
+    """process_pixels holds only a read lock (lib.rs:931): several host threads drive their own wrappers at the same time.
+    Four threads, each with its own context / frame size / lens, 16 host-buffer frames each, all bit-exact."""
+    import threading
+    specs = [dict(w=640, h=360), dict(w=512, h=288, lens="sony", pix="Luma16"), dict(w=400, h=300, digital="gopro_superview", pix="UV8"),
+             dict(w=320, h=180, pix="RGBAf", interp="Lanczos4")]
+    errors = []
+
+    def worker(spec):
+        try:
+            p, src, m0, mesh, dst0, pix, lens, digital = cases.build(spec)
+            bufs_proto = (spec["w"], spec["h"])
+            got = dst0.copy()
+            bufs = g.Buffers(g.BufferDescription((bufs_proto[0], bufs_proto[1], p.stride), src), g.BufferDescription((bufs_proto[0], bufs_proto[1], p.output_stride), got))
+            w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+            for i in range(16):
+                pi, _, mi, _, _, _, _, _ = cases.build(dict(spec, ts=200.0 + 97.0 * i))
+                want = dst0.copy()
+                assert oracle_lib.undistort_image(src, want, pi, pix, lens, digital, mi, mesh) == 0
+                got[:] = dst0
+                w.undistort_image(bufs, g.FrameTransform(matrices=mi, kernel_params=pi, mesh_data=np.zeros(0, np.float32)))
+                n, mx = cases.compare(want, got, pix)
+                if n:
+                    errors.append((spec, i, n, mx)); break
+            w.close()
+        except Exception as e:       # noqa: BLE001 - reported below
+            errors.append((spec, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in specs]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errors, errors
+
+
 # ---- randomized sweep ------------------------------------------------------------------------------------------------------
 _PAIRS = [("opencv_fisheye", d) for d in (None, "gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch")] + \
          [("gopro", None), ("gopro", "gopro_warp")] + \
