@@ -70,6 +70,56 @@ template <> struct Lens2<GF_LENS_OPENCV_FISHEYE> {
     }
 };
 
+// sony.rs:65-89 — the same shape as the fisheye model with a six-term polynomial in theta (all-zero k is F_LENS_NOOP -> scalar kernels)
+template <> struct Lens2<GF_LENS_SONY> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 a = add(mul(x, x), mul(y, y));
+        if (TRUSTED) {
+            const float lo = fminf(fminf(z.x, z.y), fminf(a.x, a.y)), hi = fmaxf(fmaxf(z.x, z.y), fmaxf(a.x, a.y));
+            bad |= !(lo >= 0x1p-56f) | !(hi < 0x1p48f);
+        } else {
+            bad |= !(z.x >= 0x1p-56f) | !(z.x < 0x1p48f) | !(z.y >= 0x1p-56f) | !(z.y < 0x1p48f) |
+                   !in_window_r2(a.x) | !in_window_r2(a.y);
+        }
+        const f2 r = sqrt_seq(a);
+        const f2 theta = atanf2_core(r, GF_ATAN_TAB);
+        const f2 theta2 = mul(theta, theta), theta3 = mul(theta2, theta), theta4 = mul(theta2, theta2), theta5 = mul(theta2, theta3), theta6 = mul(theta3, theta3);
+        f2 td = add(mul(theta, bc(P.k[0])), mul(theta2, bc(P.k[1])));
+        td = add(td, mul(theta3, bc(P.k[2])));
+        td = add(td, mul(theta4, bc(P.k[3])));
+        td = add(td, mul(theta5, bc(P.k[4])));
+        td = add(td, mul(theta6, bc(P.k[5])));
+        const f2 scale = div_seq(td, r);
+        ox = mul(x, scale); oy = mul(y, scale);
+    }
+};
+
+// opencv_standard.rs:32-48 — rational radial term + tangential + thin-prism terms; the one division besides x/z, y/z is 1 / den
+template <> struct Lens2<GF_LENS_OPENCV_STANDARD> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        const float* k = P.k;
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 r2 = add(mul(x, x), mul(y, y)), r4 = mul(r2, r2), r6 = mul(r4, r2);
+        const f2 x2t = mul(bc(2.0f), x), y2t = mul(bc(2.0f), y);
+        const f2 a1 = mul(x2t, y), a2 = add(r2, mul(x2t, x)), a3 = add(r2, mul(y2t, y));
+        const f2 cdist = add(add(add(bc(1.0f), mul(bc(k[0]), r2)), mul(bc(k[1]), r4)), mul(bc(k[4]), r6));
+        const f2 den = add(add(add(bc(1.0f), mul(bc(k[5]), r2)), mul(bc(k[6]), r4)), mul(bc(k[7]), r6));
+        // z: divisor and the reference's `w > 0` test; den: divisor of 1 / den, any sign (NaN fails the integer window test)
+        bad |= !(z.x >= 0x1p-56f) | !(z.x < 0x1p48f) | !(z.y >= 0x1p-56f) | !(z.y < 0x1p48f) | !in_window(den.x) | !in_window(den.y);
+        const f2 icdist2 = div_seq(bc(1.0f), den);
+        const f2 xr = mul(mul(x, cdist), icdist2), yr = mul(mul(y, cdist), icdist2);
+        ox = add(add(add(add(xr, mul(bc(k[2]), a1)), mul(bc(k[3]), a2)), mul(bc(k[8]), r2)), mul(bc(k[9]), r4));
+        oy = add(add(add(add(yr, mul(bc(k[2]), a3)), mul(bc(k[3]), a1)), mul(bc(k[10]), r2)), mul(bc(k[11]), r4));
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // rotate_and_distort for two pixels — cpu_undistort.rs:133-228, lean feature set
 // (no translation3d, r_limit, refraction, mesh, digital lens, input stretch).

@@ -375,6 +375,21 @@ def test_packed_kernel_cold_path_on_unusual_tables(kind):
         assert_bit_exact(dict(w=640, h=360, rs=rs, matrix_hook=_wild(kind)))
 
 
+@pytest.mark.parametrize("lens", ["sony", "opencv_standard"])
+def test_packed_kernel_other_lens_models(lens):
+    """The packed kernel also carries the sony and opencv_standard models: ordinary frames, its cold path, all 8/16-bit/f32 layouts."""
+    for pix in ("RGBA8", "Luma8", "UV16", "RGBAf", "RGB8"):
+        assert_bit_exact(dict(w=640, h=360, lens=lens, pix=pix))
+    assert_bit_exact(dict(w=1280, h=720, lens=lens, ts=2222.0, readout=33.0))
+    assert_bit_exact(dict(w=640, h=360, lens=lens, rs=False))
+    assert_bit_exact(dict(w=640, h=360, lens=lens, fov=3.0))                                   # invalid (w <= 0) regions -> cold path
+    for kind in ("nan_row", "huge", "zero_w", "on_axis", "ibis_some"):
+        assert_bit_exact(dict(w=320, h=180, lens=lens, matrix_hook=_wild(kind)))
+    if lens == "opencv_standard":      # denominators of the rational term crossing zero / huge coefficients
+        assert_bit_exact(dict(w=640, h=360, lens=lens, fov=2.0, params=dict(k=[0.1, 0.01, 0.001, 0.001, 0.0, -3.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0])))
+        assert_bit_exact(dict(w=640, h=360, lens=lens, params=dict(k=[1e20, 0.0, 0.0, 0.0, 0.0, 1e20, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])))
+
+
 def test_packed_kernel_unusual_params():
     assert_bit_exact(dict(w=640, h=360, params=dict(pixel_value_limit=200.0)))
     assert_bit_exact(dict(w=640, h=360, params=dict(k=[1e30, -1e30, 0.0, 0.0] + [0.0] * 8)))
