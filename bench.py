@@ -196,12 +196,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--lens", default=None, help="override the config's lens model (side measurement), e.g. sony, opencv_standard")
     ap.add_argument("--planes", type=int, default=1, help="planes of this geometry per frame, rendered by one gf_cuda_undistort_planes_dev call (side measurement)")
     ap.add_argument("--interp", default="Bilinear", help="Bilinear (BASELINE), Bicubic, Lanczos4, 'EWA: Robidoux', ... (side measurement)")
     args = ap.parse_args()
     select_config(args.config)
-    global INTERP
+    global INTERP, LENS, WORKLOAD
     INTERP = args.interp
+    if args.lens:
+        LENS = args.lens; WORKLOAD = WORKLOAD.replace(CFG["lens"], args.lens)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
