@@ -120,6 +120,95 @@ template <> struct Lens2<GF_LENS_OPENCV_STANDARD> {
     }
 };
 
+// z window shared by the models below: divisor of x / z, y / z and the reference's `w > 0` test (:138)
+GF_DEV bool z_outside(f2 z) { return !(z.x >= 0x1p-56f) | !(z.x < 0x1p48f) | !(z.y >= 0x1p-56f) | !(z.y < 0x1p48f); }
+
+// poly3.rs:54-63
+template <> struct Lens2<GF_LENS_POLY3> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        bad |= z_outside(z);
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 poly2 = add(mul(bc(P.k[0]), add(mul(x, x), mul(y, y))), bc(1.0f));
+        ox = mul(x, poly2); oy = mul(y, poly2);
+    }
+};
+// poly5.rs:43-53
+template <> struct Lens2<GF_LENS_POLY5> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        bad |= z_outside(z);
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 ru2 = add(mul(x, x), mul(y, y));
+        const f2 poly4 = add(add(bc(1.0f), mul(bc(P.k[0]), ru2)), mul(mul(bc(P.k[1]), ru2), ru2));
+        ox = mul(x, poly4); oy = mul(y, poly4);
+    }
+};
+// ptlens.rs:42-53 — sqrt(ru2): ru2 == 0 is fine for the exact square-root sequence only inside its window, so ru2 is windowed too
+template <> struct Lens2<GF_LENS_PTLENS> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        bad |= z_outside(z);
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 ru2 = add(mul(x, x), mul(y, y));
+        bad |= !in_window(ru2.x) | !in_window(ru2.y);
+        const f2 r = sqrt_seq(ru2);
+        const f2 poly3 = add(add(add(mul(mul(bc(P.k[0]), ru2), r), mul(bc(P.k[1]), ru2)), mul(bc(P.k[2]), r)), bc(1.0f));
+        ox = mul(x, poly3); oy = mul(y, poly3);
+    }
+};
+// generic_polynomial.rs:83-122 — like sony with twelve terms (all-zero k is F_LENS_NOOP -> scalar kernels)
+template <> struct Lens2<GF_LENS_GENERIC_POLYNOMIAL> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        const float* k = P.k;
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 a = add(mul(x, x), mul(y, y));
+        bad |= z_outside(z) | !in_window_r2(a.x) | !in_window_r2(a.y);
+        const f2 r = sqrt_seq(a);
+        const f2 t = atanf2_core(r, GF_ATAN_TAB);
+        const f2 t2 = mul(t, t), t3 = mul(t2, t), t4 = mul(t2, t2), t5 = mul(t2, t3), t6 = mul(t3, t3), t7 = mul(t3, t4), t8 = mul(t4, t4),
+                 t9 = mul(t4, t5), t10 = mul(t5, t5), t11 = mul(t5, t6), t12 = mul(t6, t6);
+        f2 td = add(mul(t, bc(k[0])), mul(t2, bc(k[1])));
+        td = add(td, mul(t3, bc(k[2])));  td = add(td, mul(t4, bc(k[3])));  td = add(td, mul(t5, bc(k[4])));   td = add(td, mul(t6, bc(k[5])));
+        td = add(td, mul(t7, bc(k[6])));  td = add(td, mul(t8, bc(k[7])));  td = add(td, mul(t9, bc(k[8])));   td = add(td, mul(t10, bc(k[9])));
+        td = add(td, mul(t11, bc(k[10]))); td = add(td, mul(t12, bc(k[11])));
+        const f2 scale = div_seq(td, r);
+        ox = mul(x, scale); oy = mul(y, scale);
+    }
+};
+// insta360.rs:27-48 — unified (Mei) model: len = |(x, y, z)|, x' = (x / len) / (z / len + xi)
+template <> struct Lens2<GF_LENS_INSTA360> {
+    static constexpr bool kHas = true;
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        const f2 k1 = bc(P.k[0]), k2 = bc(P.k[1]), k3 = bc(P.k[2]), p1 = bc(P.k[3]), p2v = bc(P.k[4]), xi = bc(P.k[5]);
+        const f2 l2 = add(add(mul(x, x), mul(y, y)), mul(z, z));
+        bad |= z_outside(z) | !in_window(l2.x) | !in_window(l2.y);       // z > 0 is the reference's test; l2 feeds the square root
+        const f2 len = sqrt_seq(l2);                                       // in [2^-30, 2^30]: a valid divisor
+        const f2 den = add(div_seq(z, len), xi);
+        bad |= !in_window(den.x) | !in_window(den.y);
+        const f2 xn = div_seq(x, len), yn = div_seq(y, len);
+        // second-stage numerators can be far smaller than the matrix products (|x| / len): keep them zero or inside the window
+        bad |= !zero_or_in_window(xn.x) | !zero_or_in_window(xn.y) | !zero_or_in_window(yn.x) | !zero_or_in_window(yn.y);
+        x = div_seq(xn, den);
+        y = div_seq(yn, den);
+        const f2 r2 = add(mul(x, x), mul(y, y)), r4 = mul(r2, r2), r6 = mul(r4, r2);
+        const f2 rad = add(add(add(bc(1.0f), mul(k1, r2)), mul(k2, r4)), mul(k3, r6));
+        ox = add(add(mul(x, rad), mul(mul(mul(bc(2.0f), p1), x), y)), mul(p2v, add(r2, mul(mul(bc(2.0f), x), x))));
+        oy = add(add(mul(y, rad), mul(mul(mul(bc(2.0f), p2v), x), y)), mul(p1, add(r2, mul(mul(bc(2.0f), y), y))));
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // rotate_and_distort for two pixels — cpu_undistort.rs:133-228, lean feature set
 // (no translation3d, r_limit, refraction, mesh, digital lens, input stretch).

@@ -375,9 +375,9 @@ def test_packed_kernel_cold_path_on_unusual_tables(kind):
         assert_bit_exact(dict(w=640, h=360, rs=rs, matrix_hook=_wild(kind)))
 
 
-@pytest.mark.parametrize("lens", ["sony", "opencv_standard"])
+@pytest.mark.parametrize("lens", ["sony", "opencv_standard", "poly3", "poly5", "ptlens", "generic_polynomial", "insta360"])
 def test_packed_kernel_other_lens_models(lens):
-    """The packed kernel also carries the sony and opencv_standard models: ordinary frames, its cold path, all 8/16-bit/f32 layouts."""
+    """The packed kernel also carries these lens models: ordinary frames, its cold path, all 8/16-bit/f32 layouts."""
     for pix in ("RGBA8", "Luma8", "UV16", "RGBAf", "RGB8"):
         assert_bit_exact(dict(w=640, h=360, lens=lens, pix=pix))
     assert_bit_exact(dict(w=1280, h=720, lens=lens, ts=2222.0, readout=33.0))
