@@ -344,7 +344,7 @@ def main():
         except Exception: pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         abytes = algorithmic_bytes(p, rows, mesh_np.size if mesh_np is not None else 0, NPL)
-        launch_ms = total_ms / max(launches, 1) * (1 + NPL if NPL > 1 else 1)      # multi-plane frames: the frame's 1 + NPL launches together
+        launch_ms = total_ms / max(args.steps * FRAMES_PER_STEP, 1)      # per frame: one launch for the headline config; coordinate + sampling passes otherwise
         achieved = abytes / (launch_ms / 1e3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:

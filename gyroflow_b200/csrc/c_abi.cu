@@ -502,8 +502,16 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const dim3 block(GF_BLOCK_X, GF_BLOCK_Y);
     const dim3 grid((A.out_cols + GF_BLOCK_X - 1) / GF_BLOCK_X, (A.out_rows + GF_BLOCK_Y - 1) / GF_BLOCK_Y);
     if (grid.x == 0 || grid.y == 0 || grid.y > 65535) return fail(ctx, GF_ERR_BAD_PARAMS, "output buffer geometry out of range");
-    if (more_planes > 0 || coord_only) {
-        const size_t need = (size_t)A.out_cols * (size_t)A.out_rows;
+    // Two-pass mode: coordinates into a device map (pass 1), then sampling from the map (pass 2, shade_from_coords_kernel).  Used for
+    // multi-plane frames, for every resampler other than bilinear (so that the 16/64-tap and EWA code lives in 11 sampling kernels
+    // instead of every lens instantiation) and for ST maps (pass 1 only).  EWA needs three coordinate maps (pixel + two probes).
+    const bool ewa = p->interpolation > 8;
+    const bool two_pass = more_planes > 0 || coord_only || p->interpolation != GF_INTERP_BILINEAR;
+    const int n_maps = (ewa && !coord_only) ? 3 : 1;
+    const size_t map_len = (size_t)A.out_cols * (size_t)A.out_rows;
+    if (two_pass) {
+        if (!ctx->fn_shade && !coord_only) return fail(ctx, GF_ERR_UNSUPPORTED_COMBO, "no sampling kernel for this pixel layout");
+        const size_t need = map_len * (size_t)n_maps;
         if (need > ctx->d_coords_len) {
             if (ctx->d_coords) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_coords); ctx->d_coords = nullptr; ctx->d_coords_len = 0; }
             CK(cudaMalloc(&ctx->d_coords, need * sizeof(uint2)));
@@ -515,21 +523,28 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
     // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
-    KernelFn x2 = ((A.feat & F_WILD) != 0 || more_planes > 0 || coord_only) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
+    KernelFn x2 = ((A.feat & F_WILD) != 0 || two_pass) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
     if (lean_ok && x2) {
         const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
         x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;
     }
-    else if (lean_ok) { ctx->fn_lean<<<grid, block, 0, st>>>(A); ctx->lean_launches++; }
-    else         { ctx->fn<<<grid, block, 0, st>>>(A); }
+    else {
+        for (int mi = 0; mi < n_maps; ++mi) {                  // one launch, or three for EWA (pixel, x-probe, y-probe)
+            if (two_pass) { A.coord_out = ctx->d_coords + (size_t)mi * map_len; A.coord_shift = mi; }
+            if (lean_ok) { ctx->fn_lean<<<grid, block, 0, st>>>(A); ctx->lean_launches++; }
+            else         { ctx->fn<<<grid, block, 0, st>>>(A); }
+            CK(cudaGetLastError());
+            if (mi > 0) ctx->launches++;
+        }
+    }
     CK(cudaGetLastError());
     ctx->launches++;
-    if (more_planes > 0) {                                     // pass 2: one sampling-only launch per plane
+    if (two_pass && !coord_only) {                             // pass 2: one sampling-only launch per plane
         for (size_t i = 0; i <= more_planes; ++i) {
             WarpArgs B = A;
             B.p = p[i];
-            B.coord_out = nullptr; B.coord_in = ctx->d_coords;
-            B.src = (const uint8_t*)in[i].ptr; B.dst = (uint8_t*)out[i].ptr; B.src_len = in[i].len; B.dst_len = out[i].len;
+            B.coord_out = nullptr; B.coord_in = ctx->d_coords; B.coord_maps = n_maps; B.coord_shift = 0;
+            if (more_planes > 0) { B.src = (const uint8_t*)in[i].ptr; B.dst = (uint8_t*)out[i].ptr; B.src_len = in[i].len; B.dst_len = out[i].len; }
             fill_uniforms(B, ctx, B.src, B.dst);
             ctx->fn_shade<<<grid, block, 0, st>>>(B);
             CK(cudaGetLastError());
@@ -697,8 +712,8 @@ GF_API int gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const
         if (in[i].kind != GF_BUF_DEVICE || out[i].kind != GF_BUF_DEVICE) return fail(ctx, GF_ERR_BAD_PARAMS, "gf_cuda_undistort_planes_dev takes DEVICE buffers");
         int rc = validate(ctx, &params[i], &in[i], &out[i], ctx->bpp); if (rc != GF_OK) return rc;
     }
-    // one coordinate pass for all planes when they share a geometry; EWA needs a per-pixel Jacobian the map does not carry
-    const bool fuse = n_planes > 1 && ctx->fn_shade && params[0].interpolation <= 8 && planes_share_geometry(params, in, out, n_planes);
+    // one coordinate pass for all planes when they share a geometry
+    const bool fuse = n_planes > 1 && ctx->fn_shade && planes_share_geometry(params, in, out, n_planes);
     if (fuse) return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, n_planes - 1);
     for (size_t i = 0; i < n_planes; ++i) {
         int rc = run_warp(ctx, &in[i], &out[i], &params[i], matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream);

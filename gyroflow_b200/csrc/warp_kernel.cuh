@@ -77,7 +77,9 @@ struct WarpArgs {
     const double*  mesh64;          // the same values widened to f64 by a helper kernel before the launch (cpu_undistort.rs:539)
     const struct MeshAux* mesh_aux; // per-frame constants derived from the mesh header by the same helper kernel
     uint2*         coord_out;       // multi-plane mode, pass 1: write the source coordinates of every output pixel here instead of sampling
-    const uint2*   coord_in;        // multi-plane mode, pass 2 (shade_from_coords_kernel): read them back
+    const uint2*   coord_in;        // pass 2 (shade_from_coords_kernel): read them back
+    int            coord_shift;     // pass 1: 0 = pixel (x, y); 1 = (x + 0.01, y); 2 = (x, y + 0.01) — the EWA Jacobian probes of :567-572
+    int            coord_maps;      // pass 2: 1, or 3 when the two probe maps follow the first one (stride out_cols * out_rows)
     unsigned long long src_len, dst_len;
     int   mesh_len;
     int   out_rows;                 // ceil(dst_len / output_stride): rows the reference iterates (par_chunks_mut)
@@ -849,9 +851,12 @@ static __device__ __noinline__ void sample_high_order(float uvx, float uvy, floa
     else                                              sample_ewa<PIX>(uvx, uvy, jac, A, sum);
 }
 
-template <int I, class PIX, bool GEN>
+// HI: may the resampler be anything but bilinear?  Only the coordinate-map shading kernel says yes; the fused warp kernels are
+// bilinear-only (the host routes every other resampler through the two-pass path), which keeps the 64-tap / EWA code and
+// its call out of all per-lens instantiations.
+template <int I, class PIX, bool GEN, bool HI = false>
 GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT], float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f)) {
-    if (I == 2 && A.p.interpolation != GF_INTERP_BILINEAR) { sample_high_order<PIX>(uvx, uvy, jac, A, sum); return; }
+    if (HI && I == 2 && A.p.interpolation != GF_INTERP_BILINEAR) { sample_high_order<PIX>(uvx, uvy, jac, A, sum); return; }
     const float offset = I == 2 ? 0.0f : (I == 4 ? 1.0f : 3.0f);
     const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
     const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
@@ -873,7 +878,7 @@ GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum
 enum { GF_COORD_NONE = 1, GF_COORD_SKIP = 2, GF_COORD_FILL = 3 };     // undistort_coord returned None / pixel not written / fill-with-background
 
 // cpu_undistort.rs:576-622 — everything after undistort_coord for one output pixel: feather mode, sampling, range fix, store.
-template <class PIX, bool GEN>
+template <class PIX, bool GEN, bool HI>
 GF_DEV void finish_pixel(bool have_uv, float u, float v, float4 jac, const WarpArgs& A, uint8_t* __restrict__ out) {
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;
@@ -899,12 +904,12 @@ GF_DEV void finish_pixel(bool have_uv, float u, float v, float4 jac, const WarpA
             u   = map_apply(u,   A.smap_x); v   = map_apply(v,   A.smap_y);
             p2x = map_apply(p2x, A.smap_x); p2y = map_apply(p2y, A.smap_y);
             float c1[C], c2[C];
-            sample_input_at<I, PIX, GEN>(u, v, A, c1, jac);
-            sample_input_at<I, PIX, GEN>(p2x, p2y, A, c2, jac);          // (the reference notes jac should be adjusted for pt2; it is not)
+            sample_input_at<I, PIX, GEN, HI>(u, v, A, c1, jac);
+            sample_input_at<I, PIX, GEN, HI>(p2x, p2y, A, c2, jac);          // (the reference notes jac should be adjusted for pt2; it is not)
             #pragma unroll
             for (int ch = 0; ch < C; ++ch) pixel[ch] = c1[ch] * alpha + c2[ch] * (1.0f - alpha);
         } else {
-            if (PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && P.interpolation == GF_INTERP_BILINEAR) {
+            if (PIX::SCALAR == SC_U8 && !has<GEN>(feat, F_FIXRANGE) && (!HI || P.interpolation == GF_INTERP_BILINEAR)) {
                 // 8-bit bilinear interior: integer arithmetic, exact (see sample_u8_bilinear)
                 const int sx0 = as_i32(rs_round(u * 32.0f)), sy0 = as_i32(rs_round(v * 32.0f));
                 const int sx = sx0 >> 5, sy = sy0 >> 5;
@@ -919,7 +924,7 @@ GF_DEV void finish_pixel(bool have_uv, float u, float v, float4 jac, const WarpA
                 }
                 sample_generic<I, PIX>(sx0, sy0, A, pixel);
             } else {
-                sample_input_at<I, PIX, GEN>(u, v, A, pixel, jac);                                               // :615
+                sample_input_at<I, PIX, GEN, HI>(u, v, A, pixel, jac);                                           // :615
             }
         }
     }
@@ -957,29 +962,16 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
         return;
     }
 
-    // :565; for EWA (interpolation > 8) the forward-difference Jacobian of :567-572 comes from two more
-    // evaluations at (x + eps, y) and (x, y + eps), run through the same (single) inlined copy of undistort_coord
+    // :565.  Pass 1 of the two-pass mode may ask for one of the EWA Jacobian probe positions (x + eps, y) / (x, y + eps), :567-572
     float u = 0.0f, v = 0.0f;
-    bool have_uv = false;
-    float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
-    const int npos = P.interpolation > 8 ? 3 : 1;
-    #pragma unroll 1
-    for (int j = 0; j < npos; ++j) {
-        const float eps = 0.01f;
-        const float qx = j == 1 ? map_apply((float)x + eps, A.omap_x) : opx;
-        const float qy = j == 2 ? map_apply((float)y + eps, A.omap_y) : opy;
-        float tu, tv;
-        const bool ok = undistort_coord<LENS, DIGITAL, GEN>(qx, qy, A, tu, tv);
-        if (j == 0) { if (!ok) break; u = tu; v = tv; have_uv = true; continue; }
-        if (!ok) { tu = 0.0f; tv = 0.0f; }                                                                           // unwrap_or_default()
-        if (j == 1) { jac.x = (tu - u) / eps; jac.z = (tv - v) / eps; }
-        else        { jac.y = (tu - u) / eps; jac.w = (tv - v) / eps; }
-    }
-    if (cmap) {      // pass 1 of the multi-plane mode: the planes of one frame share these coordinates (the host checks that they do)
+    const float qx = (cmap && A.coord_shift == 1) ? map_apply((float)x + 0.01f, A.omap_x) : opx;
+    const float qy = (cmap && A.coord_shift == 2) ? map_apply((float)y + 0.01f, A.omap_y) : opy;
+    const bool have_uv = undistort_coord<LENS, DIGITAL, GEN>(qx, qy, A, u, v);
+    if (cmap) {      // pass 1 of the two-pass mode (multi-plane frames, non-bilinear resamplers, ST maps)
         *cmap = have_uv ? make_uint2(__float_as_uint(u), __float_as_uint(v)) : make_uint2(GF_COORD_MARK, GF_COORD_NONE);
         return;
     }
-    finish_pixel<PIX, GEN>(have_uv, u, v, jac, A, out);
+    finish_pixel<PIX, GEN, false>(have_uv, u, v, make_float4(1.0f, 0.0f, 0.0f, 1.0f), A, out);
 }
 
 // Pass 2 of the multi-plane mode: one launch per plane, coordinates from the map — sampling, conversion and store only.
@@ -1002,7 +994,17 @@ shade_from_coords_kernel(const __grid_constant__ WarpArgs A) {
         PIX::store(out, (A.feat & F_DST_VEC) != 0, pixel);
         return;
     }
-    finish_pixel<PIX, true>(!marked, __uint_as_float(e.x), __uint_as_float(e.y), make_float4(1.0f, 0.0f, 0.0f, 1.0f), A, out);
+    const float u = __uint_as_float(e.x), v = __uint_as_float(e.y);
+    float4 jac = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
+    if (!marked && A.coord_maps == 3) {                        // :567-572: forward differences over eps = 0.01, None -> (0, 0)
+        const size_t plane = (size_t)A.out_cols * (size_t)A.out_rows, i = (size_t)y * (size_t)A.out_cols + (size_t)x;
+        const uint2 ex = __ldg(A.coord_in + plane + i), ey = __ldg(A.coord_in + 2 * plane + i);
+        const float eps = 0.01f;
+        const float xu = ex.x == GF_COORD_MARK ? 0.0f : __uint_as_float(ex.x), xv = ex.x == GF_COORD_MARK ? 0.0f : __uint_as_float(ex.y);
+        const float yu = ey.x == GF_COORD_MARK ? 0.0f : __uint_as_float(ey.x), yv = ey.x == GF_COORD_MARK ? 0.0f : __uint_as_float(ey.y);
+        jac = make_float4((xu - u) / eps, (yu - u) / eps, (xv - v) / eps, (yv - v) / eps);
+    }
+    finish_pixel<PIX, true, true>(!marked, u, v, jac, A, out);
 }
 
 } // namespace gf

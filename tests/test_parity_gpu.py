@@ -26,7 +26,9 @@ def run_both(case, device_buffers=False):
         bufs = g.Buffers(g.BufferDescription((bw, bh, p.stride), src), g.BufferDescription((obw, obh, p.output_stride), got))
         w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
         w.undistort_image(bufs, itm)
-        assert w.launch_count == 1
+        # bilinear: one fused launch; other resamplers: coordinate pass(es) + sampling pass (EWA: pixel + two Jacobian probes)
+        interp = case.get("interp", "Bilinear")
+        assert w.launch_count == (1 if interp == "Bilinear" else (4 if interp.startswith("EWA") else 2)), w.launch_count
         w.close()
     else:
         import torch
@@ -206,7 +208,10 @@ def _run_planes(case, n_planes, vary=None):
 
 def _assert_planes(case, n_planes, fused, vary=None):
     outs, launches, pix = _run_planes(case, n_planes, vary)
-    assert launches == (1 + n_planes if fused else n_planes), launches
+    interp = case.get("interp", "Bilinear")
+    coord_passes = 3 if interp.startswith("EWA") else 1
+    single = 1 if interp == "Bilinear" else coord_passes + 1
+    assert launches == (coord_passes + n_planes if fused else n_planes * single), launches
     for i, (want, got) in enumerate(outs):
         n, mx = cases.compare(want, got, pix)
         assert n == 0, "plane %d: %d mismatching bytes (max abs diff %s) for %r" % (i, n, mx, case)
@@ -233,8 +238,8 @@ def test_fused_planes_options():
     _assert_planes(dict(w=320, h=180, pix="Luma8", params=dict(background_mode=3, background_margin=0.1, background_margin_feather=0.1), fov=1.6), 2, fused=True)
     _assert_planes(dict(w=320, h=180, pix="Luma8", flags=abi.FLAG_FILL_WITH_BACKGROUND, params=dict(background=[0.3, 0.3, 0.3, 1.0])), 2, fused=True)
     _assert_planes(dict(w=203, h=117, pix="UV8", stride_pad=2), 2, fused=True)
-    # not fusable: EWA, and planes whose parameters differ -> n ordinary launches, same results
-    _assert_planes(dict(w=200, h=120, pix="Luma8", interp="EWA: Mitchell"), 2, fused=False)
+    _assert_planes(dict(w=200, h=120, pix="Luma8", interp="EWA: Mitchell"), 2, fused=True)         # three coordinate maps, shared
+    # not fusable: planes whose parameters differ -> n ordinary calls, same results
     diff = lambda p, i: setattr(p, "lens_correction_amount", 1.0 if i == 0 else 0.5)
     _assert_planes(dict(w=320, h=180, pix="Luma8"), 2, fused=False, vary=diff)
 
