@@ -46,6 +46,7 @@ struct gf_cuda_ctx {
     KernelFn fn_lean = nullptr;   // rare features compiled out
     KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe (unvalidated tables)
     KernelFn fn_x2t = nullptr;    // same, tables validated: no per-pixel numerator / IBIS tests
+    KernelFn fn_x2c = nullptr, fn_x2ct = nullptr;   // the packed kernel writing a coordinate map (pass 1 of the two-pass path)
     std::unordered_map<const void*, uint32_t> validated;   // device tables vouched for by gf_cuda_validate_tables_dev
     unsigned* d_vflags = nullptr;
     uint2* d_coords = nullptr; size_t d_coords_len = 0;   // multi-plane mode: the frame's coordinate map
@@ -368,6 +369,7 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
     ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_x2t = fn_x2t; ctx->fn_shade = gf_shade_kernel(layout);
+    if (!getenv("GF_DISABLE_X2")) { ctx->fn_x2c = find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, 4); ctx->fn_x2ct = find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, 5); }
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -523,7 +525,9 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
     // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
-    KernelFn x2 = ((A.feat & F_WILD) != 0 || two_pass) ? nullptr : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
+    // (two-pass: the coordinate-writing variant, except for EWA whose probe positions only the scalar kernels evaluate)
+    KernelFn x2 = ((A.feat & F_WILD) != 0 || (two_pass && n_maps != 1)) ? nullptr
+                : two_pass ? ((table_flags == 0) ? ctx->fn_x2ct : ctx->fn_x2c) : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
     if (lean_ok && x2) {
         const dim3 grid2(grid.x, (A.out_rows + GF_X2_ROWS_PER_BLOCK - 1) / GF_X2_ROWS_PER_BLOCK);
         x2<<<grid2, block, 0, st>>>(A); ctx->x2_launches++;

@@ -33,6 +33,8 @@ KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp, int l
 KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
 KernelFn gf_shade_kernel(int layout);      // pass 2 of the multi-plane mode (shade_kernel.cu)
 
+// lean == 4 / 5: the packed kernel in coordinate-output mode (pass 1 of the two-pass path), untrusted / trusted tables; one
+// instantiation per lens model serves every pixel layout
 // lean == 2 / 3: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form;
 // 3 = tables validated (no wild entries, no IBIS rows), 2 = unvalidated device tables (per-pixel numerator / IBIS tests kept)
 template <int LENS, int DIGITAL, class PIX>
@@ -45,6 +47,10 @@ static KernelFn pick_x2(int interp, bool trusted) {
 }
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
+    if (lean == 4 || lean == 5) {
+        if constexpr (Lens2<LENS>::kHas && DIGITAL == GF_LENS_NONE) return lean == 5 ? warp_kernel_x2<LENS, Pix<1, SC_U8>, 6, true, true> : warp_kernel_x2<LENS, Pix<1, SC_U8>, 6, false, true>;
+        return nullptr;
+    }
     if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp, false);
     if (lean == 3) return pick_x2<LENS, DIGITAL, PIX>(interp, true);
     switch (interp) {

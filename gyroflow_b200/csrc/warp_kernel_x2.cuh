@@ -368,7 +368,9 @@ GF_DEV void shade_lean(bool ok, bool far, float u, float v, int wu, int wv, cons
 
 #define GF_X2_ROWS_PER_BLOCK (2 * GF_BLOCK_Y)
 
-template <int LENS, class PIX, int MINB, bool TRUSTED>
+// COORD: pass 1 of the two-pass mode — write the coordinates to A.coord_out instead of sampling (pixel-format independent: the
+// pixel size then comes from KernelParams, PIX is a placeholder).
+template <int LENS, class PIX, int MINB, bool TRUSTED, bool COORD = false>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     using namespace p2;
@@ -376,8 +378,9 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
     const int y0 = (blockIdx.y * GF_BLOCK_Y + threadIdx.y) * 2;
     if (x >= A.out_cols || y0 >= A.out_rows) return;
+    const unsigned long long BYTES = COORD ? (unsigned long long)P.bytes_per_pixel : (unsigned long long)PIX::BYTES;
     const unsigned long long ostride = (unsigned long long)P.output_stride;
-    const unsigned long long off_a = (unsigned long long)y0 * ostride + (unsigned long long)x * PIX::BYTES;
+    const unsigned long long off_a = (unsigned long long)y0 * ostride + (unsigned long long)x * BYTES;
     const unsigned long long off_b = off_a + ostride;
     // lane validity: row exists, pixel fits in the buffer (short last row), bounds test of :551
     float opx, opy_a, opy_b;
@@ -393,10 +396,15 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
         opy_a = map_apply_int_lean((float)y0, A.omap_y);
         opy_b = map_apply_int_lean((float)(y0 + 1), A.omap_y);
         const bool in_x = (opx >= 0.0f) & (as_i32(opx) < P.output_width);
-        wr_a = in_x & (off_a + PIX::BYTES <= A.dst_len) & (opy_a >= 0.0f) & (as_i32(opy_a) < P.output_height);
-        wr_b = in_x & ((y0 + 1) < A.out_rows) & (off_b + PIX::BYTES <= A.dst_len) & (opy_b >= 0.0f) & (as_i32(opy_b) < P.output_height);
+        wr_a = in_x & (off_a + BYTES <= A.dst_len) & (opy_a >= 0.0f) & (as_i32(opy_a) < P.output_height);
+        wr_b = in_x & ((y0 + 1) < A.out_rows) & (off_b + BYTES <= A.dst_len) & (opy_b >= 0.0f) & (as_i32(opy_b) < P.output_height);
     }
-    if (!(wr_a | wr_b)) return;
+    uint2* const cm_a = COORD ? A.coord_out + ((size_t)y0 * (size_t)A.out_cols + (size_t)x) : nullptr;
+    const bool row_b = (y0 + 1) < A.out_rows;
+    if (!(wr_a | wr_b)) {
+        if (COORD) { *cm_a = make_uint2(GF_COORD_MARK, GF_COORD_SKIP); if (row_b) cm_a[A.out_cols] = make_uint2(GF_COORD_MARK, GF_COORD_SKIP); }
+        return;
+    }
 
     // undistort_coord, :421-517
     const float pxs = opx + P.translation2d[0];
@@ -429,6 +437,11 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
         u = mk(c.ua, c.ub); v = mk(c.va, c.vb);
     }
 
+    if (COORD) {      // the exact coordinates (hot or cold path alike); None / not-written pixels as markers
+        *cm_a = !wr_a ? make_uint2(GF_COORD_MARK, GF_COORD_SKIP) : (ok_a ? make_uint2(__float_as_uint(u.x), __float_as_uint(v.x)) : make_uint2(GF_COORD_MARK, GF_COORD_NONE));
+        if (row_b) cm_a[A.out_cols] = !wr_b ? make_uint2(GF_COORD_MARK, GF_COORD_SKIP) : (ok_b ? make_uint2(__float_as_uint(u.y), __float_as_uint(v.y)) : make_uint2(GF_COORD_MARK, GF_COORD_NONE));
+        return;
+    }
     int wu_a = 0, wu_b = 0, wv_a = 0, wv_b = 0;
     if (PIX::SCALAR == SC_U8) {                          // (u * 32).round() for both pixels: 64 * u == 2 * (32 * u) exactly.
         // |u|, |v| < 2^16 here unless far_* is set (then the result is not used), so the unguarded form of the shortcut applies;
