@@ -81,29 +81,42 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        """Started before the warm-up so that nvidia-smi is already streaming when the (sub-second) timed region begins."""
+        self.t0 = self.t1 = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append((time.perf_counter(), l)) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self): self.t0 = time.perf_counter()
+    def mark_end(self): self.t1 = time.perf_counter()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)                                   # let the last sample of the timed region arrive
         self.proc.terminate()
         try: self.proc.wait(timeout=2)
         except Exception: pass
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = (self.t1 if self.t1 is not None else time.perf_counter()) + 0.03
+        inside = [l for (t, l) in self.lines if t0 <= t <= t1]
+        window = "timed region"
+        if len(inside) < 2:                                # region shorter than the sampling period: the GPU was equally busy during warm-up
+            inside = [l for (t, l) in self.lines if t <= t1][-8:]
+            window = "timed region + the warm-up before it (region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
-        for l in self.lines:
+        for l in inside:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7: continue
             try: sm.append(float(f[0])); mx = float(f[1])
             except ValueError: continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"): reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def base_params():
@@ -274,20 +287,22 @@ def main():
                 ctx.undistort_planes_dev(all_bufs[b0:b0 + NPL], plane_params, mats[i % N_TIMESTAMPS].data_ptr(), rows,
                                          mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
 
+    clocks = ClockSampler(local); clocks.start()
     torch.cuda.synchronize()
-    for s in range(args.warmup):
+    for s in range(max(args.warmup, 3)):              # never fewer than 3 warm-up steps
         step(s)
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
-    clocks = ClockSampler(local); clocks.start()
     l0 = ctx.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
+    clocks.mark_begin()
     for s in range(args.steps):
         ev[s][0].record(tstream)
         step(s)
         ev[s][1].record(tstream)
     torch.cuda.synchronize()
+    clocks.mark_end()
     if world > 1: dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     clk = clocks.stop()
@@ -354,7 +369,7 @@ def main():
             cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "4 full 4K frames of the same workload (C port of cpu_undistort.rs, row-parallel over all host threads)"}
         out = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if INTERP == "Bilinear" else WORKLOAD.replace("bilinear", INTERP), "frame_bytes_in": int(H * p.stride), "frames_per_step": FRAMES_PER_STEP, "frames_per_step_per_gpu": FRAMES_PER_STEP,
                        "l2_policy": "inputs larger than L2: %d-frame ring of %.1f MB inputs (%d MB) + %d distinct matrix tables" % (RING, H * p.stride / 1e6, RING * H * p.stride // 1000000, N_TIMESTAMPS),
