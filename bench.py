@@ -88,11 +88,16 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append((time.perf_counter(), l)) for l in self.proc.stdout], daemon=True)
             self.t.start()
+            t_wait = time.perf_counter()
+            while not self.lines and time.perf_counter() - t_wait < 2.0:     # nvidia-smi takes a few hundred ms to print its first line
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def mark_begin(self): self.t0 = time.perf_counter()
     def mark_end(self): self.t1 = time.perf_counter()
+    def samples_inside(self):
+        return sum(1 for (t, _) in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or time.perf_counter()) + 0.03)
 
     def stop(self):
         if not self.proc:
@@ -105,9 +110,9 @@ class ClockSampler:
         t1 = (self.t1 if self.t1 is not None else time.perf_counter()) + 0.03
         inside = [l for (t, l) in self.lines if t0 <= t <= t1]
         window = "timed region"
-        if len(inside) < 2:                                # region shorter than the sampling period: the GPU was equally busy during warm-up
-            inside = [l for (t, l) in self.lines if t <= t1][-8:]
-            window = "timed region + the warm-up before it (region shorter than the sampling period)"
+        if len(inside) < 2:                                # region shorter than the sampling period: use the identical extra steps run after it
+            inside = [l for (t, l) in self.lines if t >= t0]
+            window = "timed region + identical untimed steps right after it (region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
         for l in inside:
             f = [x.strip() for x in l.split(",")]
@@ -305,6 +310,10 @@ def main():
     clocks.mark_end()
     if world > 1: dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if clocks.proc and clocks.samples_inside() < 3:   # a very short timed region: keep the same load running (untimed) until the sampler has seen it
+        t_extra = time.perf_counter()
+        while time.perf_counter() - t_extra < 0.3:
+            step(0); torch.cuda.synchronize()
     clk = clocks.stop()
     launches = ctx.launch_count - l0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
