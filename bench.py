@@ -310,12 +310,12 @@ def main():
     clocks.mark_end()
     if world > 1: dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.launch_count - l0
     if clocks.proc and clocks.samples_inside() < 3:   # a very short timed region: keep the same load running (untimed) until the sampler has seen it
         t_extra = time.perf_counter()
         while time.perf_counter() - t_extra < 0.3:
             step(0); torch.cuda.synchronize()
     clk = clocks.stop()
-    launches = ctx.launch_count - l0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
