@@ -376,7 +376,7 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
-    const int y0 = (blockIdx.y * GF_BLOCK_Y + threadIdx.y) * 2;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;          // blockDim.y: the host may launch flatter blocks (GF_X2_BLOCK_Y)
     if (x >= A.out_cols || y0 >= A.out_rows) return;
     const unsigned long long BYTES = COORD ? (unsigned long long)P.bytes_per_pixel : (unsigned long long)PIX::BYTES;
     const unsigned long long ostride = (unsigned long long)P.output_stride;
