@@ -47,8 +47,8 @@ CONFIGS = {
 CFG = CONFIGS[2]
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed `ncu --set full` captures
 # (ncu flushes the caches before the launch and the output stays in L2 after it, hence traffic < algorithmic bytes)
-NCU_TRAFFIC = {(2, "Bilinear"): 23117824 + 1014528}
-NCU_TRAFFIC_SOURCE = "profiles/r01j_x2_combined_guards_fisheye_rgba8_summary.txt"
+NCU_TRAFFIC = {(2, "Bilinear"): 23118848 + 640256}
+NCU_TRAFFIC_SOURCE = "profiles/r01l_x2_final_fisheye_rgba8_summary.txt"
 INTERP = "Bilinear"          # BASELINE configs are bilinear; --interp measures the other resamplers (side measurement, not the headline)
 W, H = CFG["w"], CFG["h"]
 PIX, LENS = CFG["pix"], CFG["lens"]
