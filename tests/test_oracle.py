@@ -97,6 +97,12 @@ def golden_cases():
     }
     for lens in ("opencv_standard", "poly3", "poly5", "ptlens", "insta360", "generic_polynomial", "gopro"):
         out["lens_" + lens] = dict(base, lens=lens)
+    for name in ("EWA: RobidouxSharp", "EWA: Robidoux", "EWA: Mitchell", "EWA: Catmull-Rom"):
+        out["ewa_" + name.split(": ")[1].lower()] = dict(w=96, h=54, interp=name)
+    out["feather_lanczos_rgbaf"] = dict(w=96, h=54, interp="Lanczos4", pix="RGBAf", fov=1.6,
+                                        params=dict(background_mode=3, background_margin=0.1, background_margin_feather=0.1))
+    out["horizontal_rs_gopro_warp"] = dict(base, lens="gopro", digital="gopro_warp", horizontal_rs=True)
+    out["refraction_rlimit"] = dict(base, params=dict(light_refraction_coefficient=1.33, r_limit=1.2))
     return out
 
 
