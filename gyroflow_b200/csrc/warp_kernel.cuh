@@ -939,7 +939,7 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
     constexpr int C = PIX::COUNT;
     const uint32_t feat = A.feat;
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
-    const int y = blockIdx.y * GF_BLOCK_Y + threadIdx.y;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= A.out_cols || y >= A.out_rows) return;
     uint2* const cmap = A.coord_out ? A.coord_out + ((size_t)y * (size_t)A.out_cols + (size_t)x) : nullptr;   // multi-plane mode, pass 1
     const unsigned long long off = (unsigned long long)y * (unsigned long long)P.output_stride + (unsigned long long)x * PIX::BYTES;
@@ -981,7 +981,7 @@ shade_from_coords_kernel(const __grid_constant__ WarpArgs A) {
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
-    const int y = blockIdx.y * GF_BLOCK_Y + threadIdx.y;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= A.out_cols || y >= A.out_rows) return;
     const uint2 e = __ldg(A.coord_in + ((size_t)y * (size_t)A.out_cols + (size_t)x));
     const bool marked = e.x == GF_COORD_MARK;
