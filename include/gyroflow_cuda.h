@@ -258,8 +258,8 @@ GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx,
  * object (rendering/mod.rs:484-548, 596-629), recomputing every pixel's source coordinate per plane.  When the planes share one
  * geometry — the four R32f planes of GBRAPF32, the U and V planes of planar YUV: all KernelParams fields equal except plane_index
  * and background, same buffer sizes/strides/rects — this call computes the coordinates once into a device map and then samples
- * each plane from it (1 + n launches, bit-identical to n separate calls).  Otherwise (or for EWA) it degrades to n ordinary
- * launches.  DEVICE buffers and device tables; `in`, `out`, `params` are arrays of n_planes. */
+ * each plane from it (1 + n launches — 3 + n for the EWA resamplers — bit-identical to n separate calls).  Otherwise it degrades
+ * to n ordinary calls.  DEVICE buffers and device tables; `in`, `out`, `params` are arrays of n_planes. */
 GF_API int         gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
                                                 const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
                                                 const float* mesh_dev, size_t mesh_len, void* cu_stream);
@@ -273,7 +273,8 @@ GF_API int         gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* ma
 GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
 GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
 GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */
-GF_API uint64_t    gf_cuda_launch_count(gf_cuda_ctx* ctx);   /* kernels launched by this ctx so far */
+GF_API uint64_t    gf_cuda_launch_count(gf_cuda_ctx* ctx);   /* warp / coordinate / sampling kernels launched by this ctx so far: 1 per bilinear
+                                                              * frame, 2 for bicubic / Lanczos4 (coordinate pass + sampling pass), 4 for EWA */
 
 /* Device self-test of the exact packed-f32x2 primitives (division, square root, atanf, uniform-divisor division)
  * against the scalar IEEE operations they replace: n pseudo-random operand sets, mismatch counts in out4[0..3].
