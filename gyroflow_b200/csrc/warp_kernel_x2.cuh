@@ -210,6 +210,85 @@ template <> struct Lens2<GF_LENS_INSTA360> {
 };
 
 // ------------------------------------------------------------------------------------------
+// packed digital lenses (the second, "digital" distortion of :216-220) for the pairs the fisheye model is compiled with
+// ------------------------------------------------------------------------------------------
+template <int D> struct Digital2 { static constexpr bool kHas = false; };
+template <> struct Digital2<GF_LENS_NONE> { static constexpr bool kHas = true; static GF_DEV void distort(f2&, f2&, const gf_kernel_params&, bool&) {} };
+// digital_stretch.rs:19-22
+template <> struct Digital2<GF_LENS_DIGITAL_STRETCH> {
+    static constexpr bool kHas = true;
+    static GF_DEV void distort(f2& x, f2& y, const gf_kernel_params& P, bool&) {
+        x = p2::mul(x, p2::bc(P.digital_lens_params[0])); y = p2::mul(y, p2::bc(P.digital_lens_params[1]));
+    }
+};
+struct Superview2 {        // gopro_superview.rs:12-19, both lanes
+    static GF_DEV void map(f2& ux, f2& uy) {
+        using namespace p2;
+        const f2 x2 = mul(ux, ux), y2 = mul(uy, uy);
+        const f2 nx = mul(ux, add(bc(1.2100393f), mul(x2, add(bc(-1.2758402f), mul(x2, bc(1.7751845f))))));
+        const f2 t1 = mul(sub(bc(0.4465308f), mul(bc(0.7683315f), y2)), y2);
+        const f2 t2 = mul(add(add(bc(-0.3574087f), mul(bc(1.1584653f), y2)), mul(bc(0.3529348f), x2)), x2);
+        const f2 ny = mul(uy, add(add(bc(0.9364505f), t1), t2));
+        ux = nx; uy = ny;
+    }
+};
+struct Superview62 {       // gopro6_superview.rs:12-17
+    static GF_DEV f2 abs2(f2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+    static GF_DEV void map(f2& ux, f2& uy) {
+        using namespace p2;
+        ux = mul(ux, sub(bc(1.0f), mul(bc(0.48f), abs2(ux))));
+        ux = mul(ux, mul(bc(0.943396f), add(bc(1.0f), mul(bc(0.157895f), abs2(ux)))));
+        uy = mul(uy, mul(bc(0.943396f), add(bc(1.0f), mul(bc(0.060000f), abs2(mul(uy, bc(2.0f)))))));
+    }
+};
+struct Hyperview2 {        // gopro_hyperview.rs:10-17
+    static GF_DEV void map(f2& ux, f2& uy) {
+        using namespace p2;
+        const f2 x2 = mul(ux, ux), y2 = mul(uy, uy);
+        f2 h = add(bc(-2735.5422363f), mul(x2, bc(1923.1572266f)));
+        h = add(bc(1551.2922363f), mul(x2, h));
+        h = add(bc(-451.5002441f), mul(x2, h));
+        h = add(bc(74.5198746f), mul(x2, h));
+        h = add(bc(-8.1668825f), mul(x2, h));
+        const f2 nx = mul(ux, add(add(bc(1.5805143f), mul(x2, h)), mul(y2, bc(-0.1086027f))));
+        const f2 ny = mul(uy, add(add(bc(1.0238225f), mul(y2, bc(-0.1025671f))), mul(x2, add(bc(-0.2639930f), mul(x2, bc(0.2979266f))))));
+        ux = nx; uy = ny;
+    }
+};
+// the *_view.rs family (ViewLens::distort in lens_models.cuh): normalise, x-scale, <= 12 fixed-point steps, de-normalise.
+// Each lane stops updating at the step where the scalar code would break; the loop ends when both have (or after 12 steps).
+template <typename Fn, int XSCALE_KIND>
+struct ViewDigital2 {
+    static constexpr bool kHas = true;
+    static GF_DEV void distort(f2& x, f2& y, const gf_kernel_params& P, bool& bad) {
+        using namespace p2;
+        const f2 sw = bc((float)P.width), sh = bc((float)P.height);
+        // numerators: source coordinates, zero or of ordinary size (anything else goes to the exact code)
+        bad |= !zero_or_in_window(x.x) | !zero_or_in_window(x.y) | !zero_or_in_window(y.x) | !zero_or_in_window(y.y);
+        x = sub(div_seq(x, sw), bc(0.5f)); y = sub(div_seq(y, sh), bc(0.5f));
+        if (XSCALE_KIND != 0) x = mul(x, bc(XSCALE_KIND == 1 ? 1.333333333f : 1.555555555f));
+        f2 ppx = x, ppy = y;
+        bool da = false, db = false;
+        #pragma unroll 1
+        for (int i = 0; i < 12; ++i) {
+            f2 dx = ppx, dy = ppy;
+            Fn::map(dx, dy);
+            dx = sub(dx, x); dy = sub(dy, y);
+            da |= (fabsf(dx.x) < 1e-6f) & (fabsf(dy.x) < 1e-6f);
+            db |= (fabsf(dx.y) < 1e-6f) & (fabsf(dy.y) < 1e-6f);
+            if (da & db) break;
+            const f2 nx = sub(ppx, dx), ny = sub(ppy, dy);
+            ppx = make_float2(da ? ppx.x : nx.x, db ? ppx.y : nx.y);
+            ppy = make_float2(da ? ppy.x : ny.x, db ? ppy.y : ny.y);
+        }
+        x = mul(add(ppx, bc(0.5f)), sw); y = mul(add(ppy, bc(0.5f)), sh);
+    }
+};
+template <> struct Digital2<GF_LENS_GOPRO_SUPERVIEW>  : ViewDigital2<Superview2, 1>  {};
+template <> struct Digital2<GF_LENS_GOPRO6_SUPERVIEW> : ViewDigital2<Superview62, 0> {};
+template <> struct Digital2<GF_LENS_GOPRO_HYPERVIEW>  : ViewDigital2<Hyperview2, 2>  {};
+
+// ------------------------------------------------------------------------------------------
 // rotate_and_distort for two pixels — cpu_undistort.rs:133-228, lean feature set
 // (no translation3d, r_limit, refraction, mesh, digital lens, input stretch).
 // ------------------------------------------------------------------------------------------
@@ -229,7 +308,7 @@ GF_DEV bool row_has_ibis(const float* __restrict__ matrices, uint32_t idx) {    
 
 // hot path: no branches.  Returns u, v for both lanes and ORs `bad`; a lane with w <= 0 (the reference's None, :138) counts as
 // bad too — it is rare (rays more than 90 degrees off axis) and the exact code handles it.
-template <int LENS, bool TRUSTED>
+template <int LENS, int DIGITAL, bool TRUSTED>
 GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, f2& ou, f2& ov, bool& bad) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
@@ -246,21 +325,22 @@ GF_DEV void rotate_and_distort_x2(f2 px, f2 py, uint32_t idx_a, uint32_t idx_b, 
     Lens2<LENS>::template distort<TRUSTED>(_x, _y, _w, P, ux, uy, bad);                                // :154
     ux = mul(ux, bc(P.f[0])); uy = mul(uy, bc(P.f[1]));                                                // :155
     ou = add(ux, bc(P.c[0])); ov = add(uy, bc(P.c[1]));                                                // :167 (no IBIS rows on this path)
+    Digital2<DIGITAL>::distort(ou, ov, P, bad);                                                        // :216-220 (the lean set has F_DIGITAL == (DIGITAL != none))
 }
 
 // cold path: the scalar kernel's exact code for both pixels of the pair, one call site per pass.
 struct PairUV { float ua, va, ub, vb; int ok; };      // ok: bit 0/1 = lane a/b is Some(..); bit 2/3 = its coordinates are outside the
                                                        // domain of the hot path's rounding shortcut (|u| or |v| >= 2^16, or NaN)
 GF_DEV bool outside_shortcut(float u, float v) { return !(fabsf(u) < 0x1p16f) | !(fabsf(v) < 0x1p16f); }
-template <int LENS>
+template <int LENS, int DIGITAL>
 static __device__ __noinline__ PairUV rotate_and_distort_cold(float px, float pya, float pyb, uint32_t idx_a, uint32_t idx_b, const WarpArgs& A, int apply_smap) {
     PairUV o; o.ua = o.va = o.ub = o.vb = 0.0f; o.ok = 0;
     float cu, cv;
-    if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pya, idx_a, A, cu, cv)) {
+    if (rotate_and_distort<LENS, DIGITAL, false>(px, pya, idx_a, A, cu, cv)) {
         if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
         o.ua = cu; o.va = cv; o.ok |= 1 | (outside_shortcut(cu, cv) ? 4 : 0);
     }
-    if (rotate_and_distort<LENS, GF_LENS_NONE, false>(px, pyb, idx_b, A, cu, cv)) {
+    if (rotate_and_distort<LENS, DIGITAL, false>(px, pyb, idx_b, A, cu, cv)) {
         if (apply_smap) { cu = map_apply(cu, A.smap_x); cv = map_apply(cv, A.smap_y); }
         o.ub = cu; o.vb = cv; o.ok |= 2 | (outside_shortcut(cu, cv) ? 8 : 0);
     }
@@ -370,7 +450,7 @@ GF_DEV void shade_lean(bool ok, bool far, float u, float v, int wu, int wv, cons
 
 // COORD: pass 1 of the two-pass mode — write the coordinates to A.coord_out instead of sampling (pixel-format independent: the
 // pixel size then comes from KernelParams, PIX is a placeholder).
-template <int LENS, class PIX, int MINB, bool TRUSTED, bool COORD = false>
+template <int LENS, int DIGITAL, class PIX, int MINB, bool TRUSTED, bool COORD = false>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     using namespace p2;
@@ -416,9 +496,9 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     if (A.feat & F_RS) {                                                                                // :470-479
         const uint32_t mid = (uint32_t)P.matrix_count / 2u;
         f2 tu, tv; bool oa = true, ob = true, bad = false;
-        rotate_and_distort_x2<LENS, TRUSTED>(px, py, mid, mid, A, tu, tv, bad);
+        rotate_and_distort_x2<LENS, DIGITAL, TRUSTED>(px, py, mid, mid, A, tu, tv, bad);
         if (bad) {                                       // cold: exact scalar code for both pixels
-            const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, mid, mid, A, 0);
+            const PairUV c = rotate_and_distort_cold<LENS, DIGITAL>(pxs, py.x, py.y, mid, mid, A, 0);
             oa = (c.ok & 1) != 0; ob = (c.ok & 2) != 0; tv = mk(c.va, c.vb);
         }
         int ra, rb;
@@ -428,11 +508,11 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     const uint32_t last = (uint32_t)(P.matrix_count - 1);
     const uint32_t idx_a = min((uint32_t)sy_a, last), idx_b = min((uint32_t)sy_b, last);               // :482
     f2 u, v; bool ok_a = true, ok_b = true, far_a = false, far_b = false, bad = false;
-    rotate_and_distort_x2<LENS, TRUSTED>(px, py, idx_a, idx_b, A, u, v, bad);                           // :483
+    rotate_and_distort_x2<LENS, DIGITAL, TRUSTED>(px, py, idx_a, idx_b, A, u, v, bad);                           // :483
     u = map_apply_x2(u, A.smap_x, bad);                                                                 // :510-515
     v = map_apply_x2(v, A.smap_y, bad);
     if (bad) {
-        const PairUV c = rotate_and_distort_cold<LENS>(pxs, py.x, py.y, idx_a, idx_b, A, 1);
+        const PairUV c = rotate_and_distort_cold<LENS, DIGITAL>(pxs, py.x, py.y, idx_a, idx_b, A, 1);
         ok_a = (c.ok & 1) != 0; ok_b = (c.ok & 2) != 0; far_a = (c.ok & 4) != 0; far_b = (c.ok & 8) != 0;
         u = mk(c.ua, c.ub); v = mk(c.va, c.vb);
     }
