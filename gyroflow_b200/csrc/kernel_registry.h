@@ -39,8 +39,8 @@ KernelFn gf_shade_kernel(int layout);      // pass 2 of the multi-plane mode (sh
 // 3 = tables validated (no wild entries, no IBIS rows), 2 = unvalidated device tables (per-pixel numerator / IBIS tests kept)
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_x2(int interp, bool trusted) {
-    // packed digital lenses exist for the pairs of the fisheye model (superview, superview6, hyperview, stretch)
-    if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas && (DIGITAL == GF_LENS_NONE || LENS == GF_LENS_OPENCV_FISHEYE)) {
+    // packed digital lenses: superview, superview6, hyperview (fisheye pairs) and digital_stretch (every packed lens model)
+    if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas) {
         // 6 resident blocks per SM (40 registers): 5 (48 registers, no spills) measured the same, 4 slower, 7 / 8 compile to the 6 code
         if (interp == GF_INTERP_BILINEAR) return trusted ? warp_kernel_x2<LENS, DIGITAL, PIX, 6, true> : warp_kernel_x2<LENS, DIGITAL, PIX, 6, false>;
     }
@@ -49,7 +49,7 @@ static KernelFn pick_x2(int interp, bool trusted) {
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
     if (lean == 4 || lean == 5) {
-        if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas && (DIGITAL == GF_LENS_NONE || LENS == GF_LENS_OPENCV_FISHEYE))
+        if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas)
             return lean == 5 ? warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, 6, true, true> : warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, 6, false, true>;
         return nullptr;
     }

@@ -390,6 +390,8 @@ def test_packed_kernel_other_lens_models(lens):
     assert_bit_exact(dict(w=640, h=360, lens=lens, fov=3.0))                                   # invalid (w <= 0) regions -> cold path
     for kind in ("nan_row", "huge", "zero_w", "on_axis", "ibis_some"):
         assert_bit_exact(dict(w=320, h=180, lens=lens, matrix_hook=_wild(kind)))
+    assert_bit_exact(dict(w=640, h=360, lens=lens, digital="digital_stretch"))                  # packed digital_stretch pair
+    assert_bit_exact(dict(w=320, h=180, lens=lens, digital="digital_stretch", pix="Luma16", matrix_hook=_wild("zero_w")))
     if lens == "opencv_standard":      # denominators of the rational term crossing zero / huge coefficients
         assert_bit_exact(dict(w=640, h=360, lens=lens, fov=2.0, params=dict(k=[0.1, 0.01, 0.001, 0.001, 0.0, -3.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0])))
         assert_bit_exact(dict(w=640, h=360, lens=lens, params=dict(k=[1e20, 0.0, 0.0, 0.0, 0.0, 1e20, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])))
