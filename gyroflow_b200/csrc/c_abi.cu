@@ -421,6 +421,19 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
     delete ctx;
 }
 
+// Which kernel renders a frame with these uniforms?  Shared by run_warp and gf_cuda_plan (the host-only query the CPU tests use).
+enum { PLAN_GENERAL = 0, PLAN_LEAN = 1, PLAN_PACKED = 2, PLAN_PACKED_TRUSTED = 3, PLAN_TWO_PASS = 0x10 };
+static int select_variant(bool has_lean, bool has_packed, int ctx_digital_lens, const WarpArgs& A, uint32_t table_flags, bool two_pass, int n_maps) {
+    // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
+    const bool lean_ok = has_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
+                         (((A.feat & F_DIGITAL) != 0) == (ctx_digital_lens != GF_LENS_NONE));
+    // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
+    // (two-pass: the coordinate-writing variant, except for EWA whose probe positions only the scalar kernels evaluate)
+    const bool packed_ok = lean_ok && has_packed && (A.feat & F_WILD) == 0 && !(two_pass && n_maps != 1);
+    const int v = packed_ok ? (table_flags == 0 ? PLAN_PACKED_TRUSTED : PLAN_PACKED) : (lean_ok ? PLAN_LEAN : PLAN_GENERAL);
+    return v | (two_pass ? PLAN_TWO_PASS : 0);
+}
+
 // `more_planes` > 0: multi-plane mode — in/out/p are arrays of 1 + more_planes planes that share one geometry (checked by the caller);
 // the coordinates are computed once (pass 1, into ctx->d_coords) and every plane is then sampled from them (pass 2).
 static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
@@ -522,13 +535,10 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         }
         A.coord_out = ctx->d_coords;
     }
-    // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
-    const bool lean_ok = ctx->fn_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
-                         (((A.feat & F_DIGITAL) != 0) == (ctx->digital_lens != GF_LENS_NONE));
-    // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
-    // (two-pass: the coordinate-writing variant, except for EWA whose probe positions only the scalar kernels evaluate)
-    KernelFn x2 = ((A.feat & F_WILD) != 0 || (two_pass && n_maps != 1)) ? nullptr
-                : two_pass ? ((table_flags == 0) ? ctx->fn_x2ct : ctx->fn_x2c) : ((table_flags == 0) ? ctx->fn_x2t : ctx->fn_x2);
+    const bool has_packed = two_pass ? (ctx->fn_x2c && ctx->fn_x2ct) : (ctx->fn_x2 && ctx->fn_x2t);
+    const int variant = select_variant(ctx->fn_lean != nullptr, has_packed, ctx->digital_lens, A, table_flags, two_pass, n_maps) & 0xf;
+    const bool lean_ok = variant != PLAN_GENERAL;
+    KernelFn x2 = variant == PLAN_PACKED_TRUSTED ? (two_pass ? ctx->fn_x2ct : ctx->fn_x2t) : variant == PLAN_PACKED ? (two_pass ? ctx->fn_x2c : ctx->fn_x2) : nullptr;
     if (lean_ok && x2) {
         // 32 x 4 threads (4 x 8 output rows... 32 x 8 pixels) per block measured 2 % faster than 32 x 8 threads (finer tail); GF_X2_BLOCK_Y overrides
         static const int by = [] { const char* e = getenv("GF_X2_BLOCK_Y"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }();
@@ -727,6 +737,32 @@ GF_API int gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const
         if (rc != GF_OK) return rc;
     }
     return GF_OK;
+}
+
+// Host-only: which kernel variant would render this frame (no CUDA call, no context).  table_flags: 0 = validated tame tables without
+// IBIS rows, non-zero = anything else.  Returns PLAN_* (0 general, 1 lean, 2 packed, 3 packed + trusted tables; | 0x10 two-pass),
+// or a negative GF_ERR_*.  A planning aid for integrators and the hook the CPU-only tests use to check the host logic.
+GF_API int gf_cuda_plan(const gf_kernel_params* params, int pixel_type, int distortion_model, int digital_lens,
+                        const gf_buffer_desc* in, const gf_buffer_desc* out, size_t mesh_len, uint32_t table_flags, size_t n_planes) {
+    if (!params || !in || !out) return GF_ERR_BAD_PARAMS;
+    int layout = 0, bpp = 0;
+    if (!pix_layout(pixel_type, &layout, &bpp)) return GF_ERR_BAD_PARAMS;
+    { int rc = validate(nullptr, params, in, out, bpp); if (rc != GF_OK) return rc; }
+    if (!find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0)) return GF_ERR_UNSUPPORTED_COMBO;
+    gf_cuda_ctx ctx;                                           // plain host object: nothing below touches the device
+    ctx.pixel_type = pixel_type; ctx.distortion_model = distortion_model; ctx.digital_lens = digital_lens;
+    ctx.interpolation = params->interpolation; ctx.layout = layout; ctx.bpp = bpp;
+    WarpArgs A; memset(&A, 0, sizeof(A));
+    A.p = *params; A.mesh_len = (int)mesh_len;
+    A.src = (const uint8_t*)in->ptr; A.dst = (uint8_t*)out->ptr; A.src_len = in->len; A.dst_len = out->len;
+    A.out_rows = (int)((out->len + (size_t)params->output_stride - 1) / (size_t)params->output_stride);
+    A.out_cols = params->output_stride / bpp;
+    fill_uniforms(A, &ctx, A.src, A.dst);
+    const bool two_pass = n_planes > 1 || params->interpolation != GF_INTERP_BILINEAR;
+    const int n_maps = params->interpolation > 8 ? 3 : 1;
+    const bool has_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1) != nullptr;
+    const bool has_packed = !getenv("GF_DISABLE_X2") && find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, two_pass ? 5 : 3) != nullptr;
+    return select_variant(has_lean, has_packed, digital_lens, A, table_flags, two_pass, n_maps);
 }
 
 GF_API int gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows) {

@@ -270,6 +270,12 @@ GF_API int         gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_plane
  * (1 = wild entry, 2 = IBIS rows; still rendered correctly), or a negative GF_ERR_*.  Host tables are scanned while they are staged. */
 GF_API int         gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows);
 
+/* Host-only planning query (no CUDA call): which kernel variant would render a frame with these parameters.
+ * table_flags: 0 = tables validated tame and IBIS-free (what the host scan / gf_cuda_validate_tables_dev establish), else non-zero.
+ * Returns 0 general, 1 lean, 2 packed, 3 packed with trusted tables, OR-ed with 0x10 when the two-pass path is used; < 0 on error. */
+GF_API int         gf_cuda_plan(const gf_kernel_params* params, int pixel_type, int distortion_model, int digital_lens,
+                                const gf_buffer_desc* in, const gf_buffer_desc* out, size_t mesh_len, uint32_t table_flags, size_t n_planes);
+
 GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
 GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
 GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */

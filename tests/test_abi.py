@@ -82,3 +82,52 @@ def test_no_cpu_fallback_without_a_gpu(gpu_available):
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(g.BackendMissing):
         abi.load_library(str(tmp_path / "libgyroflow_cuda.so"))
+
+
+def _plan(case, table_flags=0, n_planes=1, mesh_len=None):
+    """gf_cuda_plan for a tests/cases.py case (host-only, no GPU)."""
+    from tests import cases
+    lib = g.load_library()
+    p, src, m, mesh, dst0, pix, lens, digital = cases.build(case)
+    bw, bh = case.get("in_size", (case["w"], case["h"]))
+    obw, obh = case.get("out_size", (case.get("ow", case["w"]), case.get("oh", case["h"])))
+    bufs = g.Buffers(g.BufferDescription((bw, bh, p.stride), src), g.BufferDescription((obw, obh, p.output_stride), dst0))
+    i, o = bufs.input.to_c(), bufs.output.to_c()
+    ml = (mesh.size if mesh is not None else 0) if mesh_len is None else mesh_len
+    return lib.gf_cuda_plan(C.byref(p), abi.PIXEL_TYPES[pix][0], abi.LENS[lens], abi.LENS[digital] if digital else 0,
+                            C.byref(i), C.byref(o), ml, table_flags, n_planes)
+
+
+def test_kernel_variant_planning_host_logic():
+    """Which kernel the host picks (fill_uniforms + select_variant in c_abi.cu), checked without a GPU.
+    0 general, 1 lean, 2 packed, 3 packed + trusted tables; | 0x10 two-pass."""
+    base = dict(w=640, h=360)
+    assert _plan(base) == 3                                             # the north-star configuration: packed kernel, trusted tables
+    assert _plan(base, table_flags=1) == 2                              # unvalidated / wild / IBIS tables: the guarded packed variant
+    assert _plan(dict(base, rs=False)) == 3
+    for lens in ("opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony", "generic_polynomial"):
+        assert _plan(dict(base, lens=lens)) == 3, lens
+        assert _plan(dict(base, lens=lens, digital="digital_stretch")) == 3, lens
+    assert _plan(dict(base, lens="gopro")) == 1                         # no packed form: scalar lean kernel
+    assert _plan(dict(base, lens="gopro", digital="gopro_warp")) == 1
+    for d in ("gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch"):
+        assert _plan(dict(base, digital=d, pix="Luma16")) == 3, d
+    # rare per-frame features -> general kernel
+    for params in (dict(background_mode=1), dict(background_mode=3), dict(input_rotation=90.0), dict(light_refraction_coefficient=1.33),
+                   dict(r_limit=1.5), dict(lens_correction_amount=0.5), dict(input_horizontal_stretch=1.2), dict(pixel_value_limit=200.0)):
+        assert _plan(dict(base, params=params)) == 0, params
+    assert _plan(dict(base, mesh=True)) == 0 and _plan(dict(base, flags=abi.FLAG_FILL_WITH_BACKGROUND)) == 0
+    assert _plan(dict(base, flags=abi.FLAG_FIX_COLOR_RANGE)) == 0
+    # magnitudes the packed fast paths do not cover -> scalar lean kernel
+    assert _plan(dict(base, params=dict(k=[1e30, 0.0, 0.0, 0.0] + [0.0] * 8))) == 1
+    assert _plan(dict(base, params=dict(translation2d=[1e6, 0.0]))) == 1
+    assert _plan(dict(base, params=dict(c=[0.0, 180.0]))) == 1
+    # byte-aligned-only buffers (odd stride) cannot use whole-pixel vector access -> general kernel
+    assert _plan(dict(w=203, h=117, pix="RGBA8", stride_pad=3)) == 0
+    # every resampler but bilinear, and multi-plane frames: two-pass; EWA's probe passes are scalar
+    assert _plan(dict(base, interp="Lanczos4")) == 0x13 and _plan(dict(base, interp="Bicubic", lens="gopro")) == 0x11
+    assert _plan(dict(base, interp="EWA: Mitchell")) == 0x11
+    assert _plan(dict(base, pix="R32f"), n_planes=4) == 0x13
+    # validation errors come back as the reference's error classes
+    bad = dict(base); p_err = _plan(dict(w=640, h=3))
+    assert p_err == -2                                                  # SizeTooSmall (height < 4)
