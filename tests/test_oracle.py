@@ -132,3 +132,15 @@ def test_independent_numpy_restatement_agrees():
             warnings.simplefilter("ignore")          # float32 overflow warnings on far-off-axis pixels are expected
             np_restatement.undistort_image(src, got, p, m)
         assert np.array_equal(got, want), c
+    # the other closed-form lens models and the 16-bit / f32 pixel conversions
+    for c, sdt in ((dict(w=96, h=54, lens="opencv_standard"), np.uint8), (dict(w=96, h=54, lens="poly3", pix="Luma16"), np.uint16),
+                   (dict(w=96, h=54, lens="poly5", pix="UV16", fov=1.8), np.uint16), (dict(w=96, h=54, lens="ptlens", pix="R32f"), np.float32),
+                   (dict(w=96, h=54, lens="sony", pix="RGBAf", fov=2.0), np.float32), (dict(w=64, h=36, lens="sony", pix="RGBA16", rs=False), np.uint16)):
+        p, src, m, mesh, dst0, pix, lens, digital = cases.build(c)
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        got = dst0.copy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=sdt)
+        assert np.array_equal(got, want), c
