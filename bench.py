@@ -8,12 +8,16 @@ ring of input frames larger than L2, so no launch finds its source in cache.
 
   value     frames/s with frames + tables already resident in HBM (gf_cuda_undistort_image_dev), CUDA-event timed,
             max over ranks
-  e2e       frames/s through the reference-facing call gf_cuda_undistort_image with HOST (pinned) buffers:
-            H2D of the frame + tables and D2H of the result inside the timed region
+  e2e       frames/s through the reference-facing host-buffer entry points with HOST (pinned) buffers: H2D of the frame +
+            tables and D2H of the result inside the timed region, for the same FRAMES_PER_STEP-frame steps.  e2e.value keeps three
+            frames in flight (gf_cuda_undistort_image_async on three contexts), e2e.sync_call_value is the strictly sequential
+            gf_cuda_undistort_image
   roofline  algorithmic bytes per launch (in + out + rows*56 + 368) / mean launch time, vs measured HBM peak
   cpu_baseline  the CPU oracle (C port of the reference CPU path) on this box's host cores, bounded sample
 
 `--impl reference` times the reference CPU path instead (oracle port; the Rust original cannot be built: no rustc).
+Side measurements (not the headline): --config 1/3/31/4 (the other BASELINE configurations), --interp (other resamplers),
+--lens (other lens models), --planes N (multi-plane frames through gf_cuda_undistort_planes_dev).
 """
 import argparse
 import ctypes as C
