@@ -11,6 +11,7 @@
 using namespace gf;
 
 namespace {
+inline uint32_t __float_as_uint_host(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 __device__ __forceinline__ uint32_t mix(uint64_t v) {
     v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
     return (uint32_t)v;
@@ -99,7 +100,42 @@ __global__ void selftest_kernel(unsigned long long n, unsigned long long seed, u
     }
     for (int j = 0; j < 4; ++j) if (bad[j]) atomicAdd(&out[j], bad[j]);
 }
+// Exhaustive sweeps (opt-in, GF_RUN_EXHAUSTIVE=1 in the tests): every float of the packed atanf's admitted range [2^-28, 2^24) and of
+// the packed square root's window [2^-56, 2^48), two consecutive floats per thread (lane .x / lane .y), against the scalar functions.
+__global__ void sweep_kernel(uint32_t lo, uint32_t hi, int which, unsigned long long* out) {
+    unsigned long long bad = 0;
+    const uint32_t step = 2u * gridDim.x * blockDim.x;
+    for (uint64_t u = (uint64_t)lo + 2u * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x); u + 1 < hi; u += step) {
+        const float a = __uint_as_float((uint32_t)u), b = __uint_as_float((uint32_t)u + 1u);
+        if (which == 0) {
+            const p2::f2 t = p2::atanf2_core(p2::mk(a, b), p2::GF_ATAN_TAB);
+            if (!same(t.x, gf_atanf(a))) bad++;
+            if (!same(t.y, gf_atanf(b))) bad++;
+        } else {
+            const p2::f2 r = p2::sqrt_seq(p2::mk(a, b));
+            if (!same(r.x, sqrtf(a))) bad++;
+            if (!same(r.y, sqrtf(b))) bad++;
+        }
+    }
+    if (bad) atomicAdd(out, bad);
+}
 } // namespace
+
+// out2[0]: mismatches of atanf2_core over all floats in [2^-28, 2^24); out2[1]: of sqrt_seq over all floats in [2^-56, 2^48).
+extern "C" GF_API int gf_cuda_selftest_exhaustive(int device, unsigned long long* out2) {
+    if (!out2) return GF_ERR_BAD_PARAMS;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 2 * sizeof(unsigned long long)) != cudaSuccess) return GF_ERR_CUDA;
+    cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+    sweep_kernel<<<148 * 16, 256>>>(__float_as_uint_host(0x1p-28f), __float_as_uint_host(0x1p24f), 0, d);
+    sweep_kernel<<<148 * 16, 256>>>(__float_as_uint_host(0x1p-56f), __float_as_uint_host(0x1p48f), 1, d + 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out2, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    return GF_OK;
+}
 
 extern "C" GF_API int gf_cuda_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long* out4) {
     if (!out4) return GF_ERR_BAD_PARAMS;

@@ -286,6 +286,9 @@ GF_API uint64_t    gf_cuda_launch_count(gf_cuda_ctx* ctx);   /* warp / coordinat
  * against the scalar IEEE operations they replace: n pseudo-random operand sets, mismatch counts in out4[0..3].
  * No reference counterpart (test hook). */
 GF_API int         gf_cuda_selftest(int device, unsigned long long n, unsigned long long seed, unsigned long long* out4);
+/* Exhaustive variant (seconds): every input of the packed atanf ([2^-28, 2^24)) and of the packed square root ([2^-56, 2^48));
+ * out2 = mismatch counts.  Test hook. */
+GF_API int         gf_cuda_selftest_exhaustive(int device, unsigned long long* out2);
 
 
 /* ------------------------------------------------------------------------------------------

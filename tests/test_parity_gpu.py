@@ -3,6 +3,8 @@
 Every test here needs a real B200 (`-m gpu`).  A missing GPU or a missing libgyroflow_cuda.so is a FAILURE,
 never a skip: there is no fallback path to test instead.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -337,6 +339,14 @@ def test_packed_primitives_selftest():
     out = (C.c_ulonglong * 4)()
     assert lib.gf_cuda_selftest(0, 1 << 28, 12345, out) == 0
     assert list(out) == [0, 0, 0, 0], list(out)
+
+
+@pytest.mark.skipif(not os.environ.get("GF_RUN_EXHAUSTIVE"), reason="opt-in: GF_RUN_EXHAUSTIVE=1 (every input of the packed atanf / sqrt, a few seconds)")
+def test_packed_sequences_exhaustive_on_device():
+    import ctypes as C
+    out = (C.c_ulonglong * 2)()
+    assert g.load_library().gf_cuda_selftest_exhaustive(0, out) == 0
+    assert list(out) == [0, 0], list(out)
 
 
 def test_many_frames_and_rotations():
