@@ -6,7 +6,10 @@ This package is the thin host-side mirror used by tests and bench.py.
 from . import abi
 from .abi import KernelParams, BackendMissing, load_library
 from .backend import (BufferDescription, Buffers, FrameTransform, ProcessedInfo, CudaWrapper,
-                      GyroflowCoreError, list_devices, ComputeParams, DeviceGyro, zoom_dynamic)
+                      GyroflowCoreError, list_devices, ComputeParams, DeviceGyro, zoom_dynamic,
+                      scan_tables_dev, bind_thread_to_device, stab_config, get_frame_transform_at)
+from .render_queue import RenderQueue
 
 __all__ = ["abi", "KernelParams", "BackendMissing", "load_library", "BufferDescription", "Buffers", "FrameTransform",
-           "ProcessedInfo", "CudaWrapper", "GyroflowCoreError", "list_devices", "ComputeParams", "DeviceGyro", "zoom_dynamic"]
+           "ProcessedInfo", "CudaWrapper", "GyroflowCoreError", "list_devices", "ComputeParams", "DeviceGyro", "zoom_dynamic",
+           "scan_tables_dev", "bind_thread_to_device", "stab_config", "get_frame_transform_at", "RenderQueue"]

@@ -78,6 +78,39 @@ class ComputeParams(C.Structure):
         ("digital_lens_params", C.c_double * 16), ("n_digital_lens_params", C.c_int32),
         ("gyro_offset_ms", C.c_double), ("duration_ms", C.c_double),
         ("org", QuatTrack), ("smoothed", QuatTrack),
+        # optional per-clip metadata (zero = absent)
+        ("sync_offset_ts_us", C.POINTER(C.c_int64)), ("sync_offset_ms", C.POINTER(C.c_double)), ("n_sync_offsets", C.c_size_t),
+        ("per_frame_time_offsets", C.POINTER(C.c_double)), ("n_per_frame_time_offsets", C.c_size_t),
+        ("focal_length_smoothing_enabled", C.c_int32),
+        ("focal_lengths", C.POINTER(C.c_double)), ("smoothed_focal_lengths", C.POINTER(C.c_double)), ("n_focal_lengths", C.c_size_t),
+        ("readout_time_scale", C.c_double),
+        ("camera_stab", C.c_void_p), ("n_camera_stab", C.c_size_t),
+    ]
+
+
+class CameraStab(C.Structure):
+    """gf_camera_stab: CameraStabData (gyro_source/file_metadata.rs:41-48) with the Catmull-Rom points as flat arrays."""
+    _fields_ = [
+        ("offset", C.c_double), ("sensor_size", C.c_uint32 * 2), ("crop_area", C.c_float * 4), ("pixel_pitch", C.c_uint32 * 2),
+        ("ibis_pos", C.POINTER(C.c_double)), ("ibis_xyz", C.POINTER(C.c_double)), ("n_ibis", C.c_size_t),
+        ("ois_pos", C.POINTER(C.c_double)), ("ois_xyz", C.POINTER(C.c_double)), ("n_ois", C.c_size_t),
+    ]
+
+
+class StabConfig(C.Structure):
+    """gf_stab_config: the fields of `Stabilization` get_frame_transform_at reads (stabilization/mod.rs:253-326)."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("output_width", C.c_int32), ("output_height", C.c_int32),
+        ("interpolation", C.c_int32), ("pixel_type", C.c_int32), ("base_flags", C.c_int32), ("has_digital_lens", C.c_int32),
+        ("light_refraction_keyframed", C.c_int32), ("has_ibis_data", C.c_int32), ("show_safe_area", C.c_int32),
+        ("background", C.c_float * 4), ("canvas_scale", C.c_float), ("adaptive_zoom_window", C.c_double),
+    ]
+
+
+class QueueConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("distortion_model", C.c_int32), ("digital_lens", C.c_int32), ("depth", C.c_int32),
+        ("pin_numa", C.c_int32), ("checksum", C.c_int32), ("stab", StabConfig),
     ]
 
 
@@ -147,6 +180,25 @@ EXPORTS = [
                                               _P(C.c_size_t), _P(C.c_double), _P(C.c_double), C.c_void_p]),
     ("gf_cuda_find_fovs", C.c_int, [C.c_void_p, _P(ComputeParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p]),
     ("gf_zoom_dynamic_compute", C.c_int, [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_void_p]),
+    ("gf_cuda_scan_tables_dev", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("gf_cuda_undistort_image_dev_flagged", C.c_int, [C.c_void_p, _P(BufferDesc), _P(BufferDesc), _P(KernelParams),
+                                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("gf_cuda_undistort_planes_dev_flagged", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                       C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("gf_cuda_frame_transform_dev_flagged", C.c_int, [C.c_void_p, _P(ComputeParams), C.c_double, C.c_size_t, _P(KernelParams), C.c_void_p, C.c_size_t,
+                                                      C.c_void_p, _P(C.c_size_t), _P(C.c_double), _P(C.c_double), C.c_void_p]),
+    ("gf_table_flags_host", C.c_uint32, [C.c_void_p, C.c_size_t]),
+    ("gf_get_frame_transform_at", C.c_int, [_P(StabConfig), _P(ComputeParams), _P(BufferDesc), _P(BufferDesc), C.c_void_p, C.c_size_t,
+                                            C.c_size_t, C.c_double, _P(KernelParams)]),
+    ("gf_cuda_queue_create", C.c_int, [_P(C.c_void_p), _P(QueueConfig), _P(ComputeParams), _P(BufferDesc), _P(BufferDesc)]),
+    ("gf_cuda_queue_submit", C.c_int, [C.c_void_p, C.c_size_t, C.c_double, _P(BufferDesc), _P(BufferDesc), C.c_void_p, C.c_size_t]),
+    ("gf_cuda_queue_wait", C.c_int, [C.c_void_p, _P(C.c_size_t), _P(C.c_uint64)]),
+    ("gf_cuda_queue_drain", C.c_int, [C.c_void_p]),
+    ("gf_cuda_queue_launches", C.c_uint64, [C.c_void_p]),
+    ("gf_cuda_queue_destroy", None, [C.c_void_p]),
+    ("gf_cuda_queue_last_error", C.c_char_p, [C.c_void_p]),
+    ("gf_cuda_bind_thread_to_device", C.c_int, [C.c_int]),
+    ("gf_cuda_checksum_dev", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
 ]
 
 _lib = None

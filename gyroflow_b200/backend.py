@@ -146,25 +146,33 @@ class CudaWrapper:
             raise self._err(rc)
 
     def undistort_image_dev(self, buffers: Buffers, params: abi.KernelParams, matrices_dev: int, matrix_rows: int,
-                            mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0):
+                            mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0, table_flags_dev: int = 0):
+        """Device-resident tables.  table_flags_dev: device address of the table's trust verdict word (written by scan_tables_dev or by
+        DeviceGyro.frame_transform); 0 = none, the guarded code path runs."""
         i, o = buffers.input.to_c(), buffers.output.to_c()
-        rc = self._lib.gf_cuda_undistort_image_dev(self._h, C.byref(i), C.byref(o), C.byref(params),
-                                                   matrices_dev, matrix_rows, mesh_dev or None, mesh_len, stream or None)
+        if table_flags_dev:
+            rc = self._lib.gf_cuda_undistort_image_dev_flagged(self._h, C.byref(i), C.byref(o), C.byref(params), matrices_dev, matrix_rows,
+                                                               mesh_dev or None, mesh_len, table_flags_dev, stream or None)
+        else:
+            rc = self._lib.gf_cuda_undistort_image_dev(self._h, C.byref(i), C.byref(o), C.byref(params),
+                                                       matrices_dev, matrix_rows, mesh_dev or None, mesh_len, stream or None)
         if rc != 0:
             raise self._err(rc)
 
-    def undistort_planes_dev(self, buffers, params, matrices_dev: int, matrix_rows: int, mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0):
+    def undistort_planes_dev(self, buffers, params, matrices_dev: int, matrix_rows: int, mesh_dev: int = 0, mesh_len: int = 0, stream: int = 0,
+                             table_flags_dev: int = 0):
         """buffers: list of Buffers (DEVICE), params: list of KernelParams — the planes of one frame (gf_cuda_undistort_planes_dev)."""
         n = len(buffers)
         ins = (abi.BufferDesc * n)(*[b.input.to_c() for b in buffers])
         outs = (abi.BufferDesc * n)(*[b.output.to_c() for b in buffers])
         ps = (abi.KernelParams * n)(*params)
-        rc = self._lib.gf_cuda_undistort_planes_dev(self._h, n, ins, outs, ps, matrices_dev, matrix_rows, mesh_dev or None, mesh_len, stream or None)
+        rc = self._lib.gf_cuda_undistort_planes_dev_flagged(self._h, n, ins, outs, ps, matrices_dev, matrix_rows, mesh_dev or None, mesh_len,
+                                                            table_flags_dev or None, stream or None)
         if rc != 0:
             raise self._err(rc)
 
     def validate_tables_dev(self, matrices_dev: int, matrix_rows: int):
-        """Scan a device-resident table once so later undistort_image_dev calls on it may take the trusted fast path."""
+        """Synchronous query of a device table's verdict: 0 tame and IBIS-free, bit 0 wild entry, bit 1 IBIS rows.  Nothing is cached."""
         rc = self._lib.gf_cuda_validate_tables_dev(self._h, matrices_dev, matrix_rows)
         if rc < 0:
             raise self._err(rc)
@@ -198,7 +206,11 @@ class ComputeParams:
     """Owns a gf_compute_params plus the numpy arrays it points to (quaternion tracks, fovs)."""
 
     def __init__(self, kernel_params: abi.KernelParams, org, smoothed, frame_readout_time_ms=16.0, fovs=None, video_rotation=0.0,
-                 horizontal=False, inverted=False, framebuffer_inverted=False, fov_scale=1.0):
+                 horizontal=False, inverted=False, framebuffer_inverted=False, fov_scale=1.0, sync_offsets=None,
+                 per_frame_time_offsets=None, focal_lengths=None, smoothed_focal_lengths=None, readout_time_scale=0.0, camera_stab=None,
+                 gyro_offset_ms=0.0):
+        """sync_offsets: {timestamp_us: offset_ms} (GyroSource::offsets_adjusted); camera_stab: list (one per frame) of dicts with
+        offset, sensor_size, crop_area, pixel_pitch, ibis=(pos[n], xyz[n,3]), ois=(pos[n], xyz[n,3]) (CameraStabData)."""
         p = kernel_params
         c = abi.ComputeParams()
         c.width, c.height, c.output_width, c.output_height = p.width, p.height, p.output_width, p.output_height
@@ -225,6 +237,40 @@ class ComputeParams:
         c.org = abi.QuatTrack(self._ots.ctypes.data_as(C.POINTER(C.c_int64)), self._oq.ctypes.data_as(C.POINTER(C.c_double)), len(self._ots))
         c.smoothed = abi.QuatTrack(self._sts.ctypes.data_as(C.POINTER(C.c_int64)), self._sq.ctypes.data_as(C.POINTER(C.c_double)), len(self._sts))
         c.duration_ms = float(self._ots[-1] - self._ots[0]) / 1000.0
+        c.gyro_offset_ms = gyro_offset_ms
+        if sync_offsets:
+            ks = sorted(sync_offsets)
+            self._so_ts = np.asarray(ks, dtype=np.int64); self._so_ms = np.asarray([sync_offsets[k] for k in ks], dtype=np.float64)
+            c.sync_offset_ts_us = self._so_ts.ctypes.data_as(C.POINTER(C.c_int64)); c.sync_offset_ms = self._so_ms.ctypes.data_as(C.POINTER(C.c_double))
+            c.n_sync_offsets = len(ks)
+        if per_frame_time_offsets is not None:
+            self._pfo = np.ascontiguousarray(per_frame_time_offsets, dtype=np.float64)
+            c.per_frame_time_offsets = self._pfo.ctypes.data_as(C.POINTER(C.c_double)); c.n_per_frame_time_offsets = self._pfo.size
+        if focal_lengths is not None and smoothed_focal_lengths is not None:
+            self._fl = np.ascontiguousarray(focal_lengths, dtype=np.float64); self._sfl = np.ascontiguousarray(smoothed_focal_lengths, dtype=np.float64)
+            assert self._fl.size == self._sfl.size
+            c.focal_length_smoothing_enabled = 1
+            c.focal_lengths = self._fl.ctypes.data_as(C.POINTER(C.c_double)); c.smoothed_focal_lengths = self._sfl.ctypes.data_as(C.POINTER(C.c_double))
+            c.n_focal_lengths = self._fl.size
+        c.readout_time_scale = readout_time_scale
+        if camera_stab:
+            self._stab_arrays = []
+            arr = (abi.CameraStab * len(camera_stab))()
+            dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+            for i, d in enumerate(camera_stab):
+                cs = arr[i]
+                cs.offset = float(d.get("offset", 0.0))
+                cs.sensor_size[:] = [int(v) for v in d["sensor_size"]]
+                cs.crop_area[:] = [float(v) for v in d["crop_area"]]
+                cs.pixel_pitch[:] = [int(v) for v in d["pixel_pitch"]]
+                for name in ("ibis", "ois"):
+                    pos, xyz = d.get(name, (np.zeros(0), np.zeros((0, 3))))
+                    pos = np.ascontiguousarray(pos, dtype=np.float64); xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+                    assert pos.size == xyz.shape[0]
+                    self._stab_arrays += [pos, xyz]
+                    setattr(cs, name + "_pos", dp(pos)); setattr(cs, name + "_xyz", dp(xyz)); setattr(cs, "n_" + name, pos.size)
+            self._stab = arr
+            c.camera_stab = C.cast(arr, C.c_void_p); c.n_camera_stab = len(camera_stab)
         self.c = c
 
     def at_timestamp(self, timestamp_ms, frame=0):
@@ -252,10 +298,12 @@ class DeviceGyro:
             raise GyroflowCoreError(rc, "gf_cuda_gyro_upload")
         self._h = h
 
-    def frame_transform(self, timestamp_ms, matrices_dev: int, max_rows: int, frame=0, stream=0):
+    def frame_transform(self, timestamp_ms, matrices_dev: int, max_rows: int, frame=0, stream=0, table_flags_dev: int = 0):
+        """FrameTransform::at_timestamp on the device.  table_flags_dev: device word that receives the table's trust verdict.
+        stream = 0: the call waits for the kernel before returning; otherwise it only enqueues (give the warp the same stream)."""
         kp = abi.KernelParams(); rows = C.c_size_t(); fov = C.c_double(); mfov = C.c_double()
-        rc = self._lib.gf_cuda_frame_transform_dev(self._h, C.byref(self.cp.c), timestamp_ms, frame, C.byref(kp), matrices_dev, max_rows,
-                                                   C.byref(rows), C.byref(fov), C.byref(mfov), stream or None)
+        rc = self._lib.gf_cuda_frame_transform_dev_flagged(self._h, C.byref(self.cp.c), timestamp_ms, frame, C.byref(kp), matrices_dev, max_rows,
+                                                           table_flags_dev or None, C.byref(rows), C.byref(fov), C.byref(mfov), stream or None)
         if rc != 0:
             raise GyroflowCoreError(rc, "gf_cuda_frame_transform_dev")
         return kp, rows.value
@@ -316,3 +364,42 @@ def zoom_dynamic(fov_minimal, window_s, fps, method=1):
     if rc != 0:
         raise GyroflowCoreError(rc, "gf_zoom_dynamic_compute")
     return out
+
+
+def scan_tables_dev(matrices_dev: int, matrix_rows: int, table_flags_dev: int, stream: int = 0):
+    """Asynchronous: one small kernel on `stream` writes the table's trust verdict (0 = tame, IBIS-free) to the device word."""
+    rc = abi.load_library().gf_cuda_scan_tables_dev(matrices_dev, matrix_rows, table_flags_dev, stream or None)
+    if rc != 0:
+        raise GyroflowCoreError(rc, "gf_cuda_scan_tables_dev")
+
+
+def bind_thread_to_device(device: int) -> int:
+    """Pin the calling thread to the CPUs of the GPU's NUMA node (call before allocating page-locked buffers).  Returns the CPU count."""
+    return int(abi.load_library().gf_cuda_bind_thread_to_device(device))
+
+
+def stab_config(params: abi.KernelParams, pixel_type: str, digital_lens=None, base_flags=0, background=(0.0, 0.0, 0.0, 0.0),
+                canvas_scale=1.0, show_safe_area=False, adaptive_zoom_window=0.0):
+    """gf_stab_config from the per-buffer half of a KernelParams (what `Stabilization` holds: size, output_size, interpolation, ...)."""
+    st = abi.StabConfig()
+    st.width, st.height, st.output_width, st.output_height = params.width, params.height, params.output_width, params.output_height
+    st.interpolation = params.interpolation
+    st.pixel_type = abi.PIXEL_TYPES[pixel_type][0]
+    st.base_flags = base_flags
+    st.has_digital_lens = 1 if digital_lens else 0
+    st.background[:] = [float(v) for v in background]
+    st.canvas_scale = canvas_scale
+    st.show_safe_area = int(show_safe_area)
+    st.adaptive_zoom_window = adaptive_zoom_window
+    return st
+
+
+def get_frame_transform_at(stab: abi.StabConfig, cp: ComputeParams, buffers: Buffers, kernel_params: abi.KernelParams, mesh=None, frame=0, minimal_fov=1.0):
+    """Stabilization::get_frame_transform_at (stabilization/mod.rs:253-326): completes `kernel_params` (as produced by at_timestamp) in place."""
+    i, o = buffers.input.to_c(), buffers.output.to_c()
+    m = None if mesh is None else np.ascontiguousarray(mesh, dtype=np.float32)
+    rc = abi.load_library().gf_get_frame_transform_at(C.byref(stab), C.byref(cp.c), C.byref(i), C.byref(o), m.ctypes.data if m is not None and m.size else None,
+                                                      m.size if m is not None else 0, frame, minimal_fov, C.byref(kernel_params))
+    if rc != 0:
+        raise GyroflowCoreError(rc, "gf_get_frame_transform_at")
+    return kernel_params

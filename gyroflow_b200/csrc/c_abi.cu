@@ -15,9 +15,10 @@
 #include <algorithm>
 #include <string>
 #include <vector>
-#include <unordered_map>
 
 #include "kernel_registry.h"
+#include "c_abi_internal.h"
+#include <nvtx3/nvToolsExt.h>
 
 using namespace gf;
 
@@ -44,11 +45,11 @@ struct gf_cuda_ctx {
     int width = 0, height = 0, output_width = 0, output_height = 0;    // Stabilization.size / output_size
     KernelFn fn = nullptr;        // general instantiation (run-time feature tests)
     KernelFn fn_lean = nullptr;   // rare features compiled out
-    KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe (unvalidated tables)
-    KernelFn fn_x2t = nullptr;    // same, tables validated: no per-pixel numerator / IBIS tests
-    KernelFn fn_x2c = nullptr, fn_x2ct = nullptr;   // the packed kernel writing a coordinate map (pass 1 of the two-pass path)
-    std::unordered_map<const void*, uint32_t> validated;   // device tables vouched for by gf_cuda_validate_tables_dev
-    unsigned* d_vflags = nullptr;
+    KernelFn fn_x2 = nullptr;     // lean + two pixels per thread on the packed f32x2 pipe; trusted / guarded path picked from a device word
+    KernelFn fn_x2c = nullptr;    // the packed kernel writing a coordinate map (pass 1 of the two-pass path)
+    uint32_t* d_const_flags = nullptr;   // two device words {0, 1}: the verdict of the host scan of host tables, as the kernel wants it
+    uint32_t* d_vflags = nullptr;        // scratch verdict word of gf_cuda_validate_tables_dev
+    cudaStream_t last_stream = nullptr;  // the stream of the most recent call (gf_cuda_synchronize waits for it too)
     uint2* d_coords = nullptr; size_t d_coords_len = 0;   // multi-plane mode: the frame's coordinate map
     KernelFn fn_shade = nullptr;
     unsigned long long aux_launches = 0;   // helper kernels (mesh widening, table scans): not counted by gf_cuda_launch_count
@@ -196,14 +197,25 @@ __global__ void widen_mesh_kernel(const float* __restrict__ m, double* __restric
         aux->to_frame_y = make_map_dev(origin_y, origin_y + crop_h, 0.0f, height_f);
     }
 }
-__global__ void scan_tables_kernel(const float* __restrict__ m, size_t rows, unsigned* flags) {
+// one block: every thread ORs its rows, the block reduces, thread 0 WRITES the verdict (no prior memset, no atomics on the word)
+__global__ void __launch_bounds__(1024) scan_tables_kernel(const float* __restrict__ m, size_t rows, uint32_t* flags) {
+    __shared__ unsigned warp_or[32];
     unsigned f = 0;
-    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
-        const float* p = m + r * GF_MATRIX_STRIDE;
-        for (int i = 0; i < 9; ++i) { const float v = p[i], a = fabsf(v); if (!(v == 0.0f || (a >= 0x1p-40f && a <= 0x1p40f))) f |= TBL_WILD; }
-        for (int i = 9; i < 14; ++i) if (!(p[i] == 0.0f)) f |= TBL_IBIS;
+    const size_t n = rows * GF_MATRIX_STRIDE;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = m[i], a = fabsf(v);
+        const unsigned col = (unsigned)(i % GF_MATRIX_STRIDE);
+        if (col < 9u) { if (!(v == 0.0f || (a >= 0x1p-40f && a <= 0x1p40f))) f |= TBL_WILD; }
+        else if (!(v == 0.0f)) f |= TBL_IBIS;
     }
-    if (f) atomicOr(flags, f);
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31u) == 0u) warp_or[threadIdx.x >> 5] = f;
+    __syncthreads();
+    if (threadIdx.x < 32u) {
+        f = threadIdx.x < (blockDim.x >> 5) ? warp_or[threadIdx.x] : 0u;
+        f = __reduce_or_sync(0xffffffffu, f);
+        if (threadIdx.x == 0u) *flags = f;
+    }
 }
 
 bool lens_noop(int lens, const gf_kernel_params* p) {
@@ -362,14 +374,14 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     { int rc = validate(nullptr, params, in, out, bpp); if (rc != GF_OK) return rc; }
     KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0);
     KernelFn fn_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1);
-    KernelFn fn_x2 = getenv("GF_DISABLE_X2") ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 2);
-    KernelFn fn_x2t = getenv("GF_DISABLE_X2") ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 3);
+    const bool no_x2 = getenv("GF_DISABLE_X2") != nullptr;      // read per context (tests flip it between contexts)
+    KernelFn fn_x2 = no_x2 ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 2);
     if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
 
     gf_cuda_ctx* ctx = new gf_cuda_ctx();
     ctx->device = device; ctx->pixel_type = pixel_type; ctx->distortion_model = distortion_model; ctx->digital_lens = digital_lens;
-    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_x2t = fn_x2t; ctx->fn_shade = gf_shade_kernel(layout);
-    if (!getenv("GF_DISABLE_X2")) { ctx->fn_x2c = find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, 4); ctx->fn_x2ct = find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, 5); }
+    ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_shade = gf_shade_kernel(layout);
+    if (!no_x2) ctx->fn_x2c = find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, 4);
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
     ctx->drawing_len = drawing_len;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
@@ -382,6 +394,12 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     size_t rows = (size_t)std::max(std::max(params->width, params->height), std::max(params->output_width, params->output_height));
     rows = std::max(rows, (size_t)params->matrix_count);
     ctx->max_rows = rows;
+    {
+        const uint32_t words[2] = { 0u, 1u };
+        if ((e = cudaMalloc(&ctx->d_const_flags, sizeof(words))) != cudaSuccess ||
+            (e = cudaMemcpy(ctx->d_const_flags, words, sizeof(words), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMalloc(&ctx->d_vflags, sizeof(uint32_t))) != cudaSuccess) { cuda_fail(ctx, e, "table-verdict words"); return bail(GF_ERR_CUDA); }
+    }
     for (int s = 0; s < kSlots; ++s) {
         Slot& sl = ctx->slots[s];
         if ((e = cudaMallocHost(&sl.h_mat, rows * GF_MATRIX_STRIDE * sizeof(float))) != cudaSuccess ||
@@ -415,6 +433,7 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
     if (ctx->d_src) cudaFree(ctx->d_src);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     if (ctx->d_vflags) cudaFree(ctx->d_vflags);
+    if (ctx->d_const_flags) cudaFree(ctx->d_const_flags);
     if (ctx->d_coords) cudaFree(ctx->d_coords);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
@@ -427,7 +446,8 @@ static int select_variant(bool has_lean, bool has_packed, int ctx_digital_lens, 
     // lean instantiation iff no general-only feature is on, vector access is legal, and the digital-lens flag matches the template
     const bool lean_ok = has_lean && (A.feat & F_GENERAL_ONLY) == 0 && (A.feat & F_LEAN_REQUIRED) == F_LEAN_REQUIRED &&
                          (((A.feat & F_DIGITAL) != 0) == (ctx_digital_lens != GF_LENS_NONE));
-    // packed kernel: trusted variant when the tables were validated (host scan / gf_cuda_validate_tables_dev) and carry no IBIS rows
+    // packed kernel: the trusted code path runs when the table's verdict word is 0 (host scan of host tables, or the device word the
+    // table's producer / gf_cuda_scan_tables_dev wrote); table_flags here is what the HOST knows (non-zero = unknown or guarded)
     // (two-pass: the coordinate-writing variant, except for EWA whose probe positions only the scalar kernels evaluate)
     const bool packed_ok = lean_ok && has_packed && (A.feat & F_WILD) == 0 && !(two_pass && n_maps != 1);
     const int v = packed_ok ? (table_flags == 0 ? PLAN_PACKED_TRUSTED : PLAN_PACKED) : (lean_ok ? PLAN_LEAN : PLAN_GENERAL);
@@ -438,7 +458,8 @@ static int select_variant(bool has_lean, bool has_packed, int ctx_digital_lens, 
 // the coordinates are computed once (pass 1, into ctx->d_coords) and every plane is then sampled from them (pass 2).
 static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
                     const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len,
-                    bool tables_on_device, void* cu_stream, bool sync_host = true, size_t more_planes = 0, bool coord_only = false) {
+                    bool tables_on_device, void* cu_stream, bool sync_host = true, size_t more_planes = 0, bool coord_only = false,
+                    const uint32_t* table_flags_dev = nullptr, uint64_t* checksum_dev = nullptr) {
     if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
     { int rc = validate(ctx, p, in, out, ctx->bpp); if (rc != GF_OK) return rc; }
     if (!matrices) return fail(ctx, GF_ERR_NO_DATA, "NoStabilizationData: matrices is null");
@@ -457,6 +478,7 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
 
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : ctx->stream;
+    ctx->last_stream = st;
 
     WarpArgs A;
     memset(&A, 0, sizeof(A));
@@ -469,13 +491,14 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         CK(cudaEventSynchronize(sl.done));                     // the slot's previous frame has consumed its tables
     }
     if (tables_on_device) {
-        auto it = ctx->validated.find((const void*)matrices);
-        if (it != ctx->validated.end()) table_flags = it->second;
+        // the verdict travels with the data: a device word written on this stream (or ordered before it) by whoever produced the table
+        A.table_flags = table_flags_dev ? table_flags_dev : ctx->d_const_flags + 1;
         A.matrices = matrices;
         A.mesh = mesh_len ? mesh : nullptr;
     } else {
         memcpy(sl.h_mat, matrices, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float));
         table_flags = scan_tables_host(sl.h_mat, (size_t)p->matrix_count);
+        A.table_flags = ctx->d_const_flags + (table_flags ? 1 : 0);
         CK(cudaMemcpyAsync(sl.d_mat, sl.h_mat, (size_t)p->matrix_count * GF_MATRIX_STRIDE * sizeof(float), cudaMemcpyHostToDevice, st));
         A.matrices = sl.d_mat;
         if (mesh_len) {
@@ -495,7 +518,10 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const uint8_t* src = (const uint8_t*)in->ptr;
     uint8_t* dst = (uint8_t*)out->ptr;
     if (in->kind == GF_BUF_HOST) {                             // opencl.rs:359 `self.src.write(buffer)`
-        CK(cudaMemcpyAsync(ctx->d_src, in->ptr, in->len, cudaMemcpyHostToDevice, st));
+        nvtxRangePushA("gf_h2d_frame");
+        cudaError_t e_h2d = cudaMemcpyAsync(ctx->d_src, in->ptr, in->len, cudaMemcpyHostToDevice, st);
+        nvtxRangePop();
+        CK(e_h2d);
         src = ctx->d_src;
     }
     // Does the kernel write every pixel of [0,w) x [0,h)?  (output_rect == whole buffer == output size: the bounds test of
@@ -535,10 +561,12 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         }
         A.coord_out = ctx->d_coords;
     }
-    const bool has_packed = two_pass ? (ctx->fn_x2c && ctx->fn_x2ct) : (ctx->fn_x2 && ctx->fn_x2t);
+    nvtxRangePushA("gf_warp_launch");
+    struct NvtxPop { ~NvtxPop() { nvtxRangePop(); } } nvtx_pop_;
+    const bool has_packed = two_pass ? (ctx->fn_x2c != nullptr) : (ctx->fn_x2 != nullptr);
     const int variant = select_variant(ctx->fn_lean != nullptr, has_packed, ctx->digital_lens, A, table_flags, two_pass, n_maps) & 0xf;
     const bool lean_ok = variant != PLAN_GENERAL;
-    KernelFn x2 = variant == PLAN_PACKED_TRUSTED ? (two_pass ? ctx->fn_x2ct : ctx->fn_x2t) : variant == PLAN_PACKED ? (two_pass ? ctx->fn_x2c : ctx->fn_x2) : nullptr;
+    KernelFn x2 = (variant == PLAN_PACKED_TRUSTED || variant == PLAN_PACKED) ? (two_pass ? ctx->fn_x2c : ctx->fn_x2) : nullptr;
     if (lean_ok && x2) {
         // 32 x 4 threads (4 x 8 output rows... 32 x 8 pixels) per block measured 2 % faster than 32 x 8 threads (finer tail); GF_X2_BLOCK_Y overrides
         static const int by = [] { const char* e = getenv("GF_X2_BLOCK_Y"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }();
@@ -569,14 +597,33 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         }
     }
     if (use_slot) CK(cudaEventRecord(sl.done, st));
+    if (checksum_dev) {                                        // render queue: per-frame output checksum, before the result leaves the device
+        if (gf_cuda_checksum_dev(dst, std::min<size_t>(out->len, (size_t)out->height * (size_t)p->output_stride), checksum_dev, (void*)st) != GF_OK)
+            return fail(ctx, GF_ERR_CUDA, "checksum kernel failed");
+        ctx->aux_launches++;
+    }
     if (out->kind == GF_BUF_HOST) {                                                                                  // opencl.rs:413
-        if (full_cover) CK(cudaMemcpy2DAsync(out->ptr, (size_t)p->output_stride, ctx->d_dst, (size_t)p->output_stride,
-                                             (size_t)out->width * (size_t)bpp, (size_t)out->height, cudaMemcpyDeviceToHost, st));
-        else            CK(cudaMemcpyAsync(out->ptr, ctx->d_dst, out->len, cudaMemcpyDeviceToHost, st));
+        nvtxRangePushA("gf_d2h_frame");
+        cudaError_t e_d2h;
+        if (full_cover) e_d2h = cudaMemcpy2DAsync(out->ptr, (size_t)p->output_stride, ctx->d_dst, (size_t)p->output_stride,
+                                                  (size_t)out->width * (size_t)bpp, (size_t)out->height, cudaMemcpyDeviceToHost, st);
+        else            e_d2h = cudaMemcpyAsync(out->ptr, ctx->d_dst, out->len, cudaMemcpyDeviceToHost, st);
+        nvtxRangePop();
+        CK(e_d2h);
     }
     if (sync_host && (in->kind == GF_BUF_HOST || out->kind == GF_BUF_HOST)) CK(cudaStreamSynchronize(st));
     return GF_OK;
 }
+
+} // extern "C"
+
+int gf_internal_run_frame(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* params,
+                          const float* matrices_dev, size_t matrix_rows, const float* mesh_dev, size_t mesh_len,
+                          const uint32_t* table_flags_dev, void* cu_stream, uint64_t* checksum_dev) {
+    return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, false, 0, false, table_flags_dev, checksum_dev);
+}
+
+extern "C" {
 
 GF_API int gf_cuda_undistort_image(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
                                    const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
@@ -589,6 +636,20 @@ GF_API int gf_cuda_undistort_image_dev(gf_cuda_ctx* ctx, const gf_buffer_desc* i
                                        const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
                                        const float* mesh_dev, size_t mesh_len, void* cu_stream) {
     return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream);
+}
+
+GF_API int gf_cuda_undistort_image_dev_flagged(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                               const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                               const float* mesh_dev, size_t mesh_len, const uint32_t* table_flags_dev, void* cu_stream) {
+    return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, 0, false, table_flags_dev);
+}
+
+GF_API int gf_cuda_scan_tables_dev(const float* matrices_dev, size_t matrix_rows, uint32_t* table_flags_dev, void* cu_stream) {
+    if (!matrices_dev || !table_flags_dev || matrix_rows == 0) return fail(nullptr, GF_ERR_BAD_PARAMS, "null argument");
+    scan_tables_kernel<<<1, 1024, 0, (cudaStream_t)cu_stream>>>(matrices_dev, matrix_rows, table_flags_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "scan_tables_kernel");
+    return GF_OK;
 }
 
 GF_API int gf_cuda_undistort_image_async(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
@@ -724,6 +785,12 @@ static bool planes_share_geometry(const gf_kernel_params* p, const gf_buffer_des
 GF_API int gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
                                         const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
                                         const float* mesh_dev, size_t mesh_len, void* cu_stream) {
+    return gf_cuda_undistort_planes_dev_flagged(ctx, n_planes, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, nullptr, cu_stream);
+}
+
+GF_API int gf_cuda_undistort_planes_dev_flagged(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                                const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                                const float* mesh_dev, size_t mesh_len, const uint32_t* table_flags_dev, void* cu_stream) {
     if (!ctx || !in || !out || !params || n_planes == 0) return fail(ctx, GF_ERR_BAD_PARAMS, "null argument");
     for (size_t i = 0; i < n_planes; ++i) {
         if (in[i].kind != GF_BUF_DEVICE || out[i].kind != GF_BUF_DEVICE) return fail(ctx, GF_ERR_BAD_PARAMS, "gf_cuda_undistort_planes_dev takes DEVICE buffers");
@@ -731,9 +798,9 @@ GF_API int gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_planes, const
     }
     // one coordinate pass for all planes when they share a geometry
     const bool fuse = n_planes > 1 && ctx->fn_shade && planes_share_geometry(params, in, out, n_planes);
-    if (fuse) return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, n_planes - 1);
+    if (fuse) return run_warp(ctx, in, out, params, matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, n_planes - 1, false, table_flags_dev);
     for (size_t i = 0; i < n_planes; ++i) {
-        int rc = run_warp(ctx, &in[i], &out[i], &params[i], matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream);
+        int rc = run_warp(ctx, &in[i], &out[i], &params[i], matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, 0, false, table_flags_dev);
         if (rc != GF_OK) return rc;
     }
     return GF_OK;
@@ -761,21 +828,22 @@ GF_API int gf_cuda_plan(const gf_kernel_params* params, int pixel_type, int dist
     const bool two_pass = n_planes > 1 || params->interpolation != GF_INTERP_BILINEAR;
     const int n_maps = params->interpolation > 8 ? 3 : 1;
     const bool has_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1) != nullptr;
-    const bool has_packed = !getenv("GF_DISABLE_X2") && find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, two_pass ? 5 : 3) != nullptr;
+    const bool has_packed = !getenv("GF_DISABLE_X2") && find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, two_pass ? 4 : 2) != nullptr;
     return select_variant(has_lean, has_packed, digital_lens, A, table_flags, two_pass, n_maps);
 }
 
 GF_API int gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows) {
     if (!ctx || !matrices_dev) return fail(ctx, GF_ERR_BAD_PARAMS, "null argument");
     CK(cudaSetDevice(ctx->device));
-    if (!ctx->d_vflags) CK(cudaMalloc(&ctx->d_vflags, sizeof(unsigned)));
-    CK(cudaMemsetAsync(ctx->d_vflags, 0, sizeof(unsigned), ctx->stream));
-    scan_tables_kernel<<<32, 256, 0, ctx->stream>>>(matrices_dev, matrix_rows, ctx->d_vflags);
+    // A synchronous QUERY: nothing is cached.  (Round 1 kept a pointer-keyed cache of verdicts; a table rewritten in place or an
+    // allocation reused at the same address was then silently trusted.)  To render device tables on the trusted path pass a verdict
+    // word to gf_cuda_undistort_image_dev_flagged — written by gf_cuda_scan_tables_dev or by gf_cuda_frame_transform_dev.
+    CK(cudaDeviceSynchronize());                               // the table may have been written on any stream
+    scan_tables_kernel<<<1, 1024, 0, ctx->stream>>>(matrices_dev, matrix_rows, ctx->d_vflags);
     CK(cudaGetLastError());
-    unsigned f = 0;
-    CK(cudaMemcpyAsync(&f, ctx->d_vflags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t f = 0;
+    CK(cudaMemcpyAsync(&f, ctx->d_vflags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->validated[(const void*)matrices_dev] = f;
     return (int)f;      // 0 = tame and IBIS-free; bit 0 = wild entry, bit 1 = IBIS rows present (both still render correctly, on the guarded path)
 }
 
@@ -783,6 +851,7 @@ GF_API int gf_cuda_synchronize(gf_cuda_ctx* ctx) {
     if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->last_stream && ctx->last_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_stream));   // calls made with a caller-supplied stream
     return GF_OK;
 }
 

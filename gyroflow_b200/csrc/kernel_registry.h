@@ -33,28 +33,27 @@ KernelFn gf_kernel_generic_polynomial(int digital, int layout, int interp, int l
 KernelFn gf_kernel_gopro(int digital, int layout, int interp, int lean);
 KernelFn gf_shade_kernel(int layout);      // pass 2 of the multi-plane mode (shade_kernel.cu)
 
-// lean == 4 / 5: the packed kernel in coordinate-output mode (pass 1 of the two-pass path), untrusted / trusted tables; one
-// instantiation per lens model serves every pixel layout
-// lean == 2 / 3: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form;
-// 3 = tables validated (no wild entries, no IBIS rows), 2 = unvalidated device tables (per-pixel numerator / IBIS tests kept)
+// lean == 4: the packed kernel in coordinate-output mode (pass 1 of the two-pass path); one instantiation per lens model serves
+// every pixel layout
+// lean == 2: the two-pixels-per-thread packed-f32x2 kernel (warp_kernel_x2.cuh), where the lens model has a packed form; it carries
+// both the trusted-table and the guarded code path and picks one from the device word WarpArgs::table_flags
 template <int LENS, int DIGITAL, class PIX>
-static KernelFn pick_x2(int interp, bool trusted) {
+static KernelFn pick_x2(int interp) {
     // packed digital lenses: superview, superview6, hyperview (fisheye pairs) and digital_stretch (every packed lens model)
     if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas) {
         // 6 resident blocks per SM (40 registers): 5 (48 registers, no spills) measured the same, 4 slower, 7 / 8 compile to the 6 code
-        if (interp == GF_INTERP_BILINEAR) return trusted ? warp_kernel_x2<LENS, DIGITAL, PIX, 6, true> : warp_kernel_x2<LENS, DIGITAL, PIX, 6, false>;
+        if (interp == GF_INTERP_BILINEAR) return warp_kernel_x2<LENS, DIGITAL, PIX, 6>;
     }
     return nullptr;
 }
 template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
-    if (lean == 4 || lean == 5) {
+    if (lean == 4) {
         if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas)
-            return lean == 5 ? warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, 6, true, true> : warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, 6, false, true>;
+            return warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, 6, true>;
         return nullptr;
     }
-    if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp, false);
-    if (lean == 3) return pick_x2<LENS, DIGITAL, PIX>(interp, true);
+    if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp);
     switch (interp) {
     case GF_INTERP_BILINEAR: return lean ? warp_kernel<LENS, DIGITAL, PIX, 2, false> : warp_kernel<LENS, DIGITAL, PIX, 2, true>;
     // bicubic / Lanczos4: the same scalar kernels with their run-time high-order sampler (sample_high_order in warp_kernel.cuh)

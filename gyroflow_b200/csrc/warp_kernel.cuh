@@ -78,6 +78,7 @@ struct WarpArgs {
     const struct MeshAux* mesh_aux; // per-frame constants derived from the mesh header by the same helper kernel
     uint2*         coord_out;       // multi-plane mode, pass 1: write the source coordinates of every output pixel here instead of sampling
     const uint2*   coord_in;        // pass 2 (shade_from_coords_kernel): read them back
+    const uint32_t* table_flags;    // device word: 0 = the matrix table is tame and IBIS-free (packed kernel: trusted path), see warp_kernel_x2
     int            coord_shift;     // pass 1: 0 = pixel (x, y); 1 = (x + 0.01, y); 2 = (x, y + 0.01) — the EWA Jacobian probes of :567-572
     int            coord_maps;      // pass 2: 1, or 3 when the two probe maps follow the first one (stride out_cols * out_rows)
     unsigned long long src_len, dst_len;
@@ -364,10 +365,12 @@ static __device__ __noinline__ double mesh_bivariate(const MeshView mesh, uint32
 
 // ------------------------------------------------------------------------------------------
 // Exact division by a per-frame-uniform divisor: q = RN(a / d) from the precomputed rcp = RN(1/d).
-// One Markstein correction step (the same shape as the compiler's own div.rn.f32 fast path, whose refined
-// reciprocal is *less* accurate than RN(1/d)); checked against IEEE division over every float `a` for the
-// divisors that occur here (tools/udiv_check.c).  Outside a conservative magnitude window — or when the host
-// did not vouch for the divisor — the ordinary division is used.
+// One Markstein correction step: with rcp the CORRECTLY ROUNDED reciprocal and q0 = RN(a * rcp) (within one ulp of a / d),
+// RN(q0 + fma(-d, q0, a) * rcp) is the correctly rounded quotient for every a and d as long as no intermediate leaves the
+// normal range (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic, 2nd ed., Thm. 4.8) — the windows below
+// guarantee that.  tools/udiv_check.c confirms it by brute force over every float `a` of the window for a list of divisors
+// (tests/test_gf_math.py runs a strided sweep).  Outside the window — or when the host did not vouch for the divisor — the
+// ordinary division is used.
 // ------------------------------------------------------------------------------------------
 GF_DEV float div_uniform(float a, const MapC& m) {
     const float aa = fabsf(a);
@@ -816,6 +819,15 @@ GF_DEV void sample_ewa(float uvx, float uvy, float4 jac, const WarpArgs& A, floa
     #pragma unroll
     for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
     float sum_div = 0.0f;
+    // Footprint guard.  The bounding box comes straight from the Jacobian; where one probe coordinate is None (-> 0) next to a valid
+    // centre the forward difference is ~1e5 and the box spans ~1e11 taps: the reference's CPU loop would grind through them for
+    // hours, a GPU thread would hang the device.  A footprint of more than 2^22 taps (2048 x 2048; real minification ratios stay
+    // below 16 x 16) is therefore rendered as background — the one documented divergence from the reference's (impractical) result.
+    if (((long long)b1 - (long long)b0 + 1) * ((long long)b3 - (long long)b2 + 1) > (1ll << 22)) {
+        #pragma unroll
+        for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(A.bg[ch], P.pixel_value_limit);
+        return;
+    }
     for (long long in_y = b2; in_y <= (long long)b3; ++in_y) {
         const float in_fy = (float)(int)in_y - uvy;
         const float in_fy2 = in_fy * eb;

@@ -10,8 +10,9 @@
 //     practice never — the pair is re-evaluated with the scalar kernel's code (cold, out of line).  No convergence
 //     barriers, no slow-path stubs inside the arithmetic, so the scheduler can overlap the two lens evaluations' loads,
 //     MUFU ops and FFMA2 chains;
-//   * `TRUSTED` tables: the host (or gf_cuda_validate_tables_dev) has checked that every matrix entry is zero or of
-//     moderate magnitude and that no row carries IBIS data, which removes the per-pixel numerator / IBIS tests.
+//   * `TRUSTED` tables: the producer of the table (host scan, gf_cuda_scan_tables_dev, or the on-device FrameTransform producer)
+//     has established that every matrix entry is zero or of moderate magnitude and that no row carries IBIS data, and left that
+//     verdict in a device word the kernel reads at entry; it removes the per-pixel numerator / IBIS tests.
 // Only the "lean" feature set (F_GENERAL_ONLY in warp_kernel.cuh) is compiled here.
 //
 // Behavioural source: src/core/stabilization/cpu_undistort.rs:133-228, :421-517, :543-625 (as warp_kernel.cuh).
@@ -450,9 +451,8 @@ GF_DEV void shade_lean(bool ok, bool far, float u, float v, int wu, int wv, cons
 
 // COORD: pass 1 of the two-pass mode — write the coordinates to A.coord_out instead of sampling (pixel-format independent: the
 // pixel size then comes from KernelParams, PIX is a placeholder).
-template <int LENS, int DIGITAL, class PIX, int MINB, bool TRUSTED, bool COORD = false>
-__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
-warp_kernel_x2(const __grid_constant__ WarpArgs A) {
+template <int LENS, int DIGITAL, class PIX, bool TRUSTED, bool COORD>
+GF_DEV void warp_x2_body(const WarpArgs& A) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
     const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
@@ -531,6 +531,18 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     }
     if (wr_a) shade_lean<PIX>(ok_a, far_a, u.x, v.x, wu_a, wv_a, A, A.dst + off_a);                     // :615-622
     if (wr_b) shade_lean<PIX>(ok_b, far_b, u.y, v.y, wu_b, wv_b, A, A.dst + off_b);
+}
+
+// The kernel: both table-trust variants in one launch, selected by a DEVICE word.  `A.table_flags` points to the verdict on the
+// matrix table this frame reads — written on the same stream by whoever produced the table (the host scan of host tables via a
+// context-owned constant, gf_cuda_scan_tables_dev for caller-owned device tables, or the on-device producer
+// gf_cuda_frame_transform_dev itself): 0 = every entry zero or 2^-40..2^40 and no IBIS rows.  Trust is therefore a property of
+// the bytes the kernel is about to read, ordered by the stream — not of a host-side pointer cache.  The branch is uniform.
+template <int LENS, int DIGITAL, class PIX, int MINB, bool COORD = false>
+__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
+warp_kernel_x2(const __grid_constant__ WarpArgs A) {
+    if (__ldg(A.table_flags) == 0u) warp_x2_body<LENS, DIGITAL, PIX, true, COORD>(A);
+    else                            warp_x2_body<LENS, DIGITAL, PIX, false, COORD>(A);
 }
 
 } // namespace gf

@@ -15,39 +15,17 @@
 #include <cstring>
 #include <vector>
 #include "lens_models.cuh"
+#include "quat_track.cuh"
+#include "gyro_dev.h"
 
 using namespace gf;
 
 namespace {
 
-struct ZQuat { double w, i, j, k; };
-__host__ __device__ inline ZQuat zq_mul(const ZQuat& a, const ZQuat& b) {
-    return { a.w*b.w - a.i*b.i - a.j*b.j - a.k*b.k, a.w*b.i + a.i*b.w + a.j*b.k - a.k*b.j,
-             a.w*b.j - a.i*b.k + a.j*b.w + a.k*b.i, a.w*b.k + a.i*b.j - a.j*b.i + a.k*b.w };
-}
-__host__ __device__ inline ZQuat zq_slerp(const ZQuat& a, ZQuat b, double t) {
-    double d = a.w*b.w + a.i*b.i + a.j*b.j + a.k*b.k;
-    if (d < 0.0) { b = { -b.w, -b.i, -b.j, -b.k }; d = -d; }
-    if (d >= 1.0) return a;
-    const double hang = acos(d), s = sqrt(1.0 - d*d);
-    if (fabs(s) < 1e-14) return a;
-    const double ta = sin((1.0 - t) * hang) / s, tb = sin(t * hang) / s;
-    return { a.w*ta + b.w*tb, a.i*ta + b.i*tb, a.j*ta + b.j*tb, a.k*ta + b.k*tb };
-}
-struct ZTrack { const int64_t* ts; const double* q; size_t n; };
-__host__ __device__ inline ZQuat zq_at(const ZTrack& t, double duration_ms, double timestamp_ms) {     // gyro_source/mod.rs:857-879
-    if (t.n < 2 || duration_ms <= 0.0) return { 1.0, 0.0, 0.0, 0.0 };
-    int64_t lookup = (int64_t)llround(timestamp_ms * 1000.0);
-    if (lookup > t.ts[t.n - 1]) lookup = t.ts[t.n - 1];
-    if (lookup < t.ts[0]) lookup = t.ts[0];
-    size_t lo = 0, hi = t.n;
-    while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (t.ts[mid] <= lookup) lo = mid; else hi = mid; }
-    const double* p = t.q + 4 * lo;
-    const ZQuat a = { p[0], p[1], p[2], p[3] };
-    if (t.ts[lo] == lookup || lo + 1 >= t.n) return a;
-    const ZQuat b = { p[4], p[5], p[6], p[7] };
-    return zq_slerp(a, b, (double)(lookup - t.ts[lo]) / (double)(t.ts[lo + 1] - t.ts[lo]));
-}
+// quaternion tracks, slerp and the sync-offset lookup are shared with frame_transform.cu (quat_track.cuh)
+typedef Quat ZQuat;
+typedef Track ZTrack;
+__host__ __device__ inline ZQuat zq_mul(const ZQuat& a, const ZQuat& b) { return qmul(a, b); }
 
 struct ZoomFrame {              // per-frame uniforms (host, f64)
     ZQuat q0;                   // smoothed(ts) * org(ts)^-1
@@ -56,7 +34,8 @@ struct ZoomFrame {              // per-frame uniforms (host, f64)
 struct ZoomArgs {
     gf_kernel_params kp;        // as built by undistort_points (:671-683)
     ZTrack org;                 // device-resident track
-    double duration_ms, offset_ms;
+    double duration_ms;
+    SyncOffsets offsets;        // device-resident multi-point sync offsets (or the scalar)
     double new_k[9], rot_c, rot_s, row_readout_time;
     int rs_on, horizontal, suppress_rotation, lens_noop;
     float fx, fy, cx, cy;
@@ -70,7 +49,7 @@ struct ZoomArgs {
 // K_new * R for one point — frame_transform.rs:391-410 (f64), narrowed to f32 like cpu_undistort.rs:764
 __device__ void point_rotation(const ZoomArgs& A, const ZoomFrame& F, float px, float py, float (&rot)[9]) {
     const double quat_time = A.rs_on ? F.start_ts + A.row_readout_time * (double)(A.horizontal ? px : py) : F.start_ts;
-    const ZQuat q = zq_mul(F.q0, zq_at(A.org, A.duration_ms, quat_time - A.offset_ms));
+    const ZQuat q = zq_mul(F.q0, quat_at_timestamp(A.org, A.duration_ms, A.offsets, quat_time));
     const double ww = q.w*q.w, ii = q.i*q.i, jj = q.j*q.j, kk = q.k*q.k;
     const double ij = q.i*q.j*2.0, wk = q.w*q.k*2.0, wj = q.w*q.j*2.0, ik = q.i*q.k*2.0, jk = q.j*q.k*2.0, wi = q.w*q.i*2.0;
     const double rq[9] = { ww+ii-jj-kk, ij-wk, wj+ik, wk+ij, ww-ii+jj-kk, jk-wi, ik-wj, wi+jk, ww-ii-jj+kk };
@@ -323,13 +302,6 @@ bool zoom_lens_noop(int lens, const float* k) {
 
 } // namespace
 
-// shared with frame_transform.cu's handle
-struct gf_cuda_gyro {
-    int device;
-    int64_t* d_org_ts; double* d_org_q; size_t n_org;
-    cudaStream_t stream;
-};
-
 // FrameTransform::get_fov without keyframes — frame_transform.rs:52-58
 static double gf_points_fov(const gf_compute_params* cp, size_t frame, int use_fovs) {
     double fov_scale = cp->fov_scale;
@@ -354,12 +326,14 @@ static double setup_points_args(const gf_cuda_gyro* g, const gf_compute_params& 
     A.new_k[0] = A.new_k[0] * (1.0 / hr) / fov; A.new_k[4] = A.new_k[4] * (1.0 / hr) / fov;
     A.new_k[2] = (double)cp.output_width / 2.0; A.new_k[5] = (double)cp.output_height / 2.0;
     double frt = fabs(cp.frame_readout_time); if (cp.readout_inverted) frt *= -1.0;        // get_frame_readout_time(can_invert = false)
+    if (cp.readout_time_scale != 0.0) frt *= cp.readout_time_scale;                         // capture_area / sensor height of the closest lens_params entry (:26-29)
     A.row_readout_time = frt / (double)(cp.readout_horizontal ? cp.width : cp.height);
     A.rs_on = fabs(frt) > 0.0 ? 1 : 0; A.horizontal = cp.readout_horizontal; A.suppress_rotation = cp.suppress_rotation;
     const double a = cp.video_rotation * (M_PI / 180.0);
     A.rot_c = cos(a); A.rot_s = sin(a);
     A.org = ZTrack{ g->d_org_ts, g->d_org_q, g->n_org };
-    A.duration_ms = cp.duration_ms; A.offset_ms = cp.gyro_offset_ms;
+    A.duration_ms = cp.duration_ms;
+    A.offsets = SyncOffsets{ g->d_off_ts, g->d_off_ms, g->n_offsets, cp.gyro_offset_ms };
     gf_kernel_params& kp = A.kp;                                                            // cpu_undistort.rs:671-683
     kp.width = cp.width; kp.height = cp.height; kp.output_width = cp.output_width; kp.output_height = cp.output_height;
     A.fx = (float)K[0]; A.fy = (float)K[4]; A.cx = (float)K[2]; A.cy = (float)K[5];
@@ -379,11 +353,13 @@ static double setup_points_args(const gf_cuda_gyro* g, const gf_compute_params& 
     return frt;
 }
 // smoothed(ts) * org(ts)^-1 and the readout start time of one frame — frame_transform.rs:376-388
-static ZoomFrame frame_uniforms(const gf_compute_params& cp, double ts, double frt) {
+static ZoomFrame frame_uniforms(const gf_compute_params& cp, double ts, double frt, size_t frame) {
+    if (cp.per_frame_time_offsets && frame < cp.n_per_frame_time_offsets) ts += cp.per_frame_time_offsets[frame];     // frame_transform.rs:384
     const ZTrack horg{ cp.org.ts_us, cp.org.quats, cp.org.n }, hsm{ cp.smoothed.ts_us, cp.smoothed.quats, cp.smoothed.n };
     ZoomFrame f;
-    ZQuat q1 = zq_at(horg, cp.duration_ms, ts - cp.gyro_offset_ms); q1 = { q1.w, -q1.i, -q1.j, -q1.k };
-    f.q0 = zq_mul(zq_at(hsm, cp.duration_ms, ts - cp.gyro_offset_ms), q1);
+    const SyncOffsets ho{ cp.sync_offset_ts_us, cp.sync_offset_ms, (cp.sync_offset_ts_us && cp.sync_offset_ms) ? cp.n_sync_offsets : 0, cp.gyro_offset_ms };
+    const ZQuat q1 = qinv(quat_at_timestamp(horg, cp.duration_ms, ho, ts));
+    f.q0 = zq_mul(quat_at_timestamp(hsm, cp.duration_ms, ho, ts), q1);
     f.start_ts = ts - frt / 2.0;
     return f;
 }
@@ -416,7 +392,7 @@ GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, 
     A.zc_x = (float)cp.adaptive_zoom_center_offset[0] * A.in_w; A.zc_y = (float)cp.adaptive_zoom_center_offset[1] * A.in_h;
     // per-frame uniforms on the host: two O(log n) lookups per frame
     std::vector<ZoomFrame> hf(n);
-    for (size_t i = 0; i < n; ++i) hf[i] = frame_uniforms(cp, timestamps_ms[i], frt);
+    for (size_t i = 0; i < n; ++i) hf[i] = frame_uniforms(cp, timestamps_ms[i], frt, i);
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     ZoomFrame* d_frames = nullptr; double* d_out = nullptr;
     cudaError_t e;
@@ -444,7 +420,7 @@ GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp
     ZoomArgs A;
     const double fov = gf_points_fov(cp, frame, use_fovs);
     const double frt = setup_points_args(g, *cp, distortion_model, fov, lens_correction_amount, A);
-    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt);
+    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt, frame);
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     float2* d_in = nullptr; float* d_out = nullptr;
     cudaError_t e;
@@ -472,7 +448,7 @@ GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* c
     ZoomArgs A;
     const double fov = gf_points_fov(cp, frame, 1);
     const double frt = setup_points_args(g, *cp, distortion_model, fov, 1.0, A);
-    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt);
+    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt, frame);
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     const size_t n = (size_t)cp->width * (size_t)cp->height;
     fn<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, F, nullptr, n, cp->width, cp->height, out_rgb_dev);

@@ -12,6 +12,94 @@ import ctypes as C
 import numpy as np
 
 from . import abi
+from .backend import GyroflowCoreError
+
+
+class RenderQueue:
+    """One GPU's render queue (gf_cuda_queue, csrc/render_queue.cu): `depth` frames in flight, each
+    producer kernel -> [H2D] -> warp -> [checksum] -> [D2H] on its own stream; results come back in submission order.
+
+    bench.py and the multi-GPU tests drive this class: rank r of a world of G submits frames r, r + G, r + 2G, ...
+    (shard_frames) and the per-frame checksums are gathered in frame order (gather_results)."""
+
+    def __init__(self, compute_params, stab: abi.StabConfig, distortion_model: str, digital_lens, in_proto, out_proto,
+                 device=0, depth=4, pin_numa=True, checksum=False):
+        self._lib = abi.load_library()
+        self.cp = compute_params                      # keeps the arrays alive
+        cfg = abi.QueueConfig()
+        cfg.device = device
+        cfg.distortion_model = abi.LENS[distortion_model]
+        cfg.digital_lens = abi.LENS[digital_lens] if digital_lens else 0
+        cfg.depth, cfg.pin_numa, cfg.checksum = depth, int(pin_numa), int(checksum)
+        cfg.stab = stab
+        self.depth = depth
+        self.in_flight = 0
+        h = C.c_void_p()
+        i, o = in_proto.to_c(), out_proto.to_c()
+        rc = self._lib.gf_cuda_queue_create(C.byref(h), C.byref(cfg), C.byref(compute_params.c), C.byref(i), C.byref(o))
+        if rc != 0:
+            raise GyroflowCoreError(rc, "gf_cuda_queue_create: " + (self._lib.gf_cuda_last_error(None) or b"").decode())
+        self._h = h
+
+    def _err(self, rc, what):
+        return GyroflowCoreError(rc, what + ": " + (self._lib.gf_cuda_queue_last_error(self._h) or b"").decode())
+
+    def submit(self, frame: int, timestamp_ms: float, buffers, mesh=None):
+        """Enqueue one frame.  The queue must have a free slot (in_flight < depth): call wait() first otherwise."""
+        i, o = buffers.input.to_c(), buffers.output.to_c()
+        m = None if mesh is None else np.ascontiguousarray(mesh, dtype=np.float32)
+        rc = self._lib.gf_cuda_queue_submit(self._h, frame, timestamp_ms, C.byref(i), C.byref(o),
+                                            m.ctypes.data if m is not None and m.size else None, m.size if m is not None else 0)
+        if rc != 0:
+            raise self._err(rc, "gf_cuda_queue_submit")
+        self.in_flight += 1
+
+    def wait(self):
+        """Block until the oldest in-flight frame is finished; returns (frame, checksum)."""
+        f = C.c_size_t(); s = C.c_uint64()
+        rc = self._lib.gf_cuda_queue_wait(self._h, C.byref(f), C.byref(s))
+        if rc != 0:
+            raise self._err(rc, "gf_cuda_queue_wait")
+        self.in_flight -= 1
+        return int(f.value), int(s.value)
+
+    def render(self, frames, timestamp_of, buffers_of, mesh_of=None):
+        """Run `frames` (an iterable of frame indices) through the queue keeping it full; returns {frame: checksum} in frame order."""
+        out = {}
+        for f in frames:
+            if self.in_flight == self.depth:
+                k, v = self.wait(); out[k] = v
+            self.submit(f, timestamp_of(f), buffers_of(f), mesh_of(f) if mesh_of else None)
+        while self.in_flight:
+            k, v = self.wait(); out[k] = v
+        return dict(sorted(out.items()))
+
+    def drain(self):
+        rc = self._lib.gf_cuda_queue_drain(self._h)
+        if rc != 0:
+            raise self._err(rc, "gf_cuda_queue_drain")
+        self.in_flight = 0
+
+    @property
+    def launch_count(self):
+        return int(self._lib.gf_cuda_queue_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gf_cuda_queue_destroy(self._h); self._h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+
+def checksum_host(buf: np.ndarray) -> int:
+    """The queue's per-frame checksum on the host: sum(word[i] * (2 i + 1)) mod 2^64 over the buffer's 32-bit words."""
+    w = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    w = w[: w.size // 4 * 4].view(np.uint32).astype(np.uint64)
+    k = np.arange(w.size, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        return int((w * k).sum(dtype=np.uint64))
 
 
 def shard_frames(n_frames, world, rank):
@@ -50,8 +138,14 @@ def broadcast_tables(params, matrices, dist, torch, device, src=0):
     return params_from_tensor(pt), mt
 
 
+def _as_i64(v):
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
 def gather_results(local, dist, torch, device, dst=0):
-    """Collect {frame: value} dicts (small per-frame results such as checksums) on `dst`, restoring frame order."""
+    """Collect {frame: value} dicts (small per-frame results such as 64-bit checksums) on every rank, restoring frame order."""
+    local = {k: _as_i64(int(v)) for k, v in local.items()}
     world = dist.get_world_size()
     keys = torch.tensor(sorted(local), dtype=torch.int64, device=device)
     vals = torch.tensor([local[k] for k in sorted(local)], dtype=torch.int64, device=device)
@@ -66,5 +160,5 @@ def gather_results(local, dist, torch, device, dst=0):
     out = {}
     for k, v in zip(ks, vs):
         for a, b in zip(k.tolist(), v.tolist()):
-            if a >= 0: out[a] = b
+            if a >= 0: out[a] = b & ((1 << 64) - 1)
     return dict(sorted(out.items()))

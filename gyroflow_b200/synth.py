@@ -1,14 +1,9 @@
-"""Synthetic inputs for tests and bench.py: frames, a 240 Hz gyro track, lens coefficients,
-and a numpy (f64) restatement of the reference's per-frame transform producer.
-
-  quat_at_timestamp      <- GyroSource::quat_at_timestamp   src/core/gyro_source/mod.rs:857-879
-  frame_transform        <- FrameTransform::at_timestamp    src/core/stabilization/frame_transform.rs:165-350
-                            (no-metadata case: fixed camera matrix, no IBIS/OIS splines, no keyframes)
-  kernel_params_for      <- Stabilization::get_frame_transform_at  src/core/stabilization/mod.rs:253-326
+"""Synthetic inputs for tests and bench.py: high-entropy frames, a 240 Hz gyro track, lens coefficients, a
+9x9 mesh, and a KernelParams template with the reference's defaults.  DATA GENERATORS ONLY: the numpy restatement of the
+per-frame producer (FrameTransform::at_timestamp) that round 1 kept here is test infrastructure and lives in
+tests/np_producer.py; the product's producer is csrc/frame_transform.cu behind the C ABI.
 
 Quaternions are (w, x, y, z), Hamilton product, like nalgebra's UnitQuaternion<f64>.
-The values this module produces are *inputs* of the warp (matrices[], KernelParams); bit-parity is defined
-downstream of them, so numpy's pinv/slerp need not match nalgebra's to the last bit.
 """
 import math
 
@@ -69,54 +64,12 @@ def q_normalize(q):
     return q / np.linalg.norm(q, axis=-1, keepdims=True)
 
 
-def q_slerp(a, b, t):
-    """UnitQuaternion::slerp (nalgebra 0.34): shortest arc, linear fallback never needed for distinct neighbours."""
-    d = np.sum(a * b, axis=-1, keepdims=True)
-    b = np.where(d < 0.0, -b, b)
-    d = np.abs(d)
-    d = np.clip(d, -1.0, 1.0)
-    hang = np.arccos(d)
-    s = np.sqrt(1.0 - d * d)
-    t = np.asarray(t)[..., None]
-    small = s < 1e-12
-    s_safe = np.where(small, 1.0, s)
-    ta = np.where(small, 1.0 - t, np.sin((1.0 - t) * hang) / s_safe)
-    tb = np.where(small, t, np.sin(t * hang) / s_safe)
-    return a * ta + b * tb
-
-
-def q_to_matrix(q):
-    w, i, j, k = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
-    ww, ii, jj, kk = w * w, i * i, j * j, k * k
-    ij, wk, wj, ik, jk, wi = i * j * 2.0, w * k * 2.0, w * j * 2.0, i * k * 2.0, j * k * 2.0, w * i * 2.0
-    m = np.empty(q.shape[:-1] + (3, 3))
-    m[..., 0, 0] = ww + ii - jj - kk; m[..., 0, 1] = ij - wk;           m[..., 0, 2] = wj + ik
-    m[..., 1, 0] = wk + ij;           m[..., 1, 1] = ww - ii + jj - kk; m[..., 1, 2] = jk - wi
-    m[..., 2, 0] = ik - wj;           m[..., 2, 1] = wi + jk;           m[..., 2, 2] = ww - ii - jj + kk
-    return m
-
-
 class GyroTrack:
     """`TimeQuat = BTreeMap<i64 us, UnitQuaternion<f64>>` as sorted arrays (gyro_source/mod.rs:34)."""
 
     def __init__(self, ts_us, quats):
         self.ts = np.asarray(ts_us, dtype=np.int64)
         self.q = np.asarray(quats, dtype=np.float64)
-
-    def quat_at_timestamp(self, timestamp_ms):
-        """gyro_source/mod.rs:857-879 with zero sync offset; vectorised over timestamp_ms."""
-        t = np.atleast_1d(np.asarray(timestamp_ms, dtype=np.float64))
-        us = t * 1000.0
-        lookup = np.clip((np.sign(us) * np.floor(np.abs(us) + 0.5)).astype(np.int64), self.ts[0], self.ts[-1])   # f64::round: half away from zero
-        i1 = np.searchsorted(self.ts, lookup, side="right") - 1          # last key <= lookup
-        i2 = np.minimum(np.searchsorted(self.ts, lookup, side="left"), len(self.ts) - 1)   # first key >= lookup
-        t1, t2 = self.ts[i1], self.ts[i2]
-        exact = t1 == lookup
-        dt = np.where(exact, 1, t2 - t1).astype(np.float64)
-        fract = np.where(exact, 0.0, (lookup - t1).astype(np.float64) / dt)
-        out = q_slerp(self.q[i1], self.q[i2], fract)
-        out = np.where(exact[:, None], self.q[i1], out)
-        return out
 
 
 def synthetic_gyro(duration_s, rate_hz=240.0, seed=42):
@@ -222,50 +175,6 @@ def base_kernel_params(width, height, out_width=None, out_height=None, pixel_typ
     p.digital_lens = abi.LENS[digital_lens] if digital_lens else 0
     p.safe_area_rect[:] = [0.0, 0.0, float(out_width), float(out_height)]
     return p
-
-
-def frame_matrices(p, org, smoothed, timestamp_ms, frame_readout_time_ms=16.0, video_rotation_deg=0.0,
-                   horizontal=False, framebuffer_inverted=False, ibis=None):
-    """FrameTransform::at_timestamp rows — frame_transform.rs:221-308 (f64 -> f32).
-
-    ibis: optional callable row -> (sx, sy, ra_rad, ox, oy) filling m[9..13] (synthetic stand-in for the IBIS/OIS splines)."""
-    fx, fy, cx, cy = float(p.f[0]), float(p.f[1]), float(p.c[0]), float(p.c[1])
-    fov = float(p.fov)
-    new_k = np.array([[fx / fov, 0.0, p.output_width / 2.0], [0.0, fy / fov, p.output_height / 2.0], [0.0, 0.0, 1.0]])   # get_new_k :37-51
-    frt = frame_readout_time_ms
-    n = (p.width if horizontal else p.height)
-    rows = n if abs(frt) > 0.0 else 1
-    row_readout_time = frt / n
-    start_ts = timestamp_ms - frt / 2.0
-    a = math.radians(video_rotation_deg)
-    image_rotation = np.array([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
-    quat1 = q_inv(org.quat_at_timestamp(timestamp_ms)[0])
-    sq1 = smoothed.quat_at_timestamp(timestamp_ms)[0]
-    qt = start_ts + row_readout_time * np.arange(rows) if abs(frt) > 0.0 else np.array([start_ts])
-    quat = q_mul(q_mul(sq1[None, :], quat1[None, :]), org.quat_at_timestamp(qt))
-    r = image_rotation[None] @ q_to_matrix(quat)
-    if framebuffer_inverted:
-        r[:, 0, 2] *= -1; r[:, 1, 2] *= -1; r[:, 2, 0] *= -1; r[:, 2, 1] *= -1
-    else:
-        r[:, 0, 1] *= -1; r[:, 0, 2] *= -1; r[:, 1, 0] *= -1; r[:, 2, 0] *= -1
-    i_r = np.linalg.pinv(new_k[None] @ r, rcond=1e-6)
-    m = np.zeros((rows, 14), dtype=np.float32)
-    m[:, :9] = i_r.reshape(rows, 9).astype(np.float32)
-    if ibis is not None:
-        for y in range(rows):
-            m[y, 9:14] = np.asarray(ibis(y), dtype=np.float32)
-    return m
-
-
-def identity_matrices(p, rows=1):
-    """Identity quaternions: i_r = inverse(new_k) for every row."""
-    fov = float(p.fov)
-    new_k = np.array([[p.f[0] / fov, 0.0, p.output_width / 2.0], [0.0, p.f[1] / fov, p.output_height / 2.0], [0.0, 0.0, 1.0]], dtype=np.float64)
-    r = np.eye(3); r[0, 1] *= -1; r[0, 2] *= -1; r[1, 0] *= -1; r[2, 0] *= -1
-    i_r = np.linalg.pinv(new_k @ r)
-    m = np.zeros((rows, 14), dtype=np.float32)
-    m[:, :9] = i_r.reshape(1, 9).astype(np.float32)
-    return m
 
 
 # ------------------------------------------------------------------------------------------ mesh (config 4)

@@ -264,18 +264,34 @@ GF_API int         gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_plane
                                                 const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
                                                 const float* mesh_dev, size_t mesh_len, void* cu_stream);
 
-/* Device-resident tables (gf_cuda_undistort_image_dev) are untrusted by default: the kernel keeps per-pixel tests for wild matrix
- * entries and IBIS rows.  This call scans `matrix_rows x 14` floats on the device once and remembers the verdict for that pointer
- * (until gf_cuda_destroy; call it again after rewriting the table).  Returns 0 (tame, IBIS-free: fastest path), a positive bit mask
- * (1 = wild entry, 2 = IBIS rows; still rendered correctly), or a negative GF_ERR_*.  Host tables are scanned while they are staged. */
+/* Table trust for DEVICE-resident tables.  The packed kernel has a fast path that assumes every matrix entry is zero or of
+ * moderate magnitude (2^-40..2^40) and that no row carries IBIS data; otherwise it keeps per-pixel guards.  Which path runs is
+ * decided ON THE DEVICE from a verdict word that travels with the table (0 = tame and IBIS-free), read by the kernel at entry and
+ * ordered by the stream like the table itself — there is no host-side cache keyed by pointer:
+ *   - host tables (gf_cuda_undistort_image): scanned on the host while they are staged;
+ *   - gf_cuda_frame_transform_dev: writes the verdict of the table it produces into `table_flags_dev`;
+ *   - caller-owned device tables: gf_cuda_scan_tables_dev(matrices_dev, rows, table_flags_dev, stream) — asynchronous, one small
+ *     kernel on `cu_stream` (which must be ordered after the writes of the table);
+ *   - gf_cuda_undistort_image_dev (no verdict word): always the guarded path.
+ * The verdict must cover at least params->matrix_count rows.  Whoever rewrites the table must rewrite the word (or pass NULL).
+ * gf_cuda_validate_tables_dev is the synchronous query form: it waits for the device, scans, and returns 0, a positive bit mask
+ * (1 = wild entry, 2 = IBIS rows) or a negative GF_ERR_*; it remembers nothing. */
+GF_API int         gf_cuda_scan_tables_dev(const float* matrices_dev, size_t matrix_rows, uint32_t* table_flags_dev, void* cu_stream);
+GF_API int         gf_cuda_undistort_image_dev_flagged(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                                       const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                                       const float* mesh_dev, size_t mesh_len, const uint32_t* table_flags_dev, void* cu_stream);
+GF_API int         gf_cuda_undistort_planes_dev_flagged(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                                        const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
+                                                        const float* mesh_dev, size_t mesh_len, const uint32_t* table_flags_dev, void* cu_stream);
 GF_API int         gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* matrices_dev, size_t matrix_rows);
 
 /* Host-only planning query (no CUDA call): which kernel variant would render a frame with these parameters.
- * table_flags: 0 = tables validated tame and IBIS-free (what the host scan / gf_cuda_validate_tables_dev establish), else non-zero.
+ * table_flags: what the verdict word will hold — 0 = tame and IBIS-free, else non-zero.
  * Returns 0 general, 1 lean, 2 packed, 3 packed with trusted tables, OR-ed with 0x10 when the two-pass path is used; < 0 on error. */
 GF_API int         gf_cuda_plan(const gf_kernel_params* params, int pixel_type, int distortion_model, int digital_lens,
                                 const gf_buffer_desc* in, const gf_buffer_desc* out, size_t mesh_len, uint32_t table_flags, size_t n_planes);
 
+/* Waits for the context's own stream AND for the stream of the most recent call that named one. */
 GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
 GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
 GF_API const char* gf_cuda_backend_name(void);               /* ProcessedInfo.backend: "CUDA" (mod.rs:195-201) */
@@ -294,8 +310,10 @@ GF_API int         gf_cuda_selftest_exhaustive(int device, unsigned long long* o
 /* ------------------------------------------------------------------------------------------
  * Per-frame transform producer — FrameTransform::at_timestamp, src/core/stabilization/frame_transform.rs:165-350,
  * with GyroSource::quat_at_timestamp, src/core/gyro_source/mod.rs:857-879.  f64 like the reference.
- * Scope: the no-metadata case (fixed camera matrix, no keyframes, no lens interpolation, no IBIS/OIS splines, no mesh):
- * what the render path computes for an ordinary clip.  The 3x3 pinv(K_new * R) is an analytic f64 inverse (nalgebra
+ * Scope: everything at_timestamp computes from numbers — readout timing incl. the capture-area scale and per-frame time offsets,
+ * focal-length FOV compensation, multi-point sync offsets, the per-row quaternion product, the IBIS / OIS spline rows.  What it
+ * reads through Rust objects stays in Rust: keyframe curves (pass the per-timestamp values in the scalar fields),
+ * lens-profile interpolation (pass the resulting camera matrix / coefficients), mesh extraction (pass mesh_data to the warp).  The 3x3 pinv(K_new * R) is an analytic f64 inverse (nalgebra
  * uses an SVD; both round to the same f32 except for last-ulp cases — `matrices` are *inputs* of the bit-exact contract).
  * ---------------------------------------------------------------------------------------- */
 typedef struct gf_quat_track {          /* TimeQuat = BTreeMap<i64 us, UnitQuaternion<f64>> (gyro_source/mod.rs:34) as sorted arrays */
@@ -326,7 +344,27 @@ typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_p
     double  gyro_offset_ms;                                      /* offset_at_video_timestamp for a single sync point */
     double  duration_ms;                                         /* <= 0: quat_at_timestamp returns identity (:858) */
     gf_quat_track org, smoothed;                                 /* quaternions / smoothed_quaternions (stored form smooth^-1 * org) */
+    /* ---- optional per-clip metadata (zero-initialised = absent) -------------------------------------------------------------- */
+    const int64_t* sync_offset_ts_us; const double* sync_offset_ms; size_t n_sync_offsets;   /* GyroSource::offsets_adjusted, sorted by
+                                                                  * key (gyro_source/mod.rs:884-909); n == 0: gyro_offset_ms alone */
+    const double* per_frame_time_offsets; size_t n_per_frame_time_offsets;                   /* file_metadata.per_frame_time_offsets (:224) */
+    int32_t focal_length_smoothing_enabled;                      /* focal_length_fov_compensation (:70-80); NaN or <= 0 = None */
+    const double* focal_lengths; const double* smoothed_focal_lengths; size_t n_focal_lengths;
+    double  readout_time_scale;                                  /* capture_area_size.1 / sensor_size_px.1 of the lens_params entry closest
+                                                                  * to the timestamp (get_frame_readout_time :26-29); 0 = none (1.0) */
+    const struct gf_camera_stab* camera_stab; size_t n_camera_stab;   /* file_metadata.camera_stab_data, one entry per frame (:227-236, :269-287) */
 } gf_compute_params;
+
+/* CameraStabData (src/core/gyro_source/file_metadata.rs:41-48): IBIS / OIS motion of one frame as Catmull-Rom splines over the
+ * sensor row (gyro_source/splines.rs:8-83).  Points are (position, Vector3) pairs: `*_pos[n]` ascending, `*_xyz[n][3]`. */
+typedef struct gf_camera_stab {
+    double   offset;
+    uint32_t sensor_size[2];
+    float    crop_area[4];
+    uint32_t pixel_pitch[2];
+    const double* ibis_pos; const double* ibis_xyz; size_t n_ibis;
+    const double* ois_pos;  const double* ois_xyz;  size_t n_ois;
+} gf_camera_stab;
 
 /* Host producer.  Fills the fields at_timestamp sets in `out_params` (everything else zeroed: `..Default::default()`),
  * writes rows x 14 f32 to `out_matrices` (rows = 1, height, or width for horizontal readout).  Returns GF_OK or
@@ -343,6 +381,16 @@ GF_API void gf_cuda_gyro_free(gf_cuda_gyro* g);
 GF_API int  gf_cuda_frame_transform_dev(gf_cuda_gyro* g, const gf_compute_params* cp, double timestamp_ms, size_t frame,
                                         gf_kernel_params* out_params, float* matrices_dev, size_t max_rows,
                                         size_t* out_rows, double* out_fov, double* out_minimal_fov, void* cu_stream);
+/* Same, and the kernel also leaves the table's trust verdict (0 = tame and IBIS-free; see gf_cuda_undistort_image_dev_flagged) in
+ * `table_flags_dev` — produced with the table, ordered with it on the stream, no host round trip.
+ * STREAM ORDERING (both forms): with cu_stream == NULL the kernel runs on the gyro object's own stream and the call waits for it
+ * before returning, so any later consumer may read the table; with a stream the call only enqueues — give the warp call the same
+ * stream (or order the two with an event). */
+GF_API int  gf_cuda_frame_transform_dev_flagged(gf_cuda_gyro* g, const gf_compute_params* cp, double timestamp_ms, size_t frame,
+                                                gf_kernel_params* out_params, float* matrices_dev, size_t max_rows, uint32_t* table_flags_dev,
+                                                size_t* out_rows, double* out_fov, double* out_minimal_fov, void* cu_stream);
+/* the same verdict for a host table (what the staging path of gf_cuda_undistort_image computes) */
+GF_API uint32_t gf_table_flags_host(const float* matrices, size_t rows);
 
 /* ------------------------------------------------------------------------------------------
  * Adaptive-zoom companion — zooming::FovIterative (src/core/zooming/fov_iterative.rs:31-189) over
@@ -375,6 +423,66 @@ GF_API int gf_cuda_generate_stmap(gf_cuda_gyro* g, const gf_compute_params* cp, 
                                   void* cu_stream);
 
 GF_API int gf_zoom_dynamic_compute(const double* fov_minimal, size_t n, double window_s, double fps, int method, double* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Stabilization::get_frame_transform_at<T> — src/core/stabilization/mod.rs:253-326 (with get_kernel_flags :226-251 and
+ * get_rect :209-224): completes the KernelParams FrameTransform::at_timestamp produced with the per-buffer fields — pixel limits,
+ * sizes and strides, interpolation, background, bytes per pixel, flags, EWA coefficients, safe-area rect, buffer rotations,
+ * source / output rects.  Host only, no CUDA call.  `kp` in: the fields at_timestamp sets (gf_frame_transform_at_timestamp /
+ * gf_cuda_frame_transform_dev); out: complete.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gf_stab_config {            /* the fields of `Stabilization` the function reads */
+    int32_t width, height;                 /* self.size */
+    int32_t output_width, output_height;   /* self.output_size */
+    int32_t interpolation;                 /* Interpolation as i32: 2, 4, 8, 10..13 */
+    int32_t pixel_type;                    /* GF_PIX_*: T::COUNT, T::SCALAR_BYTES, T::default_max_value() */
+    int32_t base_flags;                    /* self.kernel_flags: FIX_COLOR_RANGE / FILL_WITH_BACKGROUND / DRAWING_ENABLED as set by the caller */
+    int32_t has_digital_lens;              /* compute_params.digital_lens.is_some() */
+    int32_t light_refraction_keyframed;    /* keyframes.is_keyframed(LightRefractionCoeff) */
+    int32_t has_ibis_data;                 /* file_metadata.camera_stab_data.len() > frame (cp->camera_stab is consulted as well) */
+    int32_t show_safe_area;                /* compute_params.show_safe_area */
+    float   background[4];                 /* compute_params.background */
+    float   canvas_scale;                  /* self.drawing.scale */
+    double  adaptive_zoom_window;          /* compute_params.adaptive_zoom_window */
+} gf_stab_config;
+GF_API int gf_get_frame_transform_at(const gf_stab_config* stab, const gf_compute_params* cp, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                     const float* mesh, size_t mesh_len, size_t frame, double minimal_fov, gf_kernel_params* kp);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame-sharded render queue (the shape of rendering/mod.rs:451,531-542,657-661 with rendering/render_queue.rs:550-612
+ * turned inside out: instead of whole jobs in parallel, the frames of one job run `depth` deep on one GPU, and `i -> GPU i mod G`
+ * across the processes of a box).  One queue = one device: `depth` slots, each with its own stream, device table + verdict word,
+ * and (HOST buffers) device staging.  Per submitted frame, all on the slot's stream, nothing synchronous:
+ *     gf_cuda_frame_transform_dev_flagged (table + verdict on the device)  ->  [H2D]  ->  warp  ->  [checksum]  ->  [D2H]
+ * gf_cuda_queue_submit never blocks: with `depth` frames already in flight it fails with GF_ERR_BAD_PARAMS ("queue full") — call
+ * gf_cuda_queue_wait first; gf_cuda_queue_wait blocks until the OLDEST frame is done and returns frames in submission order.  HOST buffers must be page-locked and stay valid until the
+ * frame has been waited for.  The optional checksum is sum(word[i] * (2 i + 1)) mod 2^64 over the output buffer's 32-bit words.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gf_cuda_queue gf_cuda_queue;
+typedef struct gf_queue_config {
+    int32_t device;
+    int32_t distortion_model, digital_lens;   /* GF_LENS_* (digital_lens: GF_LENS_NONE for Option::None) */
+    int32_t depth;                            /* frames in flight, 1..16 */
+    int32_t pin_numa;                         /* non-zero: gf_cuda_bind_thread_to_device(device) before any staging is allocated */
+    int32_t checksum;                         /* non-zero: compute the per-frame output checksum */
+    gf_stab_config stab;
+} gf_queue_config;
+GF_API int      gf_cuda_queue_create(gf_cuda_queue** out, const gf_queue_config* cfg, const gf_compute_params* cp,
+                                     const gf_buffer_desc* in_proto, const gf_buffer_desc* out_proto);
+GF_API int      gf_cuda_queue_submit(gf_cuda_queue* q, size_t frame, double timestamp_ms, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                     const float* mesh, size_t mesh_len);
+GF_API int      gf_cuda_queue_wait(gf_cuda_queue* q, size_t* out_frame, uint64_t* out_checksum);   /* GF_ERR_NO_DATA when nothing is in flight */
+GF_API int      gf_cuda_queue_drain(gf_cuda_queue* q);                                             /* wait for everything, discard the results */
+GF_API uint64_t gf_cuda_queue_launches(gf_cuda_queue* q);                                          /* warp + producer (+ checksum) kernels launched */
+GF_API void     gf_cuda_queue_destroy(gf_cuda_queue* q);
+GF_API const char* gf_cuda_queue_last_error(gf_cuda_queue* q);
+
+/* Bind the calling thread to the CPUs of the NUMA node the GPU hangs off (/sys/bus/pci/devices/<bdf>/local_cpulist), so that
+ * page-locked staging allocated afterwards — by this library or by the caller — is node-local and the copy threads do not cross
+ * the socket interconnect.  Returns the number of CPUs in the mask, 0 if the topology is unknown (nothing changed), < 0 on error. */
+GF_API int      gf_cuda_bind_thread_to_device(int device);
+/* sum(word[i] * (2 i + 1)) mod 2^64 over len / 4 words of device memory, accumulated into *out_dev (zeroed first), on `cu_stream` */
+GF_API int      gf_cuda_checksum_dev(const void* ptr_dev, size_t len, uint64_t* out_dev, void* cu_stream);
 
 #ifdef __cplusplus
 }

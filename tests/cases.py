@@ -5,6 +5,7 @@ import math
 import numpy as np
 
 from gyroflow_b200 import abi, synth
+from tests import np_producer
 
 _GYRO = {}
 
@@ -55,7 +56,7 @@ def build(case):
         p.flags |= case["flags"]
     rs = case.get("rs", True)
     if case.get("identity"):
-        m = synth.identity_matrices(p, rows=(h if rs else 1))
+        m = np_producer.identity_matrices(p, rows=(h if rs else 1))
     else:
         org, sm = gyro()
         ibis = None
@@ -64,7 +65,7 @@ def build(case):
             def ibis(y, n=n):
                 t = y / max(n - 1, 1)
                 return (3.0 * math.sin(6.28 * t), -3.0 * math.cos(6.28 * t), math.radians(0.2) * math.sin(3.0 * t), math.sin(9.0 * t), -math.cos(5.0 * t))
-        m = synth.frame_matrices(p, org, sm, case.get("ts", 1000.0), frame_readout_time_ms=(case.get("readout", 16.0) if rs else 0.0),
+        m = np_producer.frame_matrices(p, org, sm, case.get("ts", 1000.0), frame_readout_time_ms=(case.get("readout", 16.0) if rs else 0.0),
                                  video_rotation_deg=case.get("video_rotation", 0.0), horizontal=bool(case.get("horizontal_rs")), ibis=ibis)
     if case.get("matrix_hook"):
         m = np.ascontiguousarray(case["matrix_hook"](m.copy()), dtype=np.float32)

@@ -1,12 +1,12 @@
 """The per-frame transform producer (FrameTransform::at_timestamp, frame_transform.rs:165-350): the C++ host
-implementation against the numpy f64 restatement in gyroflow_b200/synth.py (the producer's oracle).  `matrices` are
+implementation against the numpy f64 restatement in tests/np_producer.py (the producer's oracle).  `matrices` are
 inputs of the bit-exact warp contract; nalgebra's SVD pinv is not reproducible bit for bit, so the bar is 1 f32 ulp."""
 import numpy as np
 import pytest
 
 import gyroflow_b200 as g
 from gyroflow_b200 import synth
-from tests import cases
+from tests import cases, np_producer
 
 
 def ulp_diff(a, b):
@@ -27,7 +27,7 @@ def test_host_producer_matches_numpy_restatement(kw):
             frt = -frt                          # ReadoutDirection::is_inverted (:32-34)
         if kw.get("framebuffer_inverted") and not kw.get("horizontal"):
             frt = -abs(frt)                     # get_frame_readout_time: inverted framebuffer flips the vertical readout (:29-31)
-        want = synth.frame_matrices(p, org, sm, ts, frame_readout_time_ms=frt, video_rotation_deg=kw.get("video_rotation", 0.0),
+        want = np_producer.frame_matrices(p, org, sm, ts, frame_readout_time_ms=frt, video_rotation_deg=kw.get("video_rotation", 0.0),
                                     horizontal=kw.get("horizontal", False), framebuffer_inverted=kw.get("framebuffer_inverted", False))
         assert m.shape == want.shape and kp.matrix_count == want.shape[0]
         assert float(ulp_diff(m[:, :9], want[:, :9]).max()) <= 1.0
@@ -80,3 +80,84 @@ def test_device_producer_matches_host_and_feeds_the_warp():
         assert np.array_equal(ref, tdst.cpu().numpy())
         wr.close()
     dg.close()
+
+
+# ---- the widened producer: multi-point sync offsets, per-frame time offsets, focal-length compensation, IBIS / OIS spline rows ----
+def _stab(frames, h, seed=5):
+    """Synthetic CameraStabData per frame: sensor 6000 x 4000, crop (500, 300, 5000, 3400), 8.4 um pixel pitch (x1000 nm units as in the
+    metadata), 24 spline points over the sensor rows for IBIS (x, y, roll in millidegrees) and OIS (x, y, 0)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for f in range(frames):
+        pos = np.linspace(250.0, 3750.0, 24) + rng.uniform(-20, 20, 24)
+        pos.sort()
+        ibis = np.stack([2.0e5 * np.sin(pos / 700.0 + f), -1.5e5 * np.cos(pos / 500.0), 150.0 * np.sin(pos / 900.0 + 0.3 * f)], axis=1)
+        ois = np.stack([6.0e4 * np.cos(pos / 300.0 + f), 4.0e4 * np.sin(pos / 450.0), np.zeros_like(pos)], axis=1)
+        out.append(dict(offset=12.5, sensor_size=(6000, 4000), crop_area=(500.0, 300.0, 5000.0, 3400.0), pixel_pitch=(8400, 8400),
+                        ibis=(pos, ibis), ois=(pos, ois)))
+    return out
+
+
+def test_widened_producer_matches_numpy_restatement():
+    p = synth.base_kernel_params(640, 360)
+    org, sm = cases.gyro()
+    offsets = {0: 1.5, 1_000_000: -3.0, 2_500_000: 4.0, 3_900_000: 0.5}           # offsets_adjusted: four sync points
+    pfo = [0.0, -4.0, 2.5, -1.25]
+    fl = [24.0, 24.5, float("nan"), 26.0]; sfl = [24.2, 24.4, 25.0, 25.5]
+    stab = _stab(4, 360)
+    for fbi in (False, True):
+        cp = g.ComputeParams(p, org, sm, frame_readout_time_ms=16.0, sync_offsets=offsets, per_frame_time_offsets=pfo,
+                             focal_lengths=fl, smoothed_focal_lengths=sfl, readout_time_scale=0.85, camera_stab=stab, framebuffer_inverted=fbi)
+        for frame, ts in enumerate((400.0, 1200.0, 2300.0, 3950.0)):
+            kp, m, fov, mfov = cp.at_timestamp(ts, frame)
+            comp = fl[frame] / sfl[frame] if fl[frame] == fl[frame] else 1.0           # focal_length_fov_compensation (:70-80)
+            assert kp.fov == np.float32(float(p.fov) * comp)
+            q = p.copy(); q.fov = float(p.fov) * comp
+            frt = 16.0 * 0.85 * (-1.0 if fbi else 1.0)                                 # get_frame_readout_time (:22-36)
+            want = np_producer.frame_matrices(q, org, sm, ts + pfo[frame], frame_readout_time_ms=frt, framebuffer_inverted=fbi, offsets=offsets,
+                                              stab=stab[frame], fov_f64=float(p.fov) * comp)
+            assert m.shape == want.shape
+            assert float(ulp_diff(m[:, :9], want[:, :9]).max()) <= 1.0
+            # IBIS / OIS columns: plain f64 arithmetic on both sides, narrowed once
+            assert float(ulp_diff(m[:, 9:], want[:, 9:]).max()) <= 1.0 and np.abs(want[:, 9:]).max() > 1.0
+            assert g.load_library().gf_table_flags_host(m.ctypes.data, m.shape[0]) == 2     # IBIS rows present, nothing wild
+
+
+def test_sync_offset_lookup_edges():
+    """offset_at_timestamp: 0 / 1 points, exact hits, extrapolation outside [first + 1, last - 1] (gyro_source/mod.rs:884-909)."""
+    p = synth.base_kernel_params(64, 36)
+    org, sm = cases.gyro()
+    for offsets in ({}, {500_000: 7.0}, {0: 0.0, 4_000_000: 8.0}, {1_000_000: 2.0, 1_000_001: 3.0, 3_000_000: -5.0}):
+        cp = g.ComputeParams(p, org, sm, frame_readout_time_ms=0.0, sync_offsets=offsets)
+        for ts in (-100.0, 0.0, 1000.0, 1000.001, 2999.9995, 3000.0, 4100.0):
+            _, m, _, _ = cp.at_timestamp(ts)
+            want = np_producer.frame_matrices(p, org, sm, ts, frame_readout_time_ms=0.0, offsets=offsets)
+            assert float(ulp_diff(m[:, :9], want[:, :9]).max()) <= 1.0, (offsets, ts)
+
+
+def test_get_frame_transform_at_matches_python_template():
+    """gf_get_frame_transform_at (stabilization/mod.rs:253-326) == the KernelParams the tests have been building by hand."""
+    import ctypes as C
+    for pix, interp, dig in (("RGBA8", "Bilinear", None), ("Luma16", "Lanczos4", "gopro_superview"), ("RGBAf", "EWA: Mitchell", None), ("UV8", "Bicubic", None)):
+        want = synth.base_kernel_params(640, 360, 480, 270, pixel_type=pix, digital_lens=dig, interpolation=interp, fov=1.3)
+        org, sm = cases.gyro()
+        cp = g.ComputeParams(want, org, sm, fov_scale=1.3)
+        kp, m, _, _ = cp.at_timestamp(900.0)
+        src = np.zeros((360, want.stride), np.uint8); dst = np.zeros((270, want.output_stride), np.uint8)
+        bufs = g.Buffers(g.BufferDescription((640, 360, want.stride), src), g.BufferDescription((480, 270, want.output_stride), dst))
+        st = g.stab_config(want, pix, digital_lens=dig)
+        g.get_frame_transform_at(st, cp, bufs, kp)
+        want.matrix_count = kp.matrix_count
+        want.distortion_model = kp.distortion_model; want.digital_lens = kp.digital_lens        # informational ids: not set by the reference either
+        a = bytes(C.string_at(C.byref(kp), C.sizeof(kp))); b = bytes(C.string_at(C.byref(want), C.sizeof(want)))
+        diff = [n for n, _ in type(kp)._fields_ if bytes(C.string_at(C.addressof(kp) + getattr(type(kp), n).offset, getattr(type(kp), n).size)) !=
+                bytes(C.string_at(C.addressof(want) + getattr(type(want), n).offset, getattr(type(want), n).size))]
+        assert a == b, diff
+    # rects, rotations and the rect flags
+    want = synth.base_kernel_params(640, 360)
+    cp = g.ComputeParams(want, *cases.gyro())
+    kp, _, _, _ = cp.at_timestamp(100.0)
+    src = np.zeros((400, 800 * 4), np.uint8)
+    bufs = g.Buffers(g.BufferDescription((800, 400, 3200), src, rect=(40, 20, 640, 360), rotation=90.0), g.BufferDescription((640, 360, want.output_stride), src))
+    g.get_frame_transform_at(g.stab_config(want, "RGBA8"), cp, bufs, kp)
+    assert list(kp.source_rect) == [40, 20, 640, 360] and kp.input_rotation == 90.0 and (kp.flags & 32) and not (kp.flags & 64) and kp.stride == 3200

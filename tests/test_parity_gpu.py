@@ -10,7 +10,7 @@ import pytest
 
 import gyroflow_b200 as g
 from gyroflow_b200 import abi, synth
-from tests import cases, oracle_lib
+from tests import cases, np_producer, oracle_lib
 
 pytestmark = pytest.mark.gpu
 
@@ -295,7 +295,7 @@ def test_property_frame_sharding_is_order_independent():
     org, sm = cases.gyro()
     outs = {}
     for ts in (500.0, 1500.0, 500.0, 2500.0, 1500.0):
-        mm = synth.frame_matrices(p, org, sm, ts)
+        mm = np_producer.frame_matrices(p, org, sm, ts)
         d = dst0.copy()
         w.undistort_image(bufs(d), g.FrameTransform(matrices=mm, kernel_params=p))
         if ts in outs:

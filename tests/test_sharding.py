@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from gyroflow_b200 import render_queue, synth
-from tests import cases, oracle_lib
+from tests import cases, np_producer, oracle_lib
 
 N_FRAMES = 6
 
@@ -26,7 +26,7 @@ def _frame_crc(p, src, m):
 def _tables():
     p = synth.base_kernel_params(96, 54)
     org, sm = cases.gyro()
-    mats = np.stack([synth.frame_matrices(p, org, sm, 400.0 + 37.0 * i) for i in range(N_FRAMES)])
+    mats = np.stack([np_producer.frame_matrices(p, org, sm, 400.0 + 37.0 * i) for i in range(N_FRAMES)])
     p.matrix_count = mats.shape[1]
     return p, mats
 
