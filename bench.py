@@ -143,20 +143,20 @@ def base_params():
 
 
 def make_tables(n):
-    import math
+    """Side-measurement configs: n matrix tables from the PRODUCT's host producer (gf_frame_transform_at_timestamp): synthetic gyro (or
+    identity quaternions for config 1), and for config 4 IBIS / OIS rows from Catmull-Rom splines of synthetic sensor data
+    (frame_transform.rs:227-287)."""
+    import gyroflow_b200 as g
     from gyroflow_b200 import synth
     p = base_params()
     if CFG.get("identity"):
-        mats = np.stack([synth.identity_matrices(p, rows=1) for _ in range(n)])
+        org = sm = synth.GyroTrack(np.array([0, 10_000_000], np.int64), np.array([[1.0, 0.0, 0.0, 0.0]] * 2))
     else:
         org, sm = synth.synthetic_gyro(4.0)
-        ibis = None
-        if CFG.get("ibis"):
-            def ibis(y, hh=H):
-                t = y / max(hh - 1, 1)
-                return (3.0 * math.sin(6.28 * t), -3.0 * math.cos(6.28 * t), math.radians(0.2) * math.sin(3.0 * t), math.sin(9.0 * t), -math.cos(5.0 * t))
-        mats = np.stack([synth.frame_matrices(p, org, sm, 500.0 + i * (1000.0 / 60.0), frame_readout_time_ms=16.0 if CFG.get("rs") else 0.0, ibis=ibis)
-                         for i in range(n)])   # 60 fps timestamps
+    stab = synth.synthetic_camera_stab(n, W, H) if CFG.get("ibis") else None
+    cp = g.ComputeParams(p, org, sm, frame_readout_time_ms=16.0 if CFG.get("rs") else 0.0, camera_stab=stab,
+                         fov_scale=1.05 if CFG.get("digital") else 1.0)
+    mats = np.stack([cp.at_timestamp(500.0 + i * (1000.0 / 60.0), i)[1] for i in range(n)])   # 60 fps timestamps
     p.matrix_count = mats.shape[1]
     return p, mats.astype(np.float32)
 
@@ -209,6 +209,253 @@ def run_reference(args):
     }))
 
 
+def make_job(duration_s):
+    """The job description every rank needs: KernelParams template + the two quaternion tracks (built on rank 0, broadcast)."""
+    from gyroflow_b200 import synth
+    p = base_params()
+    org, sm = synth.synthetic_gyro(duration_s)
+    return p, org, sm
+
+
+def broadcast_job(p, org, sm, rank, world, dist, torch, dev):
+    """The path's only collective: one NCCL broadcast, at job start, of the KernelParams template and the quaternion tracks
+    (240 Hz x clip length x 2 tracks x 40 B)."""
+    from gyroflow_b200 import render_queue, synth
+    pt = render_queue.params_to_tensor(p, torch).to(dev)
+    dist.broadcast(pt, src=0)
+    n = torch.tensor([len(org.ts) if rank == 0 else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src=0)
+    n = int(n.item())
+    ts = torch.from_numpy(np.ascontiguousarray(org.ts)).to(dev) if rank == 0 else torch.empty(n, dtype=torch.int64, device=dev)
+    qs = (torch.from_numpy(np.stack([org.q, sm.q])).to(dev) if rank == 0 else torch.empty((2, n, 4), dtype=torch.float64, device=dev))
+    dist.broadcast(ts, src=0); dist.broadcast(qs, src=0)
+    ts = ts.cpu().numpy(); qs = qs.cpu().numpy()
+    return render_queue.params_from_tensor(pt), synth.GyroTrack(ts, qs[0]), synth.GyroTrack(ts, qs[1])
+
+
+def run_pipeline(args, torch, dist, g, rank, world, local, dev):
+    """BASELINE config 5 literally, which at N=1 is config 2 over many frames: every frame has its own timestamp; per frame, inside the
+    timed region and without a host sync, the on-device FrameTransform producer writes the 2160 x 14 matrix table and its trust verdict,
+    then the warp kernel renders the frame (gf_cuda_queue_*: 4 frames in flight on 4 streams).  Frame i of the job runs on GPU i mod G."""
+    from gyroflow_b200 import render_queue, synth, abi
+    from tests import oracle_lib
+
+    t_pin = g.bind_thread_to_device(local)               # NUMA: before any page-locked allocation (this library's and torch's)
+    fps = 60.0
+    total_frames = (max(args.warmup, 3) + args.steps + 4) * FRAMES_PER_STEP * world
+    if rank == 0:
+        p, org, sm = make_job(total_frames / fps + 2.0)
+    else:
+        p, org, sm = base_params(), None, None
+    if world > 1:
+        p, org, sm = broadcast_job(p, org, sm, rank, world, dist, torch, dev)
+    rows = H
+    cp = g.ComputeParams(p, org, sm, frame_readout_time_ms=16.0)
+    st = g.stab_config(p, PIX)
+    ts_of = lambda f: 500.0 + f * (1000.0 / fps)
+
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    rand_frame = lambda: torch.randint(0, 256, (H, p.stride), dtype=torch.uint8, device=dev, generator=gen)
+    frames_in = [rand_frame() for _ in range(RING)]
+    frames_out = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(RING)]
+    dbufs = [g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
+                       g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel())) for a, b in zip(frames_in, frames_out)]
+    DEPTH_DEV = 4
+    q = g.RenderQueue(cp, st, LENS, None, dbufs[0].input, dbufs[0].output, device=local, depth=DEPTH_DEV, pin_numa=True, checksum=False)
+    tstream = torch.cuda.Stream(device=dev)
+
+    def step(s):                                          # FRAMES_PER_STEP frames of this rank: global frames (s * FPS + j) * world + rank
+        for j in range(FRAMES_PER_STEP):
+            f = (s * FRAMES_PER_STEP + j) * world + rank
+            if q.in_flight == DEPTH_DEV: q.wait()
+            q.submit(f, ts_of(f), dbufs[(s * FRAMES_PER_STEP + j) % RING])
+
+    clocks = ClockSampler(local); clocks.start()
+    W_STEPS = max(args.warmup, 3)
+    for s in range(W_STEPS): step(s)
+    q.drain(); torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    l0 = q.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    clocks.mark_begin()
+    e0.record(tstream)                                    # device idle: the event's timestamp is the start of the timed region
+    for s in range(args.steps): step(W_STEPS + s)
+    q.drain()                                             # every frame of every step has finished on the device
+    e1.record(tstream)
+    torch.cuda.synchronize()
+    clocks.mark_end()
+    if world > 1: dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = q.launch_count - l0
+    if clocks.proc and clocks.samples_inside() < 3:
+        t_extra = time.perf_counter()
+        while time.perf_counter() - t_extra < 0.3:
+            step(W_STEPS); q.drain()
+    clk = clocks.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    fps_value = world * FRAMES_PER_STEP / (ms_per_step / 1e3)
+
+    # ---- verification pass (untimed): a few frames of the same job with device-side checksums, gathered in frame order -------------
+    qv = g.RenderQueue(cp, st, LENS, None, dbufs[0].input, dbufs[0].output, device=local, depth=2, pin_numa=False, checksum=True)
+    n_check = 8
+    mine = render_queue.shard_frames(n_check, world, rank)
+    sums = qv.render(mine, ts_of, lambda f: dbufs[0]) if mine else {}
+    qv.close()
+    if world > 1: sums = render_queue.gather_results(sums, dist, torch, dev)
+
+    # ---- the kernel alone, one stream (roofline), and the round-1 style numbers on recycled precomputed tables ---------------------
+    dg = g.DeviceGyro(cp, device=local)
+    n_tab = N_TIMESTAMPS
+    tabs = torch.zeros((n_tab, rows, 14), dtype=torch.float32, device=dev)
+    flags = torch.zeros(n_tab, dtype=torch.int32, device=dev)
+    kps = []
+    for i in range(n_tab):
+        kp, r = dg.frame_transform(ts_of(i * world + rank), tabs[i].data_ptr(), rows, frame=i, stream=tstream.cuda_stream,
+                                   table_flags_dev=flags[i:].data_ptr())
+        kp = g.get_frame_transform_at(st, cp, dbufs[0], kp)
+        kps.append(kp)
+    tstream.synchronize()
+    assert int(flags.abs().sum().item()) == 0, "the producer's tables are tame and IBIS-free: the trusted path must run"
+    ctx = g.CudaWrapper.new(kps[0], PIX, LENS, None, dbufs[0], device=local)
+
+    def kernel_loop(n_steps, with_flags):
+        evs = []
+        for s in range(n_steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(tstream)
+            for j in range(FRAMES_PER_STEP):
+                i = s * FRAMES_PER_STEP + j
+                ctx.undistort_image_dev(dbufs[i % RING], kps[i % n_tab], tabs[i % n_tab].data_ptr(), rows, stream=tstream.cuda_stream,
+                                        table_flags_dev=flags[(i % n_tab):].data_ptr() if with_flags else 0)
+            b.record(tstream)
+            evs.append((a, b))
+        tstream.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / n_steps
+
+    side_steps = max(3, min(args.steps, 10))
+    kernel_loop(3, True)
+    ms_trusted = kernel_loop(side_steps, True)
+    kernel_loop(2, False)
+    ms_unval = kernel_loop(side_steps, False)
+    tt = torch.tensor([ms_trusted, ms_unval], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_trusted, ms_unval = float(tt[0].item()), float(tt[1].item())
+    launch_ms = ms_trusted / FRAMES_PER_STEP
+
+    # ---- e2e: the same queue with HOST buffers: per frame  producer kernel | H2D frame | warp | D2H frame  -------------------------
+    e2e = None
+    if not args.no_e2e:
+        DEPTH = args.e2e_depth
+        hin = [rand_frame().cpu().pin_memory() for _ in range(DEPTH)]
+        hout = [torch.zeros((H, p.output_stride), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+        hb = [g.Buffers(g.BufferDescription((W, H, p.stride), hin[i].numpy()), g.BufferDescription((W, H, p.output_stride), hout[i].numpy())) for i in range(DEPTH)]
+        qh = g.RenderQueue(cp, st, LENS, None, hb[0].input, hb[0].output, device=local, depth=DEPTH, pin_numa=True, checksum=False)
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_frames = e2e_steps * FRAMES_PER_STEP
+
+        def host_run(n, base):
+            for k in range(n):
+                f = (base + k) * world + rank
+                if qh.in_flight == DEPTH: qh.wait()            # the slot's previous result has landed in host memory
+                qh.submit(f, ts_of(f), hb[k % DEPTH])
+            qh.drain()
+        host_run(2 * DEPTH + 8, 0)
+        if world > 1: dist.barrier()
+        t0 = time.perf_counter()
+        host_run(e2e_frames, 64)
+        e2e_dt = time.perf_counter() - t0
+        qh.close()
+        # the strictly sequential reference-shaped call (process_pixels: host tables, H2D -> kernel -> D2H -> sync), pinned and pageable
+        kp0, m0, _, _ = cp.at_timestamp(ts_of(rank))
+        kp0 = g.get_frame_transform_at(st, cp, hb[0], kp0)
+        itm = g.FrameTransform(matrices=m0, kernel_params=kp0)
+        hctx = g.CudaWrapper.new(kp0, PIX, LENS, None, hb[0], device=local)
+        for _ in range(3): hctx.undistort_image(hb[0], itm)
+        t0 = time.perf_counter()
+        for _ in range(32): hctx.undistort_image(hb[0], itm)
+        sync_fps = 32 / (time.perf_counter() - t0)
+        pin_a, pin_b = np.array(hin[0].numpy(), copy=True), np.zeros((H, p.output_stride), np.uint8)      # ordinary (pageable) Vec<u8>-like memory
+        pb = g.Buffers(g.BufferDescription((W, H, p.stride), pin_a), g.BufferDescription((W, H, p.output_stride), pin_b))
+        for _ in range(2): hctx.undistort_image(pb, itm)
+        t0 = time.perf_counter()
+        for _ in range(16): hctx.undistort_image(pb, itm)
+        pageable_fps = 16 / (time.perf_counter() - t0)
+        hctx.close()
+        te = torch.tensor([e2e_dt, 1.0 / sync_fps, 1.0 / pageable_fps], dtype=torch.float64, device=dev)
+        if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_fps = world * e2e_frames / float(te[0].item())
+        h2d_frame = int(hin[0].numel() + 368)                 # frame + KernelParams (kernel argument); the matrix table is produced on the device
+        d2h_frame = int(W * p.bytes_per_pixel * H)
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_frame * FRAMES_PER_STEP * world, "d2h_bytes_per_step": d2h_frame * FRAMES_PER_STEP * world,
+               "h2d_bytes_per_frame": h2d_frame, "d2h_bytes_per_frame": d2h_frame, "frames_per_step": FRAMES_PER_STEP * world, "steps": e2e_steps,
+               "h2d_GBps_per_gpu": e2e_fps / world * h2d_frame / 1e9, "d2h_GBps_per_gpu": e2e_fps / world * d2h_frame / 1e9,
+               "pipeline_depth": DEPTH, "numa_cpus_bound": t_pin,
+               "sync_call_value": world / float(te[1].item()), "sync_call_pageable_value": world / float(te[2].item()),
+               "note": "value: gf_cuda_queue with page-locked HOST frames, %d in flight, per frame: on-device FrameTransform producer, H2D, warp, D2H (wall clock, %d frames); "
+                       "sync_call_value: strictly sequential gf_cuda_undistort_image with host tables (what process_pixels does), pinned; "
+                       "sync_call_pageable_value: the same with ordinary pageable buffers (BufferSource::Cpu hands a plain &mut [u8])" % (DEPTH, e2e_frames)}
+
+    if rank == 0:
+        peaks = {}
+        try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception: pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        abytes = algorithmic_bytes(p, rows)
+        achieved = abytes / (launch_ms / 1e3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = oracle_lib.load().gf_oracle_online_cpus()
+            # 4 full 4K frames of this job on the host cores: timed (cpu_baseline) AND compared with the pipeline's per-frame checksums
+            tab = torch.zeros((rows, 14), dtype=torch.float32, device=dev)
+            src = frames_in[0].cpu().numpy()
+            dst = np.zeros((H, p.output_stride), np.uint8)
+            checked, cpu_t = [], 0.0
+            for f in range(min(4, n_check)):
+                kp, r = dg.frame_transform(ts_of(f), tab.data_ptr(), rows, frame=f)
+                kp = g.get_frame_transform_at(st, cp, dbufs[0], kp)
+                m = tab.cpu().numpy()
+                if f == 0: oracle_lib.undistort_image(src, dst, kp, PIX, LENS, None, m, None, cores)      # warm-up (page faults, thread start)
+                t0 = time.perf_counter()
+                assert oracle_lib.undistort_image(src, dst, kp, PIX, LENS, None, m, None, cores) == 0
+                cpu_t += time.perf_counter() - t0
+                ok = render_queue.checksum_host(dst) == sums[f]
+                checked.append(bool(ok))
+            assert all(checked), "pipeline frames differ from the CPU oracle: %r" % (checked,)
+            cpu = {"value": len(checked) / cpu_t, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "%d full 4K frames of the same job (C port of cpu_undistort.rs, row-parallel over all host threads); each one's output checksum "
+                             "equals the checksum the GPU pipeline produced for that frame (frames 0..%d, gathered in frame order over %d rank(s))" % (len(checked), len(checked) - 1, world),
+                   "frames_checked_against_gpu": len(checked)}
+        out = {
+            "metric": METRIC, "value": fps_value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_STEPS,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frame_bytes_in": int(H * p.stride), "frames_per_step": FRAMES_PER_STEP * world, "frames_per_step_per_gpu": FRAMES_PER_STEP,
+                       "pipeline": "cfg5 shape: every frame its own timestamp; per frame inside the timed region: on-device FrameTransform producer (2160 x 14 table + trust verdict) -> warp; "
+                                   "%d frames in flight per GPU; frame i on GPU i mod %d" % (DEPTH_DEV, world),
+                       "l2_policy": "inputs larger than L2: %d-frame ring of %.1f MB inputs (%d MB); every frame a fresh matrix table" % (RING, H * p.stride / 1e6, RING * H * p.stride // 1000000),
+                       "parallelism": "frame-sharded x%d, one NCCL broadcast of KernelParams + quaternion tracks at job start" % world},
+            "clocks": clk, "gpu_launches": launches,
+            "value_trusted_precomputed": world * FRAMES_PER_STEP / (ms_trusted / 1e3),
+            "value_unvalidated": world * FRAMES_PER_STEP / (ms_unval / 1e3),
+            "value_notes": "value = the per-frame pipeline above (producer + warp kernels, multi-stream, CUDA events around the whole region); value_trusted_precomputed = warp kernel only on "
+                           "%d recycled device tables with verdict words (round 1's headline shape); value_unvalidated = the same without verdict words (guarded code path)" % n_tab,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.config, INTERP)),
+                         "traffic_source": NCU_TRAFFIC_SOURCE if (args.config, INTERP) in NCU_TRAFFIC else None,
+                         "algorithmic_bytes_per_launch": abytes, "launch_ms": launch_ms, "peak_source": peak_src,
+                         "kernel": "warp_kernel_x2 (trusted path), timed alone on one stream with CUDA events: %d launches per step" % FRAMES_PER_STEP,
+                         "note": "kernel is FP32-issue bound in bit-exact (-fmad=false) mode, not HBM bound; traffic is the DRAM bytes of ONE cold launch under ncu (output stays in L2), not a steady-state figure; see DESIGN.md"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    ctx.close(); dg.close(); q.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=5, help="frames in flight on the host-buffer path")
+    ap.add_argument("--legacy", action="store_true", help="round-1 measurement shape (recycled precomputed tables) for the default config too")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--lens", default=None, help="override the config's lens model (side measurement), e.g. sony, opencv_standard")
     ap.add_argument("--planes", type=int, default=1, help="planes of this geometry per frame, rendered by one gf_cuda_undistort_planes_dev call (side measurement)")
@@ -245,6 +494,9 @@ def main():
 
     lib = g.load_library()
     assert lib.gf_cuda_device_count() > local, "no CUDA device for this rank (there is no CPU fallback)"
+
+    if args.config == 2 and not args.lens and args.planes == 1 and INTERP == "Bilinear" and not args.legacy:
+        return run_pipeline(args, torch, dist, g, rank, world, local, dev)
 
     # ---- tables: rank 0 builds them, NCCL broadcasts them (the only collective of the path) -------------------
     from gyroflow_b200 import render_queue
@@ -283,18 +535,23 @@ def main():
     plane_params = []
     for k in range(NPL):
         q = p.copy(); q.plane_index = k; plane_params.append(q)
-    table_verdicts = [ctx.validate_tables_dev(mats[i].data_ptr(), rows) for i in range(N_TIMESTAMPS)]   # once per table, outside the timed region
+    # one verdict word per table, written by the asynchronous scan kernel once, outside the timed region (recycled tables)
+    tflags = torch.zeros(N_TIMESTAMPS, dtype=torch.int32, device=dev)
+    for i in range(N_TIMESTAMPS): g.scan_tables_dev(mats[i].data_ptr(), rows, tflags[i:].data_ptr(), stream=stream)
+    tstream.synchronize()
 
     def step(s):
         for j in range(FRAMES_PER_STEP):
             i = s * FRAMES_PER_STEP + j
             if NPL == 1:
                 ctx.undistort_image_dev(all_bufs[i % RING], p, mats[i % N_TIMESTAMPS].data_ptr(), rows,
-                                        mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
+                                        mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream,
+                                        table_flags_dev=tflags[(i % N_TIMESTAMPS):].data_ptr())
             else:       # one multi-plane frame: coordinates once, NPL sampling passes
                 b0 = (i % RING) * NPL
                 ctx.undistort_planes_dev(all_bufs[b0:b0 + NPL], plane_params, mats[i % N_TIMESTAMPS].data_ptr(), rows,
-                                         mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream)
+                                         mesh_dev.data_ptr() if mesh_dev is not None else 0, mesh_dev.numel() if mesh_dev is not None else 0, stream=stream,
+                                         table_flags_dev=tflags[(i % N_TIMESTAMPS):].data_ptr())
 
     clocks = ClockSampler(local); clocks.start()
     torch.cuda.synchronize()

@@ -177,6 +177,23 @@ def base_kernel_params(width, height, out_width=None, out_height=None, pixel_typ
     return p
 
 
+def synthetic_camera_stab(n_frames, width, height, n_points=32, seed=7):
+    """CameraStabData per frame (gyro_source/file_metadata.rs:41-48) for config 4: a 6000 x 4000 sensor read through a
+    (500, 300, 5000, 3400) crop, 8.4 um pixel pitch (stored x1000), IBIS (x, y, roll in millidegrees) and OIS (x, y) as Catmull-Rom
+    control points over the sensor rows — +-3 px / +-0.2 degrees / +-1 px at the frame's scale, different for every frame."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    crop = (500.0, 300.0, 5000.0, 3400.0); pitch = (8400, 8400)
+    sx = width / crop[2] / pitch[0]; sy = height / crop[3] / pitch[1]
+    out = []
+    for f in range(n_frames):
+        pos = np.linspace(200.0, 3800.0, n_points)
+        ph = rng.uniform(0, 2 * math.pi, 4)
+        ibis = np.stack([3.0 / sx * np.sin(pos / 600.0 + ph[0]), -3.0 / sy * np.cos(pos / 800.0 + ph[1]), 200.0 * np.sin(pos / 1100.0 + ph[2])], axis=1)
+        ois = np.stack([1.0 / sx * np.sin(pos / 350.0 + ph[3]), -1.0 / sy * np.cos(pos / 420.0 + ph[0]), np.zeros_like(pos)], axis=1)
+        out.append(dict(offset=0.0, sensor_size=(6000, 4000), crop_area=crop, pixel_pitch=pitch, ibis=(pos, ibis), ois=(pos, ois)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ mesh (config 4)
 
 

@@ -285,6 +285,44 @@ def test_full_size_cfg3_8k_luma16():
     assert_bit_exact(dict(w=7680, h=4320, pix="Luma16", digital="gopro_superview", fov=1.05))
 
 
+def test_full_size_cfg1_4k_rs_off_identity():
+    """BASELINE config 1 at its real size: 3840x2160 RGBA8, opencv_fisheye, rolling shutter off, identity quaternion."""
+    assert_bit_exact(dict(w=3840, h=2160, identity=True, rs=False))
+
+
+def test_full_size_cfg4_4k_f32_sony_ibis_mesh():
+    """BASELINE config 4 at its real size, both ways the reference renders f32: packed RGBAf in one call, and GBRAPF32 as four R32f
+    planes through gf_cuda_undistort_planes_dev (one coordinate pass + four sampling passes, rendering/mod.rs:624-629)."""
+    assert_bit_exact(dict(w=3840, h=2160, pix="RGBAf", lens="sony", ibis=True, mesh=True))
+    _assert_planes(dict(w=3840, h=2160, pix="R32f", lens="sony", ibis=True, mesh=True), 4, fused=True)
+
+
+def test_full_size_cfg3_8k_yuv422p16_with_adaptive_zoom():
+    """BASELINE config 3 as the reference runs it: 7680x4320 YUV422P16LE = three Luma16 planes (7680x4320, 3840x4320, 3840x4320;
+    rendering/mod.rs:596-610), opencv_fisheye + gopro_superview, rolling shutter on, and the per-frame fov taken from the adaptive-zoom
+    companion: gf_cuda_find_fovs over the clip -> gf_zoom_dynamic_compute (window 4 s, envelope follower) -> fovs[frame]
+    (zooming/mod.rs:35-70, frame_transform.rs:52-58)."""
+    w, h = 7680, 4320
+    p0 = synth.base_kernel_params(w, h, pixel_type="Luma16", digital_lens="gopro_superview")
+    org, sm = cases.gyro()
+    cp = g.ComputeParams(p0, org, sm)
+    ts = np.arange(90) * (1000.0 / 60.0) + 500.0
+    dg = g.DeviceGyro(cp)
+    fov_min = dg.find_fovs("opencv_fisheye", "gopro_superview", ts)
+    dg.close()
+    fovs = g.zoom_dynamic(fov_min, 4.0, 60.0, 1)
+    want_fovs = oracle_lib.zoom_dynamic(oracle_lib.find_fovs(cp, "opencv_fisheye", "gopro_superview", ts), 4.0, 60.0, 1)
+    assert np.allclose(fovs, want_fovs, rtol=1e-6, atol=0)
+    frame = 37
+    fov = float(fovs[frame])
+    assert 0.5 < fov < 1.5 and fovs.std() > 1e-4
+    # luma plane, then the two half-width chroma planes (source / output rects, stabilization/mod.rs:209-231) fused into one coordinate pass
+    assert_bit_exact(dict(w=w, h=h, pix="Luma16", digital="gopro_superview", fov=fov, ts=float(ts[frame])))
+    chroma = dict(w=w, h=h, pix="Luma16", digital="gopro_superview", fov=fov, ts=float(ts[frame]),
+                  in_size=(w // 2, h), in_rect=(0, 0, w // 2, h), out_size=(w // 2, h), out_rect=(0, 0, w // 2, h))
+    _assert_planes(chroma, 2, fused=True)
+
+
 # ---- size-independent properties at full size ------------------------------------------------------------
 def test_property_frame_sharding_is_order_independent():
     """Frames are independent units: warping frames in any order / on a reused context gives identical bytes."""
@@ -419,9 +457,11 @@ def test_packed_kernel_unusual_params():
 
 
 def test_device_tables_validated_and_not():
-    """gf_cuda_undistort_image_dev on unvalidated tables (guarded kernel) and validated ones (trusted kernel) == oracle;
-    validation reports wild entries / IBIS rows and those tables still render exactly."""
+    """gf_cuda_undistort_image_dev on device tables: without a verdict word (guarded path), with a word written by
+    gf_cuda_scan_tables_dev (trusted path when 0) — both == oracle; the scan reports wild entries / IBIS rows and those tables still
+    render exactly.  A table REWRITTEN IN PLACE is rendered correctly as long as its word is rewritten too (no pointer cache)."""
     import torch
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
     for hook, verdict in ((None, 0), (_wild("huge"), 1), (_wild("ibis_some"), 2), (_wild("nan_row"), 1)):
         case = dict(w=1280, h=720)
         if hook: case["matrix_hook"] = hook
@@ -430,19 +470,41 @@ def test_device_tables_validated_and_not():
         assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
         tsrc = torch.from_numpy(src).cuda(); tm = torch.from_numpy(m).cuda()
         outs = []
-        for validate in (False, True):
+        for use_flags in (False, True):
             tdst = torch.from_numpy(dst0.copy()).cuda()
             bufs = g.Buffers(g.BufferDescription((1280, 720, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
                              g.BufferDescription((1280, 720, p.output_stride), tdst.data_ptr(), length=tdst.numel()))
             w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
             torch.cuda.synchronize()
-            if validate:
-                assert w.validate_tables_dev(tm.data_ptr(), m.shape[0]) == verdict
             side = torch.cuda.Stream()
-            w.undistort_image_dev(bufs, p, tm.data_ptr(), m.shape[0], stream=side.cuda_stream)
+            if use_flags:
+                assert w.validate_tables_dev(tm.data_ptr(), m.shape[0]) == verdict          # synchronous query
+                flags.fill_(-1); torch.cuda.synchronize()
+                g.scan_tables_dev(tm.data_ptr(), m.shape[0], flags.data_ptr(), stream=side.cuda_stream)   # asynchronous, same stream as the warp
+            w.undistort_image_dev(bufs, p, tm.data_ptr(), m.shape[0], stream=side.cuda_stream, table_flags_dev=flags.data_ptr() if use_flags else 0)
             side.synchronize()
+            if use_flags: assert int(flags.item()) == verdict
             outs.append(tdst.cpu().numpy()); w.close()
         assert np.array_equal(outs[0], want) and np.array_equal(outs[1], want)
+    # in-place rewrite: tame table scanned (word = 0), then IBIS rows written into the SAME allocation and re-scanned
+    p, src, m, mesh, dst0, pix, lens, digital = cases.build(dict(w=640, h=360))
+    m2 = _wild("ibis_some")(m.copy())
+    tsrc = torch.from_numpy(src).cuda(); tm = torch.from_numpy(m).cuda()
+    tdst = torch.from_numpy(dst0.copy()).cuda()
+    bufs = g.Buffers(g.BufferDescription((640, 360, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
+                     g.BufferDescription((640, 360, p.output_stride), tdst.data_ptr(), length=tdst.numel()))
+    w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+    side = torch.cuda.Stream(); torch.cuda.synchronize()
+    for table in (m, m2, m):
+        with torch.cuda.stream(side):
+            tm.copy_(torch.from_numpy(table).cuda(), non_blocking=True)
+        g.scan_tables_dev(tm.data_ptr(), table.shape[0], flags.data_ptr(), stream=side.cuda_stream)
+        w.undistort_image_dev(bufs, p, tm.data_ptr(), table.shape[0], stream=side.cuda_stream, table_flags_dev=flags.data_ptr())
+        side.synchronize()
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, table, mesh) == 0
+        assert np.array_equal(tdst.cpu().numpy(), want)
+    w.close()
 
 
 def test_kernel_variants_agree(monkeypatch):
