@@ -1,8 +1,10 @@
 """An independent second restatement of the north-star path, written from the reference text in a different language
-(Python scalars of numpy.float32) than the C oracle, to cross-check it: opencv_fisheye + vertical rolling shutter +
-bilinear sampling, background mode 0, on 8-bit, 16-bit and f32 pixels, and the opencv_standard / poly3 / poly5 / ptlens /
-sony lens models beside opencv_fisheye (cpu_undistort.rs:133-167, :421-517 without the optional branches,
-:370-418, :519-633; opencv_fisheye.rs:72-93; util.rs:144-147; pixel_formats.rs u8 conversions).
+(Python scalars of numpy.float32) than the C oracle, to cross-check it: every physical lens model (opencv_fisheye,
+opencv_standard, poly3, poly5, ptlens, insta360, sony, generic_polynomial, gopro), every digital lens (gopro_superview,
+gopro6_superview, gopro_hyperview, gopro_warp, digital_stretch), vertical rolling shutter, bilinear / bicubic / Lanczos4
+sampling, background mode 0, on 8-bit, 16-bit and f32 pixels (cpu_undistort.rs:133-167 + :216-220, :421-517 without the
+optional branches, :370-418, :519-633; distortion_models/*.rs distort_point; util.rs:144-147; pixel_formats.rs conversions).
+With it every lens formula of the oracle has two independent transcriptions.
 
 TEST INFRASTRUCTURE ONLY.  numpy.float32 arithmetic is IEEE single precision without contraction; atan goes to the same
 libm `atanf` Rust's std calls (numpy's own arctan may differ in the last ulp)."""
@@ -18,10 +20,16 @@ _libm.atanf.restype = ctypes.c_float
 _libm.atanf.argtypes = [ctypes.c_float]
 _libm.sqrtf.restype = ctypes.c_float
 _libm.sqrtf.argtypes = [ctypes.c_float]
+_libm.tanf.restype = ctypes.c_float
+_libm.tanf.argtypes = [ctypes.c_float]
 
 
 def atanf(x):
     return F(_libm.atanf(float(x)))
+
+
+def tanf(x):
+    return F(_libm.tanf(float(x)))
 
 
 def sqrtf(x):
@@ -103,11 +111,139 @@ def sony_distort(x, y, z, k):                # sony.rs:65-89
     return x * scale, y * scale
 
 
+def insta360_distort(x, y, z, k):            # insta360.rs:27-48
+    k1, k2, k3, p1, p2, xi = k[0], k[1], k[2], k[3], k[4], k[5]
+    ln = sqrtf(x * x + y * y + z * z)
+    x = (x / ln) / ((z / ln) + xi)
+    y = (y / ln) / ((z / ln) + xi)
+    r2 = x * x + y * y; r4 = r2 * r2; r6 = r4 * r2
+    return (x * (F(1.0) + k1 * r2 + k2 * r4 + k3 * r6) + F(2.0) * p1 * x * y + p2 * (r2 + F(2.0) * x * x),
+            y * (F(1.0) + k1 * r2 + k2 * r4 + k3 * r6) + F(2.0) * p2 * x * y + p1 * (r2 + F(2.0) * y * y))
+
+
+def generic_polynomial_distort(x, y, z, k):  # generic_polynomial.rs:83-122
+    x = x / z; y = y / z
+    if all(k[i] == 0 for i in range(12)):
+        return x, y
+    r = sqrtf(x * x + y * y)
+    t = atanf(r)
+    t2 = t * t; t3 = t2 * t; t4 = t2 * t2; t5 = t2 * t3; t6 = t3 * t3; t7 = t3 * t4; t8 = t4 * t4; t9 = t4 * t5
+    t10 = t5 * t5; t11 = t5 * t6; t12 = t6 * t6
+    theta_d = (t * k[0] + t2 * k[1] + t3 * k[2] + t4 * k[3] + t5 * k[4] + t6 * k[5] + t7 * k[6] + t8 * k[7] + t9 * k[8]
+               + t10 * k[9] + t11 * k[10] + t12 * k[11])
+    scale = F(1.0) if r == F(0.0) else theta_d / r
+    return x * scale, y * scale
+
+
+def _gopro_poly_eval(p, k):                  # gopro.rs:19-21
+    return k[0] + p * (k[1] + p * (k[2] + p * (k[3] + p * (k[4] + p * (k[5] + p * k[6])))))
+
+
+def _gopro_poly_deriv(p, k):                 # gopro.rs:22-24
+    return k[1] + p * (F(2.0) * k[2] + p * (F(3.0) * k[3] + p * (F(4.0) * k[4] + p * (F(5.0) * k[5] + p * (F(6.0) * k[6])))))
+
+
+def gopro_distort(x, y, z, k):               # gopro.rs:56-72 with poly_invert :26-36
+    px, py = x / z, y / z
+    if k[1] == 0:
+        return px, py
+    r = sqrtf(px * px + py * py)
+    TMAX = F(1.5533)
+    tt = tanf(TMAX)
+    theta = atanf(r) if r < tt else TMAX + (r - tt) / (F(1.0) + tt * tt)
+    p = (theta - k[0]) / k[1]
+    for _ in range(10):
+        d = _gopro_poly_deriv(p, k)
+        if abs(d) < F(1e-12):
+            break
+        fix = (_gopro_poly_eval(p, k) - theta) / d
+        p = p - fix
+        if abs(fix) < F(1e-7):
+            break
+    r_norm = k[1] * p
+    scale = F(1.0) if r < F(1e-9) else r_norm / r
+    return px * scale, py * scale
+
+
 DISTORT = {"opencv_fisheye": fisheye_distort, "opencv_standard": standard_distort, "poly3": poly3_distort, "poly5": poly5_distort,
-           "ptlens": ptlens_distort, "sony": sony_distort}
+           "ptlens": ptlens_distort, "sony": sony_distort, "insta360": insta360_distort, "generic_polynomial": generic_polynomial_distort,
+           "gopro": gopro_distort}
 
 
-def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye"):   # cpu_undistort.rs:133-167 (no r_limit / refraction / IBIS / mesh / digital lens)
+# ---- digital lenses: distort_point (wide -> recorded), cpu_undistort.rs:216-220 ------------------------------------------------
+def _superview(ux, uy):                      # gopro_superview.rs:12-19
+    x2 = ux * ux; y2 = uy * uy
+    return (ux * (F(1.2100393) + x2 * (F(-1.2758402) + x2 * F(1.7751845))),
+            uy * (F(0.9364505) + (F(0.4465308) - F(0.7683315) * y2) * y2 + (F(-0.3574087) + F(1.1584653) * y2 + F(0.3529348) * x2) * x2))
+
+
+def _superview6(ux, uy):                     # gopro6_superview.rs:12-17
+    ux = ux * (F(1.0) - F(0.48) * abs(ux))
+    ux = ux * (F(0.943396) * (F(1.0) + F(0.157895) * abs(ux)))
+    uy = uy * (F(0.943396) * (F(1.0) + F(0.060000) * abs(uy * F(2.0))))
+    return ux, uy
+
+
+def _hyperview(ux, uy):                      # gopro_hyperview.rs:10-17
+    x2 = ux * ux; y2 = uy * uy
+    return (ux * (F(1.5805143) + x2 * (F(-8.1668825) + x2 * (F(74.5198746) + x2 * (F(-451.5002441) + x2 * (F(1551.2922363) + x2 * (F(-2735.5422363) + x2 * F(1923.1572266))))))
+                  + y2 * F(-0.1086027)),
+            uy * (F(1.0238225) + y2 * F(-0.1025671) + x2 * (F(-0.2639930) + x2 * F(0.2979266))))
+
+
+def _view_distort(fn, xscale):               # the distort_point shared by the three *view lenses (e.g. gopro_superview.rs:37-57)
+    def distort(x, y, p):
+        sw, sh = F(p.width), F(p.height)
+        x = (x / sw) - F(0.5); y = (y / sh) - F(0.5)
+        if xscale is not None:
+            x = x * F(xscale)
+        ppx, ppy = x, y
+        for _ in range(12):
+            dx, dy = fn(ppx, ppy)
+            dx = dx - x; dy = dy - y
+            if abs(dx) < F(1e-6) and abs(dy) < F(1e-6):
+                break
+            ppx = ppx - dx; ppy = ppy - dy
+        return (ppx + F(0.5)) * sw, (ppy + F(0.5)) * sh
+    return distort
+
+
+def _gopro_map(ux, uy, q):                   # gopro_warp.rs:22-41
+    x = min(max(ux, F(-0.5)), F(0.5)); y = min(max(uy, F(-0.5)), F(0.5))
+    x2 = x * x; y2 = y * y
+    poly_x = q[0] + x2 * (q[1] + x2 * (q[2] + x2 * (q[3] + x2 * (q[4] + x2 * (q[5] + x2 * q[6])))))
+    return (x * (poly_x + q[7] * y2) + (ux - x),
+            y * (q[8] + q[9] * y2 + q[10] * y2 * y2 + x2 * (q[11] + q[12] * y2 + q[13] * x2)) + (uy - y))
+
+
+def gopro_warp_distort(x, y, p):             # gopro_warp.rs:57-94
+    q = [F(v) for v in p.digital_lens_params]
+    factor = q[14] if q[14] != 0 else F(1.0)
+    sw, sh = F(p.width), F(p.height)
+    x = (x / sw) - F(0.5); y = (y / sh) - F(0.5)
+    tx, ty = x * factor, y
+    ppx, ppy = x, y
+    for _ in range(12):
+        dx, dy = _gopro_map(ppx, ppy, q)
+        dx = dx - tx; dy = dy - ty
+        if abs(dx) < F(1e-6) and abs(dy) < F(1e-6):
+            break
+        ppx = ppx - dx; ppy = ppy - dy
+    rx, ry = _gopro_map(ppx, ppy, q)
+    if abs(rx - tx) > F(0.02) or abs(ry - ty) > F(0.02):
+        return F(-99999.0), F(-99999.0)
+    return (ppx + F(0.5)) * sw, (ppy + F(0.5)) * sh
+
+
+def digital_stretch_distort(x, y, p):        # digital_stretch.rs:19-22
+    return x * F(p.digital_lens_params[0]), y * F(p.digital_lens_params[1])
+
+
+DIGITAL = {"gopro_superview": _view_distort(_superview, 1.333333333), "gopro6_superview": _view_distort(_superview6, None),
+           "gopro_hyperview": _view_distort(_hyperview, 1.555555555), "gopro_warp": gopro_warp_distort, "digital_stretch": digital_stretch_distort}
+
+
+def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:133-167, :216-220 (no r_limit / refraction / IBIS / mesh)
     row = m[idx]
     t3 = [F(v) for v in p.translation3d]
     _x = (px * row[0]) + (py * row[1]) + row[2] + t3[0]
@@ -118,20 +254,23 @@ def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye"):   # cpu_undist
     k = [F(v) for v in p.k]
     ux, uy = DISTORT[lens](_x, _y, _w, k)
     ux = ux * F(p.f[0]); uy = uy * F(p.f[1])
-    return ux + F(p.c[0]), uy + F(p.c[1])
+    ux = ux + F(p.c[0]); uy = uy + F(p.c[1])
+    if digital is not None and (p.flags & 2) == 2:           # :216-220
+        ux, uy = DIGITAL[digital](ux, uy, p)
+    return ux, uy
 
 
-def undistort_coord(x, y, p, m, lens="opencv_fisheye"):   # cpu_undistort.rs:421-517, the branches the north-star config takes
+def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:421-517, the branches the north-star config takes
     ox = map_coord(x, p.output_rect[0], p.output_rect[0] + p.output_rect[2], 0.0, p.output_width)
     oy = map_coord(y, p.output_rect[1], p.output_rect[1] + p.output_rect[3], 0.0, p.output_height)
     ox = ox + F(p.translation2d[0]); oy = oy + F(p.translation2d[1])
     sy = max(min(as_i32(round_half_away(oy)), p.height), 0)
     if p.matrix_count > 1:
-        pt = rotate_and_distort(ox, oy, p.matrix_count // 2, p, m, lens)
+        pt = rotate_and_distort(ox, oy, p.matrix_count // 2, p, m, lens, digital)
         if pt is not None:
             sy = max(min(as_i32(round_half_away(pt[1])), p.height), 0)
     idx = min(sy, p.matrix_count - 1)
-    uv = rotate_and_distort(ox, oy, idx, p, m, lens)
+    uv = rotate_and_distort(ox, oy, idx, p, m, lens, digital)
     if uv is None:
         return None
     u = map_coord(uv[0], 0.0, p.width, p.source_rect[0], p.source_rect[0] + p.source_rect[2])
@@ -165,6 +304,49 @@ def sample_bilinear(u, v, src, p, bg, count, sbytes=1):   # cpu_undistort.rs:370
     return [min(t, lim) if not math.isnan(float(t)) else lim for t in total]
 
 
+_COEFF_TABLES = {}
+
+
+def _coeffs(I):
+    """COEFFS of cpu_undistort.rs:21-58 (bicubic: 32 x 4, Lanczos4: 32 x 8) — the literals, parsed from the generated table the build
+    checks against the reference's 448 values (oracle/gen_coeffs.py --check-reference)."""
+    if not _COEFF_TABLES:
+        import os, re
+        txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "gf_coeffs.inc")).read()
+        for name, key in (("GF_COEFFS_BICUBIC", 4), ("GF_COEFFS_LANCZOS4", 8)):
+            body = txt[txt.index(name):]
+            body = body[body.index("{") + 1:body.index("}")]
+            _COEFF_TABLES[key] = [F(v) for v in re.findall(r"-?\d+\.\d+", body)]
+    return _COEFF_TABLES[I]
+
+
+def sample_separable(u, v, src, p, bg, count, sbytes, I):   # cpu_undistort.rs:370-418 with I = 4 (bicubic) or 8 (Lanczos4)
+    offset = F(1.0) if I == 4 else F(3.0)
+    tab = _coeffs(I)
+    u = u - offset; v = v - offset
+    sx0 = as_i32(round_half_away(u * F(32.0))); sy0 = as_i32(round_half_away(v * F(32.0)))
+    sx, sy = sx0 >> 5, sy0 >> 5
+    cx = tab[(sx0 & 31) * I:(sx0 & 31) * I + I]; cy = tab[(sy0 & 31) * I:(sy0 & 31) * I + I]
+    rx0, ry0 = p.source_rect[0], p.source_rect[1]
+    rx1, ry1 = rx0 + p.source_rect[2], ry0 + p.source_rect[3]
+    total = [F(0.0)] * 4
+    for yp in range(I):
+        if ry0 <= sy + yp < ry1:
+            xsum = [F(0.0)] * 4
+            for xp in range(I):
+                if rx0 <= sx + xp < rx1:
+                    off = ((sy + yp) * p.stride + (sx + xp) * p.bytes_per_pixel) // sbytes
+                    px = [F(src[off + c]) if c < count else F(0.0) for c in range(4)]
+                else:
+                    px = bg
+                xsum = [xsum[c] + px[c] * cx[xp] for c in range(4)]
+            total = [total[c] + xsum[c] * cy[yp] for c in range(4)]
+        else:
+            total = [total[c] + bg[c] * cy[yp] for c in range(4)]
+    lim = F(p.pixel_value_limit)
+    return [min(t, lim) if not math.isnan(float(t)) else lim for t in total]
+
+
 def to_u8(v):                                # `as u8`: truncate, saturate, NaN -> 0
     v = float(v)
     if math.isnan(v):
@@ -181,7 +363,7 @@ def to_scalar(v, sdt):                       # PixelType::from_float: Rust `as u
     return max(0, min(255 if sdt == np.uint8 else 65535, int(v)))
 
 
-def undistort_image(src, dst, p, matrices, lens="opencv_fisheye", sdt=np.uint8):
+def undistort_image(src, dst, p, matrices, lens="opencv_fisheye", sdt=np.uint8, digital=None):
     """src, dst: 2-D uint8 arrays (rows x stride).  Writes dst in place like the reference (only pixels it touches).
     sdt: the scalar type of a channel (np.uint8, np.uint16 or np.float32)."""
     m = [[F(x) for x in row] for row in np.asarray(matrices, dtype=np.float32).reshape(-1, 14)]
@@ -197,7 +379,12 @@ def undistort_image(src, dst, p, matrices, lens="opencv_fisheye", sdt=np.uint8):
             opy = map_coord(y, p.output_rect[1], p.output_rect[1] + p.output_rect[3], 0.0, p.output_height)
             if not (opx >= 0 and opy >= 0 and as_i32(opx) < p.output_width and as_i32(opy) < p.output_height):
                 continue
-            uv = undistort_coord(F(x), F(y), p, m, lens)
-            pixel = bg if uv is None else sample_bilinear(uv[0], uv[1], flat, p, bg, count, sbytes)
+            uv = undistort_coord(F(x), F(y), p, m, lens, digital)
+            if uv is None:
+                pixel = bg
+            elif p.interpolation == 2:
+                pixel = sample_bilinear(uv[0], uv[1], flat, p, bg, count, sbytes)
+            else:
+                pixel = sample_separable(uv[0], uv[1], flat, p, bg, count, sbytes, p.interpolation)
             for c in range(count):
                 dview[y, x * count + c] = to_scalar(pixel[c], sdt)

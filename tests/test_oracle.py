@@ -180,3 +180,30 @@ def test_independent_numpy_restatement_agrees():
             warnings.simplefilter("ignore")
             np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=sdt)
         assert np.array_equal(got, want), c
+
+
+def test_independent_numpy_restatement_remaining_models_and_resamplers():
+    """The lens formulas that had a single transcription in round 1 — insta360, generic_polynomial, gopro (Newton POLY inverse with the
+    89-degree continuation), the three *view digital lenses (12-step fixed point), gopro_warp (MAPX / MAPY with the off-frame sentinel),
+    digital_stretch — and the bicubic / Lanczos4 samplers, restated a second time in numpy.float32 scalars: same bytes as the C oracle."""
+    import warnings
+    from tests import cases, np_restatement
+    todo = [
+        (dict(w=72, h=40, lens="insta360"), np.uint8), (dict(w=72, h=40, lens="insta360", fov=2.0, pix="Luma16"), np.uint16),
+        (dict(w=72, h=40, lens="generic_polynomial"), np.uint8), (dict(w=72, h=40, lens="generic_polynomial", fov=2.2, pix="R32f"), np.float32),
+        (dict(w=72, h=40, lens="gopro"), np.uint8), (dict(w=72, h=40, lens="gopro", fov=3.0, pix="Luma8"), np.uint8),     # rays past 89 degrees
+        (dict(w=72, h=40, lens="gopro", digital="gopro_warp"), np.uint8), (dict(w=72, h=40, lens="gopro", digital="gopro_warp", fov=2.5), np.uint8),
+        (dict(w=72, h=40, digital="gopro_superview", fov=1.1), np.uint8), (dict(w=72, h=40, digital="gopro6_superview", pix="UV8"), np.uint8),
+        (dict(w=72, h=40, digital="gopro_hyperview", pix="Luma16", fov=1.2), np.uint16), (dict(w=72, h=40, lens="poly5", digital="digital_stretch"), np.uint8),
+        (dict(w=64, h=36, interp="Bicubic"), np.uint8), (dict(w=64, h=36, interp="Lanczos4", fov=1.8, params=dict(background=[0.2, 0.4, 0.6, 1.0])), np.uint8),
+        (dict(w=48, h=28, interp="Lanczos4", pix="RGBAf", lens="sony"), np.float32), (dict(w=48, h=28, interp="Bicubic", pix="UV16", lens="insta360"), np.uint16),
+    ]
+    for c, sdt in todo:
+        p, src, m, mesh, dst0, pix, lens, digital = cases.build(c)
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        got = dst0.copy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=sdt, digital=digital)
+        assert np.array_equal(got, want), (c, int((got != want).sum()))
