@@ -166,8 +166,10 @@ EXPORTS = [
                                           C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("gf_cuda_undistort_planes_dev", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("gf_cuda_selftest_exhaustive", C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
+    ("gf_cuda_selftest_filter", C.c_int, [C.c_int, C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]),
     ("gf_cuda_plan", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t]),
     ("gf_cuda_synchronize", C.c_int, [C.c_void_p]),
+    ("gf_cuda_set_overlays", C.c_int, [C.c_void_p, C.c_int]),
     ("gf_cuda_last_error", C.c_char_p, [C.c_void_p]),
     ("gf_cuda_backend_name", C.c_char_p, []),
     ("gf_cuda_launch_count", C.c_uint64, [C.c_void_p]),

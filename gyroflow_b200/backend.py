@@ -123,14 +123,21 @@ class CudaWrapper:
     def _err(self, rc):
         return GyroflowCoreError(rc, (self._lib.gf_cuda_last_error(self._h) or b"").decode())
 
-    def undistort_image(self, buffers: Buffers, itm: FrameTransform, drawing_buffer: bytes = b"", stream: int = 0):
+    def set_overlays(self, enabled: bool):
+        """Preview overlays (draw_pixel / draw_safe_area of the reference's GPU kernels); off by default like the CPU path."""
+        rc = self._lib.gf_cuda_set_overlays(self._h, int(enabled))
+        if rc != 0:
+            raise self._err(rc)
+
+    def undistort_image(self, buffers: Buffers, itm: FrameTransform, drawing_buffer=None, stream: int = 0):
         i, o = buffers.input.to_c(), buffers.output.to_c()
         m = np.ascontiguousarray(itm.matrices, dtype=np.float32)
         mesh = np.ascontiguousarray(itm.mesh_data, dtype=np.float32)
+        d = None if drawing_buffer is None else np.ascontiguousarray(drawing_buffer, dtype=np.uint8)
         rc = self._lib.gf_cuda_undistort_image(
             self._h, C.byref(i), C.byref(o), C.byref(itm.kernel_params),
             m.ctypes.data, m.shape[0], mesh.ctypes.data if mesh.size else None, mesh.size,
-            None, 0, stream or None)
+            d.ctypes.data if d is not None and d.size else None, d.size if d is not None else 0, stream or None)
         if rc != 0:
             raise self._err(rc)
 

@@ -50,6 +50,13 @@ struct gf_cuda_ctx {
     uint32_t* d_const_flags = nullptr;   // two device words {0, 1}: the verdict of the host scan of host tables, as the kernel wants it
     uint32_t* d_vflags = nullptr;        // scratch verdict word of gf_cuda_validate_tables_dev
     cudaStream_t last_stream = nullptr;  // the stream of the most recent call (gf_cuda_synchronize waits for it too)
+    // filtered rolling-shutter pre-pass (packed fisheye kernel): queue of deferred pixel pairs + two ping-pong counters
+    uint32_t* d_defer_q = nullptr; unsigned* d_defer_count = nullptr; uint32_t defer_cap = 0; unsigned long long filter_frames = 0;
+    bool no_filter = false;
+    // preview overlays (overlay.cu), off unless gf_cuda_set_overlays: device copy of the drawing buffer, private copy of a DEVICE input
+    int overlays = 0;
+    uint8_t* h_drawing = nullptr; uint8_t* d_drawing = nullptr; size_t drawing_cap = 0;
+    uint8_t* d_src_ovl = nullptr; size_t d_src_ovl_len = 0;
     uint2* d_coords = nullptr; size_t d_coords_len = 0;   // multi-plane mode: the frame's coordinate map
     KernelFn fn_shade = nullptr;
     unsigned long long aux_launches = 0;   // helper kernels (mesh widening, table scans): not counted by gf_cuda_launch_count
@@ -375,6 +382,7 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     KernelFn fn = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 0);
     KernelFn fn_lean = find_kernel(distortion_model, digital_lens, layout, params->interpolation, 1);
     const bool no_x2 = getenv("GF_DISABLE_X2") != nullptr;      // read per context (tests flip it between contexts)
+    const bool no_filter = getenv("GF_DISABLE_FILTER") != nullptr;
     KernelFn fn_x2 = no_x2 ? nullptr : find_kernel(distortion_model, digital_lens, layout, params->interpolation, 2);
     if (!fn) return fail(nullptr, GF_ERR_UNSUPPORTED_COMBO, "no kernel compiled for this (lens, digital lens, pixel type, interpolation)");
 
@@ -383,7 +391,7 @@ GF_API int gf_cuda_create(gf_cuda_ctx** out_ctx, int device, const gf_kernel_par
     ctx->interpolation = params->interpolation; ctx->layout = layout; ctx->bpp = bpp; ctx->fn = fn; ctx->fn_lean = fn_lean; ctx->fn_x2 = fn_x2; ctx->fn_shade = gf_shade_kernel(layout);
     if (!no_x2) ctx->fn_x2c = find_kernel(distortion_model, digital_lens, layout, GF_INTERP_BILINEAR, 4);
     ctx->width = params->width; ctx->height = params->height; ctx->output_width = params->output_width; ctx->output_height = params->output_height;
-    ctx->drawing_len = drawing_len;
+    ctx->drawing_len = drawing_len; ctx->no_filter = no_filter;
     auto bail = [&](int rc) { std::string m = ctx->last_error; gf_cuda_destroy(ctx); g_last_error = m; return rc; };
 
     cudaError_t e = cudaSetDevice(device);
@@ -434,10 +442,31 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     if (ctx->d_vflags) cudaFree(ctx->d_vflags);
     if (ctx->d_const_flags) cudaFree(ctx->d_const_flags);
+    if (ctx->h_drawing) cudaFreeHost(ctx->h_drawing);
+    if (ctx->d_drawing) cudaFree(ctx->d_drawing);
+    if (ctx->d_src_ovl) cudaFree(ctx->d_src_ovl);
+    if (ctx->d_defer_q) cudaFree(ctx->d_defer_q);
+    if (ctx->d_defer_count) cudaFree(ctx->d_defer_count);
     if (ctx->d_coords) cudaFree(ctx->d_coords);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
     delete ctx;
+}
+
+// Filtered rolling-shutter pre-pass (warp_kernel_x2.cuh, Lens2<opencv_fisheye>::approx_v): the host side of its contract.
+// The certificate |tv_approx - tv_exact| <= rho |tv - c_y| + 2^-22 |tv| assumes that the polynomial s = 1 + k0 t^2 + k1 t^4 + k2 t^6 +
+// k3 t^8 stays within [3/4, 5/4] (its rounding error and its sensitivity to the error of t are then bounded):
+// a_cap = tan^2(t_cap) with t_cap the largest angle (<= 1.55 rad) for which sum |k_i| t^(2i+2) <= 1/4.  Returns 0 when the lens is too
+// strongly curved for the filter to be worth it (t_cap < 0.5 rad).
+static float filter_a_cap(const float* k) {
+    auto B = [&](double t) { const double t2 = t * t; return t2 * (fabs((double)k[0]) + t2 * (fabs((double)k[1]) + t2 * (fabs((double)k[2]) + t2 * fabs((double)k[3])))); };
+    for (int i = 0; i < 4; ++i) if (!std::isfinite(k[i])) return 0.0f;
+    double lo = 0.0, hi = 1.55;
+    if (B(hi) > 0.25) { for (int it = 0; it < 60; ++it) { const double mid = 0.5 * (lo + hi); if (B(mid) <= 0.25) lo = mid; else hi = mid; } }
+    else lo = hi;
+    if (lo < 0.5) return 0.0f;
+    const double a = tan(lo) * tan(lo);
+    return (float)std::min(a * 0.999, 16000.0);                 // stay inside the table (r^2 < 2^14) and below the exact bound
 }
 
 // Which kernel renders a frame with these uniforms?  Shared by run_warp and gf_cuda_plan (the host-only query the CPU tests use).
@@ -459,7 +488,8 @@ static int select_variant(bool has_lean, bool has_packed, int ctx_digital_lens, 
 static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out, const gf_kernel_params* p,
                     const float* matrices, size_t matrix_rows, const float* mesh, size_t mesh_len,
                     bool tables_on_device, void* cu_stream, bool sync_host = true, size_t more_planes = 0, bool coord_only = false,
-                    const uint32_t* table_flags_dev = nullptr, uint64_t* checksum_dev = nullptr) {
+                    const uint32_t* table_flags_dev = nullptr, uint64_t* checksum_dev = nullptr,
+                    const uint8_t* drawing = nullptr, size_t drawing_len = 0) {
     if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
     { int rc = validate(ctx, p, in, out, ctx->bpp); if (rc != GF_OK) return rc; }
     if (!matrices) return fail(ctx, GF_ERR_NO_DATA, "NoStabilizationData: matrices is null");
@@ -534,6 +564,43 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         if (!full_cover) CK(cudaMemcpyAsync(ctx->d_dst, out->ptr, out->len, cudaMemcpyHostToDevice, st));
         dst = ctx->d_dst;
     }
+    // preview overlays, input stage: drawing entries with stage bit 0 are drawn onto the device copy of the input
+    const uint8_t* drawing_dev = nullptr;
+    int ovl_count = 0, ovl_scalar = 0;
+    if (ctx->overlays && more_planes == 0 && !coord_only) {
+        ovl_count = ctx->layout <= LAY_4U8 ? ctx->layout + 1 : (ctx->layout <= LAY_4U16 ? ctx->layout - LAY_1U16 + 1 : (ctx->layout == LAY_1F32 ? 1 : 4));
+        ovl_scalar = ctx->layout <= LAY_4U8 ? 0 : (ctx->layout <= LAY_4U16 ? 1 : (ctx->layout == LAY_4F16 ? 3 : 2));
+        bool any_input_stage = false;
+        if ((p->flags & GF_FLAG_DRAWING_ENABLED) && drawing && drawing_len) {
+            if (drawing_len > ctx->drawing_cap) {
+                CK(cudaStreamSynchronize(st));
+                if (ctx->h_drawing) cudaFreeHost(ctx->h_drawing);
+                if (ctx->d_drawing) cudaFree(ctx->d_drawing);
+                ctx->h_drawing = nullptr; ctx->d_drawing = nullptr; ctx->drawing_cap = 0;
+                CK(cudaMallocHost(&ctx->h_drawing, drawing_len));
+                CK(cudaMalloc(&ctx->d_drawing, drawing_len));
+                ctx->drawing_cap = drawing_len;
+            } else {
+                CK(cudaStreamSynchronize(st));                 // the previous frame's upload has left the pinned copy
+            }
+            for (size_t i = 0; i < drawing_len; ++i) { const uint8_t d = drawing[i]; ctx->h_drawing[i] = d; any_input_stage |= (d != 0 && (d & 1u) == 0u); }
+            CK(cudaMemcpyAsync(ctx->d_drawing, ctx->h_drawing, drawing_len, cudaMemcpyHostToDevice, st));   // opencl.rs: buf_drawing.write(drawing_buffer)
+            drawing_dev = ctx->d_drawing;
+        }
+        if (any_input_stage) {
+            if (in->kind == GF_BUF_DEVICE) {                   // never draw into the caller's buffer: private copy
+                if (in->len > ctx->d_src_ovl_len) {
+                    if (ctx->d_src_ovl) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_src_ovl); ctx->d_src_ovl = nullptr; ctx->d_src_ovl_len = 0; }
+                    CK(cudaMalloc(&ctx->d_src_ovl, in->len)); ctx->d_src_ovl_len = in->len;
+                }
+                CK(cudaMemcpyAsync(ctx->d_src_ovl, in->ptr, in->len, cudaMemcpyDeviceToDevice, st));
+                src = ctx->d_src_ovl;
+            }
+            if (gf_internal_draw_overlays((void*)st, const_cast<uint8_t*>(src), in->len, in->width, in->height, p->stride, p, ovl_count, ovl_scalar, 1,
+                                          drawing_dev, drawing_len) != GF_OK) return fail(ctx, GF_ERR_CUDA, "overlay kernel (input stage) failed");
+            ctx->aux_launches++;
+        }
+    }
     A.src = src; A.dst = dst; A.src_len = in->len; A.dst_len = out->len;
     const int bpp = ctx->bpp;
     A.out_rows = (int)((out->len + (size_t)p->output_stride - 1) / (size_t)p->output_stride);
@@ -571,7 +638,30 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         // 32 x 4 threads (4 x 8 output rows... 32 x 8 pixels) per block measured 2 % faster than 32 x 8 threads (finer tail); GF_X2_BLOCK_Y overrides
         static const int by = [] { const char* e = getenv("GF_X2_BLOCK_Y"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }();
         const dim3 block2(GF_BLOCK_X, by), grid2(grid.x, (A.out_rows + 2 * by - 1) / (2 * by));
-        x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
+        // filtered pre-pass: fisheye without a digital lens, rolling shutter on, geometry that fits the queue's 16 + 16 bit entries
+        const float a_cap = (ctx->distortion_model == GF_LENS_OPENCV_FISHEYE && ctx->digital_lens == GF_LENS_NONE && (A.feat & F_RS) && !ctx->no_filter &&
+                             A.out_cols <= 65536 && A.out_rows <= 131072) ? filter_a_cap(p->k) : 0.0f;
+        if (a_cap > 0.0f) {
+            if (!ctx->d_defer_q) {
+                ctx->defer_cap = 1u << 20;                             // 4 MB: 1 M pairs = a quarter of a 4K frame's pairs; a full queue falls back inline
+                CK(cudaMalloc(&ctx->d_defer_q, (size_t)ctx->defer_cap * sizeof(uint32_t)));
+                CK(cudaMalloc(&ctx->d_defer_count, 2 * sizeof(unsigned)));
+                CK(cudaMemsetAsync(ctx->d_defer_count, 0, 2 * sizeof(unsigned), st));
+            }
+            const unsigned cur = (unsigned)(ctx->filter_frames & 1ull);
+            ctx->filter_frames++;
+            A.feat |= F_FILTER;
+            A.flt.q = ctx->d_defer_q; A.flt.cap = ctx->defer_cap;
+            A.flt.count = ctx->d_defer_count + cur; A.flt.count_next = ctx->d_defer_count + (cur ^ 1u);
+            A.flt.rho = 0x1p-17f; A.flt.a_cap = a_cap; A.flt.tail = 0;
+            x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
+            CK(cudaGetLastError());
+            A.flt.tail = 1;                                            // the deferred pairs, exact pre-pass; also re-arms the other counter
+            x2<<<dim3(148 * 2, 1), block2, 0, st>>>(A);
+            ctx->launches++;
+        } else {
+            x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
+        }
     }
     else {
         for (int mi = 0; mi < n_maps; ++mi) {                  // one launch, or three for EWA (pixel, x-probe, y-probe)
@@ -597,6 +687,11 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         }
     }
     if (use_slot) CK(cudaEventRecord(sl.done, st));
+    if (ctx->overlays && more_planes == 0 && !coord_only) {    // output stage: stage-1 drawing entries + safe area, on the final pixels
+        if (gf_internal_draw_overlays((void*)st, dst, out->len, out->width, out->height, p->output_stride, p, ovl_count, ovl_scalar, 0,
+                                      drawing_dev, drawing_len) != GF_OK) return fail(ctx, GF_ERR_CUDA, "overlay kernel (output stage) failed");
+        ctx->aux_launches++;
+    }
     if (checksum_dev) {                                        // render queue: per-frame output checksum, before the result leaves the device
         if (gf_cuda_checksum_dev(dst, std::min<size_t>(out->len, (size_t)out->height * (size_t)p->output_stride), checksum_dev, (void*)st) != GF_OK)
             return fail(ctx, GF_ERR_CUDA, "checksum kernel failed");
@@ -628,8 +723,9 @@ extern "C" {
 GF_API int gf_cuda_undistort_image(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
                                    const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
                                    const float* mesh, size_t mesh_len, const uint8_t* drawing, size_t drawing_len, void* cu_stream) {
-    (void)drawing; (void)drawing_len;    // the CPU path (the parity target) draws no overlay: cpu_undistort.rs:234-251,607,617
-    return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream);
+    // the CPU path (the parity target) draws no overlay (cpu_undistort.rs:234-251,607,617): `drawing` is used only after
+    // gf_cuda_set_overlays(ctx, 1) — then like the reference's GPU kernels (opencl_undistort.cl:121-154, overlay.cu)
+    return run_warp(ctx, in, out, params, matrices, matrix_rows, mesh, mesh_len, false, cu_stream, true, 0, false, nullptr, nullptr, drawing, drawing_len);
 }
 
 GF_API int gf_cuda_undistort_image_dev(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_desc* out,
@@ -852,6 +948,12 @@ GF_API int gf_cuda_synchronize(gf_cuda_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->last_stream && ctx->last_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_stream));   // calls made with a caller-supplied stream
+    return GF_OK;
+}
+
+GF_API int gf_cuda_set_overlays(gf_cuda_ctx* ctx, int enabled) {
+    if (!ctx) return fail(nullptr, GF_ERR_BAD_PARAMS, "ctx is null");
+    ctx->overlays = enabled ? 1 : 0;
     return GF_OK;
 }
 

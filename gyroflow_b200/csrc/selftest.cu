@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+#include <vector>
 #include "../../include/gyroflow_cuda.h"
 #include "warp_kernel_x2.cuh"
 
@@ -119,7 +121,96 @@ __global__ void sweep_kernel(uint32_t lo, uint32_t hi, int which, unsigned long 
     }
     if (bad) atomicAdd(out, bad);
 }
+
+// Filtered pre-pass certificate (Lens2<opencv_fisheye>::approx_v) against the exact chain, on the real MUFU units: for `n_cfg` random
+// configurations (fisheye coefficients of either sign up to the conditioning cap, a random mid-row matrix = K_new^-1-like scale times a
+// rotation of up to ~25 degrees with random translation terms, frame sizes 1280..8192) every pixel of a sampled grid is evaluated both
+// ways.  out[0] = pixels inside the regime, out[1] = pixels whose |tv_approx - tv_exact| EXCEEDS the certificate's bound (must be 0),
+// out[2] = pixels the certificate calls uncertain (distance to the rounding boundary <= bound), out[3] = max |diff| / bound in 1e-6 units.
+struct FilterCfg { float m[9]; float k[4]; float f1, c1; float a_cap; int w, h; };
+__global__ void filter_check_kernel(const FilterCfg* __restrict__ cfgs, int n_cfg, int step, float rho, unsigned long long* out) {
+    unsigned long long in_regime = 0, violations = 0, uncertain = 0; unsigned worst = 0;
+    for (int ci = blockIdx.y; ci < n_cfg; ci += gridDim.y) {
+        const FilterCfg C = cfgs[ci];
+        gf_kernel_params P; memset(&P, 0, sizeof(P));
+        for (int i = 0; i < 4; ++i) P.k[i] = C.k[i];
+        P.f[0] = C.f1; P.f[1] = C.f1; P.c[0] = 0.5f * (float)C.w; P.c[1] = C.c1;
+        const int nx = (C.w + step - 1) / step, ny = (C.h + step - 1) / step;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx * ny; i += gridDim.x * blockDim.x) {
+            const float px = (float)((i % nx) * step + (ci % step)), py = (float)((i / nx) * step + ((ci / 3) % step));
+            const float _x = (px * C.m[0] + py * C.m[1]) + C.m[2];
+            const float _y = (px * C.m[3] + py * C.m[4]) + C.m[5];
+            const float _w = (px * C.m[6] + py * C.m[7]) + C.m[8];
+            float tvc;
+            if (!Lens2<GF_LENS_OPENCV_FISHEYE>::approx_v(_x, _y, _w, P, C.a_cap, tvc)) continue;
+            const float tv = tvc + P.c[1];
+            if (!(fabsf(tv) < 0x1p20f)) continue;
+            float ex, ey;
+            Lens<GF_LENS_OPENCV_FISHEYE>::distort(_x, _y, _w, P, false, ex, ey);       // the reference's arithmetic (scalar exact code)
+            const float tv_exact = ey * P.f[1] + P.c[1];
+            const float bound = __fmaf_rn(fabsf(tvc), rho, fabsf(tv) * 0x1p-22f);
+            const float diff = fabsf(tv - tv_exact);
+            ++in_regime;
+            if (!(diff <= bound)) ++violations;
+            const float z = tv - 0.5f;
+            if (!(fabsf(z - ((z + 12582912.0f) - 12582912.0f)) > bound)) ++uncertain;
+            const float ratio = bound > 0.0f ? diff / bound : (diff > 0.0f ? 1e9f : 0.0f);
+            worst = max(worst, (unsigned)fminf(ratio * 1e6f, 4.0e9f));
+        }
+    }
+    if (in_regime) atomicAdd(&out[0], in_regime);
+    if (violations) atomicAdd(&out[1], violations);
+    if (uncertain) atomicAdd(&out[2], uncertain);
+    atomicMax(&out[3], (unsigned long long)worst);
+}
 } // namespace
+
+extern "C" GF_API int gf_cuda_selftest_filter(int device, unsigned long long seed, int n_cfg, int step, unsigned long long* out4) {
+    if (!out4 || n_cfg < 1 || step < 1) return GF_ERR_BAD_PARAMS;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    std::vector<FilterCfg> cfgs((size_t)n_cfg);
+    uint64_t st = seed * 0x9E3779B97F4A7C15ULL + 12345u;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };   // [0, 1)
+    for (int i = 0; i < n_cfg; ++i) {
+        FilterCfg& C = cfgs[(size_t)i];
+        const int sizes[5][2] = { {3840, 2160}, {1920, 1080}, {7680, 4320}, {1280, 720}, {8192, 4320} };
+        C.w = sizes[i % 5][0]; C.h = sizes[i % 5][1];
+        // coefficients: scale a random sign pattern so that sum |k_i| t^(2i+2) reaches 1/4 somewhere between 0.6 and 1.55 rad
+        double k[4]; for (int j = 0; j < 4; ++j) k[j] = (rnd() * 2.0 - 1.0) * pow(0.35, j);
+        const double t_hit = 0.6 + 0.95 * rnd(), t2 = t_hit * t_hit;
+        const double B = t2 * (fabs(k[0]) + t2 * (fabs(k[1]) + t2 * (fabs(k[2]) + t2 * fabs(k[3]))));
+        const double sc = (i % 7 == 0) ? 0.02 / B : 0.25 / B;                 // every 7th: a weak lens (cap at 1.55 rad)
+        for (int j = 0; j < 4; ++j) C.k[j] = (float)(k[j] * sc);
+        auto Bf = [&](double t) { const double q = t * t; return q * (fabs((double)C.k[0]) + q * (fabs((double)C.k[1]) + q * (fabs((double)C.k[2]) + q * fabs((double)C.k[3])))); };
+        double lo = 0.0, hi = 1.55; if (Bf(hi) > 0.25) { for (int it = 0; it < 60; ++it) { const double mid = 0.5 * (lo + hi); if (Bf(mid) <= 0.25) lo = mid; else hi = mid; } } else lo = hi;
+        C.a_cap = (float)fmin(tan(lo) * tan(lo) * 0.999, 16000.0);
+        // mid-row matrix: (K_new R)^-1 with focal length 0.3..1.2 widths and a rotation of up to ~25 degrees about a random axis
+        const double f = (0.3 + 0.9 * rnd()) * C.w, cx = 0.5 * C.w, cy = 0.5 * C.h;
+        double ax[3] = { rnd() - 0.5, rnd() - 0.5, rnd() - 0.5 }; const double an = sqrt(ax[0]*ax[0] + ax[1]*ax[1] + ax[2]*ax[2]) + 1e-12;
+        for (double& v : ax) v /= an;
+        const double ang = 0.45 * rnd(), c = cos(ang), s = sin(ang), t = 1.0 - c;
+        const double R[9] = { t*ax[0]*ax[0] + c, t*ax[0]*ax[1] - s*ax[2], t*ax[0]*ax[2] + s*ax[1],
+                              t*ax[0]*ax[1] + s*ax[2], t*ax[1]*ax[1] + c, t*ax[1]*ax[2] - s*ax[0],
+                              t*ax[0]*ax[2] - s*ax[1], t*ax[1]*ax[2] + s*ax[0], t*ax[2]*ax[2] + c };
+        // inverse of K R = R^T K^-1, K^-1 = [[1/f, 0, -cx/f], [0, 1/f, -cy/f], [0, 0, 1]]
+        const double Ki[9] = { 1.0 / f, 0.0, -cx / f, 0.0, 1.0 / f, -cy / f, 0.0, 0.0, 1.0 };
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) C.m[r * 3 + q] = (float)(R[0 * 3 + r] * Ki[0 * 3 + q] + R[1 * 3 + r] * Ki[1 * 3 + q] + R[2 * 3 + r] * Ki[2 * 3 + q]);
+        C.f1 = (float)((0.3 + 0.9 * rnd()) * C.w); C.c1 = (float)(cy + (rnd() - 0.5) * 40.0);
+    }
+    FilterCfg* d_cfg = nullptr; unsigned long long* d_out = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_cfg, cfgs.size() * sizeof(FilterCfg))) != cudaSuccess || (e = cudaMalloc(&d_out, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+        if (d_cfg) cudaFree(d_cfg); (void)cudaGetLastError(); return GF_ERR_CUDA;
+    }
+    cudaMemcpy(d_cfg, cfgs.data(), cfgs.size() * sizeof(FilterCfg), cudaMemcpyHostToDevice);
+    cudaMemset(d_out, 0, 4 * sizeof(unsigned long long));
+    filter_check_kernel<<<dim3(148, (unsigned)(n_cfg < 64 ? n_cfg : 64)), 256>>>(d_cfg, n_cfg, step, 0x1p-17f, d_out);
+    e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out4, d_out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_cfg); cudaFree(d_out);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
+    return GF_OK;
+}
 
 // out2[0]: mismatches of atanf2_core over all floats in [2^-28, 2^24); out2[1]: of sqrt_seq over all floats in [2^-56, 2^48).
 extern "C" GF_API int gf_cuda_selftest_exhaustive(int device, unsigned long long* out2) {

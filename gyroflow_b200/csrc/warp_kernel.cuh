@@ -51,6 +51,7 @@ enum : uint32_t {
     F_PIXLIMIT   = 1u << 21,  // pixel_value_limit below the format's maximum (the min() after sampling can bite)
     F_WILD       = 1u << 22,  // lens coefficients / translation2d / source mapping outside the magnitudes the packed fast paths assume
     F_INTPRO     = 1u << 23,  // packed kernel: both output maps are the identity -> integer prologue (X2Hot below)
+    F_FILTER     = 1u << 24,  // packed kernel: filtered rolling-shutter pre-pass (approximate mid-row evaluation + deferred exact pairs)
 };
 
 // Features the specialised ("lean") instantiation compiles out entirely.  The reference's OpenCL backend does the same
@@ -79,6 +80,17 @@ struct WarpArgs {
     uint2*         coord_out;       // multi-plane mode, pass 1: write the source coordinates of every output pixel here instead of sampling
     const uint2*   coord_in;        // pass 2 (shade_from_coords_kernel): read them back
     const uint32_t* table_flags;    // device word: 0 = the matrix table is tame and IBIS-free (packed kernel: trusted path), see warp_kernel_x2
+    // filtered rolling-shutter pre-pass of the packed kernel (F_FILTER): pairs whose row choice the approximate evaluation cannot
+    // certify are appended to `q` and rendered by a second launch of the same kernel in tail mode
+    struct X2Filter {
+        uint32_t* q;                // deferred pairs: x | (y0 / 2) << 16
+        unsigned* count;            // number of entries appended by this frame's main launch
+        unsigned* count_next;       // the next frame's counter, zeroed by this frame's tail launch
+        uint32_t  cap;              // capacity of q (a full queue makes the thread take the exact pre-pass inline)
+        int       tail;             // 1 = this launch renders the queue
+        float     rho;              // relative tolerance of the certificate
+        float     a_cap;            // r^2 below which the tolerance holds for this lens (polynomial conditioning), <= 2^14
+    } flt;
     int            coord_shift;     // pass 1: 0 = pixel (x, y); 1 = (x + 0.01, y); 2 = (x, y + 0.01) — the EWA Jacobian probes of :567-572
     int            coord_maps;      // pass 2: 1, or 3 when the two probe maps follow the first one (stride out_cols * out_rows)
     unsigned long long src_len, dst_len;

@@ -18,6 +18,7 @@
 // Behavioural source: src/core/stabilization/cpu_undistort.rs:133-228, :421-517, :543-625 (as warp_kernel.cuh).
 #pragma once
 #include "warp_kernel.cuh"
+#include "approx_atan_table.inc"
 
 namespace gf {
 
@@ -40,10 +41,38 @@ GF_DEV bool zero_or_in_window(float v) {
 // All predicates are combined with & and | (never && / ||) so that no branch is generated for them.
 // ------------------------------------------------------------------------------------------
 template <int M> struct Lens2 { static constexpr bool kHas = false; };
+// lens models with an approximate v evaluation for the filtered rolling-shutter pre-pass (Lens2<M>::approx_v)
+template <int M> struct LensApprox { static constexpr bool value = false; };
+template <> struct LensApprox<GF_LENS_OPENCV_FISHEYE> { static constexpr bool value = true; };
 
 // opencv_fisheye.rs:72-93 (k != 0: the lean kernel is only chosen when F_LENS_NOOP is clear; |k| bounded by the host)
 template <> struct Lens2<GF_LENS_OPENCV_FISHEYE> {
     static constexpr bool kHas = true;
+    // FILTERED PRE-PASS.  The mid-row evaluation of cpu_undistort.rs:470-479 only decides which matrix row a pixel uses:
+    // idx = clamp(round(v_mid), 0, H).  This is v_mid - c_y computed CHEAPLY — one MUFU.RCP instead of two refined divisions, no
+    // square root, atan(r) / r from a cubic table in r^2 (approx_atan_table.inc), fused multiply-adds — together with a proven bound
+    // on its distance from the reference's own float result (DESIGN.md §4 "filtered pre-pass"):
+    //     |tv_approx - tv_exact| <= rho * |tv - c_y| + 2^-22 * |tv|,   rho = 2^-17,
+    // valid while the divisor w is in the window of the exact sequences and r^2 < a_cap (the host derives a_cap from k so that the
+    // polynomial 1 + k0 t^2 + ... stays within [3/4, 5/4], which bounds its cancellation).  (_x, _y, _w) are the reference's own
+    // unfused products — bit-identical to the exact chain — so only relative perturbations enter after them.
+    // Returns false outside that regime; tvc = (v - c_y) otherwise.
+    static GF_DEV bool approx_v(float _x, float _y, float _w, const gf_kernel_params& P, float a_cap, float& tvc) {
+        const bool ok_w = (_w >= 0x1p-56f) & (_w < 0x1p48f);
+        const float iw = p2::rcp_approx(_w);
+        const float x = _x * iw, y = _y * iw;
+        const float a = __fmaf_rn(x, x, y * y);
+        const uint32_t ab = __float_as_uint(a);
+        const int idx = min(max((int)(ab >> 19) - (int)GF_APX_BASE, 0), GF_APX_ROWS - 1);
+        const float a0 = __uint_as_float((ab & 0xfff80000u) | 0x00040000u);      // midpoint of a's 1/16-octave interval
+        const float4 c = __ldg(&GF_APX_TAB[idx]);
+        const float d = a - a0;
+        const float T = __fmaf_rn(d, __fmaf_rn(d, __fmaf_rn(d, c.w, c.z), c.y), c.x);   // atan(r) / r
+        const float t2 = (a * T) * T;                                                     // theta^2
+        const float s = __fmaf_rn(t2, __fmaf_rn(t2, __fmaf_rn(t2, __fmaf_rn(t2, P.k[3], P.k[2]), P.k[1]), P.k[0]), 1.0f);
+        tvc = ((y * T) * s) * P.f[1];
+        return ok_w & (a < a_cap);              // NaN compares false
+    }
     template <bool TRUSTED>
     static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
         using namespace p2;
@@ -451,12 +480,12 @@ GF_DEV void shade_lean(bool ok, bool far, float u, float v, int wu, int wv, cons
 
 // COORD: pass 1 of the two-pass mode — write the coordinates to A.coord_out instead of sampling (pixel-format independent: the
 // pixel size then comes from KernelParams, PIX is a placeholder).
+// exact_prepass: evaluate the mid-row transform with the reference's own arithmetic (always true unless the frame runs the filtered
+// pre-pass; true as well for the pairs the tail launch re-renders)
 template <int LENS, int DIGITAL, class PIX, bool TRUSTED, bool COORD>
-GF_DEV void warp_x2_body(const WarpArgs& A) {
+GF_DEV void warp_x2_body(const WarpArgs& A, const int x, const int y0, const bool exact_prepass) {
     using namespace p2;
     const gf_kernel_params& P = A.p;
-    const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;          // blockDim.y: the host may launch flatter blocks (GF_X2_BLOCK_Y)
     if (x >= A.out_cols || y0 >= A.out_rows) return;
     const unsigned long long BYTES = COORD ? (unsigned long long)P.bytes_per_pixel : (unsigned long long)PIX::BYTES;
     const unsigned long long ostride = (unsigned long long)P.output_stride;
@@ -493,7 +522,39 @@ GF_DEV void warp_x2_body(const WarpArgs& A) {
     const int lim = A.rs_lim;
     int sy_a, sy_b;
     round_away_clamped_x2(py, lim, sy_a, sy_b);                                                         // :465-469
-    if (A.feat & F_RS) {                                                                                // :470-479
+    bool have_row = false;
+    if constexpr (TRUSTED && LensApprox<LENS>::value && DIGITAL == GF_LENS_NONE) if (!exact_prepass) {  // F_FILTER & F_RS (host)
+        // :470-479, filtered: certify round(v_mid) from the approximate evaluation, defer the pair when it cannot be
+        const MatRow9 rm = load_row9(A.matrices, (uint32_t)P.matrix_count / 2u);
+        const float bx = pxs * rm.m01.x, by = pxs * rm.m23.y, bw = pxs * rm.m67.x;                      // the reference's products and sums, unfused
+        const float xa = (bx + py.x * rm.m01.y) + rm.m23.x, xb = (bx + py.y * rm.m01.y) + rm.m23.x;
+        const float ya = (by + py.x * rm.m45.x) + rm.m45.y, yb = (by + py.y * rm.m45.x) + rm.m45.y;
+        const float wa = (bw + py.x * rm.m67.y) + rm.m8,    wb = (bw + py.y * rm.m67.y) + rm.m8;
+        float ca, cb;
+        const bool ra = Lens2<LENS>::approx_v(xa, ya, wa, P, A.flt.a_cap, ca);
+        const bool rb = Lens2<LENS>::approx_v(xb, yb, wb, P, A.flt.a_cap, cb);
+        const float ta = ca + P.c[1], tb = cb + P.c[1];
+        // distance of t to the nearest rounding boundary n + 1/2 (|t| < 2^20: the magic-number rounding is exact)
+        const float za = ta - 0.5f, zb = tb - 0.5f;
+        const float da = fabsf(za - ((za + 12582912.0f) - 12582912.0f)), db = fabsf(zb - ((zb + 12582912.0f) - 12582912.0f));
+        const float ea = __fmaf_rn(fabsf(ca), A.flt.rho, fabsf(ta) * 0x1p-22f), eb = __fmaf_rn(fabsf(cb), A.flt.rho, fabsf(tb) * 0x1p-22f);
+        const bool sure = ra & rb & (da > ea) & (db > eb) & (fabsf(ta) < 0x1p20f) & (fabsf(tb) < 0x1p20f);
+        if (sure) {
+            round_away_clamped_x2(mk(ta, tb), lim, sy_a, sy_b);
+            have_row = true;
+        } else {                                         // append the pair to the frame's queue (warp-aggregated), rendered by the tail launch
+            const unsigned m = __activemask();
+            const unsigned lane = threadIdx.x & 31u;
+            const int leader = __ffs((int)m) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(A.flt.count, (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            const unsigned slot = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+            if (slot < A.flt.cap) { A.flt.q[slot] = (uint32_t)x | ((uint32_t)(y0 >> 1) << 16); return; }
+            // queue full: this thread evaluates the exact pre-pass itself
+        }
+    }
+    if ((A.feat & F_RS) && !have_row) {                                                                 // :470-479
         const uint32_t mid = (uint32_t)P.matrix_count / 2u;
         f2 tu, tv; bool oa = true, ob = true, bad = false;
         rotate_and_distort_x2<LENS, DIGITAL, TRUSTED>(px, py, mid, mid, A, tu, tv, bad);
@@ -538,11 +599,31 @@ GF_DEV void warp_x2_body(const WarpArgs& A) {
 // context-owned constant, gf_cuda_scan_tables_dev for caller-owned device tables, or the on-device producer
 // gf_cuda_frame_transform_dev itself): 0 = every entry zero or 2^-40..2^40 and no IBIS rows.  Trust is therefore a property of
 // the bytes the kernel is about to read, ordered by the stream — not of a host-side pointer cache.  The branch is uniform.
+//
+// Filtered frames (F_FILTER, host-selected: trusted-capable lens with an approximate form, rolling shutter on) launch this kernel
+// twice: the main launch certifies each pair's matrix row from the approximate mid-row evaluation and appends the few pairs it
+// cannot certify to a queue; the tail launch (A.flt.tail, a small grid-stride grid) renders exactly those with the exact pre-pass.
 template <int LENS, int DIGITAL, class PIX, int MINB, bool COORD = false>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
-    if (__ldg(A.table_flags) == 0u) warp_x2_body<LENS, DIGITAL, PIX, true, COORD>(A);
-    else                            warp_x2_body<LENS, DIGITAL, PIX, false, COORD>(A);
+    constexpr bool kFilter = LensApprox<LENS>::value && DIGITAL == GF_LENS_NONE;
+    const bool trusted = __ldg(A.table_flags) == 0u;
+    if constexpr (kFilter) if (A.flt.tail) {
+        const unsigned tid = (blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
+        if (tid == 0u) *A.flt.count_next = 0u;                       // re-arm the counter the NEXT frame's main launch will use
+        if (!trusted) return;                                         // the main launch deferred nothing on the guarded path
+        const unsigned n = min(*A.flt.count, A.flt.cap);
+        const unsigned stride = gridDim.x * gridDim.y * blockDim.x * blockDim.y;
+        for (unsigned i = tid; i < n; i += stride) {
+            const uint32_t e = A.flt.q[i];
+            warp_x2_body<LENS, DIGITAL, PIX, true, COORD>(A, (int)(e & 0xffffu), (int)(e >> 16) * 2, true);
+        }
+        return;
+    }
+    const int x = blockIdx.x * GF_BLOCK_X + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;          // blockDim.y: the host may launch flatter blocks (GF_X2_BLOCK_Y)
+    if (trusted) warp_x2_body<LENS, DIGITAL, PIX, true, COORD>(A, x, y0, !(kFilter && (A.feat & F_FILTER)));
+    else         warp_x2_body<LENS, DIGITAL, PIX, false, COORD>(A, x, y0, true);
 }
 
 } // namespace gf

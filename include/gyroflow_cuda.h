@@ -291,6 +291,14 @@ GF_API int         gf_cuda_validate_tables_dev(gf_cuda_ctx* ctx, const float* ma
 GF_API int         gf_cuda_plan(const gf_kernel_params* params, int pixel_type, int distortion_model, int digital_lens,
                                 const gf_buffer_desc* in, const gf_buffer_desc* out, size_t mesh_len, uint32_t table_flags, size_t n_planes);
 
+/* Preview overlays of the reference's GPU kernels — draw_pixel + draw_safe_area, src/core/gpu/opencl_undistort.cl:109-154, buffer
+ * produced by gpu/drawing.rs:8-50.  OFF by default: the CPU path, the parity target, draws none
+ * (cpu_undistort.rs:234-251).  When on, gf_cuda_undistort_image uses its `drawing` argument (if KernelParams.flags has DRAWING_ENABLED):
+ * entries with stage bit 0 are drawn onto the device copy of the input before the warp (the .cl draws them onto every source tap),
+ * entries with stage bit 1 and the safe-area shading (safe_area_rect) onto the output after it.  The caller's input buffer is never
+ * modified.  Single-plane calls only. */
+GF_API int         gf_cuda_set_overlays(gf_cuda_ctx* ctx, int enabled);
+
 /* Waits for the context's own stream AND for the stream of the most recent call that named one. */
 GF_API int         gf_cuda_synchronize(gf_cuda_ctx* ctx);
 GF_API const char* gf_cuda_last_error(gf_cuda_ctx* ctx);     /* ctx may be NULL: last global error */
@@ -305,6 +313,10 @@ GF_API int         gf_cuda_selftest(int device, unsigned long long n, unsigned l
 /* Exhaustive variant (seconds): every input of the packed atanf ([2^-28, 2^24)) and of the packed square root ([2^-56, 2^48));
  * out2 = mismatch counts.  Test hook. */
 GF_API int         gf_cuda_selftest_exhaustive(int device, unsigned long long* out2);
+/* Certificate of the filtered rolling-shutter pre-pass: n_cfg random fisheye lenses / mid-row matrices / frame sizes, every
+ * `step`-th pixel evaluated by the approximate and by the exact chain on the device.  out4 = { pixels inside the regime, pixels whose
+ * difference exceeds the proven bound (must be 0), pixels the certificate leaves uncertain, max difference / bound in 1e-6 units }. */
+GF_API int         gf_cuda_selftest_filter(int device, unsigned long long seed, int n_cfg, int step, unsigned long long* out4);
 
 
 /* ------------------------------------------------------------------------------------------

@@ -859,6 +859,59 @@ static inline void pix_from_float(uint8_t* p, v4 val, int count, int scalar) {  
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Preview overlays — src/core/gpu/opencl_undistort.cl:109-154 (draw_pixel, draw_safe_area; colours / alphas :109-120).
+ * DATA_CONVERT is convert_<T>_sat with OpenCL's default round-toward-zero = the truncating, saturating `as` cast.
+ * ---------------------------------------------------------------------------------------- */
+static const float OVL_COLORS[9][4] = { {0, 0, 0, 0}, {255, 0, 0, 255}, {0, 255, 0, 255}, {0, 0, 255, 255}, {254, 251, 71, 255},
+                                        {200, 200, 0, 255}, {255, 0, 255, 255}, {0, 128, 255, 255}, {0, 200, 200, 255} };
+static const float OVL_ALPHAS[4] = { 1.0f, 0.75f, 0.50f, 0.25f };
+void gf_oracle_draw_overlays(uint8_t* buf, size_t len, int width, int height, int stride, const gf_kernel_params* P, int pixel_type,
+                             int is_input, const uint8_t* drawing, size_t drawing_len) {
+    int count, scalar;
+    if (!pix_layout(pixel_type, &count, &scalar)) return;
+    const int sb = scalar == SC_U8 ? 1 : (scalar == SC_F32 ? 4 : 2), bpp = count * sb;
+    const int dw = P->width > P->output_width ? P->width : P->output_width;               /* max(params->width, params->output_width) */
+    for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) {
+        const size_t off = (size_t)y * (size_t)stride + (size_t)x * (size_t)bpp;
+        if (off + (size_t)bpp > len) continue;
+        uint8_t* px = buf + off;
+        if ((P->flags & 8) && drawing && drawing_len) {                                      /* draw_pixel :121-140 */
+            const float fpos = rs_round(floorf((float)y / P->canvas_scale) * ((float)dw / P->canvas_scale) + floorf((float)x / P->canvas_scale));
+            const int32_t pos = rs_f32_as_i32(fpos);
+            if (pos >= 0 && (size_t)pos < drawing_len) {
+                const uint8_t data = drawing[pos];
+                if (data > 0) {
+                    const int color = (data & 0xF8) >> 3, alpha = (data & 0x06) >> 1, stage = data & 1;
+                    if (((stage == 0 && is_input) || (stage == 1 && !is_input)) && color < 9 && alpha < 4) {
+                        v4 v = pix_to_float(px, count, scalar);
+                        const float af = OVL_ALPHAS[alpha];
+                        for (int c = 0; c < count; ++c) v.v[c] = OVL_COLORS[color][c] * af + v.v[c] * (1.0f - af);
+                        pix_from_float(px, v, count, scalar);
+                    }
+                }
+            }
+        }
+        if (!is_input) {                                                                     /* draw_safe_area :141-154 */
+            const float fx = (float)x, fy = (float)y;
+            const float* r = P->safe_area_rect;
+            const int safe = fx >= r[0] && fx <= r[2] && fy >= r[1] && fy <= r[3];
+            if (!safe) {
+                static const float factor[4] = { 0.5f, 0.5f, 0.5f, 1.0f };
+                v4 v = pix_to_float(px, count, scalar);
+                for (int c = 0; c < count; ++c) v.v[c] = v.v[c] * factor[c];
+                pix_from_float(px, v, count, scalar);
+                const int border = fx >= r[0] - 5.0f && fx <= r[2] + 5.0f && fy >= r[1] - 5.0f && fy <= r[3] + 5.0f;
+                if (border) {
+                    v = pix_to_float(px, count, scalar);
+                    for (int c = 0; c < count; ++c) v.v[c] = v.v[c] * factor[c];
+                    pix_from_float(px, v, count, scalar);
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * sample_input_at — cpu_undistort.rs:329-419, separable branch (I <= 8) :370-412.
  * Bilinear weights: COEFFS[0..64] (cpu_undistort.rs:14-19) are exactly (1 - i/32, i/32).
  * ---------------------------------------------------------------------------------------- */

@@ -85,6 +85,13 @@ double gf_oracle_find_fov(const gf_compute_params* cp, int distortion_model, int
  * in/out: n per-frame fovs. */
 void gf_oracle_zoom_dynamic(const double* fov_minimal, size_t n, double window_s, double fps, int method, double* out);
 
+/* Preview overlays of the GPU kernels (the CPU path draws none, cpu_undistort.rs:234-251): draw_pixel + draw_safe_area of
+ * src/core/gpu/opencl_undistort.cl:109-154, applied IN PLACE to a rendered buffer of `width` x `height` pixels (is_input = 0: the
+ * output-stage overlay of :644-645 / :654-655, stage-1 drawing entries + safe area; is_input = 1: the stage-0 entries the kernel draws
+ * onto every source tap, :338 / :374 — equivalent to drawing them onto the input image first).  Unfused float arithmetic. */
+void gf_oracle_draw_overlays(uint8_t* buf, size_t len, int width, int height, int stride, const gf_kernel_params* P, int pixel_type,
+                             int is_input, const uint8_t* drawing, size_t drawing_len);
+
 int gf_oracle_online_cpus(void);
 const char* gf_oracle_describe(void);
 

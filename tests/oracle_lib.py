@@ -54,6 +54,8 @@ def load():
     lib.gf_oracle_undistort_points_rs.argtypes = [P(abi.ComputeParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_size_t, C.c_double, C.c_void_p]
     lib.gf_oracle_zoom_dynamic.restype = None
     lib.gf_oracle_zoom_dynamic.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    lib.gf_oracle_draw_overlays.restype = None
+    lib.gf_oracle_draw_overlays.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, P(abi.KernelParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.gf_oracle_online_cpus.restype = C.c_int
     lib.gf_oracle_describe.restype = C.c_char_p
     _lib = lib
@@ -99,3 +101,11 @@ def zoom_dynamic(fov_minimal, window_s, fps, method=1):
     a = np.ascontiguousarray(fov_minimal, dtype=np.float64); out = np.zeros_like(a)
     lib.gf_oracle_zoom_dynamic(a.ctypes.data, a.size, window_s, fps, method, out.ctypes.data)
     return out
+
+
+def draw_overlays(buf, width, height, stride, params, pixel_type, is_input, drawing):
+    """draw_pixel / draw_safe_area of opencl_undistort.cl:109-154 in place on `buf` (oracle restatement)."""
+    lib = load()
+    d = np.ascontiguousarray(drawing if drawing is not None else np.zeros(0, np.uint8), dtype=np.uint8)
+    lib.gf_oracle_draw_overlays(buf.ctypes.data, buf.nbytes, width, height, stride, C.byref(params), abi.PIXEL_TYPES[pixel_type][0], int(is_input),
+                                d.ctypes.data if d.size else None, d.size)

@@ -28,9 +28,13 @@ def run_both(case, device_buffers=False):
         bufs = g.Buffers(g.BufferDescription((bw, bh, p.stride), src), g.BufferDescription((obw, obh, p.output_stride), got))
         w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
         w.undistort_image(bufs, itm)
-        # bilinear: one fused launch; other resamplers: coordinate pass(es) + sampling pass (EWA: pixel + two Jacobian probes)
+        # bilinear: one fused launch; other resamplers: coordinate pass(es) + sampling pass (EWA: pixel + two Jacobian probes);
+        # a frame on the filtered pre-pass (packed fisheye kernel, rolling shutter on) adds the tail launch that renders the deferred pairs
         interp = case.get("interp", "Bilinear")
-        assert w.launch_count == (1 if interp == "Bilinear" else (4 if interp.startswith("EWA") else 2)), w.launch_count
+        base = 1 if interp == "Bilinear" else (4 if interp.startswith("EWA") else 2)
+        assert w.launch_count in (base, base + 1), w.launch_count
+        if w.launch_count == base + 1:
+            assert lens == "opencv_fisheye" and digital is None and m.shape[0] > 1 and not interp.startswith("EWA") and not os.environ.get("GF_DISABLE_FILTER")
         w.close()
     else:
         import torch
@@ -213,7 +217,8 @@ def _assert_planes(case, n_planes, fused, vary=None):
     interp = case.get("interp", "Bilinear")
     coord_passes = 3 if interp.startswith("EWA") else 1
     single = 1 if interp == "Bilinear" else coord_passes + 1
-    assert launches == (coord_passes + n_planes if fused else n_planes * single), launches
+    want_l = coord_passes + n_planes if fused else n_planes * single
+    assert launches in (want_l, want_l + 1, want_l + n_planes), launches          # + tail launch(es) of the filtered pre-pass (fisheye + rolling shutter)
     for i, (want, got) in enumerate(outs):
         n, mx = cases.compare(want, got, pix)
         assert n == 0, "plane %d: %d mismatching bytes (max abs diff %s) for %r" % (i, n, mx, case)
@@ -379,8 +384,34 @@ def test_packed_primitives_selftest():
     assert list(out) == [0, 0, 0, 0], list(out)
 
 
-@pytest.mark.skipif(not os.environ.get("GF_RUN_EXHAUSTIVE"), reason="opt-in: GF_RUN_EXHAUSTIVE=1 (every input of the packed atanf / sqrt, a few seconds)")
+def test_filtered_prepass_certificate_on_device():
+    """The filtered rolling-shutter pre-pass (Lens2<opencv_fisheye>::approx_v): on the real MUFU units, over 400 random lenses / mid-row
+    matrices / frame sizes and every 3rd pixel, the approximate v never differs from the reference's float result by more than the
+    proven bound rho |tv - c| + 2^-22 |tv| (0 violations), stays well inside it, and leaves only a few percent of the pixels uncertain."""
+    import ctypes as C
+    out = (C.c_ulonglong * 4)()
+    assert g.load_library().gf_cuda_selftest_filter(0, 2024, 400, 3, out) == 0
+    n, viol, unc, worst = [int(v) for v in out]
+    assert n > 2e8, n
+    assert viol == 0, (viol, worst)
+    assert worst <= 500000, worst                  # max |diff| / bound <= 0.5: a factor two of margin on top of the analysis
+    assert unc / n < 0.05, unc / n
+
+
+def test_filtered_prepass_queue_overflow_and_extremes(monkeypatch):
+    """Frames where the certificate fails for MANY pairs — strong roll (the row boundaries run diagonally through every warp), a lens at
+    its conditioning cap, a view zoomed out past the cap, translation — still match the oracle: deferred pairs go through the tail
+    launch, a full queue falls back to the exact pre-pass inline."""
+    for c in (dict(w=1920, h=1080, video_rotation=33.0), dict(w=1920, h=1080, fov=3.5, ts=1234.0), dict(w=1280, h=720, params=dict(k=[0.18, -0.06, 0.02, -0.004] + [0.0] * 8)),
+              dict(w=1280, h=720, params=dict(k=[-0.21, 0.0, 0.0, 0.0] + [0.0] * 8), fov=1.7), dict(w=1280, h=720, params=dict(translation2d=[13.5, -7.25]), readout=33.0),
+              dict(w=3840, h=2160, ts=3456.7, pix="Luma8"), dict(w=2048, h=1152, ow=1024, oh=576), dict(w=640, h=360, out_size=(700, 400), out_rect=(30, 20, 640, 360))):
+        assert_bit_exact(c)
+        assert_bit_exact(c, device_buffers=True)
+
+
 def test_packed_sequences_exhaustive_on_device():
+    """Every input of the packed atanf ([2^-28, 2^24): 4.4e8 floats) and of the packed square root ([2^-56, 2^48)) against the scalar
+    functions, on the device (a few seconds; round 2 runs it unconditionally)."""
     import ctypes as C
     out = (C.c_ulonglong * 2)()
     assert g.load_library().gf_cuda_selftest_exhaustive(0, out) == 0
@@ -512,6 +543,10 @@ def test_kernel_variants_agree(monkeypatch):
     case = dict(w=1280, h=720)
     want, got_x2, pix = run_both(case)
     assert cases.compare(want, got_x2, pix)[0] == 0
+    monkeypatch.setenv("GF_DISABLE_FILTER", "1")                 # packed kernel with the exact pre-pass for every pair
+    _, got_nofilter, _ = run_both(case)
+    assert np.array_equal(got_x2, got_nofilter)
+    monkeypatch.delenv("GF_DISABLE_FILTER")
     monkeypatch.setenv("GF_DISABLE_X2", "1")
     _, got_lean, _ = run_both(case)
     assert np.array_equal(got_x2, got_lean)

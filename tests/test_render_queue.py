@@ -52,7 +52,7 @@ def test_queue_device_buffers_every_frame_matches_oracle():
     ts_of = lambda f: 300.0 + f * (1000.0 / FPS)
     sums = q.render(range(n), ts_of, lambda f: bufs[f])
     assert list(sums) == list(range(n))                       # frame order restored
-    assert q.launch_count == 3 * n                            # producer + warp + checksum per frame, nothing else
+    assert q.launch_count == 4 * n                            # producer + warp (main + tail of the filtered pre-pass) + checksum per frame, nothing else
     q.close()
     dg = g.DeviceGyro(cp)
     mats = torch.zeros((max(W, H), 14), dtype=torch.float32, device="cuda")
