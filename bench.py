@@ -303,7 +303,7 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
     qv = g.RenderQueue(cp, st, LENS, None, dbufs[0].input, dbufs[0].output, device=local, depth=2, pin_numa=False, checksum=True)
     n_check = 8
     mine = render_queue.shard_frames(n_check, world, rank)
-    sums = qv.render(mine, ts_of, lambda f: dbufs[0]) if mine else {}
+    sums = qv.render(mine, ts_of, lambda f: dbufs[(f // world) % RING]) if mine else {}    # distinct buffers for the frames in flight
     qv.close()
     if world > 1: sums = render_queue.gather_results(sums, dist, torch, dev)
 
@@ -468,6 +468,7 @@ def main():
     ap.add_argument("--legacy", action="store_true", help="round-1 measurement shape (recycled precomputed tables) for the default config too")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--lens", default=None, help="override the config's lens model (side measurement), e.g. sony, opencv_standard")
+    ap.add_argument("--digital", default=None, help="override the config's digital lens (side measurement), e.g. gopro_superview, digital_stretch, gopro_warp")
     ap.add_argument("--planes", type=int, default=1, help="planes of this geometry per frame, rendered by one gf_cuda_undistort_planes_dev call (side measurement)")
     ap.add_argument("--interp", default="Bilinear", help="Bilinear (BASELINE), Bicubic, Lanczos4, 'EWA: Robidoux', ... (side measurement)")
     args = ap.parse_args()
@@ -476,6 +477,8 @@ def main():
     INTERP = args.interp
     if args.lens:
         LENS = args.lens; WORKLOAD = WORKLOAD.replace(CFG["lens"], args.lens)
+    if args.digital:
+        CFG["digital"] = args.digital; WORKLOAD = WORKLOAD.replace(LENS, LENS + " + " + args.digital + " digital lens", 1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -495,7 +498,7 @@ def main():
     lib = g.load_library()
     assert lib.gf_cuda_device_count() > local, "no CUDA device for this rank (there is no CPU fallback)"
 
-    if args.config == 2 and not args.lens and args.planes == 1 and INTERP == "Bilinear" and not args.legacy:
+    if args.config == 2 and not args.lens and not args.digital and args.planes == 1 and INTERP == "Bilinear" and not args.legacy:
         return run_pipeline(args, torch, dist, g, rank, world, local, dev)
 
     # ---- tables: rank 0 builds them, NCCL broadcasts them (the only collective of the path) -------------------

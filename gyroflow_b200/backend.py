@@ -178,6 +178,19 @@ class CudaWrapper:
         if rc != 0:
             raise self._err(rc)
 
+    def undistort_planes(self, buffers, params, itm: FrameTransform, stream: int = 0):
+        """The planes of one frame in HOST memory (gf_cuda_undistort_planes): buffers = list of Buffers with numpy data, params = list of
+        KernelParams; tables from `itm` (host).  Synchronous."""
+        n = len(buffers)
+        ins = (abi.BufferDesc * n)(*[b.input.to_c() for b in buffers])
+        outs = (abi.BufferDesc * n)(*[b.output.to_c() for b in buffers])
+        ps = (abi.KernelParams * n)(*params)
+        m = np.ascontiguousarray(itm.matrices, dtype=np.float32)
+        mesh = np.ascontiguousarray(itm.mesh_data, dtype=np.float32)
+        rc = self._lib.gf_cuda_undistort_planes(self._h, n, ins, outs, ps, m.ctypes.data, m.shape[0], mesh.ctypes.data if mesh.size else None, mesh.size, stream or None)
+        if rc != 0:
+            raise self._err(rc)
+
     def validate_tables_dev(self, matrices_dev: int, matrix_rows: int):
         """Synchronous query of a device table's verdict: 0 tame and IBIS-free, bit 0 wild entry, bit 1 IBIS rows.  Nothing is cached."""
         rc = self._lib.gf_cuda_validate_tables_dev(self._h, matrices_dev, matrix_rows)

@@ -57,6 +57,8 @@ struct gf_cuda_ctx {
     int overlays = 0;
     uint8_t* h_drawing = nullptr; uint8_t* d_drawing = nullptr; size_t drawing_cap = 0;
     uint8_t* d_src_ovl = nullptr; size_t d_src_ovl_len = 0;
+    // HOST multi-plane frames (gf_cuda_undistort_planes): one device staging pair per plane beyond what d_src / d_dst hold
+    std::vector<uint8_t*> d_plane_src, d_plane_dst; std::vector<size_t> d_plane_src_len, d_plane_dst_len;
     uint2* d_coords = nullptr; size_t d_coords_len = 0;   // multi-plane mode: the frame's coordinate map
     KernelFn fn_shade = nullptr;
     unsigned long long aux_launches = 0;   // helper kernels (mesh widening, table scans): not counted by gf_cuda_launch_count
@@ -273,6 +275,9 @@ void fill_uniforms(WarpArgs& A, const gf_cuda_ctx* ctx, const uint8_t* src, cons
         for (int i = 0; i < 12; ++i) if (!(std::isfinite(p->k[i]) && fabsf(p->k[i]) <= 0x1p40f)) wild = true;
         if (!(fabsf(p->translation2d[0]) < 0x1p19f && fabsf(p->translation2d[1]) < 0x1p19f)) wild = true;
         if (!(tame(p->f[0]) && tame(p->f[1]) && std::isfinite(p->c[0]) && std::isfinite(p->c[1]))) wild = true;
+        // packed gopro lens: k1 is a divisor (paraxial guess of the Newton inversion) and the 89-degree cut-off is a literal
+        if (ctx->distortion_model == GF_LENS_GOPRO && (!(tame(p->k[1]) && p->k[1] != 0.0f) || gf_tanf(1.5533f) != 0x1.c9315ap+5f)) wild = true;
+        if (ctx->digital_lens == GF_LENS_GOPRO_WARP) for (int i = 0; i < 16; ++i) if (!(std::isfinite(p->digital_lens_params[i]) && fabsf(p->digital_lens_params[i]) <= 0x1p40f)) wild = true;
         if (wild) f |= F_WILD;
     }
     A.feat = f;
@@ -442,6 +447,8 @@ GF_API void gf_cuda_destroy(gf_cuda_ctx* ctx) {
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     if (ctx->d_vflags) cudaFree(ctx->d_vflags);
     if (ctx->d_const_flags) cudaFree(ctx->d_const_flags);
+    for (uint8_t* q : ctx->d_plane_src) if (q) cudaFree(q);
+    for (uint8_t* q : ctx->d_plane_dst) if (q) cudaFree(q);
     if (ctx->h_drawing) cudaFreeHost(ctx->h_drawing);
     if (ctx->d_drawing) cudaFree(ctx->d_drawing);
     if (ctx->d_src_ovl) cudaFree(ctx->d_src_ovl);
@@ -574,7 +581,9 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
         if ((p->flags & GF_FLAG_DRAWING_ENABLED) && drawing && drawing_len) {
             if (drawing_len > ctx->drawing_cap) {
                 CK(cudaStreamSynchronize(st));
-                if (ctx->h_drawing) cudaFreeHost(ctx->h_drawing);
+                for (uint8_t* q : ctx->d_plane_src) if (q) cudaFree(q);
+    for (uint8_t* q : ctx->d_plane_dst) if (q) cudaFree(q);
+    if (ctx->h_drawing) cudaFreeHost(ctx->h_drawing);
                 if (ctx->d_drawing) cudaFree(ctx->d_drawing);
                 ctx->h_drawing = nullptr; ctx->d_drawing = nullptr; ctx->drawing_cap = 0;
                 CK(cudaMallocHost(&ctx->h_drawing, drawing_len));
@@ -657,7 +666,9 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
             x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
             CK(cudaGetLastError());
             A.flt.tail = 1;                                            // the deferred pairs, exact pre-pass; also re-arms the other counter
-            x2<<<dim3(148 * 2, 1), block2, 0, st>>>(A);
+            // one thread per deferred pair for up to 2 % of a 4K frame's pairs in a single wave of tiny blocks (idle blocks exit at once);
+            // more entries than threads are covered by the grid-stride loop
+            x2<<<dim3(148 * 16, 1), block2, 0, st>>>(A);
             ctx->launches++;
         } else {
             x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
@@ -899,6 +910,45 @@ GF_API int gf_cuda_undistort_planes_dev_flagged(gf_cuda_ctx* ctx, size_t n_plane
         int rc = run_warp(ctx, &in[i], &out[i], &params[i], matrices_dev, matrix_rows, mesh_dev, mesh_len, true, cu_stream, true, 0, false, table_flags_dev);
         if (rc != GF_OK) return rc;
     }
+    return GF_OK;
+}
+
+// The planes of one frame in HOST memory — what the render path hands over for planar software frames (rendering/mod.rs:596-629:
+// every plane a BufferSource::Cpu slice): stage every plane to the device, render them like gf_cuda_undistort_planes_dev (one
+// coordinate pass shared by the planes of one geometry), copy every plane back, synchronise.  Host tables, like gf_cuda_undistort_image.
+GF_API int gf_cuda_undistort_planes(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                    const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
+                                    const float* mesh, size_t mesh_len, void* cu_stream) {
+    if (!ctx || !in || !out || !params || n_planes == 0) return fail(ctx, GF_ERR_BAD_PARAMS, "null argument");
+    for (size_t i = 0; i < n_planes; ++i) {
+        if (in[i].kind != GF_BUF_HOST || out[i].kind != GF_BUF_HOST) return fail(ctx, GF_ERR_BAD_PARAMS, "gf_cuda_undistort_planes takes HOST buffers (DEVICE: gf_cuda_undistort_planes_dev)");
+        int rc = validate(ctx, &params[i], &in[i], &out[i], ctx->bpp); if (rc != GF_OK) return rc;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : ctx->stream;
+    ctx->last_stream = st;
+    if (ctx->d_plane_src.size() < n_planes) { ctx->d_plane_src.resize(n_planes, nullptr); ctx->d_plane_dst.resize(n_planes, nullptr); ctx->d_plane_src_len.resize(n_planes, 0); ctx->d_plane_dst_len.resize(n_planes, 0); }
+    std::vector<gf_buffer_desc> din(in, in + n_planes), dout(out, out + n_planes);
+    for (size_t i = 0; i < n_planes; ++i) {
+        if (in[i].len > ctx->d_plane_src_len[i]) { if (ctx->d_plane_src[i]) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_plane_src[i]); ctx->d_plane_src[i] = nullptr; } CK(cudaMalloc(&ctx->d_plane_src[i], in[i].len)); ctx->d_plane_src_len[i] = in[i].len; }
+        if (out[i].len > ctx->d_plane_dst_len[i]) { if (ctx->d_plane_dst[i]) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_plane_dst[i]); ctx->d_plane_dst[i] = nullptr; } CK(cudaMalloc(&ctx->d_plane_dst[i], out[i].len)); ctx->d_plane_dst_len[i] = out[i].len; }
+        CK(cudaMemcpyAsync(ctx->d_plane_src[i], in[i].ptr, in[i].len, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_plane_dst[i], out[i].ptr, out[i].len, cudaMemcpyHostToDevice, st));   // untouched pixels keep their content, like on the CPU path
+        din[i].kind = GF_BUF_DEVICE; din[i].ptr = ctx->d_plane_src[i];
+        dout[i].kind = GF_BUF_DEVICE; dout[i].ptr = ctx->d_plane_dst[i];
+    }
+    const bool fuse = n_planes > 1 && ctx->fn_shade && planes_share_geometry(params, din.data(), dout.data(), n_planes);
+    if (fuse) {
+        int rc = run_warp(ctx, din.data(), dout.data(), params, matrices, matrix_rows, mesh, mesh_len, false, (void*)st, false, n_planes - 1);
+        if (rc != GF_OK) return rc;
+    } else {
+        for (size_t i = 0; i < n_planes; ++i) {
+            int rc = run_warp(ctx, &din[i], &dout[i], &params[i], matrices, matrix_rows, mesh, mesh_len, false, (void*)st, false);
+            if (rc != GF_OK) return rc;
+        }
+    }
+    for (size_t i = 0; i < n_planes; ++i) CK(cudaMemcpyAsync(out[i].ptr, ctx->d_plane_dst[i], out[i].len, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return GF_OK;
 }
 

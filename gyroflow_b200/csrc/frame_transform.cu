@@ -291,8 +291,8 @@ GF_API int gf_cuda_gyro_upload(gf_cuda_gyro** out, int device, const gf_compute_
               cudaMemcpy(g->d_org_ts, cp->org.ts_us, cp->org.n * sizeof(int64_t), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(g->d_org_q, cp->org.quats, cp->org.n * 4 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMalloc(&g->d_scratch, 2 * sizeof(unsigned)) == cudaSuccess &&
-              cudaMemset(g->d_scratch, 0, 2 * sizeof(unsigned)) == cudaSuccess;
+              cudaMalloc(&g->d_scratch, 2 * gf_cuda_gyro::kScratchPairs * sizeof(unsigned)) == cudaSuccess &&
+              cudaMemset(g->d_scratch, 0, 2 * gf_cuda_gyro::kScratchPairs * sizeof(unsigned)) == cudaSuccess;
     // multi-point sync offsets (offsets_adjusted) ride along with the tracks
     const SyncOffsets ho = host_offsets_of(cp);
     if (ok && ho.n > 0) {
@@ -363,7 +363,8 @@ GF_API int gf_cuda_frame_transform_dev_flagged(gf_cuda_gyro* g, const gf_compute
     C.org = Track{g->d_org_ts, g->d_org_q, g->n_org};
     C.offsets = SyncOffsets{ g->d_off_ts, g->d_off_ms, g->n_offsets, cp->gyro_offset_ms };
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
-    frame_rows_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(C, rows, matrices_dev, table_flags_dev, g->d_scratch);
+    unsigned* scratch = g->d_scratch + 2u * (g->next_scratch++ % gf_cuda_gyro::kScratchPairs);     // self-cleaning: the last block re-arms it
+    frame_rows_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(C, rows, matrices_dev, table_flags_dev, scratch);
     if (cudaGetLastError() != cudaSuccess) return GF_ERR_CUDA;
     if (!cu_stream && cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
     return GF_OK;

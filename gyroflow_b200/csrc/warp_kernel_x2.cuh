@@ -239,6 +239,60 @@ template <> struct Lens2<GF_LENS_INSTA360> {
     }
 };
 
+// gopro.rs:56-72 — angle from the radius (atan below tan(89 deg), the linear continuation above it goes to the exact code), then the
+// Newton inversion of POLY(p) = theta (:26-36) with per-lane stop masks: a lane stops updating at the step where the scalar loop
+// would `break` (|d| < 1e-12 before the update, |fix| < 1e-7 after it); the loop ends when both lanes have stopped or after 10 steps.
+template <> struct Lens2<GF_LENS_GOPRO> {
+    static constexpr bool kHas = true;
+    static GF_DEV f2 peval(f2 p, const float* k) {          // k0 + p (k1 + p (k2 + p (k3 + p (k4 + p (k5 + p k6)))))
+        using namespace p2;
+        f2 v = mul(p, bc(k[6]));
+        v = mul(p, add(bc(k[5]), v)); v = mul(p, add(bc(k[4]), v)); v = mul(p, add(bc(k[3]), v)); v = mul(p, add(bc(k[2]), v)); v = mul(p, add(bc(k[1]), v));
+        return add(bc(k[0]), v);
+    }
+    static GF_DEV f2 pderiv(f2 p, const float* k) {         // k1 + p (2 k2 + p (3 k3 + p (4 k4 + p (5 k5 + p (6 k6)))))
+        using namespace p2;
+        f2 v = mul(p, bc(6.0f * k[6]));
+        v = mul(p, add(bc(5.0f * k[5]), v)); v = mul(p, add(bc(4.0f * k[4]), v)); v = mul(p, add(bc(3.0f * k[3]), v)); v = mul(p, add(bc(2.0f * k[2]), v));
+        return add(bc(k[1]), v);
+    }
+    template <bool TRUSTED>
+    static GF_DEV void distort(f2 x, f2 y, f2 z, const gf_kernel_params& P, f2& ox, f2& oy, bool& bad) {
+        using namespace p2;
+        const float* k = P.k;
+        x = div_seq(x, z); y = div_seq(y, z);
+        const f2 a = add(mul(x, x), mul(y, y));
+        bad |= z_outside(z) | !in_window_r2(a.x) | !in_window_r2(a.y);          // r in [2^-28, 2^24): above the 1e-9 special case (:69)
+        const f2 r = sqrt_seq(a);
+        const float tt = 0x1.c9315ap+5f;                                        // tanf(1.5533f) = 57.149097...; == gf_tanf(1.5533f), asserted on the host (fill_uniforms)
+        bad |= !(r.x < tt) | !(r.y < tt);                                        // the continuation past ~89 degrees (:66): exact code
+        const f2 theta = atanf2_core(r, GF_ATAN_TAB);
+        // paraxial guess (theta - k0) / k1: k1 is frame-uniform and host-checked to be inside the division window
+        const f2 n0 = sub(theta, bc(k[0]));
+        bad |= !zero_or_in_window(n0.x) | !zero_or_in_window(n0.y);
+        f2 p = div_seq(n0, bc(k[1]));
+        bool da = false, db = false;
+        #pragma unroll 1
+        for (int i = 0; i < 10; ++i) {
+            const f2 d = pderiv(p, k);
+            da |= fabsf(d.x) < 1e-12f; db |= fabsf(d.y) < 1e-12f;               // `if d.abs() < 1e-12 { break; }`
+            if (da & db) break;
+            const f2 num = sub(peval(p, k), theta);
+            // a stopped lane keeps dividing harmlessly (its result is discarded); active lanes must be inside the division windows
+            bad |= (!da & (!in_window(d.x) | !zero_or_in_window(num.x))) | (!db & (!in_window(d.y) | !zero_or_in_window(num.y)));
+            const f2 fix = div_seq(num, mk(da ? 1.0f : d.x, db ? 1.0f : d.y));
+            const f2 np = sub(p, fix);
+            p = mk(da ? p.x : np.x, db ? p.y : np.y);
+            da |= fabsf(fix.x) < 1e-7f; db |= fabsf(fix.y) < 1e-7f;             // `if fix.abs() < 1e-7 { break; }` (after the update)
+            if (da & db) break;
+        }
+        const f2 rn = mul(bc(k[1]), p);
+        bad |= !zero_or_in_window(rn.x) | !zero_or_in_window(rn.y);
+        const f2 scale = div_seq(rn, r);
+        ox = mul(x, scale); oy = mul(y, scale);
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // packed digital lenses (the second, "digital" distortion of :216-220) for the pairs the fisheye model is compiled with
 // ------------------------------------------------------------------------------------------
@@ -312,6 +366,57 @@ struct ViewDigital2 {
             ppy = make_float2(da ? ppy.x : ny.x, db ? ppy.y : ny.y);
         }
         x = mul(add(ppx, bc(0.5f)), sw); y = mul(add(ppy, bc(0.5f)), sh);
+    }
+};
+// gopro_warp.rs:57-94 — the data-driven MAPX / MAPY warp of the `gopro` lens pair: 12-step fixed point towards (x * factor, y) from
+// the un-stretched start, per-lane stop masks, then the off-frame sentinel when the iteration did not land on the target.
+template <> struct Digital2<GF_LENS_GOPRO_WARP> {
+    static constexpr bool kHas = true;
+    static GF_DEV f2 clamp05(f2 v) { return make_float2(fminf(fmaxf(v.x, -0.5f), 0.5f), fminf(fmaxf(v.y, -0.5f), 0.5f)); }   // f32::clamp (NaN stays NaN: fmaxf(NaN, -0.5) = -0.5 differs, so NaN lanes are flagged below)
+    static GF_DEV void map(f2& ux, f2& uy, const float* q) {                       // gopro_map :22-41
+        using namespace p2;
+        const f2 x = clamp05(ux), y = clamp05(uy);
+        const f2 x2 = mul(x, x), y2 = mul(y, y);
+        f2 px = mul(x2, bc(q[6]));
+        px = mul(x2, add(bc(q[5]), px)); px = mul(x2, add(bc(q[4]), px)); px = mul(x2, add(bc(q[3]), px)); px = mul(x2, add(bc(q[2]), px)); px = mul(x2, add(bc(q[1]), px));
+        px = add(bc(q[0]), px);
+        const f2 nx = add(mul(x, add(px, mul(bc(q[7]), y2))), sub(ux, x));
+        // y * (p8 + p9 y2 + p10 y2 y2 + x2 (p11 + p12 y2 + p13 x2)) + (uy - y), sums left to right
+        const f2 inner = add(add(bc(q[11]), mul(bc(q[12]), y2)), mul(bc(q[13]), x2));
+        const f2 sy = add(add(add(bc(q[8]), mul(bc(q[9]), y2)), mul(mul(bc(q[10]), y2), y2)), mul(x2, inner));
+        const f2 ny = add(mul(y, sy), sub(uy, y));
+        ux = nx; uy = ny;
+    }
+    static GF_DEV void distort(f2& x, f2& y, const gf_kernel_params& P, bool& bad) {
+        using namespace p2;
+        const float* q = P.digital_lens_params;
+        const float factor = q[14] != 0.0f ? q[14] : 1.0f;
+        const f2 sw = bc((float)P.width), sh = bc((float)P.height);
+        bad |= !zero_or_in_window(x.x) | !zero_or_in_window(x.y) | !zero_or_in_window(y.x) | !zero_or_in_window(y.y);   // also NaN / Inf coordinates
+        x = sub(div_seq(x, sw), bc(0.5f)); y = sub(div_seq(y, sh), bc(0.5f));
+        const f2 tx = mul(x, bc(factor)), ty = y;
+        f2 ppx = x, ppy = y;
+        bool da = false, db = false;
+        #pragma unroll 1
+        for (int i = 0; i < 12; ++i) {
+            f2 dx = ppx, dy = ppy;
+            map(dx, dy, q);
+            dx = sub(dx, tx); dy = sub(dy, ty);
+            da |= (fabsf(dx.x) < 1e-6f) & (fabsf(dy.x) < 1e-6f);
+            db |= (fabsf(dx.y) < 1e-6f) & (fabsf(dy.y) < 1e-6f);
+            if (da & db) break;
+            const f2 nx = sub(ppx, dx), ny = sub(ppy, dy);
+            ppx = make_float2(da ? ppx.x : nx.x, db ? ppx.y : nx.y);
+            ppy = make_float2(da ? ppy.x : ny.x, db ? ppy.y : ny.y);
+        }
+        f2 rx = ppx, ry = ppy;
+        map(rx, ry, q);
+        const f2 ex = sub(rx, tx), ey = sub(ry, ty);
+        const bool offa = (fabsf(ex.x) > 0.02f) | (fabsf(ey.x) > 0.02f), offb = (fabsf(ex.y) > 0.02f) | (fabsf(ey.y) > 0.02f);
+        bad |= (ppx.x != ppx.x) | (ppx.y != ppx.y) | (ppy.x != ppy.x) | (ppy.y != ppy.y);       // NaN: clamp semantics differ, exact code decides
+        const f2 fx = mul(add(ppx, bc(0.5f)), sw), fy = mul(add(ppy, bc(0.5f)), sh);
+        x = make_float2(offa ? -99999.0f : fx.x, offb ? -99999.0f : fx.y);
+        y = make_float2(offa ? -99999.0f : fy.x, offb ? -99999.0f : fy.y);
     }
 };
 template <> struct Digital2<GF_LENS_GOPRO_SUPERVIEW>  : ViewDigital2<Superview2, 1>  {};

@@ -264,6 +264,13 @@ GF_API int         gf_cuda_undistort_planes_dev(gf_cuda_ctx* ctx, size_t n_plane
                                                 const gf_kernel_params* params, const float* matrices_dev, size_t matrix_rows,
                                                 const float* mesh_dev, size_t mesh_len, void* cu_stream);
 
+/* The same for planes in HOST memory with host tables — what the render path hands over for planar software frames
+ * (rendering/mod.rs:596-629: every plane a BufferSource::Cpu slice): every plane is staged to the device, the planes are rendered as
+ * above (one coordinate pass when they share a geometry), every plane is copied back; synchronous like gf_cuda_undistort_image. */
+GF_API int         gf_cuda_undistort_planes(gf_cuda_ctx* ctx, size_t n_planes, const gf_buffer_desc* in, const gf_buffer_desc* out,
+                                            const gf_kernel_params* params, const float* matrices, size_t matrix_rows,
+                                            const float* mesh, size_t mesh_len, void* cu_stream);
+
 /* Table trust for DEVICE-resident tables.  The packed kernel has a fast path that assumes every matrix entry is zero or of
  * moderate magnitude (2^-40..2^40) and that no row carries IBIS data; otherwise it keeps per-pixel guards.  Which path runs is
  * decided ON THE DEVICE from a verdict word that travels with the table (0 = tame and IBIS-free), read by the kernel at entry and

@@ -108,8 +108,9 @@ def test_kernel_variant_planning_host_logic():
     for lens in ("opencv_standard", "poly3", "poly5", "ptlens", "insta360", "sony", "generic_polynomial"):
         assert _plan(dict(base, lens=lens)) == 3, lens
         assert _plan(dict(base, lens=lens, digital="digital_stretch")) == 3, lens
-    assert _plan(dict(base, lens="gopro")) == 1                         # no packed form: scalar lean kernel
-    assert _plan(dict(base, lens="gopro", digital="gopro_warp")) == 1
+    assert _plan(dict(base, lens="gopro")) == 3                         # packed since round 2 (Newton inversion with per-lane stop masks)
+    assert _plan(dict(base, lens="gopro", digital="gopro_warp")) == 3
+    assert _plan(dict(base, lens="gopro", params=dict(k=[0.0, 1e-30, 0.0, 0.0, 0.0, 0.0, 0.0] + [0.0] * 5))) == 1     # k1 outside the division window: scalar lean kernel
     for d in ("gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch"):
         assert _plan(dict(base, digital=d, pix="Luma16")) == 3, d
     # rare per-frame features -> general kernel
@@ -125,7 +126,7 @@ def test_kernel_variant_planning_host_logic():
     # byte-aligned-only buffers (odd stride) cannot use whole-pixel vector access -> general kernel
     assert _plan(dict(w=203, h=117, pix="RGBA8", stride_pad=3)) == 0
     # every resampler but bilinear, and multi-plane frames: two-pass; EWA's probe passes are scalar
-    assert _plan(dict(base, interp="Lanczos4")) == 0x13 and _plan(dict(base, interp="Bicubic", lens="gopro")) == 0x11
+    assert _plan(dict(base, interp="Lanczos4")) == 0x13 and _plan(dict(base, interp="Bicubic", lens="gopro")) == 0x13
     assert _plan(dict(base, interp="EWA: Mitchell")) == 0x11
     assert _plan(dict(base, pix="R32f"), n_planes=4) == 0x13
     # validation errors come back as the reference's error classes

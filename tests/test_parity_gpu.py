@@ -251,6 +251,30 @@ def test_fused_planes_options():
     _assert_planes(dict(w=320, h=180, pix="Luma8"), 2, fused=False, vary=diff)
 
 
+def test_host_planes_entry_point():
+    """gf_cuda_undistort_planes: the planes of a frame as HOST slices (what rendering/mod.rs:596-629 hands over) — staged, fused where the
+    geometry is shared, copied back; bytes equal to per-plane oracle runs, untouched stride padding preserved."""
+    for case, n in ((dict(w=320, h=180, pix="R32f", lens="sony", ibis=True, mesh=True), 4),
+                    (dict(w=320, h=180, pix="Luma16", digital="gopro_superview", in_size=(160, 180), in_rect=(0, 0, 160, 180), out_size=(160, 180), out_rect=(0, 0, 160, 180)), 2),
+                    (dict(w=203, h=117, pix="Luma8", stride_pad=5), 3)):
+        built = [cases.build(dict(case, frame=i)) for i in range(n)]
+        p0, _, m, mesh, dst0, pix, lens, digital = built[0]
+        params, bufs, gots, wants = [], [], [], []
+        bw, bh = case.get("in_size", (case["w"], case["h"])); obw, obh = case.get("out_size", (case["w"], case["h"]))
+        for i, (p, src, _, _, d0, _, _, _) in enumerate(built):
+            p = p.copy(); p.plane_index = i
+            want = d0.copy()
+            assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+            got = d0.copy()
+            bufs.append(g.Buffers(g.BufferDescription((bw, bh, p.stride), src), g.BufferDescription((obw, obh, p.output_stride), got)))
+            params.append(p); gots.append(got); wants.append(want)
+        w = g.CudaWrapper.new(params[0], pix, lens, digital, bufs[0])
+        w.undistort_planes(bufs, params, g.FrameTransform(matrices=m, kernel_params=params[0], mesh_data=mesh if mesh is not None else np.zeros(0, np.float32)))
+        w.close()
+        for i in range(n):
+            assert np.array_equal(gots[i], wants[i]), (case, i)
+
+
 # ---- higher-order resamplers (SURVEY f1): bicubic, Lanczos4 (the default render setting), EWA CubicBC ------------------
 @pytest.mark.parametrize("interp", ["Bicubic", "Lanczos4"])
 def test_bicubic_and_lanczos4(interp):
@@ -474,6 +498,24 @@ def test_packed_kernel_other_lens_models(lens):
     if lens == "opencv_standard":      # denominators of the rational term crossing zero / huge coefficients
         assert_bit_exact(dict(w=640, h=360, lens=lens, fov=2.0, params=dict(k=[0.1, 0.01, 0.001, 0.001, 0.0, -3.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0])))
         assert_bit_exact(dict(w=640, h=360, lens=lens, params=dict(k=[1e20, 0.0, 0.0, 0.0, 0.0, 1e20, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])))
+
+
+def test_packed_kernel_gopro_pair():
+    """The packed forms of `gopro` (Newton POLY inversion with per-lane stop masks) and of its `gopro_warp` digital lens (12-step fixed
+    point + off-frame sentinel): ordinary frames, every pixel layout family, rays past the 89-degree continuation, wild tables, odd k."""
+    for digital in (None, "gopro_warp"):
+        for pix in ("RGBA8", "Luma8", "UV16", "RGBAf", "RGB8"):
+            assert_bit_exact(dict(w=640, h=360, lens="gopro", digital=digital, pix=pix))
+        assert_bit_exact(dict(w=1280, h=720, lens="gopro", digital=digital, ts=2222.0, readout=33.0))
+        assert_bit_exact(dict(w=640, h=360, lens="gopro", digital=digital, rs=False))
+        assert_bit_exact(dict(w=640, h=360, lens="gopro", digital=digital, fov=3.0))                 # invalid (w <= 0) regions, rays past 89 degrees, off-frame sentinel
+        assert_bit_exact(dict(w=640, h=360, lens="gopro", digital=digital, fov=0.5))
+        for kind in ("nan_row", "huge", "zero_w", "on_axis", "ibis_some"):
+            assert_bit_exact(dict(w=320, h=180, lens="gopro", digital=digital, matrix_hook=_wild(kind)))
+    assert_bit_exact(dict(w=640, h=360, lens="gopro", params=dict(k=[0.0, 1.15, 0.3, -0.5, 0.9, 0.0, 0.0] + [0.0] * 5)))     # a POLY whose derivative changes sign in range
+    assert_bit_exact(dict(w=640, h=360, lens="gopro", params=dict(k=[0.01, -1.15, 0.01, 0.12, -0.03, 0.02, 0.005] + [0.0] * 5)))
+    assert_bit_exact(dict(w=640, h=360, lens="gopro", params=dict(k=[0.0, 1e-30, 0.0, 0.0, 0.0, 0.0, 0.0] + [0.0] * 5)))
+    assert_bit_exact(dict(w=640, h=360, lens="gopro", digital="gopro_warp", params=dict(digital_lens_params=[1.55, -3.0, 9.0, -20.0, 30.0, -25.0, 9.0, 0.2, 1.0, 0.3, -0.5, -0.3, 0.9, 0.3, 1.5556, 0.0])))
 
 
 def test_packed_kernel_unusual_params():
