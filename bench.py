@@ -300,10 +300,16 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
     fps_value = world * FRAMES_PER_STEP / (ms_per_step / 1e3)
 
     # ---- verification pass (untimed): a few frames of the same job with device-side checksums, gathered in frame order -------------
-    qv = g.RenderQueue(cp, st, LENS, None, dbufs[0].input, dbufs[0].output, device=local, depth=2, pin_numa=False, checksum=True)
+    # inputs with a rank-independent seed (rank 0 re-renders them on the CPU below), one input / output buffer per frame in flight
+    vgen = torch.Generator(device=dev); vgen.manual_seed(999)
+    vin = [torch.randint(0, 256, (H, p.stride), dtype=torch.uint8, device=dev, generator=vgen) for _ in range(2)]
+    vout = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(2)]
+    vbufs = [g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
+                       g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel())) for a, b in zip(vin, vout)]
+    qv = g.RenderQueue(cp, st, LENS, None, vbufs[0].input, vbufs[0].output, device=local, depth=2, pin_numa=False, checksum=True)
     n_check = 8
     mine = render_queue.shard_frames(n_check, world, rank)
-    sums = qv.render(mine, ts_of, lambda f: dbufs[(f // world) % RING]) if mine else {}    # distinct buffers for the frames in flight
+    sums = qv.render(mine, ts_of, lambda f: vbufs[(f // world) % 2]) if mine else {}
     qv.close()
     if world > 1: sums = render_queue.gather_results(sums, dist, torch, dev)
 
@@ -411,10 +417,10 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
             cores = oracle_lib.load().gf_oracle_online_cpus()
             # 4 full 4K frames of this job on the host cores: timed (cpu_baseline) AND compared with the pipeline's per-frame checksums
             tab = torch.zeros((rows, 14), dtype=torch.float32, device=dev)
-            src = frames_in[0].cpu().numpy()
             dst = np.zeros((H, p.output_stride), np.uint8)
             checked, cpu_t = [], 0.0
             for f in range(min(4, n_check)):
+                src = vin[(f // world) % 2].cpu().numpy()                    # the input the verification pass rendered frame f from (same on every rank)
                 kp, r = dg.frame_transform(ts_of(f), tab.data_ptr(), rows, frame=f)
                 kp = g.get_frame_transform_at(st, cp, dbufs[0], kp)
                 m = tab.cpu().numpy()

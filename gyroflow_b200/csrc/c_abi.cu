@@ -668,7 +668,17 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
             A.flt.tail = 1;                                            // the deferred pairs, exact pre-pass; also re-arms the other counter
             // one thread per deferred pair for up to 2 % of a 4K frame's pairs in a single wave of tiny blocks (idle blocks exit at once);
             // more entries than threads are covered by the grid-stride loop
-            x2<<<dim3(148 * 16, 1), block2, 0, st>>>(A);
+            // programmatic dependent launch: the tail grid is scheduled while the main grid drains and waits at griddepcontrol.wait,
+            // which hides the kernel-to-kernel launch gap (the tail is ~2 % of the frame's work)
+            {
+                cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(148 * 16, 1); cfg.blockDim = block2; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                void* kargs[1] = { (void*)&A };
+                CK(cudaLaunchKernelExC(&cfg, (const void*)x2, kargs));
+            }
             ctx->launches++;
         } else {
             x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;

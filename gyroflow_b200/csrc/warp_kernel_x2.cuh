@@ -714,6 +714,7 @@ warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     constexpr bool kFilter = LensApprox<LENS>::value && DIGITAL == GF_LENS_NONE;
     const bool trusted = __ldg(A.table_flags) == 0u;
     if constexpr (kFilter) if (A.flt.tail) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");           // launched with programmatic stream serialization: wait for the main grid
         const unsigned tid = (blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
         if (tid == 0u) *A.flt.count_next = 0u;                       // re-arm the counter the NEXT frame's main launch will use
         if (!trusted) return;                                         // the main launch deferred nothing on the guarded path
