@@ -2,8 +2,9 @@
 (Python scalars of numpy.float32) than the C oracle, to cross-check it: every physical lens model (opencv_fisheye,
 opencv_standard, poly3, poly5, ptlens, insta360, sony, generic_polynomial, gopro), every digital lens (gopro_superview,
 gopro6_superview, gopro_hyperview, gopro_warp, digital_stretch), vertical rolling shutter, bilinear / bicubic / Lanczos4
-sampling, background mode 0, on 8-bit, 16-bit and f32 pixels (cpu_undistort.rs:133-167 + :216-220, :421-517 without the
-optional branches, :370-418, :519-633; distortion_models/*.rs distort_point; util.rs:144-147; pixel_formats.rs conversions).
+sampling, background modes 0-2, r_limit, light refraction, IBIS / OIS rows, input rotation and stretch, horizontal rolling shutter,
+on 8-bit, 16-bit and f32 pixels (cpu_undistort.rs:133-228 without the mesh block, :421-517 without the lens-correction blend,
+:370-418, :519-633; distortion_models/*.rs distort_point; util.rs:144-147; pixel_formats.rs conversions).
 With it every lens formula of the oracle has two independent transcriptions.
 
 TEST INFRASTRUCTURE ONLY.  numpy.float32 arithmetic is IEEE single precision without contraction; atan goes to the same
@@ -22,10 +23,22 @@ _libm.sqrtf.restype = ctypes.c_float
 _libm.sqrtf.argtypes = [ctypes.c_float]
 _libm.tanf.restype = ctypes.c_float
 _libm.tanf.argtypes = [ctypes.c_float]
+_libm.sinf.restype = ctypes.c_float
+_libm.sinf.argtypes = [ctypes.c_float]
+_libm.cosf.restype = ctypes.c_float
+_libm.cosf.argtypes = [ctypes.c_float]
 
 
 def atanf(x):
     return F(_libm.atanf(float(x)))
+
+
+def sinf(x):
+    return F(_libm.sinf(float(x)))
+
+
+def cosf(x):
+    return F(_libm.cosf(float(x)))
 
 
 def tanf(x):
@@ -243,7 +256,7 @@ DIGITAL = {"gopro_superview": _view_distort(_superview, 1.333333333), "gopro6_su
            "gopro_hyperview": _view_distort(_hyperview, 1.555555555), "gopro_warp": gopro_warp_distort, "digital_stretch": digital_stretch_distort}
 
 
-def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:133-167, :216-220 (no r_limit / refraction / IBIS / mesh)
+def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:133-228 without the mesh / focal-plane block
     row = m[idx]
     t3 = [F(v) for v in p.translation3d]
     _x = (px * row[0]) + (py * row[1]) + row[2] + t3[0]
@@ -251,30 +264,71 @@ def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None): 
     _w = (px * row[6]) + (py * row[7]) + row[8] + t3[2]
     if not (_w > F(0.0)):
         return None
+    r_limit_sq = F(p.r_limit) * F(p.r_limit)                 # :521
+    if r_limit_sq > 0 and (_x * _x + _y * _y) > r_limit_sq * _w:          # :139 (sic: * _w)
+        return None
+    lrc = F(p.light_refraction_coefficient)
+    if lrc != F(1.0) and lrc > 0:                            # :143-152
+        if _w != 0:
+            r = sqrtf(_x * _x + _y * _y) / _w
+            sin_theta_d = (r / sqrtf(F(1.0) + r * r)) * lrc
+            r_d = sin_theta_d / sqrtf(F(1.0) - sin_theta_d * sin_theta_d)
+            if r_d != 0:
+                _w = _w * (r / r_d)
     k = [F(v) for v in p.k]
     ux, uy = DISTORT[lens](_x, _y, _w, k)
     ux = ux * F(p.f[0]); uy = uy * F(p.f[1])
+    if any(row[i] != 0 for i in range(9, 14)):               # IBIS / OIS row :157-165
+        ang = row[11]
+        cos_a = cosf(-ang); sin_a = sinf(-ang)
+        ux, uy = (cos_a * ux - sin_a * uy - row[9] + row[12], sin_a * ux + cos_a * uy - row[10] + row[13])
     ux = ux + F(p.c[0]); uy = uy + F(p.c[1])
     if digital is not None and (p.flags & 2) == 2:           # :216-220
         ux, uy = DIGITAL[digital](ux, uy, p)
+    if F(p.input_horizontal_stretch) > F(0.001): ux = ux / F(p.input_horizontal_stretch)      # :222-223
+    if F(p.input_vertical_stretch) > F(0.001): uy = uy / F(p.input_vertical_stretch)
     return ux, uy
 
 
-def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:421-517, the branches the north-star config takes
+def rotate_point(px, py, angle, ox, oy, o2x, o2y):           # cpu_undistort.rs:262-265
+    return (cosf(angle) * (px - ox) - sinf(angle) * (py - oy) + o2x, sinf(angle) * (px - ox) + cosf(angle) * (py - oy) + o2y)
+
+
+def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:421-517 without the lens-correction blend (:429-460)
     ox = map_coord(x, p.output_rect[0], p.output_rect[0] + p.output_rect[2], 0.0, p.output_width)
     oy = map_coord(y, p.output_rect[1], p.output_rect[1] + p.output_rect[3], 0.0, p.output_height)
     ox = ox + F(p.translation2d[0]); oy = oy + F(p.translation2d[1])
-    sy = max(min(as_i32(round_half_away(oy)), p.height), 0)
+    hrs = (p.flags & 16) == 16
+    sy = max(min(as_i32(round_half_away(ox)), p.width), 0) if hrs else max(min(as_i32(round_half_away(oy)), p.height), 0)
     if p.matrix_count > 1:
         pt = rotate_and_distort(ox, oy, p.matrix_count // 2, p, m, lens, digital)
         if pt is not None:
-            sy = max(min(as_i32(round_half_away(pt[1])), p.height), 0)
+            sy = max(min(as_i32(round_half_away(pt[0])), p.width), 0) if hrs else max(min(as_i32(round_half_away(pt[1])), p.height), 0)
     idx = min(sy, p.matrix_count - 1)
     uv = rotate_and_distort(ox, oy, idx, p, m, lens, digital)
     if uv is None:
         return None
-    u = map_coord(uv[0], 0.0, p.width, p.source_rect[0], p.source_rect[0] + p.source_rect[2])
-    v = map_coord(uv[1], 0.0, p.height, p.source_rect[1], p.source_rect[1] + p.source_rect[3])
+    u, v = uv
+    fw, fh = F(p.width), F(p.height)
+    if F(p.input_rotation) != 0:                             # :485-491
+        rotation = F(p.input_rotation) * (F(math.pi) / F(180.0))
+        sw, sh = fw, fh
+        fw, fh = rotate_point(sw, sh, rotation, F(0.0), F(0.0), F(0.0), F(0.0))
+        fw, fh = round_half_away(abs(fw)), round_half_away(abs(fh))
+        u, v = rotate_point(u, v, rotation, sw / F(2.0), sh / F(2.0), fw / F(2.0), fh / F(2.0))
+    width_f, height_f = F(p.width), F(p.height)
+    if p.background_mode == 1:                               # edge repeat :495-499
+        u = min(max(u, F(3.0)), width_f - F(3.0)); v = min(max(v, F(3.0)), height_f - F(3.0))
+    elif p.background_mode == 2:                             # edge mirror :500-509
+        rx, ry = round_half_away(u), round_half_away(v)
+        width3, height3 = width_f - F(3.0), height_f - F(3.0)
+        if rx > width3: u = width3 - (rx - width3)
+        if rx < F(3.0): u = F(3.0) + width_f - (width3 + rx)
+        if ry > height3: v = height3 - (ry - height3)
+        if ry < F(3.0): v = F(3.0) + height_f - (height3 + ry)
+    if p.background_mode != 3:                               # :510-515
+        u = map_coord(u, 0.0, fw, p.source_rect[0], p.source_rect[0] + p.source_rect[2])
+        v = map_coord(v, 0.0, fh, p.source_rect[1], p.source_rect[1] + p.source_rect[3])
     return u, v
 
 

@@ -197,6 +197,13 @@ def test_independent_numpy_restatement_remaining_models_and_resamplers():
         (dict(w=72, h=40, digital="gopro_hyperview", pix="Luma16", fov=1.2), np.uint16), (dict(w=72, h=40, lens="poly5", digital="digital_stretch"), np.uint8),
         (dict(w=64, h=36, interp="Bicubic"), np.uint8), (dict(w=64, h=36, interp="Lanczos4", fov=1.8, params=dict(background=[0.2, 0.4, 0.6, 1.0])), np.uint8),
         (dict(w=48, h=28, interp="Lanczos4", pix="RGBAf", lens="sony"), np.float32), (dict(w=48, h=28, interp="Bicubic", pix="UV16", lens="insta360"), np.uint16),
+        # optional stages of rotate_and_distort / undistort_coord
+        (dict(w=72, h=40, ibis=True), np.uint8), (dict(w=72, h=40, ibis=True, lens="sony", pix="R32f"), np.float32),
+        (dict(w=72, h=40, fov=2.5, params=dict(r_limit=0.9)), np.uint8), (dict(w=72, h=40, params=dict(light_refraction_coefficient=1.33)), np.uint8),
+        (dict(w=72, h=40, params=dict(input_rotation=90.0)), np.uint8), (dict(w=72, h=40, params=dict(input_rotation=-13.5, background_mode=2)), np.uint8),
+        (dict(w=72, h=40, fov=1.6, params=dict(background_mode=1, background=[0.1, 0.4, 0.7, 1.0])), np.uint8),
+        (dict(w=72, h=40, horizontal_rs=True), np.uint8), (dict(w=72, h=40, params=dict(input_horizontal_stretch=1.3333, input_vertical_stretch=0.9, translation2d=[4.5, -3.25])), np.uint8),
+        (dict(w=72, h=40, video_rotation=25.0, pix="Luma16"), np.uint16),
     ]
     for c, sdt in todo:
         p, src, m, mesh, dst0, pix, lens, digital = cases.build(c)
