@@ -51,8 +51,8 @@ CONFIGS = {
 CFG = CONFIGS[2]
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed `ncu --set full` captures
 # (ncu flushes the caches before the launch and the output stays in L2 after it, hence traffic < algorithmic bytes)
-NCU_TRAFFIC = {(2, "Bilinear"): 23118848 + 640256}
-NCU_TRAFFIC_SOURCE = "profiles/r01l_x2_final_fisheye_rgba8_summary.txt"
+NCU_TRAFFIC = {(2, "Bilinear"): 23568896 + 1131264}
+NCU_TRAFFIC_SOURCE = "profiles/r02h_x2_filtered_fisheye_rgba8_summary.txt"
 INTERP = "Bilinear"          # BASELINE configs are bilinear; --interp measures the other resamplers (side measurement, not the headline)
 W, H = CFG["w"], CFG["h"]
 PIX, LENS = CFG["pix"], CFG["lens"]
@@ -260,7 +260,7 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
     frames_out = [torch.zeros((H, p.output_stride), dtype=torch.uint8, device=dev) for _ in range(RING)]
     dbufs = [g.Buffers(g.BufferDescription((W, H, p.stride), a.data_ptr(), length=a.numel()),
                        g.BufferDescription((W, H, p.output_stride), b.data_ptr(), length=b.numel())) for a, b in zip(frames_in, frames_out)]
-    DEPTH_DEV = 4
+    DEPTH_DEV = max(1, min(args.depth, RING))          # frames in flight on the device-resident path (distinct ring buffers)
     q = g.RenderQueue(cp, st, LENS, None, dbufs[0].input, dbufs[0].output, device=local, depth=DEPTH_DEV, pin_numa=True, checksum=False)
     tstream = torch.cuda.Stream(device=dev)
 
@@ -471,6 +471,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=5, help="frames in flight on the host-buffer path")
+    ap.add_argument("--depth", type=int, default=4, help="frames in flight on the device-resident path (<= 8)")
     ap.add_argument("--legacy", action="store_true", help="round-1 measurement shape (recycled precomputed tables) for the default config too")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--lens", default=None, help="override the config's lens model (side measurement), e.g. sony, opencv_standard")

@@ -646,6 +646,18 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
     const int variant = select_variant(ctx->fn_lean != nullptr, has_packed, ctx->digital_lens, A, table_flags, two_pass, n_maps) & 0xf;
     const bool lean_ok = variant != PLAN_GENERAL;
     KernelFn x2 = (variant == PLAN_PACKED_TRUSTED || variant == PLAN_PACKED) ? (two_pass ? ctx->fn_x2c : ctx->fn_x2) : nullptr;
+    // Packed-kernel launches use programmatic stream serialization: the grid may be scheduled while the previous kernel on the stream
+    // (the frame's producer kernel, the previous frame's tail, ...) is still draining; every CTA executes griddepcontrol.wait before it
+    // touches memory, so the dependency itself is unchanged and only the kernel-to-kernel launch gap disappears.
+    auto launch_pdl = [&](KernelFn fn, dim3 g, dim3 b, const WarpArgs& args) -> cudaError_t {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = st;      // 0 bytes: f32x2.cuh's opaque zero depends on it
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        void* kargs[1] = { (void*)&args };
+        return cudaLaunchKernelExC(&cfg, (const void*)fn, kargs);
+    };
     if (lean_ok && x2) {
         // 32 x 4 threads (4 x 8 output rows... 32 x 8 pixels) per block measured 2 % faster than 32 x 8 threads (finer tail); GF_X2_BLOCK_Y overrides
         const int by = ctx->x2_block_y;
@@ -666,25 +678,14 @@ static int run_warp(gf_cuda_ctx* ctx, const gf_buffer_desc* in, const gf_buffer_
             A.flt.q = ctx->d_defer_q; A.flt.cap = ctx->defer_cap;
             A.flt.count = ctx->d_defer_count + cur; A.flt.count_next = ctx->d_defer_count + (cur ^ 1u);
             A.flt.rho = 0x1p-17f; A.flt.a_cap = a_cap; A.flt.tail = 0;
-            x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
-            CK(cudaGetLastError());
+            CK(launch_pdl(x2, grid2, block2, A)); ctx->x2_launches++;
             A.flt.tail = 1;                                            // the deferred pairs, exact pre-pass; also re-arms the other counter
             // one thread per deferred pair for up to 2 % of a 4K frame's pairs in a single wave of tiny blocks (idle blocks exit at once);
             // more entries than threads are covered by the grid-stride loop
-            // programmatic dependent launch: the tail grid is scheduled while the main grid drains and waits at griddepcontrol.wait,
-            // which hides the kernel-to-kernel launch gap (the tail is ~2 % of the frame's work)
-            {
-                cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3(148 * 16, 1); cfg.blockDim = block2; cfg.dynamicSmemBytes = 0; cfg.stream = st;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                void* kargs[1] = { (void*)&A };
-                CK(cudaLaunchKernelExC(&cfg, (const void*)x2, kargs));
-            }
+            CK(launch_pdl(x2, dim3(148 * 16, 1), block2, A));
             ctx->launches++;
         } else {
-            x2<<<grid2, block2, 0, st>>>(A); ctx->x2_launches++;
+            CK(launch_pdl(x2, grid2, block2, A)); ctx->x2_launches++;
         }
     }
     else {

@@ -712,9 +712,11 @@ template <int LENS, int DIGITAL, class PIX, int MINB, bool COORD = false>
 __global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, MINB)
 warp_kernel_x2(const __grid_constant__ WarpArgs A) {
     constexpr bool kFilter = LensApprox<LENS>::value && DIGITAL == GF_LENS_NONE;
+    // launched with programmatic stream serialization (c_abi.cu: launch_pdl): nothing of the previous kernel on the stream — the matrix
+    // table and its verdict word, the deferred-pair queue and its counters, the previous frame's output — may be read or written before this
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool trusted = __ldg(A.table_flags) == 0u;
     if constexpr (kFilter) if (A.flt.tail) {
-        asm volatile("griddepcontrol.wait;" ::: "memory");           // launched with programmatic stream serialization: wait for the main grid
         const unsigned tid = (blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
         if (tid == 0u) *A.flt.count_next = 0u;                       // re-arm the counter the NEXT frame's main launch will use
         if (!trusted) return;                                         // the main launch deferred nothing on the guarded path
