@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgyroflow_cuda.so")
+LIB_PATH = os.environ.get("GF_CUDA_LIB") or os.path.join(_HERE, "libgyroflow_cuda.so")    # GF_CUDA_LIB: an alternative build (tuning experiments)
 
 MATRIX_STRIDE = 14
 MESH_MAX_LEN = 839

@@ -6,6 +6,10 @@
 #include <cstdlib>
 #include "warp_kernel_x2.cuh"
 
+#ifndef GF_X2_MINB
+#define GF_X2_MINB 6      // resident 256-thread blocks per SM the packed kernel is compiled for (register cap 65536 / (256 * MINB))
+#endif
+
 namespace gf {
 
 typedef void (*KernelFn)(const WarpArgs);
@@ -42,7 +46,7 @@ static KernelFn pick_x2(int interp) {
     // packed digital lenses: superview, superview6, hyperview (fisheye pairs) and digital_stretch (every packed lens model)
     if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas) {
         // 6 resident blocks per SM (40 registers): 5 (48 registers, no spills) measured the same, 4 slower, 7 / 8 compile to the 6 code
-        if (interp == GF_INTERP_BILINEAR) return warp_kernel_x2<LENS, DIGITAL, PIX, 6>;
+        if (interp == GF_INTERP_BILINEAR) return warp_kernel_x2<LENS, DIGITAL, PIX, GF_X2_MINB>;
     }
     return nullptr;
 }
@@ -50,7 +54,7 @@ template <int LENS, int DIGITAL, class PIX>
 static KernelFn pick_interp(int interp, int lean) {
     if (lean == 4) {
         if constexpr (Lens2<LENS>::kHas && Digital2<DIGITAL>::kHas)
-            return warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, 6, true>;
+            return warp_kernel_x2<LENS, DIGITAL, Pix<1, SC_U8>, GF_X2_MINB, true>;
         return nullptr;
     }
     if (lean == 2) return pick_x2<LENS, DIGITAL, PIX>(interp);
