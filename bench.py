@@ -390,8 +390,14 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
         t0 = time.perf_counter()
         for _ in range(16): hctx.undistort_image(pb, itm)
         pageable_fps = 16 / (time.perf_counter() - t0)
+        g.host_register(pin_a); g.host_register(pin_b)          # the same ordinary buffers, page-locked in place once (gf_cuda_host_register)
+        for _ in range(2): hctx.undistort_image(pb, itm)
+        t0 = time.perf_counter()
+        for _ in range(32): hctx.undistort_image(pb, itm)
+        registered_fps = 32 / (time.perf_counter() - t0)
+        g.host_unregister(pin_a); g.host_unregister(pin_b)
         hctx.close()
-        te = torch.tensor([e2e_dt, 1.0 / sync_fps, 1.0 / pageable_fps], dtype=torch.float64, device=dev)
+        te = torch.tensor([e2e_dt, 1.0 / sync_fps, 1.0 / pageable_fps, 1.0 / registered_fps], dtype=torch.float64, device=dev)
         if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_fps = world * e2e_frames / float(te[0].item())
         h2d_frame = int(hin[0].numel() + 368)                 # frame + KernelParams (kernel argument); the matrix table is produced on the device
@@ -401,9 +407,11 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
                "h2d_GBps_per_gpu": e2e_fps / world * h2d_frame / 1e9, "d2h_GBps_per_gpu": e2e_fps / world * d2h_frame / 1e9,
                "pipeline_depth": DEPTH, "numa_cpus_bound": t_pin,
                "sync_call_value": world / float(te[1].item()), "sync_call_pageable_value": world / float(te[2].item()),
+               "sync_call_registered_value": world / float(te[3].item()),
                "note": "value: gf_cuda_queue with page-locked HOST frames, %d in flight, per frame: on-device FrameTransform producer, H2D, warp, D2H (wall clock, %d frames); "
                        "sync_call_value: strictly sequential gf_cuda_undistort_image with host tables (what process_pixels does), pinned; "
-                       "sync_call_pageable_value: the same with ordinary pageable buffers (BufferSource::Cpu hands a plain &mut [u8])" % (DEPTH, e2e_frames)}
+                       "sync_call_pageable_value: the same with ordinary pageable buffers (BufferSource::Cpu hands a plain &mut [u8]); "
+                       "sync_call_registered_value: those ordinary buffers after gf_cuda_host_register (page-locked in place once)" % (DEPTH, e2e_frames)}
 
     if rank == 0:
         peaks = {}
@@ -452,7 +460,12 @@ def run_pipeline(args, torch, dist, g, rank, world, local, dev):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.config, INTERP)),
                          "traffic_source": NCU_TRAFFIC_SOURCE if (args.config, INTERP) in NCU_TRAFFIC else None,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": launch_ms, "peak_source": peak_src,
-                         "kernel": "warp_kernel_x2 (trusted path), timed alone on one stream with CUDA events: %d launches per step" % FRAMES_PER_STEP,
+                         # the read-only variant (input planes + tables; north_star says "HBM-read roofline") and the nominal 8 TB/s
+                         "read_only": {"bytes_per_launch": abytes - int(W * p.bytes_per_pixel * H), "achieved": (abytes - int(W * p.bytes_per_pixel * H)) / (launch_ms / 1e3) / 1e9,
+                                       "frac": (abytes - int(W * p.bytes_per_pixel * H)) / (launch_ms / 1e3) / 1e9 / peak},
+                         "frac_of_nominal_8000": achieved / 8000.0,
+                         "pipeline_achieved": abytes * fps_value / world / 1e9, "pipeline_frac": abytes * fps_value / world / 1e9 / peak,
+                         "kernel": "warp_kernel_x2 (trusted path, filtered pre-pass: main + tail launch), timed alone on one stream with CUDA events: %d frames per step" % FRAMES_PER_STEP,
                          "note": "kernel is FP32-issue bound in bit-exact (-fmad=false) mode, not HBM bound; traffic is the DRAM bytes of ONE cold launch under ncu (output stays in L2), not a steady-state figure; see DESIGN.md"},
             "cpu_baseline": cpu,
         }

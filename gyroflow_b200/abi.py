@@ -202,6 +202,8 @@ EXPORTS = [
     ("gf_cuda_queue_last_error", C.c_char_p, [C.c_void_p]),
     ("gf_cuda_bind_thread_to_device", C.c_int, [C.c_int]),
     ("gf_cuda_checksum_dev", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("gf_cuda_host_register", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("gf_cuda_host_unregister", C.c_int, [C.c_void_p]),
 ]
 
 _lib = None

@@ -398,6 +398,19 @@ def bind_thread_to_device(device: int) -> int:
     return int(abi.load_library().gf_cuda_bind_thread_to_device(device))
 
 
+def host_register(arr: np.ndarray):
+    """Page-lock a host array in place (gf_cuda_host_register); pair with host_unregister before the array is freed."""
+    rc = abi.load_library().gf_cuda_host_register(arr.ctypes.data, arr.nbytes)
+    if rc != 0:
+        raise GyroflowCoreError(rc, "gf_cuda_host_register")
+
+
+def host_unregister(arr: np.ndarray):
+    rc = abi.load_library().gf_cuda_host_unregister(arr.ctypes.data)
+    if rc != 0:
+        raise GyroflowCoreError(rc, "gf_cuda_host_unregister")
+
+
 def stab_config(params: abi.KernelParams, pixel_type: str, digital_lens=None, base_flags=0, background=(0.0, 0.0, 0.0, 0.0),
                 canvas_scale=1.0, show_safe_area=False, adaptive_zoom_window=0.0):
     """gf_stab_config from the per-buffer half of a KernelParams (what `Stabilization` holds: size, output_size, interpolation, ...)."""

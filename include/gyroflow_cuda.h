@@ -500,6 +500,11 @@ GF_API const char* gf_cuda_queue_last_error(gf_cuda_queue* q);
  * page-locked staging allocated afterwards — by this library or by the caller — is node-local and the copy threads do not cross
  * the socket interconnect.  Returns the number of CPUs in the mask, 0 if the topology is unknown (nothing changed), < 0 on error. */
 GF_API int      gf_cuda_bind_thread_to_device(int device);
+/* Page-lock an existing host allocation (a decoder frame pool, a long-lived Vec<u8> — what BufferSource::Cpu borrows from) so that
+ * HOST-buffer calls copy at the link's rate instead of through the driver's bounce buffers.  cudaHostRegister / cudaHostUnregister;
+ * the caller owns the lifetime: unregister before freeing.  Registering twice is not an error. */
+GF_API int      gf_cuda_host_register(void* ptr, size_t len);
+GF_API int      gf_cuda_host_unregister(void* ptr);
 /* sum(word[i] * (2 i + 1)) mod 2^64 over len / 4 words of device memory, accumulated into *out_dev (zeroed first), on `cu_stream` */
 GF_API int      gf_cuda_checksum_dev(const void* ptr_dev, size_t len, uint64_t* out_dev, void* cu_stream);
 

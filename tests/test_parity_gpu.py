@@ -305,6 +305,21 @@ def test_device_buffers_cuda_buffer_source():
     assert_bit_exact(dict(w=203, h=117, pix="RGB8", stride_pad=3), device_buffers=True)
 
 
+def test_host_register_in_place():
+    """gf_cuda_host_register: an ordinary host array page-locked in place renders the same bytes; double registration is not an error."""
+    p, src, m, mesh, dst0, pix, lens, digital = cases.build(dict(w=640, h=360))
+    want = dst0.copy()
+    assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+    got = dst0.copy()
+    g.host_register(src); g.host_register(got); g.host_register(got)
+    bufs = g.Buffers(g.BufferDescription((640, 360, p.stride), src), g.BufferDescription((640, 360, p.output_stride), got))
+    w = g.CudaWrapper.new(p, pix, lens, digital, bufs)
+    w.undistort_image(bufs, g.FrameTransform(matrices=m, kernel_params=p))
+    w.close()
+    g.host_unregister(src); g.host_unregister(got)
+    assert np.array_equal(got, want)
+
+
 # ---- full BASELINE sizes ---------------------------------------------------------------------------------
 def test_full_size_cfg2_4k_rgba8():
     assert_bit_exact(dict(w=3840, h=2160))

@@ -99,6 +99,33 @@ def test_queue_host_buffers_pipelined(pix, lens, digital, extra):
     dg.close()
 
 
+def test_thousand_frame_job_cfg5_shape():
+    """BASELINE config 5's shape at a reduced frame size: 1000 frames with distinct timestamps through one queue, 6 in flight, results in
+    frame order; every 40th frame against the oracle (bytes through the checksum), and no two neighbouring frames alike."""
+    import torch
+    p, cp, st = _job(w=480, h=270)
+    w, h = 480, 270
+    org, sm = synth.synthetic_gyro(1000 / FPS + 2.0)
+    cp = g.ComputeParams(p, org, sm)
+    src = synth.synthetic_frame(w, h, "RGBA8", stride=p.stride)
+    tsrc = torch.from_numpy(src).cuda()
+    ring = [torch.zeros((h, p.output_stride), dtype=torch.uint8, device="cuda") for _ in range(6)]
+    mk = lambda f: g.Buffers(g.BufferDescription((w, h, p.stride), tsrc.data_ptr(), length=tsrc.numel()),
+                             g.BufferDescription((w, h, p.output_stride), ring[f % 6].data_ptr(), length=ring[f % 6].numel()))
+    q = g.RenderQueue(cp, st, "opencv_fisheye", None, mk(0).input, mk(0).output, depth=6, checksum=True)
+    ts_of = lambda f: 200.0 + f * (1000.0 / FPS)
+    sums = q.render(range(1000), ts_of, mk)
+    q.close()
+    assert list(sums) == list(range(1000))
+    assert all(sums[f] != sums[f + 1] for f in range(999))
+    dg = g.DeviceGyro(cp)
+    mats = torch.zeros((max(w, h), 14), dtype=torch.float32, device="cuda")
+    for f in range(0, 1000, 40):
+        want = _expected(p, cp, st, dg, mats, ts_of(f), f, src, "RGBA8", "opencv_fisheye", None, mk(f))
+        assert sums[f] == render_queue.checksum_host(want), "frame %d" % f
+    dg.close()
+
+
 def test_queue_full_and_errors():
     import torch
     p, cp, st = _job()
