@@ -683,6 +683,26 @@ def _random_case(rng):
     return c
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_randomized_fisheye_filter_sweep(seed):
+    """The filtered pre-pass under random conditions: 30 frames per seed of the opencv_fisheye model with random coefficients (both signs, weak to
+    beyond the conditioning cap), focal lengths, principal points, roll / readout times, zoom, translations, sizes and 8-bit layouts — every
+    frame byte-identical to the CPU oracle (pairs the certificate cannot decide go through the tail launch or, past the cap, everything does)."""
+    rng = np.random.default_rng(7000 + seed)
+    for _ in range(30):
+        w, h = int(rng.integers(64, 420)), int(rng.integers(48, 260))
+        scale = float(rng.choice([0.02, 0.2, 1.0, 3.0]))
+        k = [float(rng.normal(0, 0.08) * scale), float(rng.normal(0, 0.03) * scale), float(rng.normal(0, 0.01) * scale), float(rng.normal(0, 0.004) * scale)] + [0.0] * 8
+        f = float(rng.uniform(0.25, 1.4) * w)
+        params = dict(k=k, f=[f, f * float(rng.uniform(0.97, 1.03))], c=[w / 2 + float(rng.uniform(-20, 20)), h / 2 + float(rng.uniform(-20, 20))])
+        if rng.integers(3) == 0: params["translation2d"] = [float(rng.uniform(-15, 15)), float(rng.uniform(-15, 15))]
+        c = dict(w=w, h=h, pix=str(rng.choice(["RGBA8", "Luma8", "UV8", "RGB8", "Luma16"])), ts=float(rng.uniform(100, 3600)), fov=float(rng.choice([0.7, 1.0, 1.0, 1.3, 2.2])),
+                 readout=float(rng.choice([8.0, 16.0, 33.0, -16.0])), video_rotation=float(rng.choice([0.0, 0.0, 2.0, 11.0, 45.0, 90.0])), params=params,
+                 interp=str(rng.choice(["Bilinear", "Bilinear", "Bilinear", "Lanczos4"])))
+        if c["pix"] == "RGB8": c["stride_pad"] = int(rng.choice([0, 1]))
+        assert_bit_exact(c)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_randomized_sweep(seed):
     """40 random combinations per seed of lens / digital lens / pixel format / resampler / size / stride / rects / per-frame options."""
