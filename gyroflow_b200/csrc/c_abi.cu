@@ -265,6 +265,7 @@ void fill_uniforms(WarpArgs& A, const gf_cuda_ctx* ctx, const uint8_t* src, cons
     if ((p->flags & 4) == 4) f |= F_FILLBG;
     if (lens_noop(ctx->distortion_model, p)) f |= F_LENS_NOOP;
     if ((reinterpret_cast<uintptr_t>(src) % (uintptr_t)align) == 0 && (p->stride % align) == 0) f |= F_SRC_VEC;
+    if ((f & F_SRC_VEC) && (reinterpret_cast<uintptr_t>(src) % 8u) == 0 && (p->stride % 8) == 0 && (A.src_len % 8ull) == 0) f |= F_SRC_VEC8;
     if ((reinterpret_cast<uintptr_t>(dst) % (uintptr_t)align) == 0 && (p->output_stride % align) == 0) f |= F_DST_VEC;
     if ((p->flags & 128) == 128) f |= F_FB_INV;
     if (p->plane_index == 0) f |= F_IS_Y;

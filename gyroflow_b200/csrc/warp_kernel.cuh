@@ -52,6 +52,7 @@ enum : uint32_t {
     F_WILD       = 1u << 22,  // lens coefficients / translation2d / source mapping outside the magnitudes the packed fast paths assume
     F_INTPRO     = 1u << 23,  // packed kernel: both output maps are the identity -> integer prologue (X2Hot below)
     F_FILTER     = 1u << 24,  // packed kernel: filtered rolling-shutter pre-pass (approximate mid-row evaluation + deferred exact pairs)
+    F_SRC_VEC8   = 1u << 25,  // source pointer, stride and length are multiples of 8: every aligned 8-byte word that holds a valid byte is readable
 };
 
 // Features the specialised ("lean") instantiation compiles out entirely.  The reference's OpenCL backend does the same
@@ -640,6 +641,69 @@ static __device__ __noinline__ void sample_generic(int sx0, int sy0, const WarpA
     for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(sum[ch], P.pixel_value_limit);
 }
 
+// Row window of the 16 / 64-tap samplers, integer formats of <= 4 bytes per pixel.  The I taps of one source row are I * BYTES
+// contiguous bytes at pixel alignment; with F_SRC_VEC8 they are fetched as the aligned 8-byte words that cover them (2..3 LDG.64
+// instead of I narrow loads) and re-aligned in registers: one select per 32-bit word for the 4-byte half, one funnel shift for
+// the byte part.  Same bytes, same arithmetic.  Used for 1- and 2-byte pixels (GF_ROW_WINDOW_MAX_BYTES).
+#ifndef GF_ROW_WINDOW
+#define GF_ROW_WINDOW 1
+#endif
+#ifndef GF_ROW_WINDOW_MAX_BYTES
+#define GF_ROW_WINDOW_MAX_BYTES 2    // measured: 8K Luma16 Lanczos4 +4 %, 4K RGBA8 (4 bytes: 5 LDG.64 + 8 SEL instead of 8 LDG.32) -4.5 %
+#endif
+#ifndef GF_HI_UNROLL
+#define GF_HI_UNROLL 2               // rows of the 16 / 64-tap loop per iteration (full unrolling stalled on instruction fetch)
+#endif
+#ifndef GF_SHADE_MINB
+#define GF_SHADE_MINB 5              // 48 registers: measured best of {none (57-64 regs), 4, 5} x unroll {1, 2}, profiles/README.md
+#endif
+#ifdef GF_SHADE_MINB
+#define GF_SHADE_BOUNDS __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y, GF_SHADE_MINB)
+#else
+#define GF_SHADE_BOUNDS __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
+#endif
+#define GF_PRAGMA_(x) _Pragma(#x)
+#define GF_PRAGMA_UNROLL(n) GF_PRAGMA_(unroll n)
+template <int I, class PIX> struct RowWindow {
+    static constexpr bool ENABLED = GF_ROW_WINDOW && (PIX::SCALAR == SC_U8 || PIX::SCALAR == SC_U16) && PIX::POW2 && PIX::BYTES <= GF_ROW_WINDOW_MAX_BYTES && (I == 4 || I == 8);
+    static constexpr int SPAN = I * PIX::BYTES;                            // bytes of taps
+    static constexpr int NT = SPAN / 4 > 0 ? SPAN / 4 : 1;                 // 32-bit words of taps
+    static constexpr int NQ = (SPAN + 8 - PIX::BYTES + 7) / 8;             // aligned 8-byte words the taps can touch
+    static GF_DEV void load(const uint8_t* __restrict__ p, uint32_t (&T)[NT]) {
+        const uint32_t o = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
+        const uint2* __restrict__ q = reinterpret_cast<const uint2*>(p - o);
+        uint32_t W[2 * NQ];
+        #pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            uint2 t = make_uint2(0u, 0u);
+            if (i < NQ - 1 || o + (uint32_t)SPAN > 8u * (uint32_t)(NQ - 1)) t = __ldg(q + i);   // the last word only when a tap reaches it
+            W[2 * i] = t.x; W[2 * i + 1] = t.y;
+        }
+        const bool hi = (o & 4u) != 0u;
+        if (PIX::BYTES == 4) {
+            #pragma unroll
+            for (int j = 0; j < NT; ++j) T[j] = hi ? W[j + 1] : W[j];
+        } else {
+            const uint32_t sh = (o & 3u) * 8u;
+            uint32_t U[NT + 1];
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) U[j] = hi ? W[j + 1] : W[j];
+            #pragma unroll
+            for (int j = 0; j < NT; ++j) T[j] = __funnelshift_r(U[j], U[j + 1], sh);
+        }
+    }
+    // tap xp as COUNT "magic" floats 2^23 + raw (see Pix::load_magic)
+    static GF_DEV void tap(const uint32_t (&T)[NT], int xp, float (&m)[PIX::COUNT]) {
+        #pragma unroll
+        for (int c = 0; c < PIX::COUNT; ++c) {
+            if (PIX::SCALAR == SC_U8) { const int b = xp * PIX::BYTES + c; m[c] = __uint_as_float(__byte_perm(T[b >> 2], 0x4b000000u, 0x7540u + (uint32_t)(b & 3))); }
+            else                      { const int h = xp * PIX::COUNT + c; m[c] = __uint_as_float(__byte_perm(T[h >> 1], 0x4b000000u, (h & 1) ? 0x7432u : 0x7410u)); }
+        }
+    }
+};
+// feature bit that makes sample_interior<I, PIX> legal
+template <int I, class PIX> __host__ __device__ constexpr uint32_t interior_bit() { return RowWindow<I, PIX>::ENABLED ? F_SRC_VEC8 : F_SRC_VEC; }
+
 // Interior fast path: all IxI taps inside source_rect, whole-pixel vector loads.  Same arithmetic, no per-tap tests.
 template <int I, class PIX>
 GF_DEV void sample_interior(int sx0, int sy0, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
@@ -672,35 +736,45 @@ GF_DEV void sample_interior(int sx0, int sy0, const WarpArgs& A, float (&sum)[PI
     } else {
         // 16 / 64 taps.  Same operations in the same order (xsum += px * cx[xp] along a row, sum += xsum * cy[yp] down the rows);
         // the schedule differs: rows are a rolled loop (the fully unrolled 64-tap body stalled on instruction fetch) with cy[yp]
-        // read from the table, integer taps are widened by PRMT + exact subtraction, and with an even channel count the
-        // multiply/add stream runs on register pairs (FADD2 / FFMA2), halving its issue slots.
+        // read from the table, and with an even channel count the multiply/add stream runs on register pairs (FFMA2), halving
+        // its issue slots.  Integer taps are widened by PRMT into m = 2^23 + raw (exact), and the product is taken as
+        // fma(m, cx, -2^23*cx): -2^23*cx is exact (a power-of-two scale), so the FMA rounds the exact real raw*cx once —
+        // the same value as float(raw) * cx — and the separate subtraction of 2^23 disappears.  (A zero tap yields +0 where
+        // the plain product yields sign(cx)*0; the running sum starts at +0 and x + (+-0) == x, so sums are identical; and since
+        // the fused form never yields -0, the first tap's 0 + t is t itself and that addition is skipped.)
         constexpr bool INT_FMT = PIX::SCALAR == SC_U8 || PIX::SCALAR == SC_U16;
         constexpr bool PAIRS = (C % 2) == 0;
         constexpr int NP = PAIRS ? C / 2 : 1;
+        using RW = RowWindow<I, PIX>;
         float cx[I];
         coeff_row<I>((uint32_t)sx0 & 31u, cx);
+        float ncx[I];
+        #pragma unroll
+        for (int xp = 0; xp < I; ++xp) ncx[xp] = cx[xp] * -8388608.0f;
         const float* __restrict__ cyp = (I == 4 ? GF_COEFFS_BICUBIC_DEV : GF_COEFFS_LANCZOS4_DEV) + (((uint32_t)sy0 & 31u) * I);
         float2 s2[NP];
         #pragma unroll
         for (int k = 0; k < NP; ++k) s2[k] = make_float2(0.0f, 0.0f);
         #pragma unroll
         for (int ch = 0; ch < C; ++ch) sum[ch] = 0.0f;
-        #pragma unroll 1
+        GF_PRAGMA_UNROLL(GF_HI_UNROLL)
         for (int yp = 0; yp < I; ++yp) {
             const float cy = __ldg(cyp + yp);
             if (PAIRS) {
                 float2 x2[NP];
                 #pragma unroll
                 for (int k = 0; k < NP; ++k) x2[k] = make_float2(0.0f, 0.0f);
+                uint32_t T[RW::NT];
+                if (RW::ENABLED) RW::load(row, T);
                 #pragma unroll
                 for (int xp = 0; xp < I; ++xp) {
                     float v[C];
-                    if (INT_FMT) PIX::load_magic(row + xp * PIX::BYTES, v); else PIX::load_vec(row + xp * PIX::BYTES, v);
+                    if (RW::ENABLED) RW::tap(T, xp, v); else if (INT_FMT) PIX::load_magic(row + xp * PIX::BYTES, v); else PIX::load_vec(row + xp * PIX::BYTES, v);
                     #pragma unroll
                     for (int k = 0; k < NP; ++k) {
-                        float2 px = make_float2(v[2 * k], v[2 * k + 1]);
-                        if (INT_FMT) px = __fadd2_rn(px, make_float2(-8388608.0f, -8388608.0f));
-                        x2[k] = p2::add(x2[k], p2::mul(px, p2::bc(cx[xp])));
+                        const float2 px = make_float2(v[2 * k], v[2 * k + 1]);
+                        const float2 t = INT_FMT ? p2::fma(px, p2::bc(cx[xp]), p2::bc(ncx[xp])) : p2::mul(px, p2::bc(cx[xp]));
+                        x2[k] = (INT_FMT && xp == 0) ? t : p2::add(x2[k], t);      // integer taps: t is never -0, so 0 + t == t
                     }
                 }
                 #pragma unroll
@@ -709,14 +783,16 @@ GF_DEV void sample_interior(int sx0, int sy0, const WarpArgs& A, float (&sum)[PI
                 float xsum[C];
                 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) xsum[ch] = 0.0f;
+                uint32_t T[RW::NT];
+                if (RW::ENABLED) RW::load(row, T);
                 #pragma unroll
                 for (int xp = 0; xp < I; ++xp) {
                     float v[C];
-                    if (INT_FMT) PIX::load_magic(row + xp * PIX::BYTES, v); else PIX::load_vec(row + xp * PIX::BYTES, v);
+                    if (RW::ENABLED) RW::tap(T, xp, v); else if (INT_FMT) PIX::load_magic(row + xp * PIX::BYTES, v); else PIX::load_vec(row + xp * PIX::BYTES, v);
                     #pragma unroll
                     for (int ch = 0; ch < C; ++ch) {
-                        const float px = INT_FMT ? v[ch] - 8388608.0f : v[ch];
-                        xsum[ch] += px * cx[xp];
+                        const float t = INT_FMT ? __fmaf_rn(v[ch], cx[xp], ncx[xp]) : v[ch] * cx[xp];
+                        xsum[ch] = (INT_FMT && xp == 0) ? t : xsum[ch] + t;
                     }
                 }
                 #pragma unroll
@@ -770,16 +846,17 @@ template <int C> GF_DEV void remap_colorrange(float (&px)[C], bool is_y) {      
 
 // sample_input_at at (u, v): picks the integer / interior / generic sampler.  Returns the clamped float sums
 // (what the reference's `sum` holds after :413-418).
-// Bicubic (I = 4) and Lanczos4 (I = 8) — cpu_undistort.rs:370-418 with offset 1 / 3 (:372-376).  One out-of-line body per pixel
-// format, shared by every lens model of a translation unit and reached from the scalar kernels through a uniform run-time branch
-// (the kernel family stays one instantiation per (lens, digital lens, pixel format) instead of three).
+// Bicubic (I = 4) and Lanczos4 (I = 8) — cpu_undistort.rs:370-418 with offset 1 / 3 (:372-376).  Only the coordinate-map shading
+// kernel reaches these (one instantiation per pixel format), through a uniform run-time branch on the resampler, and they are
+// inlined into it: as an out-of-line function the sampler saw the kernel parameters through a generic pointer (LD.E + R2UR per
+// access instead of constant-bank operands), which cost 12-18 % of the two-pass frame rate (profiles/README.md, r02n).
 template <int I, class PIX>
 GF_DEV void sample_input_at_hi(float uvx, float uvy, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
     const float offset = I == 4 ? 1.0f : 3.0f;
     const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
     const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
     const int sx = sx0 >> 5, sy = sy0 >> 5;
-    const bool interior = (A.feat & F_SRC_VEC) != 0 && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
+    const bool interior = (A.feat & interior_bit<I, PIX>()) != 0 && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
     if (interior) sample_interior<I, PIX>(sx0, sy0, A, sum);
     else          sample_generic<I, PIX>(sx0, sy0, A, sum);
 }
@@ -869,7 +946,7 @@ GF_DEV void sample_ewa(float uvx, float uvy, float4 jac, const WarpArgs& A, floa
 }
 
 template <class PIX>
-static __device__ __noinline__ void sample_high_order(float uvx, float uvy, float4 jac, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
+GF_DEV void sample_high_order(float uvx, float uvy, float4 jac, const WarpArgs& A, float (&sum)[PIX::COUNT]) {
     if (A.p.interpolation == GF_INTERP_BICUBIC)       sample_input_at_hi<4, PIX>(uvx, uvy, A, sum);
     else if (A.p.interpolation == GF_INTERP_LANCZOS4) sample_input_at_hi<8, PIX>(uvx, uvy, A, sum);
     else                                              sample_ewa<PIX>(uvx, uvy, jac, A, sum);
@@ -885,7 +962,8 @@ GF_DEV void sample_input_at(float uvx, float uvy, const WarpArgs& A, float (&sum
     const int sx0 = as_i32(rs_round((uvx - offset) * 32.0f));
     const int sy0 = as_i32(rs_round((uvy - offset) * 32.0f));
     const int sx = sx0 >> 5, sy = sy0 >> 5;
-    const bool interior = has<GEN>(A.feat, F_SRC_VEC) && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
+    const bool vec_ok = RowWindow<I, PIX>::ENABLED ? (A.feat & F_SRC_VEC8) != 0 : has<GEN>(A.feat, F_SRC_VEC);
+    const bool interior = vec_ok && sx >= A.src_rect[0] && sx + I <= A.src_rect[2] && sy >= A.src_rect[1] && sy + I <= A.src_rect[3];
     if (interior) sample_interior<I, PIX>(sx0, sy0, A, sum);
     else          sample_generic<I, PIX>(sx0, sy0, A, sum);
 }
@@ -1000,7 +1078,7 @@ warp_kernel(const __grid_constant__ WarpArgs A) {
 
 // Pass 2 of the multi-plane mode: one launch per plane, coordinates from the map — sampling, conversion and store only.
 template <class PIX>
-__global__ void __launch_bounds__(GF_BLOCK_X * GF_BLOCK_Y)
+__global__ void GF_SHADE_BOUNDS
 shade_from_coords_kernel(const __grid_constant__ WarpArgs A) {
     const gf_kernel_params& P = A.p;
     constexpr int C = PIX::COUNT;

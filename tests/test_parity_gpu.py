@@ -287,6 +287,17 @@ def test_bicubic_and_lanczos4(interp):
     assert_bit_exact(dict(w=320, h=180, interp=interp, pix="UV16", flags=abi.FLAG_FIX_COLOR_RANGE, params=dict(pixel_value_limit=60000.0)))
 
 
+@pytest.mark.parametrize("pix", ["Luma8", "UV8", "RGBA8", "BGRA8", "Luma16", "UV16", "RGB8", "RGB16", "RGBA16", "AYUV16"])
+@pytest.mark.parametrize("interp", ["Bicubic", "Lanczos4"])
+def test_high_order_every_integer_format(interp, pix):
+    """Row-window loader of the 16 / 64-tap samplers (RowWindow in warp_kernel.cuh: aligned 8-byte words + register re-alignment for formats
+    of <= 4 bytes per pixel) against the oracle: 8-byte aligned strides (window path, every tap offset occurs), an odd width with a padded
+    stride (the row's last aligned word is only partly valid), and strides that are not multiples of 8 (bounds-checked sampler instead)."""
+    assert_bit_exact(dict(w=200, h=120, interp=interp, pix=pix))
+    assert_bit_exact(dict(w=203, h=117, interp=interp, pix=pix, stride_pad=8 - (203 * abi.PIXEL_TYPES[pix][1] * np.dtype(abi.PIXEL_TYPES[pix][2]).itemsize) % 8, fov=1.3))
+    assert_bit_exact(dict(w=202, h=90, interp=interp, pix=pix, stride_pad=2 if abi.PIXEL_TYPES[pix][2] == "u2" or pix == "UV8" else 1, rs=False))
+
+
 @pytest.mark.parametrize("interp", ["EWA: RobidouxSharp", "EWA: Robidoux", "EWA: Mitchell", "EWA: Catmull-Rom"])
 def test_ewa_cubic_bc(interp):
     assert_bit_exact(dict(w=320, h=180, interp=interp))

@@ -10,7 +10,8 @@ from tests import cases
 import __graft_entry__ as ge
 ge.smoke()
 for case in (dict(w=640, h=360, video_rotation=20.0), dict(w=320, h=180, interp="Lanczos4"), dict(w=320, h=180, pix="RGBAf", lens="sony", ibis=True, mesh=True),
-             dict(w=320, h=180, lens="gopro", digital="gopro_warp", fov=2.0), dict(w=203, h=117, pix="RGB8", stride_pad=3)):
+             dict(w=320, h=180, lens="gopro", digital="gopro_warp", fov=2.0), dict(w=203, h=117, pix="RGB8", stride_pad=3),
+             dict(w=200, h=120, interp="Lanczos4", pix="Luma8", fov=1.4), dict(w=203, h=117, interp="Bicubic", pix="UV8", stride_pad=2, fov=1.4), dict(w=203, h=117, interp="Lanczos4", pix="RGBA8", stride_pad=4, fov=1.4)):
     p, src, m, mesh, dst0, pix, lens, digital = cases.build(case)
     got = dst0.copy()
     bufs = g.Buffers(g.BufferDescription((case["w"], case["h"], p.stride), src), g.BufferDescription((case["w"], case["h"], p.output_stride), got))
