@@ -10,8 +10,9 @@
  * in this image (no rustc/cargo).  The oracle is therefore pinned only by (a) review
  * against the cited lines, (b) analytical known-answer cases (identity warp, pure
  * translation, forward/inverse lens round trips) in tests/, and (c) an independent numpy
- * restatement of the fisheye + rolling-shutter + bilinear path (tests/np_restatement.py,
- * tests/test_oracle.py::test_independent_numpy_restatement_agrees).
+ * restatement of the whole path — every lens model and digital lens, every resampler, mesh /
+ * focal-plane correction, background modes, lens-correction blend (tests/np_restatement.py,
+ * tests/test_oracle.py::test_independent_numpy_restatement_*: 53 cases, same bytes).
  *
  * Float semantics mirrored from Rust: f32 ops are IEEE with no FMA contraction (build
  * with -ffp-contract=off), `as` casts truncate + saturate + NaN->0, f32::round is

@@ -3,9 +3,11 @@
 opencv_standard, poly3, poly5, ptlens, insta360, sony, generic_polynomial, gopro), every digital lens (gopro_superview,
 gopro6_superview, gopro_hyperview, gopro_warp, digital_stretch), vertical rolling shutter, bilinear / bicubic / Lanczos4
 sampling, background modes 0-2, r_limit, light refraction, IBIS / OIS rows, input rotation and stretch, horizontal rolling shutter,
-on 8-bit, 16-bit and f32 pixels (cpu_undistort.rs:133-228 without the mesh block, :421-517 without the lens-correction blend,
-:370-418, :519-633; distortion_models/*.rs distort_point; util.rs:144-147; pixel_formats.rs conversions).
-With it every lens formula of the oracle has two independent transcriptions.
+the f64 mesh correction (bivariate spline, splines.rs:100-176 / sony.rs:557-563) and focal-plane distortion, the EWA CubicBC resampler,
+background mode 3 (margin with feather), fix-colour-range and fill-with-background, and the lens-correction blend for opencv_fisheye,
+on 8-bit, 16-bit and f32 pixels (cpu_undistort.rs:133-228, :262-418, :421-517, :519-633; distortion_models/*.rs distort_point;
+gyro_source/splines.rs; util.rs:144-147; pixel_formats.rs conversions).
+With it every lens formula and every optional stage of the oracle has two independent transcriptions.
 
 TEST INFRASTRUCTURE ONLY.  numpy.float32 arithmetic is IEEE single precision without contraction; atan goes to the same
 libm `atanf` Rust's std calls (numpy's own arctan may differ in the last ulp)."""
@@ -252,11 +254,165 @@ def digital_stretch_distort(x, y, p):        # digital_stretch.rs:19-22
     return x * F(p.digital_lens_params[0]), y * F(p.digital_lens_params[1])
 
 
+def fmaxf(a, b):                             # f32::max: the other operand if one is NaN
+    if math.isnan(float(a)): return F(b)
+    if math.isnan(float(b)): return F(a)
+    return F(a) if a > b else F(b)
+
+
+def fminf(a, b):                             # f32::min
+    if math.isnan(float(a)): return F(b)
+    if math.isnan(float(b)): return F(a)
+    return F(a) if a < b else F(b)
+
+
+def fisheye_undistort_point(x, y, k):        # opencv_fisheye.rs:12-66
+    if k[0] == 0 and k[1] == 0 and k[2] == 0 and k[3] == 0:
+        return x, y
+    EPS = F(1e-6)
+    PI = F(math.pi)
+    theta_d = sqrtf(x * x + y * y)
+    theta_d = fminf(fmaxf(theta_d, -PI), PI)
+    converged = False
+    theta = theta_d
+    scale = F(0.0)
+    if abs(theta_d) > EPS:
+        theta = F(0.0)
+        for _ in range(10):
+            theta2 = theta * theta
+            theta4 = theta2 * theta2
+            theta6 = theta4 * theta2
+            theta8 = theta6 * theta2
+            k0_theta2 = k[0] * theta2
+            k1_theta4 = k[1] * theta4
+            k2_theta6 = k[2] * theta6
+            k3_theta8 = k[3] * theta8
+            theta_fix = (theta * (F(1.0) + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d) / \
+                        (F(1.0) + F(3.0) * k0_theta2 + F(5.0) * k1_theta4 + F(7.0) * k2_theta6 + F(9.0) * k3_theta8)
+            theta_fix = fminf(fmaxf(theta_fix, F(-0.9)), F(0.9))
+            theta = theta - theta_fix
+            if abs(theta_fix) < EPS:
+                converged = True
+                break
+        scale = tanf(theta) / theta_d
+    else:
+        converged = True
+    theta_flipped = (theta_d < 0 and theta > 0) or (theta_d > 0 and theta < 0)
+    if converged and not theta_flipped:
+        return x * scale, y * scale
+    return None
+
+
 DIGITAL = {"gopro_superview": _view_distort(_superview, 1.333333333), "gopro6_superview": _view_distort(_superview6, None),
            "gopro_hyperview": _view_distort(_hyperview, 1.555555555), "gopro_warp": gopro_warp_distort, "digital_stretch": digital_stretch_distort}
 
 
-def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:133-228 without the mesh / focal-plane block
+
+# ---- f64 mesh correction: gyro_source/splines.rs:100-176 (BivariateSpline) and sony.rs:557-563 (interpolate_mesh); Python floats are IEEE doubles ----
+MAX_GRID = 9
+
+
+def cubic_spline_coefficients(vals, size, n):               # splines.rs:100-124 with step = 1, offset = 0
+    h = size / (n - 1)
+    inv_h = 1.0 / h
+    three_inv_h = 3.0 * inv_h
+    h_over_3 = h / 3.0
+    inv_3h = 1.0 / (3.0 * h)
+    a = [vals[i] for i in range(n)]
+    alpha = [0.0] * MAX_GRID; mu = [0.0] * MAX_GRID; z = [0.0] * MAX_GRID
+    b = [0.0] * MAX_GRID; c = [0.0] * MAX_GRID; d = [0.0] * MAX_GRID
+    for i in range(1, n - 1):
+        alpha[i] = three_inv_h * (a[i + 1] - 2.0 * a[i] + a[i - 1])
+    for i in range(1, n - 1):
+        mu[i] = 1.0 / (4.0 - mu[i - 1])
+        z[i] = (alpha[i] * inv_h - z[i - 1]) * mu[i]
+    c[n - 1] = 0.0
+    for j in range(n - 2, -1, -1):
+        c[j] = z[j] - mu[j] * c[j + 1]
+        b[j] = (a[j + 1] - a[j]) * inv_h - h_over_3 * (c[j + 1] + 2.0 * c[j])
+        d[j] = (c[j + 1] - c[j]) * inv_3h
+    return a, b, c, d
+
+
+def _as_usize(x):                                           # Rust `as usize`: truncate, saturate at 0, NaN -> 0
+    if math.isnan(x) or x <= 0.0:
+        return 0
+    return int(min(x, 1.8446744073709552e19))
+
+
+def cubic_spline_interpolate(a, b, c, d, n, x, size):       # splines.rs:126-139
+    if x <= 0.0:
+        return a[0] + b[0] * x
+    if x >= size:
+        h = size / (n - 1)
+        slope = b[n - 2] + 2.0 * c[n - 2] * h + 3.0 * d[n - 2] * h * h
+        return a[n - 1] + slope * (x - size)
+    i = max(min(n - 2, _as_usize((n - 1.0) * x / size)), 0)
+    dx = x - size * i / (n - 1)
+    return a[i] + b[i] * dx + c[i] * dx * dx + d[i] * dx * dx * dx
+
+
+def bivariate_interpolate(n_x, n_y, size_x, size_y, mesh, mesh_offset, x, y):    # splines.rs:141-176
+    i = max(min(n_x - 2, _as_usize((n_x - 1.0) * x / size_x)), 0)
+    dx = x - size_x * i / (n_x - 1)
+    dx2 = dx * dx
+    grid = MAX_GRID
+    raw_mesh_len = n_x * n_y * 2
+    block = grid * 4
+    offs = 9 + raw_mesh_len + (mesh_offset * n_y * block) + i
+    inter = [0.0] * MAX_GRID
+    for j in range(n_y):
+        rb = offs + j * block
+        inter[j] = mesh[rb] + mesh[rb + grid] * dx + mesh[rb + grid * 2] * dx2 + mesh[rb + grid * 3] * dx2 * dx
+    a, b, c, d = cubic_spline_coefficients(inter, size_y, n_y)
+    return cubic_spline_interpolate(a, b, c, d, n_y, y, size_y)
+
+
+def interpolate_mesh(x, y, size, mesh):                     # sony.rs:557-563
+    n_x, n_y = int(mesh[1]), int(mesh[2])
+    return (bivariate_interpolate(n_x, n_y, size[0], size[1], mesh, 0, x, y), bivariate_interpolate(n_x, n_y, size[0], size[1], mesh, 1, x, y))
+
+
+def _mesh_block(ux, uy, p, mesh):                           # cpu_undistort.rs:169-214: mesh correction, then focal-plane distortion
+    fb_inverted = (p.flags & 128) == 128
+    fw, fh = F(p.width), F(p.height)
+    if len(mesh) > 0 and mesh[0] > 10.0:                    # :169-187
+        mesh_size = (mesh[3], mesh[4])
+        ox, oy = F(mesh[5]), F(mesh[6])
+        cw, ch = F(mesh[7]), F(mesh[8])
+        if fb_inverted: uy = fh - uy
+        ux = map_coord(ux, 0.0, fw, ox, ox + cw)
+        uy = map_coord(uy, 0.0, fh, oy, oy + ch)
+        nx, ny = interpolate_mesh(float(ux), float(uy), mesh_size, mesh)
+        ux = map_coord(F(nx), ox, ox + cw, 0.0, fw)
+        uy = map_coord(F(ny), oy, oy + ch, 0.0, fh)
+        if fb_inverted: uy = fh - uy
+    # :190-214 FocalPlaneDistortion.  The reference indexes mesh_data[mesh_data[0]] unconditionally (a mesh without the focal-plane block
+    # would panic there; sony.rs always appends one); oracle and kernels treat a missing block as "no focal-plane distortion".
+    if len(mesh) > 0 and mesh[0] > 0.0 and int(mesh[0]) < len(mesh) and mesh[int(mesh[0])] > 0.0:
+        o = int(mesh[0])
+        mesh_size = (mesh[3], mesh[4])
+        ox, oy = F(mesh[5]), F(mesh[6])
+        cw, ch = F(mesh[7]), F(mesh[8])
+        stblz_grid = mesh_size[1] / 8.0
+        if fb_inverted: uy = fh - uy
+        ux = map_coord(ux, 0.0, fw, ox, ox + cw)
+        uy = map_coord(uy, 0.0, fh, oy, oy + ch)
+        q = float(uy) / stblz_grid
+        idx = _as_usize(min(max(math.floor(q), 0.0), 7.0)) if not math.isnan(q) else 0
+        delta = float(uy) - stblz_grid * idx
+        ux = ux - F(mesh[o + 4 + idx * 2 + 0] * delta)
+        uy = uy - F(mesh[o + 4 + idx * 2 + 1] * delta)
+        for j in range(idx):
+            ux = ux - F(mesh[o + 4 + j * 2 + 0] * stblz_grid)
+            uy = uy - F(mesh[o + 4 + j * 2 + 1] * stblz_grid)
+        ux = map_coord(ux, ox, ox + cw, 0.0, fw)
+        uy = map_coord(uy, oy, oy + ch, 0.0, fh)
+        if fb_inverted: uy = fh - uy
+    return ux, uy
+
+
+def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None, mesh=()):   # cpu_undistort.rs:133-228
     row = m[idx]
     t3 = [F(v) for v in p.translation3d]
     _x = (px * row[0]) + (py * row[1]) + row[2] + t3[0]
@@ -283,6 +439,8 @@ def rotate_and_distort(px, py, idx, p, m, lens="opencv_fisheye", digital=None): 
         cos_a = cosf(-ang); sin_a = sinf(-ang)
         ux, uy = (cos_a * ux - sin_a * uy - row[9] + row[12], sin_a * ux + cos_a * uy - row[10] + row[13])
     ux = ux + F(p.c[0]); uy = uy + F(p.c[1])
+    if len(mesh) > 0:
+        ux, uy = _mesh_block(ux, uy, p, mesh)
     if digital is not None and (p.flags & 2) == 2:           # :216-220
         ux, uy = DIGITAL[digital](ux, uy, p)
     if F(p.input_horizontal_stretch) > F(0.001): ux = ux / F(p.input_horizontal_stretch)      # :222-223
@@ -294,18 +452,38 @@ def rotate_point(px, py, angle, ox, oy, o2x, o2y):           # cpu_undistort.rs:
     return (cosf(angle) * (px - ox) - sinf(angle) * (py - oy) + o2x, sinf(angle) * (px - ox) + cosf(angle) * (py - oy) + o2y)
 
 
-def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:421-517 without the lens-correction blend (:429-460)
+def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None, mesh=()):   # cpu_undistort.rs:421-517 (the lens-correction blend :429-460 for opencv_fisheye without a digital lens)
     ox = map_coord(x, p.output_rect[0], p.output_rect[0] + p.output_rect[2], 0.0, p.output_width)
     oy = map_coord(y, p.output_rect[1], p.output_rect[1] + p.output_rect[3], 0.0, p.output_height)
     ox = ox + F(p.translation2d[0]); oy = oy + F(p.translation2d[1])
+    lca = F(p.lens_correction_amount)
+    if lca < F(1.0):                                         # :429-460 "add lens distortion back"
+        assert lens == "opencv_fisheye" and (digital is None or (p.flags & 2) == 0), "restated for opencv_fisheye only"
+        factor = fmaxf(F(1.0) - lca, F(0.001))               # :525-527
+        out_cx, out_cy = F(p.output_width) / F(2.0), F(p.output_height) / F(2.0)
+        out_fx, out_fy = F(p.f[0]) / F(p.fov) / factor, F(p.f[1]) / F(p.fov) / factor
+        nx, ny = (ox - out_cx) / out_fx, (oy - out_cy) / out_fy
+        pt = fisheye_undistort_point(nx, ny, [F(v) for v in p.k])
+        if pt is not None:
+            nx, ny = pt
+        lrc = F(p.light_refraction_coefficient)
+        if lrc != F(1.0) and lrc > 0:
+            r = sqrtf(nx * nx + ny * ny)
+            if r != 0:
+                sin_theta_d = (r / sqrtf(F(1.0) + r * r)) / lrc
+                r_d = sin_theta_d / sqrtf(F(1.0) - sin_theta_d * sin_theta_d)
+                fac = r_d / r
+                nx, ny = nx * fac, ny * fac
+        nx, ny = nx * out_fx + out_cx, ny * out_fy + out_cy
+        ox, oy = nx * (F(1.0) - lca) + ox * lca, ny * (F(1.0) - lca) + oy * lca
     hrs = (p.flags & 16) == 16
     sy = max(min(as_i32(round_half_away(ox)), p.width), 0) if hrs else max(min(as_i32(round_half_away(oy)), p.height), 0)
     if p.matrix_count > 1:
-        pt = rotate_and_distort(ox, oy, p.matrix_count // 2, p, m, lens, digital)
+        pt = rotate_and_distort(ox, oy, p.matrix_count // 2, p, m, lens, digital, mesh)
         if pt is not None:
             sy = max(min(as_i32(round_half_away(pt[0])), p.width), 0) if hrs else max(min(as_i32(round_half_away(pt[1])), p.height), 0)
     idx = min(sy, p.matrix_count - 1)
-    uv = rotate_and_distort(ox, oy, idx, p, m, lens, digital)
+    uv = rotate_and_distort(ox, oy, idx, p, m, lens, digital, mesh)
     if uv is None:
         return None
     u, v = uv
@@ -401,6 +579,91 @@ def sample_separable(u, v, src, p, bg, count, sbytes, I):   # cpu_undistort.rs:3
     return [min(t, lim) if not math.isnan(float(t)) else lim for t in total]
 
 
+# ---- EWA (elliptical weighted average) CubicBC resampler: cpu_undistort.rs:271-369 ----
+def affine_bbox(jac):                        # :274-279
+    jx, jy, jz, jw = jac
+    return (F(2.0) * fmaxf(fmaxf(abs(jx + jy), abs(jx - jy)), F(1.0)), F(2.0) * fmaxf(fmaxf(abs(jz + jw), abs(jz - jw)), F(1.0)))
+
+
+def clamped_ellipse(jac):                    # :281-314
+    jx, jy, jz, jw = jac
+    f0 = abs(jx * jw - jy * jz)
+    f = fmaxf(f0 * f0, F(0.1))
+    a = (jz * jz + jw * jw) / f
+    b = F(-2.0) * (jx * jz + jy * jw) / f
+    c = (jx * jx + jy * jy) / f
+    vx, vy = c - a, -b
+    lv = sqrtf(vx * vx + vy * vy)
+    v0 = vx / lv if lv > F(0.01) else F(1.0)
+    cc = sqrtf(fmaxf(F(1.0) + v0, F(0.0)) / F(2.0))
+    s = sqrtf(fmaxf(F(1.0) - v0, F(0.0)) / F(2.0))
+    a0 = a * cc * cc - b * cc * s + c * s * s
+    c0 = a * s * s + b * cc * s + c * cc * cc
+    bt1 = b * (cc * cc - s * s)
+    bt2 = F(2.0) * (a - c) * cc * s
+    b0 = bt1 + bt2
+    b0v2 = bt1 - bt2
+    if abs(b0) > abs(b0v2):
+        s = -s
+        b0 = b0v2
+    a0 = fminf(a0, F(1.0))
+    c0 = fminf(c0, F(1.0))
+    sn = -s
+    return (a0 * cc * cc - b0 * cc * sn + c0 * sn * sn,
+            F(2.0) * a0 * cc * sn + b0 * cc * cc - b0 * sn * sn - F(2.0) * c0 * cc * sn,
+            a0 * sn * sn + b0 * cc * sn + c0 * cc * cc)
+
+
+def bc2(x, p):                               # :316-326
+    x = abs(x)
+    x2 = x * x
+    cp = [F(v) for v in p.ewa_coeffs_p]; cq = [F(v) for v in p.ewa_coeffs_q]
+    if x < F(1.0):
+        return cp[0] + cp[1] * x + cp[2] * x2 + cp[3] * x2 * x
+    elif x < F(2.0):
+        return cq[0] + cq[1] * x + cq[2] * x2 + cq[3] * x2 * x
+    return F(0.0)
+
+
+def sample_ewa(u, v, jac, src, p, bg, count, sbytes):       # :331-369
+    tx, ty = affine_bbox(jac)
+    b0 = as_i32(F(math.floor(float(u - tx)))); b1 = as_i32(F(math.ceil(float(u + tx))))
+    b2 = as_i32(F(math.floor(float(v - ty)))); b3 = as_i32(F(math.ceil(float(v + ty))))
+    total = [F(0.0)] * 4
+    sum_div = F(0.0)
+    A, B, C = clamped_ellipse(jac)
+    rx0, ry0 = p.source_rect[0], p.source_rect[1]
+    rx1, ry1 = rx0 + p.source_rect[2], ry0 + p.source_rect[3]
+    for in_y in range(b2, b3 + 1):
+        in_fy = F(in_y) - v
+        in_fy2 = in_fy * B
+        in_fy3 = in_fy * in_fy * C
+        for in_x in range(b0, b1 + 1):
+            in_fx = F(in_x) - u
+            dr = in_fx * in_fx * A + in_fx * in_fy2 + in_fy3
+            k = bc2(sqrtf(dr), p)
+            if k == 0:
+                continue
+            if ry0 <= in_y < ry1 and rx0 <= in_x < rx1:
+                off = (in_y * p.stride + in_x * p.bytes_per_pixel) // sbytes
+                px = [F(src[off + c]) if c < count else F(0.0) for c in range(4)]
+            else:
+                px = bg
+            total = [total[c] + k * px[c] for c in range(4)]
+            sum_div = sum_div + k
+    total = [t / sum_div for t in total]
+    lim = F(p.pixel_value_limit)             # :413-418 applies to every resampler
+    return [fminf(t, lim) for t in total]
+
+
+def remap_colorrange(px, is_y):              # :254-260
+    s = F(0.85882352) if is_y else F(0.87843137)
+    px = [v * s for v in px]
+    px[0] = px[0] + F(16.0)
+    px[1] = px[1] + F(16.0)
+    return px
+
+
 def to_u8(v):                                # `as u8`: truncate, saturate, NaN -> 0
     v = float(v)
     if math.isnan(v):
@@ -417,15 +680,27 @@ def to_scalar(v, sdt):                       # PixelType::from_float: Rust `as u
     return max(0, min(255 if sdt == np.uint8 else 65535, int(v)))
 
 
-def undistort_image(src, dst, p, matrices, lens="opencv_fisheye", sdt=np.uint8, digital=None):
-    """src, dst: 2-D uint8 arrays (rows x stride).  Writes dst in place like the reference (only pixels it touches).
-    sdt: the scalar type of a channel (np.uint8, np.uint16 or np.float32)."""
+def _sample(u, v, jac, flat, p, bg, count, sbytes):
+    if p.interpolation > 8:
+        return sample_ewa(u, v, jac, flat, p, bg, count, sbytes)
+    if p.interpolation == 2:
+        return sample_bilinear(u, v, flat, p, bg, count, sbytes)
+    return sample_separable(u, v, flat, p, bg, count, sbytes, p.interpolation)
+
+
+def undistort_image(src, dst, p, matrices, lens="opencv_fisheye", sdt=np.uint8, digital=None, mesh=None):
+    """src, dst: 2-D uint8 arrays (rows x stride).  Writes dst in place like the reference (only pixels it touches) — the main loop
+    cpu_undistort.rs:543-625.  sdt: the scalar type of a channel (np.uint8, np.uint16 or np.float32); mesh: the f32 mesh or None."""
     m = [[F(x) for x in row] for row in np.asarray(matrices, dtype=np.float32).reshape(-1, 14)]
+    mesh64 = [float(v) for v in np.asarray(mesh, dtype=np.float32)] if mesh is not None else []       # :539 widened once
     sbytes = np.dtype(sdt).itemsize
     count = p.bytes_per_pixel // sbytes
     flat = src.reshape(-1).view(sdt)
     dview = dst.view(sdt)                    # rows x (stride / sbytes) scalars (strides are multiples of the scalar size in these tests)
     bg = [F(p.background[c]) * F(p.max_pixel_value) for c in range(4)]
+    fill_bg = (p.flags & 4) == 4
+    fix_range = (p.flags & 1) == 1
+    is_y = p.plane_index == 0
     for y in range(dst.shape[0]):
         npix = min(dst.shape[1], p.output_stride) // p.bytes_per_pixel
         for x in range(npix):
@@ -433,12 +708,47 @@ def undistort_image(src, dst, p, matrices, lens="opencv_fisheye", sdt=np.uint8, 
             opy = map_coord(y, p.output_rect[1], p.output_rect[1] + p.output_rect[3], 0.0, p.output_height)
             if not (opx >= 0 and opy >= 0 and as_i32(opx) < p.output_width and as_i32(opy) < p.output_height):
                 continue
-            uv = undistort_coord(F(x), F(y), p, m, lens, digital)
-            if uv is None:
-                pixel = bg
-            elif p.interpolation == 2:
-                pixel = sample_bilinear(uv[0], uv[1], flat, p, bg, count, sbytes)
-            else:
-                pixel = sample_separable(uv[0], uv[1], flat, p, bg, count, sbytes, p.interpolation)
+            if fill_bg:                                                                   # :559-562
+                for c in range(count):
+                    dview[y, x * count + c] = to_scalar(bg[c], sdt)
+                continue
+            pixel = bg
+            uv = undistort_coord(F(x), F(y), p, m, lens, digital, mesh64)
+            if uv is not None:
+                jac = (F(1.0), F(0.0), F(0.0), F(1.0))
+                if p.interpolation > 8:                                                   # :567-572 forward differences, None -> (0, 0)
+                    eps = F(0.01)
+                    a = undistort_coord(F(x) + eps, F(y), p, m, lens, digital, mesh64) or (F(0.0), F(0.0))
+                    b = undistort_coord(F(x), F(y) + eps, p, m, lens, digital, mesh64) or (F(0.0), F(0.0))
+                    xyx = (a[0] - uv[0], a[1] - uv[1]); xyy = (b[0] - uv[0], b[1] - uv[1])
+                    jac = (xyx[0] / eps, xyy[0] / eps, xyx[1] / eps, xyy[1] / eps)
+                u, v = uv
+                if p.background_mode == 3:                                                # :576-611 margin with feather
+                    width_f, height_f = F(p.width), F(p.height)
+                    widthf, heightf = width_f - F(1.0), height_f - F(1.0)
+                    feather = fmaxf(F(p.background_margin_feather) * heightf, F(0.0001))
+                    p2x, p2y = u, v
+                    alpha = F(1.0)
+                    if (u > widthf - feather) or (u < feather) or (v > heightf - feather) or (v < feather):
+                        alpha = fmaxf(fminf(fminf(fminf(fminf(widthf - u, heightf - v), u), v) / feather, F(1.0)), F(0.0))
+                        p2x, p2y = p2x / width_f, p2y / height_f
+                        mg = F(1.0) - F(p.background_margin)
+                        p2x, p2y = ((p2x - F(0.5)) * mg) + F(0.5), ((p2y - F(0.5)) * mg) + F(0.5)
+                        p2x, p2y = p2x * width_f, p2y * height_f
+                    fw, fh = width_f, height_f
+                    if F(p.input_rotation) != 0:
+                        rotation = F(p.input_rotation) * (F(math.pi) / F(180.0))
+                        fw, fh = rotate_point(fw, fh, rotation, F(0.0), F(0.0), F(0.0), F(0.0))
+                        fw, fh = round_half_away(abs(fw)), round_half_away(abs(fh))
+                    sr = p.source_rect
+                    u, v = map_coord(u, 0.0, fw, sr[0], sr[0] + sr[2]), map_coord(v, 0.0, fh, sr[1], sr[1] + sr[3])
+                    p2x, p2y = map_coord(p2x, 0.0, fw, sr[0], sr[0] + sr[2]), map_coord(p2y, 0.0, fh, sr[1], sr[1] + sr[3])
+                    c1 = _sample(u, v, jac, flat, p, bg, count, sbytes)
+                    c2 = _sample(p2x, p2y, jac, flat, p, bg, count, sbytes)
+                    pixel = [c1[c] * alpha + c2[c] * (F(1.0) - alpha) for c in range(4)]
+                else:
+                    pixel = _sample(u, v, jac, flat, p, bg, count, sbytes)
+            if fix_range:
+                pixel = remap_colorrange(list(pixel), is_y)
             for c in range(count):
                 dview[y, x * count + c] = to_scalar(pixel[c], sdt)

@@ -214,3 +214,36 @@ def test_independent_numpy_restatement_remaining_models_and_resamplers():
             warnings.simplefilter("ignore")
             np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=sdt, digital=digital)
         assert np.array_equal(got, want), (c, int((got != want).sum()))
+
+
+def test_independent_numpy_restatement_mesh_ewa_feather_and_blend():
+    """The stages that still had a single transcription — the f64 mesh correction (bivariate spline of splines.rs with the per-row
+    coefficient blocks of sony.rs) and focal-plane distortion incl. the inverted-framebuffer flips, the EWA CubicBC resampler with its
+    forward-difference Jacobian, background mode 3 (margin with feather, two samples blended), the lens-correction blend
+    (opencv_fisheye undistort_point + refraction), fix-colour-range and fill-with-background — restated a second time in
+    tests/np_restatement.py: same bytes as the C oracle."""
+    import warnings
+    from tests import cases, np_restatement
+    todo = [
+        (dict(w=64, h=36, lens="sony", mesh=True, pix="R32f"), np.float32), (dict(w=64, h=36, lens="sony", mesh=True, fpd=True, ibis=True), np.uint8),
+        (dict(w=56, h=32, mesh=True, fpd=True, flags=abi.FLAG_FRAMEBUFFER_INVERTED, fov=1.5, pix="Luma16"), np.uint16),
+        (dict(w=56, h=32, lens="opencv_standard", mesh=True, mesh_n=5, rs=False), np.uint8),
+        (dict(w=48, h=28, interp="EWA: Robidoux"), np.uint8), (dict(w=40, h=24, interp="EWA: Mitchell", ow=20, oh=12, pix="RGBAf", params=dict(background=[0.2, 0.4, 0.6, 1.0])), np.float32),
+        (dict(w=40, h=24, interp="EWA: Catmull-Rom", fov=1.7, pix="Luma16", lens="sony"), np.uint16), (dict(w=40, h=24, interp="EWA: RobidouxSharp", rs=False, pix="UV8"), np.uint8),
+        (dict(w=64, h=36, fov=1.6, params=dict(background_mode=3, background_margin=0.1, background_margin_feather=0.1)), np.uint8),
+        (dict(w=56, h=32, fov=1.4, interp="Bicubic", params=dict(background_mode=3, background_margin=0.2, background_margin_feather=0.05, input_rotation=90.0)), np.uint8),
+        (dict(w=64, h=36, params=dict(lens_correction_amount=0.4)), np.uint8),
+        (dict(w=64, h=36, fov=1.5, params=dict(lens_correction_amount=0.0, light_refraction_coefficient=1.33), pix="Luma16"), np.uint16),
+        (dict(w=64, h=36, pix="UV16", flags=abi.FLAG_FIX_COLOR_RANGE, params=dict(pixel_value_limit=60000.0)), np.uint16),
+        (dict(w=64, h=36, pix="Luma8", flags=abi.FLAG_FIX_COLOR_RANGE, params=dict(plane_index=1)), np.uint8),
+        (dict(w=40, h=24, flags=abi.FLAG_FILL_WITH_BACKGROUND, params=dict(background=[0.9, 0.1, 0.5, 1.0])), np.uint8),
+    ]
+    for c, sdt in todo:
+        p, src, m, mesh, dst0, pix, lens, digital = cases.build(c)
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        got = dst0.copy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=sdt, digital=digital, mesh=mesh)
+        assert np.array_equal(got, want), (c, int((got != want).sum()))
