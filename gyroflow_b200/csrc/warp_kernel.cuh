@@ -261,6 +261,14 @@ template <int COUNT_, int SCALAR_> struct Pix {
 // f32 mesh to f64 once per frame (cpu_undistort.rs:539); here each element is widened on load.
 // ------------------------------------------------------------------------------------------
 #define GF_MAX_GRID 9
+#ifndef GF_MESH9_INLINE
+#define GF_MESH9_INLINE 1
+#endif
+#if GF_MESH9_INLINE
+#define GF_MESH9_QUAL GF_DEV
+#else
+#define GF_MESH9_QUAL static __device__ __noinline__
+#endif
 struct MeshView {
     const double* __restrict__ m;
     GF_DEV double operator[](uint32_t i) const { return __ldg(m + i); }
@@ -285,7 +293,7 @@ struct MeshAux {
 // Same operations in the same order as the general routine below, restricted to what the result depends on:
 // the tridiagonal forward sweep z[], the back-substitution c[] only down to the interval k that contains y, and b, d only at k
 // (the extrapolation branches use k = 0 and k = n - 2).  Fully unrolled, everything in registers.
-static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, const MeshAux& aux, uint32_t n_x, double size_x, double size_y, double x, double y,
+GF_MESH9_QUAL void mesh_interpolate9(const MeshView mesh, const MeshAux& aux, uint32_t n_x, double size_x, double size_y, double x, double y,
                                                        double& out_x, double& out_y) {
     using namespace spline_mu;
     constexpr uint32_t n = 9, grid = GF_MAX_GRID, block = GF_MAX_GRID * 4;
@@ -300,14 +308,17 @@ static __device__ __noinline__ void mesh_interpolate9(const MeshView mesh, const
     else if (mode == 2) k = n - 2;
     const double dy = y - size_y * (double)k / (double)(n - 1);
     const double MU[8] = {M0, M1, M2, M3, M4, M5, M6, M7};
+    // one base pointer, compile-time offsets from it: with 32-bit index arithmetic every one of the 72 loads carried its own
+    // IMAD.WIDE (unsigned wrap-around has to be preserved); the element order and the arithmetic are unchanged
+    const double* __restrict__ base = mesh.m + (9u + n_x * n * 2u + i);
     #pragma unroll 1
     for (uint32_t mo = 0; mo < 2; ++mo) {
-        const uint32_t offs = 9 + n_x * n * 2 + mo * n * block + i;
+        const double* __restrict__ rows = base + (size_t)mo * (n * block);
         double a[9];
         #pragma unroll
-        for (uint32_t j = 0; j < n; ++j) {
-            const uint32_t rb = offs + j * block;
-            a[j] = mesh[rb] + mesh[rb + grid] * dx + mesh[rb + grid * 2] * dx2 + mesh[rb + grid * 3] * dx2 * dx;
+        for (int j = 0; j < (int)n; ++j) {
+            const double* __restrict__ r = rows + j * (int)block;
+            a[j] = __ldg(r) + __ldg(r + grid) * dx + __ldg(r + grid * 2) * dx2 + __ldg(r + grid * 3) * dx2 * dx;
         }
         double z[8];
         z[0] = 0.0;
