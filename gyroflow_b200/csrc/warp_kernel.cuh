@@ -928,20 +928,26 @@ GF_DEV void sample_ewa(float uvx, float uvy, float4 jac, const WarpArgs& A, floa
         for (int ch = 0; ch < C; ++ch) sum[ch] = rs_min(A.bg[ch], P.pixel_value_limit);
         return;
     }
-    for (long long in_y = b2; in_y <= (long long)b3; ++in_y) {
-        const float in_fy = (float)(int)in_y - uvy;
+    // After the guard both spans fit an int; counting taps instead of comparing coordinates keeps the loops in 32-bit arithmetic
+    // even when a bound is a saturated INT_MAX.  When the whole box lies inside source_rect the per-tap tests are skipped.
+    const int nx = (int)((long long)b1 - (long long)b0 + 1), ny = (int)((long long)b3 - (long long)b2 + 1);
+    const bool box_in = b0 >= rx0 && b1 < rx1 && b2 >= ry0 && b3 < ry1;
+    const uint8_t* row = A.src + (long long)b2 * (long long)P.stride + (long long)b0 * (long long)PIX::BYTES;
+    for (int iy = 0; iy < ny; ++iy, row += P.stride) {
+        const int in_y = b2 + iy;
+        const float in_fy = (float)in_y - uvy;
         const float in_fy2 = in_fy * eb;
         const float in_fy3 = in_fy * in_fy * ec;
-        const bool row_in = in_y >= ry0 && in_y < ry1;
-        const uint8_t* row = A.src + in_y * (long long)P.stride;
-        for (long long in_x = b0; in_x <= (long long)b1; ++in_x) {
-            const float in_fx = (float)(int)in_x - uvx;
+        const bool row_in = box_in || (in_y >= ry0 && in_y < ry1);
+        const uint8_t* tap = row;
+        for (int ix = 0; ix < nx; ++ix, tap += PIX::BYTES) {
+            const int in_x = b0 + ix;
+            const float in_fx = (float)in_x - uvx;
             const float dr = in_fx * in_fx * ea + in_fx * in_fy2 + in_fy3;
             const float k = bc2(sqrtf(dr), P);                         // cylindrical filtering
             if (k == 0.0f) continue;
             float px[C];
-            if (row_in && in_x >= rx0 && in_x < rx1) {
-                const uint8_t* tap = row + in_x * (long long)PIX::BYTES;
+            if (box_in || (row_in && in_x >= rx0 && in_x < rx1)) {
                 if (vec) PIX::load_vec(tap, px); else PIX::load_bytes(tap, px);
             } else {
                 #pragma unroll
