@@ -62,6 +62,16 @@ class QuatTrack(C.Structure):
     _fields_ = [("ts_us", C.POINTER(C.c_int64)), ("quats", C.POINTER(C.c_double)), ("n", C.c_size_t)]
 
 
+class KeyframeTrack(C.Structure):
+    """gf_keyframe_track: one KeyframeManager track (keyframes.rs:83-90): ascending keys in us, value and easing (0..3) per key."""
+    _fields_ = [("ts_us", C.POINTER(C.c_int64)), ("value", C.POINTER(C.c_double)), ("easing", C.POINTER(C.c_uint8)), ("n", C.c_size_t)]
+
+
+KEYFRAME_TYPES = {"Fov": 0, "VideoRotation": 1, "ZoomingCenterX": 2, "ZoomingCenterY": 3, "BackgroundMargin": 4, "BackgroundFeather": 5,
+                  "LensCorrectionStrength": 6, "LightRefractionCoeff": 7}      # GF_KF_* / KeyframeType (keyframes.rs:27-72)
+EASING = {"NoEasing": 0, "EaseIn": 1, "EaseOut": 2, "EaseInOut": 3}             # keyframes.rs:74-81
+
+
 class ComputeParams(C.Structure):
     """gf_compute_params: the slice of ComputeParams (compute_params.rs:13-69) FrameTransform::at_timestamp reads."""
     _fields_ = [
@@ -85,6 +95,7 @@ class ComputeParams(C.Structure):
         ("focal_lengths", C.POINTER(C.c_double)), ("smoothed_focal_lengths", C.POINTER(C.c_double)), ("n_focal_lengths", C.c_size_t),
         ("readout_time_scale", C.c_double),
         ("camera_stab", C.c_void_p), ("n_camera_stab", C.c_size_t),
+        ("keyframes", KeyframeTrack * 8), ("keyframe_timestamp_scale", C.c_double),
     ]
 
 
@@ -192,7 +203,9 @@ EXPORTS = [
                                                       C.c_void_p, _P(C.c_size_t), _P(C.c_double), _P(C.c_double), C.c_void_p]),
     ("gf_table_flags_host", C.c_uint32, [C.c_void_p, C.c_size_t]),
     ("gf_get_frame_transform_at", C.c_int, [_P(StabConfig), _P(ComputeParams), _P(BufferDesc), _P(BufferDesc), C.c_void_p, C.c_size_t,
-                                            C.c_size_t, C.c_double, _P(KernelParams)]),
+                                            C.c_double, C.c_size_t, C.c_double, _P(KernelParams)]),
+    ("gf_abi_struct_size", C.c_size_t, [C.c_int]),
+    ("gf_keyframe_value_at", C.c_int, [C.c_void_p, C.c_double, C.c_double, _P(C.c_double)]),
     ("gf_cuda_queue_create", C.c_int, [_P(C.c_void_p), _P(QueueConfig), _P(ComputeParams), _P(BufferDesc), _P(BufferDesc)]),
     ("gf_cuda_queue_submit", C.c_int, [C.c_void_p, C.c_size_t, C.c_double, _P(BufferDesc), _P(BufferDesc), C.c_void_p, C.c_size_t]),
     ("gf_cuda_queue_wait", C.c_int, [C.c_void_p, _P(C.c_size_t), _P(C.c_uint64)]),

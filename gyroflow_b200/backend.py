@@ -228,9 +228,10 @@ class ComputeParams:
     def __init__(self, kernel_params: abi.KernelParams, org, smoothed, frame_readout_time_ms=16.0, fovs=None, video_rotation=0.0,
                  horizontal=False, inverted=False, framebuffer_inverted=False, fov_scale=1.0, sync_offsets=None,
                  per_frame_time_offsets=None, focal_lengths=None, smoothed_focal_lengths=None, readout_time_scale=0.0, camera_stab=None,
-                 gyro_offset_ms=0.0):
+                 gyro_offset_ms=0.0, keyframes=None, keyframe_timestamp_scale=0.0):
         """sync_offsets: {timestamp_us: offset_ms} (GyroSource::offsets_adjusted); camera_stab: list (one per frame) of dicts with
-        offset, sensor_size, crop_area, pixel_pitch, ibis=(pos[n], xyz[n,3]), ois=(pos[n], xyz[n,3]) (CameraStabData)."""
+        offset, sensor_size, crop_area, pixel_pitch, ibis=(pos[n], xyz[n,3]), ois=(pos[n], xyz[n,3]) (CameraStabData);
+        keyframes: {KeyframeType name: [(timestamp_us, value, easing name), ...]} for the types at_timestamp reads (abi.KEYFRAME_TYPES)."""
         p = kernel_params
         c = abi.ComputeParams()
         c.width, c.height, c.output_width, c.output_height = p.width, p.height, p.output_width, p.output_height
@@ -273,6 +274,16 @@ class ComputeParams:
             c.focal_lengths = self._fl.ctypes.data_as(C.POINTER(C.c_double)); c.smoothed_focal_lengths = self._sfl.ctypes.data_as(C.POINTER(C.c_double))
             c.n_focal_lengths = self._fl.size
         c.readout_time_scale = readout_time_scale
+        c.keyframe_timestamp_scale = keyframe_timestamp_scale
+        self._kf_arrays = []
+        for name, keys in (keyframes or {}).items():
+            keys = sorted(keys)
+            ts = np.asarray([k[0] for k in keys], dtype=np.int64); val = np.asarray([k[1] for k in keys], dtype=np.float64)
+            ea = np.asarray([abi.EASING[k[2]] if len(k) > 2 else abi.EASING["EaseInOut"] for k in keys], dtype=np.uint8)
+            self._kf_arrays += [ts, val, ea]
+            t = c.keyframes[abi.KEYFRAME_TYPES[name]]
+            t.ts_us = ts.ctypes.data_as(C.POINTER(C.c_int64)); t.value = val.ctypes.data_as(C.POINTER(C.c_double))
+            t.easing = ea.ctypes.data_as(C.POINTER(C.c_uint8)); t.n = len(keys)
         if camera_stab:
             self._stab_arrays = []
             arr = (abi.CameraStab * len(camera_stab))()
@@ -427,12 +438,12 @@ def stab_config(params: abi.KernelParams, pixel_type: str, digital_lens=None, ba
     return st
 
 
-def get_frame_transform_at(stab: abi.StabConfig, cp: ComputeParams, buffers: Buffers, kernel_params: abi.KernelParams, mesh=None, frame=0, minimal_fov=1.0):
+def get_frame_transform_at(stab: abi.StabConfig, cp: ComputeParams, buffers: Buffers, kernel_params: abi.KernelParams, mesh=None, frame=0, minimal_fov=1.0, timestamp_ms=0.0):
     """Stabilization::get_frame_transform_at (stabilization/mod.rs:253-326): completes `kernel_params` (as produced by at_timestamp) in place."""
     i, o = buffers.input.to_c(), buffers.output.to_c()
     m = None if mesh is None else np.ascontiguousarray(mesh, dtype=np.float32)
     rc = abi.load_library().gf_get_frame_transform_at(C.byref(stab), C.byref(cp.c), C.byref(i), C.byref(o), m.ctypes.data if m is not None and m.size else None,
-                                                      m.size if m is not None else 0, frame, minimal_fov, C.byref(kernel_params))
+                                                      m.size if m is not None else 0, float(timestamp_ms), frame, minimal_fov, C.byref(kernel_params))
     if rc != 0:
         raise GyroflowCoreError(rc, "gf_get_frame_transform_at")
     return kernel_params

@@ -364,6 +364,13 @@ GF_API int gf_cuda_supports(const gf_buffer_desc* in, const gf_buffer_desc* out)
 }
 
 GF_API const char* gf_cuda_version(void) { return "gyroflow-b200 0.1 (sm_100a)"; }
+GF_API size_t gf_abi_struct_size(int which) {
+    switch (which) {
+    case 0: return sizeof(gf_kernel_params);  case 1: return sizeof(gf_buffer_desc);    case 2: return sizeof(gf_compute_params);
+    case 3: return sizeof(gf_camera_stab);    case 4: return sizeof(gf_keyframe_track); case 5: return sizeof(gf_stab_config);
+    case 6: return sizeof(gf_queue_config);   default: return 0;
+    }
+}
 GF_API const char* gf_cuda_backend_name(void) { return "CUDA"; }
 
 GF_API int gf_lens_from_name(const char* id) {

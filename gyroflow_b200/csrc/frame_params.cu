@@ -39,7 +39,7 @@ void get_rect(const gf_buffer_desc* d, int32_t (&r)[4]) {                      /
 } // namespace
 
 extern "C" GF_API int gf_get_frame_transform_at(const gf_stab_config* st, const gf_compute_params* cp, const gf_buffer_desc* in, const gf_buffer_desc* out,
-                                                const float* mesh, size_t mesh_len, size_t frame, double minimal_fov, gf_kernel_params* kp) {
+                                                const float* mesh, size_t mesh_len, double timestamp_ms, size_t frame, double minimal_fov, gf_kernel_params* kp) {
     if (!st || !cp || !in || !out || !kp) return GF_ERR_BAD_PARAMS;
     int count = 0, sbytes = 0; float maxv = 0.0f; bool has_max = false;
     if (!pixel_info(st->pixel_type, &count, &sbytes, &maxv, &has_max)) return GF_ERR_BAD_PARAMS;
@@ -94,9 +94,11 @@ extern "C" GF_API int gf_get_frame_transform_at(const gf_stab_config* st, const 
         kp->ewa_coeffs_q[3] = (-1.0f * b - 6.0f * c) / 6.0f;
     }
 
-    float sa_fov = 1.0f;                                                        // :297-308 (the Fov keyframe value arrives in cp->fov_scale)
+    float sa_fov = 1.0f;                                                        // :297-308
     if (st->show_safe_area || cp->fov_overview) {
-        const float fov = (float)cp->fov_scale;
+        double kf_fov = cp->fov_scale;                                          // keyframes.value_at_video_timestamp(Fov, ts).unwrap_or(fov_scale)
+        (void)gf_keyframe_value_at(&cp->keyframes[GF_KF_FOV], timestamp_ms, cp->keyframe_timestamp_scale, &kf_fov);
+        const float fov = (float)kf_fov;
         if (cp->fov_overview) sa_fov = (st->adaptive_zoom_window == 0.0 ? 1.0f : 1.0f / fov) + 1.0f;
         else                  sa_fov = fov / (st->adaptive_zoom_window == 0.0 ? (float)minimal_fov : 1.0f);
     }

@@ -135,9 +135,46 @@ __global__ void frame_rows_kernel(const __grid_constant__ RowCtx C, size_t rows,
     }
 }
 
-// get_fov — frame_transform.rs:52-58 (the Fov keyframe value, if any, arrives in cp->fov_scale)
-double get_fov(const gf_compute_params* cp, size_t frame, bool use_fovs, bool for_ui) {
-    double fov_scale = cp->fov_scale;
+// KeyframeManager::value_at_video_timestamp for one track — keyframes.rs:169-205 (without the custom_provider closure).
+// Easing::get (keyframes.rs:279-291, sic: "b_in -> EaseOut", "a_out -> EaseIn") and Easing::interpolate (:292-302) with
+// simple_easing 1.0.2's sine_in / sine_out / sine_in_out — easings.net: 1 - cos(x PI / 2), sin(x PI / 2), -(cos(PI x) - 1) / 2 — in f32
+// through libm's cosf / sinf, like Rust's f32::cos / f32::sin on Linux.
+bool keyframe_value(const gf_keyframe_track& t, double timestamp_ms, double scale, double* out) {
+    if (!t.ts_us || !t.value || t.n == 0) return false;
+    if (t.n == 1) { *out = t.value[0]; return true; }
+    const double sc = scale != 0.0 ? scale : 1.0;
+    const double r = round(timestamp_ms * 1000.0 * sc);                                        // f64::round, then `as i64` (saturating, NaN -> 0)
+    const int64_t timestamp_us = r != r ? 0 : (r >= 9223372036854775807.0 ? INT64_MAX : (r <= -9223372036854775808.0 ? INT64_MIN : (int64_t)r));
+    const int64_t first = t.ts_us[0], last = t.ts_us[t.n - 1];
+    int64_t lookup = timestamp_us < last ? timestamp_us : last; if (lookup < first) lookup = first;     // .min(last_ts).max(first_ts)
+    size_t lo = 0, hi = t.n;                                                                   // range(..=lookup).next_back(): last key <= lookup
+    while (lo < hi) { const size_t mid = (lo + hi) / 2; if (t.ts_us[mid] <= lookup) lo = mid + 1; else hi = mid; }
+    if (lo == 0) return false;
+    const size_t i1 = lo - 1;
+    if (t.ts_us[i1] == lookup) { *out = t.value[i1]; return true; }
+    if (i1 + 1 >= t.n) return false;                                                           // range(lookup..).next()
+    const size_t i2 = i1 + 1;
+    const double time_delta = (double)(t.ts_us[i2] - t.ts_us[i1]);
+    double x = (double)(timestamp_us - t.ts_us[i1]) / time_delta;
+    const int ea = t.easing ? t.easing[i1] : 0, eb = t.easing ? t.easing[i2] : 0;
+    const bool a_out = ea == 2 || ea == 3, b_in = eb == 1 || eb == 3;
+    const int e = (a_out && b_in) ? 3 : (b_in ? 2 : (a_out ? 1 : 0));
+    const float xf = (float)x, PI_F = 3.14159265358979323846f;
+    if (e == 1)      x = (double)(1.0f - cosf(xf * PI_F / 2.0f));
+    else if (e == 2) x = (double)sinf(xf * PI_F / 2.0f);
+    else if (e == 3) x = (double)(-(cosf(PI_F * xf) - 1.0f) / 2.0f);
+    *out = t.value[i1] * (1.0 - x) + t.value[i2] * x;
+    return true;
+}
+// `params.keyframes.value_at_video_timestamp(typ, ts).unwrap_or(default)`
+double keyframed(const gf_compute_params* cp, int typ, double timestamp_ms, double dflt) {
+    double v;
+    return keyframe_value(cp->keyframes[typ], timestamp_ms, cp->keyframe_timestamp_scale, &v) ? v : dflt;
+}
+
+// get_fov — frame_transform.rs:52-58
+double get_fov(const gf_compute_params* cp, size_t frame, bool use_fovs, double timestamp_ms, bool for_ui) {
+    double fov_scale = keyframed(cp, GF_KF_FOV, timestamp_ms, cp->fov_scale);
     fov_scale += (cp->fov_overview && use_fovs && !for_ui) ? 1.0 : 0.0;
     double fov = 1.0;
     if (use_fovs) {
@@ -178,9 +215,17 @@ struct StabPoints { Spline3 ibis, ois; };
 size_t prepare(const gf_compute_params* cp, double timestamp_ms, size_t frame, const Track& org, const Track& smoothed_host,
                const SyncOffsets& host_offsets, const StabPoints* stab_points,
                RowCtx& C, gf_kernel_params* kp, double* out_fov, double* out_minimal_fov) {
+    // ----------- Keyframes :167-174 (evaluated at the frame's own timestamp, before per_frame_time_offsets) -----------
+    const double video_rotation = keyframed(cp, GF_KF_VIDEO_ROTATION, timestamp_ms, cp->video_rotation);
+    const double background_margin = keyframed(cp, GF_KF_BACKGROUND_MARGIN, timestamp_ms, cp->background_margin);
+    const double background_feather = keyframed(cp, GF_KF_BACKGROUND_FEATHER, timestamp_ms, cp->background_margin_feather);
+    const double lens_correction_amount = keyframed(cp, GF_KF_LENS_CORRECTION_STRENGTH, timestamp_ms, cp->lens_correction_amount);
+    const double zoom_center_x = keyframed(cp, GF_KF_ZOOMING_CENTER_X, timestamp_ms, cp->adaptive_zoom_center_offset[0]);
+    const double zoom_center_y = keyframed(cp, GF_KF_ZOOMING_CENTER_Y, timestamp_ms, cp->adaptive_zoom_center_offset[1]);
+    const double light_refraction_coefficient = keyframed(cp, GF_KF_LIGHT_REFRACTION_COEFF, timestamp_ms, cp->light_refraction_coefficient);
     const double fl_compensation = focal_length_fov_compensation(cp, frame);                                              // :190
-    double fov = get_fov(cp, frame, true, false) * fl_compensation;                                                       // :191
-    double ui_fov = get_fov(cp, frame, true, true);
+    double fov = get_fov(cp, frame, true, timestamp_ms, false) * fl_compensation;                                         // :191
+    double ui_fov = get_fov(cp, frame, true, timestamp_ms, true);
     if (cp->has_optimal_fov) { if (cp->n_fovs == 0) fov *= cp->lens_optimal_fov; else ui_fov /= cp->lens_optimal_fov; }   // :193-199
     const double* K = cp->camera_matrix;
     const double hr = cp->input_horizontal_stretch > 0.01 ? cp->input_horizontal_stretch : 1.0;                          // :38
@@ -196,7 +241,7 @@ size_t prepare(const gf_compute_params* cp, double timestamp_ms, size_t frame, c
     const double start_ts = timestamp_ms - frame_readout_time / 2.0;                                                      // :225
     const size_t rows = fabs(frame_readout_time) > 0.0 ? n : 1;                                                           // :247
 
-    const double a = cp->video_rotation * (M_PI / 180.0);
+    const double a = video_rotation * (M_PI / 180.0);
     const Quat quat1 = qinv(quat_at_timestamp(org, cp->duration_ms, host_offsets, timestamp_ms));                         // :243
     const Quat sq1 = quat_at_timestamp(smoothed_host, cp->duration_ms, host_offsets, timestamp_ms);                       // :244
     C.org = org; C.duration_ms = cp->duration_ms; C.offsets = host_offsets;
@@ -227,18 +272,18 @@ size_t prepare(const gf_compute_params* cp, double timestamp_ms, size_t frame, c
         for (int i = 0; i < 12; ++i) kp->k[i] = (float)cp->distortion_coeffs[i];
         kp->fov = (float)fov;
         kp->r_limit = (float)cp->radial_distortion_limit;
-        kp->lens_correction_amount = (float)cp->lens_correction_amount;
+        kp->lens_correction_amount = (float)lens_correction_amount;
         kp->input_vertical_stretch = (float)(cp->input_vertical_stretch > 0.01 ? cp->input_vertical_stretch : 1.0);
         kp->input_horizontal_stretch = (float)hr;
         kp->background_mode = cp->background_mode;
-        kp->background_margin = (float)cp->background_margin;
-        kp->background_margin_feather = (float)cp->background_margin_feather;
-        double zy = cp->adaptive_zoom_center_offset[1];
+        kp->background_margin = (float)background_margin;
+        kp->background_margin_feather = (float)background_feather;
+        double zy = zoom_center_y;
         if (cp->framebuffer_inverted) zy *= -1.0;                                                                         // :318-320
-        kp->translation2d[0] = (float)(cp->adaptive_zoom_center_offset[0] * (double)cp->width / fov);
+        kp->translation2d[0] = (float)(zoom_center_x * (double)cp->width / fov);
         kp->translation2d[1] = (float)(zy * (double)cp->height / fov);
         for (int i = 0; i < cp->n_digital_lens_params && i < 16; ++i) kp->digital_lens_params[i] = (float)cp->digital_lens_params[i];
-        kp->light_refraction_coefficient = (float)cp->light_refraction_coefficient;
+        kp->light_refraction_coefficient = (float)light_refraction_coefficient;
     }
     if (out_fov) *out_fov = ui_fov;                                                                                       // :345
     if (out_minimal_fov) *out_minimal_fov = frame < cp->n_minimal_fovs ? cp->minimal_fovs[frame] : 1.0;                   // :346
@@ -254,6 +299,13 @@ SyncOffsets host_offsets_of(const gf_compute_params* cp) {
 #include "gyro_dev.h"
 
 extern "C" {
+
+GF_API int gf_keyframe_value_at(const gf_keyframe_track* track, double timestamp_ms, double timestamp_scale, double* out) {
+    double v;
+    if (!track || !keyframe_value(*track, timestamp_ms, timestamp_scale, &v)) return 0;
+    if (out) *out = v;
+    return 1;
+}
 
 GF_API int gf_frame_transform_at_timestamp(const gf_compute_params* cp, double timestamp_ms, size_t frame,
                                            gf_kernel_params* out_params, float* out_matrices, size_t max_rows,

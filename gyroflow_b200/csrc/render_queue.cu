@@ -155,7 +155,7 @@ GF_API int gf_cuda_queue_create(gf_cuda_queue** out, const gf_queue_config* cfg,
     // a template KernelParams good enough for gf_cuda_create's validation (sizes, strides, interpolation, pixel size)
     gf_kernel_params kp; memset(&kp, 0, sizeof(kp));
     kp.matrix_count = 1;
-    rc = gf_get_frame_transform_at(&cfg->stab, cp, in_proto, out_proto, nullptr, 0, 0, 1.0, &kp);
+    rc = gf_get_frame_transform_at(&cfg->stab, cp, in_proto, out_proto, nullptr, 0, 0.0, 0, 1.0, &kp);
     if (rc != GF_OK) return bail(rc);
     q->max_rows = (size_t)(cp->width > cp->height ? cp->width : cp->height);
     q->slots.resize((size_t)cfg->depth);
@@ -191,7 +191,7 @@ GF_API int gf_cuda_queue_submit(gf_cuda_queue* q, size_t frame, double timestamp
                                                  &rows, &fov, &minimal_fov, (void*)s.stream);
     if (rc != GF_OK) { nvtxRangePop(); return qfail(q, rc, "gf_cuda_frame_transform_dev_flagged failed"); }
     q->launches++;
-    rc = gf_get_frame_transform_at(&q->cfg.stab, &q->cp, in, out, mesh, mesh_len, frame, minimal_fov, &kp);
+    rc = gf_get_frame_transform_at(&q->cfg.stab, &q->cp, in, out, mesh, mesh_len, timestamp_ms, frame, minimal_fov, &kp);
     if (rc != GF_OK) { nvtxRangePop(); return qfail(q, rc, "gf_get_frame_transform_at failed"); }
     const float* mesh_dev = nullptr;
     if (mesh && mesh_len) {

@@ -202,6 +202,9 @@ GF_API int         gf_cuda_device_count(void);
 GF_API int         gf_cuda_device_name(int device, char* buf, size_t buf_len);   /* "[CUDA] NVIDIA B200" style name */
 GF_API int         gf_cuda_supports(const gf_buffer_desc* in, const gf_buffer_desc* out); /* is_buffer_supported opencl.rs:451 */
 GF_API const char* gf_cuda_version(void);
+/* sizeof() of the structs that cross this ABI, for binding generators and their tests: 0 gf_kernel_params, 1 gf_buffer_desc,
+ * 2 gf_compute_params, 3 gf_camera_stab, 4 gf_keyframe_track, 5 gf_stab_config, 6 gf_queue_config; 0 for any other index. */
+GF_API size_t gf_abi_struct_size(int which);
 
 /* ---- lens plugin surface: DistortionModel::from_name / id  distortion_models/mod.rs:79-90 -- */
 GF_API int         gf_lens_from_name(const char* id);     /* unknown -> GF_LENS_OPENCV_FISHEYE, like from_name's default */
@@ -341,6 +344,17 @@ typedef struct gf_quat_track {          /* TimeQuat = BTreeMap<i64 us, UnitQuate
     size_t         n;
 } gf_quat_track;
 
+/* One KeyframeManager track (src/core/keyframes.rs:83-90, the BTreeMap<i64, Keyframe> of one KeyframeType): keys ascending in
+ * microseconds, easing per key (keyframes.rs:74-81: 0 NoEasing, 1 EaseIn, 2 EaseOut, 3 EaseInOut).  A custom_provider closure
+ * (keyframes.rs:112, :170-176) has no C form: bake it into a track on the Rust side. */
+typedef struct gf_keyframe_track { const int64_t* ts_us; const double* value; const uint8_t* easing; size_t n; } gf_keyframe_track;
+enum { GF_KF_FOV = 0, GF_KF_VIDEO_ROTATION, GF_KF_ZOOMING_CENTER_X, GF_KF_ZOOMING_CENTER_Y, GF_KF_BACKGROUND_MARGIN, GF_KF_BACKGROUND_FEATHER,
+       GF_KF_LENS_CORRECTION_STRENGTH, GF_KF_LIGHT_REFRACTION_COEFF, GF_KF_COUNT };
+/* KeyframeManager::value_at_video_timestamp (keyframes.rs:169-205) for one track: returns 1 and writes *out for Some(value), 0 for None.
+ * Between two keys the value is eased with Easing::get / Easing::interpolate (keyframes.rs:279-303; simple_easing 1.0.2 sine_in /
+ * sine_out / sine_in_out in f32). */
+GF_API int gf_keyframe_value_at(const gf_keyframe_track* track, double timestamp_ms, double timestamp_scale, double* out);
+
 typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_params.rs:13-69) + lens data at_timestamp reads */
     int32_t width, height, output_width, output_height;
     double  camera_matrix[9];           /* row-major, already scaled to the frame (get_lens_data_at_timestamp :95-160) */
@@ -372,6 +386,9 @@ typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_p
     double  readout_time_scale;                                  /* capture_area_size.1 / sensor_size_px.1 of the lens_params entry closest
                                                                   * to the timestamp (get_frame_readout_time :26-29); 0 = none (1.0) */
     const struct gf_camera_stab* camera_stab; size_t n_camera_stab;   /* file_metadata.camera_stab_data, one entry per frame (:227-236, :269-287) */
+    /* keyframed scalars at_timestamp evaluates per frame (frame_transform.rs:53, :167-174): a track with n > 0 replaces the constant above */
+    gf_keyframe_track keyframes[GF_KF_COUNT];
+    double  keyframe_timestamp_scale;                            /* KeyframeManager::timestamp_scale; 0 = None (1.0) */
 } gf_compute_params;
 
 /* CameraStabData (src/core/gyro_source/file_metadata.rs:41-48): IBIS / OIS motion of one frame as Catmull-Rom splines over the
@@ -465,7 +482,8 @@ typedef struct gf_stab_config {            /* the fields of `Stabilization` the 
     double  adaptive_zoom_window;          /* compute_params.adaptive_zoom_window */
 } gf_stab_config;
 GF_API int gf_get_frame_transform_at(const gf_stab_config* stab, const gf_compute_params* cp, const gf_buffer_desc* in, const gf_buffer_desc* out,
-                                     const float* mesh, size_t mesh_len, size_t frame, double minimal_fov, gf_kernel_params* kp);
+                                     const float* mesh, size_t mesh_len, double timestamp_ms, size_t frame, double minimal_fov, gf_kernel_params* kp);
+/* timestamp_ms: the frame's video timestamp — only the Fov keyframe of the safe-area rectangle reads it (mod.rs:299). */
 
 /* ------------------------------------------------------------------------------------------
  * Frame-sharded render queue (the shape of rendering/mod.rs:451,531-542,657-661 with rendering/render_queue.rs:550-612

@@ -168,3 +168,47 @@ def identity_matrices(p, rows=1):
     return m
 
 
+
+
+# ---- KeyframeManager::value_at_video_timestamp for one track: keyframes.rs:169-205, Easing::get / interpolate :279-303 ----
+def _easing_get(a, b):                       # keyframes.rs:279-291 (names as in the enum :74-81)
+    a_out = a in ("EaseOut", "EaseInOut")
+    b_in = b in ("EaseIn", "EaseInOut")
+    if a_out and b_in: return "EaseInOut"
+    if b_in: return "EaseOut"
+    if a_out: return "EaseIn"
+    return "NoEasing"
+
+
+def _easing_interpolate(e, a, b, x):         # keyframes.rs:292-302; simple_easing 1.0.2 (easings.net sine family) on f32
+    import ctypes, ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.cosf.restype = ctypes.c_float; libm.cosf.argtypes = [ctypes.c_float]
+    libm.sinf.restype = ctypes.c_float; libm.sinf.argtypes = [ctypes.c_float]
+    f = np.float32
+    xf = f(x); pi = f(math.pi)
+    if e == "EaseIn":      x = float(f(1.0) - f(libm.cosf(float(xf * pi / f(2.0)))))
+    elif e == "EaseOut":   x = float(f(libm.sinf(float(xf * pi / f(2.0)))))
+    elif e == "EaseInOut": x = float(-(f(libm.cosf(float(pi * xf))) - f(1.0)) / f(2.0))
+    return a * (1.0 - x) + b * x
+
+
+def keyframe_value_at(keys, timestamp_ms, timestamp_scale=None):
+    """keys: [(timestamp_us, value, easing name)] in any order (a BTreeMap in the reference).  Returns the value or None."""
+    keys = sorted(keys)
+    if len(keys) == 0: return None
+    if len(keys) == 1: return keys[0][1]
+    first_ts, last_ts = keys[0][0], keys[-1][0]
+    t = timestamp_ms * 1000.0 * (timestamp_scale if timestamp_scale is not None else 1.0)
+    timestamp_us = int(math.copysign(math.floor(abs(t) + 0.5), t))            # f64::round (half away from zero) as i64
+    lookup_ts = max(min(timestamp_us, last_ts), first_ts)
+    below = [k for k in keys if k[0] <= lookup_ts]
+    if not below: return None
+    o1 = below[-1]
+    if o1[0] == lookup_ts: return o1[1]
+    above = [k for k in keys if k[0] >= lookup_ts]
+    if not above: return None
+    o2 = above[0]
+    time_delta = float(o2[0] - o1[0])
+    alpha = float(timestamp_us - o1[0]) / time_delta
+    return _easing_interpolate(_easing_get(o1[2], o2[2]), o1[1], o2[1], alpha)

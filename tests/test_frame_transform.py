@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import gyroflow_b200 as g
-from gyroflow_b200 import synth
+from gyroflow_b200 import abi, synth
 from tests import cases, np_producer
 
 
@@ -161,3 +161,94 @@ def test_get_frame_transform_at_matches_python_template():
     bufs = g.Buffers(g.BufferDescription((800, 400, 3200), src, rect=(40, 20, 640, 360), rotation=90.0), g.BufferDescription((640, 360, want.output_stride), src))
     g.get_frame_transform_at(g.stab_config(want, "RGBA8"), cp, bufs, kp)
     assert list(kp.source_rect) == [40, 20, 640, 360] and kp.input_rotation == 90.0 and (kp.flags & 32) and not (kp.flags & 64) and kp.stride == 3200
+
+
+def _random_track(rng, n, span_us=4_000_000):
+    ts = sorted(int(t) for t in rng.choice(span_us, size=n, replace=False))
+    names = list(abi.EASING)
+    return [(t, float(rng.uniform(-3.0, 3.0)), names[int(rng.integers(0, 4))]) for t in ts]
+
+
+def test_keyframe_value_matches_numpy_restatement():
+    """gf_keyframe_value_at == KeyframeManager::value_at_video_timestamp restated in tests/np_producer.py (keyframes.rs:169-205, easing
+    :279-303): empty / single-key tracks, before the first and after the last key, exactly on a key, all 16 easing pairs, a timestamp scale."""
+    import ctypes as C
+    lib = g.load_library()
+    rng = np.random.default_rng(11)
+
+    def c_value(keys, ts_ms, scale):
+        keys = sorted(keys)
+        ts = np.asarray([k[0] for k in keys], dtype=np.int64); val = np.asarray([k[1] for k in keys], dtype=np.float64)
+        ea = np.asarray([abi.EASING[k[2]] for k in keys], dtype=np.uint8)
+        t = abi.KeyframeTrack(ts.ctypes.data_as(C.POINTER(C.c_int64)), val.ctypes.data_as(C.POINTER(C.c_double)), ea.ctypes.data_as(C.POINTER(C.c_uint8)), len(keys))
+        out = C.c_double(123.0)
+        ok = lib.gf_keyframe_value_at(C.byref(t), ts_ms, scale if scale is not None else 0.0, C.byref(out))
+        return out.value if ok else None
+
+    assert c_value([], 100.0, None) is None and np_producer.keyframe_value_at([], 100.0) is None
+    assert lib.gf_keyframe_value_at(None, 1.0, 0.0, None) == 0
+    assert c_value([(500_000, 2.5, "EaseIn")], -7.0, None) == 2.5 == np_producer.keyframe_value_at([(500_000, 2.5, "EaseIn")], -7.0)
+    for ea in abi.EASING:                                     # all 16 (left, right) easing pairs
+        for eb in abi.EASING:
+            keys = [(1_000_000, -1.0, ea), (3_000_000, 2.0, eb)]
+            for ts_ms in (0.0, 1000.0, 1000.0005, 1234.567, 2000.0, 2999.9996, 3000.0, 9000.0):
+                assert c_value(keys, ts_ms, None) == np_producer.keyframe_value_at(keys, ts_ms), (ea, eb, ts_ms)
+    for _ in range(40):                                       # random tracks, with and without timestamp_scale
+        keys = _random_track(rng, int(rng.integers(2, 9)))
+        scale = None if rng.random() < 0.5 else float(rng.uniform(0.5, 2.0))
+        for ts_ms in rng.uniform(-200.0, 4400.0, size=25):
+            assert c_value(keys, float(ts_ms), scale) == np_producer.keyframe_value_at(keys, float(ts_ms), scale), (keys, ts_ms, scale)
+
+
+def test_keyframed_producer_equals_constants_at_the_keyframe_values():
+    """at_timestamp with keyframe tracks (frame_transform.rs:53, :167-174) == at_timestamp of a ComputeParams whose constants are the values
+    the restated KeyframeManager gives at that timestamp: video rotation, zoom centre, margins, lens-correction strength, refraction, FOV —
+    byte-identical KernelParams and matrices; get_frame_transform_at reads the Fov track for the safe-area rectangle (mod.rs:299)."""
+    p = synth.base_kernel_params(640, 360)
+    org, sm = cases.gyro()
+    rng = np.random.default_rng(5)
+    tracks = {name: _random_track(rng, 4) for name in abi.KEYFRAME_TYPES}
+    tracks["Fov"] = [(t, 1.0 + abs(v) * 0.2, e) for t, v, e in tracks["Fov"]]
+    tracks["LensCorrectionStrength"] = [(t, min(abs(v) / 3.0, 1.0), e) for t, v, e in tracks["LensCorrectionStrength"]]
+    tracks["LightRefractionCoeff"] = [(t, 1.0 + abs(v) * 0.1, e) for t, v, e in tracks["LightRefractionCoeff"]]
+    fovs = [1.1, 1.2, 1.3]
+    for fbi in (False, True):
+        cp = g.ComputeParams(p, org, sm, frame_readout_time_ms=16.0, fovs=fovs, keyframes=tracks, framebuffer_inverted=fbi, fov_scale=1.7, video_rotation=3.0)
+        for frame, ts in enumerate((150.0, 1700.0, 3999.0)):
+            v = {name: np_producer.keyframe_value_at(tracks[name], ts) for name in tracks}
+            ref = g.ComputeParams(p, org, sm, frame_readout_time_ms=16.0, fovs=fovs, framebuffer_inverted=fbi, fov_scale=v["Fov"], video_rotation=v["VideoRotation"])
+            ref.c.adaptive_zoom_center_offset[0] = v["ZoomingCenterX"]; ref.c.adaptive_zoom_center_offset[1] = v["ZoomingCenterY"]
+            ref.c.background_margin = v["BackgroundMargin"]; ref.c.background_margin_feather = v["BackgroundFeather"]
+            ref.c.lens_correction_amount = v["LensCorrectionStrength"]; ref.c.light_refraction_coefficient = v["LightRefractionCoeff"]
+            kp, m, fov, mfov = cp.at_timestamp(ts, frame)
+            kp2, m2, fov2, mfov2 = ref.at_timestamp(ts, frame)
+            assert bytes(kp) == bytes(kp2) and np.array_equal(m, m2) and fov == fov2 and mfov == mfov2
+            assert kp.lens_correction_amount == np.float32(v["LensCorrectionStrength"]) and kp.background_margin == np.float32(v["BackgroundMargin"])
+            # safe-area rectangle of get_frame_transform_at: the Fov track, not fov_scale
+            bufs = g.Buffers(g.BufferDescription((640, 360, 640 * 4), np.zeros(1, np.uint8)), g.BufferDescription((640, 360, 640 * 4), np.zeros(1, np.uint8)))
+            st = g.stab_config(p, "RGBA8"); st.show_safe_area = 1; st.adaptive_zoom_window = 1.0
+            a = g.get_frame_transform_at(st, cp, bufs, abi.KernelParams.from_buffer_copy(bytes(kp)), timestamp_ms=ts)
+            b = g.get_frame_transform_at(st, ref, bufs, abi.KernelParams.from_buffer_copy(bytes(kp2)), timestamp_ms=ts)
+            assert list(a.safe_area_rect) == list(b.safe_area_rect) and a.safe_area_rect[0] != 0.0
+
+
+@pytest.mark.gpu
+def test_device_producer_with_keyframes_matches_host():
+    """The device producer evaluates the same keyframe tracks as the host producer: identical KernelParams, tables within 1 ulp."""
+    import torch
+    w, h = 640, 360
+    p = synth.base_kernel_params(w, h)
+    org, sm = cases.gyro()
+    rng = np.random.default_rng(9)
+    tracks = {"VideoRotation": _random_track(rng, 5), "ZoomingCenterX": [(t, v * 0.05, e) for t, v, e in _random_track(rng, 3)],
+              "Fov": [(t, 1.0 + abs(v) * 0.1, e) for t, v, e in _random_track(rng, 4)], "LensCorrectionStrength": [(0, 1.0, "EaseOut"), (4_000_000, 0.3, "EaseIn")]}
+    cp = g.ComputeParams(p, org, sm, keyframes=tracks)
+    dg = g.DeviceGyro(cp)
+    mats = torch.zeros((h, 14), dtype=torch.float32, device="cuda")
+    for ts in (10.0, 900.0, 2600.0, 3990.0):
+        kp, rows = dg.frame_transform(ts, mats.data_ptr(), h)
+        torch.cuda.synchronize()
+        kp2, want, _, _ = cp.at_timestamp(ts)
+        assert bytes(kp) == bytes(kp2) and rows == h
+        assert float(ulp_diff(mats.cpu().numpy()[:, :9], want[:, :9]).max()) <= 1.0
+    dg.close()
