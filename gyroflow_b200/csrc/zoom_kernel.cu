@@ -30,6 +30,11 @@ __host__ __device__ inline ZQuat zq_mul(const ZQuat& a, const ZQuat& b) { return
 struct ZoomFrame {              // per-frame uniforms (host, f64)
     ZQuat q0;                   // smoothed(ts) * org(ts)^-1
     double start_ts;
+    // keyframed values of this frame (fov_iterative.rs:44-46, frame_transform.rs:354, cpu_undistort.rs:661); `keyed` = some track exists
+    int keyed;
+    double rot_c, rot_s;
+    float zc_x, zc_y, lrc;
+    int lc; float amount, factor, out_fx, out_fy;
 };
 struct ZoomArgs {
     gf_kernel_params kp;        // as built by undistort_points (:671-683)
@@ -164,11 +169,22 @@ constexpr int ZOOM_RECT_LEN = 120;
 constexpr int ZOOM_INTERP_LEN = 63;       // (30 + 1) * 3 - 30
 
 template <int LENS, int DIGITAL>
-__global__ void __launch_bounds__(128) find_fov_kernel(const ZoomArgs A, const ZoomFrame* __restrict__ frames, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) find_fov_kernel(const __grid_constant__ ZoomArgs A0, const ZoomFrame* __restrict__ frames, double* __restrict__ out) {
     __shared__ float rect[2 * ZOOM_RECT_LEN], poly[2 * ZOOM_RECT_LEN];
     __shared__ float sw, sh; __shared__ int sidx;
     const ZoomFrame F = frames[blockIdx.x];
     const int tid = threadIdx.x;
+    // keyframed clips: this frame's rotation / zoom centre / lens-correction strength / refraction replace the per-call values
+    __shared__ ZoomArgs SA;
+    if (F.keyed) {
+        if (tid == 0) {
+            SA = A0;
+            SA.rot_c = F.rot_c; SA.rot_s = F.rot_s; SA.zc_x = F.zc_x; SA.zc_y = F.zc_y; SA.kp.light_refraction_coefficient = F.lrc;
+            SA.lc = F.lc; SA.amount = F.amount; SA.factor = F.factor; SA.out_fx = F.out_fx; SA.out_fy = F.out_fy;
+        }
+        __syncthreads();
+    }
+    const ZoomArgs& A = F.keyed ? SA : A0;
     const float cx = A.in_w / 2.0f, cy = A.in_h / 2.0f;
     if (tid < ZOOM_RECT_LEN) {
         float x, y; rect_point(A, tid, x, y);
@@ -302,7 +318,7 @@ bool zoom_lens_noop(int lens, const float* k) {
 
 } // namespace
 
-// FrameTransform::get_fov without keyframes — frame_transform.rs:52-58
+// FrameTransform::get_fov — frame_transform.rs:52-58 (callers pass a ComputeParams whose fov_scale is already the Fov keyframe value)
 static double gf_points_fov(const gf_compute_params* cp, size_t frame, int use_fovs) {
     double fov_scale = cp->fov_scale;
     if (cp->fov_overview && use_fovs) fov_scale += 1.0;
@@ -361,13 +377,52 @@ static ZoomFrame frame_uniforms(const gf_compute_params& cp, double ts, double f
     const ZQuat q1 = qinv(quat_at_timestamp(horg, cp.duration_ms, ho, ts));
     f.q0 = zq_mul(quat_at_timestamp(hsm, cp.duration_ms, ho, ts), q1);
     f.start_ts = ts - frt / 2.0;
+    f.keyed = 0;
     return f;
+}
+// KeyframeManager::value_at_video_timestamp(...).unwrap_or(default) for one of the tracks in gf_compute_params
+static double zoom_keyframed(const gf_compute_params& cp, int typ, double ts, double dflt) {
+    double v = dflt;
+    (void)gf_keyframe_value_at(&cp.keyframes[typ], ts, cp.keyframe_timestamp_scale, &v);
+    return v;
+}
+// at_timestamp_for_points / undistort_points for ONE timestamp: the tracks they read become the constants of a private copy
+static gf_compute_params resolve_point_keyframes(const gf_compute_params& cp, double ts) {
+    gf_compute_params r = cp;
+    r.video_rotation = zoom_keyframed(cp, GF_KF_VIDEO_ROTATION, ts, cp.video_rotation);                                  // frame_transform.rs:354
+    r.light_refraction_coefficient = zoom_keyframed(cp, GF_KF_LIGHT_REFRACTION_COEFF, ts, cp.light_refraction_coefficient);   // cpu_undistort.rs:661
+    r.fov_scale = zoom_keyframed(cp, GF_KF_FOV, ts, cp.fov_scale);                                                       // get_fov :53
+    return r;
+}
+static bool zoom_any_keyframes(const gf_compute_params& cp) {
+    const int used[] = { GF_KF_VIDEO_ROTATION, GF_KF_ZOOMING_CENTER_X, GF_KF_ZOOMING_CENTER_Y, GF_KF_LENS_CORRECTION_STRENGTH, GF_KF_LIGHT_REFRACTION_COEFF };
+    for (int t : used) if (cp.keyframes[t].n > 0 && cp.keyframes[t].ts_us && cp.keyframes[t].value) return true;
+    return false;
+}
+// The values of frame `ts` that replace ZoomArgs' per-call ones (`A` supplies fx / fy / fov / sizes): video rotation
+// (frame_transform.rs:354), refraction (cpu_undistort.rs:661), zoom centre and lens-correction strength (fov_iterative.rs:44-46;
+// `lens_correction_default` = what the caller would have used without a track).
+static void fill_keyed(ZoomFrame& f, const gf_compute_params& cp, const ZoomArgs& A, double ts, double fov, double lens_correction_default, bool zoom_center) {
+    f.keyed = 1;
+    const double a = zoom_keyframed(cp, GF_KF_VIDEO_ROTATION, ts, cp.video_rotation) * (M_PI / 180.0);
+    f.rot_c = cos(a); f.rot_s = sin(a);
+    f.lrc = (float)zoom_keyframed(cp, GF_KF_LIGHT_REFRACTION_COEFF, ts, cp.light_refraction_coefficient);
+    f.zc_x = A.zc_x; f.zc_y = A.zc_y;
+    if (zoom_center) {
+        f.zc_x = (float)zoom_keyframed(cp, GF_KF_ZOOMING_CENTER_X, ts, cp.adaptive_zoom_center_offset[0]) * A.in_w;
+        f.zc_y = (float)zoom_keyframed(cp, GF_KF_ZOOMING_CENTER_Y, ts, cp.adaptive_zoom_center_offset[1]) * A.in_h;
+    }
+    const double lca = zoom_center ? zoom_keyframed(cp, GF_KF_LENS_CORRECTION_STRENGTH, ts, lens_correction_default) : lens_correction_default;
+    f.lc = lca < 1.0 ? 1 : 0;
+    f.amount = (float)lca; f.factor = fmaxf(1.0f - f.amount, 0.001f);
+    f.out_fx = A.fx / (float)fov / f.factor; f.out_fy = A.fy / (float)fov / f.factor;
 }
 
 
 extern "C" {
 
-// FovIterative::compute for `n` frames (zooming/fov_iterative.rs:31-74 without trim ranges / keyframes): out[i] = find_fov(frame i).
+// FovIterative::compute for `n` frames (zooming/fov_iterative.rs:31-74 without trim ranges): out[i] = find_fov(frame i), with the frame's
+// keyframed zoom centre / lens-correction strength (:41-52), video rotation and refraction when gf_compute_params carries those tracks.
 // `cp` is the user's ComputeParams; the calculate_fovs adjustments (fov_scale = 1, fovs cleared, output size = input size,
 // zooming/mod.rs:41-49) are applied here.
 GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, int distortion_model, int digital_lens,
@@ -392,7 +447,14 @@ GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, 
     A.zc_x = (float)cp.adaptive_zoom_center_offset[0] * A.in_w; A.zc_y = (float)cp.adaptive_zoom_center_offset[1] * A.in_h;
     // per-frame uniforms on the host: two O(log n) lookups per frame
     std::vector<ZoomFrame> hf(n);
-    for (size_t i = 0; i < n; ++i) hf[i] = frame_uniforms(cp, timestamps_ms[i], frt, i);
+    const bool keyed = zoom_any_keyframes(cp);
+    if (keyed) {          // the lens-correction constants of ZoomArgs are needed even when the default strength is 1
+        A.out_cx = (float)cp.output_width / 2.0f; A.out_cy = (float)cp.output_height / 2.0f; A.fov = (float)fov;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        hf[i] = frame_uniforms(cp, timestamps_ms[i], frt, i);
+        if (keyed) fill_keyed(hf[i], cp, A, timestamps_ms[i], fov, cp.lens_correction_amount, true);
+    }
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     ZoomFrame* d_frames = nullptr; double* d_out = nullptr;
     cudaError_t e;
@@ -409,15 +471,17 @@ GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, 
 }
 
 // undistort_points_with_rolling_shutter for an arbitrary point list (cpu_undistort.rs:636-641): host in / host out, synchronous.
-GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp_user, int distortion_model, int digital_lens,
                                     double timestamp_ms, size_t frame, int use_fovs, double lens_correction_amount,
                                     const float* points_xy, size_t n, float* out_xy, void* cu_stream) {
-    if (!g || !cp || !points_xy || !out_xy) return GF_ERR_BAD_PARAMS;
+    if (!g || !cp_user || !points_xy || !out_xy) return GF_ERR_BAD_PARAMS;
     if (n == 0) return GF_OK;
     PointsFn fn = pick_points(distortion_model, digital_lens);
     if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
     if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
     ZoomArgs A;
+    const gf_compute_params rcp = resolve_point_keyframes(*cp_user, timestamp_ms);     // video rotation, refraction, Fov at this timestamp
+    const gf_compute_params* cp = &rcp;
     const double fov = gf_points_fov(cp, frame, use_fovs);
     const double frt = setup_points_args(g, *cp, distortion_model, fov, lens_correction_amount, A);
     const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt, frame);
@@ -438,11 +502,13 @@ GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp
 
 // The "redistort" ST map (stmap.rs:112-116): undistort_points of every pixel centre of the width x height frame, written to
 // device memory as RGB f32 (x / width, 1 - y / height, 0).  Asynchronous on the stream.
-GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* cp, int distortion_model, int digital_lens,
+GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* cp_user, int distortion_model, int digital_lens,
                                      double timestamp_ms, size_t frame, float* out_rgb_dev, void* cu_stream) {
-    if (!g || !cp || !out_rgb_dev) return GF_ERR_BAD_PARAMS;
+    if (!g || !cp_user || !out_rgb_dev) return GF_ERR_BAD_PARAMS;
     PointsFn fn = pick_points(distortion_model, digital_lens);
     if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
+    const gf_compute_params rcp = resolve_point_keyframes(*cp_user, timestamp_ms);     // video rotation, refraction, Fov at this timestamp
+    const gf_compute_params* cp = &rcp;
     if (cp->width < 1 || cp->height < 1) return GF_ERR_BAD_PARAMS;
     if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
     ZoomArgs A;

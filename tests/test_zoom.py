@@ -62,3 +62,37 @@ def test_device_find_fovs_matches_oracle(lens, digital, kw):
     dg.close()
     assert np.allclose(got, want, rtol=1e-6, atol=0), float(np.abs(got / want - 1).max())
     assert (got == want).mean() > 0.9            # almost always identical; the rest is f64 device-vs-host libm in the rotation
+
+
+@pytest.mark.gpu
+def test_device_find_fovs_with_keyframes_matches_oracle_per_frame():
+    """Keyframed clips (fov_iterative.rs:41-52): every frame uses ITS zoom centre and lens-correction strength, and the point path its video
+    rotation (frame_transform.rs:354) and refraction coefficient (cpu_undistort.rs:661).  The device result for frame i equals the oracle's
+    find_fov on a ComputeParams whose constants are the restated KeyframeManager's values at that frame's timestamp."""
+    from tests import np_producer
+    tracks = {"VideoRotation": [(0, -8.0, "EaseInOut"), (900_000, 14.0, "EaseOut"), (2_000_000, 3.0, "NoEasing")],
+              "ZoomingCenterX": [(100_000, -0.04, "EaseIn"), (1_500_000, 0.05, "EaseInOut")],
+              "ZoomingCenterY": [(0, 0.03, "NoEasing"), (1_900_000, -0.02, "EaseOut")],
+              "LensCorrectionStrength": [(0, 1.0, "EaseInOut"), (1_000_000, 0.35, "EaseInOut"), (2_000_000, 0.8, "EaseIn")],
+              "LightRefractionCoeff": [(0, 1.0, "NoEasing"), (2_000_000, 1.33, "NoEasing")]}
+    lens, digital = "opencv_fisheye", None
+    cp = make_cp(lens=lens, digital=digital, keyframes=tracks)
+    ts = np.arange(0, 120, 3) * (1000.0 / 60.0)
+    dg = g.DeviceGyro(cp)
+    got = dg.find_fovs(lens, digital, ts)
+    # single-timestamp point path: rotation / refraction resolved at the timestamp
+    pts = np.array([[100.0, 80.0], [960.0, 540.0], [1800.0, 1000.0]], np.float32)
+    got_pts = dg.undistort_points(lens, digital, pts, float(ts[7]))
+    dg.close()
+    want = np.zeros_like(got)
+    for i, t in enumerate(ts):
+        v = {k: np_producer.keyframe_value_at(tracks[k], float(t)) for k in tracks}
+        ref = make_cp(lens=lens, digital=digital, video_rotation=v["VideoRotation"], params=dict(lens_correction_amount=v["LensCorrectionStrength"], light_refraction_coefficient=v["LightRefractionCoeff"]))
+        ref.c.adaptive_zoom_center_offset[0] = v["ZoomingCenterX"]; ref.c.adaptive_zoom_center_offset[1] = v["ZoomingCenterY"]
+        ref.c.lens_correction_amount = v["LensCorrectionStrength"]; ref.c.light_refraction_coefficient = v["LightRefractionCoeff"]
+        want[i] = oracle_lib.find_fovs(ref, lens, digital, [float(t)])[0]
+        if i == 7:
+            rd = g.DeviceGyro(ref); want_pts = rd.undistort_points(lens, digital, pts, float(t)); rd.close()
+            assert np.array_equal(got_pts, want_pts)
+    assert np.allclose(got, want, rtol=1e-6, atol=0), float(np.abs(got / want - 1).max())
+    assert (got == want).mean() > 0.9 and np.ptp(want) > 0.01
