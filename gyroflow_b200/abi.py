@@ -96,7 +96,14 @@ class ComputeParams(C.Structure):
         ("readout_time_scale", C.c_double),
         ("camera_stab", C.c_void_p), ("n_camera_stab", C.c_size_t),
         ("keyframes", KeyframeTrack * 8), ("keyframe_timestamp_scale", C.c_double),
+        ("lens_per_frame", C.c_void_p), ("n_lens_per_frame", C.c_size_t),
     ]
+
+
+class LensData(C.Structure):
+    """gf_lens_data: one frame's get_lens_data_at_timestamp result (frame_transform.rs:82-163)."""
+    _fields_ = [("camera_matrix", C.c_double * 9), ("distortion_coeffs", C.c_double * 12), ("radial_distortion_limit", C.c_double),
+                ("input_horizontal_stretch", C.c_double), ("input_vertical_stretch", C.c_double)]
 
 
 class CameraStab(C.Structure):

@@ -228,7 +228,7 @@ class ComputeParams:
     def __init__(self, kernel_params: abi.KernelParams, org, smoothed, frame_readout_time_ms=16.0, fovs=None, video_rotation=0.0,
                  horizontal=False, inverted=False, framebuffer_inverted=False, fov_scale=1.0, sync_offsets=None,
                  per_frame_time_offsets=None, focal_lengths=None, smoothed_focal_lengths=None, readout_time_scale=0.0, camera_stab=None,
-                 gyro_offset_ms=0.0, keyframes=None, keyframe_timestamp_scale=0.0):
+                 gyro_offset_ms=0.0, keyframes=None, keyframe_timestamp_scale=0.0, lens_per_frame=None):
         """sync_offsets: {timestamp_us: offset_ms} (GyroSource::offsets_adjusted); camera_stab: list (one per frame) of dicts with
         offset, sensor_size, crop_area, pixel_pitch, ibis=(pos[n], xyz[n,3]), ois=(pos[n], xyz[n,3]) (CameraStabData);
         keyframes: {KeyframeType name: [(timestamp_us, value, easing name), ...]} for the types at_timestamp reads (abi.KEYFRAME_TYPES)."""
@@ -275,6 +275,15 @@ class ComputeParams:
             c.n_focal_lengths = self._fl.size
         c.readout_time_scale = readout_time_scale
         c.keyframe_timestamp_scale = keyframe_timestamp_scale
+        if lens_per_frame:        # list of dicts: camera_matrix[9], distortion_coeffs[12], radial_distortion_limit, input_horizontal_stretch, input_vertical_stretch
+            arr = (abi.LensData * len(lens_per_frame))()
+            for i, d in enumerate(lens_per_frame):
+                arr[i].camera_matrix[:] = [float(v) for v in d["camera_matrix"]]
+                arr[i].distortion_coeffs[:] = [float(v) for v in d["distortion_coeffs"]]
+                arr[i].radial_distortion_limit = float(d.get("radial_distortion_limit", 0.0))
+                arr[i].input_horizontal_stretch = float(d.get("input_horizontal_stretch", 1.0)); arr[i].input_vertical_stretch = float(d.get("input_vertical_stretch", 1.0))
+            self._lens = arr
+            c.lens_per_frame = C.cast(arr, C.c_void_p); c.n_lens_per_frame = len(lens_per_frame)
         self._kf_arrays = []
         for name, keys in (keyframes or {}).items():
             keys = sorted(keys)

@@ -227,8 +227,15 @@ size_t prepare(const gf_compute_params* cp, double timestamp_ms, size_t frame, c
     double fov = get_fov(cp, frame, true, timestamp_ms, false) * fl_compensation;                                         // :191
     double ui_fov = get_fov(cp, frame, true, timestamp_ms, true);
     if (cp->has_optimal_fov) { if (cp->n_fovs == 0) fov *= cp->lens_optimal_fov; else ui_fov /= cp->lens_optimal_fov; }   // :193-199
-    const double* K = cp->camera_matrix;
-    const double hr = cp->input_horizontal_stretch > 0.01 ? cp->input_horizontal_stretch : 1.0;                          // :38
+    // ----------- Lens :183-188: this frame's get_lens_data_at_timestamp result when the caller supplies one per frame -----------
+    const gf_lens_data* lens = (cp->lens_per_frame && frame < cp->n_lens_per_frame) ? &cp->lens_per_frame[frame] : nullptr;
+    const double* K = lens ? lens->camera_matrix : cp->camera_matrix;
+    const double* dist = lens ? lens->distortion_coeffs : cp->distortion_coeffs;
+    const double r_limit = lens ? lens->radial_distortion_limit : cp->radial_distortion_limit;
+    const double ihs = lens ? lens->input_horizontal_stretch : cp->input_horizontal_stretch;
+    const double ivs = lens ? lens->input_vertical_stretch : cp->input_vertical_stretch;
+    const double hr_frame = ihs > 0.01 ? ihs : 1.0;                                                                     // :146 (the lens of this timestamp)
+    const double hr = cp->input_horizontal_stretch > 0.01 ? cp->input_horizontal_stretch : 1.0;                         // :38 get_new_k reads params.lens, the base profile
     const double img_dim_ratio = 1.0 / hr;
     double new_k[9]; memcpy(new_k, K, sizeof(new_k));
     new_k[0] = new_k[0] * img_dim_ratio / fov; new_k[4] = new_k[4] * img_dim_ratio / fov;                                 // :46-47
@@ -269,12 +276,12 @@ size_t prepare(const gf_compute_params* cp, double timestamp_ms, size_t frame, c
         kp->matrix_count = (int32_t)rows;
         kp->f[0] = (float)K[0]; kp->f[1] = (float)K[4];
         kp->c[0] = (float)K[2]; kp->c[1] = (float)K[5];
-        for (int i = 0; i < 12; ++i) kp->k[i] = (float)cp->distortion_coeffs[i];
+        for (int i = 0; i < 12; ++i) kp->k[i] = (float)dist[i];
         kp->fov = (float)fov;
-        kp->r_limit = (float)cp->radial_distortion_limit;
+        kp->r_limit = (float)r_limit;
         kp->lens_correction_amount = (float)lens_correction_amount;
-        kp->input_vertical_stretch = (float)(cp->input_vertical_stretch > 0.01 ? cp->input_vertical_stretch : 1.0);
-        kp->input_horizontal_stretch = (float)hr;
+        kp->input_vertical_stretch = (float)(ivs > 0.01 ? ivs : 1.0);
+        kp->input_horizontal_stretch = (float)hr_frame;
         kp->background_mode = cp->background_mode;
         kp->background_margin = (float)background_margin;
         kp->background_margin_feather = (float)background_feather;

@@ -203,7 +203,7 @@ GF_API int         gf_cuda_device_name(int device, char* buf, size_t buf_len);  
 GF_API int         gf_cuda_supports(const gf_buffer_desc* in, const gf_buffer_desc* out); /* is_buffer_supported opencl.rs:451 */
 GF_API const char* gf_cuda_version(void);
 /* sizeof() of the structs that cross this ABI, for binding generators and their tests: 0 gf_kernel_params, 1 gf_buffer_desc,
- * 2 gf_compute_params, 3 gf_camera_stab, 4 gf_keyframe_track, 5 gf_stab_config, 6 gf_queue_config; 0 for any other index. */
+ * 2 gf_compute_params, 3 gf_camera_stab, 4 gf_keyframe_track, 5 gf_stab_config, 6 gf_queue_config, 7 gf_lens_data; 0 for any other index. */
 GF_API size_t gf_abi_struct_size(int which);
 
 /* ---- lens plugin surface: DistortionModel::from_name / id  distortion_models/mod.rs:79-90 -- */
@@ -389,7 +389,15 @@ typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_p
     /* keyframed scalars at_timestamp evaluates per frame (frame_transform.rs:53, :167-174): a track with n > 0 replaces the constant above */
     gf_keyframe_track keyframes[GF_KF_COUNT];
     double  keyframe_timestamp_scale;                            /* KeyframeManager::timestamp_scale; 0 = None (1.0) */
+    /* per-frame result of get_lens_data_at_timestamp (:82-163) for clips whose lens changes over time (interpolated lens profiles,
+     * telemetry lens_params of zoom lenses): entry `frame` replaces camera_matrix / distortion_coeffs / radial_distortion_limit /
+     * input_*_stretch above in at_timestamp.  Rust evaluates it once per job; NULL = the constants above for every frame. */
+    const struct gf_lens_data* lens_per_frame; size_t n_lens_per_frame;
 } gf_compute_params;
+typedef struct gf_lens_data {
+    double camera_matrix[9]; double distortion_coeffs[12]; double radial_distortion_limit;
+    double input_horizontal_stretch, input_vertical_stretch;
+} gf_lens_data;
 
 /* CameraStabData (src/core/gyro_source/file_metadata.rs:41-48): IBIS / OIS motion of one frame as Catmull-Rom splines over the
  * sensor row (gyro_source/splines.rs:8-83).  Points are (position, Vector3) pairs: `*_pos[n]` ascending, `*_xyz[n][3]`. */
@@ -493,7 +501,8 @@ GF_API int gf_get_frame_transform_at(const gf_stab_config* stab, const gf_comput
  *     gf_cuda_frame_transform_dev_flagged (table + verdict on the device)  ->  [H2D]  ->  warp  ->  [checksum]  ->  [D2H]
  * gf_cuda_queue_submit never blocks: with `depth` frames already in flight it fails with GF_ERR_BAD_PARAMS ("queue full") — call
  * gf_cuda_queue_wait first; gf_cuda_queue_wait blocks until the OLDEST frame is done and returns frames in submission order.  HOST buffers must be page-locked and stay valid until the
- * frame has been waited for.  The optional checksum is sum(word[i] * (2 i + 1)) mod 2^64 over the output buffer's 32-bit words.
+ * frame has been waited for.  `cp` is copied shallowly: the arrays it points to (tracks are uploaded at creation; fovs, offsets, focal lengths,
+ * camera_stab, keyframe tracks, lens_per_frame are read per frame on the host) must stay valid until gf_cuda_queue_destroy.  The optional checksum is sum(word[i] * (2 i + 1)) mod 2^64 over the output buffer's 32-bit words.
  * ---------------------------------------------------------------------------------------- */
 typedef struct gf_cuda_queue gf_cuda_queue;
 typedef struct gf_queue_config {

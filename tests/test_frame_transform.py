@@ -252,3 +252,32 @@ def test_device_producer_with_keyframes_matches_host():
         assert bytes(kp) == bytes(kp2) and rows == h
         assert float(ulp_diff(mats.cpu().numpy()[:, :9], want[:, :9]).max()) <= 1.0
     dg.close()
+
+
+def test_per_frame_lens_data_replaces_the_constants():
+    """lens_per_frame[frame] (the caller's get_lens_data_at_timestamp result, frame_transform.rs:82-163, :183-188) drives K, the distortion
+    coefficients, r_limit and the stretch of that frame: identical to a ComputeParams built with those values as constants — except that
+    get_new_k keeps reading the BASE profile's horizontal stretch (:38), which the test pins with a different per-frame stretch."""
+    p = synth.base_kernel_params(640, 360)
+    org, sm = cases.gyro()
+    base = g.ComputeParams(p, org, sm)
+    lens = []
+    for i in range(3):
+        K = list(base.c.camera_matrix); K[0] *= 1.0 + 0.1 * i; K[4] *= 1.0 + 0.1 * i; K[2] += 3.0 * i; K[5] -= 2.0 * i
+        lens.append(dict(camera_matrix=K, distortion_coeffs=[v * (1.0 - 0.2 * i) for v in base.c.distortion_coeffs], radial_distortion_limit=0.5 * i,
+                         input_horizontal_stretch=1.0 + 0.25 * i, input_vertical_stretch=1.0 - 0.1 * i))
+    cp = g.ComputeParams(p, org, sm, lens_per_frame=lens)
+    for frame, ts in enumerate((300.0, 1500.0, 2900.0, 3500.0)):
+        kp, m, fov, _ = cp.at_timestamp(ts, frame)
+        ref = g.ComputeParams(p, org, sm)
+        if frame < 3:
+            d = lens[frame]
+            ref.c.camera_matrix[:] = d["camera_matrix"]; ref.c.distortion_coeffs[:] = d["distortion_coeffs"]; ref.c.radial_distortion_limit = d["radial_distortion_limit"]
+            ref.c.input_vertical_stretch = d["input_vertical_stretch"]
+        kp2, m2, fov2, _ = ref.at_timestamp(ts, frame)            # base horizontal stretch (1.0) in both: get_new_k's ratio
+        assert np.array_equal(m, m2) and fov == fov2
+        if frame < 3:
+            assert kp.input_horizontal_stretch == np.float32(lens[frame]["input_horizontal_stretch"]) and kp2.input_horizontal_stretch == 1.0
+            kp2.input_horizontal_stretch = kp.input_horizontal_stretch
+            assert kp.r_limit == np.float32(0.5 * frame) and list(kp.k) == [np.float32(v) for v in lens[frame]["distortion_coeffs"]]
+        assert bytes(kp) == bytes(kp2)
