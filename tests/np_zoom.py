@@ -1,0 +1,206 @@
+"""Second, independent restatement of the adaptive-zoom companion — TEST INFRASTRUCTURE ONLY.
+
+  at_timestamp_for_points   <- FrameTransform::at_timestamp_for_points    src/core/stabilization/frame_transform.rs:352-410
+  undistort_points          <- undistort_points (opencv_fisheye, no digital lens / mesh / IBIS shifts)
+                                                                           src/core/stabilization/cpu_undistort.rs:652-858
+  find_fov                  <- FovIterative::find_fov / nearest_edge / points_around_rect / interpolate_points
+                                                                           src/core/zooming/fov_iterative.rs:76-200
+
+Written from the Rust text in numpy scalars; the C oracle (oracle/gf_oracle.c, gf_oracle_find_fov) and the CUDA kernels
+(gyroflow_b200/csrc/zoom_kernel.cu) are checked against it in tests/test_zoom.py.  The rotations come from numpy's f64 slerp /
+matrix products (tests/np_producer.py), not nalgebra's, so the bar is a relative 1e-6 on the resulting FOV, like the device-vs-oracle bar.
+"""
+import math
+
+import numpy as np
+
+from gyroflow_b200.synth import q_mul, q_inv
+from tests import np_producer
+from tests.np_restatement import F, fisheye_distort, fisheye_undistort_point, sqrtf
+
+
+def get_fov(c, frame, use_fovs):                                                  # frame_transform.rs:52-58 (no Fov keyframe here)
+    fov_scale = c.fov_scale + (1.0 if (c.fov_overview and use_fovs) else 0.0)
+    if use_fovs:
+        fovs = [c.fovs[i] for i in range(c.n_fovs)]
+        f = fovs[frame] if frame < len(fovs) else (fovs[-1] if len(fovs) > 1 else 1.0)
+        fov = f * fov_scale
+    else:
+        fov = 1.0
+    fov = max(fov, 0.001)
+    return fov * c.width / max(c.output_width, 1)
+
+
+def at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs):            # frame_transform.rs:352-410
+    c = cp.c
+    K = np.array(list(c.camera_matrix), dtype=np.float64).reshape(3, 3)
+    fov = get_fov(c, frame, use_fovs)
+    hr = c.input_horizontal_stretch if c.input_horizontal_stretch > 0.01 else 1.0  # get_new_k :37-51
+    new_k = K.copy()
+    new_k[0, 0] = new_k[0, 0] * (1.0 / hr) / fov; new_k[1, 1] = new_k[1, 1] * (1.0 / hr) / fov
+    new_k[0, 2] = c.output_width / 2.0; new_k[1, 2] = c.output_height / 2.0
+    frt = abs(c.frame_readout_time)                                                # get_frame_readout_time(can_invert = false) :21-36
+    if c.readout_inverted: frt *= -1.0
+    n = c.width if c.readout_horizontal else c.height
+    row_readout_time = frt / n
+    start_ts = timestamp_ms - frt / 2.0
+    a = c.video_rotation * (math.pi / 180.0)
+    image_rotation = np.array([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    org = type("T", (), dict(ts=cp._ots, q=cp._oq))
+    sm = type("T", (), dict(ts=cp._sts, q=cp._sq))
+    quat1 = q_inv(np_producer.quat_at_timestamp(org, timestamp_ms)[0])
+    sq1 = np_producer.quat_at_timestamp(sm, timestamp_ms)[0]
+    pts = points if abs(frt) > 0.0 else [(0.0, 0.0)]
+    rotations = []
+    for (x, y) in pts:
+        qt = start_ts + row_readout_time * float(x if c.readout_horizontal else y) if abs(frt) > 0.0 else start_ts
+        quat = q_mul(q_mul(sq1[None, :], quat1[None, :]), np_producer.quat_at_timestamp(org, qt))[0]
+        r = image_rotation @ np_producer.q_to_matrix(quat)
+        r[0, 1] *= -1.0; r[0, 2] *= -1.0; r[1, 0] *= -1.0; r[2, 0] *= -1.0
+        if c.suppress_rotation:
+            r = np.eye(3)
+        rotations.append(new_k @ r)
+    return K, rotations, fov
+
+
+def _refract(px, py, lrc):                                                         # cpu_undistort.rs:767-776
+    if lrc != F(1.0) and lrc > 0:
+        r = sqrtf(px * px + py * py)
+        if r != 0:
+            sin_theta_d = (r / sqrtf(F(1.0) + r * r)) / lrc
+            r_d = sin_theta_d / sqrtf(F(1.0) - sin_theta_d * sin_theta_d)
+            fac = r_d / r
+            return px * fac, py * fac
+    return px, py
+
+
+def undistort_points(cp, points, K, rotations, lens_correction_amount, fov):      # cpu_undistort.rs:652-858, opencv_fisheye only
+    c = cp.c
+    fx, fy, cx, cy = F(K[0, 0]), F(K[1, 1]), F(K[0, 2]), F(K[1, 2])
+    k = [F(v) for v in list(c.distortion_coeffs)]
+    lrc = F(c.light_refraction_coefficient)
+    lc = None
+    if lens_correction_amount < 1.0:                                               # :686-694
+        out_c = (F(c.output_width) / F(2.0), F(c.output_height) / F(2.0))
+        amount = F(lens_correction_amount)
+        factor = max(F(1.0) - amount, F(0.001))
+        out_f = (fx / F(fov) / factor, fy / F(fov) / factor)
+        lc = (out_c, amount, factor, out_f)
+    out = []
+    for index, (x, y) in enumerate(points):
+        x, y = F(x), F(y)
+        if c.input_horizontal_stretch > 0.001: x = x * F(c.input_horizontal_stretch)      # :702-703
+        if c.input_vertical_stretch > 0.001: y = y * F(c.input_vertical_stretch)
+        pwx, pwy = (x - cx) / fx, (y - cy) / fy                                    # :760
+        rot = np.asarray(rotations[index] if index < len(rotations) else rotations[0], dtype=np.float64).astype(np.float32)
+        pt = fisheye_undistort_point(pwx, pwy, k)
+        if pt is None:
+            out.append((F(-1000000.0), F(-1000000.0)))
+            continue
+        px, py = _refract(pt[0], pt[1], lrc)
+        pr = [rot[i, 0] * px + rot[i, 1] * py + rot[i, 2] * F(1.0) for i in range(3)]   # rot * (x, y, 1) in f32
+        px, py = pr[0] / pr[2], pr[1] / pr[2]
+        if lc is not None:                                                         # :782-852: solve amount*o + factor*R(o) = pt by Newton
+            out_c, amount, factor, out_f = lc
+
+            def r_of(ox, oy):
+                nx, ny = (ox - out_c[0]) / out_f[0], (oy - out_c[1]) / out_f[1]
+                d = fisheye_undistort_point(nx, ny, k)
+                if d is not None: nx, ny = d
+                nx, ny = _refract(nx, ny, lrc)
+                return (nx * out_f[0]) + out_c[0], (ny * out_f[1]) + out_c[1]
+
+            nx, ny = (px - out_c[0]) / out_f[0], (py - out_c[1]) / out_f[1]
+            dx, dy = fisheye_distort(nx, ny, F(1.0), k)
+            p2x, p2y = (dx * out_f[0]) + out_c[0], (dy * out_f[1]) + out_c[1]
+            if math.isfinite(float(p2x)) and math.isfinite(float(p2y)):
+                ox, oy = p2x * factor + px * amount, p2y * factor + py * amount
+            else:
+                ox, oy = px, py
+            for _ in range(10):
+                rx, ry = r_of(ox, oy)
+                g0, g1 = amount * ox + factor * rx - px, amount * oy + factor * ry - py
+                if abs(g0) < F(0.02) and abs(g1) < F(0.02): break
+                eps = F(1.0)
+                rxx, rxy = r_of(ox + eps, oy)
+                ryx, ryy = r_of(ox, oy + eps)
+                j11 = amount + factor * (rxx - rx) / eps; j21 = factor * (rxy - ry) / eps
+                j12 = factor * (ryx - rx) / eps;          j22 = amount + factor * (ryy - ry) / eps
+                det = j11 * j22 - j12 * j21
+                if not math.isfinite(float(det)) or abs(det) < F(1e-9): break
+                ddx = (j22 * g0 - j12 * g1) / det
+                ddy = (-j21 * g0 + j11 * g1) / det
+                if not math.isfinite(float(ddx)) or not math.isfinite(float(ddy)): break
+                ox, oy = ox - ddx, oy - ddy
+            px, py = ox, oy
+        out.append((px, py))
+    return out
+
+
+def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False):   # :636-641
+    K, rotations, fov = at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs)
+    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov)
+
+
+def points_around_rect(w, h, w_div, h_div, margin):                                # fov_iterative.rs:154-177
+    w, h, margin = F(w), F(h), F(margin)
+    w = w - margin * F(2.0); h = h - margin * F(2.0)
+    wcnt, hcnt = max(w_div, 2) - 1, max(h_div, 2) - 1
+    wstep, hstep = w / F(wcnt), h / F(hcnt)
+    pts = [(F(i) * wstep, F(0.0)) for i in range(wcnt)] + [(w, F(i) * hstep) for i in range(hcnt)] + \
+          [(F(wcnt - i) * wstep, h) for i in range(wcnt)] + [(F(0.0), F(hcnt - i) * hstep) for i in range(hcnt)]
+    return [(x + margin, y + margin) for x, y in pts]
+
+
+def interpolate_points(pts, steps):                                                # fov_iterative.rs:182-192
+    d = steps + 1
+    new_len = d * len(pts) - steps
+    out = []
+    for i in range(new_len):
+        idx1 = i // d
+        idx2 = min(idx1 + 1, len(pts) - 1)
+        f = F(i % d) / F(d)
+        out.append((pts[idx1][0] + f * (pts[idx2][0] - pts[idx1][0]), pts[idx1][1] + f * (pts[idx2][1] - pts[idx1][1])))
+    return out
+
+
+def nearest_edge(polygon, center, initial, inv_aspect):                            # fov_iterative.rs:136-151
+    idx, mp = None, initial
+    for i, (x, y) in enumerate(polygon):
+        ap = (abs(x - center[0]), abs(y - center[1]))
+        if ap[0] < mp[0] and ap[1] < mp[1]:
+            if ap[1] > ap[0] * inv_aspect:
+                idx, mp = i, (ap[1] / inv_aspect, ap[1])
+            else:
+                idx, mp = i, (ap[0], ap[0] * inv_aspect)
+    return idx, mp
+
+
+def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0):               # FovIterative::new :76-89 + find_fov :91-134
+    """`cp` must already carry the calculate_fovs adjustments (zooming/mod.rs:41-49): fov_scale 1, no fovs, output size = input size."""
+    c = cp.c
+    ratio = F(c.width) / F(max(org_output_size[0], 1))
+    input_dim = (F(c.width), F(c.height))
+    output_dim = (F(org_output_size[0]) * ratio, F(org_output_size[1]) * ratio)
+    inv_aspect = output_dim[1] / output_dim[0]
+    rect = points_around_rect(input_dim[0], input_dim[1], 31, 31, margin)
+    center = (input_dim[0] / F(2.0), input_dim[1] / F(2.0))
+    zx, zy, lca = c.adaptive_zoom_center_offset[0], c.adaptive_zoom_center_offset[1], c.lens_correction_amount
+
+    def shifted(pts):
+        poly = undistort_points_with_rolling_shutter(cp, pts, timestamp_ms, frame, lca, False)
+        return [(x - F(zx) * input_dim[0], y - F(zy) * input_dim[1]) for x, y in poly]
+
+    polygon = shifted(rect)
+    nearest = (None, (F(1000000.0), F(1000000.0) * inv_aspect))
+    for _ in range(1, 5):
+        nearest = nearest_edge(polygon, center, nearest[1], inv_aspect)
+        if nearest[0] is None:
+            break
+        n = len(rect)
+        idx = nearest[0]
+        # `idx.overflowing_sub(1).0 % len`: usize wrap-around, (2^64 - 1) % len for idx == 0
+        relevant = [rect[((idx - 1) % (1 << 64)) % n], rect[idx], rect[(idx + 1) % n]]
+        polygon = shifted(interpolate_points(relevant, 30))
+        nearest = nearest_edge(polygon, center, nearest[1], inv_aspect)
+    return float(nearest[1][0] * F(2.0) / output_dim[0])
