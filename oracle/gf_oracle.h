@@ -12,7 +12,8 @@
  * translation, forward/inverse lens round trips) in tests/, and (c) an independent numpy
  * restatement of the whole path — every lens model and digital lens, every resampler, mesh /
  * focal-plane correction, background modes, lens-correction blend (tests/np_restatement.py,
- * tests/test_oracle.py::test_independent_numpy_restatement_*: 53 cases, same bytes).
+ * tests/test_oracle.py::test_independent_numpy_restatement_*: 70 cases, same bytes; tests/np_zoom.py for
+ * the adaptive-zoom companion).
  *
  * Float semantics mirrored from Rust: f32 ops are IEEE with no FMA contraction (build
  * with -ffp-contract=off), `as` casts truncate + saturate + NaN->0, f32::round is

@@ -4,7 +4,8 @@ opencv_standard, poly3, poly5, ptlens, insta360, sony, generic_polynomial, gopro
 gopro6_superview, gopro_hyperview, gopro_warp, digital_stretch), vertical rolling shutter, bilinear / bicubic / Lanczos4
 sampling, background modes 0-2, r_limit, light refraction, IBIS / OIS rows, input rotation and stretch, horizontal rolling shutter,
 the f64 mesh correction (bivariate spline, splines.rs:100-176 / sony.rs:557-563) and focal-plane distortion, the EWA CubicBC resampler,
-background mode 3 (margin with feather), fix-colour-range and fill-with-background, and the lens-correction blend for opencv_fisheye,
+background mode 3 (margin with feather), fix-colour-range and fill-with-background, and the lens-correction blend with every model's
+undistort_point (physical and digital),
 on 8-bit, 16-bit and f32 pixels (cpu_undistort.rs:133-228, :262-418, :421-517, :519-633; distortion_models/*.rs distort_point;
 gyro_source/splines.rs; util.rs:144-147; pixel_formats.rs conversions).
 With it every lens formula and every optional stage of the oracle has two independent transcriptions.
@@ -303,6 +304,169 @@ def fisheye_undistort_point(x, y, k):        # opencv_fisheye.rs:12-66
     return None
 
 
+# ---- undistort_point of the other lens models (the lens-correction blend, ST maps and the zoom companion call them) ----
+NEWTON_EPS = F(0.00001)
+
+
+def standard_undistort_point(x, y, k):       # opencv_standard.rs:12-31
+    x0, y0 = x, y
+    for _ in range(20):
+        r2 = x * x + y * y
+        icdist = (F(1.0) + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (F(1.0) + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+        if icdist < 0:
+            return None
+        delta_x = F(2.0) * k[2] * x * y + k[3] * (r2 + F(2.0) * x * x) + k[8] * r2 + k[9] * r2 * r2
+        delta_y = k[2] * (r2 + F(2.0) * y * y) + F(2.0) * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2
+        x = (x0 - delta_x) * icdist
+        y = (y0 - delta_y) * icdist
+    return x, y
+
+
+def _radial_newton(x, y, f, df):             # the loop shared by poly3.rs:14-51, poly5.rs:14-42, ptlens.rs:15-42
+    rd = sqrtf(x * x + y * y)
+    if rd == 0:
+        return None
+    ru = rd
+    for i in range(10):
+        fru = f(ru, rd)
+        if fru >= -NEWTON_EPS and fru < NEWTON_EPS:
+            break
+        if i > 5:
+            return None
+        ru = ru - (fru / df(ru))
+    if ru < 0:
+        return None
+    ru = ru / rd
+    return x * ru, y * ru
+
+
+def poly3_undistort_point(x, y, k):          # poly3.rs:14-51
+    inv_k1 = F(1.0) / k[0]
+    rd = sqrtf(x * x + y * y)
+    rd_div_k1 = rd * inv_k1
+    return _radial_newton(x, y, lambda ru, _rd: ru * ru * ru + ru * inv_k1 - rd_div_k1, lambda ru: F(3.0) * ru * ru + inv_k1)
+
+
+def poly5_undistort_point(x, y, k):          # poly5.rs:14-42
+    def f(ru, rd):
+        ru2 = ru * ru
+        return ru * (F(1.0) + k[0] * ru2 + k[1] * ru2 * ru2) - rd
+
+    def df(ru):
+        ru2 = ru * ru
+        return F(1.0) + F(3.0) * k[0] * ru2 + F(5.0) * k[1] * ru2 * ru2
+    return _radial_newton(x, y, f, df)
+
+
+def ptlens_undistort_point(x, y, k):         # ptlens.rs:15-42
+    return _radial_newton(x, y, lambda ru, rd: ru * (k[0] * ru * ru * ru + k[1] * ru * ru + k[2] * ru + F(1.0)) - rd,
+                          lambda ru: F(4.0) * k[0] * ru * ru * ru + F(3.0) * k[1] * ru * ru + F(2.0) * k[2] * ru + F(1.0))
+
+
+def _theta_newton(x, y, k, n):               # sony.rs:10-61 (n = 6) and generic_polynomial.rs:18-81 (n = 12): Newton on theta * sum k_i theta^i = theta_d
+    if all(k[i] == 0 for i in range(4 if n == 6 else 12)):
+        return x, y
+    EPS = F(1e-6)
+    theta_d = sqrtf(x * x + y * y)
+    converged = False
+    theta = theta_d
+    scale = F(0.0)
+    if abs(theta_d) > EPS:
+        theta = F(0.0)
+        for _ in range(10):
+            t2 = theta * theta; t3 = t2 * theta; t4 = t2 * t2; t5 = t2 * t3
+            pw = [None, theta, t2, t3, t4, t5]
+            if n == 12:
+                t6 = t3 * t3; t7 = t3 * t4; t8 = t4 * t4; t9 = t4 * t5; t10 = t5 * t5; t11 = t5 * t6
+                pw += [t6, t7, t8, t9, t10, t11]
+            terms = [k[0]] + [k[i] * pw[i] for i in range(1, n)]
+            num = terms[0]
+            for t in terms[1:]: num = num + t
+            den = terms[0]
+            for i in range(1, n): den = den + F(i + 1) * terms[i]
+            theta_fix = (theta * num - theta_d) / den
+            theta = theta - theta_fix
+            if abs(theta_fix) < EPS:
+                converged = True
+                break
+        scale = tanf(theta) / theta_d
+    else:
+        converged = True
+    flipped = (theta_d < 0 and theta > 0) or (theta_d > 0 and theta < 0)
+    if converged and not flipped:
+        return x * scale, y * scale
+    return None
+
+
+def sony_undistort_point(x, y, k):
+    return _theta_newton(x, y, k, 6)
+
+
+def generic_polynomial_undistort_point(x, y, k):
+    return _theta_newton(x, y, k, 12)
+
+
+def insta360_undistort_point(x, y, k):       # insta360.rs:10-25: fixed point on distort_point, up to 200 steps
+    px, py = x, y
+    for _ in range(200):
+        dx, dy = insta360_distort(px, py, F(1.0), k)
+        d0, d1 = dx - x, dy - y
+        if abs(d0) < F(1e-6) and abs(d1) < F(1e-6):
+            break
+        px = px - d0; py = py - d1
+    return px, py
+
+
+def gopro_undistort_point(x, y, k):          # gopro.rs:40-55
+    if k[1] == 0:
+        return x, y
+    r_norm = sqrtf(x * x + y * y)
+    if r_norm < F(1e-9):
+        return x, y
+    p = r_norm / k[1]
+    theta = _gopro_poly_eval(p, k)
+    TMAX = F(1.5533)
+    tt = tanf(TMAX)
+    rr = tanf(theta) if theta < TMAX else tt + (theta - TMAX) * (F(1.0) + tt * tt)
+    scale = rr / r_norm
+    return x * scale, y * scale
+
+
+UNDISTORT = {"opencv_fisheye": fisheye_undistort_point, "opencv_standard": standard_undistort_point, "poly3": poly3_undistort_point,
+             "poly5": poly5_undistort_point, "ptlens": ptlens_undistort_point, "sony": sony_undistort_point, "insta360": insta360_undistort_point,
+             "generic_polynomial": generic_polynomial_undistort_point, "gopro": gopro_undistort_point}
+
+
+def _view_undistort(fn, xscale):             # e.g. gopro_superview.rs:23-34: the forward polynomial in normalised output coordinates
+    def undistort(ux, uy, p):
+        ow, oh = F(p.output_width), F(p.output_height)
+        ux, uy = (ux / ow) - F(0.5), (uy / oh) - F(0.5)
+        ux, uy = fn(ux, uy)
+        if xscale is not None:
+            ux = ux / F(xscale)
+        return (ux + F(0.5)) * ow, (uy + F(0.5)) * oh
+    return undistort
+
+
+def gopro_warp_undistort(ux, uy, p):         # gopro_warp.rs:42-55
+    q = [F(v) for v in p.digital_lens_params]
+    factor = q[14] if q[14] != 0 else F(1.0)
+    ow, oh = F(p.output_width), F(p.output_height)
+    ux, uy = (ux / ow) - F(0.5), (uy / oh) - F(0.5)
+    ux, uy = _gopro_map(ux, uy, q)
+    ux = ux / factor
+    return (ux + F(0.5)) * ow, (uy + F(0.5)) * oh
+
+
+def digital_stretch_undistort(ux, uy, p):    # digital_stretch.rs:12-15
+    return ux / F(p.digital_lens_params[0]), uy / F(p.digital_lens_params[1])
+
+
+DIGITAL_UNDISTORT = {"gopro_superview": _view_undistort(_superview, 1.333333333), "gopro6_superview": _view_undistort(_superview6, None),
+                     "gopro_hyperview": _view_undistort(_hyperview, 1.555555555), "gopro_warp": gopro_warp_undistort,
+                     "digital_stretch": digital_stretch_undistort}
+
+
 DIGITAL = {"gopro_superview": _view_distort(_superview, 1.333333333), "gopro6_superview": _view_distort(_superview6, None),
            "gopro_hyperview": _view_distort(_hyperview, 1.555555555), "gopro_warp": gopro_warp_distort, "digital_stretch": digital_stretch_distort}
 
@@ -452,18 +616,23 @@ def rotate_point(px, py, angle, ox, oy, o2x, o2y):           # cpu_undistort.rs:
     return (cosf(angle) * (px - ox) - sinf(angle) * (py - oy) + o2x, sinf(angle) * (px - ox) + cosf(angle) * (py - oy) + o2y)
 
 
-def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None, mesh=()):   # cpu_undistort.rs:421-517 (the lens-correction blend :429-460 for opencv_fisheye without a digital lens)
+def undistort_coord(x, y, p, m, lens="opencv_fisheye", digital=None, mesh=()):   # cpu_undistort.rs:421-517 (incl. the lens-correction blend :429-460)
     ox = map_coord(x, p.output_rect[0], p.output_rect[0] + p.output_rect[2], 0.0, p.output_width)
     oy = map_coord(y, p.output_rect[1], p.output_rect[1] + p.output_rect[3], 0.0, p.output_height)
     ox = ox + F(p.translation2d[0]); oy = oy + F(p.translation2d[1])
     lca = F(p.lens_correction_amount)
     if lca < F(1.0):                                         # :429-460 "add lens distortion back"
-        assert lens == "opencv_fisheye" and (digital is None or (p.flags & 2) == 0), "restated for opencv_fisheye only"
         factor = fmaxf(F(1.0) - lca, F(0.001))               # :525-527
         out_cx, out_cy = F(p.output_width) / F(2.0), F(p.output_height) / F(2.0)
         out_fx, out_fy = F(p.f[0]) / F(p.fov) / factor, F(p.f[1]) / F(p.fov) / factor
-        nx, ny = (ox - out_cx) / out_fx, (oy - out_cy) / out_fy
-        pt = fisheye_undistort_point(nx, ny, [F(v) for v in p.k])
+        nx, ny = ox, oy
+        if digital is not None and (p.flags & 2) == 2:       # :432-441 digital warp in the un-zoomed (fov = 1) frame
+            fov = F(p.fov)
+            uzx, uzy = (nx - out_cx) * fov + out_cx, (ny - out_cy) * fov + out_cy
+            d = DIGITAL_UNDISTORT[digital](uzx, uzy, p)
+            nx, ny = (d[0] - out_cx) / fov + out_cx, (d[1] - out_cy) / fov + out_cy
+        nx, ny = (nx - out_cx) / out_fx, (ny - out_cy) / out_fy
+        pt = UNDISTORT[lens](nx, ny, [F(v) for v in p.k])
         if pt is not None:
             nx, ny = pt
         lrc = F(p.light_refraction_coefficient)

@@ -247,3 +247,27 @@ def test_independent_numpy_restatement_mesh_ewa_feather_and_blend():
             warnings.simplefilter("ignore")
             np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=sdt, digital=digital, mesh=mesh)
         assert np.array_equal(got, want), (c, int((got != want).sum()))
+
+
+def test_independent_numpy_restatement_lens_correction_blend_every_model():
+    """The lens-correction blend (cpu_undistort.rs:429-460) calls undistort_point of the physical model and, with a digital lens, of the
+    digital one in the un-zoomed frame.  Every model's undistort_point — opencv_standard's 20-step fixed point, the radial Newton of poly3 /
+    poly5 / ptlens with its bail-out, the theta Newton of sony / generic_polynomial, insta360's 200-step fixed point, gopro's POLY with the
+    89-degree continuation, the forward polynomials of the *view / gopro_warp digital lenses, digital_stretch — restated a second time in
+    tests/np_restatement.py: same bytes as the C oracle."""
+    import warnings
+    from tests import cases, np_restatement
+    todo = [dict(w=56, h=32, lens=lens, params=dict(lens_correction_amount=0.35)) for lens in np_restatement.UNDISTORT]
+    todo += [dict(w=56, h=32, digital=d, params=dict(lens_correction_amount=0.5)) for d in ("gopro_superview", "gopro6_superview", "gopro_hyperview", "digital_stretch")]
+    todo += [dict(w=56, h=32, lens="gopro", digital="gopro_warp", params=dict(lens_correction_amount=0.6)),
+             dict(w=56, h=32, lens="poly3", fov=2.5, params=dict(lens_correction_amount=0.1)),            # far off axis: the Newton bail-out (None) path
+             dict(w=56, h=32, lens="sony", digital="gopro_superview", fov=1.4, params=dict(lens_correction_amount=0.0, light_refraction_coefficient=1.33))]
+    for c in todo:
+        p, src, m, mesh, dst0, pix, lens, digital = cases.build(c)
+        want = dst0.copy()
+        assert oracle_lib.undistort_image(src, want, p, pix, lens, digital, m, mesh) == 0
+        got = dst0.copy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np_restatement.undistort_image(src, got, p, m, lens=lens, sdt=np.uint8, digital=digital, mesh=mesh)
+        assert np.array_equal(got, want), (c, int((got != want).sum()))
