@@ -82,3 +82,51 @@ def test_generate_stmap_matches_oracle(lens, digital, per_frame, kw):
     assert np.array_equal(und, want_und), "undistort map differs: %d values" % int((und != want_und).sum())
     # the redistort map goes through f64 rotation matrices built with device vs host libm: equal to 1e-6 (bit-equal in practice)
     assert np.allclose(dist, want_dist, rtol=1e-6, atol=1e-6, equal_nan=True), float(np.nanmax(np.abs(dist - want_dist)))
+
+
+def test_oracle_stmap_matches_second_restatement():
+    """generate_stmaps (stmap.rs:24-136) for opencv_fisheye with the SECOND transcriptions: the undistort map from
+    tests/np_restatement.rotate_and_distort + the rolling-shutter row pick of :88-109, the redistort map from
+    tests/np_zoom.undistort_points_with_rolling_shutter(use_fovs = true), both in the (x / w, 1 - y / h, 0) encoding of :131-135 —
+    against the oracle's maps.  The undistort map is byte-identical given the same matrices; the redistort map within the 1e-6 its f64
+    rotations allow."""
+    import warnings
+    from tests import np_restatement as npr, np_zoom
+    for per_frame in (True, False):
+        cp = make_cp(w=64, h=36)
+        ts, frame = 1000.0 / 60.0 * 40, 40
+        nw, nh, want_dist, want_und = oracle_stmap(cp, "opencv_fisheye", None, ts, frame, per_frame)
+        # ---- the state generate_stmaps leaves compute_params in for each map (:28-34, :73-76, :112-113) ----
+        c = cp.c
+        w, h = c.width, c.height
+        saved = (c.frame_readout_time, c.suppress_rotation, c.n_fovs, c.fov_scale)
+        if not per_frame: c.frame_readout_time = 0.0
+        c.suppress_rotation = 1; c.n_fovs = 0
+        c.fov_scale = float(max(F(nw) / F(w), F(nh) / F(h)))
+        c.width = c.output_width = nw; c.height = c.output_height = nh
+        kp, mats, _, _ = cp.at_timestamp(ts, frame)
+        kp.width = kp.output_width = nw; kp.height = kp.output_height = nh
+        kp.flags = 0
+        m = [[F(v) for v in row] for row in np.asarray(mats, dtype=np.float32)]
+        got_und = np.zeros((nh, nw, 3), np.float32)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for yi in range(nh):
+                for xi in range(nw):
+                    x, y = F(xi), F(yi)
+                    sy = max(min(npr.as_i32(npr.round_half_away(y)), kp.height), 0)
+                    if kp.matrix_count > 1:
+                        pt = npr.rotate_and_distort(x, y, kp.matrix_count // 2, kp, m)
+                        if pt is not None:
+                            sy = max(min(npr.as_i32(npr.round_half_away(pt[1])), kp.height), 0)
+                    uv = npr.rotate_and_distort(x, y, min(sy, kp.matrix_count - 1), kp, m) or (F(0.0), F(0.0))
+                    got_und[yi, xi] = (uv[0] / F(nw), F(1.0) - (uv[1] / F(nh)), 0.0)
+            assert np.array_equal(got_und, want_und)
+            c.width = c.output_width = w; c.height = c.output_height = h
+            got_dist = np.zeros((h, w, 3), np.float32)
+            for yi in range(0, h, 5):                                      # every 5th row keeps the pure-Python loop short
+                for xi in range(w):
+                    (ux, uy), = np_zoom.undistort_points_with_rolling_shutter(cp, [(F(xi), F(yi))], ts, frame, 1.0, use_fovs=True)
+                    got_dist[yi, xi] = (ux / F(w), F(1.0) - (uy / F(h)), 0.0)
+            assert np.allclose(got_dist[::5], want_dist[::5], rtol=0, atol=2e-6)
+        c.frame_readout_time, c.suppress_rotation, c.n_fovs, c.fov_scale = saved
