@@ -204,3 +204,49 @@ def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0):             
         polygon = shifted(interpolate_points(relevant, 30))
         nearest = nearest_edge(polygon, center, nearest[1], inv_aspect)
     return float(nearest[1][0] * F(2.0) / output_dim[0])
+
+
+# ---- zoom_dynamic::compute, static-window branch — src/core/zooming/zoom_dynamic.rs:56-76 and helpers :80-124, :167-191 (Python floats = f64) ----
+def zoom_dynamic(fov_values, window_s, fps, method):
+    """method 0: GaussianFilter (rolling minimum, then a normalised Gaussian over `frames` samples); 1: EnvelopeFollower (two passes)."""
+    v = [float(x) for x in fov_values]
+
+    def pad_edge(arr, n):                                                         # :111-124
+        return [arr[0]] * n + list(arr) + [arr[-1]] * n
+
+    def envelope_follower(a, alpha):                                              # :167-191 with a constant alpha
+        q = a[-1]
+        rev = []
+        for x in reversed(a):
+            q = min(x, x * alpha + q * (1.0 - alpha))
+            rev.append(q)                                                         # rev[0] belongs to the LAST sample
+        q = rev[-1]
+        out = []
+        for x in reversed(rev):
+            q = min(x, x * alpha + q * (1.0 - alpha))
+            out.append(q)
+        return out
+
+    if method == 0:
+        frames = int(math.floor(window_s * fps))                                  # get_frames_per_window :80-86
+        if frames % 2 == 0:
+            frames += 1
+        padded = pad_edge(v, frames // 2)
+        fov_min = [min(padded[i:i + frames]) for i in range(len(padded) - frames + 1)]          # min_rolling :88-92
+        padded = pad_edge(fov_min, frames // 2)
+        std = frames / 6.0
+        sig2 = 2.0 * std ** 2                                                     # gaussian_window :100-103 (powi(2) == x * x)
+        half = frames // 2
+        w = [math.exp(-float(x * x) / sig2) for x in range(-half, half + 1)]
+        s = 0.0
+        for t in w: s += t
+        w = [t / s for t in w]                                                    # gaussian_window_normalized :105-110
+        out = []
+        for i in range(len(padded) - frames + 1):                                 # convolve :94-98: left-to-right sum of products
+            acc = 0.0
+            for x, y in zip(padded[i:i + frames], w): acc += x * y
+            out.append(acc)
+        return out
+    first = 1.0 - math.exp(-(1.0 / fps) / window_s)                               # :69-73
+    second = 1.0 - math.exp(-(1.0 / fps) / 0.2)
+    return envelope_follower(envelope_follower(v, first), second)

@@ -38,6 +38,11 @@ def test_zoom_dynamic_host_matches_oracle_bit_for_bit():
         b = oracle_lib.zoom_dynamic(fm, 4.0, 60.0, method)
         assert np.array_equal(a, b)
         assert (a <= fm + 1e-12).all() if method == 1 else a.shape == fm.shape      # the envelope never exceeds the per-frame minimum
+        from tests import np_zoom
+        assert np.array_equal(a, np.asarray(np_zoom.zoom_dynamic(fm, 4.0, 60.0, method)))       # second transcription (zoom_dynamic.rs:56-76)
+    for window_s, fps in ((0.5, 29.97), (2.0, 24.0)):                            # even / odd window lengths
+        for method in (0, 1):
+            assert np.array_equal(g.zoom_dynamic(fm[:97], window_s, fps, method), np.asarray(np_zoom.zoom_dynamic(fm[:97], window_s, fps, method)))
 
 
 @pytest.mark.gpu
