@@ -387,8 +387,13 @@ static double zoom_keyframed(const gf_compute_params& cp, int typ, double ts, do
     return v;
 }
 // at_timestamp_for_points / undistort_points for ONE timestamp: the tracks they read become the constants of a private copy
-static gf_compute_params resolve_point_keyframes(const gf_compute_params& cp, double ts) {
+static gf_compute_params resolve_point_keyframes(const gf_compute_params& cp, double ts, size_t frame) {
     gf_compute_params r = cp;
+    if (cp.lens_per_frame && frame < cp.n_lens_per_frame) {                         // get_lens_data_at_timestamp of this frame (:360)
+        const gf_lens_data& L = cp.lens_per_frame[frame];
+        memcpy(r.camera_matrix, L.camera_matrix, sizeof(r.camera_matrix)); memcpy(r.distortion_coeffs, L.distortion_coeffs, sizeof(r.distortion_coeffs));
+        r.radial_distortion_limit = L.radial_distortion_limit;
+    }
     r.video_rotation = zoom_keyframed(cp, GF_KF_VIDEO_ROTATION, ts, cp.video_rotation);                                  // frame_transform.rs:354
     r.light_refraction_coefficient = zoom_keyframed(cp, GF_KF_LIGHT_REFRACTION_COEFF, ts, cp.light_refraction_coefficient);   // cpu_undistort.rs:661
     r.fov_scale = zoom_keyframed(cp, GF_KF_FOV, ts, cp.fov_scale);                                                       // get_fov :53
@@ -480,7 +485,7 @@ GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp
     if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
     if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }
     ZoomArgs A;
-    const gf_compute_params rcp = resolve_point_keyframes(*cp_user, timestamp_ms);     // video rotation, refraction, Fov at this timestamp
+    const gf_compute_params rcp = resolve_point_keyframes(*cp_user, timestamp_ms, frame);     // video rotation, refraction, Fov at this timestamp
     const gf_compute_params* cp = &rcp;
     const double fov = gf_points_fov(cp, frame, use_fovs);
     const double frt = setup_points_args(g, *cp, distortion_model, fov, lens_correction_amount, A);
@@ -507,7 +512,7 @@ GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* c
     if (!g || !cp_user || !out_rgb_dev) return GF_ERR_BAD_PARAMS;
     PointsFn fn = pick_points(distortion_model, digital_lens);
     if (!fn) return GF_ERR_UNSUPPORTED_COMBO;
-    const gf_compute_params rcp = resolve_point_keyframes(*cp_user, timestamp_ms);     // video rotation, refraction, Fov at this timestamp
+    const gf_compute_params rcp = resolve_point_keyframes(*cp_user, timestamp_ms, frame);     // video rotation, refraction, Fov at this timestamp
     const gf_compute_params* cp = &rcp;
     if (cp->width < 1 || cp->height < 1) return GF_ERR_BAD_PARAMS;
     if (cudaSetDevice(g->device) != cudaSuccess) { (void)cudaGetLastError(); return GF_ERR_CUDA; }

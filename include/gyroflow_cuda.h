@@ -391,7 +391,8 @@ typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_p
     double  keyframe_timestamp_scale;                            /* KeyframeManager::timestamp_scale; 0 = None (1.0) */
     /* per-frame result of get_lens_data_at_timestamp (:82-163) for clips whose lens changes over time (interpolated lens profiles,
      * telemetry lens_params of zoom lenses): entry `frame` replaces camera_matrix / distortion_coeffs / radial_distortion_limit /
-     * input_*_stretch above in at_timestamp.  Rust evaluates it once per job; NULL = the constants above for every frame. */
+     * input_*_stretch above in at_timestamp, and camera_matrix / distortion_coeffs in the single-timestamp point path (gf_cuda_undistort_points,
+     * ST maps); gf_cuda_find_fovs keeps the constants.  Rust evaluates it once per job; NULL = the constants above for every frame. */
     const struct gf_lens_data* lens_per_frame; size_t n_lens_per_frame;
 } gf_compute_params;
 typedef struct gf_lens_data {
