@@ -1,7 +1,7 @@
 """Second, independent restatement of the adaptive-zoom companion — TEST INFRASTRUCTURE ONLY.
 
   at_timestamp_for_points   <- FrameTransform::at_timestamp_for_points    src/core/stabilization/frame_transform.rs:352-410
-  undistort_points          <- undistort_points (opencv_fisheye, no digital lens / mesh / IBIS shifts)
+  undistort_points          <- undistort_points (every lens model and digital lens; no mesh / IBIS shifts)
                                                                            src/core/stabilization/cpu_undistort.rs:652-858
   find_fov                  <- FovIterative::find_fov / nearest_edge / points_around_rect / interpolate_points
                                                                            src/core/zooming/fov_iterative.rs:76-200
@@ -16,7 +16,8 @@ import numpy as np
 
 from gyroflow_b200.synth import q_mul, q_inv
 from tests import np_producer
-from tests.np_restatement import F, fisheye_distort, fisheye_undistort_point, sqrtf
+from tests import np_restatement as npr
+from tests.np_restatement import F, sqrtf
 
 
 def get_fov(c, frame, use_fovs):                                                  # frame_transform.rs:52-58 (no Fov keyframe here)
@@ -74,8 +75,18 @@ def _refract(px, py, lrc):                                                      
     return px, py
 
 
-def undistort_points(cp, points, K, rotations, lens_correction_amount, fov):      # cpu_undistort.rs:652-858, opencv_fisheye only
+class _KP:                                                                         # the KernelParams undistort_points builds (:671-683)
+    pass
+
+
+def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:652-858 (no mesh / IBIS shifts)
     c = cp.c
+    kp = _KP()
+    kp.width, kp.height, kp.output_width, kp.output_height = c.width, c.height, c.output_width, c.output_height
+    kp.digital_lens_params = [F(v) for v in list(c.digital_lens_params)]
+    und, dist = npr.UNDISTORT[lens], npr.DISTORT[lens]
+    dund = npr.DIGITAL_UNDISTORT[digital] if digital else None
+    ddist = npr.DIGITAL[digital] if digital else None
     fx, fy, cx, cy = F(K[0, 0]), F(K[1, 1]), F(K[0, 2]), F(K[1, 2])
     k = [F(v) for v in list(c.distortion_coeffs)]
     lrc = F(c.light_refraction_coefficient)
@@ -91,9 +102,11 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov):    
         x, y = F(x), F(y)
         if c.input_horizontal_stretch > 0.001: x = x * F(c.input_horizontal_stretch)      # :702-703
         if c.input_vertical_stretch > 0.001: y = y * F(c.input_vertical_stretch)
+        if dund is not None:                                                       # :705-710
+            x, y = dund(x, y, kp)
         pwx, pwy = (x - cx) / fx, (y - cy) / fy                                    # :760
         rot = np.asarray(rotations[index] if index < len(rotations) else rotations[0], dtype=np.float64).astype(np.float32)
-        pt = fisheye_undistort_point(pwx, pwy, k)
+        pt = und(pwx, pwy, k)
         if pt is None:
             out.append((F(-1000000.0), F(-1000000.0)))
             continue
@@ -104,15 +117,23 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov):    
             out_c, amount, factor, out_f = lc
 
             def r_of(ox, oy):
+                if dund is not None:                                               # un-zoom -> digital warp -> re-zoom (:795-801)
+                    uzx, uzy = (ox - out_c[0]) * F(fov) + out_c[0], (oy - out_c[1]) * F(fov) + out_c[1]
+                    d = dund(uzx, uzy, kp)
+                    ox, oy = (d[0] - out_c[0]) / F(fov) + out_c[0], (d[1] - out_c[1]) / F(fov) + out_c[1]
                 nx, ny = (ox - out_c[0]) / out_f[0], (oy - out_c[1]) / out_f[1]
-                d = fisheye_undistort_point(nx, ny, k)
+                d = und(nx, ny, k)
                 if d is not None: nx, ny = d
                 nx, ny = _refract(nx, ny, lrc)
                 return (nx * out_f[0]) + out_c[0], (ny * out_f[1]) + out_c[1]
 
             nx, ny = (px - out_c[0]) / out_f[0], (py - out_c[1]) / out_f[1]
-            dx, dy = fisheye_distort(nx, ny, F(1.0), k)
+            dx, dy = dist(nx, ny, F(1.0), k)
             p2x, p2y = (dx * out_f[0]) + out_c[0], (dy * out_f[1]) + out_c[1]
+            if ddist is not None:                                                  # :826-830
+                uzx, uzy = (p2x - out_c[0]) * F(fov) + out_c[0], (p2y - out_c[1]) * F(fov) + out_c[1]
+                dd = ddist(uzx, uzy, kp)
+                p2x, p2y = (dd[0] - out_c[0]) / F(fov) + out_c[0], (dd[1] - out_c[1]) / F(fov) + out_c[1]
             if math.isfinite(float(p2x)) and math.isfinite(float(p2y)):
                 ox, oy = p2x * factor + px * amount, p2y * factor + py * amount
             else:
@@ -137,9 +158,9 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov):    
     return out
 
 
-def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False):   # :636-641
+def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False, lens="opencv_fisheye", digital=None):   # :636-641
     K, rotations, fov = at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs)
-    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov)
+    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens, digital)
 
 
 def points_around_rect(w, h, w_div, h_div, margin):                                # fov_iterative.rs:154-177
@@ -176,7 +197,7 @@ def nearest_edge(polygon, center, initial, inv_aspect):                         
     return idx, mp
 
 
-def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0):               # FovIterative::new :76-89 + find_fov :91-134
+def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0, lens="opencv_fisheye", digital=None):               # FovIterative::new :76-89 + find_fov :91-134
     """`cp` must already carry the calculate_fovs adjustments (zooming/mod.rs:41-49): fov_scale 1, no fovs, output size = input size."""
     c = cp.c
     ratio = F(c.width) / F(max(org_output_size[0], 1))
@@ -188,7 +209,7 @@ def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0):             
     zx, zy, lca = c.adaptive_zoom_center_offset[0], c.adaptive_zoom_center_offset[1], c.lens_correction_amount
 
     def shifted(pts):
-        poly = undistort_points_with_rolling_shutter(cp, pts, timestamp_ms, frame, lca, False)
+        poly = undistort_points_with_rolling_shutter(cp, pts, timestamp_ms, frame, lca, False, lens, digital)
         return [(x - F(zx) * input_dim[0], y - F(zy) * input_dim[1]) for x, y in poly]
 
     polygon = shifted(rect)

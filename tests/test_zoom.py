@@ -105,21 +105,25 @@ def test_device_find_fovs_with_keyframes_matches_oracle_per_frame():
 
 @pytest.mark.parametrize("kw", [dict(), dict(ow=1280, oh=720), dict(video_rotation=12.0), dict(frame_readout_time_ms=0.0),
                                 dict(params=dict(lens_correction_amount=0.4)), dict(params=dict(lens_correction_amount=0.7, light_refraction_coefficient=1.33)),
-                                dict(horizontal=True, inverted=True)])
+                                dict(horizontal=True, inverted=True),
+                                dict(lens="sony"), dict(lens="opencv_standard", digital="digital_stretch"), dict(lens="gopro", digital="gopro_warp"),
+                                dict(digital="gopro_superview", params=dict(lens_correction_amount=0.4)), dict(lens="poly5", params=dict(lens_correction_amount=0.7)),
+                                dict(lens="insta360"), dict(lens="generic_polynomial", digital="gopro_hyperview")])
 def test_oracle_find_fov_matches_second_restatement(kw):
     """FovIterative::find_fov over undistort_points_with_rolling_shutter, restated a second time in numpy scalars (tests/np_zoom.py, from
     fov_iterative.rs:76-200, cpu_undistort.rs:652-858, frame_transform.rs:352-410) == the C oracle, to the 1e-6 the rotations allow (numpy's
     slerp / matrix products vs the oracle's); most frames are bit-identical."""
     import warnings
     from tests import np_zoom
-    cp = make_cp(lens="opencv_fisheye", **dict(kw))
+    kw = dict(kw); lens = kw.pop("lens", "opencv_fisheye"); digital = kw.pop("digital", None)
+    cp = make_cp(lens=lens, digital=digital, **dict(kw))
     ts = np.arange(0, 120, 17) * (1000.0 / 60.0)
-    want = oracle_lib.find_fovs(cp, "opencv_fisheye", None, ts)
+    want = oracle_lib.find_fovs(cp, lens, digital, ts)
     org = (cp.c.output_width, cp.c.output_height)
-    adj = make_cp(lens="opencv_fisheye", **dict(kw))                  # calculate_fovs adjustments, zooming/mod.rs:41-49
+    adj = make_cp(lens=lens, digital=digital, **dict(kw))             # calculate_fovs adjustments, zooming/mod.rs:41-49
     adj.c.fov_scale = 1.0; adj.c.n_fovs = 0; adj.c.n_minimal_fovs = 0; adj.c.output_width = adj.c.width; adj.c.output_height = adj.c.height
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        got = np.array([np_zoom.find_fov(adj, org, float(t), i) for i, t in enumerate(ts)])
+        got = np.array([np_zoom.find_fov(adj, org, float(t), i, lens=lens, digital=digital) for i, t in enumerate(ts)])
     assert np.allclose(got, want, rtol=1e-6, atol=0), (got, want)
     assert (got == want).mean() >= 0.5 and 0.3 < want.min() and want.max() < 3.0
