@@ -2,7 +2,7 @@
 //
 // Behavioural source: FovIterative::find_fov / nearest_edge / points_around_rect / interpolate_points
 // (src/core/zooming/fov_iterative.rs:91-189), undistort_points_with_rolling_shutter + undistort_points
-// (src/core/stabilization/cpu_undistort.rs:636-858, no mesh / IBIS shifts), FrameTransform::at_timestamp_for_points
+// (src/core/stabilization/cpu_undistort.rs:636-858, with the IBIS / OIS shifts, no mesh), FrameTransform::at_timestamp_for_points
 // (src/core/stabilization/frame_transform.rs:352-438), calculate_fovs (src/core/zooming/mod.rs:35-70) and the
 // static-window temporal filters of zoom_dynamic.rs:56-126,177-200.
 //
@@ -27,9 +27,15 @@ typedef Quat ZQuat;
 typedef Track ZTrack;
 __host__ __device__ inline ZQuat zq_mul(const ZQuat& a, const ZQuat& b) { return qmul(a, b); }
 
+struct ZoomStab {               // camera_stab_data[frame] as at_timestamp_for_points uses it (frame_transform.rs:412-431); spline points in HBM
+    int present;
+    double offset, crop_y, crop_h, scale_x, scale_y, height;
+    Spline3 ibis, ois;
+};
 struct ZoomFrame {              // per-frame uniforms (host, f64)
     ZQuat q0;                   // smoothed(ts) * org(ts)^-1
     double start_ts;
+    ZoomStab stab;
     // keyframed values of this frame (fov_iterative.rs:44-46, frame_transform.rs:354, cpu_undistort.rs:661); `keyed` = some track exists
     int keyed;
     double rot_c, rot_s;
@@ -67,6 +73,23 @@ __device__ void point_rotation(const ZoomArgs& A, const ZoomFrame& F, float px, 
     for (int t = 0; t < 9; ++t) rot[t] = (float)m[t];
 }
 
+// The IBIS / OIS shift of point `index` — frame_transform.rs:412-431.  points_iter is the point list when rolling-shutter correction is
+// on and the single point (0, 0) otherwise, so with correction off only index 0 has an entry (cpu_undistort.rs:748 `v.get(index)`).
+__device__ bool point_shift(const ZoomArgs& A, const ZoomFrame& F, float py, size_t index, float (&sh)[5]) {
+    const ZoomStab& S = F.stab;
+    if (!S.present) return false;
+    if (!A.rs_on && index != 0) return false;
+    const double yy = A.rs_on ? (double)py : 0.0;
+    const double y = (yy - 0.0) * ((S.crop_y + S.crop_h) - S.crop_y) / (S.height - 0.0) + S.crop_y;       // map_coord (util.rs:144-147), f64
+    double s[3], o[3];
+    if (!catmull_rom3(S.ibis, y + S.offset, s)) { s[0] = 0.0; s[1] = 0.0; s[2] = 0.0; }                  // .unwrap_or_default()
+    if (!catmull_rom3(S.ois,  y + S.offset, o)) { o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; }
+    const double ra = s[2] / 1000.0;
+    sh[0] = (float)(s[0] * S.scale_x); sh[1] = (float)(s[1] * S.scale_y); sh[2] = (float)(ra * (M_PI / 180.0));
+    sh[3] = (float)(o[0] * S.scale_x); sh[4] = (float)(o[1] * S.scale_y);
+    return true;
+}
+
 template <int LENS, int DIGITAL>
 __device__ void lc_r_of(const ZoomArgs& A, float ox, float oy, float& rx, float& ry) {        // cpu_undistort.rs:794-815
     const gf_kernel_params& P = A.kp;
@@ -93,7 +116,7 @@ __device__ void lc_r_of(const ZoomArgs& A, float ox, float oy, float& rx, float&
 
 // one point of undistort_points — cpu_undistort.rs:699-857
 template <int LENS, int DIGITAL>
-__device__ void undistort_point_rs(const ZoomArgs& A, const ZoomFrame& F, float px, float py, float& outx, float& outy) {
+__device__ void undistort_point_rs(const ZoomArgs& A, const ZoomFrame& F, float px, float py, size_t index, float& outx, float& outy) {
     const gf_kernel_params& P = A.kp;
     float rot[9];
     point_rotation(A, F, px, py, rot);                  // rotation time uses the *distorted* point (:393)
@@ -101,6 +124,14 @@ __device__ void undistort_point_rs(const ZoomArgs& A, const ZoomFrame& F, float 
     if (A.hstretch != 0.0f) x *= A.hstretch;
     if (A.vstretch != 0.0f) y *= A.vstretch;
     if (DIGITAL != GF_LENS_NONE) { float tx, ty; if (Lens<DIGITAL>::undistort(x, y, P, false, tx, ty)) { x = tx; y = ty; } }
+    float sh[5];
+    if (point_shift(A, F, py, index, sh)) {             // cpu_undistort.rs:748-757 (sic: y is rotated with the already rotated x)
+        const float cos_a = gf_cosf(sh[2]), sin_a = gf_sinf(sh[2]);
+        x = x - A.cx - sh[3] + sh[0];
+        y = y - A.cy - sh[4] + sh[1];
+        x = cos_a * x - sin_a * y + A.cx;
+        y = sin_a * x + cos_a * y + A.cy;
+    }
     const float pwx = (x - A.cx) / A.fx, pwy = (y - A.cy) / A.fy;
     float ptx, pty;
     if (!Lens<LENS>::undistort(pwx, pwy, P, A.lens_noop != 0, ptx, pty)) { outx = -1000000.0f; outy = -1000000.0f; return; }
@@ -189,7 +220,7 @@ __global__ void __launch_bounds__(128) find_fov_kernel(const __grid_constant__ Z
     if (tid < ZOOM_RECT_LEN) {
         float x, y; rect_point(A, tid, x, y);
         rect[2 * tid] = x; rect[2 * tid + 1] = y;
-        float ux, uy; undistort_point_rs<LENS, DIGITAL>(A, F, x, y, ux, uy);
+        float ux, uy; undistort_point_rs<LENS, DIGITAL>(A, F, x, y, (size_t)tid, ux, uy);
         poly[2 * tid] = ux - A.zc_x; poly[2 * tid + 1] = uy - A.zc_y;
     }
     if (tid == 0) { sw = 1000000.0f; sh = 1000000.0f * A.inv_aspect; }
@@ -220,7 +251,7 @@ __global__ void __launch_bounds__(128) find_fov_kernel(const __grid_constant__ Z
             const float f = (float)(tid % d) / (float)d;
             const float dx = rect[2 * ra] + f * (rect[2 * rb] - rect[2 * ra]);
             const float dy = rect[2 * ra + 1] + f * (rect[2 * rb + 1] - rect[2 * ra + 1]);
-            undistort_point_rs<LENS, DIGITAL>(A, F, dx, dy, nx, ny);
+            undistort_point_rs<LENS, DIGITAL>(A, F, dx, dy, (size_t)tid, nx, ny);
         }
         __syncthreads();                                 // everyone has read rect/poly of this round
         if (tid < ZOOM_INTERP_LEN) { poly[2 * tid] = nx - A.zc_x; poly[2 * tid + 1] = ny - A.zc_y; }
@@ -276,7 +307,7 @@ __global__ void __launch_bounds__(128) points_kernel(const ZoomArgs A, const Zoo
     if (pts) { const float2 p = pts[i]; px = p.x; py = p.y; }
     else     { px = (float)(int)(i % (size_t)grid_w); py = (float)(int)(i / (size_t)grid_w); }
     float ox, oy;
-    undistort_point_rs<LENS, DIGITAL>(A, F, px, py, ox, oy);
+    undistort_point_rs<LENS, DIGITAL>(A, F, px, py, pts ? i : (size_t)0, ox, oy);      // ST map: every pixel is its own one-point call (stmap.rs:114-116)
     if (pts) { out[2 * i] = ox; out[2 * i + 1] = oy; }
     else     { out[3 * i] = ox / (float)grid_w; out[3 * i + 1] = 1.0f - (oy / (float)grid_h); out[3 * i + 2] = 0.0f; }
 }
@@ -369,7 +400,7 @@ static double setup_points_args(const gf_cuda_gyro* g, const gf_compute_params& 
     return frt;
 }
 // smoothed(ts) * org(ts)^-1 and the readout start time of one frame — frame_transform.rs:376-388
-static ZoomFrame frame_uniforms(const gf_compute_params& cp, double ts, double frt, size_t frame) {
+static ZoomFrame frame_uniforms(const gf_cuda_gyro* g, const gf_compute_params& cp, double ts, double frt, size_t frame) {
     if (cp.per_frame_time_offsets && frame < cp.n_per_frame_time_offsets) ts += cp.per_frame_time_offsets[frame];     // frame_transform.rs:384
     const ZTrack horg{ cp.org.ts_us, cp.org.quats, cp.org.n }, hsm{ cp.smoothed.ts_us, cp.smoothed.quats, cp.smoothed.n };
     ZoomFrame f;
@@ -378,6 +409,17 @@ static ZoomFrame frame_uniforms(const gf_compute_params& cp, double ts, double f
     f.q0 = zq_mul(quat_at_timestamp(hsm, cp.duration_ms, ho, ts), q1);
     f.start_ts = ts - frt / 2.0;
     f.keyed = 0;
+    memset(&f.stab, 0, sizeof(f.stab));
+    if (cp.camera_stab && frame < cp.n_camera_stab && frame < g->stab_index.size() && !(cp.suppress_rotation && cp.frame_readout_time == 0.0)) {   // :412, :432-434
+        const gf_camera_stab& is = cp.camera_stab[frame];
+        const gf_cuda_gyro::StabIndex& ix = g->stab_index[frame];
+        f.stab.present = 1;
+        f.stab.offset = is.offset; f.stab.crop_y = (double)is.crop_area[1]; f.stab.crop_h = (double)is.crop_area[3]; f.stab.height = (double)cp.height;
+        f.stab.scale_x = (double)cp.width  / (double)is.crop_area[2] / (double)is.pixel_pitch[0];
+        f.stab.scale_y = (double)cp.height / (double)is.crop_area[3] / (double)is.pixel_pitch[1];
+        f.stab.ibis = Spline3{ g->d_stab + ix.ibis_pos, g->d_stab + ix.ibis_val, ix.n_ibis };
+        f.stab.ois  = Spline3{ g->d_stab + ix.ois_pos,  g->d_stab + ix.ois_val,  ix.n_ois };
+    }
     return f;
 }
 // KeyframeManager::value_at_video_timestamp(...).unwrap_or(default) for one of the tracks in gf_compute_params
@@ -457,7 +499,7 @@ GF_API int gf_cuda_find_fovs(gf_cuda_gyro* g, const gf_compute_params* cp_user, 
         A.out_cx = (float)cp.output_width / 2.0f; A.out_cy = (float)cp.output_height / 2.0f; A.fov = (float)fov;
     }
     for (size_t i = 0; i < n; ++i) {
-        hf[i] = frame_uniforms(cp, timestamps_ms[i], frt, i);
+        hf[i] = frame_uniforms(g, cp, timestamps_ms[i], frt, i);
         if (keyed) fill_keyed(hf[i], cp, A, timestamps_ms[i], fov, cp.lens_correction_amount, true);
     }
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
@@ -489,7 +531,7 @@ GF_API int gf_cuda_undistort_points(gf_cuda_gyro* g, const gf_compute_params* cp
     const gf_compute_params* cp = &rcp;
     const double fov = gf_points_fov(cp, frame, use_fovs);
     const double frt = setup_points_args(g, *cp, distortion_model, fov, lens_correction_amount, A);
-    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt, frame);
+    const ZoomFrame F = frame_uniforms(g, *cp, timestamp_ms, frt, frame);
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     float2* d_in = nullptr; float* d_out = nullptr;
     cudaError_t e;
@@ -519,7 +561,7 @@ GF_API int gf_cuda_stmap_distort_dev(gf_cuda_gyro* g, const gf_compute_params* c
     ZoomArgs A;
     const double fov = gf_points_fov(cp, frame, 1);
     const double frt = setup_points_args(g, *cp, distortion_model, fov, 1.0, A);
-    const ZoomFrame F = frame_uniforms(*cp, timestamp_ms, frt, frame);
+    const ZoomFrame F = frame_uniforms(g, *cp, timestamp_ms, frt, frame);
     cudaStream_t st = cu_stream ? (cudaStream_t)cu_stream : g->stream;
     const size_t n = (size_t)cp->width * (size_t)cp->height;
     fn<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, F, nullptr, n, cp->width, cp->height, out_rgb_dev);

@@ -1288,6 +1288,50 @@ static double pts_get_fov(const gf_compute_params* cp, size_t frame, int use_fov
     return fov * (double)cp->width / (double)(cp->output_width > 1 ? cp->output_width : 1);
 }
 
+/* CatmullRom<Vector3<f64>>::interpolate — gyro_source/splines.rs:22-83 (search_lower_cp :57-73, catmull_rom :75-80).
+ * pos[n] ascending, val[n][3].  Returns 0 for None. */
+static int catmull_rom3(const double* pos, const double* val, size_t n, double t, double out[3]) {
+    if (n < 2 || t != t) return 0;
+    size_t lo = 0, hi = n;                                           /* binary_search_by: first index with pos >= t */
+    while (lo < hi) { size_t mid = lo + (hi - lo) / 2; if (pos[mid] < t) lo = mid + 1; else hi = mid; }
+    size_t lower;
+    if (lo < n && pos[lo] == t) { if (lo == n - 1) return 0; lower = lo; }          /* Ok(i) */
+    else { if (lo >= n || lo == 0) return 0; lower = lo - 1; }                     /* Err(i) */
+    if (lower + 1 >= n) return 0;
+    const double k = (t - pos[lower]) / (pos[lower + 1] - pos[lower]);              /* normalize */
+    for (int c = 0; c < 3; ++c) {
+        const double a = val[3 * lower + c], b = val[3 * (lower + 1) + c];
+        const double x = lower == 0 ? a * 2.0 - b : val[3 * (lower - 1) + c];
+        const double y = lower + 2 >= n ? b * 2.0 - a : val[3 * (lower + 2) + c];
+        out[c] = ((((a * 3.0 - x) - b * 3.0) + y) * 0.5) * k * k * k + ((b - x) * 0.5) * k + a + (((b * 4.0 + a * -5.0 + x + x) - y) * 0.5) * k * k;
+    }
+    return 1;
+}
+/* the `shifts` of at_timestamp_for_points — frame_transform.rs:412-434: (sx, sy, ra, ox, oy) per element of points_iter (ONE element,
+ * the point (0, 0), when rolling-shutter correction is off).  Returns the number of entries written (0 = None). */
+static size_t shifts_for_points(const gf_compute_params* cp, const float* pts, size_t n, size_t frame, float* shifts /* n x 5 */) {
+    if (!cp->camera_stab || frame >= cp->n_camera_stab) return 0;
+    if (cp->suppress_rotation && cp->frame_readout_time == 0.0) return 0;                                   /* :432-434 */
+    const gf_camera_stab* is = &cp->camera_stab[frame];
+    double frt = fabs(cp->frame_readout_time);
+    const size_t cnt = frt > 0.0 ? n : 1;
+    const double scale_x = (double)cp->width  / (double)is->crop_area[2] / (double)is->pixel_pitch[0];
+    const double scale_y = (double)cp->height / (double)is->crop_area[3] / (double)is->pixel_pitch[1];
+    for (size_t p = 0; p < cnt; ++p) {
+        const double py = frt > 0.0 ? (double)pts[2 * p + 1] : 0.0;
+        const double out_min = (double)is->crop_area[1], out_max = (double)is->crop_area[1] + (double)is->crop_area[3];
+        const double y = (py - 0.0) * (out_max - out_min) / ((double)cp->height - 0.0) + out_min;         /* map_coord, f64 */
+        double s[3] = {0.0, 0.0, 0.0}, o[3] = {0.0, 0.0, 0.0};
+        if (!catmull_rom3(is->ibis_pos, is->ibis_xyz, is->n_ibis, y + is->offset, s)) { s[0] = s[1] = s[2] = 0.0; }
+        if (!catmull_rom3(is->ois_pos, is->ois_xyz, is->n_ois, y + is->offset, o)) { o[0] = o[1] = o[2] = 0.0; }
+        const double ra = s[2] / 1000.0;
+        float* d = shifts + 5 * p;
+        d[0] = (float)(s[0] * scale_x); d[1] = (float)(s[1] * scale_y); d[2] = (float)(ra * (M_PI / 180.0));
+        d[3] = (float)(o[0] * scale_x); d[4] = (float)(o[1] * scale_y);
+    }
+    return cnt;
+}
+
 /* at_timestamp_for_points — frame_transform.rs:352-438: per-point K_new * R (f64), use_fovs = false */
 static void rotations_for_points(const gf_compute_params* cp, const float* pts, size_t n, double timestamp_ms, size_t frame, int use_fovs,
                                  double* rot /* n x 9 */, double* fov_out) {
@@ -1350,7 +1394,8 @@ static v2 lc_r_of(const lc_ctx* L, v2 o) {
 
 /* undistort_points — cpu_undistort.rs:652-858 (mesh = None, shift_per_point = None) */
 static void undistort_points(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
-                             const double* rot_per_point, double lens_correction_amount, double fov, float* out) {
+                             const double* rot_per_point, double lens_correction_amount, double fov,
+                             const float* shifts, size_t n_shifts, float* out) {
     const double* K = cp->camera_matrix;
     const float fx = (float)K[0], fy = (float)K[4], cx = (float)K[2], cy = (float)K[5];
     gf_kernel_params kp; memset(&kp, 0, sizeof(kp));                /* :671-683 */
@@ -1375,6 +1420,14 @@ static void undistort_points(const gf_compute_params* cp, int model, int digital
         if (cp->input_horizontal_stretch > 0.001) x *= (float)cp->input_horizontal_stretch;     /* :702-703 */
         if (cp->input_vertical_stretch   > 0.001) y *= (float)cp->input_vertical_stretch;
         if (digital != GF_LENS_NONE) { v2 t; if (lens_undistort(digital, (v2){x, y}, &kp, &t)) { x = t.x; y = t.y; } }   /* :705-710 */
+        if (shifts && idx < n_shifts) {                              /* :748-757 (sic: y is rotated with the UPDATED x) */
+            const float* sh = shifts + 5 * idx;
+            const float cos_a = cosf(sh[2]), sin_a = sinf(sh[2]);
+            x = x - cx - sh[3] + sh[0];
+            y = y - cy - sh[4] + sh[1];
+            x = cos_a * x - sin_a * y + cx;
+            y = sin_a * x + cos_a * y + cy;
+        }
         v2 pw = { (x - cx) / fx, (y - cy) / fy };                    /* :762 */
         float rot[9]; for (int t = 0; t < 9; ++t) rot[t] = (float)rot_per_point[9*idx + t];      /* :764 */
         v2 pt;
@@ -1433,7 +1486,10 @@ void gf_oracle_undistort_points_rs_ex(const gf_compute_params* cp, int model, in
     double* rot = (double*)malloc(n * 9 * sizeof(double));
     double fov;
     rotations_for_points(cp, distorted, n, timestamp_ms, frame, use_fovs, rot, &fov);
-    undistort_points(cp, model, digital, distorted, n, rot, lens_correction_amount, fov, out);
+    float* shifts = (float*)malloc(n * 5 * sizeof(float));
+    const size_t n_shifts = shifts_for_points(cp, distorted, n, frame, shifts);
+    undistort_points(cp, model, digital, distorted, n, rot, lens_correction_amount, fov, n_shifts ? shifts : NULL, n_shifts, out);
+    free(shifts);
     free(rot);
 }
 void gf_oracle_undistort_points_rs(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,

@@ -1,7 +1,7 @@
 """Second, independent restatement of the adaptive-zoom companion — TEST INFRASTRUCTURE ONLY.
 
   at_timestamp_for_points   <- FrameTransform::at_timestamp_for_points    src/core/stabilization/frame_transform.rs:352-410
-  undistort_points          <- undistort_points (every lens model and digital lens; no mesh / IBIS shifts)
+  undistort_points          <- undistort_points (every lens model and digital lens, IBIS / OIS shifts; no mesh)
                                                                            src/core/stabilization/cpu_undistort.rs:652-858
   find_fov                  <- FovIterative::find_fov / nearest_edge / points_around_rect / interpolate_points
                                                                            src/core/zooming/fov_iterative.rs:76-200
@@ -32,7 +32,24 @@ def get_fov(c, frame, use_fovs):                                                
     return fov * c.width / max(c.output_width, 1)
 
 
-def at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs):            # frame_transform.rs:352-410
+def point_shifts(cp, pts, stab):                                                   # frame_transform.rs:412-431 (IBIS / OIS shift of every point)
+    c = cp.c
+    cx, cy, cw, ch = [float(np.float32(v)) for v in stab["crop_area"]]
+    pp = stab["pixel_pitch"]
+    sc = (c.width / cw / float(pp[0]), c.height / ch / float(pp[1]))               # no framebuffer sign here, unlike at_timestamp
+    out = []
+    z = np.zeros(3)
+    for (_x, y) in pts:
+        ys = (float(y) - 0.0) * ((cy + ch) - cy) / (float(c.height) - 0.0) + cy    # map_coord in f64
+        sv = np_producer.catmull_rom(np.asarray(stab["ibis"][0], float), np.asarray(stab["ibis"][1], float), ys + stab["offset"])
+        ov = np_producer.catmull_rom(np.asarray(stab["ois"][0], float), np.asarray(stab["ois"][1], float), ys + stab["offset"])
+        sv = z if sv is None else sv; ov = z if ov is None else ov
+        ra = sv[2] / 1000.0
+        out.append((F(sv[0] * sc[0]), F(sv[1] * sc[1]), F(ra * (math.pi / 180.0)), F(ov[0] * sc[0]), F(ov[1] * sc[1])))
+    return out
+
+
+def at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs, stab=None):  # frame_transform.rs:352-438
     c = cp.c
     K = np.array(list(c.camera_matrix), dtype=np.float64).reshape(3, 3)
     fov = get_fov(c, frame, use_fovs)
@@ -61,7 +78,10 @@ def at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs):         
         if c.suppress_rotation:
             r = np.eye(3)
         rotations.append(new_k @ r)
-    return K, rotations, fov
+    shifts = point_shifts(cp, pts, stab) if stab is not None else None            # one entry per element of points_iter: a single one when RS is off
+    if c.suppress_rotation and c.frame_readout_time == 0.0:                        # :432-434
+        shifts = None
+    return K, rotations, fov, shifts
 
 
 def _refract(px, py, lrc):                                                         # cpu_undistort.rs:767-776
@@ -79,7 +99,7 @@ class _KP:                                                                      
     pass
 
 
-def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens="opencv_fisheye", digital=None):   # cpu_undistort.rs:652-858 (no mesh / IBIS shifts)
+def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens="opencv_fisheye", digital=None, shifts=None):   # cpu_undistort.rs:652-858 (no mesh / IBIS shifts)
     c = cp.c
     kp = _KP()
     kp.width, kp.height, kp.output_width, kp.output_height = c.width, c.height, c.output_width, c.output_height
@@ -104,6 +124,13 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens
         if c.input_vertical_stretch > 0.001: y = y * F(c.input_vertical_stretch)
         if dund is not None:                                                       # :705-710
             x, y = dund(x, y, kp)
+        if shifts is not None and index < len(shifts):                             # :748-757 (sic: y is rotated with the UPDATED x)
+            sh = shifts[index]
+            cos_a = npr.cosf(sh[2]); sin_a = npr.sinf(sh[2])
+            x = x - cx - sh[3] + sh[0]
+            y = y - cy - sh[4] + sh[1]
+            x = cos_a * x - sin_a * y + cx
+            y = sin_a * x + cos_a * y + cy
         pwx, pwy = (x - cx) / fx, (y - cy) / fy                                    # :760
         rot = np.asarray(rotations[index] if index < len(rotations) else rotations[0], dtype=np.float64).astype(np.float32)
         pt = und(pwx, pwy, k)
@@ -158,9 +185,10 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens
     return out
 
 
-def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False, lens="opencv_fisheye", digital=None):   # :636-641
-    K, rotations, fov = at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs)
-    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens, digital)
+def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False, lens="opencv_fisheye", digital=None, stab=None):   # :636-641
+    """stab: the CameraStabData dict of this frame (as given to backend.ComputeParams(camera_stab=[...])) or None."""
+    K, rotations, fov, shifts = at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs, stab)
+    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens, digital, shifts)
 
 
 def points_around_rect(w, h, w_div, h_div, margin):                                # fov_iterative.rs:154-177
@@ -197,7 +225,7 @@ def nearest_edge(polygon, center, initial, inv_aspect):                         
     return idx, mp
 
 
-def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0, lens="opencv_fisheye", digital=None):               # FovIterative::new :76-89 + find_fov :91-134
+def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0, lens="opencv_fisheye", digital=None, stab=None):               # FovIterative::new :76-89 + find_fov :91-134
     """`cp` must already carry the calculate_fovs adjustments (zooming/mod.rs:41-49): fov_scale 1, no fovs, output size = input size."""
     c = cp.c
     ratio = F(c.width) / F(max(org_output_size[0], 1))
@@ -209,7 +237,7 @@ def find_fov(cp, org_output_size, timestamp_ms, frame, margin=2.0, lens="opencv_
     zx, zy, lca = c.adaptive_zoom_center_offset[0], c.adaptive_zoom_center_offset[1], c.lens_correction_amount
 
     def shifted(pts):
-        poly = undistort_points_with_rolling_shutter(cp, pts, timestamp_ms, frame, lca, False, lens, digital)
+        poly = undistort_points_with_rolling_shutter(cp, pts, timestamp_ms, frame, lca, False, lens, digital, stab)
         return [(x - F(zx) * input_dim[0], y - F(zy) * input_dim[1]) for x, y in poly]
 
     polygon = shifted(rect)

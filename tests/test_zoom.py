@@ -127,3 +127,73 @@ def test_oracle_find_fov_matches_second_restatement(kw):
         got = np.array([np_zoom.find_fov(adj, org, float(t), i, lens=lens, digital=digital) for i, t in enumerate(ts)])
     assert np.allclose(got, want, rtol=1e-6, atol=0), (got, want)
     assert (got == want).mean() >= 0.5 and 0.3 < want.min() and want.max() < 3.0
+
+
+def _zoom_stab(frames, h, seed=5):
+    rng = np.random.default_rng(seed)
+    out = []
+    for f in range(frames):
+        pos = np.linspace(200.0, 3800.0, 9)
+        ibis = np.stack([9.0e4 * np.sin(pos / 500.0 + f), 7.0e4 * np.cos(pos / 700.0 + 0.3 * f), 900.0 * np.sin(pos / 900.0 + f)], axis=1) + rng.normal(0, 500.0, (9, 3))
+        ois = np.stack([6.0e4 * np.cos(pos / 300.0 + f), 4.0e4 * np.sin(pos / 450.0), np.zeros_like(pos)], axis=1)
+        out.append(dict(offset=12.5, sensor_size=(6000, 4000), crop_area=(500.0, 300.0, 5000.0, 3400.0), pixel_pitch=(8400, 8400), ibis=(pos, ibis), ois=(pos, ois)))
+    return out
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(frame_readout_time_ms=0.0), dict(lens="sony", params=dict(lens_correction_amount=0.6)),
+                                dict(frame_readout_time_ms=0.0, suppress=True)])
+def test_point_path_ibis_shifts_oracle_matches_second_restatement(kw):
+    """The IBIS / OIS `shifts` of at_timestamp_for_points (frame_transform.rs:412-434) and their use in undistort_points
+    (cpu_undistort.rs:748-757, where y is rotated with the already rotated x): C oracle == tests/np_zoom.py.  With rolling-shutter
+    correction off only the FIRST point is shifted (points_iter is the single point (0, 0)); with suppress_rotation on top, none."""
+    import warnings
+    from tests import np_zoom
+    kw = dict(kw); lens = kw.pop("lens", "opencv_fisheye"); suppress = kw.pop("suppress", False)
+    stab = _zoom_stab(3, 1080)
+    cp = make_cp(lens=lens, camera_stab=stab, **kw)
+    plain = make_cp(lens=lens, **kw)
+    if suppress: cp.c.suppress_rotation = 1; plain.c.suppress_rotation = 1
+    lib = oracle_lib.load()
+    pts = np.array([[3.0, 2.0], [960.0, 540.0], [1900.0, 30.0], [40.0, 1070.0], [1500.0, 800.0]], np.float32)
+    for frame, ts in enumerate((300.0, 1500.0, 2900.0)):
+        lca = float(cp.c.lens_correction_amount)
+        want = np.zeros_like(pts); base = np.zeros_like(pts)
+        lib.gf_oracle_undistort_points_rs_ex(C.byref(cp.c), abi.LENS[lens], 0, pts.ctypes.data, len(pts), ts, frame, lca, 0, want.ctypes.data)
+        lib.gf_oracle_undistort_points_rs_ex(C.byref(plain.c), abi.LENS[lens], 0, pts.ctypes.data, len(pts), ts, frame, lca, 0, base.ctypes.data)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = np.array(np_zoom.undistort_points_with_rolling_shutter(cp, [tuple(p) for p in pts], ts, frame, lca, False, lens, None, stab[frame]), np.float32)
+        assert np.allclose(got, want, rtol=0, atol=2e-3), (got, want)
+        moved = np.abs(want - base).max(axis=1) > 0.5
+        if suppress:                      assert not moved.any()
+        elif "frame_readout_time_ms" in kw: assert moved[0] and not moved[1:].any()
+        else:                             assert moved.all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(frame_readout_time_ms=0.0), dict(lens="sony", params=dict(lens_correction_amount=0.6))])
+def test_device_point_path_with_ibis_shifts_matches_oracle(kw):
+    """The zoom kernels apply the per-point IBIS / OIS shifts (frame_transform.rs:412-434, cpu_undistort.rs:748-757) from the spline points in
+    HBM: undistort_points and find_fovs on the device == the oracle (which test_point_path_ibis_shifts_oracle_matches_second_restatement
+    ties to the second transcription), including the rolling-shutter-off quirk (only the first point of a call is shifted)."""
+    kw = dict(kw); lens = kw.pop("lens", "opencv_fisheye")
+    n = 24
+    stab = _zoom_stab(n, 1080)
+    cp = make_cp(lens=lens, camera_stab=stab, **kw)
+    lib = oracle_lib.load()
+    dg = g.DeviceGyro(cp)
+    pts = np.array([[3.0, 2.0], [960.0, 540.0], [1900.0, 30.0], [40.0, 1070.0], [1500.0, 800.0]], np.float32)
+    lca = float(cp.c.lens_correction_amount)
+    for frame, ts in ((0, 300.0), (7, 1500.0), (20, 2900.0)):
+        want = np.zeros_like(pts)
+        lib.gf_oracle_undistort_points_rs_ex(C.byref(cp.c), abi.LENS[lens], 0, pts.ctypes.data, len(pts), ts, frame, lca, 0, want.ctypes.data)
+        got = dg.undistort_points(lens, None, pts, ts, frame=frame, lens_correction_amount=lca)
+        assert np.allclose(got, want, rtol=0, atol=2e-3), (frame, got, want)
+    ts = np.arange(n) * (1000.0 / 60.0) * 5
+    want = oracle_lib.find_fovs(cp, lens, None, ts)
+    got = dg.find_fovs(lens, None, ts)
+    plain = make_cp(lens=lens, **kw)
+    base = oracle_lib.find_fovs(plain, lens, None, ts)
+    dg.close()
+    assert np.allclose(got, want, rtol=1e-6, atol=0), float(np.abs(got / want - 1).max())
+    assert np.abs(want / base - 1).max() > 1e-3          # the shifts do move the polygon
