@@ -97,7 +97,13 @@ class ComputeParams(C.Structure):
         ("camera_stab", C.c_void_p), ("n_camera_stab", C.c_size_t),
         ("keyframes", KeyframeTrack * 8), ("keyframe_timestamp_scale", C.c_double),
         ("lens_per_frame", C.c_void_p), ("n_lens_per_frame", C.c_size_t),
+        ("distorting_mesh", C.c_void_p), ("n_distorting_mesh", C.c_size_t),
     ]
+
+
+class MeshF64(C.Structure):
+    """gf_mesh_f64: one frame's distorting mesh (file_metadata.mesh_correction[frame].0)."""
+    _fields_ = [("data", C.POINTER(C.c_double)), ("len", C.c_size_t)]
 
 
 class LensData(C.Structure):

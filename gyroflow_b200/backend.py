@@ -228,7 +228,7 @@ class ComputeParams:
     def __init__(self, kernel_params: abi.KernelParams, org, smoothed, frame_readout_time_ms=16.0, fovs=None, video_rotation=0.0,
                  horizontal=False, inverted=False, framebuffer_inverted=False, fov_scale=1.0, sync_offsets=None,
                  per_frame_time_offsets=None, focal_lengths=None, smoothed_focal_lengths=None, readout_time_scale=0.0, camera_stab=None,
-                 gyro_offset_ms=0.0, keyframes=None, keyframe_timestamp_scale=0.0, lens_per_frame=None):
+                 gyro_offset_ms=0.0, keyframes=None, keyframe_timestamp_scale=0.0, lens_per_frame=None, distorting_meshes=None):
         """sync_offsets: {timestamp_us: offset_ms} (GyroSource::offsets_adjusted); camera_stab: list (one per frame) of dicts with
         offset, sensor_size, crop_area, pixel_pitch, ibis=(pos[n], xyz[n,3]), ois=(pos[n], xyz[n,3]) (CameraStabData);
         keyframes: {KeyframeType name: [(timestamp_us, value, easing name), ...]} for the types at_timestamp reads (abi.KEYFRAME_TYPES)."""
@@ -293,6 +293,16 @@ class ComputeParams:
             t = c.keyframes[abi.KEYFRAME_TYPES[name]]
             t.ts_us = ts.ctypes.data_as(C.POINTER(C.c_int64)); t.value = val.ctypes.data_as(C.POINTER(C.c_double))
             t.easing = ea.ctypes.data_as(C.POINTER(C.c_uint8)); t.n = len(keys)
+        if distorting_meshes:     # one f64 mesh (or None) per frame: file_metadata.mesh_correction[frame].0
+            arr = (abi.MeshF64 * len(distorting_meshes))()
+            self._dmesh_arrays = []
+            for i, mesh in enumerate(distorting_meshes):
+                if mesh is None:
+                    continue
+                a = np.ascontiguousarray(mesh, dtype=np.float64); self._dmesh_arrays.append(a)
+                arr[i].data = a.ctypes.data_as(C.POINTER(C.c_double)); arr[i].len = a.size
+            self._dmesh = arr
+            c.distorting_mesh = C.cast(arr, C.c_void_p); c.n_distorting_mesh = len(distorting_meshes)
         if camera_stab:
             self._stab_arrays = []
             arr = (abi.CameraStab * len(camera_stab))()

@@ -368,7 +368,8 @@ GF_API size_t gf_abi_struct_size(int which) {
     switch (which) {
     case 0: return sizeof(gf_kernel_params);  case 1: return sizeof(gf_buffer_desc);    case 2: return sizeof(gf_compute_params);
     case 3: return sizeof(gf_camera_stab);    case 4: return sizeof(gf_keyframe_track); case 5: return sizeof(gf_stab_config);
-    case 6: return sizeof(gf_queue_config);   case 7: return sizeof(gf_lens_data);      default: return 0;
+    case 6: return sizeof(gf_queue_config);   case 7: return sizeof(gf_lens_data);
+    case 8: return sizeof(gf_mesh_f64);       default: return 0;
     }
 }
 GF_API const char* gf_cuda_backend_name(void) { return "CUDA"; }

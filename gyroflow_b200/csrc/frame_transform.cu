@@ -377,6 +377,19 @@ GF_API int gf_cuda_gyro_upload(gf_cuda_gyro** out, int device, const gf_compute_
             ok = cudaMalloc(&g->d_stab, flat.size() * sizeof(double)) == cudaSuccess &&
                  cudaMemcpy(g->d_stab, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    // per-frame distorting meshes of the point path (mesh_correction[frame].0)
+    if (ok && cp->distorting_mesh && cp->n_distorting_mesh > 0) {
+        std::vector<double> flat;
+        g->mesh_index.resize(cp->n_distorting_mesh);
+        for (size_t f = 0; f < cp->n_distorting_mesh; ++f) {
+            const gf_mesh_f64& m = cp->distorting_mesh[f];
+            g->mesh_index[f].off = flat.size(); g->mesh_index[f].len = m.data ? m.len : 0;
+            if (m.data) flat.insert(flat.end(), m.data, m.data + m.len);
+        }
+        if (!flat.empty())
+            ok = cudaMalloc(&g->d_mesh, flat.size() * sizeof(double)) == cudaSuccess &&
+                 cudaMemcpy(g->d_mesh, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) { (void)cudaGetLastError(); gf_cuda_gyro_free(g); return GF_ERR_CUDA; }
     *out = g;
     return GF_OK;
@@ -391,6 +404,7 @@ GF_API void gf_cuda_gyro_free(gf_cuda_gyro* g) {
     if (g->d_off_ts) cudaFree(g->d_off_ts);
     if (g->d_off_ms) cudaFree(g->d_off_ms);
     if (g->d_stab) cudaFree(g->d_stab);
+    if (g->d_mesh) cudaFree(g->d_mesh);
     if (g->d_scratch) cudaFree(g->d_scratch);
     if (g->stream) cudaStreamDestroy(g->stream);
     (void)cudaGetLastError();

@@ -12,6 +12,9 @@ struct gf_cuda_gyro {
     double* d_stab = nullptr;                                                       // IBIS / OIS spline points of every frame, flat
     struct StabIndex { size_t ibis_pos, ibis_val, n_ibis, ois_pos, ois_val, n_ois; };
     std::vector<StabIndex> stab_index;                                              // offsets into d_stab per frame
+    double* d_mesh = nullptr;                                                       // distorting meshes of every frame (point path), flat
+    struct MeshIndex { size_t off, len; };
+    std::vector<MeshIndex> mesh_index;
     // verdict accumulator + ticket of frame_rows_kernel: a pool of pairs handed out round-robin, so that producer launches that overlap
     // on different streams (the render queue's slots) never share one
     static constexpr unsigned kScratchPairs = 64;

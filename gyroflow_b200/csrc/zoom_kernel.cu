@@ -2,7 +2,7 @@
 //
 // Behavioural source: FovIterative::find_fov / nearest_edge / points_around_rect / interpolate_points
 // (src/core/zooming/fov_iterative.rs:91-189), undistort_points_with_rolling_shutter + undistort_points
-// (src/core/stabilization/cpu_undistort.rs:636-858, with the IBIS / OIS shifts, no mesh), FrameTransform::at_timestamp_for_points
+// (src/core/stabilization/cpu_undistort.rs:636-858, with the IBIS / OIS shifts and the distorting mesh), FrameTransform::at_timestamp_for_points
 // (src/core/stabilization/frame_transform.rs:352-438), calculate_fovs (src/core/zooming/mod.rs:35-70) and the
 // static-window temporal filters of zoom_dynamic.rs:56-126,177-200.
 //
@@ -15,6 +15,7 @@
 #include <cstring>
 #include <vector>
 #include "lens_models.cuh"
+#include "warp_kernel.cuh"      // MeshView + mesh_bivariate (the f64 bivariate spline, splines.rs:141-176)
 #include "quat_track.cuh"
 #include "gyro_dev.h"
 
@@ -36,6 +37,7 @@ struct ZoomFrame {              // per-frame uniforms (host, f64)
     ZQuat q0;                   // smoothed(ts) * org(ts)^-1
     double start_ts;
     ZoomStab stab;
+    const double* mesh; uint32_t mesh_len;      // this frame's distorting mesh in HBM (mesh_correction[frame].0), or nullptr
     // keyframed values of this frame (fov_iterative.rs:44-46, frame_transform.rs:354, cpu_undistort.rs:661); `keyed` = some track exists
     int keyed;
     double rot_c, rot_s;
@@ -90,6 +92,50 @@ __device__ bool point_shift(const ZoomArgs& A, const ZoomFrame& F, float py, siz
     return true;
 }
 
+// map_coord (util.rs:144-147) in f32, IEEE division
+__device__ __forceinline__ float pm_map(float x, float in_min, float in_max, float out_min, float out_max) {
+    return (x - in_min) * (out_max - out_min) / (in_max - in_min) + out_min;
+}
+// The mesh block of undistort_points — cpu_undistort.rs:712-746: focal-plane distortion first (added here, subtracted in the warp), then
+// the distorting mesh through the f64 bivariate spline.  No inverted-framebuffer flips on this path.
+__device__ void point_mesh(const ZoomArgs& A, const ZoomFrame& F, float& x, float& y) {
+    const double* __restrict__ m = F.mesh;
+    const float fw = (float)A.kp.width, fh = (float)A.kp.height;
+    const double m0 = __ldg(m);
+    const double size_x = __ldg(m + 3), size_y = __ldg(m + 4);
+    const float ox = (float)__ldg(m + 5), oy = (float)__ldg(m + 6), cw = (float)__ldg(m + 7), ch = (float)__ldg(m + 8);
+    const uint32_t o = as_usize_small(m0);
+    if (m0 > 0.0 && o < F.mesh_len && __ldg(m + o) > 0.0) {          // FocalPlaneDistortion :714-733 (the reference indexes unchecked)
+        const double stblz_grid = size_y / 8.0;
+        x = pm_map(x, 0.0f, fw, ox, ox + cw);
+        y = pm_map(y, 0.0f, fh, oy, oy + ch);
+        const double q = floor((double)y / stblz_grid);
+        const uint32_t idx = as_usize_small(fmin(fmax(q, 0.0), 7.0));            // f64::max / min ignore NaN: NaN -> 0
+        const double delta = (double)y - stblz_grid * (double)idx;
+        x += (float)(__ldg(m + o + 4 + idx * 2 + 0) * delta);
+        y += (float)(__ldg(m + o + 4 + idx * 2 + 1) * delta);
+        for (uint32_t j = 0; j < idx; ++j) {
+            x += (float)(__ldg(m + o + 4 + j * 2 + 0) * stblz_grid);
+            y += (float)(__ldg(m + o + 4 + j * 2 + 1) * stblz_grid);
+        }
+        x = pm_map(x, ox, ox + cw, 0.0f, fw);
+        y = pm_map(y, oy, oy + ch, 0.0f, fh);
+    }
+    if (m0 > 10.0) {                                                 // :735-745
+        x = pm_map(x, 0.0f, fw, ox, ox + cw);
+        y = pm_map(y, 0.0f, fh, oy, oy + ch);
+        const uint32_t n_x = as_usize_small(__ldg(m + 1)), n_y = as_usize_small(__ldg(m + 2));
+        const MeshView mv{ m };
+        double nx = (double)x, ny = (double)y;
+        if (n_x >= 2 && n_x <= GF_MAX_GRID && n_y >= 2 && n_y <= GF_MAX_GRID) {
+            nx = mesh_bivariate(mv, n_x, n_y, size_x, size_y, 0, (double)x, (double)y);
+            ny = mesh_bivariate(mv, n_x, n_y, size_x, size_y, 1, (double)x, (double)y);
+        }
+        x = pm_map((float)nx, ox, ox + cw, 0.0f, fw);
+        y = pm_map((float)ny, oy, oy + ch, 0.0f, fh);
+    }
+}
+
 template <int LENS, int DIGITAL>
 __device__ void lc_r_of(const ZoomArgs& A, float ox, float oy, float& rx, float& ry) {        // cpu_undistort.rs:794-815
     const gf_kernel_params& P = A.kp;
@@ -124,6 +170,7 @@ __device__ void undistort_point_rs(const ZoomArgs& A, const ZoomFrame& F, float 
     if (A.hstretch != 0.0f) x *= A.hstretch;
     if (A.vstretch != 0.0f) y *= A.vstretch;
     if (DIGITAL != GF_LENS_NONE) { float tx, ty; if (Lens<DIGITAL>::undistort(x, y, P, false, tx, ty)) { x = tx; y = ty; } }
+    if (F.mesh && F.mesh_len > 9) point_mesh(A, F, x, y);          // cpu_undistort.rs:712-746
     float sh[5];
     if (point_shift(A, F, py, index, sh)) {             // cpu_undistort.rs:748-757 (sic: y is rotated with the already rotated x)
         const float cos_a = gf_cosf(sh[2]), sin_a = gf_sinf(sh[2]);
@@ -410,6 +457,10 @@ static ZoomFrame frame_uniforms(const gf_cuda_gyro* g, const gf_compute_params& 
     f.start_ts = ts - frt / 2.0;
     f.keyed = 0;
     memset(&f.stab, 0, sizeof(f.stab));
+    f.mesh = nullptr; f.mesh_len = 0;
+    if (g->d_mesh && frame < g->mesh_index.size() && g->mesh_index[frame].len > 9) {                 // mesh_correction.get(frame) (:369-373)
+        f.mesh = g->d_mesh + g->mesh_index[frame].off; f.mesh_len = (uint32_t)g->mesh_index[frame].len;
+    }
     if (cp.camera_stab && frame < cp.n_camera_stab && frame < g->stab_index.size() && !(cp.suppress_rotation && cp.frame_readout_time == 0.0)) {   // :412, :432-434
         const gf_camera_stab& is = cp.camera_stab[frame];
         const gf_cuda_gyro::StabIndex& ix = g->stab_index[frame];

@@ -203,7 +203,7 @@ GF_API int         gf_cuda_device_name(int device, char* buf, size_t buf_len);  
 GF_API int         gf_cuda_supports(const gf_buffer_desc* in, const gf_buffer_desc* out); /* is_buffer_supported opencl.rs:451 */
 GF_API const char* gf_cuda_version(void);
 /* sizeof() of the structs that cross this ABI, for binding generators and their tests: 0 gf_kernel_params, 1 gf_buffer_desc,
- * 2 gf_compute_params, 3 gf_camera_stab, 4 gf_keyframe_track, 5 gf_stab_config, 6 gf_queue_config, 7 gf_lens_data; 0 for any other index. */
+ * 2 gf_compute_params, 3 gf_camera_stab, 4 gf_keyframe_track, 5 gf_stab_config, 6 gf_queue_config, 7 gf_lens_data, 8 gf_mesh_f64; 0 for any other index. */
 GF_API size_t gf_abi_struct_size(int which);
 
 /* ---- lens plugin surface: DistortionModel::from_name / id  distortion_models/mod.rs:79-90 -- */
@@ -394,7 +394,12 @@ typedef struct gf_compute_params {      /* the slice of ComputeParams (compute_p
      * input_*_stretch above in at_timestamp, and camera_matrix / distortion_coeffs in the single-timestamp point path (gf_cuda_undistort_points,
      * ST maps); gf_cuda_find_fovs keeps the constants.  Rust evaluates it once per job; NULL = the constants above for every frame. */
     const struct gf_lens_data* lens_per_frame; size_t n_lens_per_frame;
+    /* file_metadata.mesh_correction[frame].0 — the DISTORTING mesh (f64, sony.rs:483-511 layout) the point path applies
+     * (frame_transform.rs:369-373, cpu_undistort.rs:712-746: adaptive zoom, undistort_points, the redistort ST map).  The warp itself takes
+     * the undistorting mesh (.1, f32) as a call argument.  NULL = no mesh; an entry with len == 0 = none for that frame. */
+    const struct gf_mesh_f64* distorting_mesh; size_t n_distorting_mesh;
 } gf_compute_params;
+typedef struct gf_mesh_f64 { const double* data; size_t len; } gf_mesh_f64;
 typedef struct gf_lens_data {
     double camera_matrix[9]; double distortion_coeffs[12]; double radial_distortion_limit;
     double input_horizontal_stretch, input_vertical_stretch;

@@ -1395,7 +1395,7 @@ static v2 lc_r_of(const lc_ctx* L, v2 o) {
 /* undistort_points — cpu_undistort.rs:652-858 (mesh = None, shift_per_point = None) */
 static void undistort_points(const gf_compute_params* cp, int model, int digital, const float* distorted, size_t n,
                              const double* rot_per_point, double lens_correction_amount, double fov,
-                             const float* shifts, size_t n_shifts, float* out) {
+                             const float* shifts, size_t n_shifts, size_t frame, float* out) {
     const double* K = cp->camera_matrix;
     const float fx = (float)K[0], fy = (float)K[4], cx = (float)K[2], cy = (float)K[5];
     gf_kernel_params kp; memset(&kp, 0, sizeof(kp));                /* :671-683 */
@@ -1420,6 +1420,34 @@ static void undistort_points(const gf_compute_params* cp, int model, int digital
         if (cp->input_horizontal_stretch > 0.001) x *= (float)cp->input_horizontal_stretch;     /* :702-703 */
         if (cp->input_vertical_stretch   > 0.001) y *= (float)cp->input_vertical_stretch;
         if (digital != GF_LENS_NONE) { v2 t; if (lens_undistort(digital, (v2){x, y}, &kp, &t)) { x = t.x; y = t.y; } }   /* :705-710 */
+        if (cp->distorting_mesh && frame < cp->n_distorting_mesh && cp->distorting_mesh[frame].data && cp->distorting_mesh[frame].len > 9) {   /* :712-746 */
+            const double* md = cp->distorting_mesh[frame].data; const size_t mlen = cp->distorting_mesh[frame].len;
+            const float fw = (float)cp->width, fh = (float)cp->height;
+            const float ox = (float)md[5], oy = (float)md[6], cw = (float)md[7], chh = (float)md[8];
+            const size_t o = md[0] > 0.0 ? (size_t)md[0] : 0;
+            if (md[0] > 0.0 && o < mlen && md[o] > 0.0) {            /* FocalPlaneDistortion :714-733 (added on this path) */
+                const double stblz_grid = md[4] / 8.0;
+                x = map_coord(x, 0.0f, fw, ox, ox + cw);
+                y = map_coord(y, 0.0f, fh, oy, oy + chh);
+                double q = floor((double)y / stblz_grid);
+                q = q != q ? 0.0 : (q < 0.0 ? 0.0 : (q > 7.0 ? 7.0 : q));
+                const size_t fi = (size_t)q;
+                const double delta = (double)y - stblz_grid * (double)fi;
+                x += (float)(md[o + 4 + fi * 2 + 0] * delta);
+                y += (float)(md[o + 4 + fi * 2 + 1] * delta);
+                for (size_t j = 0; j < fi; ++j) { x += (float)(md[o + 4 + j * 2 + 0] * stblz_grid); y += (float)(md[o + 4 + j * 2 + 1] * stblz_grid); }
+                x = map_coord(x, ox, ox + cw, 0.0f, fw);
+                y = map_coord(y, oy, oy + chh, 0.0f, fh);
+            }
+            if (md[0] > 10.0) {                                      /* :735-745 */
+                x = map_coord(x, 0.0f, fw, ox, ox + cw);
+                y = map_coord(y, 0.0f, fh, oy, oy + chh);
+                double nx, ny;
+                gf_oracle_interpolate_mesh((double)x, (double)y, md, &nx, &ny);
+                x = map_coord((float)nx, ox, ox + cw, 0.0f, fw);
+                y = map_coord((float)ny, oy, oy + chh, 0.0f, fh);
+            }
+        }
         if (shifts && idx < n_shifts) {                              /* :748-757 (sic: y is rotated with the UPDATED x) */
             const float* sh = shifts + 5 * idx;
             const float cos_a = cosf(sh[2]), sin_a = sinf(sh[2]);
@@ -1488,7 +1516,7 @@ void gf_oracle_undistort_points_rs_ex(const gf_compute_params* cp, int model, in
     rotations_for_points(cp, distorted, n, timestamp_ms, frame, use_fovs, rot, &fov);
     float* shifts = (float*)malloc(n * 5 * sizeof(float));
     const size_t n_shifts = shifts_for_points(cp, distorted, n, frame, shifts);
-    undistort_points(cp, model, digital, distorted, n, rot, lens_correction_amount, fov, n_shifts ? shifts : NULL, n_shifts, out);
+    undistort_points(cp, model, digital, distorted, n, rot, lens_correction_amount, fov, n_shifts ? shifts : NULL, n_shifts, frame, out);
     free(shifts);
     free(rot);
 }

@@ -1,7 +1,7 @@
 """Second, independent restatement of the adaptive-zoom companion — TEST INFRASTRUCTURE ONLY.
 
   at_timestamp_for_points   <- FrameTransform::at_timestamp_for_points    src/core/stabilization/frame_transform.rs:352-410
-  undistort_points          <- undistort_points (every lens model and digital lens, IBIS / OIS shifts; no mesh)
+  undistort_points          <- undistort_points (every lens model and digital lens, IBIS / OIS shifts, distorting mesh + focal-plane distortion)
                                                                            src/core/stabilization/cpu_undistort.rs:652-858
   find_fov                  <- FovIterative::find_fov / nearest_edge / points_around_rect / interpolate_points
                                                                            src/core/zooming/fov_iterative.rs:76-200
@@ -99,7 +99,29 @@ class _KP:                                                                      
     pass
 
 
-def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens="opencv_fisheye", digital=None, shifts=None):   # cpu_undistort.rs:652-858 (no mesh / IBIS shifts)
+def _point_mesh(x, y, c, mesh):                                                   # cpu_undistort.rs:712-746 (mesh: list of f64)
+    fw, fh = F(c.width), F(c.height)
+    ox, oy, cw, ch = F(mesh[5]), F(mesh[6]), F(mesh[7]), F(mesh[8])
+    mc = npr.map_coord
+    o = int(mesh[0]) if mesh[0] > 0.0 else 0
+    if mesh[0] > 0.0 and o < len(mesh) and mesh[o] > 0.0:                          # FocalPlaneDistortion: ADDED on this path
+        stblz_grid = mesh[4] / 8.0
+        x = mc(x, 0.0, fw, ox, ox + cw); y = mc(y, 0.0, fh, oy, oy + ch)
+        q = math.floor(float(y) / stblz_grid)
+        idx = int(min(max(q, 0.0), 7.0)) if not math.isnan(q) else 0
+        delta = float(y) - stblz_grid * idx
+        x = x + F(mesh[o + 4 + idx * 2 + 0] * delta); y = y + F(mesh[o + 4 + idx * 2 + 1] * delta)
+        for j in range(idx):
+            x = x + F(mesh[o + 4 + j * 2 + 0] * stblz_grid); y = y + F(mesh[o + 4 + j * 2 + 1] * stblz_grid)
+        x = mc(x, ox, ox + cw, 0.0, fw); y = mc(y, oy, oy + ch, 0.0, fh)
+    if mesh[0] > 10.0:
+        x = mc(x, 0.0, fw, ox, ox + cw); y = mc(y, 0.0, fh, oy, oy + ch)
+        nx, ny = npr.interpolate_mesh(float(x), float(y), (mesh[3], mesh[4]), mesh)
+        x = mc(F(nx), ox, ox + cw, 0.0, fw); y = mc(F(ny), oy, oy + ch, 0.0, fh)
+    return x, y
+
+
+def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens="opencv_fisheye", digital=None, shifts=None, mesh=None):   # cpu_undistort.rs:652-858 (no mesh / IBIS shifts)
     c = cp.c
     kp = _KP()
     kp.width, kp.height, kp.output_width, kp.output_height = c.width, c.height, c.output_width, c.output_height
@@ -124,6 +146,8 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens
         if c.input_vertical_stretch > 0.001: y = y * F(c.input_vertical_stretch)
         if dund is not None:                                                       # :705-710
             x, y = dund(x, y, kp)
+        if mesh is not None and len(mesh) > 9:
+            x, y = _point_mesh(x, y, c, mesh)
         if shifts is not None and index < len(shifts):                             # :748-757 (sic: y is rotated with the UPDATED x)
             sh = shifts[index]
             cos_a = npr.cosf(sh[2]); sin_a = npr.sinf(sh[2])
@@ -185,10 +209,10 @@ def undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens
     return out
 
 
-def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False, lens="opencv_fisheye", digital=None, stab=None):   # :636-641
+def undistort_points_with_rolling_shutter(cp, points, timestamp_ms, frame, lens_correction_amount, use_fovs=False, lens="opencv_fisheye", digital=None, stab=None, mesh=None):   # :636-641
     """stab: the CameraStabData dict of this frame (as given to backend.ComputeParams(camera_stab=[...])) or None."""
     K, rotations, fov, shifts = at_timestamp_for_points(cp, points, timestamp_ms, frame, use_fovs, stab)
-    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens, digital, shifts)
+    return undistort_points(cp, points, K, rotations, lens_correction_amount, fov, lens, digital, shifts, mesh)
 
 
 def points_around_rect(w, h, w_div, h_div, margin):                                # fov_iterative.rs:154-177

@@ -137,6 +137,6 @@ def test_kernel_variant_planning_host_logic():
 def test_struct_sizes_match_the_library():
     """Every struct that crosses the C ABI has the same size in the ctypes mirror (gyroflow_b200/abi.py) and in the compiled library."""
     lib = abi.load_library()
-    for which, cls in enumerate((abi.KernelParams, abi.BufferDesc, abi.ComputeParams, abi.CameraStab, abi.KeyframeTrack, abi.StabConfig, abi.QueueConfig, abi.LensData)):
+    for which, cls in enumerate((abi.KernelParams, abi.BufferDesc, abi.ComputeParams, abi.CameraStab, abi.KeyframeTrack, abi.StabConfig, abi.QueueConfig, abi.LensData, abi.MeshF64)):
         assert lib.gf_abi_struct_size(which) == C.sizeof(cls), (which, cls.__name__)
     assert lib.gf_abi_struct_size(99) == 0

@@ -197,3 +197,53 @@ def test_device_point_path_with_ibis_shifts_matches_oracle(kw):
     dg.close()
     assert np.allclose(got, want, rtol=1e-6, atol=0), float(np.abs(got / want - 1).max())
     assert np.abs(want / base - 1).max() > 1e-3          # the shifts do move the polygon
+
+
+def _distorting_mesh(w, h, fpd):
+    from gyroflow_b200 import synth
+    return np.asarray(synth.synthetic_mesh(w, h, amp=6.0, n=9, with_fpd=fpd), dtype=np.float64)     # same layout as mesh_correction[frame].0 (sony.rs:483-511)
+
+
+@pytest.mark.parametrize("fpd", [False, True])
+def test_point_path_distorting_mesh_oracle_matches_second_restatement(fpd):
+    """The mesh block of undistort_points (cpu_undistort.rs:712-746: focal-plane distortion ADDED, then the distorting mesh through the f64
+    bivariate spline): C oracle == tests/np_zoom.py, with and without the focal-plane block, combined with IBIS shifts."""
+    import warnings
+    from tests import np_zoom
+    stab = _zoom_stab(2, 1080)
+    meshes = [_distorting_mesh(1920, 1080, fpd), None]
+    cp = make_cp(lens="sony", camera_stab=stab, distorting_meshes=meshes)
+    plain = make_cp(lens="sony", camera_stab=stab)
+    lib = oracle_lib.load()
+    pts = np.array([[3.0, 2.0], [960.0, 540.0], [1900.0, 30.0], [40.0, 1070.0], [1500.0, 800.0]], np.float32)
+    for frame, ts in enumerate((300.0, 1500.0)):
+        want = np.zeros_like(pts); base = np.zeros_like(pts)
+        lib.gf_oracle_undistort_points_rs_ex(C.byref(cp.c), abi.LENS["sony"], 0, pts.ctypes.data, len(pts), ts, frame, 1.0, 0, want.ctypes.data)
+        lib.gf_oracle_undistort_points_rs_ex(C.byref(plain.c), abi.LENS["sony"], 0, pts.ctypes.data, len(pts), ts, frame, 1.0, 0, base.ctypes.data)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mesh = None if meshes[frame] is None else [float(v) for v in meshes[frame]]
+            got = np.array(np_zoom.undistort_points_with_rolling_shutter(cp, [tuple(p) for p in pts], ts, frame, 1.0, False, "sony", None, stab[frame], mesh), np.float32)
+        assert np.allclose(got, want, rtol=0, atol=2e-3), (got, want)
+        assert (np.abs(want - base).max() > 1.0) == (frame == 0)          # frame 1 has no mesh
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fpd", [False, True])
+def test_device_point_path_with_distorting_mesh_matches_oracle(fpd):
+    n = 12
+    meshes = [_distorting_mesh(1920, 1080, fpd) if i % 3 != 2 else None for i in range(n)]
+    cp = make_cp(lens="sony", camera_stab=_zoom_stab(n, 1080), distorting_meshes=meshes)
+    lib = oracle_lib.load()
+    dg = g.DeviceGyro(cp)
+    pts = np.array([[3.0, 2.0], [960.0, 540.0], [1900.0, 30.0], [40.0, 1070.0], [1500.0, 800.0]], np.float32)
+    for frame, ts in ((0, 300.0), (2, 900.0), (7, 1500.0)):
+        want = np.zeros_like(pts)
+        lib.gf_oracle_undistort_points_rs_ex(C.byref(cp.c), abi.LENS["sony"], 0, pts.ctypes.data, len(pts), ts, frame, 1.0, 0, want.ctypes.data)
+        got = dg.undistort_points("sony", None, pts, ts, frame=frame)
+        assert np.allclose(got, want, rtol=0, atol=2e-3), (frame, got, want)
+    ts = np.arange(n) * (1000.0 / 60.0) * 9
+    want = oracle_lib.find_fovs(cp, "sony", None, ts)
+    got = dg.find_fovs("sony", None, ts)
+    dg.close()
+    assert np.allclose(got, want, rtol=1e-6, atol=0), float(np.abs(got / want - 1).max())
